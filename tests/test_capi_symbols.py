@@ -1,0 +1,47 @@
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute, no GPU)."""
+import ctypes
+import glob
+import os
+import re
+
+from xivo_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    syms = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        for m in re.finditer(r"\b(xivo_[a-z0-9_]+)\s*\(", src):
+            syms.add(m.group(1))
+    return syms
+
+
+def test_library_exports_all_declared_symbols():
+    assert os.path.exists(capi.LIB_PATH), "build libxivo_b200.so first (python -m xivo_b200.build)"
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in sorted(syms) if not hasattr(lib, s)]
+    assert not missing, f"declared in include/ but not exported: {missing}"
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device ctx creation must fail loudly (code XIVO_ERR_CUDA), never fall back."""
+    lib = capi.lib()
+    h = ctypes.c_void_p()
+    rc = lib.xivo_ctx_create(0, ctypes.byref(h))
+    if rc == 0:  # running on a GPU box: fine, just clean up
+        lib.xivo_ctx_destroy(h)
+    else:
+        assert rc == -2
+        assert b"no CPU path" in lib.xivo_last_error()
+
+
+def test_pyramid_layout_matches_opencv_level_rule():
+    total, lv = capi.Context.pyramid_layout(480, 640, 1, 15, 5)
+    assert [(r, c) for r, c, _ in lv] == [(480, 640), (240, 320), (120, 160), (60, 80), (30, 40)]
+    total, lv = capi.Context.pyramid_layout(512, 512, 3, 15, 5)
+    assert len(lv) == 6 and lv[-1][:2] == (16, 16) and total >= sum(r * c * 3 for r, c, _ in lv)

@@ -1,0 +1,127 @@
+"""GPU parity: tracker kernels through the C ABI vs the committed cv2 golden vectors and the C
+oracle.  Integer stages are bit-exact; LK positions agree to float rounding."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tracker_oracle as T
+from xivo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "tracker_cv2.npz"))
+
+
+def test_pyramid_golden(ctx):
+    lv = ctx.build_pyramid(G["a"], 15, 5)
+    assert len(lv) == 3
+    for i, l in enumerate(lv):
+        assert np.array_equal(l, G[f"pyr{i}"])
+    lv3 = ctx.build_pyramid(G["pyr3_0"], 15, 5)
+    for i, l in enumerate(lv3):
+        assert np.array_equal(l, G[f"pyr3_{i}"])
+
+
+@pytest.mark.parametrize("shape,cn", [((480, 640), 1), ((512, 512), 3), ((477, 635), 1), ((1024, 1280), 1), ((33, 47), 3)])
+def test_pyramid_vs_oracle(ctx, shape, cn):
+    a, _ = synth.frame_pair(shape[0], shape[1], seed=1)
+    img = a if cn == 1 else synth.to_bgr(a, True)
+    got, ref = ctx.build_pyramid(img, 15, 5), T.pyramid(img, 15, 5)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+
+
+@pytest.mark.parametrize("thr", [10, 20])
+def test_fast_golden(ctx, thr):
+    xy, sc, n = ctx.fast_detect(G["a"], thr)
+    g = G[f"fast{thr}"]
+    assert n == len(g) and np.array_equal(xy, g[:, :2]) and np.array_equal(sc, g[:, 2])
+
+
+def test_fast_bgr_golden(ctx):
+    xy, sc, n = ctx.fast_detect(G["pyr3_0"], 20)
+    g = G["fast20_bgr"]
+    assert n == len(g) and np.array_equal(xy, g[:, :2]) and np.array_equal(sc, g[:, 2])
+
+
+@pytest.mark.parametrize("shape,thr,nonmax", [((480, 640), 20, True), ((512, 512), 5, True), ((1024, 1280), 20, True),
+                                              ((61, 67), 10, True), ((240, 320), 20, False), ((7, 9), 5, True)])
+def test_fast_vs_oracle(ctx, shape, thr, nonmax):
+    a, _ = synth.frame_pair(shape[0], shape[1], seed=2)
+    xy, sc, n = ctx.fast_detect(a, thr, nonmax, max_kp=1 << 17)
+    rxy, rsc, rn = T.fast_detect(a, thr, nonmax)
+    assert n == rn
+    assert np.array_equal(xy, rxy) and np.array_equal(sc, rsc)
+
+
+def test_fast_constant_image_has_no_corners(ctx):
+    xy, sc, n = ctx.fast_detect(np.full((64, 64), 127, np.uint8), 5)
+    assert n == 0 and len(xy) == 0
+
+
+def test_fast_truncation_reports_total(ctx):
+    a, _ = synth.frame_pair(240, 320, seed=4)
+    xy_all, _, n_all = ctx.fast_detect(a, 5)
+    xy, sc, n = ctx.fast_detect(a, 5, max_kp=10)
+    assert n == n_all and len(xy) == 10 and np.array_equal(xy, xy_all[:10])
+
+
+@pytest.mark.parametrize("name", ["gray", "bgr"])
+def test_lk_golden(ctx, name):
+    a, b = (G["a"], G["b"]) if name == "gray" else (synth.to_bgr(G["a"], True), synth.to_bgr(G["b"], True))
+    p1, st, er = ctx.lk_track(a, b, G["lk_p0"], G["lk_init"])
+    assert np.array_equal(st, G[f"lk_{name}_st"])
+    ok = st == 1
+    assert np.abs(p1[ok] - G[f"lk_{name}_p1"][ok]).max() < 5e-3  # OpenCV's own float-lane rounding
+    assert np.abs(er[ok] - G[f"lk_{name}_err"][ok]).max() < 5e-3
+
+
+@pytest.mark.parametrize("shape,cn,npts,init_off", [((480, 640), 1, 150, (0, 0)), ((480, 640), 3, 150, (-2.5, -1.5)),
+                                                    ((512, 512), 3, 200, (0, 0)), ((1024, 1280), 1, 800, (1.0, 1.0))])
+def test_lk_vs_oracle(ctx, shape, cn, npts, init_off):
+    a, b = synth.frame_pair(shape[0], shape[1], seed=0)
+    xy, sc, _ = T.fast_detect(a, 20)
+    order = np.lexsort((xy[:, 0], xy[:, 1], -sc))[:npts]
+    p0 = xy[order].astype(np.float32)
+    if cn == 3:
+        a, b = synth.to_bgr(a), synth.to_bgr(b)
+    init = p0 + np.float32(init_off)
+    p1, st, er = ctx.lk_track(a, b, p0, init)
+    r1, rst, rer = T.lk_track(a, b, p0, init)
+    # status table is an index table -> must match exactly; positions to float rounding
+    assert np.array_equal(st, rst)
+    ok = st == 1
+    assert ok.sum() > 0.9 * len(p0)
+    assert np.abs(p1[ok] - r1[ok]).max() < 1e-4
+    assert np.abs(er[ok] - rer[ok]).max() < 1e-4
+    assert np.abs((p1[ok] - p0[ok]).mean(0) - np.array([-3.0, -2.0])).max() < 0.1
+
+
+def test_lk_edge_cases(ctx):
+    a, b = synth.frame_pair(240, 320, seed=6)
+    # points outside the image, on the border, on a flat patch; plus an empty call
+    p0 = np.float32([[-40, -40], [0, 0], [319, 239], [400, 100], [160, 120]])
+    flat = a.copy()
+    flat[80:160, 100:220] = 128
+    p1, st, er = ctx.lk_track(flat, b, p0, p0)
+    r1, rst, rer = T.lk_track(flat, b, p0, p0)
+    assert np.array_equal(st, rst)
+    assert st[0] == 0 and st[3] == 0 and st[4] == 0  # out of bounds / minEig rejections
+    ok = st == 1
+    if ok.any():
+        assert np.abs(p1[ok] - r1[ok]).max() < 1e-4
+    p1, st, er = ctx.lk_track(a, b, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
+    assert len(p1) == 0
+
+
+def test_lk_no_initial_flow_and_params(ctx):
+    a, b = synth.frame_pair(240, 320, seed=7, shift=(1, 0))
+    xy, sc, _ = T.fast_detect(a, 20)
+    p0 = xy[np.lexsort((xy[:, 0], xy[:, 1], -sc))[:64]].astype(np.float32)
+    for kw in (dict(use_initial_flow=False), dict(win=11, max_level=3), dict(max_iter=5, eps=0.1), dict(win=21, max_level=2)):
+        p1, st, _ = ctx.lk_track(a, b, p0, p0 + 3.0, **kw)
+        r1, rst, _ = T.lk_track(a, b, p0, p0 + 3.0, **kw)
+        assert np.array_equal(st, rst)
+        ok = st == 1
+        assert np.abs(p1[ok] - r1[ok]).max() < 1e-4

@@ -1,0 +1,90 @@
+"""Pins oracle/tracker_oracle.c against (a) the committed cv2 golden vectors and (b) cv2 itself
+when it is importable (it is in this image).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import tracker_oracle as T
+from xivo_b200 import synth
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "tracker_cv2.npz"))
+
+
+def test_pyrdown_matches_golden():
+    lv = T.pyramid(G["a"], 15, 5)
+    assert len(lv) == 3
+    for i, l in enumerate(lv):
+        assert np.array_equal(l, G[f"pyr{i}"])
+    lv3 = T.pyramid(G["pyr3_0"], 15, 5)
+    for i, l in enumerate(lv3):
+        assert np.array_equal(l, G[f"pyr3_{i}"])
+
+
+def test_gray_matches_golden():
+    assert np.array_equal(T.bgr2gray(G["pyr3_0"]), G["gray_from_bgr"])
+
+
+@pytest.mark.parametrize("thr", [10, 20])
+def test_fast_matches_golden(thr):
+    xy, sc, n = T.fast_detect(G["a"], thr)
+    g = G[f"fast{thr}"]
+    assert n == len(g)
+    assert np.array_equal(xy, g[:, :2]) and np.array_equal(sc, g[:, 2])
+
+
+def test_fast_bgr_matches_golden():
+    xy, sc, n = T.fast_detect(G["pyr3_0"], 20)
+    g = G["fast20_bgr"]
+    assert n == len(g) and np.array_equal(xy, g[:, :2]) and np.array_equal(sc, g[:, 2])
+
+
+@pytest.mark.parametrize("name,img", [("gray", ("a", "b")), ("bgr", None)])
+def test_lk_matches_golden(name, img):
+    if name == "gray":
+        a, b = G["a"], G["b"]
+    else:
+        a, b = synth.to_bgr(G["a"], True), synth.to_bgr(G["b"], True)
+    p1, st, er = T.lk_track(a, b, G["lk_p0"], G["lk_init"])
+    assert np.array_equal(st, G[f"lk_{name}_st"])
+    ok = st == 1
+    # OpenCV sums float SIMD lanes; the oracle sums exactly -> sub-milli-pixel differences
+    assert np.abs(p1[ok] - G[f"lk_{name}_p1"][ok]).max() < 5e-3
+    assert np.abs(er[ok] - G[f"lk_{name}_err"][ok]).max() < 5e-3
+
+
+def test_against_live_cv2_full_size():
+    cv2 = pytest.importorskip("cv2")
+    a, b = synth.frame_pair(480, 640, seed=0)
+    assert np.array_equal(T.pyrdown(a), cv2.pyrDown(a))
+    n, pyr = cv2.buildOpticalFlowPyramid(a, (15, 15), 5, withDerivatives=True)
+    assert n + 1 == len(T.pyramid(a, 15, 5))
+    assert np.array_equal(T.scharr(a), pyr[1])
+    kps = cv2.FastFeatureDetector_create(20, True).detect(a, None)
+    xy, sc, n = T.fast_detect(a, 20)
+    ref = np.array([[k.pt[0], k.pt[1], k.response] for k in kps], np.int32)
+    assert n == len(ref) and np.array_equal(xy, ref[:, :2]) and np.array_equal(sc, ref[:, 2])
+    order = np.lexsort((xy[:, 0], xy[:, 1], -sc))[:200]
+    p0 = xy[order].astype(np.float32)
+    crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    p1c, stc, _ = cv2.calcOpticalFlowPyrLK(a, b, p0, p0.copy(), winSize=(15, 15), maxLevel=5, criteria=crit,
+                                           flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    p1, st, _ = T.lk_track(a, b, p0, p0)
+    assert (st == stc.ravel()).mean() > 0.99
+    ok = (st == 1) & (stc.ravel() == 1)
+    assert np.abs(p1[ok] - p1c[ok]).max() < 5e-3
+    assert np.abs((p1[ok] - p0[ok]).mean(0) - np.array([-3.0, -2.0])).max() < 0.1
+
+
+def test_selection_logic_spacing():
+    a, _ = synth.frame_pair(240, 320, seed=5)
+    xy, sc, _ = T.fast_detect(a, 20)
+    m = T.Mask(240, 320, margin=8, mask_size=15)
+    m.reset()
+    picked = T.select_keypoints(m, xy, sc, 60)
+    assert 0 < len(picked) <= 60
+    pts = xy[picked]
+    assert pts[:, 0].min() >= 8 and pts[:, 0].max() < 320 - 8 and pts[:, 1].min() >= 8 and pts[:, 1].max() < 240 - 8
+    d = np.abs(pts[:, None, :] - pts[None, :, :]).max(-1) + np.eye(len(pts)) * 100
+    assert d.min() > 7  # no two picks inside each other's 15x15 box
+    assert all(sc[picked[i]] >= sc[picked[i + 1]] for i in range(len(picked) - 1))

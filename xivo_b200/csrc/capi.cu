@@ -1,0 +1,418 @@
+// C-ABI layer, kernel-level entry points (include/xivo_b200.h).  Host buffers in, host
+// buffers out; everything in between is the CUDA kernels of tracker_kernels.cu / ekf_kernels.cu.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "../../include/xivo_b200.h"
+#include "ctx.h"
+#include "kernels.h"
+
+namespace xb {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+std::atomic<unsigned long long> g_launches{0};
+}  // namespace xb
+
+using namespace xb;
+
+#define API_BEGIN             \
+  if (!ctx) {                 \
+    set_error("null ctx");    \
+    return XIVO_ERR_ARG;      \
+  }                           \
+  XB_CUDA(cudaSetDevice(ctx->device));
+
+static CameraParams cam_from(const double* c) {
+  CameraParams p;
+  p.model = (int)c[0];
+  p.rows = (int)c[1];
+  p.cols = (int)c[2];
+  p.fx = c[3]; p.fy = c[4]; p.cx = c[5]; p.cy = c[6];
+  p.k0 = c[7]; p.k1 = c[8]; p.k2 = c[9]; p.k3 = c[10];
+  return p;
+}
+
+extern "C" {
+
+const char* xivo_last_error(void) { return g_err; }
+int xivo_version(void) { return 100; }
+unsigned long long xivo_launch_count(void) { return g_launches.load(); }
+
+int xivo_ctx_create(int device, xivo_ctx** out) {
+  if (!out) { set_error("null out"); return XIVO_ERR_ARG; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); xivo_b200 has no CPU path", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    return XIVO_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { set_error("device %d out of range [0,%d)", device, n); return XIVO_ERR_ARG; }
+  XB_CUDA(cudaSetDevice(device));
+  xivo_ctx* c = new xivo_ctx();
+  c->device = device;
+  XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return XIVO_OK;
+}
+
+void xivo_ctx_destroy(xivo_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+unsigned long long xivo_pyramid_layout(int rows, int cols, int cn, int win, int max_level, int* n_levels, int* level_rows,
+                                       int* level_cols, unsigned long long* level_off) {
+  PyrDesc d = make_pyr_desc(rows, cols, cn, win, max_level);
+  if (n_levels) *n_levels = d.n_levels;
+  for (int l = 0; l < d.n_levels; ++l) {
+    if (level_rows) level_rows[l] = d.rows[l];
+    if (level_cols) level_cols[l] = d.cols[l];
+    if (level_off) level_off[l] = d.off[l];
+  }
+  return d.total;
+}
+
+int xivo_build_pyramid(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int cn, int win, int max_level, uint8_t* out) {
+  API_BEGIN;
+  XB_REQUIRE(img && out && rows > 0 && cols > 0 && (cn == 1 || cn == 3), "build_pyramid: bad arguments");
+  PyrDesc d = make_pyr_desc(rows, cols, cn, win, max_level);
+  DevBuf<uint8_t> pyr(d.total);
+  XB_REQUIRE(pyr.ok(), "cudaMalloc failed");
+  cudaStream_t st = ctx->stream;
+  XB_CUDA(cudaMemcpyAsync(pyr.p, img, (size_t)rows * cols * cn, cudaMemcpyHostToDevice, st));
+  int rc = launch_build_pyramid(st, pyr.p, d.total, d, 1);
+  if (rc) return rc;
+  g_launches += d.n_levels - 1;
+  XB_CUDA(cudaMemcpyAsync(out, pyr.p, d.total, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+int xivo_fast_detect(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int cn, int threshold, int nonmax, int* kp_xy,
+                     int* kp_score, int max_kp, int* n_kp) {
+  API_BEGIN;
+  XB_REQUIRE(img && kp_xy && kp_score && n_kp && max_kp > 0 && (cn == 1 || cn == 3), "fast_detect: bad arguments");
+  cudaStream_t st = ctx->stream;
+  const int cap = std::max(max_kp, 1 << 16);
+  DevBuf<uint8_t> dimg((size_t)rows * cols * cn);
+  DevBuf<unsigned> dkp(cap);
+  DevBuf<int> dcnt(1);
+  XB_REQUIRE(dimg.ok() && dkp.ok() && dcnt.ok(), "cudaMalloc failed");
+  XB_CUDA(cudaMemcpyAsync(dimg.p, img, (size_t)rows * cols * cn, cudaMemcpyHostToDevice, st));
+  int rc = launch_fast_detect(st, dimg.p, 0, rows, cols, cn, threshold, nonmax, dkp.p, cap, dcnt.p, 1);
+  if (rc) return rc;
+  g_launches += 1;
+  int cnt = 0;
+  XB_CUDA(cudaMemcpyAsync(&cnt, dcnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  const int got = std::min(cnt, cap);
+  std::vector<unsigned> kp(got);
+  if (got) XB_CUDA(cudaMemcpy(kp.data(), dkp.p, sizeof(unsigned) * got, cudaMemcpyDeviceToHost));
+  std::sort(kp.begin(), kp.end());  // packed (y, x, score): ascending == raster order
+  *n_kp = cnt;
+  for (int i = 0; i < std::min(got, max_kp); ++i) {
+    kp_xy[2 * i] = (kp[i] >> 8) & 0xfff;
+    kp_xy[2 * i + 1] = kp[i] >> 20;
+    kp_score[i] = kp[i] & 0xff;
+  }
+  return XIVO_OK;
+}
+
+int xivo_lk_track(xivo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int rows, int cols, int cn, const float* prev_pts,
+                  float* next_pts, uint8_t* status, float* err, int npts, int win, int max_level, int max_iter, double eps,
+                  int use_initial_flow, double min_eig_threshold) {
+  API_BEGIN;
+  XB_REQUIRE(prev && next && prev_pts && next_pts && status && npts >= 0 && (cn == 1 || cn == 3), "lk_track: bad arguments");
+  if (npts == 0) return XIVO_OK;
+  cudaStream_t st = ctx->stream;
+  PyrDesc d = make_pyr_desc(rows, cols, cn, win, max_level);
+  DevBuf<uint8_t> pyr(2 * d.total);
+  DevBuf<float> dp0(2 * (size_t)npts), dp1(2 * (size_t)npts), derr(npts);
+  DevBuf<uint8_t> dst(npts);
+  DevBuf<int> dn(1);
+  XB_REQUIRE(pyr.ok() && dp0.ok() && dp1.ok() && derr.ok() && dst.ok() && dn.ok(), "cudaMalloc failed");
+  const size_t ib = (size_t)rows * cols * cn;
+  XB_CUDA(cudaMemcpyAsync(pyr.p, prev, ib, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(pyr.p + d.total, next, ib, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dp0.p, prev_pts, sizeof(float) * 2 * npts, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dp1.p, next_pts, sizeof(float) * 2 * npts, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dn.p, &npts, sizeof(int), cudaMemcpyHostToDevice, st));
+  int rc = launch_build_pyramid(st, pyr.p, d.total, d, 2);  // prev and next as a batch of two
+  if (rc) return rc;
+  rc = launch_lk_track(st, pyr.p, pyr.p + d.total, 0, d, dp0.p, dp1.p, dst.p, derr.p, dn.p, npts, 1, win, max_iter, eps,
+                       use_initial_flow, min_eig_threshold);
+  if (rc) return rc;
+  g_launches += d.n_levels;
+  XB_CUDA(cudaMemcpyAsync(next_pts, dp1.p, sizeof(float) * 2 * npts, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(status, dst.p, npts, cudaMemcpyDeviceToHost, st));
+  if (err) XB_CUDA(cudaMemcpyAsync(err, derr.p, sizeof(float) * npts, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+// Uploads the per-filter tables of one filter and runs the Jacobian/gate kernel.
+struct FeatTables {
+  DevBuf<CameraParams> cam{1};
+  DevBuf<double> X{kPoseDoubles}, groups, fx, fxp, P, R{1};
+  DevBuf<int> fref, fsind, nfeat{1};
+  DevBuf<FeatJac> jac;
+  EkfLayout lay;
+  bool ok() const { return cam.ok() && X.ok() && groups.ok() && fx.ok() && fxp.ok() && fref.ok() && fsind.ok() && jac.ok() && P.ok(); }
+};
+
+static int upload_tables(cudaStream_t st, FeatTables& t, int G, int F, const double* camera, const double* X24,
+                         const double* groups, int n, const double* feat_x, const double* feat_xp, const int* feat_ref,
+                         const int* feat_sind, const double* P, double R) {
+  XB_REQUIRE(G > 0 && F > 0 && n >= 0 && n <= F, "need 0 <= n <= F");
+  for (int i = 0; i < n; ++i)
+    XB_REQUIRE(feat_ref[i] >= 0 && feat_ref[i] < G && feat_sind[i] >= 0 && feat_sind[i] < F, "slot index out of range");
+  t.lay = EkfLayout{G, F};
+  const int N = t.lay.N();
+  t.groups.alloc((size_t)G * kGroupDoubles);
+  t.fx.alloc((size_t)F * 3);
+  t.fxp.alloc((size_t)F * 2);
+  t.fref.alloc(F);
+  t.fsind.alloc(F);
+  t.jac.alloc(F);
+  t.P.alloc((size_t)N * N);
+  XB_REQUIRE(t.ok(), "cudaMalloc failed");
+  CameraParams cp = cam_from(camera);
+  XB_CUDA(cudaMemcpyAsync(t.cam.p, &cp, sizeof(cp), cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(t.X.p, X24, sizeof(double) * kPoseDoubles, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(t.groups.p, groups, sizeof(double) * G * kGroupDoubles, cudaMemcpyHostToDevice, st));
+  if (n) {
+    XB_CUDA(cudaMemcpyAsync(t.fx.p, feat_x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+    XB_CUDA(cudaMemcpyAsync(t.fxp.p, feat_xp, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+    XB_CUDA(cudaMemcpyAsync(t.fref.p, feat_ref, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    XB_CUDA(cudaMemcpyAsync(t.fsind.p, feat_sind, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  }
+  XB_CUDA(cudaMemcpyAsync(t.nfeat.p, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(t.R.p, &R, sizeof(double), cudaMemcpyHostToDevice, st));
+  if (P) XB_CUDA(cudaMemcpyAsync(t.P.p, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
+  else XB_CUDA(cudaMemsetAsync(t.P.p, 0, sizeof(double) * N * N, st));
+  return 0;
+}
+
+int xivo_jacobian_batch(xivo_ctx* ctx, int G, int F, const double* camera, const double* X24, const double* groups, int n,
+                        const double* feat_x, const double* feat_xp, const int* feat_ref_sind, const int* feat_sind,
+                        const double* P, double R, double* J_dense, double* inn, double* mh) {
+  API_BEGIN;
+  XB_REQUIRE(camera && X24 && groups && (n == 0 || (feat_x && feat_xp && feat_ref_sind && feat_sind)), "jacobian_batch: null input");
+  cudaStream_t st = ctx->stream;
+  FeatTables t;
+  int rc = upload_tables(st, t, G, F, camera, X24, groups, n, feat_x, feat_xp, feat_ref_sind, feat_sind, P, R);
+  if (rc) return rc;
+  const int N = t.lay.N();
+  DevBuf<double> Jd(J_dense ? (size_t)F * 2 * N : 0);
+  XB_REQUIRE(Jd.ok(), "cudaMalloc failed");
+  rc = launch_jacobian_gate(st, t.lay, t.cam.p, t.X.p, t.groups.p, t.fx.p, t.fxp.p, t.fref.p, t.fsind.p, t.nfeat.p, t.P.p, t.R.p,
+                            t.jac.p, J_dense ? Jd.p : nullptr, 1);
+  if (rc) return rc;
+  g_launches += 1;
+  std::vector<FeatJac> hj(n);
+  if (n) XB_CUDA(cudaMemcpyAsync(hj.data(), t.jac.p, sizeof(FeatJac) * n, cudaMemcpyDeviceToHost, st));
+  if (J_dense && n) XB_CUDA(cudaMemcpyAsync(J_dense, Jd.p, sizeof(double) * n * 2 * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) {
+    if (inn) { inn[2 * i] = hj[i].inn[0]; inn[2 * i + 1] = hj[i].inn[1]; }
+    if (mh) mh[i] = P ? hj[i].mh : -1.0;
+  }
+  return XIVO_OK;
+}
+
+int xivo_mh_gate(xivo_ctx* ctx, int G, int F, const double* camera, const double* X24, const double* groups, int n,
+                 const double* feat_x, const double* feat_xp, const int* feat_ref_sind, const int* feat_sind, const double* P,
+                 double R, double* mh) {
+  if (!P || !mh) { set_error("mh_gate: P and mh are required"); return XIVO_ERR_ARG; }
+  return xivo_jacobian_batch(ctx, G, F, camera, X24, groups, n, feat_x, feat_xp, feat_ref_sind, feat_sind, P, R, nullptr, nullptr, mh);
+}
+
+int xivo_ekf_update(xivo_ctx* ctx, int N, int M, const double* H, double* P, const double* inn, const double* diagR, double* err) {
+  API_BEGIN;
+  XB_REQUIRE(N > 0 && M >= 0 && P && err && (M == 0 || (H && inn && diagR)), "ekf_update: bad arguments");
+  if (M == 0) {
+    for (int i = 0; i < N; ++i) err[i] = 0.0;
+    return XIVO_OK;
+  }
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dH((size_t)M * N), dP((size_t)N * N), dinn(M), dR(M), derr(N), dHP((size_t)M * N), dKt((size_t)M * N);
+  XB_REQUIRE(dH.ok() && dP.ok() && dinn.ok() && dR.ok() && derr.ok() && dHP.ok() && dKt.ok(), "cudaMalloc failed");
+  XB_CUDA(cudaMemcpyAsync(dH.p, H, sizeof(double) * M * N, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dP.p, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dinn.p, inn, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dR.p, diagR, sizeof(double) * M, cudaMemcpyHostToDevice, st));
+  int rc = launch_ekf_update_dense(st, N, M, dH.p, dR.p, dinn.p, dP.p, derr.p, dHP.p, dKt.p, 1);
+  if (rc) return rc;
+  g_launches += 2;
+  XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(err, derr.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+int xivo_filter_update(xivo_ctx* ctx, int G, int F, const double* camera, const double* X24, const double* groups, int n,
+                       const double* feat_x, const double* feat_xp, const int* feat_ref_sind, const int* feat_sind,
+                       const int* sel, int nsel, double R, double* P, double* err, double* H_dense) {
+  API_BEGIN;
+  XB_REQUIRE(P && err && nsel >= 0 && nsel <= n && (nsel == 0 || sel), "filter_update: bad arguments");
+  for (int i = 0; i < nsel; ++i) XB_REQUIRE(sel[i] >= 0 && sel[i] < n, "filter_update: sel out of range");
+  cudaStream_t st = ctx->stream;
+  FeatTables t;
+  int rc = upload_tables(st, t, G, F, camera, X24, groups, n, feat_x, feat_xp, feat_ref_sind, feat_sind, P, R);
+  if (rc) return rc;
+  const int N = t.lay.N(), Mmax = 2 * F;
+  DevBuf<int> dsel(F), dnsel(1);
+  DevBuf<double> derr(N), dHP((size_t)Mmax * N), dKt((size_t)Mmax * N), dH(H_dense ? (size_t)Mmax * N : 0);
+  XB_REQUIRE(dsel.ok() && dnsel.ok() && derr.ok() && dHP.ok() && dKt.ok() && dH.ok(), "cudaMalloc failed");
+  if (nsel) XB_CUDA(cudaMemcpyAsync(dsel.p, sel, sizeof(int) * nsel, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dnsel.p, &nsel, sizeof(int), cudaMemcpyHostToDevice, st));
+  rc = launch_jacobian_gate(st, t.lay, t.cam.p, t.X.p, t.groups.p, t.fx.p, t.fxp.p, t.fref.p, t.fsind.p, t.nfeat.p, t.P.p, t.R.p,
+                            t.jac.p, nullptr, 1);
+  if (rc) return rc;
+  rc = launch_ekf_update(st, t.lay, t.jac.p, dsel.p, dnsel.p, t.R.p, t.P.p, derr.p, dHP.p, dKt.p, H_dense ? dH.p : nullptr, 1);
+  if (rc) return rc;
+  g_launches += 3;
+  XB_CUDA(cudaMemcpyAsync(P, t.P.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(err, derr.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+  if (H_dense && nsel) XB_CUDA(cudaMemcpyAsync(H_dense, dH.p, sizeof(double) * 2 * nsel * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+int xivo_subfilter_batch(xivo_ctx* ctx, const double* camera, const double* X24, int n, const double* x, const double* P33,
+                         const double* xp, const double* ref, const double* outlier_counter, double Rtri, double mh_thresh,
+                         double* x_out, double* P33_out, double* outlier_counter_out) {
+  API_BEGIN;
+  XB_REQUIRE(camera && X24 && n >= 0, "subfilter_batch: bad arguments");
+  if (n == 0) return XIVO_OK;
+  cudaStream_t st = ctx->stream;
+  std::vector<SubfilterIn> hin(n);
+  for (int i = 0; i < n; ++i) {
+    memcpy(hin[i].x, x + 3 * i, 24);
+    memcpy(hin[i].P, P33 + 9 * i, 72);
+    memcpy(hin[i].xp, xp + 2 * i, 16);
+    memcpy(hin[i].ref, ref + 12 * i, 96);
+    hin[i].outlier_counter = outlier_counter[i];
+    hin[i].filter = 0;
+    hin[i].pad = 0;
+  }
+  DevBuf<SubfilterIn> din(n);
+  DevBuf<SubfilterOut> dout(n);
+  DevBuf<CameraParams> dcam(1);
+  DevBuf<double> dX(kPoseDoubles);
+  XB_REQUIRE(din.ok() && dout.ok() && dcam.ok() && dX.ok(), "cudaMalloc failed");
+  CameraParams cp = cam_from(camera);
+  XB_CUDA(cudaMemcpyAsync(dcam.p, &cp, sizeof(cp), cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dX.p, X24, sizeof(double) * kPoseDoubles, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(din.p, hin.data(), sizeof(SubfilterIn) * n, cudaMemcpyHostToDevice, st));
+  int rc = launch_subfilter(st, dcam.p, dX.p, din.p, dout.p, n, Rtri, mh_thresh);
+  if (rc) return rc;
+  g_launches += 1;
+  std::vector<SubfilterOut> hout(n);
+  XB_CUDA(cudaMemcpyAsync(hout.data(), dout.p, sizeof(SubfilterOut) * n, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; ++i) {
+    memcpy(x_out + 3 * i, hout[i].x, 24);
+    memcpy(P33_out + 9 * i, hout[i].P, 72);
+    outlier_counter_out[i] = hout[i].outlier_counter;
+  }
+  return XIVO_OK;
+}
+
+int xivo_oos_project(xivo_ctx* ctx, int G, int F, const double* camera, const double* gbc12, int nf, int k, const double* Xs,
+                     const double* obs_pose, const int* obs_sind, const double* obs_xp, double* Hf, double* Hx, double* inn,
+                     double* Hx_proj, double* inn_proj) {
+  API_BEGIN;
+  XB_REQUIRE(camera && gbc12 && nf >= 0 && Xs && obs_pose && obs_sind && obs_xp && Hf && Hx && inn && Hx_proj && inn_proj,
+             "oos_project: null argument");
+  if (nf == 0) return XIVO_OK;
+  for (int i = 0; i < nf * k; ++i) XB_REQUIRE(obs_sind[i] >= 0 && obs_sind[i] < G, "oos_project: group slot out of range");
+  cudaStream_t st = ctx->stream;
+  EkfLayout lay{G, F};
+  const int N = lay.N(), R2 = 2 * k;
+  DevBuf<CameraParams> dcam(1);
+  DevBuf<double> dg(12), dXs((size_t)nf * 3), dpose((size_t)nf * k * 12), dxp((size_t)nf * k * 2), dHf((size_t)nf * R2 * 3),
+      dHx((size_t)nf * R2 * N), dinn((size_t)nf * R2), dHp((size_t)nf * R2 * N), dip((size_t)nf * R2);
+  DevBuf<int> dsind((size_t)nf * k);
+  XB_REQUIRE(dcam.ok() && dg.ok() && dXs.ok() && dpose.ok() && dxp.ok() && dHf.ok() && dHx.ok() && dinn.ok() && dHp.ok() &&
+                 dip.ok() && dsind.ok(),
+             "cudaMalloc failed");
+  CameraParams cp = cam_from(camera);
+  XB_CUDA(cudaMemcpyAsync(dcam.p, &cp, sizeof(cp), cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dg.p, gbc12, 96, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dXs.p, Xs, sizeof(double) * nf * 3, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dpose.p, obs_pose, sizeof(double) * nf * k * 12, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dxp.p, obs_xp, sizeof(double) * nf * k * 2, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dsind.p, obs_sind, sizeof(int) * nf * k, cudaMemcpyHostToDevice, st));
+  int rc = launch_oos(st, lay, dcam.p, dg.p, dXs.p, dpose.p, dsind.p, dxp.p, k, nf, dHf.p, dHx.p, dinn.p, dHp.p, dip.p);
+  if (rc) return rc;
+  g_launches += 1;
+  XB_CUDA(cudaMemcpyAsync(Hf, dHf.p, sizeof(double) * nf * R2 * 3, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(Hx, dHx.p, sizeof(double) * nf * R2 * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(inn, dinn.p, sizeof(double) * nf * R2, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(Hx_proj, dHp.p, sizeof(double) * nf * R2 * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(inn_proj, dip.p, sizeof(double) * nf * R2, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+int xivo_cov_edit(xivo_ctx* ctx, int N, double* P, const int* ops, const double* blk, int nops) {
+  API_BEGIN;
+  XB_REQUIRE(N > 0 && P && nops >= 0 && (nops == 0 || ops), "cov_edit: bad arguments");
+  if (nops == 0) return XIVO_OK;
+  std::vector<EditOp> h(nops);
+  for (int i = 0; i < nops; ++i) {
+    h[i].type = ops[4 * i];
+    h[i].a = ops[4 * i + 1];
+    h[i].b = ops[4 * i + 2];
+    h[i].n = ops[4 * i + 3];
+    XB_REQUIRE(h[i].type >= 0 && h[i].type <= 2, "cov_edit: unknown op");
+    const int n = h[i].type == 2 ? 3 : h[i].n;
+    XB_REQUIRE(h[i].a >= 0 && h[i].a + n <= N && (h[i].type != 1 || (h[i].b >= 0 && h[i].b + n <= N)), "cov_edit: range");
+    for (int k = 0; k < 9; ++k) h[i].blk[k] = (blk && h[i].type == 2) ? blk[9 * i + k] : 0.0;
+  }
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dP((size_t)N * N);
+  DevBuf<EditOp> dops(nops);
+  DevBuf<int> dn(1);
+  XB_REQUIRE(dP.ok() && dops.ok() && dn.ok(), "cudaMalloc failed");
+  XB_CUDA(cudaMemcpyAsync(dP.p, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dops.p, h.data(), sizeof(EditOp) * nops, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dn.p, &nops, sizeof(int), cudaMemcpyHostToDevice, st));
+  int rc = launch_cov_edit(st, N, dP.p, dops.p, dn.p, nops, 1);
+  if (rc) return rc;
+  g_launches += 1;
+  XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+int xivo_cov_propagate(xivo_ctx* ctx, int N, double* P, const double* Phi, const double* Pmm) {
+  API_BEGIN;
+  XB_REQUIRE(N >= 23 && P && Phi && Pmm, "cov_propagate: bad arguments");
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dP((size_t)N * N), dPhi(529), dPmm(529);
+  XB_REQUIRE(dP.ok() && dPhi.ok() && dPmm.ok(), "cudaMalloc failed");
+  XB_CUDA(cudaMemcpyAsync(dP.p, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dPhi.p, Phi, sizeof(double) * 529, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dPmm.p, Pmm, sizeof(double) * 529, cudaMemcpyHostToDevice, st));
+  int rc = launch_cov_propagate(st, N, dP.p, dPhi.p, dPmm.p, nullptr, 1);
+  if (rc) return rc;
+  g_launches += 1;
+  XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+}  // extern "C"

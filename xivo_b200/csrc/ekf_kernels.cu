@@ -1,0 +1,635 @@
+// EKF kernels (HOT LOOPs 2-4 of SURVEY.md §3.2): per-feature Jacobian + Mahalanobis gate,
+// measurement update, covariance slot surgery, propagation strips, depth sub-filter, OOS
+// projection.  All fp64 (the reference is fp64 Eigen, /root/reference/common/alias.h:11);
+// the covariance P stays resident in HBM, one N x N block per independent filter.
+#include "kernels.h"
+
+namespace xb {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Jacobian + gate.  One warp per in-state feature.
+// Follows Feature::ComputeJacobian (/root/reference/src/feature.cpp:542-656) for the chain
+// x -> Xc -> Xbr -> Xs -> Xb -> Xcn -> xcn -> xp and the MH distance of Estimator::MHGating
+// (/root/reference/src/update.cpp:60-69), exploiting that J has only 21 non-zero columns
+// (the reference multiplies the full 2xN by NxN).
+// ------------------------------------------------------------------------------------------
+__device__ void compute_feature_jacobian(const EkfLayout lay, const CameraParams& cam, const double* X, const double* grp,
+                                         const double* x, const double* xp, int ref_sind, int f_sind, FeatJac* o) {
+  M3 Rsb, Rbc, Rr;
+  V3 Tsb, Tbc, Tr;
+  for (int i = 0; i < 9; ++i) { Rsb.m[i] = X[i]; Rbc.m[i] = X[12 + i]; Rr.m[i] = grp[i]; }
+  for (int i = 0; i < 3; ++i) { Tsb.v[i] = X[9 + i]; Tbc.v[i] = X[21 + i]; Tr.v[i] = grp[9 + i]; }
+  const M3 Rsb_t = m3_t(Rsb), Rbc_t = m3_t(Rbc);
+  // unproject_logz (/root/reference/common/project.h:79-95)
+  const double z = exp(x[2]);
+  const V3 Xc{{x[0] * z, x[1] * z, z}};
+  const M3 dXc_dx{{z, 0, x[0] * z, 0, z, x[1] * z, 0, 0, z}};
+  const V3 Xbr = v3_add(m3_mulv(Rbc, Xc), Tbc);
+  const V3 Xs = v3_add(m3_mulv(Rr, Xbr), Tr);
+  const V3 Xb = m3_mulv(Rsb_t, v3_sub(Xs, Tsb));
+  const V3 Xcn = m3_mulv(Rbc_t, v3_sub(Xb, Tbc));
+  const M3 A = m3_mul(Rbc_t, Rsb_t);  // dXcn_dXs
+  const M3 B = m3_mul(A, Rr);         // dXcn_dXbr
+  const M3 dXcn_dTbc = m3_add(m3_neg(Rbc_t), B);
+  const M3 dXcn_dWbc = m3_add(m3_hat(Xcn), m3_mul(B, m3_neg(m3_mul(Rbc, m3_hat(Xc)))));
+  const M3 dXcn_dTsb = m3_neg(A);
+  const M3 dXcn_dWsb = m3_mul(Rbc_t, m3_hat(Xb));
+  const M3 dXcn_dTsbr = A;
+  const M3 dXcn_dWsbr = m3_mul(A, m3_neg(m3_mul(Rr, m3_hat(Xbr))));
+  const M3 dXcn_dx = m3_mul(m3_mul(B, Rbc), dXc_dx);
+  // project (/root/reference/common/project.h:11-24)
+  const double iz = 1.0 / Xcn.v[2];
+  const double xcn0 = Xcn.v[0] * iz, xcn1 = Xcn.v[1] * iz;
+  const double P23[6] = {iz, 0, -Xcn.v[0] * iz * iz, 0, iz, -Xcn.v[1] * iz * iz};
+  double u, v, Jc[4];
+  camera_project(cam, xcn0, xcn1, &u, &v, Jc);
+  M23 d;
+  for (int j = 0; j < 3; ++j) {
+    d.m[j] = Jc[0] * P23[j] + Jc[1] * P23[3 + j];
+    d.m[3 + j] = Jc[2] * P23[j] + Jc[3] * P23[3 + j];
+  }
+  const M3* blocks[7] = {&dXcn_dWsb, &dXcn_dTsb, &dXcn_dWbc, &dXcn_dTbc, &dXcn_dWsbr, &dXcn_dTsbr, &dXcn_dx};
+  for (int b = 0; b < 7; ++b) {
+    const M23 jb = m23_mul(d, *blocks[b]);
+    for (int j = 0; j < 3; ++j) {
+      o->J[0][3 * b + j] = jb.m[j];
+      o->J[1][3 * b + j] = jb.m[3 + j];
+    }
+  }
+  o->inn[0] = xp[0] - u;
+  o->inn[1] = xp[1] - v;
+  o->goff = lay.goff(ref_sind);
+  o->foff = lay.foff(f_sind);
+}
+
+__device__ __forceinline__ int jac_col(int k, int goff, int foff) {
+  // compact column k (0..20) -> error-state column
+  return k < 6 ? k : (k < 12 ? 15 + (k - 6) : (k < 18 ? goff + (k - 12) : foff + (k - 18)));
+}
+
+__global__ void __launch_bounds__(32) jacobian_gate_kernel(EkfLayout lay, const CameraParams* __restrict__ cam,
+                                                           const double* __restrict__ X, const double* __restrict__ groups,
+                                                           const double* __restrict__ feat_x, const double* __restrict__ feat_xp,
+                                                           const int* __restrict__ feat_ref, const int* __restrict__ feat_sind,
+                                                           const int* __restrict__ nfeat, const double* __restrict__ P,
+                                                           const double* __restrict__ Rmeas, FeatJac* __restrict__ out,
+                                                           double* __restrict__ J_dense) {
+  const int b = blockIdx.y, i = blockIdx.x, lane = threadIdx.x;
+  if (i >= nfeat[b]) return;
+  const int N = lay.N();
+  __shared__ FeatJac sj;
+  const size_t fi = (size_t)b * lay.F + i;
+  if (lane == 0) {
+    const int ref = feat_ref[fi];
+    compute_feature_jacobian(lay, cam[b], X + (size_t)b * kPoseDoubles, groups + ((size_t)b * lay.G + ref) * kGroupDoubles,
+                             feat_x + 3 * fi, feat_xp + 2 * fi, ref, feat_sind[fi], &sj);
+  }
+  __syncwarp();
+  const double* __restrict__ Pb = P + (size_t)b * N * N;
+  const int goff = sj.goff, foff = sj.foff;
+  double s00 = 0, s01 = 0, s11 = 0;
+  for (int t = lane; t < kJacNnz * kJacNnz; t += 32) {
+    const int a = t / kJacNnz, c = t - a * kJacNnz;
+    const double p = Pb[(size_t)jac_col(a, goff, foff) * N + jac_col(c, goff, foff)];
+    const double j0a = sj.J[0][a], j1a = sj.J[1][a];
+    s00 += j0a * p * sj.J[0][c];
+    s01 += j0a * p * sj.J[1][c];
+    s11 += j1a * p * sj.J[1][c];
+  }
+  s00 = warp_sum_d(s00);
+  s01 = warp_sum_d(s01);
+  s11 = warp_sum_d(s11);
+  const double R = Rmeas[b];
+  s00 += R;
+  s11 += R;
+  const double r0 = sj.inn[0], r1 = sj.inn[1];
+  const double mh = (r0 * r0 * s11 - 2.0 * r0 * r1 * s01 + r1 * r1 * s00) / (s00 * s11 - s01 * s01);
+  if (lane == 0) {
+    sj.mh = mh;
+    out[fi] = sj;
+  }
+  if (J_dense) {
+    // coalesced zero fill of the two dense rows, then the 42 non-zeros
+    double* __restrict__ Jd = J_dense + fi * 2 * (size_t)N;
+    for (int c = lane; c < 2 * N; c += 32) Jd[c] = 0.0;
+    __syncwarp();
+    for (int t = lane; t < 2 * kJacNnz; t += 32) {
+      const int r = t / kJacNnz, k = t - r * kJacNnz;
+      Jd[(size_t)r * N + jac_col(k, goff, foff)] = sj.J[r][k];
+    }
+  }
+}
+
+int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const double* X, const double* groups,
+                         const double* feat_x, const double* feat_xp, const int* feat_ref, const int* feat_sind,
+                         const int* nfeat, const double* P, const double* Rmeas, FeatJac* out, double* J_dense, int batch) {
+  dim3 grid(lay.F, batch);
+  jacobian_gate_kernel<<<grid, 32, 0, st>>>(lay, cam, X, groups, feat_x, feat_xp, feat_ref, feat_sind, nfeat, P, Rmeas, out,
+                                            J_dense);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Measurement update.
+// Reference: Estimator::FilterUpdate + UpdateJosephForm (/root/reference/src/update.cpp:120-153,
+// /root/reference/src/estimator.cpp:1257-1288): S = H P H^T + R, K^T = S^-1 (H P), err = K inn,
+// P <- (KH-I) P (KH-I)^T + K R K^T.
+// Here: gain kernel (one CTA per filter) forms HP from the 18 non-zeros per row of H
+// (FillJacobianBlock layout incl. its group-rotation quirk, feature.cpp:675-676), S, Cholesky of
+// S in shared memory, K^T by substitution; covariance kernel (upper-triangle 32x32 tiles over
+// all SMs) applies P <- P - K (H P) with the result mirrored so P stays exactly symmetric.
+// Algebra: for the optimal gain Joseph's form equals P - K H P exactly; expanding Joseph gives
+// P - K HP + K^T-side term K (S K^T - H P) whose bracket is the solve residual (~1e-16 |HP|).
+// ------------------------------------------------------------------------------------------
+constexpr int GAIN_THREADS = 512;
+constexpr int kHnnz = 21;
+
+template <bool SPARSE>
+__global__ void __launch_bounds__(GAIN_THREADS) ekf_gain_kernel(int N, EkfLayout lay, const FeatJac* __restrict__ jac,
+                                                                const int* __restrict__ sel, const int* __restrict__ nsel,
+                                                                int Mdense, const double* __restrict__ Hd,
+                                                                const double* __restrict__ diagR, const double* __restrict__ innd,
+                                                                const double* __restrict__ Rmeas, const double* __restrict__ P,
+                                                                double* __restrict__ err, double* __restrict__ HP,
+                                                                double* __restrict__ Kt, double* __restrict__ H_dense, int Mmax) {
+  extern __shared__ __align__(16) double sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int M = SPARSE ? 2 * nsel[b] : Mdense;
+  const double* __restrict__ Pb = P + (size_t)b * N * N;
+  double* __restrict__ HPb = HP + (size_t)b * Mmax * N;
+  double* __restrict__ Ktb = Kt + (size_t)b * Mmax * N;
+  double* __restrict__ errb = err + (size_t)b * N;
+  if (M == 0) {
+    for (int j = tid; j < N; j += GAIN_THREADS) errb[j] = 0.0;
+    return;
+  }
+  // shared: S (M x M), inn (M), [sparse] Hval (M x 21), Hcol (M x 21 ints)
+  double* S = sm;
+  double* inn = S + (size_t)Mmax * Mmax;
+  double* Hval = inn + Mmax;
+  int* Hcol = reinterpret_cast<int*>(Hval + (size_t)(SPARSE ? Mmax * kHnnz : 0));
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+
+  if (SPARSE) {
+    for (int t = tid; t < M * kHnnz; t += GAIN_THREADS) {
+      const int r = t / kHnnz, k = t - r * kHnnz;
+      const FeatJac& f = jac[(size_t)b * lay.F + sel[(size_t)b * lay.F + (r >> 1)]];
+      // FillJacobianBlock: H(:, goff:goff+3) <- J(:, goff+3:goff+6); H(:, goff+3:goff+6) stays 0
+      double v = f.J[r & 1][k];
+      if (k >= 12 && k < 15) v = f.J[r & 1][k + 3];
+      else if (k >= 15 && k < 18) v = 0.0;
+      Hval[t] = v;
+      Hcol[t] = jac_col(k, f.goff, f.foff);
+      if (k == 0) inn[r] = f.inn[r & 1];
+    }
+  } else {
+    for (int r = tid; r < M; r += GAIN_THREADS) inn[r] = innd[(size_t)b * M + r];
+  }
+  __syncthreads();
+  if (SPARSE && H_dense) {
+    double* __restrict__ Hb = H_dense + (size_t)b * Mmax * N;
+    for (int t = tid; t < M * N; t += GAIN_THREADS) Hb[t] = 0.0;
+    __syncthreads();
+    for (int t = tid; t < M * kHnnz; t += GAIN_THREADS) Hb[(size_t)(t / kHnnz) * N + Hcol[t]] = Hval[t];
+  }
+  // ---- a. HP = H P
+  for (int t = tid; t < M * N; t += GAIN_THREADS) {
+    const int r = t / N, j = t - r * N;
+    double acc = 0.0;
+    if (SPARSE) {
+#pragma unroll
+      for (int k = 0; k < kHnnz; ++k) acc += Hval[r * kHnnz + k] * Pb[(size_t)Hcol[r * kHnnz + k] * N + j];
+    } else {
+      const double* __restrict__ hr = Hd + ((size_t)b * M + r) * N;
+      for (int k = 0; k < N; ++k) acc += hr[k] * Pb[(size_t)k * N + j];
+    }
+    HPb[t] = acc;
+  }
+  __syncthreads();
+  // ---- b. S = HP H^T + R (lower triangle incl. diagonal is what Cholesky reads; fill both)
+  for (int t = tid; t < M * M; t += GAIN_THREADS) {
+    const int r = t / M, s = t - r * M;
+    double acc = 0.0;
+    if (SPARSE) {
+#pragma unroll
+      for (int k = 0; k < kHnnz; ++k) acc += HPb[(size_t)r * N + Hcol[s * kHnnz + k]] * Hval[s * kHnnz + k];
+      if (r == s) acc += Rmeas[b];
+    } else {
+      const double* __restrict__ hs = Hd + ((size_t)b * M + s) * N;
+      for (int k = 0; k < N; ++k) acc += HPb[(size_t)r * N + k] * hs[k];
+      if (r == s) acc += diagR[(size_t)b * M + r];
+    }
+    S[r * Mmax + s] = acc;
+  }
+  __syncthreads();
+  // ---- c. Cholesky S = L L^T (right-looking, in place in the lower triangle)
+  for (int k = 0; k < M; ++k) {
+    if (tid == 0) {
+      const double dkk = S[k * Mmax + k];
+      if (!(dkk > 0.0)) bad = 1;
+      S[k * Mmax + k] = sqrt(dkk);
+    }
+    __syncthreads();
+    const double inv = 1.0 / S[k * Mmax + k];
+    for (int i = k + 1 + tid; i < M; i += GAIN_THREADS) S[i * Mmax + k] *= inv;
+    __syncthreads();
+    const int rem = M - k - 1;
+    for (int t = tid; t < rem * rem; t += GAIN_THREADS) {
+      const int ii = t / rem, jj = t - ii * rem;
+      if (jj <= ii) {
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        S[i * Mmax + j] -= S[i * Mmax + k] * S[j * Mmax + k];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- d. K^T = S^-1 HP by forward/back substitution, one thread per state column; err = K inn
+  for (int j = tid; j < N; j += GAIN_THREADS) {
+    for (int r = 0; r < M; ++r) {
+      double acc = HPb[(size_t)r * N + j];
+      for (int t = 0; t < r; ++t) acc -= S[r * Mmax + t] * Ktb[(size_t)t * N + j];
+      Ktb[(size_t)r * N + j] = acc / S[r * Mmax + r];
+    }
+    double e = 0.0;
+    for (int r = M - 1; r >= 0; --r) {
+      double acc = Ktb[(size_t)r * N + j];
+      for (int t = r + 1; t < M; ++t) acc -= S[t * Mmax + r] * Ktb[(size_t)t * N + j];
+      acc /= S[r * Mmax + r];
+      Ktb[(size_t)r * N + j] = acc;
+      e += acc * inn[r];
+    }
+    errb[j] = bad ? nan("") : e;
+  }
+}
+
+constexpr int CT = 32;  // covariance tile
+__global__ void __launch_bounds__(256) ekf_cov_kernel(int N, const int* __restrict__ nsel, int Mdense, int Mmax,
+                                                      const double* __restrict__ HP, const double* __restrict__ Kt,
+                                                      double* __restrict__ P) {
+  const int b = blockIdx.z;
+  const int M = nsel ? 2 * nsel[b] : Mdense;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (M == 0 || ti > tj) return;
+  __shared__ double sK[16][CT + 1], sH[16][CT + 1];
+  const double* __restrict__ HPb = HP + (size_t)b * Mmax * N;
+  const double* __restrict__ Ktb = Kt + (size_t)b * Mmax * N;
+  double* __restrict__ Pb = P + (size_t)b * N * N;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 2 x 2 outputs each
+  const int i0 = ti * CT, j0 = tj * CT;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  for (int r0 = 0; r0 < M; r0 += 16) {
+    for (int t = threadIdx.x; t < 16 * CT; t += 256) {
+      const int rr = t / CT, c = t - rr * CT;
+      const int r = r0 + rr;
+      sK[rr][c] = (r < M && i0 + c < N) ? Ktb[(size_t)r * N + i0 + c] : 0.0;
+      sH[rr][c] = (r < M && j0 + c < N) ? HPb[(size_t)r * N + j0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const double k0 = sK[rr][ty], k1 = sK[rr][ty + 16], h0 = sH[rr][tx], h1 = sH[rr][tx + 16];
+      acc[0][0] += k0 * h0;
+      acc[0][1] += k0 * h1;
+      acc[1][0] += k1 * h0;
+      acc[1][1] += k1 * h1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * c;
+      if (i < N && j < N && i <= j) {
+        const double v = Pb[(size_t)i * N + j] - acc[a][c];
+        Pb[(size_t)i * N + j] = v;
+        if (i != j) Pb[(size_t)j * N + i] = v;
+      }
+    }
+}
+
+static size_t gain_smem(int Mmax, bool sparse) {
+  size_t s = sizeof(double) * ((size_t)Mmax * Mmax + Mmax);
+  if (sparse) s += (size_t)Mmax * kHnnz * (sizeof(double) + sizeof(int));
+  return s;
+}
+
+int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel, const double* Rmeas,
+                      double* P, double* err, double* HP, double* Kt, double* H_dense, int batch) {
+  const int N = lay.N(), Mmax = 2 * lay.F;
+  const size_t smem = gain_smem(Mmax, true);
+  XB_REQUIRE(smem <= 227 * 1024, "EKF update: 2*F too large for the shared-memory Cholesky");
+  XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ekf_gain_kernel<true><<<batch, GAIN_THREADS, smem, st>>>(N, lay, jac, sel, nsel, 0, nullptr, nullptr, nullptr, Rmeas, P, err, HP,
+                                                          Kt, H_dense, Mmax);
+  const int nt = (N + CT - 1) / CT;
+  ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nsel, 0, Mmax, HP, Kt, P);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,
+                            double* err, double* HP, double* Kt, int batch) {
+  const size_t smem = gain_smem(M, false);
+  XB_REQUIRE(smem <= 227 * 1024, "EKF update: M too large for the shared-memory Cholesky");
+  XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EkfLayout lay{0, 0};
+  ekf_gain_kernel<false><<<batch, GAIN_THREADS, smem, st>>>(N, lay, nullptr, nullptr, nullptr, M, H, diagR, inn, nullptr, P, err,
+                                                           HP, Kt, nullptr, M);
+  const int nt = (N + CT - 1) / CT;
+  ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nullptr, M, M, HP, Kt, P);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Covariance edit list: the reference edits P in many tiny steps per frame
+// (/root/reference/src/estimator.cpp:739-846, :1362-1391, :1474-1478); with P device-resident
+// the host queues them and one launch applies them in order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cov_edit_kernel(int N, double* __restrict__ P, const EditOp* __restrict__ ops,
+                                                       const int* __restrict__ nops, int max_ops) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* __restrict__ Pb = P + (size_t)b * N * N;
+  const int n = nops[b];
+  for (int o = 0; o < n; ++o) {
+    const EditOp op = ops[(size_t)b * max_ops + o];
+    if (op.type == 0) {
+      for (int t = tid; t < op.n * N; t += 256) {
+        const int r = t / N, c = t - r * N;
+        Pb[(size_t)(op.a + r) * N + c] = 0.0;
+        Pb[(size_t)c * N + op.a + r] = 0.0;
+      }
+    } else if (op.type == 1) {
+      for (int t = tid; t < op.n * N; t += 256) {  // rows: P[a+r, :] = P[b+r, :]
+        const int r = t / N, c = t - r * N;
+        Pb[(size_t)(op.a + r) * N + c] = Pb[(size_t)(op.b + r) * N + c];
+      }
+      __syncthreads();
+      for (int t = tid; t < op.n * N; t += 256) {  // cols: P[:, a+r] = P[:, b+r]
+        const int r = t / N, c = t - r * N;
+        Pb[(size_t)c * N + op.a + r] = Pb[(size_t)c * N + op.b + r];
+      }
+    } else if (op.type == 2) {
+      if (tid < 9) Pb[(size_t)(op.a + tid / 3) * N + op.a + tid % 3] = op.blk[tid];
+    }
+    __syncthreads();
+  }
+}
+
+int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops, const int* nops, int max_ops, int batch) {
+  cov_edit_kernel<<<batch, 256, 0, st>>>(N, P, ops, nops, max_ops);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Propagation strips (/root/reference/src/princedormand.cpp:208-215, rk4.cpp:95-102, composed over
+// the sub-steps of all IMU samples since the previous frame): the 23x23 motion block is
+// integrated on the host in fp64; the device applies Phi to the motion/structure strips.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cov_propagate_kernel(int N, double* __restrict__ P, const double* __restrict__ Phi,
+                                                            const double* __restrict__ Pmm, const unsigned char* __restrict__ active) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (active && !active[b]) return;
+  __shared__ double sPhi[23 * 23];
+  double* __restrict__ Pb = P + (size_t)b * N * N;
+  for (int t = tid; t < 23 * 23; t += 256) sPhi[t] = Phi[(size_t)b * 529 + t];
+  __syncthreads();
+  for (int j = 23 + tid; j < N; j += 256) {
+    double col[23];
+#pragma unroll
+    for (int k = 0; k < 23; ++k) col[k] = Pb[(size_t)k * N + j];
+#pragma unroll 1
+    for (int i = 0; i < 23; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 23; ++k) acc += sPhi[i * 23 + k] * col[k];
+      Pb[(size_t)i * N + j] = acc;
+      Pb[(size_t)j * N + i] = acc;
+    }
+  }
+  for (int t = tid; t < 529; t += 256) Pb[(size_t)(t / 23) * N + t % 23] = Pmm[(size_t)b * 529 + t];
+}
+
+int launch_cov_propagate(cudaStream_t st, int N, double* P, const double* Phi, const double* Pmm, const unsigned char* active,
+                         int batch) {
+  cov_propagate_kernel<<<batch, 256, 0, st>>>(N, P, Phi, Pmm, active);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Depth sub-filter: Feature::SubfilterUpdate (/root/reference/src/feature.cpp:246-297).
+// ------------------------------------------------------------------------------------------
+__global__ void subfilter_kernel(const CameraParams* __restrict__ cam, const double* __restrict__ X,
+                                 const SubfilterIn* __restrict__ in, SubfilterOut* __restrict__ out, int n, double Rtri,
+                                 double mh_thresh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SubfilterIn f = in[i];
+  const double* Xb = X + (size_t)f.filter * kPoseDoubles;
+  M3 Rsb, Rbc, Rr;
+  V3 Tsb, Tbc, Tr;
+  for (int k = 0; k < 9; ++k) { Rsb.m[k] = Xb[k]; Rbc.m[k] = Xb[12 + k]; Rr.m[k] = f.ref[k]; }
+  for (int k = 0; k < 3; ++k) { Tsb.v[k] = Xb[9 + k]; Tbc.v[k] = Xb[21 + k]; Tr.v[k] = f.ref[9 + k]; }
+  const double z = exp(f.x[2]);
+  const V3 Xc{{f.x[0] * z, f.x[1] * z, z}};
+  const M3 dXc_dx{{z, 0, f.x[0] * z, 0, z, f.x[1] * z, 0, 0, z}};
+  // gtot = (gsb gbc)^-1 (gref gbc)
+  const M3 Rsc = m3_mul(Rsb, Rbc), Rrc = m3_mul(Rr, Rbc);
+  const V3 Tsc = v3_add(m3_mulv(Rsb, Tbc), Tsb), Trc = v3_add(m3_mulv(Rr, Tbc), Tr);
+  const M3 Rsc_t = m3_t(Rsc);
+  const M3 Rtot = m3_mul(Rsc_t, Rrc);
+  const V3 Ttot = m3_mulv(Rsc_t, v3_sub(Trc, Tsc));
+  const V3 Xcn = v3_add(m3_mulv(Rtot, Xc), Ttot);
+  const double iz = 1.0 / Xcn.v[2];
+  const double P23[6] = {iz, 0, -Xcn.v[0] * iz * iz, 0, iz, -Xcn.v[1] * iz * iz};
+  double u, v, Jc[4];
+  camera_project(cam[f.filter], Xcn.v[0] * iz, Xcn.v[1] * iz, &u, &v, Jc);
+  M23 d;
+  for (int j = 0; j < 3; ++j) {
+    d.m[j] = Jc[0] * P23[j] + Jc[1] * P23[3 + j];
+    d.m[3 + j] = Jc[2] * P23[j] + Jc[3] * P23[3 + j];
+  }
+  const M23 H = m23_mul(m23_mul(d, Rtot), dXc_dx);
+  const double r0 = f.xp[0] - u, r1 = f.xp[1] - v;
+  // PHt (3x2), S = H P H^T + Rtri
+  double PHt[6];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 2; ++c) PHt[2 * a + c] = f.P[3 * a] * H.m[3 * c] + f.P[3 * a + 1] * H.m[3 * c + 1] + f.P[3 * a + 2] * H.m[3 * c + 2];
+  double S00 = H.m[0] * PHt[0] + H.m[1] * PHt[2] + H.m[2] * PHt[4] + Rtri;
+  double S01 = H.m[0] * PHt[1] + H.m[1] * PHt[3] + H.m[2] * PHt[5];
+  double S10 = H.m[3] * PHt[0] + H.m[4] * PHt[2] + H.m[5] * PHt[4];
+  double S11 = H.m[3] * PHt[1] + H.m[4] * PHt[3] + H.m[5] * PHt[5] + Rtri;
+  const double det0 = S00 * S11 - S01 * S10;
+  const double ratio = (r0 * (S11 * r0 - S01 * r1) + r1 * (-S10 * r0 + S00 * r1)) / det0 / mh_thresh;
+  double oc;
+  if (ratio > 1) {
+    S00 += Rtri * (ratio - 1);
+    S11 += Rtri * (ratio - 1);
+    oc = f.outlier_counter + sqrt(ratio);
+  } else {
+    oc = 0.0;
+  }
+  const double det = S00 * S11 - S01 * S10;
+  const double Si[4] = {S11 / det, -S01 / det, -S10 / det, S00 / det};
+  double K[6];  // 3x2 = PHt * Sinv
+  for (int a = 0; a < 3; ++a) {
+    K[2 * a] = PHt[2 * a] * Si[0] + PHt[2 * a + 1] * Si[2];
+    K[2 * a + 1] = PHt[2 * a] * Si[1] + PHt[2 * a + 1] * Si[3];
+  }
+  SubfilterOut o;
+  for (int a = 0; a < 3; ++a) o.x[a] = f.x[a] + K[2 * a] * r0 + K[2 * a + 1] * r1;
+  double A[9];  // I - K H
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) A[3 * a + c] = (a == c ? 1.0 : 0.0) - (K[2 * a] * H.m[c] + K[2 * a + 1] * H.m[3 + c]);
+  double AP[9];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) AP[3 * a + c] = A[3 * a] * f.P[c] + A[3 * a + 1] * f.P[3 + c] + A[3 * a + 2] * f.P[6 + c];
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c)
+      o.P[3 * a + c] = AP[3 * a] * A[3 * c] + AP[3 * a + 1] * A[3 * c + 1] + AP[3 * a + 2] * A[3 * c + 2] +
+                       Rtri * (K[2 * a] * K[2 * c] + K[2 * a + 1] * K[2 * c + 1]);
+  o.outlier_counter = oc;
+  out[i] = o;
+}
+
+int launch_subfilter(cudaStream_t st, const CameraParams* cam, const double* X, const SubfilterIn* in, SubfilterOut* out, int n,
+                     double Rtri, double mh_thresh) {
+  if (n == 0) return 0;
+  subfilter_kernel<<<(n + 127) / 128, 128, 0, st>>>(cam, X, in, out, n, Rtri, mh_thresh);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// OOS / MSCKF blocks + left-nullspace projection.
+// Blocks: Feature::ComputeOOSJacobianInternal (/root/reference/src/oos.cpp:39-89).
+// Projection: the reference multiplies by a basis of ker(Hf^T) from FullPivLU::kernel
+// (/root/reference/src/helpers.cpp:13-23), which is neither unique nor orthonormal; we apply the
+// three Householder reflectors that triangularise Hf and drop the first 3 rows, i.e. A = Q[:, 3:]
+// is orthonormal (what the Givens variant, helpers.cpp:48-75, intends), so the projected noise
+// stays Roos * I.  Parity is therefore on invariants (A^T Hf = 0, row space of A^T Hx).
+// ------------------------------------------------------------------------------------------
+constexpr int OOS_THREADS = 128;
+constexpr int OOS_MAXROWS = 64;  // 2k <= 64
+
+__global__ void __launch_bounds__(OOS_THREADS) oos_kernel(EkfLayout lay, const CameraParams* __restrict__ cam,
+                                                          const double* __restrict__ gbc, const double* __restrict__ Xs,
+                                                          const double* __restrict__ obs_pose, const int* __restrict__ obs_sind,
+                                                          const double* __restrict__ obs_xp, int k, double* __restrict__ Hf,
+                                                          double* __restrict__ Hx, double* __restrict__ inn,
+                                                          double* __restrict__ Hx_proj, double* __restrict__ inn_proj) {
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const int N = lay.N(), R2 = 2 * k;
+  __shared__ double sHf[OOS_MAXROWS][3], sinn[OOS_MAXROWS], sv[OOS_MAXROWS];
+  __shared__ double sbeta;
+  double* __restrict__ Hxf = Hx + (size_t)f * R2 * N;
+  for (int t = tid; t < R2 * N; t += OOS_THREADS) Hxf[t] = 0.0;
+  __syncthreads();
+  if (tid < k) {
+    M3 Rbc, Rsb;
+    V3 Tbc, Tsb;
+    const double* gp = obs_pose + ((size_t)f * k + tid) * kGroupDoubles;
+    for (int i = 0; i < 9; ++i) { Rbc.m[i] = gbc[i]; Rsb.m[i] = gp[i]; }
+    for (int i = 0; i < 3; ++i) { Tbc.v[i] = gbc[9 + i]; Tsb.v[i] = gp[9 + i]; }
+    const M3 Rsb_t = m3_t(Rsb), Rbc_t = m3_t(Rbc);
+    const V3 X{{Xs[3 * f], Xs[3 * f + 1], Xs[3 * f + 2]}};
+    const V3 Xb = m3_mulv(Rsb_t, v3_sub(X, Tsb));
+    const V3 Xcn = m3_mulv(Rbc_t, v3_sub(Xb, Tbc));
+    const double iz = 1.0 / Xcn.v[2];
+    const double P23[6] = {iz, 0, -Xcn.v[0] * iz * iz, 0, iz, -Xcn.v[1] * iz * iz};
+    double u, v, Jc[4];
+    camera_project(cam[0], Xcn.v[0] * iz, Xcn.v[1] * iz, &u, &v, Jc);
+    M23 d;
+    for (int j = 0; j < 3; ++j) {
+      d.m[j] = Jc[0] * P23[j] + Jc[1] * P23[3 + j];
+      d.m[3 + j] = Jc[2] * P23[j] + Jc[3] * P23[3 + j];
+    }
+    const M23 dRbct = m23_mul(d, Rbc_t);
+    const M23 hf = m23_mul(dRbct, Rsb_t);
+    const M23 hW = m23_mul(dRbct, m3_hat(Xb));
+    const M23 hT = m23_mul(dRbct, m3_neg(Rsb_t));
+    const M23 hWbc = m23_mul(d, m3_hat(Xcn));
+    const M23 hTbc = m23_mul(d, m3_neg(Rbc_t));
+    const int goff = lay.goff(obs_sind[(size_t)f * k + tid]);
+    for (int r = 0; r < 2; ++r) {
+      const int row = 2 * tid + r;
+      for (int j = 0; j < 3; ++j) {
+        sHf[row][j] = hf.m[3 * r + j];
+        Hxf[(size_t)row * N + goff + j] = hW.m[3 * r + j];
+        Hxf[(size_t)row * N + goff + 3 + j] = hT.m[3 * r + j];
+        Hxf[(size_t)row * N + 15 + j] = hWbc.m[3 * r + j];
+        Hxf[(size_t)row * N + 18 + j] = hTbc.m[3 * r + j];
+      }
+      sinn[row] = obs_xp[((size_t)f * k + tid) * 2 + r] - (r == 0 ? u : v);
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < R2 * 3; t += OOS_THREADS) Hf[(size_t)f * R2 * 3 + t] = sHf[t / 3][t % 3];
+  for (int t = tid; t < R2; t += OOS_THREADS) inn[(size_t)f * R2 + t] = sinn[t];
+  // working copy of Hx for the projection
+  double* __restrict__ W = Hx_proj ? Hx_proj + (size_t)f * R2 * N : nullptr;  // caller sizes Hx_proj as 2k x N scratch+output
+  if (!W) return;
+  for (int t = tid; t < R2 * N; t += OOS_THREADS) W[t] = Hxf[t];
+  __syncthreads();
+  for (int c = 0; c < 3; ++c) {
+    if (tid == 0) {
+      double nrm = 0.0;
+      for (int r = c; r < R2; ++r) nrm += sHf[r][c] * sHf[r][c];
+      nrm = sqrt(nrm);
+      const double alpha = sHf[c][c] > 0 ? -nrm : nrm;
+      double vnorm2 = 0.0;
+      for (int r = c; r < R2; ++r) {
+        sv[r] = sHf[r][c] - (r == c ? alpha : 0.0);
+        vnorm2 += sv[r] * sv[r];
+      }
+      sbeta = vnorm2 > 0 ? 2.0 / vnorm2 : 0.0;
+    }
+    __syncthreads();
+    // apply (I - beta v v^T) to Hf columns, inn (thread 0..3) and to the N columns of W
+    if (tid < 4) {
+      double dot = 0.0;
+      for (int r = c; r < R2; ++r) dot += sv[r] * (tid < 3 ? sHf[r][tid] : sinn[r]);
+      dot *= sbeta;
+      for (int r = c; r < R2; ++r) {
+        if (tid < 3) sHf[r][tid] -= dot * sv[r];
+        else sinn[r] -= dot * sv[r];
+      }
+    }
+    for (int j = tid; j < N; j += OOS_THREADS) {
+      double dot = 0.0;
+      for (int r = c; r < R2; ++r) dot += sv[r] * W[(size_t)r * N + j];
+      dot *= sbeta;
+      for (int r = c; r < R2; ++r) W[(size_t)r * N + j] -= dot * sv[r];
+    }
+    __syncthreads();
+  }
+  // rows 3.. are the projected system; compact them to the front of the output
+  for (int r = 3; r < R2; ++r) {
+    for (int j = tid; j < N; j += OOS_THREADS) W[(size_t)(r - 3) * N + j] = W[(size_t)r * N + j];
+    __syncthreads();
+  }
+  for (int t = tid; t < R2 - 3; t += OOS_THREADS) inn_proj[(size_t)f * R2 + t] = sinn[t + 3];
+}
+
+int launch_oos(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const double* Rbc_Tbc, const double* Xs,
+               const double* obs_pose, const int* obs_sind, const double* obs_xp, int k, int nf, double* Hf, double* Hx,
+               double* inn, double* Hx_proj, double* inn_proj) {
+  XB_REQUIRE(2 * k <= OOS_MAXROWS && k >= 2, "OOS: 2 <= observations <= 32");
+  if (nf == 0) return 0;
+  oos_kernel<<<nf, OOS_THREADS, 0, st>>>(lay, cam, Rbc_Tbc, Xs, obs_pose, obs_sind, obs_xp, k, Hf, Hx, inn, Hx_proj, inn_proj);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace xb

@@ -1,0 +1,89 @@
+// Internal launcher declarations shared by the C-ABI layer and the host estimator.
+// Every launcher works on DEVICE pointers, takes a batch dimension (independent sequences /
+// filters) and enqueues on the given stream without synchronising.
+#pragma once
+#include "common.cuh"
+
+namespace xb {
+
+// ---------------- tracker (tracker_kernels.cu) ----------------
+int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const PyrDesc& d, int batch);
+int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, int rows, int cols, int cn,
+                       int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch);
+size_t lk_smem_bytes(int win, int cn);
+int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, unsigned long long pyr_stride,
+                    const PyrDesc& d, const float* prev_pts, float* next_pts, uint8_t* status, float* err,
+                    const int* npts_dev, int max_pts, int batch, int win, int max_iter, double eps, int use_initial_flow,
+                    double min_eig);
+
+// ---------------- EKF (ekf_kernels.cu) ----------------
+// Error-state layout, /root/reference/src/core.h:40-105 (default build: no online calibration).
+struct EkfLayout {
+  int G, F;
+  __host__ __device__ int N() const { return 23 + 6 * G + 3 * F; }
+  __host__ __device__ int goff(int s) const { return 23 + 6 * s; }
+  __host__ __device__ int foff(int s) const { return 23 + 6 * G + 3 * s; }
+};
+constexpr int kJacNnz = 21;  // non-zero columns of one feature's 2xN Jacobian
+
+// Per-feature output of the Jacobian/gate kernel (compact form of Feature::J_, inn_).
+struct FeatJac {
+  double J[2][kJacNnz];  // columns: Wsb(3) Tsb(3) Wbc(3) Tbc(3) Wsbr(3) Tsbr(3) x(3)
+  double inn[2];
+  double mh;  // Mahalanobis distance r^T (J P J^T + R)^-1 r
+  int goff, foff;
+};
+
+// Motion + calibration state the Jacobians need: Rsb(9) Tsb(3) Rbc(9) Tbc(3), row-major.
+constexpr int kPoseDoubles = 24;
+constexpr int kGroupDoubles = 12;  // Rsb(9) Tsb(3) of a group slot
+
+int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam /*device, per filter*/,
+                         const double* X /*B x 24*/, const double* groups /*B x G x 12*/, const double* feat_x /*B x F x 3*/,
+                         const double* feat_xp /*B x F x 2*/, const int* feat_ref /*B x F*/, const int* feat_sind /*B x F*/,
+                         const int* nfeat /*B*/, const double* P /*B x N x N*/, const double* Rmeas /*B*/,
+                         FeatJac* out /*B x F*/, double* J_dense /*B x F x 2 x N or null*/, int batch);
+
+// Stack H (FillJacobianBlock semantics) for the selected features and do the measurement update.
+//   sel: B x F indices into the feature table, nsel: B counts (M = 2*nsel)
+// scratch: HP (B x 2F x N), Kt (B x 2F x N).  Outputs: err (B x N), P updated in place.
+int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel,
+                      const double* Rmeas /*B*/, double* P, double* err, double* HP, double* Kt, double* H_dense /*or null*/,
+                      int batch);
+
+// Dense-input variant used by the kernel-level C ABI (arbitrary H, diagR), same kernels underneath.
+int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,
+                            double* err, double* HP, double* Kt, int batch);
+
+// Covariance edit list (AddGroupToState / AddFeatureToState / Remove* / FixFeatureXY / SwitchRefGroup).
+struct EditOp {
+  int type;  // 0 = zero rows+cols [a, a+n); 1 = copy rows then cols b -> a (n wide); 2 = set 3x3 block at (a, a)
+  int a, b, n;
+  double blk[9];
+};
+int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops /*B x max_ops*/, const int* nops /*B*/, int max_ops,
+                    int batch);
+
+// Propagation: P[0:23,0:23] <- Pmm ; P[0:23,23:] <- Phi P[0:23,23:] and the symmetric strip.
+int launch_cov_propagate(cudaStream_t st, int N, double* P, const double* Phi /*B x 23 x 23*/, const double* Pmm /*B x 23 x 23*/,
+                         const unsigned char* active /*B or null*/, int batch);
+
+// Depth sub-filter, thread per feature (Feature::SubfilterUpdate).
+struct SubfilterIn {
+  double x[3], P[9], xp[2], ref[kGroupDoubles], outlier_counter;
+  int filter;  // which filter (sequence) the feature belongs to
+  int pad;
+};
+struct SubfilterOut {
+  double x[3], P[9], outlier_counter;
+};
+int launch_subfilter(cudaStream_t st, const CameraParams* cam /*per filter*/, const double* X /*B x 24*/, const SubfilterIn* in,
+                     SubfilterOut* out, int n, double Rtri, double mh_thresh);
+
+// OOS / MSCKF: per-observation blocks + left-nullspace projection (Householder), one CTA per feature.
+int launch_oos(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const double* Rbc_Tbc /*12*/, const double* Xs /*nf x 3*/,
+               const double* obs_pose /*nf x k x 12*/, const int* obs_sind /*nf x k*/, const double* obs_xp /*nf x k x 2*/,
+               int k, int nf, double* Hf /*nf x 2k x 3*/, double* Hx /*nf x 2k x N*/, double* inn /*nf x 2k*/,
+               double* Hx_proj /*nf x 2k x N scratch; first 2k-3 rows valid*/, double* inn_proj /*nf x 2k; first 2k-3 valid*/);
+
+}  // namespace xb

@@ -1,0 +1,491 @@
+// Tracker kernels (HOT LOOP 1 of SURVEY.md §3.2): image pyramid, FAST-9/16 score + NMS,
+// pyramidal Lucas-Kanade.  Integer / fixed-point semantics follow OpenCV exactly
+// (the arithmetic the reference calls at /root/reference/src/tracker.cpp:224, :493, :526);
+// float math in LK is compiled with -fmad=false so it rounds like the scalar CPU code.
+//
+// All kernels take a batch dimension (blockIdx.z or .y = independent sequence) because the
+// only way a 640x480 frame fills a B200 is by processing many sequences per launch.
+#include "kernels.h"
+
+namespace xb {
+
+// ------------------------------------------------------------------------------------------
+// pyrDown: 5-tap [1 4 6 4 1] separable, BORDER_REFLECT_101, (sum+128)>>8   (cv::pyrDown, u8)
+// Replaces cv::buildOpticalFlowPyramid's per-level pyrDown (tracker.cpp:476,493).  Scharr
+// derivatives are NOT materialised: the LK kernel recomputes them from the staged patch.
+// Tile: 32x8 output pixels; input region (2*32+3)x(2*8+3) staged in shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int PD_TX = 32, PD_TY = 8;
+
+template <int CN>
+__global__ void __launch_bounds__(PD_TX* PD_TY) pyrdown_kernel(uint8_t* __restrict__ pyr, unsigned long long pyr_stride,
+                                                                PyrDesc d, int lvl_src) {
+  const int srows = d.rows[lvl_src], scols = d.cols[lvl_src];
+  const int drows = d.rows[lvl_src + 1], dcols = d.cols[lvl_src + 1];
+  const uint8_t* __restrict__ src = pyr + (size_t)blockIdx.z * pyr_stride + d.off[lvl_src];
+  uint8_t* __restrict__ dst = pyr + (size_t)blockIdx.z * pyr_stride + d.off[lvl_src + 1];
+  constexpr int RW = 2 * PD_TX + 3, RH = 2 * PD_TY + 3;
+  __shared__ uint8_t tile[RH][RW * CN + 1];
+  __shared__ unsigned short hsum[RH][PD_TX * CN];
+  const int ox = blockIdx.x * PD_TX, oy = blockIdx.y * PD_TY;
+  const int tid = threadIdx.y * PD_TX + threadIdx.x;
+  const int sx0 = 2 * ox - 2, sy0 = 2 * oy - 2;
+  for (int i = tid; i < RH * RW; i += PD_TX * PD_TY) {
+    int ry = i / RW, rx = i - ry * RW;
+    int sy = reflect101(sy0 + ry, srows), sx = reflect101(sx0 + rx, scols);
+    const uint8_t* p = src + ((size_t)sy * scols + sx) * CN;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) tile[ry][rx * CN + c] = p[c];
+  }
+  __syncthreads();
+  // horizontal pass for all RH rows
+  for (int i = tid; i < RH * PD_TX * CN; i += PD_TX * PD_TY) {
+    int ry = i / (PD_TX * CN), r = i - ry * (PD_TX * CN);
+    int x = r / CN, c = r - x * CN;
+    const uint8_t* t = &tile[ry][(2 * x) * CN + c];
+    int s = t[0] + t[4 * CN] + 4 * (t[CN] + t[3 * CN]) + 6 * t[2 * CN];
+    hsum[ry][r] = (unsigned short)s;
+  }
+  __syncthreads();
+  const int x = ox + threadIdx.x, y = oy + threadIdx.y;
+  if (x < dcols && y < drows) {
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+      int r = threadIdx.x * CN + c, ry = 2 * threadIdx.y;
+      int s = hsum[ry][r] + hsum[ry + 4][r] + 4 * (hsum[ry + 1][r] + hsum[ry + 3][r]) + 6 * hsum[ry + 2][r];
+      dst[((size_t)y * dcols + x) * CN + c] = (uint8_t)((s + 128) >> 8);
+    }
+  }
+}
+
+int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const PyrDesc& d, int batch) {
+  for (int l = 0; l + 1 < d.n_levels; ++l) {
+    dim3 grid((d.cols[l + 1] + PD_TX - 1) / PD_TX, (d.rows[l + 1] + PD_TY - 1) / PD_TY, batch);
+    dim3 block(PD_TX, PD_TY);
+    if (d.cn == 1) pyrdown_kernel<1><<<grid, block, 0, st>>>(pyr, pyr_stride, d, l);
+    else pyrdown_kernel<3><<<grid, block, 0, st>>>(pyr, pyr_stride, d, l);
+  }
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST-9/16 + cornerScore + 3x3 non-max suppression (cv::FastFeatureDetector, TYPE_9_16).
+// One CTA = 64x16 output pixels.  Stage (64+8)x(16+8) grey pixels (ring radius 3 + NMS 1),
+// compute the score on (64+2)x(16+2), suppress, append packed keypoints with an atomic
+// cursor.  For 3-channel input the BGR->grey fixed-point conversion (cv2 4.13 15-bit
+// coefficients) is fused into the tile load, so the image is read exactly once from HBM.
+// Output: packed (y<<20 | x<<8 | score); order is arbitrary (host sorts on the composite key).
+// ------------------------------------------------------------------------------------------
+constexpr int FT_TX = 64, FT_TY = 16, FT_THREADS = 256;
+constexpr int FT_RW = FT_TX + 8, FT_RH = FT_TY + 8;  // pixel region
+constexpr int FT_SW = FT_TX + 2, FT_SH = FT_TY + 2;  // score region
+
+__device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_RW + 4], int rx, int ry, int thr) {
+  // t indexed [row][col] in region coords; (rx, ry) is the centre.
+  const int v = t[ry][rx];
+  int d[16];
+  d[0] = v - t[ry + 3][rx];
+  d[4] = v - t[ry][rx + 3];
+  d[8] = v - t[ry - 3][rx];
+  d[12] = v - t[ry][rx - 3];
+  // any 9-arc of the 16-ring contains >= 2 of the 4 compass points
+  int nb = (d[0] < -thr) + (d[4] < -thr) + (d[8] < -thr) + (d[12] < -thr);
+  int nd = (d[0] > thr) + (d[4] > thr) + (d[8] > thr) + (d[12] > thr);
+  if (nb < 2 && nd < 2) return 0;
+  d[1] = v - t[ry + 3][rx + 1];
+  d[2] = v - t[ry + 2][rx + 2];
+  d[3] = v - t[ry + 1][rx + 3];
+  d[5] = v - t[ry - 1][rx + 3];
+  d[6] = v - t[ry - 2][rx + 2];
+  d[7] = v - t[ry - 3][rx + 1];
+  d[9] = v - t[ry - 3][rx - 1];
+  d[10] = v - t[ry - 2][rx - 2];
+  d[11] = v - t[ry - 1][rx - 3];
+  d[13] = v - t[ry + 1][rx - 3];
+  d[14] = v - t[ry + 2][rx - 2];
+  d[15] = v - t[ry + 3][rx - 1];
+  unsigned mb = 0, md = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    mb |= (unsigned)(d[k] < -thr) << k;
+    md |= (unsigned)(d[k] > thr) << k;
+  }
+  mb |= mb << 16;
+  md |= md << 16;
+  unsigned ab = mb, ad = md;
+#pragma unroll
+  for (int k = 1; k < 9; ++k) {
+    ab &= mb >> k;
+    ad &= md >> k;
+  }
+  if (((ab | ad) & 0xffffu) == 0) return 0;
+  // cornerScore<16>: max over the 16 arcs of min(d) / min(-d), minus 1
+  int best = -1000;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    int mn = d[s], mx = d[s];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) {
+      int e = d[(s + k) & 15];
+      mn = min(mn, e);
+      mx = max(mx, e);
+    }
+    best = max(best, max(mn, -mx));
+  }
+  return best - 1;  // corner  <=>  best > thr
+}
+
+template <int CN>
+__global__ void __launch_bounds__(FT_THREADS) fast_kernel(const uint8_t* __restrict__ img, unsigned long long img_stride,
+                                                          int rows, int cols, int thr, int nonmax,
+                                                          unsigned* __restrict__ kp_out, int max_kp,
+                                                          int* __restrict__ kp_count) {
+  __shared__ uint8_t tile[FT_RH][FT_RW + 4];
+  __shared__ short score[FT_SH][FT_SW + 2];
+  const uint8_t* __restrict__ src = img + (size_t)blockIdx.z * img_stride;
+  const int ox = blockIdx.x * FT_TX, oy = blockIdx.y * FT_TY;
+  const int tid = threadIdx.x;
+  // region origin in image coordinates
+  const int gx0 = ox - 4, gy0 = oy - 4;
+  for (int i = tid; i < FT_RH * FT_RW; i += FT_THREADS) {
+    int ry = i / FT_RW, rx = i - ry * FT_RW;
+    int gx = gx0 + rx, gy = gy0 + ry;
+    int val = 0;
+    if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+      const uint8_t* p = src + ((size_t)gy * cols + gx) * CN;
+      if (CN == 1) val = p[0];
+      else val = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15;
+    }
+    tile[ry][rx] = (uint8_t)val;
+  }
+  __syncthreads();
+  for (int i = tid; i < FT_SH * FT_SW; i += FT_THREADS) {
+    int sy = i / FT_SW, sx = i - sy * FT_SW;
+    int gx = ox - 1 + sx, gy = oy - 1 + sy;
+    int s = 0;
+    if (gx >= 3 && gx < cols - 3 && gy >= 3 && gy < rows - 3) s = fast_score(tile, sx + 3, sy + 3, thr);
+    score[sy][sx] = (short)s;
+  }
+  __syncthreads();
+  for (int i = tid; i < FT_TY * FT_TX; i += FT_THREADS) {
+    int ty = i / FT_TX, tx = i - ty * FT_TX;
+    int gx = ox + tx, gy = oy + ty;
+    if (gx >= cols || gy >= rows) continue;
+    int s = score[ty + 1][tx + 1];
+    if (s <= 0) continue;
+    bool keep = true;
+    if (nonmax) {
+      keep = s > score[ty][tx] && s > score[ty][tx + 1] && s > score[ty][tx + 2] && s > score[ty + 1][tx] &&
+             s > score[ty + 1][tx + 2] && s > score[ty + 2][tx] && s > score[ty + 2][tx + 1] && s > score[ty + 2][tx + 2];
+    }
+    if (keep) {
+      int idx = atomicAdd(&kp_count[blockIdx.z], 1);
+      if (idx < max_kp) kp_out[(size_t)blockIdx.z * max_kp + idx] = ((unsigned)gy << 20) | ((unsigned)gx << 8) | (unsigned)s;
+    }
+  }
+}
+
+int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, int rows, int cols, int cn,
+                       int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch) {
+  XB_REQUIRE(rows < 4096 && cols < 4096, "FAST: image dimension must be < 4096 (12-bit packed coordinates)");
+  XB_REQUIRE(thr >= 0 && thr < 255, "FAST: threshold out of range");
+  XB_CUDA(cudaMemsetAsync(kp_count, 0, sizeof(int) * batch, st));
+  dim3 grid((cols + FT_TX - 1) / FT_TX, (rows + FT_TY - 1) / FT_TY, batch);
+  if (cn == 1) fast_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+  else fast_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pyramidal Lucas-Kanade (cv::calcOpticalFlowPyrLK / LKTrackerInvoker restated).
+// One warp per feature walks the levels coarse -> fine.  Per level the warp stages the
+// (win+3)^2 patch of the previous image in shared memory, derives the Scharr gradients from it
+// (OpenCV materialises them; we never write them to HBM), builds the fixed-point template
+// (14-bit bilinear weights, 5 guard bits) and iterates; window sums are exact integers reduced
+// with warp shuffles, then converted to float once (OpenCV sums float SIMD lanes; the integer
+// sum is the value those floats approximate).
+// ------------------------------------------------------------------------------------------
+constexpr int LK_WARPS = 4;
+constexpr int LK_MAX_WIN = 21;
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+struct LKParams {
+  int win, max_iter, use_initial_flow, max_pts;
+  float eps_sq_f;  // unused (double compare below)
+  double eps_sq, min_eig;
+};
+
+template <int CN>
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
+                                                          unsigned long long pyr_stride, PyrDesc d,
+                                                          const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+                                                          uint8_t* __restrict__ status, float* __restrict__ err,
+                                                          const int* __restrict__ npts, LKParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.y;
+  const int p = blockIdx.x * LK_WARPS + warp;
+  if (p >= npts[seq]) return;  // whole warp exits together
+  const int win = prm.win;
+  const int RW = win + 3;  // staged region side (patch + bilinear + Scharr halo)
+  const int DW = win + 1;  // derivative tile side
+  // per-warp shared memory carve-up
+  const int reg_bytes = ((RW * RW * CN + 15) / 16) * 16;
+  const int dt_elems = DW * DW * CN * 2;
+  const int iw_elems = win * win * CN;
+  const int per_warp = reg_bytes + 2 * (dt_elems + iw_elems * 3);
+  uint8_t* region = smem_raw + (size_t)warp * (((per_warp + 15) / 16) * 16);
+  short* dtile = reinterpret_cast<short*>(region + reg_bytes);
+  short* Iw = dtile + dt_elems;
+  short* dIw = Iw + iw_elems;
+
+  const uint8_t* __restrict__ ppyr = prev_pyr + (size_t)seq * pyr_stride;
+  const uint8_t* __restrict__ npyr = next_pyr + (size_t)seq * pyr_stride;
+  const size_t pi = (size_t)seq * prm.max_pts + p;
+  const float ppx = prev_pts[2 * pi], ppy = prev_pts[2 * pi + 1];
+  float outx = next_pts[2 * pi], outy = next_pts[2 * pi + 1];
+  int st = 1;
+  float errv = 0.f;
+  const float half = (win - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  const int max_level = d.n_levels - 1;
+
+  for (int level = max_level; level >= 0; --level) {
+    const int rows = d.rows[level], cols = d.cols[level];
+    const uint8_t* __restrict__ I = ppyr + d.off[level];
+    const uint8_t* __restrict__ J = npyr + d.off[level];
+    const float scale = (float)(1. / (1 << level));
+    float px = ppx * scale, py = ppy * scale;
+    float nx, ny;
+    if (level == max_level) {
+      if (prm.use_initial_flow) { nx = outx * scale; ny = outy * scale; }
+      else { nx = px; ny = py; }
+    } else {
+      nx = outx * 2.f;
+      ny = outy * 2.f;
+    }
+    outx = nx;
+    outy = ny;
+    px -= half;
+    py -= half;
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) {
+      if (level == 0) { st = 0; errv = 0.f; }
+      continue;
+    }
+    float a = px - ipx, b = py - ipy;
+    int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+    int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+    int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+    int iw11 = 16384 - iw00 - iw01 - iw10;
+
+    __syncwarp();
+    // stage region: origin (ipx-1, ipy-1), REFLECT_101 == reads of OpenCV's padded level
+    for (int i = lane; i < RW * RW; i += 32) {
+      int ry = i / RW, rx = i - ry * RW;
+      int sy = reflect101(ipy - 1 + ry, rows), sx = reflect101(ipx - 1 + rx, cols);
+      const uint8_t* q = I + ((size_t)sy * cols + sx) * CN;
+#pragma unroll
+      for (int c = 0; c < CN; ++c) region[i * CN + c] = q[c];
+    }
+    __syncwarp();
+    // Scharr derivatives on the (win+1)^2 grid; zero outside the image (BORDER_CONSTANT)
+    for (int i = lane; i < DW * DW; i += 32) {
+      int ty = i / DW, tx = i - ty * DW;
+      int X = ipx + tx, Y = ipy + ty;
+      bool inside = (X >= 0 && X < cols && Y >= 0 && Y < rows);
+      const uint8_t* r0 = region + ((ty)*RW + tx) * CN;  // row Y-1, col X-1
+      const uint8_t* r1 = r0 + RW * CN;
+      const uint8_t* r2 = r1 + RW * CN;
+#pragma unroll
+      for (int c = 0; c < CN; ++c) {
+        int dx = 0, dy = 0;
+        if (inside) {
+          int t0l = (r0[c] + r2[c]) * 3 + r1[c] * 10;
+          int t0r = (r0[2 * CN + c] + r2[2 * CN + c]) * 3 + r1[2 * CN + c] * 10;
+          int t1l = r2[c] - r0[c], t1c = r2[CN + c] - r0[CN + c], t1r = r2[2 * CN + c] - r0[2 * CN + c];
+          dx = t0r - t0l;
+          dy = (t1r + t1l) * 3 + t1c * 10;
+        }
+        dtile[(i * CN + c) * 2] = (short)dx;
+        dtile[(i * CN + c) * 2 + 1] = (short)dy;
+      }
+    }
+    __syncwarp();
+    // template + structure tensor
+    int sA11 = 0, sA12 = 0, sA22 = 0;  // per-lane partials fit int32 (<= 22 terms of < 1.7e7)
+    long long lA11 = 0, lA12 = 0, lA22 = 0;
+    for (int i = lane; i < win * win; i += 32) {
+      int y = i / win, x = i - y * win;
+      const uint8_t* q = region + ((y + 1) * RW + (x + 1)) * CN;
+      const short* dq = dtile + (y * DW + x) * CN * 2;
+#pragma unroll
+      for (int c = 0; c < CN; ++c) {
+        int ival = descale(q[c] * iw00 + q[CN + c] * iw01 + q[RW * CN + c] * iw10 + q[RW * CN + CN + c] * iw11, 9);
+        int ix = descale(dq[2 * c] * iw00 + dq[2 * (CN + c)] * iw01 + dq[2 * (DW * CN + c)] * iw10 + dq[2 * (DW * CN + CN + c)] * iw11, 14);
+        int iy = descale(dq[2 * c + 1] * iw00 + dq[2 * (CN + c) + 1] * iw01 + dq[2 * (DW * CN + c) + 1] * iw10 +
+                             dq[2 * (DW * CN + CN + c) + 1] * iw11,
+                         14);
+        Iw[i * CN + c] = (short)ival;
+        dIw[(i * CN + c) * 2] = (short)ix;
+        dIw[(i * CN + c) * 2 + 1] = (short)iy;
+        sA11 += ix * ix;
+        sA12 += ix * iy;
+        sA22 += iy * iy;
+      }
+      // flush partials every sample group to stay inside int32 for any CN/win
+      lA11 += sA11; lA12 += sA12; lA22 += sA22;
+      sA11 = sA12 = sA22 = 0;
+    }
+    lA11 = warp_sum_ll(lA11);
+    lA12 = warp_sum_ll(lA12);
+    lA22 = warp_sum_ll(lA22);
+    __syncwarp();
+    const float A11 = __ll2float_rn(lA11) * FLT_SCALE, A12 = __ll2float_rn(lA12) * FLT_SCALE, A22 = __ll2float_rn(lA22) * FLT_SCALE;
+    float D = A11 * A22 - A12 * A12;
+    const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if ((double)minEig < prm.min_eig || D < 1.1920928955078125e-7f) {
+      if (level == 0) st = 0;
+      continue;
+    }
+    D = 1.f / D;
+    nx -= half;
+    ny -= half;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < prm.max_iter; ++j) {
+      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+      if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+        if (level == 0) st = 0;
+        break;
+      }
+      a = nx - inx;
+      b = ny - iny;
+      iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+      iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+      iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+      iw11 = 16384 - iw00 - iw01 - iw10;
+      const bool interior = (inx >= 0 && iny >= 0 && inx + win < cols && iny + win < rows);
+      long long lb1 = 0, lb2 = 0;
+      for (int i = lane; i < win * win; i += 32) {
+        int y = i / win, x = i - y * win;
+        int X0 = inx + x, X1 = X0 + 1, Y0 = iny + y, Y1 = Y0 + 1;
+        if (!interior) {
+          X0 = reflect101(X0, cols); X1 = reflect101(X1, cols);
+          Y0 = reflect101(Y0, rows); Y1 = reflect101(Y1, rows);
+        }
+        const uint8_t* q00 = J + ((size_t)Y0 * cols + X0) * CN;
+        const uint8_t* q01 = J + ((size_t)Y0 * cols + X1) * CN;
+        const uint8_t* q10 = J + ((size_t)Y1 * cols + X0) * CN;
+        const uint8_t* q11 = J + ((size_t)Y1 * cols + X1) * CN;
+        int s1 = 0, s2 = 0;
+#pragma unroll
+        for (int c = 0; c < CN; ++c) {
+          int diff = descale(__ldg(q00 + c) * iw00 + __ldg(q01 + c) * iw01 + __ldg(q10 + c) * iw10 + __ldg(q11 + c) * iw11, 9) -
+                     Iw[i * CN + c];
+          s1 += diff * dIw[(i * CN + c) * 2];
+          s2 += diff * dIw[(i * CN + c) * 2 + 1];
+        }
+        lb1 += s1;
+        lb2 += s2;
+      }
+      lb1 = warp_sum_ll(lb1);
+      lb2 = warp_sum_ll(lb2);
+      const float b1 = __ll2float_rn(lb1) * FLT_SCALE, b2 = __ll2float_rn(lb2) * FLT_SCALE;
+      const float dx = (A12 * b2 - A22 * b1) * D;
+      const float dy = (A12 * b1 - A11 * b2) * D;
+      nx += dx;
+      ny += dy;
+      outx = nx + half;
+      outy = ny + half;
+      if ((double)dx * dx + (double)dy * dy <= prm.eps_sq) break;
+      if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+        outx -= dx * 0.5f;
+        outy -= dy * 0.5f;
+        break;
+      }
+      pdx = dx;
+      pdy = dy;
+    }
+    if (st && level == 0) {
+      // default-flags error measure: mean |J - I| over the window / 32 (lkpyramid.cpp tail)
+      const float fx = outx - half, fy = outy - half;
+      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+      if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+        st = 0;
+        continue;
+      }
+      const float aa = fx - inx, bb = fy - iny;
+      iw00 = __float2int_rn((1.f - aa) * (1.f - bb) * 16384.f);
+      iw01 = __float2int_rn(aa * (1.f - bb) * 16384.f);
+      iw10 = __float2int_rn((1.f - aa) * bb * 16384.f);
+      iw11 = 16384 - iw00 - iw01 - iw10;
+      long long le = 0;
+      for (int i = lane; i < win * win; i += 32) {
+        int y = i / win, x = i - y * win;
+        int X0 = reflect101(inx + x, cols), X1 = reflect101(inx + x + 1, cols);
+        int Y0 = reflect101(iny + y, rows), Y1 = reflect101(iny + y + 1, rows);
+#pragma unroll
+        for (int c = 0; c < CN; ++c) {
+          int diff = descale(J[((size_t)Y0 * cols + X0) * CN + c] * iw00 + J[((size_t)Y0 * cols + X1) * CN + c] * iw01 +
+                                 J[((size_t)Y1 * cols + X0) * CN + c] * iw10 + J[((size_t)Y1 * cols + X1) * CN + c] * iw11,
+                             9) -
+                     Iw[i * CN + c];
+          le += abs(diff);
+        }
+      }
+      le = warp_sum_ll(le);
+      errv = __ll2float_rn(le) * 1.f / (float)(32 * win * CN * win);
+    }
+  }
+  if (lane == 0) {
+    next_pts[2 * pi] = outx;
+    next_pts[2 * pi + 1] = outy;
+    status[pi] = (uint8_t)st;
+    if (err) err[pi] = errv;
+  }
+}
+
+size_t lk_smem_bytes(int win, int cn) {
+  const int RW = win + 3, DW = win + 1;
+  const int reg_bytes = ((RW * RW * cn + 15) / 16) * 16;
+  const int per_warp = reg_bytes + 2 * (DW * DW * cn * 2 + win * win * cn * 3);
+  return (size_t)LK_WARPS * (((per_warp + 15) / 16) * 16);
+}
+
+int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, unsigned long long pyr_stride,
+                    const PyrDesc& d, const float* prev_pts, float* next_pts, uint8_t* status, float* err,
+                    const int* npts_dev, int max_pts, int batch, int win, int max_iter, double eps, int use_initial_flow,
+                    double min_eig) {
+  XB_REQUIRE(win >= 3 && win <= LK_MAX_WIN && (win & 1), "LK: win_size must be odd and in [3, 21]");
+  XB_REQUIRE(d.cn == 1 || d.cn == 3, "LK: 1 or 3 channels");
+  LKParams prm;
+  prm.win = win;
+  prm.max_iter = max_iter < 0 ? 0 : (max_iter > 100 ? 100 : max_iter);
+  double e = eps < 0 ? 0 : (eps > 10 ? 10 : eps);
+  prm.eps_sq = e * e;
+  prm.eps_sq_f = (float)prm.eps_sq;
+  prm.min_eig = min_eig;
+  prm.use_initial_flow = use_initial_flow;
+  prm.max_pts = max_pts;
+  size_t smem = lk_smem_bytes(win, d.cn);
+  dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, batch);
+  if (d.cn == 1) {
+    XB_CUDA(cudaFuncSetAttribute(lk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lk_kernel<1><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, d, prev_pts, next_pts, status, err, npts_dev, prm);
+  } else {
+    XB_CUDA(cudaFuncSetAttribute(lk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lk_kernel<3><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, d, prev_pts, next_pts, status, err, npts_dev, prm);
+  }
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace xb
