@@ -91,7 +91,7 @@ int xivo_build_pyramid(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, in
   XB_REQUIRE(pyr.ok(), "cudaMalloc failed");
   cudaStream_t st = ctx->stream;
   XB_CUDA(cudaMemcpyAsync(pyr.p, img, (size_t)rows * cols * cn, cudaMemcpyHostToDevice, st));
-  int rc = launch_build_pyramid(st, pyr.p, d.total, d, 1);
+  int rc = launch_build_pyramid(st, pyr.p, d.total, nullptr, d, 1);
   if (rc) return rc;
   g_launches += d.n_levels - 1;
   XB_CUDA(cudaMemcpyAsync(out, pyr.p, d.total, cudaMemcpyDeviceToHost, st));
@@ -110,7 +110,7 @@ int xivo_fast_detect(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int 
   DevBuf<int> dcnt(1);
   XB_REQUIRE(dimg.ok() && dkp.ok() && dcnt.ok(), "cudaMalloc failed");
   XB_CUDA(cudaMemcpyAsync(dimg.p, img, (size_t)rows * cols * cn, cudaMemcpyHostToDevice, st));
-  int rc = launch_fast_detect(st, dimg.p, 0, rows, cols, cn, threshold, nonmax, dkp.p, cap, dcnt.p, 1);
+  int rc = launch_fast_detect(st, dimg.p, 0, nullptr, rows, cols, cn, threshold, nonmax, dkp.p, cap, dcnt.p, 1);
   if (rc) return rc;
   g_launches += 1;
   int cnt = 0;
@@ -148,9 +148,9 @@ int xivo_lk_track(xivo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int r
   XB_CUDA(cudaMemcpyAsync(dp0.p, prev_pts, sizeof(float) * 2 * npts, cudaMemcpyHostToDevice, st));
   XB_CUDA(cudaMemcpyAsync(dp1.p, next_pts, sizeof(float) * 2 * npts, cudaMemcpyHostToDevice, st));
   XB_CUDA(cudaMemcpyAsync(dn.p, &npts, sizeof(int), cudaMemcpyHostToDevice, st));
-  int rc = launch_build_pyramid(st, pyr.p, d.total, d, 2);  // prev and next as a batch of two
+  int rc = launch_build_pyramid(st, pyr.p, d.total, nullptr, d, 2);  // prev and next as a batch of two
   if (rc) return rc;
-  rc = launch_lk_track(st, pyr.p, pyr.p + d.total, 0, d, dp0.p, dp1.p, dst.p, derr.p, dn.p, npts, 1, win, max_iter, eps,
+  rc = launch_lk_track(st, pyr.p, pyr.p + d.total, 0, nullptr, nullptr, d, dp0.p, dp1.p, dst.p, derr.p, dn.p, npts, 1, win, max_iter, eps,
                        use_initial_flow, min_eig_threshold);
   if (rc) return rc;
   g_launches += d.n_levels;

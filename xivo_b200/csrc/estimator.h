@@ -1,0 +1,312 @@
+// Host state machine of the estimator: the reference's Estimator / Tracker / Graph /
+// MemoryManager control flow restated around the CUDA kernels.  One `Estimator` per
+// independent sequence; a `Batch` advances B of them in lock-step so that every kernel launch
+// and every host<->device synchronisation is shared by all sequences.
+//
+// Reference files followed (relative to /root/reference): src/estimator.cpp, src/manager.cpp,
+// src/update.cpp, src/tracker.cpp, src/graph.cpp, src/graphbase.cpp, src/mm.cpp, src/group.h,
+// src/feature.cpp, src/options.cpp, src/princedormand.cpp, src/rk4.cpp, src/core.h.
+//
+// Determinism note (DESIGN.md "documented deviations"): wherever the reference's result depends
+// on std::unordered_map iteration order, heap addresses or an unstable std::sort, this
+// implementation (and the oracle) use: ascending id for graph iteration, pool-slot order for
+// MakePtrVectorUnique, std::stable_sort for candidate ranking.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <list>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "hostmath.h"
+#include "json.h"
+#include "kernels.h"
+
+namespace xb {
+
+enum class TrackStatus : int { CREATED = 0, TRACKED = 1, DROPPED = 2 };
+enum class FeatureStatus : int { CREATED = 0, INITIALIZING = 1, READY = 2, INSTATE = 3, REJECTED_BY_FILTER = 4, REJECTED_BY_TRACKER = 5, NULLREFED = 6, GAUGE = 7 };
+enum class GroupStatus : int { CREATED = 0, INSTATE = 1, FLOATING = 2, GAUGE = 3 };
+
+struct Group {
+  int id = -1, sind = -1, lifetime = 0, slot = -1;
+  GroupStatus status = GroupStatus::CREATED;
+  M3 Rsb = m3_eye();
+  V3 Tsb{{0, 0, 0}};
+  bool instate() const { return status == GroupStatus::INSTATE || status == GroupStatus::GAUGE; }
+  SE3h gsb() const { return SE3h{Rsb, Tsb}; }
+};
+
+struct Feature {
+  int id = -1, sind = -1, lifetime = 0, slot = -1, init_counter = 0;
+  FeatureStatus status = FeatureStatus::CREATED;
+  TrackStatus tstatus = TrackStatus::CREATED;
+  Group* ref = nullptr;
+  double x[3] = {0, 0, 2.0};
+  double P[9] = {0};
+  double pred[2] = {-1, -1};
+  double outlier_counter = 0;
+  bool tri_ok = false;
+  float response = 0.f;
+  std::vector<std::array<double, 2>> track;  // Track (vector of pixel observations)
+  V3 Xs{{0, 0, 0}};
+  bool instate() const { return status == FeatureStatus::INSTATE || status == FeatureStatus::GAUGE; }
+  const std::array<double, 2>& xp() const { return track.back(); }
+  double z() const { return std::exp(x[2]); }
+  double score() const { return -P[8]; }
+};
+
+// CircBufWithHash of src/mm.cpp:35-121 (USE_MAPPER off).
+template <typename T>
+class Pool {
+ public:
+  void init(int n) {
+    items_.clear();
+    items_.reserve(n);
+    for (int i = 0; i < n; ++i) {
+      items_.emplace_back(new T());
+      items_.back()->slot = i;
+    }
+    initialized_.assign(n, false);
+    active_.assign(n, false);
+    n_init_ = 0;
+    search_ = 0;
+  }
+  T* get() {  // returns nullptr when full (reference: LOG(FATAL))
+    const int n = (int)items_.size();
+    if (n_init_ < n) {
+      for (;;) {
+        if (!initialized_[search_]) {
+          initialized_[search_] = active_[search_] = true;
+          ++n_init_;
+          T* r = items_[search_].get();
+          search_ = (search_ + 1) % n;
+          return r;
+        }
+        search_ = (search_ + 1) % n;
+      }
+    }
+    const int start = search_;
+    do {
+      if (!active_[search_]) {
+        active_[search_] = true;
+        T* r = items_[search_].get();
+        search_ = (search_ + 1) % n;
+        return r;
+      }
+      search_ = (search_ + 1) % n;
+    } while (search_ != start);
+    return nullptr;
+  }
+  void deactivate(T* t) { active_[t->slot] = false; }
+  void destroy(T* t) {
+    if (initialized_[t->slot]) --n_init_;
+    active_[t->slot] = false;
+    initialized_[t->slot] = false;
+  }
+
+ private:
+  std::vector<std::unique_ptr<T>> items_;
+  std::vector<char> initialized_, active_;
+  int n_init_ = 0, search_ = 0;
+};
+
+// Visibility graph (src/graph.cpp, src/graphbase.cpp) with ordered containers.
+struct Graph {
+  std::map<int, Feature*> features;
+  std::map<int, Group*> groups;
+  std::map<int, std::map<int, std::array<double, 2>>> feature_adj;  // fid -> gid -> pixel
+  std::map<int, std::set<int>> group_adj;                            // gid -> fids
+  std::map<int, std::set<int>> gauge_features;                       // gid -> fids
+  void add_feature(Feature* f);
+  void add_group(Group* g);
+  void remove_feature(Feature* f);
+  void remove_group(Group* g);
+  void add_group_to_feature(Group* g, Feature* f);
+  void add_feature_to_group(Feature* f, Group* g);
+  bool has_feature(int fid) const { return features.count(fid) != 0; }
+  template <typename Pred>
+  std::vector<Feature*> features_if(Pred p) const {
+    std::vector<Feature*> out;
+    for (auto& kv : features)
+      if (p(kv.second)) out.push_back(kv.second);
+    return out;
+  }
+  template <typename Pred>
+  std::vector<Group*> groups_if(Pred p) const {
+    std::vector<Group*> out;
+    for (auto& kv : groups)
+      if (p(kv.second)) out.push_back(kv.second);
+    return out;
+  }
+  Group* find_new_owner(Feature* f) const;
+};
+
+struct TrackerCfg {
+  int mask_size = 15, margin = 16, num_features_min = 120, num_features_max = 150, max_pixel_displacement = 64;
+  int win_size = 15, max_level = 4, max_iter = 15;
+  double eps = 0.01;
+  int fast_threshold = 5;
+  bool fast_nonmax = true, normalize = false;
+};
+
+struct EstimatorCfg {
+  bool simulation = false;
+  std::string integration_method = "unspecified";
+  bool clamp_signals = false;
+  double max_accel[3] = {0, 0, 0}, max_gyro[3] = {0, 0, 0};
+  double sub_Rtri = 3.5 * 3.5, sub_mh = 5.991;
+  int sub_ready_steps = 5;
+  bool triangulate_pre_subfilter = false;
+  double tri_zmin = 0.05, tri_zmax = 5.0;
+  double adapt_weight = 0.99;
+  int adapt_min_lifetime = 5;
+  int remove_outlier_counter = 10, group_degrees_fixed = 4, max_group_lifetime = 1;
+  M3 Ca = m3_eye(), Cg = m3_eye();
+  V3 g{{0, 0, -9.8}};
+  double Qmodel[529] = {0}, Qimu[144] = {0};
+  double R = 1, Roos = 1;
+  double init_z = 1, init_std_x = 1, init_std_y = 1, init_std_z = 1, min_z = 0.05, max_z = 5;
+  double init_std_x_badtri = 1, init_std_y_badtri = 1, init_std_z_badtri = 1;
+  bool use_MH_gating = true;
+  int min_inliers = 5;
+  double MH_thresh = 5.991, MH_mult = 1.1;
+  double owner_change_cov_factor = 1.5;
+  int strict_criteria_timesteps = 5, num_gauge_xy_features = 3;
+  double collinear_thresh = 1e-3, max_subfilter_outlier = 0.01;
+  int gravity_init_counter = 20;
+  double pd_stepsize = 0.002, rk4_stepsize = 0.002;
+  int max_features_mem = 256, max_groups_mem = 128;
+  int message_buffer_size = 10;
+};
+
+struct MotionX {
+  M3 Rsb = m3_eye(), Rbc = m3_eye(), Rsg = m3_eye();
+  V3 Tsb{{0, 0, 0}}, Vsb{{0, 0, 0}}, bg{{0, 0, 0}}, ba{{0, 0, 0}}, Tbc{{0, 0, 0}};
+  int counter = 0;
+};
+
+struct Msg {
+  uint64_t ts = 0;
+  int type = 0;  // 0 inertial, 1 visual image, 2 visual tracker-only, 3 point cloud, 4 point cloud tracker-only
+  double gyro[3] = {0, 0, 0}, accel[3] = {0, 0, 0};
+  int img_slot = -1;
+  std::vector<int> ids;
+  std::vector<double> xp_depth;
+  uint64_t seqno = 0;
+};
+
+class Batch;
+
+class Estimator {
+ public:
+  Estimator(const Json& cfg, EkfLayout lay, bool tracker_only);
+  // ---- message heap (src/estimator.cpp:923-1046)
+  void push(Msg&& m);
+  bool pop_ready(Msg* out);
+  // ---- inertial path (src/estimator.cpp:475-592)
+  void inertial_internal(uint64_t ts, const double* gyro, const double* accel);
+  // ---- visual path, split at the device phases
+  bool visual_begin(uint64_t ts, int type);  // false -> message dropped / vision not initialised
+  void predict_features();
+  void tracker_update_pointcloud(const std::vector<int>& ids, const std::vector<double>& xp_depth);
+  void update_step_pre();                                                // lifetimes, ProcessTracks pass 1
+  void update_step_after_subfilter(const SubfilterOut* out);            // ProcessTracks pass 2, SelectAndAddNewFeatures
+  void update_step_after_gate(const double* mh);                        // OutlierRejection .. in_current_ekf_update_
+  void update_step_after_update(const double* err, const double* Pmm, const double* diagP, bool had_update);
+  void tracker_only_finish();
+
+  // helpers used by Batch
+  EkfLayout lay;
+  EstimatorCfg c;
+  TrackerCfg tc;
+  CameraParams cam;
+  bool tracker_only = false;
+  MotionX X;
+  double Pmm[529];  // host mirror of the motion block of P
+  double Phi[529];  // pending strip transition (product of per-substep F)
+  bool prop_pending = false;
+  std::vector<EditOp> edits;  // pending covariance edits, in order
+  std::vector<double> diagP;  // last downloaded diagonal of P
+  std::vector<char> gsel, fsel;
+  Graph graph;
+  Pool<Feature> fpool;
+  Pool<Group> gpool;
+  std::list<Feature*> tracks;  // Tracker::features_
+  std::vector<Feature*> instate_features, new_features, inliers, in_update, subfilter_list;
+  std::vector<Group*> instate_groups, needs_new_gauge;
+  std::set<int> affected_groups;
+  std::vector<int> just_dropped_ids;
+  std::map<int, double> ids_to_depths;
+  bool sim_initialize_depths = false;
+  int gauge_group = -1;
+  int feature_counter = 10000, group_counter = 0;
+  // tracker bookkeeping (src/tracker.h)
+  bool tracker_initialized = false;
+  std::vector<uint8_t> mask;
+  int mask_half = -1;  // MaskOut's function-local static (tracker.cpp:763)
+  int rows = 0, cols = 0;
+  int num_failed_to_track = 0, num_new_detections = 0, num_mh_rejected = 0;
+  // time / imu (src/estimator.cpp)
+  bool gravity_initialized = false, vision_initialized = false, meas_update_initialized = false;
+  int gravity_init_counter = 0, imu_counter = 0, vision_counter = 0;
+  std::vector<V3> gravity_init_buf;
+  uint64_t last_imu_time = 0, curr_imu_time = 0, last_vision_time = 0, curr_vision_time = 0, last_time = 0, curr_time = 0;
+  V3 last_accel{{0, 0, 0}}, curr_accel{{0, 0, 0}}, last_gyro{{0, 0, 0}}, curr_gyro{{0, 0, 0}}, slope_accel{{0, 0, 0}}, slope_gyro{{0, 0, 0}};
+  int error = 0;  // sticky error code (reference: throw / LOG(FATAL))
+  std::string error_msg;
+
+  SE3h gsb() const { return SE3h{X.Rsb, X.Tsb}; }
+  SE3h gbc() const { return SE3h{X.Rbc, X.Tbc}; }
+  Feature* create_feature(double x, double y);
+  void destroy_feature(Feature* f) { fpool.destroy(f); }
+  void deactivate_feature(Feature* f) { fpool.deactivate(f); }
+  // mask helpers (tracker.cpp:760-774)
+  void reset_mask();
+  void mask_out(double x, double y);
+  bool mask_valid(double x, double y) const;
+
+ private:
+  std::vector<Msg> buf_;
+  bool buf_initialized_ = false;
+  uint64_t seqno_ = 0;
+  bool good_timestamp(uint64_t now) const;
+  void update_system_clock(uint64_t now);
+  bool initialize_gravity();
+  void propagate(bool visual_meas);
+  void compose_motion(MotionX& Xs, const V3& V, const V3& gyro, const V3& accel, double dt) const;
+  void motion_jacobian(const MotionX& Xs, const V3& gyro, const V3& accel, double* F, double* G) const;
+  void integrator_step(bool pd, const V3& gyro0, const V3& accel0, double dt);
+  void integrate(const V3& gyro0, const V3& accel0, double dt);
+  void state_plus(const double* dX);
+  // state slots
+  void add_group_to_state(Group* g);
+  void add_feature_to_state(Feature* f);
+  void remove_group_from_state(Group* g);
+  void remove_feature_from_state(Feature* f);
+  void fix_feature_xy(Feature* f);
+  // manager.cpp
+  void select_and_add_new_features();
+  void add_features_within_groups();
+  void zero_gauge_xy_add_features();
+  void add_group_of_features(int free_group_slots);
+  void discard_affected_groups();
+  void find_new_gauge_features();
+  std::vector<Feature*> graph_find_new_gauge_features(Group* g);
+  void destroy_features(const std::vector<Feature*>& v);
+  void discard_features(const std::vector<Feature*>& v);
+  void discard_group(Group* g);
+  void adapt_initial_depth();
+  void enforce_max_group_lifetime();
+  void switch_ref_group();
+  bool candidate(const Feature* f, bool strict) const;
+  V3 feature_Xc(const Feature* f, M3* J = nullptr) const;
+  V3 feature_Xs(Feature* f, M3* J = nullptr) const;
+  bool change_owner(Feature* f, Group* nref);
+  void feature_initialize(Feature* f, double z0, double sx, double sy, double sz);
+};
+
+}  // namespace xb

@@ -7,12 +7,14 @@
 namespace xb {
 
 // ---------------- tracker (tracker_kernels.cu) ----------------
-int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const PyrDesc& d, int batch);
-int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, int rows, int cols, int cn,
-                       int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch);
+// seq_off (device, optional): per-sequence byte offset of the pyramid / image; ~0ull = skip that sequence.
+int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off,
+                         const PyrDesc& d, int batch);
+int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off,
+                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch);
 size_t lk_smem_bytes(int win, int cn);
 int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, unsigned long long pyr_stride,
-                    const PyrDesc& d, const float* prev_pts, float* next_pts, uint8_t* status, float* err,
+                    const unsigned long long* prev_off, const unsigned long long* next_off, const PyrDesc& d, const float* prev_pts, float* next_pts, uint8_t* status, float* err,
                     const int* npts_dev, int max_pts, int batch, int win, int max_iter, double eps, int use_initial_flow,
                     double min_eig);
 

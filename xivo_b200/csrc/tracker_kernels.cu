@@ -19,11 +19,14 @@ constexpr int PD_TX = 32, PD_TY = 8;
 
 template <int CN>
 __global__ void __launch_bounds__(PD_TX* PD_TY) pyrdown_kernel(uint8_t* __restrict__ pyr, unsigned long long pyr_stride,
-                                                                PyrDesc d, int lvl_src) {
+                                                                const unsigned long long* __restrict__ seq_off, PyrDesc d,
+                                                                int lvl_src) {
   const int srows = d.rows[lvl_src], scols = d.cols[lvl_src];
   const int drows = d.rows[lvl_src + 1], dcols = d.cols[lvl_src + 1];
-  const uint8_t* __restrict__ src = pyr + (size_t)blockIdx.z * pyr_stride + d.off[lvl_src];
-  uint8_t* __restrict__ dst = pyr + (size_t)blockIdx.z * pyr_stride + d.off[lvl_src + 1];
+  const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * pyr_stride;
+  if (soff == ~0ull) return;  // inactive sequence
+  const uint8_t* __restrict__ src = pyr + soff + d.off[lvl_src];
+  uint8_t* __restrict__ dst = pyr + soff + d.off[lvl_src + 1];
   constexpr int RW = 2 * PD_TX + 3, RH = 2 * PD_TY + 3;
   __shared__ uint8_t tile[RH][RW * CN + 1];
   __shared__ unsigned short hsum[RH][PD_TX * CN];
@@ -58,12 +61,13 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) pyrdown_kernel(uint8_t* __restri
   }
 }
 
-int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const PyrDesc& d, int batch) {
+int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off,
+                         const PyrDesc& d, int batch) {
   for (int l = 0; l + 1 < d.n_levels; ++l) {
     dim3 grid((d.cols[l + 1] + PD_TX - 1) / PD_TX, (d.rows[l + 1] + PD_TY - 1) / PD_TY, batch);
     dim3 block(PD_TX, PD_TY);
-    if (d.cn == 1) pyrdown_kernel<1><<<grid, block, 0, st>>>(pyr, pyr_stride, d, l);
-    else pyrdown_kernel<3><<<grid, block, 0, st>>>(pyr, pyr_stride, d, l);
+    if (d.cn == 1) pyrdown_kernel<1><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l);
+    else pyrdown_kernel<3><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l);
   }
   XB_CUDA(cudaGetLastError());
   return 0;
@@ -82,34 +86,39 @@ constexpr int FT_RW = FT_TX + 8, FT_RH = FT_TY + 8;  // pixel region
 constexpr int FT_SW = FT_TX + 2, FT_SH = FT_TY + 2;  // score region
 
 __device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_RW + 4], int rx, int ry, int thr) {
-  // t indexed [row][col] in region coords; (rx, ry) is the centre.
+  // t indexed [row][col] in region coords; (rx, ry) is the centre.  Works on the raw ring values
+  // p[k] (no signed differences): nvcc 12.9 / sm_100a was observed on B200 to fuse
+  // max(best, max(mn, -mx)) into a 3-input VIMNMX and drop the negation (the kernel returned
+  // max_k(v - p_k) - 1; see profiles/r01_notes.md), so the only arithmetic here is min/max of plain
+  // operands plus two final subtractions.
   const int v = t[ry][rx];
-  int d[16];
-  d[0] = v - t[ry + 3][rx];
-  d[4] = v - t[ry][rx + 3];
-  d[8] = v - t[ry - 3][rx];
-  d[12] = v - t[ry][rx - 3];
+  const int lo = v - thr, hi = v + thr;
+  int p[16];
+  p[0] = t[ry + 3][rx];
+  p[4] = t[ry][rx + 3];
+  p[8] = t[ry - 3][rx];
+  p[12] = t[ry][rx - 3];
   // any 9-arc of the 16-ring contains >= 2 of the 4 compass points
-  int nb = (d[0] < -thr) + (d[4] < -thr) + (d[8] < -thr) + (d[12] < -thr);
-  int nd = (d[0] > thr) + (d[4] > thr) + (d[8] > thr) + (d[12] > thr);
+  const int nb = (p[0] > hi) + (p[4] > hi) + (p[8] > hi) + (p[12] > hi);
+  const int nd = (p[0] < lo) + (p[4] < lo) + (p[8] < lo) + (p[12] < lo);
   if (nb < 2 && nd < 2) return 0;
-  d[1] = v - t[ry + 3][rx + 1];
-  d[2] = v - t[ry + 2][rx + 2];
-  d[3] = v - t[ry + 1][rx + 3];
-  d[5] = v - t[ry - 1][rx + 3];
-  d[6] = v - t[ry - 2][rx + 2];
-  d[7] = v - t[ry - 3][rx + 1];
-  d[9] = v - t[ry - 3][rx - 1];
-  d[10] = v - t[ry - 2][rx - 2];
-  d[11] = v - t[ry - 1][rx - 3];
-  d[13] = v - t[ry + 1][rx - 3];
-  d[14] = v - t[ry + 2][rx - 2];
-  d[15] = v - t[ry + 3][rx - 1];
+  p[1] = t[ry + 3][rx + 1];
+  p[2] = t[ry + 2][rx + 2];
+  p[3] = t[ry + 1][rx + 3];
+  p[5] = t[ry - 1][rx + 3];
+  p[6] = t[ry - 2][rx + 2];
+  p[7] = t[ry - 3][rx + 1];
+  p[9] = t[ry - 3][rx - 1];
+  p[10] = t[ry - 2][rx - 2];
+  p[11] = t[ry - 1][rx - 3];
+  p[13] = t[ry + 1][rx - 3];
+  p[14] = t[ry + 2][rx - 2];
+  p[15] = t[ry + 3][rx - 1];
   unsigned mb = 0, md = 0;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    mb |= (unsigned)(d[k] < -thr) << k;
-    md |= (unsigned)(d[k] > thr) << k;
+    mb |= (unsigned)(p[k] > hi) << k;
+    md |= (unsigned)(p[k] < lo) << k;
   }
   mb |= mb << 16;
   md |= md << 16;
@@ -120,80 +129,90 @@ __device__ __forceinline__ int fast_score(const uint8_t (*t)[FT_RW + 4], int rx,
     ad &= md >> k;
   }
   if (((ab | ad) & 0xffffu) == 0) return 0;
-  // cornerScore<16>: max over the 16 arcs of min(d) / min(-d), minus 1
-  int best = -1000;
+  // cornerScore<16>: largest t such that some 9-arc is entirely darker than v - t or entirely
+  // brighter than v + t:  best = max( v - min_arcs(max p) , max_arcs(min p) - v ), score = best - 1.
+  int arc_max_min = 255, arc_min_max = 0;
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
-    int mn = d[s], mx = d[s];
+    int mn = p[s], mx = p[s];
 #pragma unroll
     for (int k = 1; k < 9; ++k) {
-      int e = d[(s + k) & 15];
-      mn = min(mn, e);
-      mx = max(mx, e);
+      mn = min(mn, p[(s + k) & 15]);
+      mx = max(mx, p[(s + k) & 15]);
     }
-    best = max(best, max(mn, -mx));
+    arc_max_min = min(arc_max_min, mx);
+    arc_min_max = max(arc_min_max, mn);
   }
-  return best - 1;  // corner  <=>  best > thr
+  const int dark = v - arc_max_min, bright = arc_min_max - v;
+  return (dark > bright ? dark : bright) - 1;  // corner  <=>  best > thr
 }
 
 template <int CN>
 __global__ void __launch_bounds__(FT_THREADS) fast_kernel(const uint8_t* __restrict__ img, unsigned long long img_stride,
-                                                          int rows, int cols, int thr, int nonmax,
-                                                          unsigned* __restrict__ kp_out, int max_kp,
+                                                          const unsigned long long* __restrict__ seq_off, int rows, int cols,
+                                                          int thr, int nonmax, unsigned* __restrict__ kp_out, int max_kp,
                                                           int* __restrict__ kp_count) {
   __shared__ uint8_t tile[FT_RH][FT_RW + 4];
   __shared__ short score[FT_SH][FT_SW + 2];
-  const uint8_t* __restrict__ src = img + (size_t)blockIdx.z * img_stride;
+  const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * img_stride;
+  if (soff == ~0ull) return;  // inactive sequence
+  const uint8_t* __restrict__ src = img + soff;
   const int ox = blockIdx.x * FT_TX, oy = blockIdx.y * FT_TY;
-  const int tid = threadIdx.x;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 thread layout, no integer divisions
   // region origin in image coordinates
   const int gx0 = ox - 4, gy0 = oy - 4;
-  for (int i = tid; i < FT_RH * FT_RW; i += FT_THREADS) {
-    int ry = i / FT_RW, rx = i - ry * FT_RW;
-    int gx = gx0 + rx, gy = gy0 + ry;
-    int val = 0;
-    if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-      const uint8_t* p = src + ((size_t)gy * cols + gx) * CN;
-      if (CN == 1) val = p[0];
-      else val = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15;
+  for (int ry = ty; ry < FT_RH; ry += 8) {
+    const int gy = gy0 + ry;
+    for (int rx = tx; rx < FT_RW; rx += 32) {
+      const int gx = gx0 + rx;
+      int val = 0;
+      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+        const uint8_t* p = src + ((size_t)gy * cols + gx) * CN;
+        if (CN == 1) val = p[0];
+        else val = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15;
+      }
+      tile[ry][rx] = (uint8_t)val;
     }
-    tile[ry][rx] = (uint8_t)val;
   }
   __syncthreads();
-  for (int i = tid; i < FT_SH * FT_SW; i += FT_THREADS) {
-    int sy = i / FT_SW, sx = i - sy * FT_SW;
-    int gx = ox - 1 + sx, gy = oy - 1 + sy;
-    int s = 0;
-    if (gx >= 3 && gx < cols - 3 && gy >= 3 && gy < rows - 3) s = fast_score(tile, sx + 3, sy + 3, thr);
-    score[sy][sx] = (short)s;
+  for (int sy = ty; sy < FT_SH; sy += 8) {
+    const int gy = oy - 1 + sy;
+    for (int sx = tx; sx < FT_SW; sx += 32) {
+      const int gx = ox - 1 + sx;
+      int s = 0;
+      if (gx >= 3 && gx < cols - 3 && gy >= 3 && gy < rows - 3) s = fast_score(tile, sx + 3, sy + 3, thr);
+      score[sy][sx] = (short)s;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < FT_TY * FT_TX; i += FT_THREADS) {
-    int ty = i / FT_TX, tx = i - ty * FT_TX;
-    int gx = ox + tx, gy = oy + ty;
-    if (gx >= cols || gy >= rows) continue;
-    int s = score[ty + 1][tx + 1];
-    if (s <= 0) continue;
-    bool keep = true;
-    if (nonmax) {
-      keep = s > score[ty][tx] && s > score[ty][tx + 1] && s > score[ty][tx + 2] && s > score[ty + 1][tx] &&
-             s > score[ty + 1][tx + 2] && s > score[ty + 2][tx] && s > score[ty + 2][tx + 1] && s > score[ty + 2][tx + 2];
-    }
-    if (keep) {
-      int idx = atomicAdd(&kp_count[blockIdx.z], 1);
-      if (idx < max_kp) kp_out[(size_t)blockIdx.z * max_kp + idx] = ((unsigned)gy << 20) | ((unsigned)gx << 8) | (unsigned)s;
+  for (int py = ty; py < FT_TY; py += 8) {
+    const int gy = oy + py;
+    for (int px = tx; px < FT_TX; px += 32) {
+      const int gx = ox + px;
+      if (gx >= cols || gy >= rows) continue;
+      const int s = score[py + 1][px + 1];
+      if (s <= 0) continue;
+      bool keep = true;
+      if (nonmax) {
+        keep = s > score[py][px] && s > score[py][px + 1] && s > score[py][px + 2] && s > score[py + 1][px] &&
+               s > score[py + 1][px + 2] && s > score[py + 2][px] && s > score[py + 2][px + 1] && s > score[py + 2][px + 2];
+      }
+      if (keep) {
+        const int idx = atomicAdd(&kp_count[blockIdx.z], 1);
+        if (idx < max_kp) kp_out[(size_t)blockIdx.z * max_kp + idx] = ((unsigned)gy << 20) | ((unsigned)gx << 8) | (unsigned)s;
+      }
     }
   }
 }
 
-int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, int rows, int cols, int cn,
-                       int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch) {
+int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off,
+                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch) {
   XB_REQUIRE(rows < 4096 && cols < 4096, "FAST: image dimension must be < 4096 (12-bit packed coordinates)");
   XB_REQUIRE(thr >= 0 && thr < 255, "FAST: threshold out of range");
   XB_CUDA(cudaMemsetAsync(kp_count, 0, sizeof(int) * batch, st));
   dim3 grid((cols + FT_TX - 1) / FT_TX, (rows + FT_TY - 1) / FT_TY, batch);
-  if (cn == 1) fast_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
-  else fast_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+  if (cn == 1) fast_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+  else fast_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -225,7 +244,9 @@ struct LKParams {
 
 template <int CN>
 __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
-                                                          unsigned long long pyr_stride, PyrDesc d,
+                                                          unsigned long long pyr_stride,
+                                                          const unsigned long long* __restrict__ prev_off,
+                                                          const unsigned long long* __restrict__ next_off, PyrDesc d,
                                                           const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                                                           uint8_t* __restrict__ status, float* __restrict__ err,
                                                           const int* __restrict__ npts, LKParams prm) {
@@ -247,8 +268,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(const uint8_t* __rest
   short* Iw = dtile + dt_elems;
   short* dIw = Iw + iw_elems;
 
-  const uint8_t* __restrict__ ppyr = prev_pyr + (size_t)seq * pyr_stride;
-  const uint8_t* __restrict__ npyr = next_pyr + (size_t)seq * pyr_stride;
+  const uint8_t* __restrict__ ppyr = prev_pyr + (prev_off ? prev_off[seq] : (unsigned long long)seq * pyr_stride);
+  const uint8_t* __restrict__ npyr = next_pyr + (next_off ? next_off[seq] : (unsigned long long)seq * pyr_stride);
   const size_t pi = (size_t)seq * prm.max_pts + p;
   const float ppx = prev_pts[2 * pi], ppy = prev_pts[2 * pi + 1];
   float outx = next_pts[2 * pi], outy = next_pts[2 * pi + 1];
@@ -461,7 +482,7 @@ size_t lk_smem_bytes(int win, int cn) {
 }
 
 int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, unsigned long long pyr_stride,
-                    const PyrDesc& d, const float* prev_pts, float* next_pts, uint8_t* status, float* err,
+                    const unsigned long long* prev_off, const unsigned long long* next_off, const PyrDesc& d, const float* prev_pts, float* next_pts, uint8_t* status, float* err,
                     const int* npts_dev, int max_pts, int batch, int win, int max_iter, double eps, int use_initial_flow,
                     double min_eig) {
   XB_REQUIRE(win >= 3 && win <= LK_MAX_WIN && (win & 1), "LK: win_size must be odd and in [3, 21]");
@@ -479,10 +500,10 @@ int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* nex
   dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, batch);
   if (d.cn == 1) {
     XB_CUDA(cudaFuncSetAttribute(lk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lk_kernel<1><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, d, prev_pts, next_pts, status, err, npts_dev, prm);
+    lk_kernel<1><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
   } else {
     XB_CUDA(cudaFuncSetAttribute(lk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lk_kernel<3><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, d, prev_pts, next_pts, status, err, npts_dev, prm);
+    lk_kernel<3><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
   }
   XB_CUDA(cudaGetLastError());
   return 0;
