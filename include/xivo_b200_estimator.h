@@ -1,0 +1,89 @@
+/*
+ * xivo_b200_estimator.h — estimator-level C ABI (handle based).
+ *
+ * Mirrors the reference's public class API for the hot path — Estimator::{InertialMeas,
+ * VisualMeas, VisualMeasTrackerOnly, VisualMeasPointCloud, VisualMeasPointCloudTrackerOnly} and the
+ * read-back accessors (src/estimator.h:131-231), which pybind11/pyxivo.cpp:332-398 exposes to
+ * Python — with two deliberate differences forced by the reference's design:
+ *   - de-singletonised: the reference allows one estimator per process (static singletons,
+ *     src/factory.cpp:18-22); here one handle holds `n_seq` independent estimators that advance
+ *     in lock-step, so that every CUDA launch and host<->device sync is shared by all sequences
+ *     (the filter is sequential per stream; batching sequences is the only parallel axis);
+ *   - kMaxGroup / kMaxFeature (compile-time -DEKF_MAX_GROUPS / -DEKF_MAX_FEATURES in the
+ *     reference, src/core.h:92-105) are creation-time arguments.
+ * cfg_json is the text of a reference config (cfg/*.json, JSON with comments).  "camera_cfg" and
+ * "tracker_cfg" may be embedded objects or paths, as in src/factory.cpp:31-45.
+ * All functions return 0 or a negative XIVO_ERR_* code (include/xivo_b200.h); nothing throws.
+ */
+#ifndef XIVO_B200_ESTIMATOR_H_
+#define XIVO_B200_ESTIMATOR_H_
+
+#include "xivo_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xivo_batch xivo_batch;
+
+/* CreateSystem / CreateSystemTrackerOnly (src/factory.cpp:17-122) for n_seq sequences. */
+int xivo_batch_create(xivo_ctx* ctx, const char* cfg_json, int n_seq, int max_groups, int max_features,
+                      int tracker_only, xivo_batch** out);
+void xivo_batch_destroy(xivo_batch* b);
+int xivo_batch_size(const xivo_batch* b);
+int xivo_batch_state_dim(const xivo_batch* b); /* kFullSize = 23 + 6 G + 3 F */
+
+/* Estimator::InertialMeas (src/estimator.cpp:1036-1046), one sample per sequence.
+ * ts_ns[n_seq], gyro[n_seq*3], accel[n_seq*3]. */
+int xivo_batch_inertial_meas(xivo_batch* b, const uint64_t* ts_ns, const double* gyro, const double* accel);
+
+/* Estimator::VisualMeas / VisualMeasTrackerOnly (src/estimator.cpp:943-979), one frame per sequence.
+ * imgs[n_seq]: rows x cols x channels uint8, tightly packed (pyxivo.cpp:97-108 requires the same).
+ * The pixels are copied to the device before the call returns control of the buffers: unlike the
+ * reference (which keeps a shallow cv::Mat header for up to 10 queued messages) the caller may
+ * reuse the memory immediately when it is pinned, and after the call returns otherwise. */
+int xivo_batch_visual_meas(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs, int rows, int cols,
+                           int channels, int tracker_only);
+
+/* Same, with the frames already resident in device memory (imgs_dev[s] are device pointers on this
+ * context's GPU); used to measure the device-resident throughput. */
+int xivo_batch_visual_meas_device(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs_dev, int rows, int cols,
+                                  int channels, int tracker_only);
+
+/* Per-kernel CUDA-event timing + host<->device byte counters (bench.py's roofline / e2e fields). */
+void xivo_profile_enable(int on);
+void xivo_profile_reset(void);
+int xivo_profile_report(char* json_out, int capacity);
+
+/* Estimator::VisualMeasPointCloud[TrackerOnly] (src/estimator.cpp:982-1032).
+ * n_pts[n_seq]; ids[s]: n_pts[s] ints; xp_depth[s]: n_pts[s] x 3 (x, y, depth) row-major. */
+int xivo_batch_visual_meas_pointcloud(xivo_batch* b, const uint64_t* ts_ns, const int* n_pts, const int* const* ids,
+                                      const double* const* xp_depth, int tracker_only);
+
+/* ---- read-back (estimator_accessors.cpp); `seq` selects the sequence ------------------------ */
+int xivo_get_gsb(xivo_batch* b, int seq, double out12[12]); /* 3x4 row-major [R|T], Estimator::gsb */
+int xivo_get_gbc(xivo_batch* b, int seq, double out12[12]);
+int xivo_get_gsc(xivo_batch* b, int seq, double out12[12]);
+int xivo_get_motion(xivo_batch* b, int seq, double Vsb[3], double bg[3], double ba[3], double Rsg[9]);
+int xivo_get_P(xivo_batch* b, int seq, double* out /* N x N */); /* Estimator::P() */
+int xivo_get_Pstate(xivo_batch* b, int seq, double out81[81]);   /* Estimator::Pstate(): top-left 9x9 */
+/* counters: {num_instate_features, num_instate_groups, gauge_group, num_mh_rejected,
+ *            num_tracker_failed, num_tracker_new_detections, vision_counter, imu_counter,
+ *            MeasurementUpdateInitialized, VisionInitialized, num_tracked, sticky_error} */
+#define XIVO_NUM_COUNTERS 12
+int xivo_get_counters(xivo_batch* b, int seq, int out[XIVO_NUM_COUNTERS]);
+int xivo_get_time_ns(xivo_batch* b, int seq, uint64_t* ts); /* Estimator::ts() */
+/* tracked_features_no_descriptor(): ids and last pixel positions of Tracker::features_. */
+int xivo_get_tracked_features(xivo_batch* b, int seq, int* ids, double* xy, int* status, int max_n, int* n);
+/* InstateFeatureIDs/Sinds/Positions(Xs)/x and reference group ids. */
+int xivo_get_instate_features(xivo_batch* b, int seq, int* ids, int* sinds, int* ref_group_ids, double* Xs3,
+                              double* x3, int max_n, int* n);
+/* InstateGroupIDs/Sinds/Poses (3x4 row-major each). */
+int xivo_get_instate_groups(xivo_batch* b, int seq, int* ids, int* sinds, double* gsb12, int max_n, int* n);
+int xivo_init_with_sim_depths(xivo_batch* b); /* Estimator::InitWithSimDepths */
+const char* xivo_batch_error(xivo_batch* b, int seq);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,823 @@
+"""oracle/estimator_oracle.py — TEST INFRASTRUCTURE ONLY.
+
+CPU (numpy fp64) restatement of the reference's per-frame pipeline: message heap, IMU propagation,
+tracker bookkeeping, UpdateStep (ProcessTracks, SelectAndAddNewFeatures, Jacobians, MH gating,
+FilterUpdate in Joseph form, AbsorbError, group/feature management).  It follows
+/root/reference/src/{estimator,manager,update,tracker,graph,graphbase,mm,feature,options}.cpp with a
+dense N x N covariance exactly like the reference (no device, no batching).  The tracker arithmetic
+comes from oracle/tracker_oracle.c (pinned on cv2).
+
+Parity status: the reference cannot be built here (OpenCV C++ absent), and it has no end-to-end
+test or golden trajectory -> trajectory parity is UNPINNED against the reference;
+this oracle is pinned only through its parts (tests/test_oracle_ekf.py, test_oracle_tracker.py).
+Where the reference's behaviour depends on hash-map iteration order, heap addresses or an unstable
+sort, this oracle uses the same documented conventions as the product: ascending ids,
+pool-slot order for pointer sorts, stable sorts, a deterministic rotation instead of the
+random_device-seeded shuffle.
+"""
+from __future__ import annotations
+
+import heapq
+import math
+
+import numpy as np
+
+from . import ekf_oracle as E
+from . import tracker_oracle as T
+
+CREATED, TRACKED, DROPPED = 0, 1, 2
+F_CREATED, F_INITIALIZING, F_READY, F_INSTATE, F_REJECTED, F_REJ_TRACKER, F_NULLREFED, F_GAUGE = range(8)
+G_CREATED, G_INSTATE, G_FLOATING, G_GAUGE = range(4)
+
+
+class Group:
+    def __init__(self, slot):
+        self.slot = slot
+        self.id = self.sind = -1
+        self.lifetime = 0
+        self.status = G_CREATED
+        self.Rsb, self.Tsb = np.eye(3), np.zeros(3)
+
+    def instate(self):
+        return self.status in (G_INSTATE, G_GAUGE)
+
+
+class Feature:
+    def __init__(self, slot):
+        self.slot = slot
+        self.reset(-1, 0, 0)
+
+    def reset(self, fid, x, y):
+        self.id, self.sind, self.lifetime, self.init_counter = fid, -1, 0, 0
+        self.status, self.tstatus, self.ref = F_CREATED, CREATED, None
+        self.x = np.array([x, y, 2.0])
+        self.P = np.zeros((3, 3))
+        self.pred = np.array([-1.0, -1.0])
+        self.outlier_counter = 0.0
+        self.track = [np.array([x, y], dtype=np.float64)]
+        self.response = 0.0
+
+    def instate(self):
+        return self.status in (F_INSTATE, F_GAUGE)
+
+    def xp(self):
+        return self.track[-1]
+
+    def z(self):
+        return math.exp(self.x[2])
+
+
+class Pool:
+    """CircBufWithHash, src/mm.cpp:35-121 (USE_MAPPER off)."""
+
+    def __init__(self, n, cls):
+        self.items = [cls(i) for i in range(n)]
+        self.init = [False] * n
+        self.act = [False] * n
+        self.n_init, self.search = 0, 0
+
+    def get(self):
+        n = len(self.items)
+        if self.n_init < n:
+            while True:
+                if not self.init[self.search]:
+                    self.init[self.search] = self.act[self.search] = True
+                    self.n_init += 1
+                    r = self.items[self.search]
+                    self.search = (self.search + 1) % n
+                    return r
+                self.search = (self.search + 1) % n
+        start = self.search
+        while True:
+            if not self.act[self.search]:
+                self.act[self.search] = True
+                r = self.items[self.search]
+                self.search = (self.search + 1) % n
+                return r
+            self.search = (self.search + 1) % n
+            if self.search == start:
+                raise RuntimeError("out of slots in the memory manager")
+
+    def deactivate(self, t):
+        self.act[t.slot] = False
+
+    def destroy(self, t):
+        if self.init[t.slot]:
+            self.n_init -= 1
+        self.act[t.slot] = self.init[t.slot] = False
+
+
+def rot_of(v):
+    v = np.asarray(v, dtype=np.float64)
+    if v.size == 3:
+        return E.so3_exp(v)
+    return E.quat_normalize_rot(v.reshape(3, 3))
+
+
+class EstimatorOracle:
+    def __init__(self, cfg: dict, G=15, F=30, tracker_only=False):
+        self.lay = E.Layout(G, F)
+        N = self.lay.N
+        self.tracker_only = tracker_only
+        c = cfg
+        self.simulation = c.get("simulation", False)
+        self.method = c.get("integration_method", "unspecified")
+        sf = c.get("subfilter", {})
+        self.sub_Rtri = sf.get("visual_meas_std", 3.5) ** 2
+        self.sub_mh = sf.get("MH_thresh", 5.991)
+        self.sub_ready = sf.get("ready_steps", 5)
+        ad = c.get("adaptive_initial_depth", {})
+        self.adapt_w, self.adapt_life = ad.get("median_weight", 0.99), ad.get("minimum_feature_lifetime", 5)
+        self.remove_outlier_counter = c.get("remove_outlier_counter", 10)
+        self.group_degrees_fixed = c.get("group_degrees_fixed", 4)
+        self.max_group_lifetime = c.get("max_group_lifetime", 1)
+        ic = c["imu_calib"]
+        self.Ca = np.array(ic["Car"], float).reshape(3, 3) @ np.diag(ic["Cas"])
+        self.Cg = np.array(ic["Cgr"], float).reshape(3, 3) @ np.diag(ic["Cgs"])
+        self.g = np.array(c["gravity"], float)
+        Xj = c["X"]
+        bg, ba = np.array(Xj["bg"], float), np.array(Xj["ba"], float)
+        if c.get("imu_tk_convention", False):
+            bg, ba = -self.Cg @ bg, -self.Ca @ ba
+        Wsg = np.array(list(Xj["Wsg"])[:2] + [0.0], float)
+        self.X = E.MotionState(rot_of(Xj["Wsb"]), np.array(Xj["Tsb"], float), np.array(Xj["Vsb"], float), bg, ba, rot_of(Xj["Wbc"]),
+                               np.array(Xj["Tbc"], float), E.so3_exp(Wsg))
+        Pj = c["P"]
+        d = np.ones(N)
+        d[0:3], d[3:6], d[6:9], d[9:12], d[12:15], d[15:18] = Pj["Wsb"], Pj["Tsb"], Pj["Vsb"], Pj["bg"], Pj["ba"], Pj["Wbc"]
+        d[18:21] = Pj["Tbc"]
+        d[21:23] = Pj["Wsg"]
+        self.P = np.diag(d * d)  # identity elsewhere (estimator.cpp:258-302)
+        self.err = np.zeros(N)
+        Qm = c["Qmodel"]
+        q = np.zeros(23)
+        q[0:3], q[15:18], q[21:23] = Qm["Wsb"], Qm["Wbc"], Qm["Wsg"]
+        self.Qmodel = np.diag(q * q)
+        Qi = c["Qimu"]
+        qi = np.concatenate([np.broadcast_to(np.array(Qi[k], float), (3,)) for k in ("gyro", "accel", "gyro_bias", "accel_bias")])
+        self.Qimu = np.diag(qi * qi)
+        self.R = c["visual_meas_std"] ** 2
+        cj = c["camera_cfg"]
+        model = {"pinhole": 0, "equidistant": 3}[cj["model"]]
+        self.cam = E.Camera(model, cj["rows"], cj["cols"], cj["fx"], cj["fy"], cj["cx"], cj["cy"], tuple(cj.get("k0123", (0, 0, 0, 0))))
+        fl = self.cam.focal_length()
+        self.init_z = c["initial_z"]
+        self.init_std = (c["initial_std_x"] / fl, c["initial_std_y"] / fl, c["initial_std_z"])
+        self.min_z, self.max_z = c["min_depth"], c["max_depth"]
+        self.use_MH = c.get("use_MH_gating", True)
+        self.min_inliers = c.get("min_inliers", 5)
+        self.MH_thresh, self.MH_mult = c.get("MH_thresh", 5.991), c.get("MH_adjust_factor", 1.1)
+        self.owner_cov_factor = c.get("filter_owner_change_cov_factor", 1.5)
+        self.strict_steps = c.get("strict_criteria_timesteps", 5)
+        self.n_gauge = c.get("num_gauge_xy_features", 3)
+        self.collinear_thresh = c.get("collinear_cross_prod_thresh", 1e-3)
+        self.max_sub_outlier = c.get("max_subfilter_outlier", 0.01)
+        self.h0 = c.get("PrinceDormand", {}).get("stepsize", 0.002) if self.method == "PrinceDormand" else c.get("RK4", {}).get("stepsize", 0.002)
+        mem = c.get("memory", {})
+        self.fpool = Pool(mem.get("max_features", 256), Feature)
+        self.gpool = Pool(mem.get("max_groups", 128), Group)
+        self.msg_buf_size = c.get("message_buffer_size", 10)
+        if self.simulation:
+            self.gravity_init_counter, self.gravity_initialized = 0, True
+        else:
+            self.gravity_init_counter, self.gravity_initialized = c.get("gravity_init_counter", 20), False
+        tj = c["tracker_cfg"]
+        self.t_mask_size, self.t_margin = tj.get("mask_size", 15), tj.get("margin", 16)
+        self.t_min, self.t_max = tj.get("num_features_min", 120), tj.get("num_features_max", 150)
+        self.t_max_disp = tj.get("max_pixel_displacement", 64)
+        klt = tj.get("KLT", {})
+        self.klt = dict(win=klt.get("win_size", 15), max_level=klt.get("max_level", 4), max_iter=klt.get("max_iter", 15), eps=klt.get("eps", 0.01))
+        self.fast_thr = tj.get("FAST", {}).get("threshold", 5)
+        self.fast_nms = tj.get("FAST", {}).get("nonmaxSuppression", True)
+        # bookkeeping
+        self.gsel, self.fsel = [False] * G, [False] * F
+        self.features, self.groups = {}, {}
+        self.feature_adj, self.group_adj, self.gauge_features = {}, {}, {}
+        self.tracks = []
+        self.needs_new_gauge = []
+        self.gauge_group = -1
+        self.feature_counter, self.group_counter = 10000, 0
+        self.ids_to_depths, self.sim_init_depths = {}, False
+        self.instate_features = []
+        self.tracker_initialized = False
+        self.mask, self.prev_img = None, None
+        self.num_mh_rejected = 0
+        self.vision_initialized = False
+        self.imu_counter = self.vision_counter = 0
+        self.gravity_buf = []
+        self.last_time = self.curr_time = 0
+        self.last_accel = self.curr_accel = self.last_gyro = self.curr_gyro = np.zeros(3)
+        self.slope_accel = self.slope_gyro = np.zeros(3)
+        self.buf, self.buf_init, self.seq = [], False, 0
+        self.meas_update_initialized = False
+
+    # ---------------------------------------------------------------- public API
+    def InertialMeas(self, ts, gyro, accel):
+        self._push((ts, 0, (np.array(gyro, float), np.array(accel, float))))
+
+    def VisualMeasPointCloud(self, ts, ids, xp_depth):
+        self._push((ts, 3, (np.array(ids), np.array(xp_depth, float).reshape(-1, 3))))
+
+    def VisualMeas(self, ts, img):
+        self._push((ts, 1, np.ascontiguousarray(img)))
+
+    def VisualMeasTrackerOnly(self, ts, img):
+        self._push((ts, 2, np.ascontiguousarray(img)))
+
+    def gsb(self):
+        return np.column_stack([self.X.Rsb, self.X.Tsb])
+
+    # ---------------------------------------------------------------- message heap (estimator.cpp:923-941)
+    def _push(self, m):
+        # std::push_heap / pop_heap with cmp(ts): execution order among equal timestamps follows the
+        # libstdc++ heap algorithms in the reference; ties are broken by arrival order here AND in the
+        # product's test streams (IMU pushed before vision on equal ts, as pyxivo_pcw.py:111 orders them).
+        item = (m[0], self.seq, m)
+        self.seq += 1
+        self.buf.append(item)
+        if not self.buf_init:
+            if len(self.buf) >= self.msg_buf_size:
+                heapq.heapify(self.buf)
+                self.buf_init = True
+        else:
+            # keep a valid heap
+            heapq.heapify(self.buf)
+        if self.buf_init and len(self.buf) > self.msg_buf_size:
+            _, _, msg = heapq.heappop(self.buf)
+            self._execute(msg)
+
+    def _execute(self, m):
+        ts, kind, p = m
+        if kind == 0:
+            self.inertial_internal(ts, p[0], p[1])
+        else:
+            self.visual_internal(ts, kind, p)
+
+    # ---------------------------------------------------------------- time / imu
+    def good_timestamp(self, now):
+        return now // 1000000 >= self.curr_time // 1000000
+
+    def inertial_internal(self, ts, gyro, accel):
+        if not self.good_timestamp(ts):
+            return
+        self.imu_counter += 1
+        if not self.gravity_initialized:
+            self.gravity_buf.append(accel)
+            if self.simulation or len(self.gravity_buf) >= self.gravity_init_counter:
+                if not self.simulation:
+                    mean = np.mean(self.gravity_buf, axis=0)
+                    ac = self.Ca @ mean - self.X.ba
+                    a, b = -self.g / np.linalg.norm(self.g), ac / np.linalg.norm(ac)
+                    axis = np.cross(a, b)
+                    s, cs = np.linalg.norm(axis), float(a @ b)
+                    W = axis * (math.atan2(s, cs) / s) if s > 1e-12 else np.zeros(3)
+                    W[2] = 0
+                    self.X.Rsg = E.so3_exp(W)
+                self.last_time = ts
+                self.curr_accel = self.last_accel = accel
+                self.curr_gyro = self.last_gyro = gyro
+                self.gravity_initialized = True
+                self.gravity_buf = []
+        elif self.vision_initialized:
+            self.last_time, self.curr_time = self.curr_time, ts
+            self.curr_accel, self.curr_gyro = accel, gyro
+            self.propagate(False)
+
+    def propagate(self, visual):
+        dt = (self.curr_time - self.last_time) * 1e-9
+        if dt == 0:
+            return
+        if not visual:
+            self.slope_accel = (self.curr_accel - self.last_accel) / dt
+            self.slope_gyro = (self.curr_gyro - self.last_gyro) / dt
+            accel0, gyro0 = self.last_accel, self.last_gyro
+            self.last_accel, self.last_gyro = self.curr_accel, self.curr_gyro
+        else:
+            accel0, gyro0 = self.last_accel, self.last_gyro
+            self.last_accel = accel0 + self.slope_accel * dt
+            self.last_gyro = gyro0 + self.slope_gyro * dt
+        Phi, Pmm = E.integrate(self.method, self.X, self.P[:23, :23].copy(), gyro0, accel0, self.slope_gyro, self.slope_accel, dt, self.Cg,
+                               self.Ca, self.g, self.Qimu, self.h0)
+        E.apply_propagation(self.P, Phi, Pmm, self.Qmodel)
+
+    # ---------------------------------------------------------------- graph
+    def g_add_feature(self, f):
+        self.features[f.id] = f
+        self.feature_adj[f.id] = {}
+
+    def g_add_group(self, g):
+        self.groups[g.id] = g
+        self.group_adj[g.id] = set()
+        self.gauge_features[g.id] = set()
+
+    def g_remove_feature(self, f):
+        del self.features[f.id]
+        for gid in self.feature_adj[f.id]:
+            self.group_adj[gid].discard(f.id)
+        del self.feature_adj[f.id]
+        if f.ref is not None:
+            self.gauge_features.setdefault(f.ref.id, set()).discard(f.id)
+
+    def g_remove_group(self, g):
+        del self.groups[g.id]
+        for fid in self.group_adj[g.id]:
+            self.feature_adj[fid].pop(g.id, None)
+        del self.group_adj[g.id]
+        self.gauge_features.pop(g.id, None)
+
+    def g_link(self, f, g):
+        self.group_adj[g.id].add(f.id)
+        self.feature_adj[f.id].setdefault(g.id, f.xp().copy())
+
+    def feats(self, pred=lambda f: True):
+        return [self.features[k] for k in sorted(self.features) if pred(self.features[k])]
+
+    def grps(self, pred=lambda g: True):
+        return [self.groups[k] for k in sorted(self.groups) if pred(self.groups[k])]
+
+    # ---------------------------------------------------------------- features
+    def create_feature(self, x, y):
+        f = self.fpool.get()
+        f.reset(self.feature_counter, x, y)
+        self.feature_counter += 1
+        return f
+
+    def gbc(self):
+        return self.X.Rbc, self.X.Tbc
+
+    def feature_Xs(self, f):
+        Xc, J = E.unproject_logz(f.x)
+        Rsc = f.ref.Rsb @ self.X.Rbc
+        Tsc = f.ref.Rsb @ self.X.Tbc + f.ref.Tsb
+        return Rsc @ Xc + Tsc, Rsc @ J
+
+    def change_owner(self, f, nref):
+        Rsc = nref.Rsb @ self.X.Rbc
+        Tsc = nref.Rsb @ self.X.Tbc + nref.Tsb
+        Xs, dXs_dx = self.feature_Xs(f)
+        Xcn = Rsc.T @ (Xs - Tsc)
+        if Xcn[2] < 0:
+            return False
+        xn, dxn = E.project_logz(Xcn)
+        J = dxn @ (Rsc.T @ dXs_dx)
+        f.x = xn
+        f.P = J @ f.P @ J.T
+        f.ref = nref
+        return True
+
+    # ---------------------------------------------------------------- state slots
+    def remove_group_from_state(self, g):
+        E.remove_group_from_state(self.lay, self.P, self.err, g.sind)
+        self.gsel[g.sind] = False
+        g.sind, g.status = -1, G_FLOATING
+
+    def remove_feature_from_state(self, f):
+        E.remove_feature_from_state(self.lay, self.P, self.err, f.sind)
+        self.fsel[f.sind] = False
+        f.sind = -1
+
+    def add_group_to_state(self, g):
+        idx = self.gsel.index(False)
+        self.gsel[idx] = True
+        g.sind, g.status = idx, G_INSTATE
+        E.add_group_to_state(self.lay, self.P, self.err, idx)
+
+    def add_feature_to_state(self, f):
+        idx = self.fsel.index(False)
+        self.fsel[idx] = True
+        f.status, f.sind = F_INSTATE, idx
+        E.add_feature_to_state(self.lay, self.P, idx, f.P)
+
+    # ---------------------------------------------------------------- visual
+    def visual_internal(self, ts, kind, payload):
+        if not self.good_timestamp(ts):
+            return
+        pc = kind in (3, 4)
+        if pc != self.simulation:
+            raise ValueError("VisualMeas / VisualMeasPointCloud called in the wrong mode")
+        self.vision_counter += 1
+        if not self.vision_initialized:
+            if self.gravity_initialized:
+                self.curr_time = ts
+                self.vision_initialized = True
+        else:
+            self.last_time, self.curr_time = self.curr_time, ts
+        tracker_only = kind in (2, 4)
+        if not tracker_only:
+            if not self.vision_initialized:
+                return
+            self.propagate(True)
+            self.predict_features()
+        if pc:
+            ids, xpd = payload
+            if kind == 3:
+                for i, fid in enumerate(ids):
+                    self.ids_to_depths.setdefault(int(fid), float(xpd[i, 2]))
+            self.tracker_update_pointcloud(ids, xpd)
+        else:
+            self.tracker_update_lk(payload)
+        if tracker_only:
+            for f in [f for f in self.tracks if f.tstatus == DROPPED]:
+                self.tracks.remove(f)
+                self.fpool.destroy(f)
+            if self.gauge_group == -1:
+                self.switch_ref_group()
+            return
+        self.update_step()
+        if self.gauge_group == -1:
+            self.switch_ref_group()
+
+    def predict_features(self):
+        gsb = (self.X.Rsb, self.X.Tsb)
+        for f in self.tracks:
+            if f.ref is None:
+                continue
+            f.pred = E.predict_pixel(self.cam, f.x, (f.ref.Rsb, f.ref.Tsb), gsb, self.gbc())
+
+    def tracker_update_pointcloud(self, ids, xpd):
+        meas = {int(i): xpd[k, :2].copy() for k, i in enumerate(ids)}
+        marked = {int(i): False for i in ids}
+        dropped = 0
+        for f in self.tracks:
+            m = meas.get(f.id)
+            if m is not None and np.linalg.norm(m - f.xp()) < self.t_max_disp:
+                f.track.append(m)
+                f.tstatus = TRACKED
+                marked[f.id] = True
+            else:
+                f.tstatus = DROPPED
+                dropped += 1
+        n_add = self.t_max - len(self.tracks) + dropped
+        for fid in ids:
+            if n_add <= 0:
+                break
+            fid = int(fid)
+            if not marked[fid]:
+                f = self.create_feature(*meas[fid])
+                f.id = fid
+                self.tracks.append(f)
+            n_add -= 1
+
+    def tracker_update_lk(self, img):
+        rows, cols = img.shape[:2]
+        if self.mask is None:
+            self.mask = T.Mask(rows, cols, self.t_margin, self.t_mask_size)
+        if not self.tracker_initialized:
+            self.mask.m[:] = 0
+            self.mask.reset()
+            self.prev_img = img
+            self.detect_lk(img, self.t_max)
+            self.tracker_initialized = True
+            return
+        self.mask.reset()
+        if not self.tracks:
+            self.tracker_initialized = False
+            return
+        p0 = np.array([f.xp() for f in self.tracks], np.float32)
+        p1 = p0.copy()
+        for i, f in enumerate(self.tracks):
+            if f.pred[0] != -1 and f.pred[1] != -1:
+                p1[i] = f.pred.astype(np.float32)
+                f.pred = np.array([-1.0, -1.0])
+        r1, st, _ = T.lk_track(self.prev_img, img, p0, p1, **self.klt)
+        valid, dropped = 0, []
+        for i, f in enumerate(self.tracks):
+            ok = bool(st[i])
+            if ok:
+                q = r1[i].astype(np.float64)
+                if self.mask.valid(q[0], q[1]) and np.linalg.norm(f.xp() - q) < self.t_max_disp:
+                    f.tstatus = TRACKED
+                    f.track.append(q)
+                    self.mask.mask_out(q[0], q[1])
+                    valid += 1
+                else:
+                    ok = False
+            if not ok:
+                dropped.append(f)
+        if valid < self.t_min:
+            self.detect_lk(img, self.t_max - valid)
+        for f in dropped:
+            f.tstatus = DROPPED
+        self.prev_img = img
+
+    def detect_lk(self, img, num_to_add):
+        xy, sc, _ = T.fast_detect(img, self.fast_thr, self.fast_nms)
+        for i in T.select_keypoints(self.mask, xy, sc, num_to_add):
+            f = self.create_feature(float(xy[i][0]), float(xy[i][1]))
+            f.response = float(sc[i])
+            self.tracks.append(f)
+
+    # ---------------------------------------------------------------- UpdateStep (manager.cpp:18-167)
+    def candidate(self, f, strict):
+        good = (f.status == F_READY or (not strict and f.status == F_INITIALIZING)) and f.outlier_counter < self.max_sub_outlier
+        return good and self.min_z < f.z() < self.max_z
+
+    @staticmethod
+    def cand_key(f):  # CandidateComparison: (status desc, score desc) with score = -P(2,2); stable
+        return (-f.status, f.P[2, 2])
+
+    def update_step(self):
+        lay = self.lay
+        affected, new_features, self.inliers, in_update = set(), [], [], []
+        for f in self.features.values():
+            f.lifetime += 1
+        for g in self.groups.values():
+            g.lifetime += 1
+        gsb = (self.X.Rsb, self.X.Tsb)
+        # ProcessTracks (manager.cpp:171-250)
+        keep = []
+        for f in self.tracks:
+            if f.tstatus == CREATED:
+                new_features.append(f)
+            elif f.instate() and f.tstatus == DROPPED:
+                self.g_remove_feature(f)
+                if f.status == F_GAUGE:
+                    self.needs_new_gauge.append(f.ref)
+                self.remove_feature_from_state(f)
+                affected.add(f.ref.id)
+                self.fpool.deactivate(f)
+            elif not f.instate() and f.tstatus == DROPPED:
+                self.g_remove_feature(f)
+                self.fpool.destroy(f)
+            elif f.instate() and f.tstatus == TRACKED:
+                keep.append(f)
+            else:
+                f.init_counter += 1
+                f.x, f.P, f.outlier_counter = E.subfilter_update(self.cam, f.x, f.P, f.xp(), gsb, self.gbc(), (f.ref.Rsb, f.ref.Tsb),
+                                                                self.sub_Rtri, self.sub_mh, f.outlier_counter)
+                f.status = F_READY if f.init_counter > self.sub_ready else F_INITIALIZING
+                if f.outlier_counter > self.remove_outlier_counter:
+                    self.g_remove_feature(f)
+                    self.fpool.destroy(f)
+                else:
+                    keep.append(f)
+        self.tracks = keep
+        self.affected = affected
+        inst = self.feats(lambda f: f.instate())
+        if len(inst) < lay.F:
+            self.select_and_add(inst)
+        inst = sorted(set(inst), key=lambda f: f.slot)  # MakePtrVectorUnique
+        # Jacobians + gating
+        Js, inns = {}, {}
+        for f in inst:
+            J, r, _ = E.feature_jacobian(lay, self.cam, self.X.Rsb, self.X.Tsb, self.X.Rbc, self.X.Tbc, f.ref.Rsb, f.ref.Tsb, f.x, f.xp(),
+                                         f.ref.sind, f.sind)
+            Js[f.id], inns[f.id] = J, r
+        if inst:
+            if self.use_MH and len(inst) > self.min_inliers:
+                dist = [E.mh_distance(Js[f.id], self.P, inns[f.id], self.R) for f in inst]
+                self.num_mh_rejected = 0
+                thresh, inl, to_destroy = self.MH_thresh, [], []
+                while len(inl) < self.min_inliers:
+                    for f in inst:
+                        if f.status != F_GAUGE:
+                            f.status = F_INSTATE
+                    inl, to_destroy = [], []
+                    for f, d in zip(inst, dist):
+                        if d < thresh:
+                            inl.append(f)
+                        else:
+                            self.num_mh_rejected += 1
+                            to_destroy.append(f)
+                    thresh *= self.MH_mult
+                for f in to_destroy:
+                    if f.status == F_GAUGE:
+                        self.needs_new_gauge.append(f.ref)
+                    f.status = F_REJECTED
+                    affected.add(f.ref.id)
+                for f in to_destroy:
+                    self.g_remove_feature(f)
+                for f in to_destroy:
+                    self.remove_feature_from_state(f)
+                    self.fpool.destroy(f)
+                    self.tracks.remove(f)
+                self.inliers = inl
+            else:
+                self.inliers = list(inst)
+        before = set(self.features)
+        self.discard_affected_groups()
+        self.find_new_gauge_features()
+        self.tracks = [f for f in self.tracks if not (f.id in before and f.id not in self.features)]
+        in_update = [f for f in self.inliers if f.instate()]
+        if in_update:
+            inst_groups = self.grps(lambda g: g.instate())
+            M = 2 * len(in_update)
+            H, inn = np.zeros((M, lay.N)), np.zeros(M)
+            for i, f in enumerate(in_update):
+                E.fill_jacobian_block(lay, H, 2 * i, Js[f.id], f.ref.sind, f.sind)
+                inn[2 * i : 2 * i + 2] = inns[f.id]
+            self.P, err, _, _ = E.update_joseph(H, self.P, inn, np.full(M, self.R))
+            self.absorb(err, inst_groups, in_update)
+        self.instate_features = in_update
+        self.meas_update_initialized = True
+        g = self.gpool.get()
+        g.__init__(g.slot)
+        g.id = self.group_counter
+        self.group_counter += 1
+        g.Rsb, g.Tsb = self.X.Rsb.copy(), self.X.Tsb.copy()
+        self.g_add_group(g)
+        self.tracks = []
+        for f in new_features:
+            f.ref = g
+            z0 = self.ids_to_depths[f.id] if self.sim_init_depths else self.init_z
+            f.x[:2] = self.cam.unproject(f.xp())
+            f.x[2] = math.log(z0)
+            f.P = np.diag(np.array(self.init_std) ** 2)
+            f.status = F_INITIALIZING
+            self.g_add_feature(f)
+            self.g_link(f, g)
+            self.tracks.append(f)
+        for f in self.feats(lambda f: f.tstatus == TRACKED):
+            self.g_link(f, g)
+            self.tracks.append(f)
+        # AdaptInitialDepth (manager.cpp:255-278)
+        depth = [f.z() for f in self.feats(lambda f: f.instate() or (f.status == F_READY and f.lifetime > self.adapt_life))]
+        if depth:
+            med = depth[len(depth) >> 1]
+            if not (med < self.min_z or med > self.max_z):
+                self.init_z = (1 - self.adapt_w) * self.init_z + self.adapt_w * med
+        # EnforceMaxGroupLifetime (manager.cpp:282-303)
+        for gg in self.grps():
+            if gg.lifetime > self.max_group_lifetime and not any(self.features[fid].ref is gg for fid in self.group_adj[gg.id]):
+                self.g_remove_group(gg)
+                self.gpool.deactivate(gg)
+
+    def absorb(self, err, inst_groups, in_update):
+        X = self.X
+        X.Rsb = X.Rsb @ E.so3_exp(err[0:3])
+        X.Tsb = X.Tsb + err[3:6]
+        X.Vsb = X.Vsb + err[6:9]
+        X.bg = X.bg + err[9:12]
+        X.ba = X.ba + err[12:15]
+        X.Rbc = X.Rbc @ E.so3_exp(err[15:18])
+        X.Tbc = X.Tbc + err[18:21]
+        X.Rsg = X.Rsg @ E.so3_exp(np.array([err[21], err[22], 0.0]))
+        X.counter += 1
+        if X.counter % 50 == 0:
+            X.Rsb, X.Rbc = E.quat_normalize_rot(X.Rsb), E.quat_normalize_rot(X.Rbc)
+            w = E.so3_log(X.Rsg)
+            w[2] = 0
+            X.Rsg = E.so3_exp(w)
+        for g in inst_groups:
+            o = self.lay.goff(g.sind)
+            g.Rsb = g.Rsb @ E.so3_exp(err[o : o + 3])
+            g.Tsb = g.Tsb + err[o + 3 : o + 6]
+        for f in in_update:
+            o = self.lay.foff(f.sind)
+            f.x = f.x + err[o : o + 3]
+        self.err[:] = 0
+
+    def select_and_add(self, inst):  # manager.cpp:332-355
+        free_g = self.gsel.count(False)
+        free_f = self.lay.F - len(inst)
+        if self.n_gauge == 0:
+            self.zero_gauge_add(inst)
+        elif free_f < self.n_gauge or free_g == 0:
+            self.add_within_groups(inst)
+        else:
+            self.add_group_of_features(inst, free_g)
+            self.add_within_groups(inst)
+
+    def add_within_groups(self, inst):
+        strict = not (self.vision_counter < self.strict_steps)
+        cands = sorted(self.feats(lambda f: self.candidate(f, strict) and f.ref.instate()), key=lambda f: f.slot)
+        cands.sort(key=self.cand_key)
+        for f in cands:
+            if len(inst) >= self.lay.F:
+                break
+            inst.append(f)
+            self.add_feature_to_state(f)
+
+    def zero_gauge_add(self, inst):
+        free = self.gsel.count(False)
+        strict = not (self.vision_counter < self.strict_steps)
+        cands = sorted(self.feats(lambda f: self.candidate(f, strict)), key=lambda f: f.slot)
+        cands.sort(key=self.cand_key)
+        for f in cands:
+            if len(inst) >= self.lay.F:
+                break
+            if not f.ref.instate() and free <= 0:
+                continue
+            inst.append(f)
+            self.add_feature_to_state(f)
+            if not f.ref.instate():
+                self.add_group_to_state(f.ref)
+                self.needs_new_gauge.append(f.ref)
+                free -= 1
+
+    def add_group_of_features(self, inst, free_g):
+        to_add = self.lay.F - len(inst)
+        n_owned = lambda g: sum(1 for f in self.features.values() if f.ref is g and f.status == F_READY)
+        cands = self.grps(lambda g: g.status == G_CREATED and n_owned(g) >= self.n_gauge)
+        cands.sort(key=lambda g: -n_owned(g))
+        for g in cands:
+            feats = self.feats(lambda f: f.ref is g and f.status == F_READY)
+            feats.sort(key=self.cand_key)
+            for f in feats:
+                self.add_feature_to_state(f)
+                inst.append(f)
+                to_add -= 1
+                if to_add == 0:
+                    break
+            self.add_group_to_state(g)
+            self.needs_new_gauge.append(g)
+            free_g -= 1
+            if to_add < self.n_gauge or free_g == 0:
+                break
+
+    def discard_affected_groups(self):  # manager.cpp:307-328
+        for gid in sorted(self.affected):
+            g = self.groups.get(gid)
+            if g is None:
+                continue
+            n_in = sum(1 for f in self.features.values() if f.ref is g and f.instate())
+            if n_in < self.n_gauge or (self.n_gauge == 0 and n_in == 0):
+                failed = []
+                for fid in sorted(self.group_adj[gid]):
+                    f = self.features[fid]
+                    if f.ref is not g:
+                        continue
+                    nref = None
+                    for ogid in sorted(self.feature_adj[fid]):
+                        og = self.groups[ogid]
+                        if ogid != gid and og.status == G_INSTATE:
+                            nref = og
+                            break
+                    if nref is not None:
+                        ok = self.change_owner(f, nref)
+                        f.P = f.P * self.owner_cov_factor
+                        if not ok:
+                            failed.append(f)
+                    else:
+                        failed.append(f)
+                for f in failed:
+                    self.g_remove_feature(f)
+                    if f.instate():
+                        self.remove_feature_from_state(f)
+                    self.fpool.deactivate(f)
+                for f in failed:
+                    f.status = F_NULLREFED
+                if g.id == self.gauge_group:
+                    self.gauge_group = -1
+                self.g_remove_group(g)
+                if g.instate():
+                    self.remove_group_from_state(g)
+                self.gpool.deactivate(g)
+        self.affected = set()
+
+    def find_new_gauge_features(self):  # update.cpp:35-47 + graph.cpp:276-361
+        for g in self.needs_new_gauge:
+            if self.groups.get(g.id) is not g:
+                continue
+            gf = self.gauge_features[g.id]
+            num_to_find = self.n_gauge - len(gf)
+            cands = self.feats(lambda f: f.status == F_INSTATE and f.ref is g)
+            backup_c = list(cands)
+
+            def fill(C):
+                out = []
+                for f in C[: max(0, min(num_to_find, len(C)))]:
+                    gf.add(f.id)
+                    out.append(f)
+                return out
+
+            found = []
+            if not cands or num_to_find == 0:
+                pass
+            elif len(cands) <= num_to_find:
+                found = fill(cands)
+            else:
+                backup = set(gf)
+                for NT in range(10):
+                    gf.clear()
+                    gf.update(backup)
+                    found = fill(cands)
+                    if len(gf) >= 3:
+                        pts = [E.unproject_logz(self.features[fid].x)[0] for fid in sorted(gf)]
+                        v1 = pts[1] - pts[0]
+                        col = all(np.linalg.norm(np.cross(v1, p - pts[0])) <= self.collinear_thresh for p in pts[2:])
+                        if col:
+                            cands = cands[1:] + cands[:1]
+                            if NT == 9:
+                                gf.clear()
+                                gf.update(backup)
+                                fill(backup_c)
+                        else:
+                            break
+            for f in found:
+                f.status = F_GAUGE
+                E.fix_feature_xy(self.lay, self.P, f.sind)
+        self.needs_new_gauge = []
+
+    def switch_ref_group(self):  # estimator.cpp:1362-1407
+        cands = self.grps(lambda g: g.instate())
+        if not cands:
+            return
+        cov = lambda g: float(np.trace(self.P[self.lay.goff(g.sind) : self.lay.goff(g.sind) + 6, self.lay.goff(g.sind) : self.lay.goff(g.sind) + 6]))
+        best = cands[0]
+        for g in cands:
+            if cov(g) < cov(best):
+                best = g
+        self.gauge_group = best.id
+        best.status = G_GAUGE
+        E.switch_ref_group_cov(self.lay, self.P, best.sind, self.group_degrees_fixed)

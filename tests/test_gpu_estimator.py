@@ -1,0 +1,144 @@
+"""GPU parity of the full per-frame pipeline (estimator-level C ABI) against the numpy oracle
+pipeline on identical synthetic streams.  Tolerances (fp64 device kernels vs fp64 numpy; the update
+uses the algebraically identical symmetric standard form instead of Joseph's):
+  pose trajectory   |dT| <= 1e-7 m, |dR| <= 1e-8 after every frame
+  covariance        |dP| <= 1e-7 * max|P| at the end
+  id / slot tables  exact."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.estimator_oracle import EstimatorOracle
+from xivo_b200 import pyxivo, sim
+
+pytestmark = pytest.mark.gpu
+CFG = os.path.join(os.path.dirname(pyxivo.__file__), "cfg")
+
+
+def run_oracle_pcw(cfg, msgs, G, F, sim_depths):
+    est = EstimatorOracle(cfg, G=G, F=F)
+    est.sim_init_depths = sim_depths
+    out = []
+    for k, ts, p in msgs:
+        if k == "imu":
+            est.InertialMeas(ts, p[0], p[1])
+        else:
+            est.VisualMeasPointCloud(ts, p[0], p[1])
+            out.append((est.gsb().copy(), sorted(f.id for f in est.instate_features), est.gauge_group))
+    return est, out
+
+
+@pytest.mark.parametrize("G,F,method,sim_depths", [(4, 14, "PrinceDormand", True), (15, 30, "RK4", True), (4, 14, "PrinceDormand", False)])
+def test_pcw_trajectory_parity(G, F, method, sim_depths):
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    cfg["integration_method"] = method
+    msgs, traj = sim.pcw_stream(cfg, duration=3.0, seed=0)
+    ref, ref_out = run_oracle_pcw(cfg, msgs, G, F, sim_depths)
+    b = pyxivo.Batch(cfg, n_seq=2, max_groups=G, max_features=F)
+    if sim_depths:
+        b.init_with_sim_depths()
+    k = 0
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            b.inertial_meas(ts, p[0], p[1])
+        else:
+            b.visual_meas_pointcloud(ts, p[0], p[1])
+            g_ref, ids_ref, gauge_ref = ref_out[k]
+            k += 1
+            for s in range(2):
+                g = b.gsb(s)
+                assert np.abs(g[:, 3] - g_ref[:, 3]).max() <= 1e-7, f"frame {k} seq {s}"
+                assert np.abs(g[:, :3] - g_ref[:, :3]).max() <= 1e-8
+                assert sorted(b.instate_features(s)["ids"].tolist()) == ids_ref
+                assert b.counters(s)["gauge_group"] == gauge_ref
+    P = b.P(0)
+    assert np.abs(P - ref.P).max() <= 1e-7 * np.abs(ref.P).max()
+    assert np.array_equal(P, P.T)
+    assert np.array_equal(b.P(1), P)  # identical inputs -> bit-identical sequences
+    V, bg, ba, Rsg = b.motion(0)
+    assert np.abs(V - ref.X.Vsb).max() <= 1e-7
+    if sim_depths:
+        t_end = b.now(0) * 1e-9
+        assert np.linalg.norm(b.gsb(0)[:, 3] - traj.pos(t_end)) < 0.05  # and it is actually a working VIO
+    b.close()
+
+
+def test_pcw_single_sequence_pyxivo_facade():
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    msgs, _ = sim.pcw_stream(cfg, duration=1.0, seed=3)
+    ref, ref_out = run_oracle_pcw(cfg, msgs, 4, 14, True)
+    e = pyxivo.Estimator(cfg, max_groups=4, max_features=14)
+    e.InitWithSimDepths()
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            e.InertialMeas(ts, *p[0], *p[1])
+        else:
+            e.VisualMeasPointCloud(ts, p[0], p[1])
+    assert np.abs(e.gsb() - ref.gsb()).max() <= 1e-7
+    assert e.num_instate_features() == len(ref.instate_features)
+    assert sorted(e.InstateFeatureIDs().tolist()) == sorted(f.id for f in ref.instate_features)
+    assert e.MeasurementUpdateInitialized() and e.VisionInitialized()
+    e.close()
+
+
+def test_wrong_mode_is_an_error_not_a_fallback():
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    b = pyxivo.Batch(cfg, n_seq=1, max_groups=4, max_features=14, overrides={"message_buffer_size": 0})
+    img = np.zeros((480, 640), np.uint8)
+    with pytest.raises(pyxivo.XivoError):  # VisualMeas in simulation mode throws in the reference too
+        b.visual_meas(0, [img])
+        b.visual_meas(40_000_000, [img])
+    b.close()
+
+
+@pytest.mark.parametrize("channels", [1, 3])
+def test_image_pipeline_parity(channels):
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    cfg["camera_cfg"].update(rows=240, cols=320, fx=137.5, fy=137.5, cx=160, cy=120)
+    cfg["tracker_cfg"].update(num_features_min=60, num_features_max=80)
+    msgs, traj = sim.image_stream(cfg, duration=1.6, channels=channels, seed=1)
+    G, F = 4, 14
+    ref = EstimatorOracle(cfg, G=G, F=F)
+    b = pyxivo.Batch(cfg, n_seq=1, max_groups=G, max_features=F)
+    nframes = 0
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            ref.InertialMeas(ts, p[0], p[1])
+            b.inertial_meas(ts, p[0], p[1])
+        else:
+            ref.VisualMeas(ts, p)
+            b.visual_meas(ts, [p])
+            nframes += 1
+            ids, xy, st = b.tracked_features(0)
+            rid = [f.id for f in ref.tracks]
+            # feature-ID / match tables must be identical; positions to float rounding
+            assert ids.tolist() == rid, f"frame {nframes}"
+            if rid:
+                rxy = np.array([f.xp() for f in ref.tracks])
+                assert np.abs(xy - rxy).max() <= 1e-3
+            g, gr = b.gsb(0), ref.gsb()
+            assert np.abs(g - gr).max() <= 1e-5, f"frame {nframes}"
+    assert nframes > 25 and len(ref.tracks) >= 30
+    c = b.counters(0)
+    assert c["num_instate_features"] == len(ref.instate_features) and c["VisionInitialized"] == 1
+    b.close()
+
+
+def test_tracker_only_mode():
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    cfg["camera_cfg"].update(rows=240, cols=320, fx=137.5, fy=137.5, cx=160, cy=120)
+    cfg["tracker_cfg"].update(num_features_min=75, num_features_max=100)
+    msgs, _ = sim.image_stream(cfg, duration=1.0, seed=2)
+    ref = EstimatorOracle(cfg, G=4, F=14, tracker_only=True)
+    b = pyxivo.Batch(cfg, n_seq=3, max_groups=4, max_features=14, tracker_only=True)
+    for kind, ts, p in msgs:
+        if kind != "img":
+            continue
+        ref.VisualMeasTrackerOnly(ts, p)
+        b.visual_meas(ts, [p, p, p], tracker_only=True)
+        for s in range(3):
+            ids, xy, _ = b.tracked_features(s)
+            assert ids.tolist() == [f.id for f in ref.tracks]
+    assert len(ref.tracks) > 50
+    b.close()

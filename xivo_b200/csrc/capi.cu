@@ -217,7 +217,7 @@ int xivo_jacobian_batch(xivo_ctx* ctx, int G, int F, const double* camera, const
   DevBuf<double> Jd(J_dense ? (size_t)F * 2 * N : 0);
   XB_REQUIRE(Jd.ok(), "cudaMalloc failed");
   rc = launch_jacobian_gate(st, t.lay, t.cam.p, t.X.p, t.groups.p, t.fx.p, t.fxp.p, t.fref.p, t.fsind.p, t.nfeat.p, t.P.p, t.R.p,
-                            t.jac.p, J_dense ? Jd.p : nullptr, 1);
+                            t.jac.p, J_dense ? Jd.p : nullptr, nullptr, 1);
   if (rc) return rc;
   g_launches += 1;
   std::vector<FeatJac> hj(n);
@@ -278,7 +278,7 @@ int xivo_filter_update(xivo_ctx* ctx, int G, int F, const double* camera, const 
   if (nsel) XB_CUDA(cudaMemcpyAsync(dsel.p, sel, sizeof(int) * nsel, cudaMemcpyHostToDevice, st));
   XB_CUDA(cudaMemcpyAsync(dnsel.p, &nsel, sizeof(int), cudaMemcpyHostToDevice, st));
   rc = launch_jacobian_gate(st, t.lay, t.cam.p, t.X.p, t.groups.p, t.fx.p, t.fxp.p, t.fref.p, t.fsind.p, t.nfeat.p, t.P.p, t.R.p,
-                            t.jac.p, nullptr, 1);
+                            t.jac.p, nullptr, nullptr, 1);
   if (rc) return rc;
   rc = launch_ekf_update(st, t.lay, t.jac.p, dsel.p, dnsel.p, t.R.p, t.P.p, derr.p, dHP.p, dKt.p, H_dense ? dH.p : nullptr, 1);
   if (rc) return rc;

@@ -3,6 +3,7 @@
 // projection.  All fp64 (the reference is fp64 Eigen, /root/reference/common/alias.h:11);
 // the covariance P stays resident in HBM, one N x N block per independent filter.
 #include "kernels.h"
+#include "prof.h"
 
 namespace xb {
 
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(32) jacobian_gate_kernel(EkfLayout lay, const 
                                                            const int* __restrict__ feat_ref, const int* __restrict__ feat_sind,
                                                            const int* __restrict__ nfeat, const double* __restrict__ P,
                                                            const double* __restrict__ Rmeas, FeatJac* __restrict__ out,
-                                                           double* __restrict__ J_dense) {
+                                                           double* __restrict__ J_dense, double* __restrict__ mh_out) {
   const int b = blockIdx.y, i = blockIdx.x, lane = threadIdx.x;
   if (i >= nfeat[b]) return;
   const int N = lay.N();
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(32) jacobian_gate_kernel(EkfLayout lay, const 
   if (lane == 0) {
     sj.mh = mh;
     out[fi] = sj;
+    if (mh_out) mh_out[fi] = mh;
   }
   if (J_dense) {
     // coalesced zero fill of the two dense rows, then the 42 non-zeros
@@ -128,10 +130,12 @@ __global__ void __launch_bounds__(32) jacobian_gate_kernel(EkfLayout lay, const 
 
 int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const double* X, const double* groups,
                          const double* feat_x, const double* feat_xp, const int* feat_ref, const int* feat_sind,
-                         const int* nfeat, const double* P, const double* Rmeas, FeatJac* out, double* J_dense, int batch) {
+                         const int* nfeat, const double* P, const double* Rmeas, FeatJac* out, double* J_dense, double* mh_out,
+                         int batch) {
   dim3 grid(lay.F, batch);
+  ProfScope ps("jacobian_gate", st);
   jacobian_gate_kernel<<<grid, 32, 0, st>>>(lay, cam, X, groups, feat_x, feat_xp, feat_ref, feat_sind, nfeat, P, Rmeas, out,
-                                            J_dense);
+                                            J_dense, mh_out);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -328,10 +332,15 @@ int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const 
   const size_t smem = gain_smem(Mmax, true);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: 2*F too large for the shared-memory Cholesky");
   XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int pi_ = Prof::get().start("ekf_gain", st);
   ekf_gain_kernel<true><<<batch, GAIN_THREADS, smem, st>>>(N, lay, jac, sel, nsel, 0, nullptr, nullptr, nullptr, Rmeas, P, err, HP,
                                                           Kt, H_dense, Mmax);
+  Prof::get().stop(pi_, st);
   const int nt = (N + CT - 1) / CT;
-  ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nsel, 0, Mmax, HP, Kt, P);
+  {
+    ProfScope ps("ekf_cov", st);
+    ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nsel, 0, Mmax, HP, Kt, P);
+  }
   XB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -386,6 +395,7 @@ __global__ void __launch_bounds__(256) cov_edit_kernel(int N, double* __restrict
 }
 
 int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops, const int* nops, int max_ops, int batch) {
+  ProfScope ps("cov_edit", st);
   cov_edit_kernel<<<batch, 256, 0, st>>>(N, P, ops, nops, max_ops);
   XB_CUDA(cudaGetLastError());
   return 0;
@@ -422,7 +432,28 @@ __global__ void __launch_bounds__(256) cov_propagate_kernel(int N, double* __res
 
 int launch_cov_propagate(cudaStream_t st, int N, double* P, const double* Phi, const double* Pmm, const unsigned char* active,
                          int batch) {
+  ProfScope ps("cov_propagate", st);
   cov_propagate_kernel<<<batch, 256, 0, st>>>(N, P, Phi, Pmm, active);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Pack what the host needs after an update into one contiguous block per filter:
+// [err (N) | P[0:23,0:23] (529) | diag(P) (N)]  -> a single D2H copy per batch.
+__global__ void __launch_bounds__(256) pack_state_kernel(int N, const double* __restrict__ P, const double* __restrict__ err,
+                                                         double* __restrict__ out) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double* __restrict__ Pb = P + (size_t)b * N * N;
+  double* __restrict__ ob = out + (size_t)b * (2 * N + 529);
+  for (int t = tid; t < N; t += 256) {
+    ob[t] = err[(size_t)b * N + t];
+    ob[N + 529 + t] = Pb[(size_t)t * N + t];
+  }
+  for (int t = tid; t < 529; t += 256) ob[N + t] = Pb[(size_t)(t / 23) * N + t % 23];
+}
+int launch_pack_state(cudaStream_t st, int N, const double* P, const double* err, double* out, int batch) {
+  ProfScope ps("pack_state", st);
+  pack_state_kernel<<<batch, 256, 0, st>>>(N, P, err, out);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -506,6 +537,7 @@ __global__ void subfilter_kernel(const CameraParams* __restrict__ cam, const dou
 int launch_subfilter(cudaStream_t st, const CameraParams* cam, const double* X, const SubfilterIn* in, SubfilterOut* out, int n,
                      double Rtri, double mh_thresh) {
   if (n == 0) return 0;
+  ProfScope ps("subfilter", st);
   subfilter_kernel<<<(n + 127) / 128, 128, 0, st>>>(cam, X, in, out, n, Rtri, mh_thresh);
   XB_CUDA(cudaGetLastError());
   return 0;

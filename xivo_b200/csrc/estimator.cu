@@ -1,0 +1,730 @@
+// Estimator-level C ABI (include/xivo_b200_estimator.h): a Batch of independent estimators that
+// advance in lock-step.  The host state machines (estimator_host.cpp.inc) decide; every numeric hot
+// loop runs in the CUDA kernels of tracker_kernels.cu / ekf_kernels.cu, batched over sequences.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <stdexcept>
+
+#include "../../include/xivo_b200_estimator.h"
+#include "ctx.h"
+#include "estimator.h"
+#include "prof.h"
+
+#include "estimator_host.cpp.inc"
+
+namespace xb {
+extern std::atomic<unsigned long long> g_launches;
+
+// Pinned host mirror + device array.
+template <typename T>
+struct Mirror {
+  T* h = nullptr;
+  T* d = nullptr;
+  size_t n = 0;
+  bool alloc(size_t count) {
+    n = count;
+    if (!count) return true;
+    if (cudaMallocHost(reinterpret_cast<void**>(&h), count * sizeof(T)) != cudaSuccess) return false;
+    if (cudaMalloc(reinterpret_cast<void**>(&d), count * sizeof(T)) != cudaSuccess) return false;
+    memset(h, 0, count * sizeof(T));
+    return cudaMemset(d, 0, count * sizeof(T)) == cudaSuccess;
+  }
+  void release() {
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    h = d = nullptr;
+  }
+  cudaError_t up(cudaStream_t st, size_t count = 0, size_t off = 0) {
+    Prof::get().h2d += (count ? count : n) * sizeof(T);
+    return cudaMemcpyAsync(d + off, h + off, (count ? count : n) * sizeof(T), cudaMemcpyHostToDevice, st);
+  }
+  cudaError_t down(cudaStream_t st, size_t count = 0, size_t off = 0) {
+    Prof::get().d2h += (count ? count : n) * sizeof(T);
+    return cudaMemcpyAsync(h + off, d + off, (count ? count : n) * sizeof(T), cudaMemcpyDeviceToHost, st);
+  }
+};
+
+class Batch {
+ public:
+  xivo_ctx* ctx;
+  int B, N, maxops, max_sub;
+  EkfLayout lay;
+  std::vector<std::unique_ptr<Estimator>> est;
+  // EKF device state
+  double* dP = nullptr;
+  double *dHP = nullptr, *dKt = nullptr, *dErr = nullptr;
+  FeatJac* dJac = nullptr;
+  Mirror<CameraParams> cam;
+  Mirror<double> X, groups, fx, fxp, R, Phi, Pmm, mh, pack;
+  Mirror<int> fref, fsind, nfeat, sel, nsel, nops;
+  Mirror<unsigned char> active;
+  Mirror<EditOp> ops;
+  Mirror<SubfilterIn> sub_in;
+  Mirror<SubfilterOut> sub_out;
+  // tracker device state (allocated at the first image)
+  bool img_ready = false;
+  int rows = 0, cols = 0, cn = 0, ring_n = 0, max_pts = 0, max_kp = 0;
+  PyrDesc pd;
+  uint8_t* dRing = nullptr;   // B x ring_n x img_bytes
+  uint8_t* dPyr = nullptr;    // B x 2 x pd.total
+  std::vector<int> ring_next, prev_slot;
+  Mirror<unsigned long long> off_prev, off_cur;
+  Mirror<float> pts0, pts1, lkerr;
+  Mirror<uint8_t> lkst;
+  Mirror<int> npts, kpcount;
+  Mirror<unsigned> kp;
+  std::string err;
+
+  Batch(xivo_ctx* c, const Json& cfg, int nseq, EkfLayout l, bool tracker_only) : ctx(c), B(nseq), lay(l) {
+    N = lay.N();
+    for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
+    maxops = 4 * (lay.F + lay.G) + 16;
+    max_sub = est[0]->tc.num_features_max + 8;
+    bool ok = cudaMalloc(reinterpret_cast<void**>(&dP), sizeof(double) * B * N * N) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&dHP), sizeof(double) * B * 2 * lay.F * N) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&dKt), sizeof(double) * B * 2 * lay.F * N) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&dErr), sizeof(double) * B * N) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&dJac), sizeof(FeatJac) * B * lay.F) == cudaSuccess;
+    ok = ok && cam.alloc(B) && X.alloc((size_t)B * kPoseDoubles) && groups.alloc((size_t)B * lay.G * kGroupDoubles) &&
+         fx.alloc((size_t)B * lay.F * 3) && fxp.alloc((size_t)B * lay.F * 2) && R.alloc(B) && Phi.alloc((size_t)B * 529) &&
+         Pmm.alloc((size_t)B * 529) && mh.alloc((size_t)B * lay.F) && pack.alloc((size_t)B * (2 * N + 529)) &&
+         fref.alloc((size_t)B * lay.F) && fsind.alloc((size_t)B * lay.F) && nfeat.alloc(B) && sel.alloc((size_t)B * lay.F) &&
+         nsel.alloc(B) && nops.alloc(B) && active.alloc(B) && ops.alloc((size_t)B * maxops) &&
+         sub_in.alloc((size_t)B * max_sub) && sub_out.alloc((size_t)B * max_sub);
+    if (!ok) throw std::runtime_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    // initial covariance: identity with the motion block from the config (estimator.cpp:258-302)
+    std::vector<double> P0((size_t)N * N, 0.0);
+    for (int i = 0; i < N; ++i) P0[(size_t)i * N + i] = 1.0;
+    for (int i = 0; i < 23; ++i)
+      for (int j = 0; j < 23; ++j) P0[(size_t)i * N + j] = est[0]->Pmm[i * 23 + j];
+    for (int b = 0; b < B; ++b) {
+      cudaMemcpy(dP + (size_t)b * N * N, P0.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice);
+      cam.h[b] = est[b]->cam;
+      R.h[b] = est[b]->c.R;
+      for (int i = 0; i < N; ++i) est[b]->diagP[i] = P0[(size_t)i * N + i];
+    }
+    cam.up(ctx->stream);
+    R.up(ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  ~Batch() {
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr})
+      if (p) cudaFree(p);
+    cam.release(); X.release(); groups.release(); fx.release(); fxp.release(); R.release(); Phi.release(); Pmm.release();
+    mh.release(); pack.release(); fref.release(); fsind.release(); nfeat.release(); sel.release(); nsel.release();
+    nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); off_prev.release();
+    off_cur.release(); pts0.release(); pts1.release(); lkerr.release(); lkst.release(); npts.release(); kpcount.release();
+    kp.release();
+  }
+
+  int fail(int code, const std::string& m) {
+    err = m;
+    set_error("%s", m.c_str());
+    return code;
+  }
+
+  // ---- staging helpers -------------------------------------------------------------------
+  int stage_edits(const std::vector<int>& act) {
+    for (int b = 0; b < B; ++b) nops.h[b] = 0;
+    for (int b : act) {
+      auto& e = est[b]->edits;
+      if ((int)e.size() > maxops) return fail(XIVO_ERR_STATE, "covariance edit list overflow");
+      nops.h[b] = (int)e.size();
+      for (size_t i = 0; i < e.size(); ++i) ops.h[(size_t)b * maxops + i] = e[i];
+      e.clear();
+    }
+    return 0;
+  }
+  void stage_propagation(const std::vector<int>& act) {
+    for (int b = 0; b < B; ++b) active.h[b] = 0;
+    for (int b : act) {
+      Estimator& e = *est[b];
+      if (!e.prop_pending) continue;
+      active.h[b] = 1;
+      memcpy(Phi.h + (size_t)b * 529, e.Phi, sizeof(e.Phi));
+      memcpy(Pmm.h + (size_t)b * 529, e.Pmm, sizeof(e.Pmm));
+      for (int i = 0; i < 529; ++i) e.Phi[i] = (i / 23 == i % 23) ? 1.0 : 0.0;
+      e.prop_pending = false;
+    }
+  }
+  // apply pending propagation + edits of the given sequences (used before P read-back)
+  int flush(const std::vector<int>& act) {
+    cudaStream_t st = ctx->stream;
+    stage_propagation(act);
+    if (int rc = stage_edits(act)) return rc;
+    XB_CUDA(Phi.up(st)); XB_CUDA(Pmm.up(st)); XB_CUDA(active.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
+    if (int rc = launch_cov_propagate(st, N, dP, Phi.d, Pmm.d, active.d, B)) return rc;
+    if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
+    g_launches += 2;
+    XB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+
+  // ---- image tracker ---------------------------------------------------------------------
+  int ensure_images(int r, int c, int ch) {
+    if (img_ready) {
+      if (r != rows || c != cols || ch != cn) return fail(XIVO_ERR_ARG, "image geometry changed between frames");
+      return 0;
+    }
+    Estimator& e0 = *est[0];
+    if (ch != 1 && ch != 3) return fail(XIVO_ERR_ARG, "images must have 1 or 3 channels");
+    rows = r; cols = c; cn = ch;
+    pd = make_pyr_desc(rows, cols, cn, e0.tc.win_size, e0.tc.max_level);
+    ring_n = e0.c.message_buffer_size + 2;
+    max_pts = e0.tc.num_features_max + 8;
+    max_kp = std::max(4096, std::min(1 << 16, rows * cols / 8));
+    const size_t ib = (size_t)rows * cols * cn;
+    bool ok = cudaMalloc(reinterpret_cast<void**>(&dRing), (size_t)B * ring_n * ib) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&dPyr), (size_t)B * 2 * pd.total) == cudaSuccess;
+    ok = ok && off_prev.alloc(B) && off_cur.alloc(B) && pts0.alloc((size_t)B * max_pts * 2) && pts1.alloc((size_t)B * max_pts * 2) &&
+         lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && npts.alloc(B) && kpcount.alloc(B) &&
+         kp.alloc((size_t)B * max_kp);
+    if (!ok) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
+    ring_next.assign(B, 0);
+    prev_slot.assign(B, 0);
+    for (auto& e : est) {
+      e->rows = rows; e->cols = cols;
+      e->mask.assign((size_t)rows * cols, 0);
+    }
+    img_ready = true;
+    return 0;
+  }
+
+  // Tracker::DetectLK's selection (tracker.cpp:224-229, :295-328) from the packed keypoints of one sequence.
+  void detect_select(Estimator& e, const unsigned* kps, int n, int num_to_add) {
+    // runByPixelsMask, then order (score desc, y asc, x asc): bucket by score, sort buckets lazily
+    std::vector<unsigned> bucket[256];
+    for (int i = 0; i < n; ++i) {
+      const unsigned k = kps[i];
+      const int x = (k >> 8) & 0xfff, y = k >> 20;
+      if (e.mask[(size_t)y * e.cols + x]) bucket[k & 0xff].push_back(k);
+    }
+    for (int s = 255; s >= 0; --s) {
+      auto& v = bucket[s];
+      if (v.empty()) continue;
+      std::sort(v.begin(), v.end());  // packed (y, x, score) ascending == (y, x) ascending within a score
+      for (unsigned k : v) {
+        const double x = (k >> 8) & 0xfff, y = k >> 20;
+        if (e.mask_valid(x, y)) {
+          Feature* f = e.create_feature(x, y);
+          if (!f) return;
+          f->response = (float)s;
+          e.tracks.push_back(f);
+          e.num_new_detections++;
+          e.mask_out(x, y);
+          --num_to_add;
+        }
+        if (num_to_add <= 0 || s < 5) return;
+      }
+    }
+  }
+
+  // Tracker::UpdateLK (tracker.cpp:463-629) for the sequences in `act` whose message holds ring slot
+  // slots[b].  Descriptor / rescue / homography branches are out of scope.
+  int tracker_update_lk(const std::vector<int>& act, const std::vector<int>& slots) {
+    cudaStream_t st = ctx->stream;
+    const size_t ib = (size_t)rows * cols * cn;
+    std::vector<int> lk_list, det_list;
+    std::vector<int> det_budget(B, 0);
+    for (int b = 0; b < B; ++b) { off_cur.h[b] = ~0ull; off_prev.h[b] = 0; npts.h[b] = 0; }
+    for (size_t i = 0; i < act.size(); ++i) {
+      const int b = act[i];
+      Estimator& e = *est[b];
+      const int cur = 1 - prev_slot[b];
+      off_cur.h[b] = ((size_t)b * 2 + cur) * pd.total;
+      off_prev.h[b] = ((size_t)b * 2 + prev_slot[b]) * pd.total;
+      XB_CUDA(cudaMemcpyAsync(dPyr + off_cur.h[b], dRing + ((size_t)b * ring_n + slots[i]) * ib, ib, cudaMemcpyDeviceToDevice, st));
+      if (!e.tracker_initialized) {
+        std::fill(e.mask.begin(), e.mask.end(), 0);
+        e.reset_mask();
+        det_list.push_back(b);
+        det_budget[b] = e.tc.num_features_max;
+        continue;
+      }
+      e.reset_mask();
+      int n = 0;
+      for (Feature* f : e.tracks) {
+        if (n >= max_pts) return fail(XIVO_ERR_STATE, "tracker feature list exceeds max_pts");
+        float* p0 = pts0.h + ((size_t)b * max_pts + n) * 2;
+        float* p1 = pts1.h + ((size_t)b * max_pts + n) * 2;
+        p0[0] = (float)f->xp()[0]; p0[1] = (float)f->xp()[1];
+        if (f->pred[0] != -1 && f->pred[1] != -1) {
+          p1[0] = (float)f->pred[0]; p1[1] = (float)f->pred[1];
+          f->pred[0] = f->pred[1] = -1;
+        } else {
+          p1[0] = p0[0]; p1[1] = p0[1];
+        }
+        ++n;
+      }
+      if (n == 0) {  // tracker.cpp:520-523: no swap, re-initialise on the next frame
+        e.tracker_initialized = false;
+        off_cur.h[b] = ~0ull;
+        continue;
+      }
+      npts.h[b] = n;
+      lk_list.push_back(b);
+    }
+    XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st));
+    if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B)) return rc;
+    g_launches += pd.n_levels - 1;
+    if (!lk_list.empty()) {
+      XB_CUDA(pts0.up(st)); XB_CUDA(pts1.up(st));
+      const TrackerCfg& tc = est[0]->tc;
+      if (int rc = launch_lk_track(st, dPyr, dPyr, 0, off_prev.d, off_cur.d, pd, pts0.d, pts1.d, lkst.d, lkerr.d, npts.d, max_pts, B,
+                                   tc.win_size, tc.max_iter, tc.eps, 1, 1e-4))
+        return rc;
+      g_launches += 1;
+      XB_CUDA(pts1.down(st)); XB_CUDA(lkst.down(st));
+      XB_CUDA(cudaStreamSynchronize(st));
+      for (int b : lk_list) {
+        Estimator& e = *est[b];
+        int i = 0, num_valid = 0, num_failed = 0;
+        std::vector<Feature*> dropped;
+        for (Feature* f : e.tracks) {
+          const float* p1 = pts1.h + ((size_t)b * max_pts + i) * 2;
+          bool ok = lkst.h[(size_t)b * max_pts + i] != 0;
+          if (ok) {
+            const double dx = f->xp()[0] - (double)p1[0], dy = f->xp()[1] - (double)p1[1];
+            if (e.mask_valid(p1[0], p1[1]) && std::sqrt(dx * dx + dy * dy) < e.tc.max_pixel_displacement) {
+              f->tstatus = TrackStatus::TRACKED;
+              f->track.push_back({(double)p1[0], (double)p1[1]});
+              e.mask_out(p1[0], p1[1]);
+              ++num_valid;
+            } else {
+              ok = false;
+            }
+          }
+          if (!ok) { ++num_failed; dropped.push_back(f); }
+          ++i;
+        }
+        e.num_new_detections = 0;
+        e.num_failed_to_track = num_failed;
+        for (Feature* f : dropped) f->tstatus = TrackStatus::DROPPED;  // (no rescue path: set right away)
+        if (num_valid < e.tc.num_features_min) {
+          det_list.push_back(b);
+          det_budget[b] = e.tc.num_features_max - num_valid;
+        }
+      }
+    }
+    if (!det_list.empty()) {
+      // FAST on the current level-0 image of the sequences that need new features
+      for (int b = 0; b < B; ++b) off_prev.h[b] = ~0ull;  // reuse off_prev as the FAST selector
+      for (int b : det_list) off_prev.h[b] = ((size_t)b * 2 + (1 - prev_slot[b])) * pd.total;
+      XB_CUDA(off_prev.up(st));
+      const TrackerCfg& tc = est[0]->tc;
+      if (int rc = launch_fast_detect(st, dPyr, 0, off_prev.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B))
+        return rc;
+      g_launches += 1;
+      XB_CUDA(kpcount.down(st));
+      XB_CUDA(cudaStreamSynchronize(st));
+      for (int b : det_list) {
+        const int n = std::min(kpcount.h[b], max_kp);
+        if (n) { Prof::get().d2h += sizeof(unsigned) * n; XB_CUDA(cudaMemcpyAsync(kp.h + (size_t)b * max_kp, kp.d + (size_t)b * max_kp, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st)); }
+      }
+      XB_CUDA(cudaStreamSynchronize(st));
+      for (int b : det_list) {
+        Estimator& e = *est[b];
+        detect_select(e, kp.h + (size_t)b * max_kp, std::min(kpcount.h[b], max_kp), det_budget[b]);
+        e.tracker_initialized = true;
+      }
+    }
+    for (int b : act)
+      if (off_cur.h[b] != ~0ull) prev_slot[b] = 1 - prev_slot[b];  // std::swap(pyramid, pyramid_)
+    return 0;
+  }
+
+  // ---- one visual message per active sequence ----------------------------------------------
+  int process_visual(const std::vector<int>& act_in, std::vector<Msg>& msgs) {
+    cudaStream_t st = ctx->stream;
+    std::vector<int> act, full, lk_act, lk_slots;
+    for (size_t i = 0; i < act_in.size(); ++i) {
+      const int b = act_in[i];
+      Estimator& e = *est[b];
+      Msg& m = msgs[i];
+      const bool proceed = e.visual_begin(m.ts, m.type);
+      if (e.error) return fail(e.error, e.error_msg);
+      if (!proceed) continue;
+      if (m.type == 1 || m.type == 3) e.predict_features();
+      if (m.type == 3) {
+        for (size_t k = 0; k < m.ids.size(); ++k) e.ids_to_depths.insert({m.ids[k], m.xp_depth[3 * k + 2]});
+      }
+      if (m.type == 3 || m.type == 4) {
+        e.tracker_update_pointcloud(m.ids, m.xp_depth);
+        if (e.error) return fail(e.error, e.error_msg);
+      } else {
+        lk_act.push_back(b);
+        lk_slots.push_back(m.img_slot);
+      }
+      act.push_back(b);
+      if (m.type == 1 || m.type == 3) full.push_back(b);
+      else if (m.type == 4) e.tracker_only_finish();  // image type 2: after the tracker ran (below)
+    }
+    if (!lk_act.empty()) {
+      if (int rc = tracker_update_lk(lk_act, lk_slots)) return rc;
+      for (int b : lk_act)
+        if (est[b]->error) return fail(est[b]->error, est[b]->error_msg);
+      for (size_t i = 0; i < act_in.size(); ++i)
+        if (msgs[i].type == 2 && std::find(act.begin(), act.end(), act_in[i]) != act.end()) est[act_in[i]]->tracker_only_finish();
+    }
+    if (full.empty()) return 0;
+
+    // ---- ProcessTracks + depth sub-filter (device) ----
+    int nsub = 0;
+    for (int b : full) {
+      Estimator& e = *est[b];
+      e.update_step_pre();
+      if ((int)e.subfilter_list.size() > max_sub) return fail(XIVO_ERR_STATE, "sub-filter list exceeds capacity");
+      for (Feature* f : e.subfilter_list) {
+        SubfilterIn& s = sub_in.h[nsub++];
+        memcpy(s.x, f->x, sizeof(s.x));
+        memcpy(s.P, f->P, sizeof(s.P));
+        s.xp[0] = f->xp()[0]; s.xp[1] = f->xp()[1];
+        memcpy(s.ref, f->ref->Rsb.m, 72);
+        memcpy(s.ref + 9, f->ref->Tsb.v, 24);
+        s.outlier_counter = f->outlier_counter;
+        s.filter = b;
+        s.pad = 0;
+      }
+      double* Xh = X.h + (size_t)b * kPoseDoubles;
+      memcpy(Xh, e.X.Rsb.m, 72); memcpy(Xh + 9, e.X.Tsb.v, 24); memcpy(Xh + 12, e.X.Rbc.m, 72); memcpy(Xh + 21, e.X.Tbc.v, 24);
+    }
+    XB_CUDA(X.up(st));
+    if (nsub) {
+      XB_CUDA(sub_in.up(st, nsub));
+      if (int rc = launch_subfilter(st, cam.d, X.d, sub_in.d, sub_out.d, nsub, est[0]->c.sub_Rtri, est[0]->c.sub_mh)) return rc;
+      g_launches += 1;
+      XB_CUDA(sub_out.down(st, nsub));
+      XB_CUDA(cudaStreamSynchronize(st));
+    }
+    {
+      int o = 0;
+      for (int b : full) {
+        Estimator& e = *est[b];
+        const int n = (int)e.subfilter_list.size();
+        e.update_step_after_subfilter(sub_out.h + o);
+        o += n;
+        if (e.error) return fail(e.error, e.error_msg);
+      }
+    }
+    // ---- propagation strips + edits + Jacobians + gate (device) ----
+    for (int b = 0; b < B; ++b) nfeat.h[b] = 0;
+    for (int b : full) {
+      Estimator& e = *est[b];
+      const int n = (int)e.instate_features.size();
+      nfeat.h[b] = n;
+      for (auto& kv : e.graph.groups) {
+        Group* g = kv.second;
+        if (g->sind < 0) continue;
+        double* gh = groups.h + ((size_t)b * lay.G + g->sind) * kGroupDoubles;
+        memcpy(gh, g->Rsb.m, 72);
+        memcpy(gh + 9, g->Tsb.v, 24);
+      }
+      for (int i = 0; i < n; ++i) {
+        Feature* f = e.instate_features[i];
+        const size_t fi = (size_t)b * lay.F + i;
+        memcpy(fx.h + 3 * fi, f->x, 24);
+        fxp.h[2 * fi] = f->xp()[0]; fxp.h[2 * fi + 1] = f->xp()[1];
+        fref.h[fi] = f->ref->sind;
+        fsind.h[fi] = f->sind;
+        if (f->ref->sind < 0 || f->sind < 0) return fail(XIVO_ERR_STATE, "in-state feature without state slot");
+      }
+    }
+    stage_propagation(full);
+    if (int rc = stage_edits(full)) return rc;
+    XB_CUDA(groups.up(st)); XB_CUDA(fx.up(st)); XB_CUDA(fxp.up(st)); XB_CUDA(fref.up(st)); XB_CUDA(fsind.up(st));
+    XB_CUDA(nfeat.up(st)); XB_CUDA(Phi.up(st)); XB_CUDA(Pmm.up(st)); XB_CUDA(active.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
+    if (int rc = launch_cov_propagate(st, N, dP, Phi.d, Pmm.d, active.d, B)) return rc;
+    if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
+    if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B))
+      return rc;
+    g_launches += 3;
+    XB_CUDA(mh.down(st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    // ---- gating decisions (host), post-gate edits, update (device) ----
+    for (int b = 0; b < B; ++b) nsel.h[b] = 0;
+    for (int b : full) {
+      Estimator& e = *est[b];
+      const std::vector<Feature*> order = e.instate_features;  // index space of mh / the device feature table
+      e.update_step_after_gate(mh.h + (size_t)b * lay.F);
+      if (e.error) return fail(e.error, e.error_msg);
+      int k = 0;
+      for (Feature* f : e.in_update) {
+        const auto it = std::find(order.begin(), order.end(), f);
+        sel.h[(size_t)b * lay.F + k++] = (int)(it - order.begin());
+      }
+      nsel.h[b] = k;
+    }
+    if (int rc = stage_edits(full)) return rc;
+    XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st)); XB_CUDA(sel.up(st)); XB_CUDA(nsel.up(st));
+    if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
+    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B)) return rc;
+    if (int rc = launch_pack_state(st, N, dP, dErr, pack.d, B)) return rc;
+    g_launches += 4;
+    XB_CUDA(pack.down(st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    Prof::get().collect();
+    for (int b : full) {
+      Estimator& e = *est[b];
+      const double* pk = pack.h + (size_t)b * (2 * N + 529);
+      for (int i = 0; i < N; ++i)
+        if (nsel.h[b] && !(pk[i] == pk[i])) return fail(XIVO_ERR_STATE, "innovation covariance not positive definite");
+      e.update_step_after_update(pk, pk + N, pk + N + 529, nsel.h[b] > 0);
+      if (e.error) return fail(e.error, e.error_msg);
+    }
+    return 0;
+  }
+
+  // Push one message per sequence, then execute whatever each heap releases (MaintainBuffer).
+  int ingest(std::vector<Msg>& in) {
+    for (int b = 0; b < B; ++b) est[b]->push(std::move(in[b]));
+    std::vector<int> vis;
+    std::vector<Msg> vmsgs;
+    for (int b = 0; b < B; ++b) {
+      Msg m;
+      if (!est[b]->pop_ready(&m)) continue;
+      if (m.type == 0) {
+        est[b]->inertial_internal(m.ts, m.gyro, m.accel);
+      } else {
+        vis.push_back(b);
+        vmsgs.push_back(std::move(m));
+      }
+    }
+    if (vis.empty()) return 0;
+    return process_visual(vis, vmsgs);
+  }
+};
+
+}  // namespace xb
+
+using namespace xb;
+struct xivo_batch {
+  std::unique_ptr<Batch> impl;
+};
+
+#define BATCH_BEGIN                                        \
+  if (!b || !b->impl) {                                    \
+    set_error("null batch");                               \
+    return XIVO_ERR_ARG;                                   \
+  }                                                        \
+  Batch& B_ = *b->impl;                                    \
+  XB_CUDA(cudaSetDevice(B_.ctx->device));
+#define SEQ_CHECK                                                  \
+  if (seq < 0 || seq >= B_.B) {                                    \
+    set_error("sequence index %d out of range", seq);              \
+    return XIVO_ERR_ARG;                                           \
+  }
+
+extern "C" {
+
+int xivo_batch_create(xivo_ctx* ctx, const char* cfg_json, int n_seq, int max_groups, int max_features, int tracker_only,
+                      xivo_batch** out) {
+  if (!ctx || !cfg_json || !out || n_seq <= 0 || max_groups <= 0 || max_features <= 0) {
+    set_error("batch_create: bad arguments");
+    return XIVO_ERR_ARG;
+  }
+  XB_CUDA(cudaSetDevice(ctx->device));
+  try {
+    Json cfg = Json::parse(cfg_json);
+    std::unique_ptr<Batch> impl(new Batch(ctx, cfg, n_seq, EkfLayout{max_groups, max_features}, tracker_only != 0));
+    *out = new xivo_batch{std::move(impl)};
+  } catch (const std::exception& e) {
+    set_error("batch_create: %s", e.what());
+    return XIVO_ERR_ARG;
+  }
+  return XIVO_OK;
+}
+
+void xivo_batch_destroy(xivo_batch* b) {
+  if (!b) return;
+  if (b->impl) cudaSetDevice(b->impl->ctx->device);
+  delete b;
+}
+int xivo_batch_size(const xivo_batch* b) { return b && b->impl ? b->impl->B : 0; }
+int xivo_batch_state_dim(const xivo_batch* b) { return b && b->impl ? b->impl->N : 0; }
+
+int xivo_batch_inertial_meas(xivo_batch* b, const uint64_t* ts_ns, const double* gyro, const double* accel) {
+  BATCH_BEGIN;
+  XB_REQUIRE(ts_ns && gyro && accel, "inertial_meas: null argument");
+  std::vector<Msg> in(B_.B);
+  for (int s = 0; s < B_.B; ++s) {
+    in[s].ts = ts_ns[s];
+    in[s].type = 0;
+    memcpy(in[s].gyro, gyro + 3 * s, 24);
+    memcpy(in[s].accel, accel + 3 * s, 24);
+  }
+  return B_.ingest(in);
+}
+
+static int visual_meas_impl(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs, int rows, int cols, int channels,
+                            int tracker_only, bool on_device) {
+  BATCH_BEGIN;
+  XB_REQUIRE(ts_ns && imgs && rows > 0 && cols > 0, "visual_meas: bad arguments");
+  if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
+  const size_t ib = (size_t)rows * cols * channels;
+  std::vector<Msg> in(B_.B);
+  for (int s = 0; s < B_.B; ++s) {
+    XB_REQUIRE(imgs[s], "visual_meas: null image");
+    const int slot = B_.ring_next[s];
+    B_.ring_next[s] = (slot + 1) % B_.ring_n;
+    if (!on_device) Prof::get().h2d += ib;
+    XB_CUDA(cudaMemcpyAsync(B_.dRing + ((size_t)s * B_.ring_n + slot) * ib, imgs[s], ib,
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, B_.ctx->stream));
+    in[s].ts = ts_ns[s];
+    in[s].type = tracker_only ? 2 : 1;
+    in[s].img_slot = slot;
+  }
+  return B_.ingest(in);
+}
+
+int xivo_batch_visual_meas(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs, int rows, int cols, int channels,
+                           int tracker_only) {
+  return visual_meas_impl(b, ts_ns, imgs, rows, cols, channels, tracker_only, false);
+}
+int xivo_batch_visual_meas_device(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs_dev, int rows, int cols,
+                                  int channels, int tracker_only) {
+  return visual_meas_impl(b, ts_ns, imgs_dev, rows, cols, channels, tracker_only, true);
+}
+void xivo_profile_enable(int on) { Prof::get().enabled = on != 0; }
+void xivo_profile_reset(void) { Prof::get().reset(); }
+int xivo_profile_report(char* buf, int n) {
+  const std::string s = Prof::get().json();
+  if ((int)s.size() + 1 > n) return XIVO_ERR_ARG;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return 0;
+}
+
+int xivo_batch_visual_meas_pointcloud(xivo_batch* b, const uint64_t* ts_ns, const int* n_pts, const int* const* ids,
+                                      const double* const* xp_depth, int tracker_only) {
+  BATCH_BEGIN;
+  XB_REQUIRE(ts_ns && n_pts && ids && xp_depth, "visual_meas_pointcloud: null argument");
+  std::vector<Msg> in(B_.B);
+  for (int s = 0; s < B_.B; ++s) {
+    in[s].ts = ts_ns[s];
+    in[s].type = tracker_only ? 4 : 3;
+    in[s].ids.assign(ids[s], ids[s] + n_pts[s]);
+    in[s].xp_depth.assign(xp_depth[s], xp_depth[s] + 3 * (size_t)n_pts[s]);
+  }
+  return B_.ingest(in);
+}
+
+static void put34(const SE3h& g, double* out) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) out[4 * i + j] = g.R.m[3 * i + j];
+    out[4 * i + 3] = g.T.v[i];
+  }
+}
+int xivo_get_gsb(xivo_batch* b, int seq, double* out) { BATCH_BEGIN; SEQ_CHECK; put34(B_.est[seq]->gsb(), out); return 0; }
+int xivo_get_gbc(xivo_batch* b, int seq, double* out) { BATCH_BEGIN; SEQ_CHECK; put34(B_.est[seq]->gbc(), out); return 0; }
+int xivo_get_gsc(xivo_batch* b, int seq, double* out) {
+  BATCH_BEGIN; SEQ_CHECK;
+  put34(se3_mul(B_.est[seq]->gsb(), B_.est[seq]->gbc()), out);
+  return 0;
+}
+int xivo_get_motion(xivo_batch* b, int seq, double* Vsb, double* bg, double* ba, double* Rsg) {
+  BATCH_BEGIN; SEQ_CHECK;
+  const MotionX& X = B_.est[seq]->X;
+  if (Vsb) memcpy(Vsb, X.Vsb.v, 24);
+  if (bg) memcpy(bg, X.bg.v, 24);
+  if (ba) memcpy(ba, X.ba.v, 24);
+  if (Rsg) memcpy(Rsg, X.Rsg.m, 72);
+  return 0;
+}
+int xivo_get_P(xivo_batch* b, int seq, double* out) {
+  BATCH_BEGIN; SEQ_CHECK;
+  XB_REQUIRE(out, "get_P: null output");
+  if (int rc = B_.flush({seq})) return rc;
+  XB_CUDA(cudaMemcpy(out, B_.dP + (size_t)seq * B_.N * B_.N, sizeof(double) * B_.N * B_.N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int xivo_get_Pstate(xivo_batch* b, int seq, double* out81) {
+  BATCH_BEGIN; SEQ_CHECK;
+  const double* Pm = B_.est[seq]->Pmm;  // the host mirror of the motion block is authoritative between frames
+  for (int i = 0; i < 9; ++i)
+    for (int j = 0; j < 9; ++j) out81[9 * i + j] = Pm[23 * i + j];
+  return 0;
+}
+int xivo_get_counters(xivo_batch* b, int seq, int* out) {
+  BATCH_BEGIN; SEQ_CHECK;
+  Estimator& e = *B_.est[seq];
+  int ng = 0;
+  for (auto& kv : e.graph.groups) ng += kv.second->instate();
+  out[0] = (int)e.instate_features.size();
+  out[1] = ng;
+  out[2] = e.gauge_group;
+  out[3] = e.num_mh_rejected;
+  out[4] = e.num_failed_to_track;
+  out[5] = e.num_new_detections;
+  out[6] = e.vision_counter;
+  out[7] = e.imu_counter;
+  out[8] = e.meas_update_initialized;
+  out[9] = e.vision_initialized;
+  out[10] = (int)e.tracks.size();
+  out[11] = e.error;
+  return 0;
+}
+int xivo_get_time_ns(xivo_batch* b, int seq, uint64_t* ts) { BATCH_BEGIN; SEQ_CHECK; *ts = B_.est[seq]->curr_time; return 0; }
+int xivo_get_tracked_features(xivo_batch* b, int seq, int* ids, double* xy, int* status, int max_n, int* n) {
+  BATCH_BEGIN; SEQ_CHECK;
+  int k = 0;
+  for (Feature* f : B_.est[seq]->tracks) {
+    if (k < max_n) {
+      if (ids) ids[k] = f->id;
+      if (xy) { xy[2 * k] = f->xp()[0]; xy[2 * k + 1] = f->xp()[1]; }
+      if (status) status[k] = (int)f->tstatus;
+    }
+    ++k;
+  }
+  *n = k;
+  return 0;
+}
+int xivo_get_instate_features(xivo_batch* b, int seq, int* ids, int* sinds, int* refs, double* Xs3, double* x3, int max_n, int* n) {
+  BATCH_BEGIN; SEQ_CHECK;
+  Estimator& e = *B_.est[seq];
+  int k = 0;
+  for (Feature* f : e.instate_features) {
+    if (k < max_n) {
+      if (ids) ids[k] = f->id;
+      if (sinds) sinds[k] = f->sind;
+      if (refs) refs[k] = f->ref ? f->ref->id : -1;
+      if (x3) memcpy(x3 + 3 * k, f->x, 24);
+      if (Xs3 && f->ref) {
+        const SE3h gsc = se3_mul(f->ref->gsb(), e.gbc());
+        const double z = std::exp(f->x[2]);
+        const V3 Xs = se3_apply(gsc, V3{{f->x[0] * z, f->x[1] * z, z}});
+        memcpy(Xs3 + 3 * k, Xs.v, 24);
+      }
+    }
+    ++k;
+  }
+  *n = k;
+  return 0;
+}
+int xivo_get_instate_groups(xivo_batch* b, int seq, int* ids, int* sinds, double* gsb12, int max_n, int* n) {
+  BATCH_BEGIN; SEQ_CHECK;
+  int k = 0;
+  for (auto& kv : B_.est[seq]->graph.groups) {
+    Group* g = kv.second;
+    if (!g->instate()) continue;
+    if (k < max_n) {
+      if (ids) ids[k] = g->id;
+      if (sinds) sinds[k] = g->sind;
+      if (gsb12) put34(g->gsb(), gsb12 + 12 * k);
+    }
+    ++k;
+  }
+  *n = k;
+  return 0;
+}
+int xivo_init_with_sim_depths(xivo_batch* b) {
+  BATCH_BEGIN;
+  for (auto& e : B_.est) e->sim_initialize_depths = true;
+  return 0;
+}
+const char* xivo_batch_error(xivo_batch* b, int seq) {
+  if (!b || !b->impl || seq < 0 || seq >= b->impl->B) return "";
+  return b->impl->est[seq]->error_msg.c_str();
+}
+
+}  // extern "C"

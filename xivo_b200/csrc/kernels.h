@@ -44,7 +44,8 @@ int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam
                          const double* X /*B x 24*/, const double* groups /*B x G x 12*/, const double* feat_x /*B x F x 3*/,
                          const double* feat_xp /*B x F x 2*/, const int* feat_ref /*B x F*/, const int* feat_sind /*B x F*/,
                          const int* nfeat /*B*/, const double* P /*B x N x N*/, const double* Rmeas /*B*/,
-                         FeatJac* out /*B x F*/, double* J_dense /*B x F x 2 x N or null*/, int batch);
+                         FeatJac* out /*B x F*/, double* J_dense /*B x F x 2 x N or null*/, double* mh_out /*B x F or null*/,
+                         int batch);
 
 // Stack H (FillJacobianBlock semantics) for the selected features and do the measurement update.
 //   sel: B x F indices into the feature table, nsel: B counts (M = 2*nsel)
@@ -69,6 +70,9 @@ int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops /*B x m
 // Propagation: P[0:23,0:23] <- Pmm ; P[0:23,23:] <- Phi P[0:23,23:] and the symmetric strip.
 int launch_cov_propagate(cudaStream_t st, int N, double* P, const double* Phi /*B x 23 x 23*/, const double* Pmm /*B x 23 x 23*/,
                          const unsigned char* active /*B or null*/, int batch);
+
+// [err | Pmm | diag(P)] per filter, 2N+529 doubles each.
+int launch_pack_state(cudaStream_t st, int N, const double* P, const double* err, double* out, int batch);
 
 // Depth sub-filter, thread per feature (Feature::SubfilterUpdate).
 struct SubfilterIn {

@@ -6,6 +6,7 @@
 // All kernels take a batch dimension (blockIdx.z or .y = independent sequence) because the
 // only way a 640x480 frame fills a B200 is by processing many sequences per launch.
 #include "kernels.h"
+#include "prof.h"
 
 namespace xb {
 
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) pyrdown_kernel(uint8_t* __restri
 
 int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off,
                          const PyrDesc& d, int batch) {
+  ProfScope ps("pyrdown", st);
   for (int l = 0; l + 1 < d.n_levels; ++l) {
     dim3 grid((d.cols[l + 1] + PD_TX - 1) / PD_TX, (d.rows[l + 1] + PD_TY - 1) / PD_TY, batch);
     dim3 block(PD_TX, PD_TY);
@@ -210,6 +212,7 @@ int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long i
   XB_REQUIRE(rows < 4096 && cols < 4096, "FAST: image dimension must be < 4096 (12-bit packed coordinates)");
   XB_REQUIRE(thr >= 0 && thr < 255, "FAST: threshold out of range");
   XB_CUDA(cudaMemsetAsync(kp_count, 0, sizeof(int) * batch, st));
+  ProfScope ps("fast_detect", st);
   dim3 grid((cols + FT_TX - 1) / FT_TX, (rows + FT_TY - 1) / FT_TY, batch);
   if (cn == 1) fast_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
   else fast_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
@@ -498,6 +501,7 @@ int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* nex
   prm.max_pts = max_pts;
   size_t smem = lk_smem_bytes(win, d.cn);
   dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, batch);
+  ProfScope ps("lk_track", st);
   if (d.cn == 1) {
     XB_CUDA(cudaFuncSetAttribute(lk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lk_kernel<1><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);

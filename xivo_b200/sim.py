@@ -1,0 +1,182 @@
+"""Synthetic visual-inertial data: analytic trajectory -> IMU samples, a random
+point-cloud world for the VisualMeasPointCloud path (the reference's own simulation entry,
+scripts/pyxivo_pcw.py) and a textured-plane renderer for the image path.  numpy/scipy only.
+Test/bench infrastructure — not part of the hot path."""
+from __future__ import annotations
+
+import dataclasses
+import json
+import re
+
+import numpy as np
+from scipy import ndimage
+
+G_S = np.array([0.0, 0.0, -9.8])
+
+
+def strip_json_comments(text: str) -> str:
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = []
+    for line in text.splitlines():
+        i, in_str = 0, False
+        while i < len(line):
+            ch = line[i]
+            if ch == '"' and (i == 0 or line[i - 1] != "\\"):
+                in_str = not in_str
+            if not in_str and line[i : i + 2] == "//":
+                line = line[:i]
+                break
+            i += 1
+        out.append(line)
+    text = "\n".join(out)
+    return re.sub(r",(\s*[}\]])", r"\1", text)
+
+
+def load_cfg(text_or_path: str) -> dict:
+    if "{" not in text_or_path:
+        text_or_path = open(text_or_path).read()
+    return json.loads(strip_json_comments(text_or_path))
+
+
+def rodrigues(w):
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + K
+    return np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th**2 * (K @ K)
+
+
+@dataclasses.dataclass
+class Trajectory:
+    """Lissajous position + small oscillating attitude.  Starts at rest at the origin with identity
+    attitude (p, v, theta all zero at t = 0 thanks to the (1 - cos) / sin^2 shaping)."""
+
+    amp: np.ndarray = dataclasses.field(default_factory=lambda: np.array([0.6, 0.4, 0.2]))
+    freq: np.ndarray = dataclasses.field(default_factory=lambda: np.array([0.5, 0.35, 0.25]))
+    rot_amp: np.ndarray = dataclasses.field(default_factory=lambda: np.array([0.10, 0.08, 0.25]))
+    rot_freq: np.ndarray = dataclasses.field(default_factory=lambda: np.array([0.3, 0.2, 0.15]))
+
+    def pos(self, t):
+        w = 2 * np.pi * self.freq
+        return self.amp * (1 - np.cos(w * t))
+
+    def vel(self, t):
+        w = 2 * np.pi * self.freq
+        return self.amp * w * np.sin(w * t)
+
+    def acc(self, t):
+        w = 2 * np.pi * self.freq
+        return self.amp * w * w * np.cos(w * t)
+
+    def theta(self, t):
+        w = 2 * np.pi * self.rot_freq
+        return self.rot_amp * np.sin(w * t) ** 2
+
+    def R(self, t):
+        return rodrigues(self.theta(t))
+
+    def gyro(self, t, h=1e-6):
+        Rm, Rp = self.R(t - h), self.R(t + h)
+        dR = Rm.T @ Rp
+        return np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]]) / (4 * h)
+
+    def accel(self, t):
+        return self.R(t).T @ (self.acc(t) - G_S)
+
+
+def make_world(n=1000, seed=0, xlim=(-4, 4), ylim=(1.0, 6.0), zlim=(-3, 3)):
+    rng = np.random.default_rng(seed)
+    return np.column_stack([rng.uniform(*xlim, n), rng.uniform(*ylim, n), rng.uniform(*zlim, n)])
+
+
+def camera_pose(traj, t, Rbc, Tbc):
+    Rsb, Tsb = traj.R(t), traj.pos(t)
+    return Rsb @ Rbc, Rsb @ Tbc + Tsb
+
+
+def observe_points(world, Rsc, Tsc, K, rows, cols, rng, sigma=0.5, zmin=0.3, zmax=4.5, border=10):
+    Xc = (world - Tsc) @ Rsc
+    z = Xc[:, 2]
+    ok = (z > zmin) & (z < zmax)
+    u = K[0] * Xc[:, 0] / np.where(ok, z, 1) + K[2]
+    v = K[1] * Xc[:, 1] / np.where(ok, z, 1) + K[3]
+    ok &= (u > border) & (u < cols - border) & (v > border) & (v < rows - border)
+    idx = np.nonzero(ok)[0]
+    xp = np.column_stack([u[idx], v[idx]]) + rng.normal(0, sigma, (len(idx), 2))
+    return idx.astype(np.int32), np.column_stack([xp, z[idx]])
+
+
+def pcw_stream(cfg: dict, duration=4.0, imu_dt=0.005, vision_dt=0.04, seed=0, noise_accel=1e-4, noise_gyro=1e-5,
+               pixel_sigma=0.5, npts=1500, traj=None):
+    """Message list [(kind, ts_ns, payload)] in arrival order (IMU first on ties), like
+    scripts/pyxivo_pcw.py:103-113.  kind 'imu' -> (gyro, accel); 'pc' -> (ids, xp_depth)."""
+    traj = traj or Trajectory()
+    rng = np.random.default_rng(seed + 1)
+    cam = cfg["camera_cfg"]
+    K = (cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    X = cfg["X"]
+    Wbc = np.array(X["Wbc"], dtype=float)
+    Rbc = rodrigues(Wbc) if Wbc.size == 3 else Wbc.reshape(3, 3)
+    Tbc = np.array(X["Tbc"], dtype=float)
+    world = make_world(npts, seed)
+    msgs = []
+    for t in np.arange(0, duration, imu_dt):
+        msgs.append((t, 0, "imu", (traj.gyro(t) + rng.normal(0, noise_gyro, 3), traj.accel(t) + rng.normal(0, noise_accel, 3))))
+    for t in np.arange(0, duration, vision_dt):
+        Rsc, Tsc = camera_pose(traj, t, Rbc, Tbc)
+        ids, xpd = observe_points(world, Rsc, Tsc, K, cam["rows"], cam["cols"], rng, pixel_sigma)
+        msgs.append((t, 1, "pc", (ids, xpd)))
+    msgs.sort(key=lambda m: (m[0], m[1]))
+    return [(k, int(round(t * 1e9)), p) for (t, _, k, p) in msgs], traj
+
+
+class PlaneRenderer:
+    """Textured wall y = y0 seen by a pinhole camera: each pixel ray is intersected with the plane
+    and the texture is sampled bilinearly.  Physically consistent, so LK tracks are 3-D consistent."""
+
+    def __init__(self, rows, cols, K, y0=3.0, seed=0, tex_scale=110.0, size=2048):
+        from . import synth
+
+        self.rows, self.cols, self.K, self.y0, self.s, self.size = rows, cols, K, y0, tex_scale, size
+        self.tex = synth.texture_canvas(size - 64, size - 64, seed, pad=32)
+        v, u = np.mgrid[0:rows, 0:cols]
+        self.rays = np.stack([(u - K[2]) / K[0], (v - K[3]) / K[1], np.ones_like(u, dtype=float)], -1)
+
+    def render(self, Rsc, Tsc, noise_rng=None):
+        d = self.rays @ Rsc.T
+        lam = (self.y0 - Tsc[1]) / d[..., 1]
+        X = Tsc[0] + lam * d[..., 0]
+        Z = Tsc[2] + lam * d[..., 2]
+        tx = X * self.s + self.size / 2
+        ty = -Z * self.s + self.size / 2
+        img = ndimage.map_coordinates(self.tex, [ty, tx], order=1, mode="reflect")
+        if noise_rng is not None:
+            img = img + noise_rng.normal(0, 1.5, img.shape)
+        return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def image_stream(cfg: dict, duration=2.0, imu_dt=0.005, vision_dt=0.04, seed=0, noise_accel=1e-4, noise_gyro=1e-5,
+                 stationary=0.2, channels=1, traj=None):
+    """IMU + rendered frames.  `stationary` seconds of rest first so that gravity initialisation
+    (estimator.cpp:439-473) sees still samples when simulation=false."""
+    traj = traj or Trajectory()
+    rng = np.random.default_rng(seed + 1)
+    cam = cfg["camera_cfg"]
+    K = (cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    X = cfg["X"]
+    Wbc = np.array(X["Wbc"], dtype=float)
+    Rbc = rodrigues(Wbc) if Wbc.size == 3 else Wbc.reshape(3, 3)
+    Tbc = np.array(X["Tbc"], dtype=float)
+    rend = PlaneRenderer(cam["rows"], cam["cols"], K, seed=seed)
+    tt = lambda t: max(0.0, t - stationary)
+    msgs = []
+    for t in np.arange(0, duration, imu_dt):
+        msgs.append((t, 0, "imu", (traj.gyro(tt(t)) * (t >= stationary) + rng.normal(0, noise_gyro, 3), traj.accel(tt(t)) + rng.normal(0, noise_accel, 3))))
+    for t in np.arange(0, duration, vision_dt):
+        Rsc, Tsc = camera_pose(traj, tt(t), Rbc, Tbc)
+        img = rend.render(Rsc, Tsc, rng)
+        if channels == 3:
+            img = np.repeat(img[:, :, None], 3, axis=2)
+        msgs.append((t, 1, "img", np.ascontiguousarray(img)))
+    msgs.sort(key=lambda m: (m[0], m[1]))
+    return [(k, int(round(t * 1e9)), p) for (t, _, k, p) in msgs], traj
