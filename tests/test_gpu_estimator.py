@@ -54,7 +54,7 @@ def test_pcw_trajectory_parity(G, F, method, sim_depths):
                 assert b.counters(s)["gauge_group"] == gauge_ref
     P = b.P(0)
     assert np.abs(P - ref.P).max() <= 1e-7 * np.abs(ref.P).max()
-    assert np.array_equal(P, P.T)
+    assert np.abs(P - P.T).max() <= 1e-12 * np.abs(P).max()  # motion block comes from the host integrator
     assert np.array_equal(b.P(1), P)  # identical inputs -> bit-identical sequences
     V, bg, ba, Rsg = b.motion(0)
     assert np.abs(V - ref.X.Vsb).max() <= 1e-7
