@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native XIVO inner loop.
+
+Metric (BASELINE.json): VIO frames/s on synthetic 640x480 + 200 Hz IMU streams, whole job.
+Workload (BASELINE.json configs[1]): full VIO, 640x480 pinhole, 150 tracked features, EKF state
+dim 89 (G=4, F=14), `--seqs` independent sequences per GPU advancing in lock-step (the filter is
+sequential per stream; batching sequences is the only parallel axis — SURVEY.md §8e).  One "step" =
+one frame (+ its 8 IMU samples) for every sequence on every GPU.
+
+  python bench.py --gpus N --steps K --warmup W              # this repo (CUDA)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU arithmetic, all host cores
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with the frames already resident in HBM;
+`e2e` = the same through the estimator-level C ABI with pinned HOST frames (H2D inside the timed
+region, pose read back every step).  `roofline` describes the kernel with the largest share of
+device time in the timed region (CUDA-event durations recorded by the library on its launch stream).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS, G, F = 480, 640, 4, 14
+IMU_PER_FRAME = 8
+FRAME_NS = 40_000_000
+PREROLL_FRAMES = 12  # gravity init (stationary) + first detections, never timed
+
+
+def load_cfg():
+    from xivo_b200 import sim
+
+    return sim.load_cfg(os.path.join(ROOT, "xivo_b200", "cfg", "vio_640x480.json"))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), tf=d.get("bf16_tflops_sustained", 1400.0), src="MEASURED_PEAKS.json (sustained)")
+    return dict(hbm=6650.0, tf=1590.0, src="fallback B200_PROFILING.md")
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].strip().lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def make_streams(cfg, n_streams, n_frames):
+    """n_streams distinct synthetic sequences (seeds 0..), each n_frames frames + IMU."""
+    from xivo_b200 import sim
+
+    out = []
+    for s in range(n_streams):
+        msgs, _ = sim.image_stream(cfg, duration=n_frames * 0.04 + 1e-9, seed=s, channels=1, fast=True)
+        frames = [p for k, _, p in msgs if k == "img"]
+        imu = [(ts, p) for k, ts, p in msgs if k == "imu"]
+        out.append((frames[:n_frames], imu))
+    return out
+
+
+def run_ours(args):
+    import torch
+
+    from xivo_b200 import capi, pyxivo
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = load_cfg()
+    B, K, W = args.seqs, args.steps, args.warmup
+    n_frames = PREROLL_FRAMES + 2 * (W + K) + 4
+    streams = make_streams(cfg, min(B, args.streams), n_frames)
+    S = len(streams)
+    # pinned host copies (e2e pass) and device copies (device-resident pass)
+    host = torch.empty((S, n_frames, ROWS, COLS), dtype=torch.uint8).pin_memory()
+    for s, (frames, _) in enumerate(streams):
+        for f, img in enumerate(frames):
+            host[s, f] = torch.from_numpy(img)
+    dev = host.cuda()
+    hnp = host.numpy()
+    fbytes = ROWS * COLS
+    host_ptr = [[hnp[s, f].ctypes.data for f in range(n_frames)] for s in range(S)]
+    dev_ptr = [[dev.data_ptr() + (s * n_frames + f) * fbytes for f in range(n_frames)] for s in range(S)]
+    seq_stream = [(b + rank) % S for b in range(B)]
+    # IMU arrays per step: (B,3)
+    imu_ts = np.array([[ts for ts, _ in streams[s][1]] for s in range(S)], dtype=np.uint64)
+    imu_g = np.array([[p[0] for _, p in streams[s][1]] for s in range(S)])
+    imu_a = np.array([[p[1] for _, p in streams[s][1]] for s in range(S)])
+
+    ctx = capi.Context(local)
+    bt = pyxivo.Batch(cfg, n_seq=B, max_groups=G, max_features=F, ctx=ctx)
+    L = capi.lib()
+    import ctypes as C
+
+    L.xivo_ctx_stream.restype = C.c_void_p
+    ext = torch.cuda.ExternalStream(L.xivo_ctx_stream(ctx._h))
+    idx = np.array(seq_stream)
+
+    def step(f, device_resident):
+        for j in range(IMU_PER_FRAME):
+            k = f * IMU_PER_FRAME + j
+            bt.inertial_meas(imu_ts[idx, k], imu_g[idx, k], imu_a[idx, k])
+        ts = np.full(B, f * FRAME_NS, dtype=np.uint64)
+        ptrs = (C.c_void_p * B)(*[(dev_ptr if device_resident else host_ptr)[s][f] for s in seq_stream])
+        fn = L.xivo_batch_visual_meas_device if device_resident else L.xivo_batch_visual_meas
+        rc = fn(bt._h, ts.ctypes.data_as(C.c_void_p), ptrs, ROWS, COLS, 1, 0)
+        if rc != 0:
+            raise RuntimeError(L.xivo_last_error().decode())
+        return bt.gsb(0)  # host read of the step's result (pose); the err/P_mm D2H happened inside the call
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    f = 0
+    for _ in range(PREROLL_FRAMES):
+        step(f, True)
+        f += 1
+
+    def timed(device_resident, profile):
+        nonlocal f
+        for _ in range(W):
+            step(f, device_resident)
+            f += 1
+        L.xivo_profile_reset()
+        L.xivo_profile_enable(1 if profile else 0)
+        launches0 = capi.launch_count()
+        clk = ClockSampler(local)
+        barrier()
+        clk.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(ext)
+        ntracked = 0
+        for _ in range(K):
+            step(f, device_resident)
+            ntracked += bt.counters(0)["num_tracked"]
+            f += 1
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = clk.stop()
+        ms = e0.elapsed_time(e1)
+        L.xivo_profile_enable(0)
+        buf = C.create_string_buffer(1 << 16)
+        L.xivo_profile_report(buf, len(buf))
+        prof = json.loads(buf.value.decode())
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked / K)
+
+    r_dev = timed(True, True)
+    r_e2e = timed(False, False)
+    frames_total = world * B * K
+    value = frames_total / (r_dev["ms"] * 1e-3)
+    e2e = frames_total / (r_e2e["ms"] * 1e-3)
+
+    peaks = measured_peaks()
+    prof = r_dev["prof"]
+    kern = {k: v for k, v in prof.items() if not k.startswith("_")}
+    upd_ms = kern.get("ekf_gain", {}).get("ms", 0) + kern.get("ekf_cov", {}).get("ms", 0)
+    merged = {k: dict(v) for k, v in kern.items() if k not in ("ekf_gain", "ekf_cov", "ekf_update")}
+    if upd_ms:
+        merged["ekf_update"] = dict(calls=kern.get("ekf_gain", {}).get("calls", 0), ms=upd_ms, work=kern.get("ekf_update", {}).get("work", 0))
+    tot_ms = sum(v["ms"] for v in merged.values()) or 1.0
+    dom = max(merged, key=lambda k: merged[k]["ms"])
+    d = merged[dom]
+    bound = "tensor" if dom == "ekf_update" else "hbm"
+    per_launch_s = d["ms"] * 1e-3 / max(d["calls"], 1)
+    work_per_launch = d["work"] / max(d["calls"], 1)
+    if bound == "hbm":
+        achieved, peak, unit = work_per_launch / per_launch_s / 1e9, peaks["hbm"], "GB/s"
+    else:
+        achieved, peak, unit = work_per_launch / per_launch_s / 1e12, peaks["tf"], "TFLOP/s"
+    roofline = dict(kernel=dom, bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=None, peak_source=peaks["src"],
+                    share_of_device_time=d["ms"] / tot_ms, launches=d["calls"], avg_launch_us=per_launch_s * 1e6,
+                    kernels={k: dict(ms=round(v["ms"], 4), calls=v["calls"], share=round(v["ms"] / tot_ms, 4)) for k, v in merged.items()},
+                    device_busy_frac=tot_ms / r_dev["ms"])
+
+    out = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_baseline
+
+            cores = min(os.cpu_count() or 1, args.cpu_cores) if args.cpu_cores else (os.cpu_count() or 1)
+            t0 = time.time()
+            r = cpu_baseline.run(cfg, cores, 25, 14, G, F)
+            cpu = dict(value=r["fps"], unit="frames/s", cores=cores, kind="port",
+                       sample=f"{cores} concurrent synthetic 640x480 sequences x 25 frames; timed: cv2 LK+FAST and Eigen-3.3.9 gate+update on the restated pipeline's inputs ({r['mean_frame_ms']:.2f} ms/frame/core, eigen={r['eigen']}, {time.time() - t0:.0f}s)",
+                       stage_share=r["stage_share"])
+        out = dict(metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=W,
+                   ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                   config=dict(workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
+                               sequences_per_gpu=B, distinct_streams=S, frames_per_step=world * B, channels=1,
+                               l2_policy="inputs larger than L2 are not needed: every step reads a new frame set (B x 307 KB) from the stream buffers; covariance/pyramids are the resident state by design",
+                               message_buffer_size=cfg.get("message_buffer_size", 10)),
+                   e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * fbytes,
+                            d2h_bytes_per_step=(r_e2e["prof"]["_d2h_bytes"] / K) if r_e2e["prof"]["_d2h_bytes"] else None, ms_per_step=r_e2e["ms"] / K),
+                   gpu_launches=r_dev["launches"], clocks=r_dev["clocks"], roofline=roofline, cpu_baseline=cpu,
+                   tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K)
+        print(json.dumps(out))
+    bt.close()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline
+
+    cfg = load_cfg()
+    cores = min(os.cpu_count() or 1, args.cpu_cores) if args.cpu_cores else (os.cpu_count() or 1)
+    K, W = args.steps, args.warmup
+    K_eff = min(K, 60)  # bounded sample: the restated pipeline around the timed numerics is Python
+    t0 = time.time()
+    r = cpu_baseline.run(cfg, cores, K_eff, PREROLL_FRAMES + W, G, F)
+    ms_per_step = r["mean_frame_ms"]  # one step = one frame on each of `cores` concurrent sequences
+    out = dict(impl="reference", metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=r["fps"], unit="frames/s", n_gpus=args.gpus,
+               steps=K_eff, warmup=W, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+               config=dict(workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
+                           sequences=cores, channels=1),
+               cpu_baseline=dict(value=r["fps"], unit="frames/s", cores=cores, kind="port",
+                                 sample=f"{cores} concurrent sequences x {K_eff} frames after {PREROLL_FRAMES + W} untimed; timed numerics: cv2 LK+FAST (OpenCV calls of tracker.cpp) and Eigen 3.3.9 MHGating+UpdateJosephForm (eigen={r['eigen']}); {time.time() - t0:.0f}s wall",
+                                 stage_share=r["stage_share"]),
+               e2e=dict(value=r["fps"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seqs", type=int, default=32, help="independent sequences per GPU (lock-step batch)")
+    ap.add_argument("--streams", type=int, default=4, help="distinct synthetic input streams shared by the sequences")
+    ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,8 @@ int xivo_ctx_create(int device, xivo_ctx** out);
 void xivo_ctx_destroy(xivo_ctx* ctx);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 unsigned long long xivo_launch_count(void);
+/* the cudaStream_t every kernel of this context is launched on (so callers can bracket work with CUDA events) */
+void* xivo_ctx_stream(xivo_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel-level entry points (parity-test surface).

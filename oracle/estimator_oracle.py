@@ -210,6 +210,7 @@ class EstimatorOracle:
         self.slope_accel = self.slope_gyro = np.zeros(3)
         self.buf, self.buf_init, self.seq = [], False, 0
         self.meas_update_initialized = False
+        self.stage_timer = None  # bench.py's CPU-baseline legs install a StageTimer here
 
     # ---------------------------------------------------------------- public API
     def InertialMeas(self, ts, gyro, accel):
@@ -480,6 +481,8 @@ class EstimatorOracle:
                 p1[i] = f.pred.astype(np.float32)
                 f.pred = np.array([-1.0, -1.0])
         r1, st, _ = T.lk_track(self.prev_img, img, p0, p1, **self.klt)
+        if self.stage_timer is not None:
+            self.stage_timer.lk(self.prev_img, img, p0, p1, self.klt)
         valid, dropped = 0, []
         for i, f in enumerate(self.tracks):
             ok = bool(st[i])
@@ -502,6 +505,8 @@ class EstimatorOracle:
 
     def detect_lk(self, img, num_to_add):
         xy, sc, _ = T.fast_detect(img, self.fast_thr, self.fast_nms)
+        if self.stage_timer is not None:
+            self.stage_timer.fast(img, self.fast_thr, self.fast_nms)
         for i in T.select_keypoints(self.mask, xy, sc, num_to_add):
             f = self.create_feature(float(xy[i][0]), float(xy[i][1]))
             f.response = float(sc[i])
@@ -566,6 +571,8 @@ class EstimatorOracle:
         if inst:
             if self.use_MH and len(inst) > self.min_inliers:
                 dist = [E.mh_distance(Js[f.id], self.P, inns[f.id], self.R) for f in inst]
+                if self.stage_timer is not None:
+                    self.stage_timer.gate(np.array([Js[f.id] for f in inst]), self.P, np.array([inns[f.id] for f in inst]), self.R)
                 self.num_mh_rejected = 0
                 thresh, inl, to_destroy = self.MH_thresh, [], []
                 while len(inl) < self.min_inliers:
@@ -606,6 +613,8 @@ class EstimatorOracle:
             for i, f in enumerate(in_update):
                 E.fill_jacobian_block(lay, H, 2 * i, Js[f.id], f.ref.sind, f.sind)
                 inn[2 * i : 2 * i + 2] = inns[f.id]
+            if self.stage_timer is not None:
+                self.stage_timer.update(H, self.P, inn, np.full(M, self.R))
             self.P, err, _, _ = E.update_joseph(H, self.P, inn, np.full(M, self.R))
             self.absorb(err, inst_groups, in_update)
         self.instate_features = in_update

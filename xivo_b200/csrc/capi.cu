@@ -45,6 +45,7 @@ extern "C" {
 const char* xivo_last_error(void) { return g_err; }
 int xivo_version(void) { return 100; }
 unsigned long long xivo_launch_count(void) { return g_launches.load(); }
+void* xivo_ctx_stream(xivo_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int xivo_ctx_create(int device, xivo_ctx** out) {
   if (!out) { set_error("null out"); return XIVO_ERR_ARG; }

@@ -269,6 +269,11 @@ class Batch {
     XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st));
     if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B)) return rc;
     g_launches += pd.n_levels - 1;
+    {
+      int nact = 0;
+      for (int b = 0; b < B; ++b) nact += off_cur.h[b] != ~0ull;
+      Prof::get().add_work("pyrdown", nact * (7.0 / 3.0) * rows * cols * cn);  // (7/3) W H c bytes
+    }
     if (!lk_list.empty()) {
       XB_CUDA(pts0.up(st)); XB_CUDA(pts1.up(st));
       const TrackerCfg& tc = est[0]->tc;
@@ -276,6 +281,11 @@ class Batch {
                                    tc.win_size, tc.max_iter, tc.eps, 1, 1e-4))
         return rc;
       g_launches += 1;
+      {
+        double np_ = 0;
+        for (int b : lk_list) np_ += npts.h[b];
+        Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
+      }
       XB_CUDA(pts1.down(st)); XB_CUDA(lkst.down(st));
       XB_CUDA(cudaStreamSynchronize(st));
       for (int b : lk_list) {
@@ -317,6 +327,7 @@ class Batch {
       if (int rc = launch_fast_detect(st, dPyr, 0, off_prev.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B))
         return rc;
       g_launches += 1;
+      Prof::get().add_work("fast_detect", det_list.size() * 2.0 * rows * cols);  // §8d: 2 W H bytes
       XB_CUDA(kpcount.down(st));
       XB_CUDA(cudaStreamSynchronize(st));
       for (int b : det_list) {
@@ -440,6 +451,11 @@ class Batch {
     if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B))
       return rc;
     g_launches += 3;
+    {
+      double nf = 0;
+      for (int b : full) nf += nfeat.h[b];
+      Prof::get().add_work("jacobian_gate", nf * 2.0 * N * 8.0);  // §8d: M N 8 bytes of H written
+    }
     XB_CUDA(mh.down(st));
     XB_CUDA(cudaStreamSynchronize(st));
     // ---- gating decisions (host), post-gate edits, update (device) ----
@@ -462,6 +478,10 @@ class Batch {
     if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B)) return rc;
     if (int rc = launch_pack_state(st, N, dP, dErr, pack.d, B)) return rc;
     g_launches += 4;
+    for (int b : full) {
+      const double M = 2.0 * nsel.h[b], Nn = N;
+      if (M > 0) Prof::get().add_work("ekf_update", 4 * Nn * Nn * Nn + 6 * M * Nn * Nn + 4 * M * M * Nn + M * M * M / 3.0);  // §8d Joseph flop count
+    }
     XB_CUDA(pack.down(st));
     XB_CUDA(cudaStreamSynchronize(st));
     Prof::get().collect();

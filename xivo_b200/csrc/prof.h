@@ -14,6 +14,7 @@ namespace xb {
 struct ProfEntry {
   unsigned long long calls = 0;
   double ms = 0;
+  double work = 0;  // algorithmic bytes or flops attributed by the host at the launch site
 };
 class Prof {
  public:
@@ -55,6 +56,11 @@ class Prof {
     }
     pending_.clear();
   }
+  void add_work(const char* name, double w) {
+    if (!enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    acc_[name].work += w;
+  }
   void reset() {
     collect();
     std::lock_guard<std::mutex> lk(mu_);
@@ -69,7 +75,8 @@ class Prof {
     bool first = true;
     for (auto& kv : acc_) {
       char buf[256];
-      snprintf(buf, sizeof(buf), "%s\"%s\": {\"calls\": %llu, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.calls, kv.second.ms);
+      snprintf(buf, sizeof(buf), "%s\"%s\": {\"calls\": %llu, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ", kv.first.c_str(), kv.second.calls, kv.second.ms,
+               kv.second.work);
       s += buf;
       first = false;
     }

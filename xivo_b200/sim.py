@@ -142,21 +142,27 @@ class PlaneRenderer:
         v, u = np.mgrid[0:rows, 0:cols]
         self.rays = np.stack([(u - K[2]) / K[0], (v - K[3]) / K[1], np.ones_like(u, dtype=float)], -1)
 
-    def render(self, Rsc, Tsc, noise_rng=None):
+    def render(self, Rsc, Tsc, noise_rng=None, fast=False):
+        """fast=True uses cv2.remap (bench only: ~40x quicker, fixed-point bilinear weights)."""
         d = self.rays @ Rsc.T
         lam = (self.y0 - Tsc[1]) / d[..., 1]
         X = Tsc[0] + lam * d[..., 0]
         Z = Tsc[2] + lam * d[..., 2]
         tx = X * self.s + self.size / 2
         ty = -Z * self.s + self.size / 2
-        img = ndimage.map_coordinates(self.tex, [ty, tx], order=1, mode="reflect")
+        if fast:
+            import cv2
+
+            img = cv2.remap(self.tex, tx.astype(np.float32), ty.astype(np.float32), cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+        else:
+            img = ndimage.map_coordinates(self.tex, [ty, tx], order=1, mode="reflect")
         if noise_rng is not None:
             img = img + noise_rng.normal(0, 1.5, img.shape)
         return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 
 def image_stream(cfg: dict, duration=2.0, imu_dt=0.005, vision_dt=0.04, seed=0, noise_accel=1e-4, noise_gyro=1e-5,
-                 stationary=0.2, channels=1, traj=None):
+                 stationary=0.2, channels=1, traj=None, fast=False):
     """IMU + rendered frames.  `stationary` seconds of rest first so that gravity initialisation
     (estimator.cpp:439-473) sees still samples when simulation=false."""
     traj = traj or Trajectory()
@@ -174,7 +180,7 @@ def image_stream(cfg: dict, duration=2.0, imu_dt=0.005, vision_dt=0.04, seed=0, 
         msgs.append((t, 0, "imu", (traj.gyro(tt(t)) * (t >= stationary) + rng.normal(0, noise_gyro, 3), traj.accel(tt(t)) + rng.normal(0, noise_accel, 3))))
     for t in np.arange(0, duration, vision_dt):
         Rsc, Tsc = camera_pose(traj, tt(t), Rbc, Tbc)
-        img = rend.render(Rsc, Tsc, rng)
+        img = rend.render(Rsc, Tsc, rng, fast)
         if channels == 3:
             img = np.repeat(img[:, :, None], 3, axis=2)
         msgs.append((t, 1, "img", np.ascontiguousarray(img)))
