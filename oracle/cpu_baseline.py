@@ -138,3 +138,14 @@ def run(cfg, n_procs, n_frames, skip, G, F, channels=1):
     tot = sum(stage.values()) or 1.0
     return dict(fps=fps, mean_frame_ms=mean_ms, stage_share={k: v / tot for k, v in stage.items()}, eigen=res[0]["eigen"], cv2=res[0]["cv2"],
                 frames=sum(len(r["per_frame"]) for r in res), ninstate=res[0]["ninstate"], ntracks=res[0]["ntracks"])
+
+
+if __name__ == "__main__":  # python -m oracle.cpu_baseline <cfg.json> <procs> <frames> <skip> <G> <F>  -> JSON on stdout
+    import json
+    import sys
+
+    cfg_path, procs, frames, skip, G_, F_ = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+    sys.path.insert(0, os.path.dirname(_HERE))
+    from xivo_b200 import sim
+
+    print(json.dumps(run(sim.load_cfg(cfg_path), procs, frames, skip, G_, F_)))
