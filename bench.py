@@ -228,7 +228,8 @@ def run_ours(args):
 
     peaks = measured_peaks()
     prof = r_dev["prof"]
-    kern = {k: v for k, v in prof.items() if not k.startswith("_")}
+    kern = {k: v for k, v in prof.items() if not k.startswith("_") and not k.startswith("host:")}
+    host_phases = {k[5:]: round(v["ms"] / K, 4) for k, v in prof.items() if k.startswith("host:")}
     upd_ms = kern.get("ekf_gain", {}).get("ms", 0) + kern.get("ekf_cov", {}).get("ms", 0)
     merged = {k: dict(v) for k, v in kern.items() if k not in ("ekf_gain", "ekf_cov", "ekf_update")}
     if upd_ms:
@@ -268,7 +269,7 @@ def run_ours(args):
                    e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * fbytes,
                             d2h_bytes_per_step=(r_e2e["prof"]["_d2h_bytes"] / K) if r_e2e["prof"]["_d2h_bytes"] else None, ms_per_step=r_e2e["ms"] / K),
                    gpu_launches=r_dev["launches"], clocks=r_dev["clocks"], roofline=roofline, cpu_baseline=cpu,
-                   tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K)
+                   tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K, host_phase_ms_per_step=host_phases)
         print(json.dumps(out))
     bt.close()
     if world > 1:

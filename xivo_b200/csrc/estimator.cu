@@ -1,10 +1,14 @@
 // Estimator-level C ABI (include/xivo_b200_estimator.h): a Batch of independent estimators that
 // advance in lock-step.  The host state machines (estimator_host.cpp.inc) decide; every numeric hot
 // loop runs in the CUDA kernels of tracker_kernels.cu / ekf_kernels.cu, batched over sequences.
+#include <omp.h>
+
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 #include "../../include/xivo_b200_estimator.h"
 #include "ctx.h"
@@ -45,8 +49,37 @@ struct Mirror {
   }
 };
 
+// Host wall-clock phases go into the same profile report as the kernels ("host:<phase>").
+struct HostScope {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  explicit HostScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~HostScope() {
+    if (!Prof::get().enabled.load(std::memory_order_relaxed)) return;
+    Prof::get().add_host(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+
 class Batch {
  public:
+  int nthreads = 1;
+  // Per-sequence host logic is independent across sequences: run it on a small OpenMP team.  CUDA calls
+  // stay on the calling thread.
+  template <typename Fn>
+  void pfor(const std::vector<int>& idx, Fn fn) {
+    const int n = (int)idx.size();
+    if (nthreads <= 1 || n <= 1) {
+      for (int i = 0; i < n; ++i) fn(idx[i], i);
+      return;
+    }
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
+    for (int i = 0; i < n; ++i) fn(idx[i], i);
+  }
+  int first_error(const std::vector<int>& idx) {
+    for (int b : idx)
+      if (est[b]->error) return fail(est[b]->error, est[b]->error_msg);
+    return 0;
+  }
   xivo_ctx* ctx;
   int B, N, maxops, max_sub;
   EkfLayout lay;
@@ -79,6 +112,12 @@ class Batch {
   Batch(xivo_ctx* c, const Json& cfg, int nseq, EkfLayout l, bool tracker_only) : ctx(c), B(nseq), lay(l) {
     N = lay.N();
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
+    {
+      const char* env = getenv("XIVO_THREADS");
+      int hw = (int)std::thread::hardware_concurrency();
+      nthreads = env ? atoi(env) : std::min(32, std::max(1, hw / 2));
+      nthreads = std::max(1, std::min(nthreads, B));
+    }
     maxops = 4 * (lay.F + lay.G) + 16;
     max_sub = est[0]->tc.num_features_max + 8;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dP), sizeof(double) * B * N * N) == cudaSuccess &&
@@ -222,49 +261,60 @@ class Batch {
   }
 
   // Tracker::UpdateLK (tracker.cpp:463-629) for the sequences in `act` whose message holds ring slot
-  // slots[b].  Descriptor / rescue / homography branches are out of scope.
+  // slots[i].  Descriptor / rescue / homography branches are out of scope.
   int tracker_update_lk(const std::vector<int>& act, const std::vector<int>& slots) {
     cudaStream_t st = ctx->stream;
     const size_t ib = (size_t)rows * cols * cn;
     std::vector<int> lk_list, det_list;
-    std::vector<int> det_budget(B, 0);
+    std::vector<int> det_budget(B, 0), kind(B, 0);  // kind: 1 = first frame (detect only), 2 = LK, 3 = empty list
     for (int b = 0; b < B; ++b) { off_cur.h[b] = ~0ull; off_prev.h[b] = 0; npts.h[b] = 0; }
-    for (size_t i = 0; i < act.size(); ++i) {
-      const int b = act[i];
-      Estimator& e = *est[b];
-      const int cur = 1 - prev_slot[b];
-      off_cur.h[b] = ((size_t)b * 2 + cur) * pd.total;
-      off_prev.h[b] = ((size_t)b * 2 + prev_slot[b]) * pd.total;
-      XB_CUDA(cudaMemcpyAsync(dPyr + off_cur.h[b], dRing + ((size_t)b * ring_n + slots[i]) * ib, ib, cudaMemcpyDeviceToDevice, st));
-      if (!e.tracker_initialized) {
-        std::fill(e.mask.begin(), e.mask.end(), 0);
-        e.reset_mask();
-        det_list.push_back(b);
-        det_budget[b] = e.tc.num_features_max;
-        continue;
+    std::atomic<int> overflow{0};
+    {
+      HostScope hs("tracker_prepare");
+      for (size_t i = 0; i < act.size(); ++i) {
+        const int b = act[i];
+        const int cur = 1 - prev_slot[b];
+        off_cur.h[b] = ((size_t)b * 2 + cur) * pd.total;
+        off_prev.h[b] = ((size_t)b * 2 + prev_slot[b]) * pd.total;
+        XB_CUDA(cudaMemcpyAsync(dPyr + off_cur.h[b], dRing + ((size_t)b * ring_n + slots[i]) * ib, ib, cudaMemcpyDeviceToDevice, st));
       }
-      e.reset_mask();
-      int n = 0;
-      for (Feature* f : e.tracks) {
-        if (n >= max_pts) return fail(XIVO_ERR_STATE, "tracker feature list exceeds max_pts");
-        float* p0 = pts0.h + ((size_t)b * max_pts + n) * 2;
-        float* p1 = pts1.h + ((size_t)b * max_pts + n) * 2;
-        p0[0] = (float)f->xp()[0]; p0[1] = (float)f->xp()[1];
-        if (f->pred[0] != -1 && f->pred[1] != -1) {
-          p1[0] = (float)f->pred[0]; p1[1] = (float)f->pred[1];
-          f->pred[0] = f->pred[1] = -1;
-        } else {
-          p1[0] = p0[0]; p1[1] = p0[1];
+      pfor(act, [&](int b, int) {
+        Estimator& e = *est[b];
+        if (!e.tracker_initialized) {
+          std::fill(e.mask.begin(), e.mask.end(), 0);
+          e.reset_mask();
+          kind[b] = 1;
+          return;
         }
-        ++n;
+        e.reset_mask();
+        int n = 0;
+        for (Feature* f : e.tracks) {
+          if (n >= max_pts) { overflow = 1; return; }
+          float* p0 = pts0.h + ((size_t)b * max_pts + n) * 2;
+          float* p1 = pts1.h + ((size_t)b * max_pts + n) * 2;
+          p0[0] = (float)f->xp()[0]; p0[1] = (float)f->xp()[1];
+          if (f->pred[0] != -1 && f->pred[1] != -1) {
+            p1[0] = (float)f->pred[0]; p1[1] = (float)f->pred[1];
+            f->pred[0] = f->pred[1] = -1;
+          } else {
+            p1[0] = p0[0]; p1[1] = p0[1];
+          }
+          ++n;
+        }
+        if (n == 0) {  // tracker.cpp:520-523: no swap, re-initialise on the next frame
+          e.tracker_initialized = false;
+          kind[b] = 3;
+          return;
+        }
+        npts.h[b] = n;
+        kind[b] = 2;
+      });
+      if (overflow) return fail(XIVO_ERR_STATE, "tracker feature list exceeds max_pts");
+      for (int b : act) {
+        if (kind[b] == 1) { det_list.push_back(b); det_budget[b] = est[b]->tc.num_features_max; }
+        else if (kind[b] == 2) lk_list.push_back(b);
+        else off_cur.h[b] = ~0ull;
       }
-      if (n == 0) {  // tracker.cpp:520-523: no swap, re-initialise on the next frame
-        e.tracker_initialized = false;
-        off_cur.h[b] = ~0ull;
-        continue;
-      }
-      npts.h[b] = n;
-      lk_list.push_back(b);
     }
     XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st));
     if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B)) return rc;
@@ -288,10 +338,11 @@ class Batch {
       }
       XB_CUDA(pts1.down(st)); XB_CUDA(lkst.down(st));
       XB_CUDA(cudaStreamSynchronize(st));
-      for (int b : lk_list) {
+      HostScope hs("tracker_accept");
+      std::vector<int> need(B, 0);
+      pfor(lk_list, [&](int b, int) {
         Estimator& e = *est[b];
         int i = 0, num_valid = 0, num_failed = 0;
-        std::vector<Feature*> dropped;
         for (Feature* f : e.tracks) {
           const float* p1 = pts1.h + ((size_t)b * max_pts + i) * 2;
           bool ok = lkst.h[(size_t)b * max_pts + i] != 0;
@@ -306,17 +357,15 @@ class Batch {
               ok = false;
             }
           }
-          if (!ok) { ++num_failed; dropped.push_back(f); }
+          if (!ok) { ++num_failed; f->tstatus = TrackStatus::DROPPED; }  // (no rescue path: dropped right away)
           ++i;
         }
         e.num_new_detections = 0;
         e.num_failed_to_track = num_failed;
-        for (Feature* f : dropped) f->tstatus = TrackStatus::DROPPED;  // (no rescue path: set right away)
-        if (num_valid < e.tc.num_features_min) {
-          det_list.push_back(b);
-          det_budget[b] = e.tc.num_features_max - num_valid;
-        }
-      }
+        if (num_valid < e.tc.num_features_min) need[b] = e.tc.num_features_max - num_valid;
+      });
+      for (int b : lk_list)
+        if (need[b] > 0) { det_list.push_back(b); det_budget[b] = need[b]; }
     }
     if (!det_list.empty()) {
       // FAST on the current level-0 image of the sequences that need new features
@@ -335,11 +384,12 @@ class Batch {
         if (n) { Prof::get().d2h += sizeof(unsigned) * n; XB_CUDA(cudaMemcpyAsync(kp.h + (size_t)b * max_kp, kp.d + (size_t)b * max_kp, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st)); }
       }
       XB_CUDA(cudaStreamSynchronize(st));
-      for (int b : det_list) {
+      HostScope hs("tracker_select");
+      pfor(det_list, [&](int b, int) {
         Estimator& e = *est[b];
         detect_select(e, kp.h + (size_t)b * max_kp, std::min(kpcount.h[b], max_kp), det_budget[b]);
         e.tracker_initialized = true;
-      }
+      });
     }
     for (int b : act)
       if (off_cur.h[b] != ~0ull) prev_slot[b] = 1 - prev_slot[b];  // std::swap(pyramid, pyramid_)
@@ -350,57 +400,72 @@ class Batch {
   int process_visual(const std::vector<int>& act_in, std::vector<Msg>& msgs) {
     cudaStream_t st = ctx->stream;
     std::vector<int> act, full, lk_act, lk_slots;
+    std::vector<char> proceed(act_in.size(), 0);
+    {
+      HostScope hs("visual_begin");
+      std::vector<int> ord(act_in.size());
+      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+      pfor(ord, [&](int i, int) {
+        Estimator& e = *est[act_in[i]];
+        Msg& m = msgs[i];
+        if (!e.visual_begin(m.ts, m.type) || e.error) return;
+        proceed[i] = 1;
+        if (m.type == 1 || m.type == 3) e.predict_features();
+        if (m.type == 3)
+          for (size_t k = 0; k < m.ids.size(); ++k) e.ids_to_depths.insert({m.ids[k], m.xp_depth[3 * k + 2]});
+        if (m.type == 3 || m.type == 4) {
+          e.tracker_update_pointcloud(m.ids, m.xp_depth);
+          if (m.type == 4 && !e.error) e.tracker_only_finish();
+        }
+      });
+    }
+    if (int rc = first_error(act_in)) return rc;
     for (size_t i = 0; i < act_in.size(); ++i) {
+      if (!proceed[i]) continue;
       const int b = act_in[i];
-      Estimator& e = *est[b];
-      Msg& m = msgs[i];
-      const bool proceed = e.visual_begin(m.ts, m.type);
-      if (e.error) return fail(e.error, e.error_msg);
-      if (!proceed) continue;
-      if (m.type == 1 || m.type == 3) e.predict_features();
-      if (m.type == 3) {
-        for (size_t k = 0; k < m.ids.size(); ++k) e.ids_to_depths.insert({m.ids[k], m.xp_depth[3 * k + 2]});
-      }
-      if (m.type == 3 || m.type == 4) {
-        e.tracker_update_pointcloud(m.ids, m.xp_depth);
-        if (e.error) return fail(e.error, e.error_msg);
-      } else {
-        lk_act.push_back(b);
-        lk_slots.push_back(m.img_slot);
-      }
       act.push_back(b);
-      if (m.type == 1 || m.type == 3) full.push_back(b);
-      else if (m.type == 4) e.tracker_only_finish();  // image type 2: after the tracker ran (below)
+      if (msgs[i].type == 1 || msgs[i].type == 2) { lk_act.push_back(b); lk_slots.push_back(msgs[i].img_slot); }
+      if (msgs[i].type == 1 || msgs[i].type == 3) full.push_back(b);
     }
     if (!lk_act.empty()) {
       if (int rc = tracker_update_lk(lk_act, lk_slots)) return rc;
-      for (int b : lk_act)
-        if (est[b]->error) return fail(est[b]->error, est[b]->error_msg);
+      if (int rc = first_error(lk_act)) return rc;
       for (size_t i = 0; i < act_in.size(); ++i)
-        if (msgs[i].type == 2 && std::find(act.begin(), act.end(), act_in[i]) != act.end()) est[act_in[i]]->tracker_only_finish();
+        if (proceed[i] && msgs[i].type == 2) est[act_in[i]]->tracker_only_finish();
     }
     if (full.empty()) return 0;
 
     // ---- ProcessTracks + depth sub-filter (device) ----
-    int nsub = 0;
-    for (int b : full) {
-      Estimator& e = *est[b];
-      e.update_step_pre();
-      if ((int)e.subfilter_list.size() > max_sub) return fail(XIVO_ERR_STATE, "sub-filter list exceeds capacity");
-      for (Feature* f : e.subfilter_list) {
-        SubfilterIn& s = sub_in.h[nsub++];
-        memcpy(s.x, f->x, sizeof(s.x));
-        memcpy(s.P, f->P, sizeof(s.P));
-        s.xp[0] = f->xp()[0]; s.xp[1] = f->xp()[1];
-        memcpy(s.ref, f->ref->Rsb.m, 72);
-        memcpy(s.ref + 9, f->ref->Tsb.v, 24);
-        s.outlier_counter = f->outlier_counter;
-        s.filter = b;
-        s.pad = 0;
+    std::vector<int> sub_off(B + 1, 0);
+    {
+      HostScope hs("process_tracks");
+      pfor(full, [&](int b, int) { est[b]->update_step_pre(); });
+      int nsub = 0;
+      for (int b : full) {
+        if ((int)est[b]->subfilter_list.size() > max_sub) return fail(XIVO_ERR_STATE, "sub-filter list exceeds capacity");
+        sub_off[b] = nsub;
+        nsub += (int)est[b]->subfilter_list.size();
       }
-      double* Xh = X.h + (size_t)b * kPoseDoubles;
-      memcpy(Xh, e.X.Rsb.m, 72); memcpy(Xh + 9, e.X.Tsb.v, 24); memcpy(Xh + 12, e.X.Rbc.m, 72); memcpy(Xh + 21, e.X.Tbc.v, 24);
+      sub_off[B] = nsub;
+      pfor(full, [&](int b, int) {
+        Estimator& e = *est[b];
+        int o = sub_off[b];
+        for (Feature* f : e.subfilter_list) {
+          SubfilterIn& s = sub_in.h[o++];
+          memcpy(s.x, f->x, sizeof(s.x));
+          memcpy(s.P, f->P, sizeof(s.P));
+          s.xp[0] = f->xp()[0]; s.xp[1] = f->xp()[1];
+          memcpy(s.ref, f->ref->Rsb.m, 72);
+          memcpy(s.ref + 9, f->ref->Tsb.v, 24);
+          s.outlier_counter = f->outlier_counter;
+          s.filter = b;
+          s.pad = 0;
+        }
+        double* Xh = X.h + (size_t)b * kPoseDoubles;
+        memcpy(Xh, e.X.Rsb.m, 72); memcpy(Xh + 9, e.X.Tsb.v, 24); memcpy(Xh + 12, e.X.Rbc.m, 72); memcpy(Xh + 21, e.X.Tbc.v, 24);
+      });
     }
+    const int nsub = sub_off[B];
     XB_CUDA(X.up(st));
     if (nsub) {
       XB_CUDA(sub_in.up(st, nsub));
@@ -409,41 +474,39 @@ class Batch {
       XB_CUDA(sub_out.down(st, nsub));
       XB_CUDA(cudaStreamSynchronize(st));
     }
+    // ---- select/add features, fill the device tables ----
+    std::atomic<int> bad_slot{0};
     {
-      int o = 0;
-      for (int b : full) {
+      HostScope hs("select_and_tables");
+      for (int b = 0; b < B; ++b) nfeat.h[b] = 0;
+      pfor(full, [&](int b, int) {
         Estimator& e = *est[b];
-        const int n = (int)e.subfilter_list.size();
-        e.update_step_after_subfilter(sub_out.h + o);
-        o += n;
-        if (e.error) return fail(e.error, e.error_msg);
-      }
+        e.update_step_after_subfilter(sub_out.h + sub_off[b]);
+        if (e.error) return;
+        const int n = (int)e.instate_features.size();
+        nfeat.h[b] = n;
+        for (auto& kv : e.graph.groups) {
+          Group* g = kv.second;
+          if (g->sind < 0) continue;
+          double* gh = groups.h + ((size_t)b * lay.G + g->sind) * kGroupDoubles;
+          memcpy(gh, g->Rsb.m, 72);
+          memcpy(gh + 9, g->Tsb.v, 24);
+        }
+        for (int i = 0; i < n; ++i) {
+          Feature* f = e.instate_features[i];
+          const size_t fi = (size_t)b * lay.F + i;
+          memcpy(fx.h + 3 * fi, f->x, 24);
+          fxp.h[2 * fi] = f->xp()[0]; fxp.h[2 * fi + 1] = f->xp()[1];
+          if (f->ref->sind < 0 || f->sind < 0) { bad_slot = 1; return; }
+          fref.h[fi] = f->ref->sind;
+          fsind.h[fi] = f->sind;
+        }
+      });
+      if (int rc = first_error(full)) return rc;
+      if (bad_slot) return fail(XIVO_ERR_STATE, "in-state feature without state slot");
+      stage_propagation(full);
+      if (int rc = stage_edits(full)) return rc;
     }
-    // ---- propagation strips + edits + Jacobians + gate (device) ----
-    for (int b = 0; b < B; ++b) nfeat.h[b] = 0;
-    for (int b : full) {
-      Estimator& e = *est[b];
-      const int n = (int)e.instate_features.size();
-      nfeat.h[b] = n;
-      for (auto& kv : e.graph.groups) {
-        Group* g = kv.second;
-        if (g->sind < 0) continue;
-        double* gh = groups.h + ((size_t)b * lay.G + g->sind) * kGroupDoubles;
-        memcpy(gh, g->Rsb.m, 72);
-        memcpy(gh + 9, g->Tsb.v, 24);
-      }
-      for (int i = 0; i < n; ++i) {
-        Feature* f = e.instate_features[i];
-        const size_t fi = (size_t)b * lay.F + i;
-        memcpy(fx.h + 3 * fi, f->x, 24);
-        fxp.h[2 * fi] = f->xp()[0]; fxp.h[2 * fi + 1] = f->xp()[1];
-        fref.h[fi] = f->ref->sind;
-        fsind.h[fi] = f->sind;
-        if (f->ref->sind < 0 || f->sind < 0) return fail(XIVO_ERR_STATE, "in-state feature without state slot");
-      }
-    }
-    stage_propagation(full);
-    if (int rc = stage_edits(full)) return rc;
     XB_CUDA(groups.up(st)); XB_CUDA(fx.up(st)); XB_CUDA(fxp.up(st)); XB_CUDA(fref.up(st)); XB_CUDA(fsind.up(st));
     XB_CUDA(nfeat.up(st)); XB_CUDA(Phi.up(st)); XB_CUDA(Pmm.up(st)); XB_CUDA(active.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
     if (int rc = launch_cov_propagate(st, N, dP, Phi.d, Pmm.d, active.d, B)) return rc;
@@ -459,20 +522,24 @@ class Batch {
     XB_CUDA(mh.down(st));
     XB_CUDA(cudaStreamSynchronize(st));
     // ---- gating decisions (host), post-gate edits, update (device) ----
-    for (int b = 0; b < B; ++b) nsel.h[b] = 0;
-    for (int b : full) {
-      Estimator& e = *est[b];
-      const std::vector<Feature*> order = e.instate_features;  // index space of mh / the device feature table
-      e.update_step_after_gate(mh.h + (size_t)b * lay.F);
-      if (e.error) return fail(e.error, e.error_msg);
-      int k = 0;
-      for (Feature* f : e.in_update) {
-        const auto it = std::find(order.begin(), order.end(), f);
-        sel.h[(size_t)b * lay.F + k++] = (int)(it - order.begin());
-      }
-      nsel.h[b] = k;
+    {
+      HostScope hs("gating");
+      for (int b = 0; b < B; ++b) nsel.h[b] = 0;
+      pfor(full, [&](int b, int) {
+        Estimator& e = *est[b];
+        const std::vector<Feature*> order = e.instate_features;  // index space of mh / the device feature table
+        e.update_step_after_gate(mh.h + (size_t)b * lay.F);
+        if (e.error) return;
+        int k = 0;
+        for (Feature* f : e.in_update) {
+          const auto it = std::find(order.begin(), order.end(), f);
+          sel.h[(size_t)b * lay.F + k++] = (int)(it - order.begin());
+        }
+        nsel.h[b] = k;
+      });
+      if (int rc = first_error(full)) return rc;
+      if (int rc = stage_edits(full)) return rc;
     }
-    if (int rc = stage_edits(full)) return rc;
     XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st)); XB_CUDA(sel.up(st)); XB_CUDA(nsel.up(st));
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
     if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B)) return rc;
@@ -485,32 +552,39 @@ class Batch {
     XB_CUDA(pack.down(st));
     XB_CUDA(cudaStreamSynchronize(st));
     Prof::get().collect();
-    for (int b : full) {
-      Estimator& e = *est[b];
-      const double* pk = pack.h + (size_t)b * (2 * N + 529);
-      for (int i = 0; i < N; ++i)
-        if (nsel.h[b] && !(pk[i] == pk[i])) return fail(XIVO_ERR_STATE, "innovation covariance not positive definite");
-      e.update_step_after_update(pk, pk + N, pk + N + 529, nsel.h[b] > 0);
-      if (e.error) return fail(e.error, e.error_msg);
+    std::atomic<int> notpd{0};
+    {
+      HostScope hs("absorb_and_manage");
+      pfor(full, [&](int b, int) {
+        Estimator& e = *est[b];
+        const double* pk = pack.h + (size_t)b * (2 * N + 529);
+        for (int i = 0; i < N; ++i)
+          if (nsel.h[b] && !(pk[i] == pk[i])) { notpd = 1; return; }
+        e.update_step_after_update(pk, pk + N, pk + N + 529, nsel.h[b] > 0);
+      });
     }
-    return 0;
+    if (notpd) return fail(XIVO_ERR_STATE, "innovation covariance not positive definite");
+    return first_error(full);
   }
 
   // Push one message per sequence, then execute whatever each heap releases (MaintainBuffer).
   int ingest(std::vector<Msg>& in) {
-    for (int b = 0; b < B; ++b) est[b]->push(std::move(in[b]));
-    std::vector<int> vis;
-    std::vector<Msg> vmsgs;
-    for (int b = 0; b < B; ++b) {
-      Msg m;
-      if (!est[b]->pop_ready(&m)) continue;
-      if (m.type == 0) {
-        est[b]->inertial_internal(m.ts, m.gyro, m.accel);
-      } else {
-        vis.push_back(b);
-        vmsgs.push_back(std::move(m));
-      }
+    std::vector<int> all(B), vis;
+    std::vector<Msg> popped(B), vmsgs;
+    std::vector<char> has(B, 0);
+    for (int b = 0; b < B; ++b) all[b] = b;
+    {
+      HostScope hs("ingest_imu");
+      pfor(all, [&](int b, int) {
+        est[b]->push(std::move(in[b]));
+        Msg m;
+        if (!est[b]->pop_ready(&m)) return;
+        if (m.type == 0) est[b]->inertial_internal(m.ts, m.gyro, m.accel);
+        else { popped[b] = std::move(m); has[b] = 1; }
+      });
     }
+    for (int b = 0; b < B; ++b)
+      if (has[b]) { vis.push_back(b); vmsgs.push_back(std::move(popped[b])); }
     if (vis.empty()) return 0;
     return process_visual(vis, vmsgs);
   }

@@ -56,6 +56,12 @@ class Prof {
     }
     pending_.clear();
   }
+  void add_host(const char* name, double ms) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto& e = acc_[std::string("host:") + name];
+    e.calls++;
+    e.ms += ms;
+  }
   void add_work(const char* name, double w) {
     if (!enabled.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(mu_);
