@@ -110,6 +110,8 @@ def make_streams(cfg, n_streams, n_frames):
 
 
 def run_ours(args):
+    os.environ.setdefault("OMP_WAIT_POLICY", "ACTIVE")  # keep the host team spinning between phases
+    os.environ.setdefault("GOMP_SPINCOUNT", "100000000")
     import torch
 
     from xivo_b200 import capi, pyxivo
@@ -157,13 +159,14 @@ def run_ours(args):
     idx = np.array(seq_stream)
 
     def step(f, device_resident):
-        for j in range(IMU_PER_FRAME):
-            k = f * IMU_PER_FRAME + j
-            bt.inertial_meas(imu_ts[idx, k], imu_g[idx, k], imu_a[idx, k])
+        ks = slice(f * IMU_PER_FRAME, (f + 1) * IMU_PER_FRAME)
+        its = np.ascontiguousarray(imu_ts[idx, ks].T)            # (8, B)
+        ig = np.ascontiguousarray(imu_g[idx, ks].transpose(1, 0, 2))  # (8, B, 3)
+        ia = np.ascontiguousarray(imu_a[idx, ks].transpose(1, 0, 2))
         ts = np.full(B, f * FRAME_NS, dtype=np.uint64)
         ptrs = (C.c_void_p * B)(*[(dev_ptr if device_resident else host_ptr)[s][f] for s in seq_stream])
-        fn = L.xivo_batch_visual_meas_device if device_resident else L.xivo_batch_visual_meas
-        rc = fn(bt._h, ts.ctypes.data_as(C.c_void_p), ptrs, ROWS, COLS, 1, 0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = L.xivo_batch_step(bt._h, IMU_PER_FRAME, vp(its), vp(ig), vp(ia), vp(ts), ptrs, ROWS, COLS, 1, int(device_resident))
         if rc != 0:
             raise RuntimeError(L.xivo_last_error().decode())
         return bt.gsb(0)  # host read of the step's result (pose); the err/P_mm D2H happened inside the call

@@ -50,6 +50,13 @@ int xivo_batch_visual_meas(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* 
 int xivo_batch_visual_meas_device(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs_dev, int rows, int cols,
                                   int channels, int tracker_only);
 
+/* One lock-step "frame step": n_imu InertialMeas calls followed by one VisualMeas call per sequence,
+ * with exactly the semantics of issuing them one by one (same message heap), in a single call so that
+ * the per-call overhead is paid once.  imu_ts: n_imu x n_seq, gyro/accel: n_imu x n_seq x 3.
+ * on_device != 0: imgs are device pointers. */
+int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const double* gyro, const double* accel,
+                    const uint64_t* frame_ts, const uint8_t* const* imgs, int rows, int cols, int channels, int on_device);
+
 /* Per-kernel CUDA-event timing + host<->device byte counters (bench.py's roofline / e2e fields). */
 void xivo_profile_enable(int on);
 void xivo_profile_reset(void);

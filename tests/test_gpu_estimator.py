@@ -142,3 +142,30 @@ def test_tracker_only_mode():
             assert ids.tolist() == [f.id for f in ref.tracks]
     assert len(ref.tracks) > 50
     b.close()
+
+
+def test_step_call_equals_message_by_message():
+    """xivo_batch_step (8 IMU + 1 frame per call) must be bit-identical to issuing the messages one by one."""
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    cfg["camera_cfg"].update(rows=240, cols=320, fx=137.5, fy=137.5, cx=160, cy=120)
+    cfg["tracker_cfg"].update(num_features_min=60, num_features_max=80)
+    msgs, _ = sim.image_stream(cfg, duration=1.2, seed=4)
+    a = pyxivo.Batch(cfg, n_seq=2, max_groups=4, max_features=14)
+    b = pyxivo.Batch(cfg, n_seq=2, max_groups=4, max_features=14)
+    imu = [m for m in msgs if m[0] == "imu"]
+    frames = [m for m in msgs if m[0] == "img"]
+    for f, (_, fts, img) in enumerate(frames):
+        chunk = imu[8 * f : 8 * f + 8]
+        if len(chunk) < 8:
+            break
+        for _, ts, p in chunk:
+            a.inertial_meas(ts, p[0], p[1])
+        a.visual_meas(fts, [img, img])
+        b.step([ts for _, ts, _ in chunk], [p[0] for _, _, p in chunk], [p[1] for _, _, p in chunk], fts, [img, img])
+        for s in range(2):
+            assert np.array_equal(a.gsb(s), b.gsb(s))
+            assert a.tracked_features(s)[0].tolist() == b.tracked_features(s)[0].tolist()
+    assert np.array_equal(a.P(0), b.P(0))
+    assert a.counters(0)["num_instate_features"] > 0
+    a.close()
+    b.close()

@@ -233,18 +233,27 @@ class Batch {
 
   // Tracker::DetectLK's selection (tracker.cpp:224-229, :295-328) from the packed keypoints of one sequence.
   void detect_select(Estimator& e, const unsigned* kps, int n, int num_to_add) {
-    // runByPixelsMask, then order (score desc, y asc, x asc): bucket by score, sort buckets lazily
-    std::vector<unsigned> bucket[256];
+    // runByPixelsMask, then order (score desc, y asc, x asc): counting sort by score into one reusable
+    // array, each score bucket sorted lazily (the greedy pick usually stops in the first few buckets).
+    static thread_local std::vector<unsigned> sorted;
+    int cnt[257] = {0};
     for (int i = 0; i < n; ++i) {
       const unsigned k = kps[i];
-      const int x = (k >> 8) & 0xfff, y = k >> 20;
-      if (e.mask[(size_t)y * e.cols + x]) bucket[k & 0xff].push_back(k);
+      if (e.mask[(size_t)(k >> 20) * e.cols + ((k >> 8) & 0xfff)]) cnt[(k & 0xff) + 1]++;
+    }
+    for (int s = 0; s < 256; ++s) cnt[s + 1] += cnt[s];  // cnt[s] = start of bucket s
+    sorted.resize(cnt[256]);
+    int cursor[256];
+    for (int s = 0; s < 256; ++s) cursor[s] = cnt[s];
+    for (int i = 0; i < n; ++i) {
+      const unsigned k = kps[i];
+      if (e.mask[(size_t)(k >> 20) * e.cols + ((k >> 8) & 0xfff)]) sorted[cursor[k & 0xff]++] = k;
     }
     for (int s = 255; s >= 0; --s) {
-      auto& v = bucket[s];
-      if (v.empty()) continue;
-      std::sort(v.begin(), v.end());  // packed (y, x, score) ascending == (y, x) ascending within a score
-      for (unsigned k : v) {
+      if (cnt[s + 1] == cnt[s]) continue;
+      std::sort(sorted.begin() + cnt[s], sorted.begin() + cnt[s + 1]);  // packed (y, x, score): (y, x) ascending within a score
+      for (int i = cnt[s]; i < cnt[s + 1]; ++i) {
+        const unsigned k = sorted[i];
         const double x = (k >> 8) & 0xfff, y = k >> 20;
         if (e.mask_valid(x, y)) {
           Feature* f = e.create_feature(x, y);
@@ -567,6 +576,38 @@ class Batch {
     return first_error(full);
   }
 
+  // Several messages per sequence in one call (same semantics as pushing them one by one): every
+  // sequence runs ahead through its IMU messages until its heap releases a visual message; those are
+  // then processed together, and the loop continues with the remaining messages.
+  int ingest_many(std::vector<std::vector<Msg>>& in) {
+    std::vector<int> all(B), vis;
+    std::vector<size_t> pos(B, 0);
+    std::vector<Msg> popped(B), vmsgs;
+    std::vector<char> has(B, 0);
+    for (int b = 0; b < B; ++b) all[b] = b;
+    for (;;) {
+      {
+        HostScope hs("ingest_imu");
+        pfor(all, [&](int b, int) {
+          has[b] = 0;
+          while (pos[b] < in[b].size()) {
+            est[b]->push(std::move(in[b][pos[b]++]));
+            Msg m;
+            if (!est[b]->pop_ready(&m)) continue;
+            if (m.type == 0) est[b]->inertial_internal(m.ts, m.gyro, m.accel);
+            else { popped[b] = std::move(m); has[b] = 1; return; }
+          }
+        });
+      }
+      vis.clear();
+      vmsgs.clear();
+      for (int b = 0; b < B; ++b)
+        if (has[b]) { vis.push_back(b); vmsgs.push_back(std::move(popped[b])); }
+      if (vis.empty()) return 0;
+      if (int rc = process_visual(vis, vmsgs)) return rc;
+    }
+  }
+
   // Push one message per sequence, then execute whatever each heap releases (MaintainBuffer).
   int ingest(std::vector<Msg>& in) {
     std::vector<int> all(B), vis;
@@ -680,6 +721,37 @@ int xivo_batch_visual_meas_device(xivo_batch* b, const uint64_t* ts_ns, const ui
                                   int channels, int tracker_only) {
   return visual_meas_impl(b, ts_ns, imgs_dev, rows, cols, channels, tracker_only, true);
 }
+int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const double* gyro, const double* accel, const uint64_t* frame_ts,
+                    const uint8_t* const* imgs, int rows, int cols, int channels, int on_device) {
+  BATCH_BEGIN;
+  XB_REQUIRE(n_imu >= 0 && frame_ts && imgs && (n_imu == 0 || (imu_ts && gyro && accel)), "batch_step: bad arguments");
+  if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
+  const size_t ib = (size_t)rows * cols * channels;
+  const int nb = B_.B;
+  std::vector<std::vector<Msg>> in(nb);
+  for (int s = 0; s < nb; ++s) {
+    XB_REQUIRE(imgs[s], "batch_step: null image");
+    in[s].resize(n_imu + 1);
+    for (int k = 0; k < n_imu; ++k) {
+      Msg& m = in[s][k];
+      m.ts = imu_ts[(size_t)k * nb + s];
+      m.type = 0;
+      memcpy(m.gyro, gyro + ((size_t)k * nb + s) * 3, 24);
+      memcpy(m.accel, accel + ((size_t)k * nb + s) * 3, 24);
+    }
+    const int slot = B_.ring_next[s];
+    B_.ring_next[s] = (slot + 1) % B_.ring_n;
+    if (!on_device) Prof::get().h2d += ib;
+    XB_CUDA(cudaMemcpyAsync(B_.dRing + ((size_t)s * B_.ring_n + slot) * ib, imgs[s], ib,
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, B_.ctx->stream));
+    Msg& v = in[s][n_imu];
+    v.ts = frame_ts[s];
+    v.type = 1;
+    v.img_slot = slot;
+  }
+  return B_.ingest_many(in);
+}
+
 void xivo_profile_enable(int on) { Prof::get().enabled = on != 0; }
 void xivo_profile_reset(void) { Prof::get().reset(); }
 int xivo_profile_report(char* buf, int n) {

@@ -93,6 +93,24 @@ class Batch:
         self._keep = imgs
         _check(capi.lib().xivo_batch_visual_meas(self._h, _p(ts), ptrs, rows, cols, ch, int(bool(tracker_only))), "xivo_batch_visual_meas")
 
+    def step(self, imu_ts, gyro, accel, frame_ts, imgs):
+        """n_imu InertialMeas + one VisualMeas per sequence in one call (xivo_batch_step).
+        imu_ts: (n_imu, n) or (n_imu,), gyro/accel: (n_imu, n, 3) or (n_imu, 3)."""
+        if isinstance(imgs, np.ndarray):
+            imgs = [imgs] * self.n
+        imgs = [np.ascontiguousarray(i, dtype=np.uint8) for i in imgs]
+        rows, cols = imgs[0].shape[:2]
+        ch = 1 if imgs[0].ndim == 2 else imgs[0].shape[2]
+        its = np.asarray(imu_ts, dtype=np.uint64)
+        n_imu = its.shape[0]
+        its = np.ascontiguousarray(np.broadcast_to(its.reshape(n_imu, -1), (n_imu, self.n)))
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gyro, dtype=np.float64).reshape(n_imu, -1, 3), (n_imu, self.n, 3)))
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(accel, dtype=np.float64).reshape(n_imu, -1, 3), (n_imu, self.n, 3)))
+        fts = np.ascontiguousarray(np.broadcast_to(np.asarray(frame_ts, dtype=np.uint64), (self.n,)))
+        ptrs = (C.c_void_p * self.n)(*[i.ctypes.data for i in imgs])
+        self._keep = imgs
+        _check(capi.lib().xivo_batch_step(self._h, n_imu, _p(its), _p(g), _p(a), _p(fts), ptrs, rows, cols, ch, 0), "xivo_batch_step")
+
     def visual_meas_pointcloud(self, ts_ns, ids, xp_depth, tracker_only=False):
         """ids / xp_depth: lists of per-sequence arrays, or single arrays shared by all."""
         if isinstance(ids, np.ndarray):
