@@ -270,6 +270,9 @@ class Estimator {
   bool mask_valid(double x, double y) const;
 
  private:
+  struct IntegratorScratch {
+    double FK[7][207], PK[7][529], P0[529], A[207], acc[529], Fd[207], T9[207];
+  } scratch_;
   std::vector<Msg> buf_;
   bool buf_initialized_ = false;
   uint64_t seqno_ = 0;
