@@ -143,33 +143,52 @@ def run_ours(args):
     fbytes = ROWS * COLS
     host_ptr = [[hnp[s, f].ctypes.data for f in range(n_frames)] for s in range(S)]
     dev_ptr = [[dev.data_ptr() + (s * n_frames + f) * fbytes for f in range(n_frames)] for s in range(S)]
-    seq_stream = [(b + rank) % S for b in range(B)]
+    from xivo_b200 import replicas
+
+    seq_stream = replicas.assign_streams(rank, world, B, S)
     # IMU arrays per step: (B,3)
     imu_ts = np.array([[ts for ts, _ in streams[s][1]] for s in range(S)], dtype=np.uint64)
     imu_g = np.array([[p[0] for _, p in streams[s][1]] for s in range(S)])
     imu_a = np.array([[p[1] for _, p in streams[s][1]] for s in range(S)])
 
-    ctx = capi.Context(local)
-    bt = pyxivo.Batch(cfg, n_seq=B, max_groups=G, max_features=F, ctx=ctx)
+    # NB independent batches per GPU, each with its own stream and driven by its own host thread
+    # (ctypes releases the GIL): the host phases of one batch overlap the kernels of the others.
+    NB = max(1, min(args.batches, B))
+    sizes = [B // NB + (1 if i < B % NB else 0) for i in range(NB)]
     L = capi.lib()
     import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
 
     L.xivo_ctx_stream.restype = C.c_void_p
-    ext = torch.cuda.ExternalStream(L.xivo_ctx_stream(ctx._h))
-    idx = np.array(seq_stream)
+    ctxs, bts, exts, idxs = [], [], [], []
+    o = 0
+    for nb in sizes:
+        c = capi.Context(local)
+        ctxs.append(c)
+        bts.append(pyxivo.Batch(cfg, n_seq=nb, max_groups=G, max_features=F, ctx=c))
+        exts.append(torch.cuda.ExternalStream(L.xivo_ctx_stream(c._h)))
+        idxs.append(np.array(seq_stream[o : o + nb]))
+        o += nb
+    pool = ThreadPoolExecutor(NB)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
 
-    def step(f, device_resident):
+    def step_one(i, f, device_resident):
+        idx, nb = idxs[i], sizes[i]
         ks = slice(f * IMU_PER_FRAME, (f + 1) * IMU_PER_FRAME)
-        its = np.ascontiguousarray(imu_ts[idx, ks].T)            # (8, B)
-        ig = np.ascontiguousarray(imu_g[idx, ks].transpose(1, 0, 2))  # (8, B, 3)
+        its = np.ascontiguousarray(imu_ts[idx, ks].T)                 # (8, nb)
+        ig = np.ascontiguousarray(imu_g[idx, ks].transpose(1, 0, 2))  # (8, nb, 3)
         ia = np.ascontiguousarray(imu_a[idx, ks].transpose(1, 0, 2))
-        ts = np.full(B, f * FRAME_NS, dtype=np.uint64)
-        ptrs = (C.c_void_p * B)(*[(dev_ptr if device_resident else host_ptr)[s][f] for s in seq_stream])
-        vp = lambda a: a.ctypes.data_as(C.c_void_p)
-        rc = L.xivo_batch_step(bt._h, IMU_PER_FRAME, vp(its), vp(ig), vp(ia), vp(ts), ptrs, ROWS, COLS, 1, int(device_resident))
+        ts = np.full(nb, f * FRAME_NS, dtype=np.uint64)
+        ptrs = (C.c_void_p * nb)(*[(dev_ptr if device_resident else host_ptr)[s][f] for s in idx])
+        rc = L.xivo_batch_step(bts[i]._h, IMU_PER_FRAME, vp(its), vp(ig), vp(ia), vp(ts), ptrs, ROWS, COLS, 1, int(device_resident))
         if rc != 0:
             raise RuntimeError(L.xivo_last_error().decode())
-        return bt.gsb(0)  # host read of the step's result (pose); the err/P_mm D2H happened inside the call
+        return bts[i].gsb(0)  # host read of the step's result (pose); the err/P_mm D2H happened inside the call
+
+    def step(f, device_resident):
+        if NB == 1:
+            return [step_one(0, f, device_resident)]
+        return list(pool.map(lambda i: step_one(i, f, device_resident), range(NB)))
 
     def barrier():
         torch.cuda.synchronize()
@@ -183,7 +202,7 @@ def run_ours(args):
     for _ in range(PREROLL_FRAMES):
         step(f, True)
         f += 1
-    log("preroll done", bt.counters(0))
+    log("preroll done", bts[0].counters(0))
 
     def timed(device_resident, profile):
         nonlocal f
@@ -196,29 +215,27 @@ def run_ours(args):
         clk = ClockSampler(local)
         barrier()
         clk.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(NB)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(NB)]
         t0 = time.perf_counter()
-        e0.record(ext)
+        for i in range(NB):
+            e0[i].record(exts[i])
         ntracked = 0
         for _ in range(K):
             step(f, device_resident)
-            ntracked += bt.counters(0)["num_tracked"]
+            ntracked += bts[0].counters(0)["num_tracked"]
             f += 1
-        e1.record(ext)
+        for i in range(NB):
+            e1[i].record(exts[i])
         barrier()
         wall = time.perf_counter() - t0
         clocks = clk.stop()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0[0].elapsed_time(e1[i]) for i in range(NB))  # first start -> last end, on the launch streams
         L.xivo_profile_enable(0)
         buf = C.create_string_buffer(1 << 16)
         L.xivo_profile_report(buf, len(buf))
         prof = json.loads(buf.value.decode())
-        if world > 1:
-            import torch.distributed as dist
-
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = replicas.max_over_ranks(ms, device="cuda")
         return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked / K)
 
     r_dev = timed(True, True)
@@ -266,7 +283,7 @@ def run_ours(args):
         out = dict(metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=W,
                    ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                    config=dict(workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
-                               sequences_per_gpu=B, distinct_streams=S, frames_per_step=world * B, channels=1,
+                               sequences_per_gpu=B, batches_per_gpu=NB, host_threads_per_batch=int(os.environ.get("XIVO_THREADS", "0")) or None, distinct_streams=S, frames_per_step=world * B, channels=1,
                                l2_policy="inputs larger than L2 are not needed: every step reads a new frame set (B x 307 KB) from the stream buffers; covariance/pyramids are the resident state by design",
                                message_buffer_size=cfg.get("message_buffer_size", 10)),
                    e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * fbytes,
@@ -274,7 +291,9 @@ def run_ours(args):
                    gpu_launches=r_dev["launches"], clocks=r_dev["clocks"], roofline=roofline, cpu_baseline=cpu,
                    tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K, host_phase_ms_per_step=host_phases)
         print(json.dumps(out))
-    bt.close()
+    pool.shutdown()
+    for b_ in bts:
+        b_.close()
     if world > 1:
         import torch.distributed as dist
 
@@ -311,6 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=32, help="independent sequences per GPU (lock-step batch)")
+    ap.add_argument("--batches", type=int, default=4, help="independent lock-step batches per GPU, one host thread each")
     ap.add_argument("--streams", type=int, default=4, help="distinct synthetic input streams shared by the sequences")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

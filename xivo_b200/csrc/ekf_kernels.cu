@@ -332,7 +332,7 @@ int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const 
   const size_t smem = gain_smem(Mmax, true);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: 2*F too large for the shared-memory Cholesky");
   XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int pi_ = Prof::get().start("ekf_gain", st);
+  ProfRec* pi_ = Prof::get().start("ekf_gain", st);
   ekf_gain_kernel<true><<<batch, GAIN_THREADS, smem, st>>>(N, lay, jac, sel, nsel, 0, nullptr, nullptr, nullptr, Rmeas, P, err, HP,
                                                           Kt, H_dense, Mmax);
   Prof::get().stop(pi_, st);

@@ -1,11 +1,14 @@
-// Optional per-kernel timing with CUDA events on the launching stream, and H2D/D2H byte counters.
-// bench.py turns it on for the timed region: roofline.achieved must come from event durations
-// measured live there, not from a profiler run.
+// Optional per-kernel timing with CUDA events on the launching stream, host phase timers and
+// H2D/D2H byte counters.  bench.py turns it on for the timed region: roofline.achieved must come from
+// event durations measured live there, not from a profiler run.  Safe with several batches driving
+// different streams from different host threads.
 #pragma once
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdio>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -16,6 +19,11 @@ struct ProfEntry {
   double ms = 0;
   double work = 0;  // algorithmic bytes or flops attributed by the host at the launch site
 };
+struct ProfRec {
+  std::string name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool armed = false;
+};
 class Prof {
  public:
   static Prof& get() {
@@ -24,37 +32,48 @@ class Prof {
   }
   std::atomic<bool> enabled{false};
   std::atomic<unsigned long long> h2d{0}, d2h{0};
-  // record start; returns an index to pass to stop()
-  int start(const char* name, cudaStream_t st) {
-    if (!enabled.load(std::memory_order_relaxed)) return -1;
+  ProfRec* start(const char* name, cudaStream_t st) {
+    if (!enabled.load(std::memory_order_relaxed)) return nullptr;
+    std::unique_ptr<ProfRec> r(new ProfRec());
+    r->name = name;
+    cudaEventCreate(&r->a);
+    cudaEventCreate(&r->b);
+    cudaEventRecord(r->a, st);
+    ProfRec* p = r.get();
     std::lock_guard<std::mutex> lk(mu_);
-    Rec r;
-    r.name = name;
-    cudaEventCreate(&r.a);
-    cudaEventCreate(&r.b);
-    cudaEventRecord(r.a, st);
-    pending_.push_back(r);
-    return (int)pending_.size() - 1;
+    pending_.push_back(std::move(r));
+    return p;
   }
-  void stop(int idx, cudaStream_t st) {
-    if (idx < 0) return;
+  void stop(ProfRec* r, cudaStream_t st) {
+    if (!r) return;
+    cudaEventRecord(r->b, st);
     std::lock_guard<std::mutex> lk(mu_);
-    cudaEventRecord(pending_[idx].b, st);
+    r->armed = true;
   }
-  // call after the stream has been synchronised
-  void collect() {
+  // harvest every finished record (records of other streams still in flight stay pending)
+  void collect(bool wait = false) {
     std::lock_guard<std::mutex> lk(mu_);
+    std::vector<std::unique_ptr<ProfRec>> keep;
     for (auto& r : pending_) {
+      if (!r->armed) {
+        keep.push_back(std::move(r));
+        continue;
+      }
+      if (wait) cudaEventSynchronize(r->b);
+      if (cudaEventQuery(r->b) != cudaSuccess) {
+        keep.push_back(std::move(r));
+        continue;
+      }
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
-        auto& e = acc_[r.name];
+      if (cudaEventElapsedTime(&ms, r->a, r->b) == cudaSuccess) {
+        auto& e = acc_[r->name];
         e.calls++;
         e.ms += ms;
       }
-      cudaEventDestroy(r.a);
-      cudaEventDestroy(r.b);
+      cudaEventDestroy(r->a);
+      cudaEventDestroy(r->b);
     }
-    pending_.clear();
+    pending_.swap(keep);
   }
   void add_host(const char* name, double ms) {
     std::lock_guard<std::mutex> lk(mu_);
@@ -68,21 +87,21 @@ class Prof {
     acc_[name].work += w;
   }
   void reset() {
-    collect();
+    collect(true);
     std::lock_guard<std::mutex> lk(mu_);
     acc_.clear();
     h2d = 0;
     d2h = 0;
   }
   std::string json() {
-    collect();
+    collect(true);
     std::lock_guard<std::mutex> lk(mu_);
     std::string s = "{";
     bool first = true;
     for (auto& kv : acc_) {
       char buf[256];
-      snprintf(buf, sizeof(buf), "%s\"%s\": {\"calls\": %llu, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ", kv.first.c_str(), kv.second.calls, kv.second.ms,
-               kv.second.work);
+      snprintf(buf, sizeof(buf), "%s\"%s\": {\"calls\": %llu, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ", kv.first.c_str(), kv.second.calls,
+               kv.second.ms, kv.second.work);
       s += buf;
       first = false;
     }
@@ -92,19 +111,15 @@ class Prof {
   }
 
  private:
-  struct Rec {
-    std::string name;
-    cudaEvent_t a, b;
-  };
   std::mutex mu_;
-  std::vector<Rec> pending_;
+  std::vector<std::unique_ptr<ProfRec>> pending_;
   std::map<std::string, ProfEntry> acc_;
 };
 
 struct ProfScope {
-  int idx;
+  ProfRec* rec;
   cudaStream_t st;
-  ProfScope(const char* name, cudaStream_t s) : idx(Prof::get().start(name, s)), st(s) {}
-  ~ProfScope() { Prof::get().stop(idx, st); }
+  ProfScope(const char* name, cudaStream_t s) : rec(Prof::get().start(name, s)), st(s) {}
+  ~ProfScope() { Prof::get().stop(rec, st); }
 };
 }  // namespace xb
