@@ -186,3 +186,38 @@ def test_oos_projection_invariants(ctx, k):
         assert np.abs(Hp[f].T @ Hp[f] - rHp.T @ rHp).max() <= 1e-8 * np.abs(rHp.T @ rHp).max()
         assert np.abs(Hp[f].T @ ip[f] - rHp.T @ rip).max() <= 1e-8 * max(1.0, np.abs(rHp.T @ rip).max())
         assert abs(ip[f] @ ip[f] - rip @ rip) <= 1e-8 * (rip @ rip)
+
+
+@pytest.mark.parametrize("method", ["PrinceDormand", "RK4"])
+def test_imu_propagate_matches_oracle(ctx, method):
+    """Device integrator vs the numpy restatement of Propagate + PrinceDormand/RK4 (fp64, 1e-10)."""
+    rng = np.random.default_rng(7)
+    lay = E.Layout(4, 14)
+    N = lay.N
+    A = rng.normal(size=(N, N))
+    scale = np.exp(rng.uniform(-4, 0, N))
+    P = (A @ A.T / N + np.eye(N)) * np.outer(scale, scale)
+    P = 0.5 * (P + P.T)
+    X = E.MotionState(synth.random_rotation(rng, 0.3), rng.normal(0, 1, 3), rng.normal(0, 0.5, 3), rng.normal(0, 0.01, 3), rng.normal(0, 0.05, 3),
+                      np.eye(3), np.zeros(3), synth.random_rotation(rng, 0.02))
+    Cg = np.eye(3) + 0.01 * rng.normal(size=(3, 3))
+    Ca = np.eye(3) + 0.01 * rng.normal(size=(3, 3))
+    g = np.array([0.0, 0.0, -9.8])
+    qimu = np.array([2.5e-5] * 3 + [2.5e-3] * 3 + [1e-8] * 3 + [1e-7] * 3)
+    qmodel = np.zeros(23)
+    qmodel[0:3], qmodel[15:18], qmodel[21:23] = 1e-4, 1e-6, 1e-7
+    segs = []
+    Pr, Xr = P.copy(), X.copy()
+    for k in range(9):
+        gyro0, accel0 = rng.normal(0, 0.2, 3), np.array([0.0, 0.0, 9.8]) + rng.normal(0, 0.5, 3)
+        sg, sa = rng.normal(0, 2.0, 3), rng.normal(0, 5.0, 3)
+        dt = [0.005, 0.0025, 0.0071, 0.04][k % 4]
+        segs.append(np.concatenate([gyro0, accel0, sg, sa, [dt]]))
+        Phi, Pmm = E.integrate(method, Xr, Pr[:23, :23].copy(), gyro0, accel0, sg, sa, dt, Cg, Ca, g, np.diag(qimu), 0.002)
+        E.apply_propagation(Pr, Phi, Pmm, np.diag(qmodel))
+    X30 = np.concatenate([X.Rsb.ravel(), X.Tsb, X.Vsb, X.bg, X.ba, X.Rsg.ravel()])
+    Pg, Xg = ctx.imu_propagate(P, X30, segs, Cg, Ca, g, qimu, qmodel, 0.002, method == "PrinceDormand")
+    Xref = np.concatenate([Xr.Rsb.ravel(), Xr.Tsb, Xr.Vsb, Xr.bg, Xr.ba, Xr.Rsg.ravel()])
+    assert np.abs(Xg - Xref).max() <= 1e-10 * max(1.0, np.abs(Xref).max())
+    assert np.abs(Pg - Pr).max() <= 1e-10 * np.abs(Pr).max()
+    assert np.abs(Pg - Pg.T).max() <= 1e-13 * np.abs(Pg).max()

@@ -15,6 +15,19 @@
 #include "estimator.h"
 #include "prof.h"
 
+namespace xb {
+// Host wall-clock phases go into the same profile report as the kernels ("host:<phase>").
+struct HostScope {
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  explicit HostScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~HostScope() {
+    if (!Prof::get().enabled.load(std::memory_order_relaxed)) return;
+    Prof::get().add_host(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+}  // namespace xb
+
 #include "estimator_host.cpp.inc"
 
 namespace xb {
@@ -46,17 +59,6 @@ struct Mirror {
   cudaError_t down(cudaStream_t st, size_t count = 0, size_t off = 0) {
     Prof::get().d2h += (count ? count : n) * sizeof(T);
     return cudaMemcpyAsync(h + off, d + off, (count ? count : n) * sizeof(T), cudaMemcpyDeviceToHost, st);
-  }
-};
-
-// Host wall-clock phases go into the same profile report as the kernels ("host:<phase>").
-struct HostScope {
-  const char* name;
-  std::chrono::steady_clock::time_point t0;
-  explicit HostScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
-  ~HostScope() {
-    if (!Prof::get().enabled.load(std::memory_order_relaxed)) return;
-    Prof::get().add_host(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   }
 };
 
@@ -95,6 +97,10 @@ class Batch {
   Mirror<EditOp> ops;
   Mirror<SubfilterIn> sub_in;
   Mirror<SubfilterOut> sub_out;
+  Mirror<ImuSegment> segs;
+  Mirror<int> nsegs;
+  Mirror<ImuConst> icst;
+  Mirror<double> Xm;
   // tracker device state (allocated at the first image)
   bool img_ready = false;
   int rows = 0, cols = 0, cn = 0, ring_n = 0, max_pts = 0, max_kp = 0;
@@ -130,7 +136,8 @@ class Batch {
          Pmm.alloc((size_t)B * 529) && mh.alloc((size_t)B * lay.F) && pack.alloc((size_t)B * (2 * N + 529)) &&
          fref.alloc((size_t)B * lay.F) && fsind.alloc((size_t)B * lay.F) && nfeat.alloc(B) && sel.alloc((size_t)B * lay.F) &&
          nsel.alloc(B) && nops.alloc(B) && active.alloc(B) && ops.alloc((size_t)B * maxops) &&
-         sub_in.alloc((size_t)B * max_sub) && sub_out.alloc((size_t)B * max_sub);
+         sub_in.alloc((size_t)B * max_sub) && sub_out.alloc((size_t)B * max_sub) && segs.alloc((size_t)B * kMaxSegments) && nsegs.alloc(B) &&
+         icst.alloc(B) && Xm.alloc((size_t)B * kMotionDoubles);
     if (!ok) throw std::runtime_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     // initial covariance: identity with the motion block from the config (estimator.cpp:258-302)
     std::vector<double> P0((size_t)N * N, 0.0);
@@ -141,10 +148,21 @@ class Batch {
       cudaMemcpy(dP + (size_t)b * N * N, P0.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice);
       cam.h[b] = est[b]->cam;
       R.h[b] = est[b]->c.R;
+      {
+        const EstimatorCfg& ec = est[b]->c;
+        ImuConst& ic = icst.h[b];
+        memcpy(ic.Cg, ec.Cg.m, 72); memcpy(ic.Ca, ec.Ca.m, 72); memcpy(ic.g, ec.g.v, 24);
+        for (int i = 0; i < 12; ++i) ic.qimu[i] = ec.Qimu[i * 12 + i];
+        for (int i = 0; i < 23; ++i) ic.qmodel[i] = ec.Qmodel[i * 23 + i];
+        ic.pd = ec.integration_method == "PrinceDormand" ? 1 : 0;
+        ic.h0 = ic.pd ? ec.pd_stepsize : ec.rk4_stepsize;
+        ic.pad = 0;
+      }
       for (int i = 0; i < N; ++i) est[b]->diagP[i] = P0[(size_t)i * N + i];
     }
     cam.up(ctx->stream);
     R.up(ctx->stream);
+    icst.up(ctx->stream);
     cudaStreamSynchronize(ctx->stream);
   }
   ~Batch() {
@@ -153,7 +171,8 @@ class Batch {
       if (p) cudaFree(p);
     cam.release(); X.release(); groups.release(); fx.release(); fxp.release(); R.release(); Phi.release(); Pmm.release();
     mh.release(); pack.release(); fref.release(); fsind.release(); nfeat.release(); sel.release(); nsel.release();
-    nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); off_prev.release();
+    nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); segs.release(); nsegs.release();
+    icst.release(); Xm.release(); off_prev.release();
     off_cur.release(); pts0.release(); pts1.release(); lkerr.release(); lkst.release(); npts.release(); kpcount.release();
     kp.release();
   }
@@ -176,27 +195,48 @@ class Batch {
     }
     return 0;
   }
-  void stage_propagation(const std::vector<int>& act) {
-    for (int b = 0; b < B; ++b) active.h[b] = 0;
+  // Run the queued Propagate calls of the given sequences on the device (imu_integrate_kernel) and
+  // bring the propagated nominal state back.  One launch + one sync for all of them.
+  int integrate(const std::vector<int>& act) {
+    cudaStream_t st = ctx->stream;
+    bool any = false;
+    for (int b = 0; b < B; ++b) nsegs.h[b] = 0;
     for (int b : act) {
       Estimator& e = *est[b];
-      if (!e.prop_pending) continue;
-      active.h[b] = 1;
-      memcpy(Phi.h + (size_t)b * 529, e.Phi, sizeof(e.Phi));
-      memcpy(Pmm.h + (size_t)b * 529, e.Pmm, sizeof(e.Pmm));
-      for (int i = 0; i < 529; ++i) e.Phi[i] = (i / 23 == i % 23) ? 1.0 : 0.0;
+      const int n = (int)e.segments.size();
+      if (!n) continue;
+      if (n > kMaxSegments) return fail(XIVO_ERR_STATE, "IMU segment queue overflow");
+      any = true;
+      nsegs.h[b] = n;
+      memcpy(segs.h + (size_t)b * kMaxSegments, e.segments.data(), sizeof(ImuSegment) * n);
+      double* x = Xm.h + (size_t)b * kMotionDoubles;
+      memcpy(x, e.X.Rsb.m, 72); memcpy(x + 9, e.X.Tsb.v, 24); memcpy(x + 12, e.X.Vsb.v, 24);
+      memcpy(x + 15, e.X.bg.v, 24); memcpy(x + 18, e.X.ba.v, 24); memcpy(x + 21, e.X.Rsg.m, 72);
+    }
+    if (!any) return 0;
+    XB_CUDA(segs.up(st)); XB_CUDA(nsegs.up(st)); XB_CUDA(Xm.up(st));
+    if (int rc = launch_imu_integrate(st, N, dP, Xm.d, segs.d, nsegs.d, icst.d, B)) return rc;
+    g_launches += 1;
+    XB_CUDA(Xm.down(st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    for (int b : act) {
+      Estimator& e = *est[b];
+      if (!nsegs.h[b]) continue;
+      const double* x = Xm.h + (size_t)b * kMotionDoubles;
+      memcpy(e.X.Rsb.m, x, 72); memcpy(e.X.Tsb.v, x + 9, 24); memcpy(e.X.Vsb.v, x + 12, 24);
+      e.segments.clear();
       e.prop_pending = false;
     }
+    return 0;
   }
-  // apply pending propagation + edits of the given sequences (used before P read-back)
+  // apply pending propagation + edits of the given sequences (used before state / P read-back)
   int flush(const std::vector<int>& act) {
     cudaStream_t st = ctx->stream;
-    stage_propagation(act);
+    if (int rc = integrate(act)) return rc;
     if (int rc = stage_edits(act)) return rc;
-    XB_CUDA(Phi.up(st)); XB_CUDA(Pmm.up(st)); XB_CUDA(active.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
-    if (int rc = launch_cov_propagate(st, N, dP, Phi.d, Pmm.d, active.d, B)) return rc;
+    XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
-    g_launches += 2;
+    g_launches += 1;
     XB_CUDA(cudaStreamSynchronize(st));
     return 0;
   }
@@ -419,6 +459,22 @@ class Batch {
         Msg& m = msgs[i];
         if (!e.visual_begin(m.ts, m.type) || e.error) return;
         proceed[i] = 1;
+      });
+    }
+    if (int rc = first_error(act_in)) return rc;
+    {
+      // propagate up to the frame time on the device, then predict / point-cloud bookkeeping on the host
+      std::vector<int> prop;
+      for (size_t i = 0; i < act_in.size(); ++i)
+        if (proceed[i] && (msgs[i].type == 1 || msgs[i].type == 3)) prop.push_back(act_in[i]);
+      if (int rc = integrate(prop)) return rc;
+      HostScope hs("predict");
+      std::vector<int> ord(act_in.size());
+      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+      pfor(ord, [&](int i, int) {
+        if (!proceed[i]) return;
+        Estimator& e = *est[act_in[i]];
+        Msg& m = msgs[i];
         if (m.type == 1 || m.type == 3) e.predict_features();
         if (m.type == 3)
           for (size_t k = 0; k < m.ids.size(); ++k) e.ids_to_depths.insert({m.ids[k], m.xp_depth[3 * k + 2]});
@@ -513,16 +569,14 @@ class Batch {
       });
       if (int rc = first_error(full)) return rc;
       if (bad_slot) return fail(XIVO_ERR_STATE, "in-state feature without state slot");
-      stage_propagation(full);
       if (int rc = stage_edits(full)) return rc;
     }
     XB_CUDA(groups.up(st)); XB_CUDA(fx.up(st)); XB_CUDA(fxp.up(st)); XB_CUDA(fref.up(st)); XB_CUDA(fsind.up(st));
-    XB_CUDA(nfeat.up(st)); XB_CUDA(Phi.up(st)); XB_CUDA(Pmm.up(st)); XB_CUDA(active.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
-    if (int rc = launch_cov_propagate(st, N, dP, Phi.d, Pmm.d, active.d, B)) return rc;
+    XB_CUDA(nfeat.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
     if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B))
       return rc;
-    g_launches += 3;
+    g_launches += 2;
     {
       double nf = 0;
       for (int b : full) nf += nfeat.h[b];
@@ -594,16 +648,28 @@ class Batch {
             est[b]->push(std::move(in[b][pos[b]++]));
             Msg m;
             if (!est[b]->pop_ready(&m)) continue;
-            if (m.type == 0) est[b]->inertial_internal(m.ts, m.gyro, m.accel);
-            else { popped[b] = std::move(m); has[b] = 1; return; }
+            if (m.type == 0) {
+              est[b]->inertial_internal(m.ts, m.gyro, m.accel);
+              if (est[b]->needs_state_now()) { has[b] = 2; return; }  // integrate on the device before going on
+            } else { popped[b] = std::move(m); has[b] = 1; return; }
           }
         });
       }
       vis.clear();
       vmsgs.clear();
-      for (int b = 0; b < B; ++b)
-        if (has[b]) { vis.push_back(b); vmsgs.push_back(std::move(popped[b])); }
-      if (vis.empty()) return 0;
+      std::vector<int> need_int;
+      bool more = false;
+      for (int b = 0; b < B; ++b) {
+        if (has[b] == 1) { vis.push_back(b); vmsgs.push_back(std::move(popped[b])); }
+        if (has[b] == 2) need_int.push_back(b);
+        more = more || pos[b] < in[b].size();
+      }
+      if (!need_int.empty())
+        if (int rc = integrate(need_int)) return rc;
+      if (vis.empty()) {
+        if (!more) return 0;
+        continue;
+      }
       if (int rc = process_visual(vis, vmsgs)) return rc;
     }
   }
@@ -620,12 +686,17 @@ class Batch {
         est[b]->push(std::move(in[b]));
         Msg m;
         if (!est[b]->pop_ready(&m)) return;
-        if (m.type == 0) est[b]->inertial_internal(m.ts, m.gyro, m.accel);
+        if (m.type == 0) { est[b]->inertial_internal(m.ts, m.gyro, m.accel); if (est[b]->needs_state_now()) has[b] = 2; }
         else { popped[b] = std::move(m); has[b] = 1; }
       });
     }
-    for (int b = 0; b < B; ++b)
-      if (has[b]) { vis.push_back(b); vmsgs.push_back(std::move(popped[b])); }
+    std::vector<int> need_int;
+    for (int b = 0; b < B; ++b) {
+      if (has[b] == 1) { vis.push_back(b); vmsgs.push_back(std::move(popped[b])); }
+      if (has[b] == 2) need_int.push_back(b);
+    }
+    if (!need_int.empty())
+      if (int rc = integrate(need_int)) return rc;
     if (vis.empty()) return 0;
     return process_visual(vis, vmsgs);
   }
@@ -781,15 +852,22 @@ static void put34(const SE3h& g, double* out) {
     out[4 * i + 3] = g.T.v[i];
   }
 }
-int xivo_get_gsb(xivo_batch* b, int seq, double* out) { BATCH_BEGIN; SEQ_CHECK; put34(B_.est[seq]->gsb(), out); return 0; }
+int xivo_get_gsb(xivo_batch* b, int seq, double* out) {
+  BATCH_BEGIN; SEQ_CHECK;
+  if (int rc = B_.integrate({seq})) return rc;
+  put34(B_.est[seq]->gsb(), out);
+  return 0;
+}
 int xivo_get_gbc(xivo_batch* b, int seq, double* out) { BATCH_BEGIN; SEQ_CHECK; put34(B_.est[seq]->gbc(), out); return 0; }
 int xivo_get_gsc(xivo_batch* b, int seq, double* out) {
   BATCH_BEGIN; SEQ_CHECK;
+  if (int rc = B_.integrate({seq})) return rc;
   put34(se3_mul(B_.est[seq]->gsb(), B_.est[seq]->gbc()), out);
   return 0;
 }
 int xivo_get_motion(xivo_batch* b, int seq, double* Vsb, double* bg, double* ba, double* Rsg) {
   BATCH_BEGIN; SEQ_CHECK;
+  if (int rc = B_.integrate({seq})) return rc;
   const MotionX& X = B_.est[seq]->X;
   if (Vsb) memcpy(Vsb, X.Vsb.v, 24);
   if (bg) memcpy(bg, X.bg.v, 24);
@@ -806,9 +884,9 @@ int xivo_get_P(xivo_batch* b, int seq, double* out) {
 }
 int xivo_get_Pstate(xivo_batch* b, int seq, double* out81) {
   BATCH_BEGIN; SEQ_CHECK;
-  const double* Pm = B_.est[seq]->Pmm;  // the host mirror of the motion block is authoritative between frames
+  if (int rc = B_.flush({seq})) return rc;
   for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < 9; ++j) out81[9 * i + j] = Pm[23 * i + j];
+    XB_CUDA(cudaMemcpy(out81 + 9 * i, B_.dP + (size_t)seq * B_.N * B_.N + (size_t)i * B_.N, sizeof(double) * 9, cudaMemcpyDeviceToHost));
   return 0;
 }
 int xivo_get_counters(xivo_batch* b, int seq, int* out) {

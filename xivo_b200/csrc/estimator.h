@@ -229,6 +229,9 @@ class Estimator {
   double Pmm[529];  // host mirror of the motion block of P
   double Phi[529];  // pending strip transition (product of per-substep F)
   bool prop_pending = false;
+  std::vector<ImuSegment> segments;  // Propagate calls not yet integrated on the device
+  // true when host logic needs the propagated nominal state before the next message (clamping uses Rsb)
+  bool needs_state_now() const { return !segments.empty() && (c.clamp_signals || (int)segments.size() >= kMaxSegments - 2); }
   std::vector<EditOp> edits;  // pending covariance edits, in order
   std::vector<double> diagP;  // last downloaded diagonal of P
   std::vector<char> gsel, fsel;
@@ -270,9 +273,6 @@ class Estimator {
   bool mask_valid(double x, double y) const;
 
  private:
-  struct IntegratorScratch {
-    double FK[7][207], PK[7][529], P0[529], A[207], acc[529], Fd[207], T9[207];
-  } scratch_;
   std::vector<Msg> buf_;
   bool buf_initialized_ = false;
   uint64_t seqno_ = 0;
@@ -280,10 +280,6 @@ class Estimator {
   void update_system_clock(uint64_t now);
   bool initialize_gravity();
   void propagate(bool visual_meas);
-  void compose_motion(MotionX& Xs, const V3& V, const V3& gyro, const V3& accel, double dt) const;
-  void motion_jacobian(const MotionX& Xs, const V3& gyro, const V3& accel, double* F, double* G) const;
-  void integrator_step(bool pd, const V3& gyro0, const V3& accel0, double dt);
-  void integrate(const V3& gyro0, const V3& accel0, double dt);
   void state_plus(const double* dX);
   // state slots
   void add_group_to_state(Group* g);

@@ -93,3 +93,23 @@ int launch_oos(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const do
                double* Hx_proj /*nf x 2k x N scratch; first 2k-3 rows valid*/, double* inn_proj /*nf x 2k; first 2k-3 valid*/);
 
 }  // namespace xb
+
+namespace xb {
+// ---------------- IMU propagation on device (ekf_kernels.cu) ----------------
+// One integration segment = one Estimator::Propagate call (src/estimator.cpp:539-592): constant
+// slopes, duration dt, split into fixed sub-steps like PrinceDormand()/RK4() do.
+struct ImuSegment {
+  double gyro0[3], accel0[3], slope_gyro[3], slope_accel[3], dt;
+};
+constexpr int kMaxSegments = 24;
+constexpr int kMotionDoubles = 30;  // Rsb(9) Tsb(3) Vsb(3) bg(3) ba(3) Rsg(9)
+struct ImuConst {                   // per filter
+  double Cg[9], Ca[9], g[3], qimu[12], qmodel[23], h0;
+  int pd;  // 1 = Prince-Dormand, 0 = RK4
+  int pad;
+};
+// Integrates nominal motion state, P[0:23,0:23] and the strips P[0:23,23:] / P[23:,0:23] through
+// the queued segments of every filter.  Xm: B x 30 in/out.
+int launch_imu_integrate(cudaStream_t st, int N, double* P, double* Xm, const ImuSegment* segs /*B x kMaxSegments*/,
+                         const int* nseg /*B*/, const ImuConst* cst /*B*/, int batch);
+}  // namespace xb
