@@ -133,16 +133,17 @@ int xivo_cov_edit(xivo_ctx* ctx, int N, double* P, const int* ops, const double*
  * P[0:23,0:23] <- Pmm, P[0:23,23:] <- Phi P[0:23,23:] (+ symmetric strip). */
 int xivo_cov_propagate(xivo_ctx* ctx, int N, double* P, const double* Phi, const double* Pmm);
 
-/* IMU propagation through nseg Estimator::Propagate calls (src/estimator.cpp:539-592 with
- * PrinceDormand / RK4 sub-stepping, src/princedormand.cpp:60-221, src/rk4.cpp:14-103): nominal motion
- * state, P[0:23,0:23], the motion/structure strips of P, and + Qmodel per call.
- *   X30   : Rsb(9) Tsb(3) Vsb(3) bg(3) ba(3) Rsg(9), in/out
- *   seg13 : nseg x {gyro0(3) accel0(3) slope_gyro(3) slope_accel(3) dt}
+/* Covariance side of Estimator::Propagate (src/estimator.cpp:539-592 with PrinceDormand / RK4
+ * sub-stepping, src/princedormand.cpp:85-221, src/rk4.cpp:35-103): P[0:23,0:23], the motion/structure
+ * strips of P, and + Qmodel per Propagate call.  The nominal state is a short sequential chain that the
+ * caller integrates; for every Runge-Kutta stage it passes what the motion Jacobian
+ * (ComputeMotionJacobianAt, src/estimator.cpp:614-702) depends on:
+ *   stage16 : nstages x {Rsb(9), Cg*gyro-bg (3), Ca*accel-ba (3), h}; h = sub-step length on the first
+ *             stage of each sub-step, negative when that sub-step closes a Propagate call
  *   qimu12 / qmodel23 : diagonals of Qimu (gyro, accel, gyro bias, accel bias) and Qmodel
- *   h0    : fixed sub-step ("stepsize"), negative = one step per call */
-int xivo_imu_propagate(xivo_ctx* ctx, int N, double* P, double* X30, int nseg, const double* seg13, const double* Cg9,
-                       const double* Ca9, const double* g3, const double* qimu12, const double* qmodel23, double h0,
-                       int prince_dormand);
+ *   stages_per_step : 7 (Prince-Dormand) or 4 (RK4) */
+int xivo_imu_cov_propagate(xivo_ctx* ctx, int N, double* P, int nstages, const double* stage16, const double* g3,
+                           const double* qimu12, const double* qmodel23, int stages_per_step);
 
 /* ---------------------------------------------------------------------------------------------
  * Estimator-level entry points (handle based; one handle = a batch of independent estimators

@@ -489,10 +489,13 @@ def compose_motion(X: MotionState, V, gyro, accel, dt, Cg, Ca, g):
     X.Rsb = X.Rsb @ so3_exp(gyro_c * dt)
 
 
-def motion_jacobian(X: MotionState, gyro, accel, Cg, Ca, g):
-    """Estimator::ComputeMotionJacobianAt, src/estimator.cpp:614-702 -> F (23x23), G (23x12)."""
+def motion_jacobian(X: MotionState, gyro, accel, Cg, Ca, g, rec=None, h=0.0):
+    """Estimator::ComputeMotionJacobianAt, src/estimator.cpp:614-702 -> F (23x23), G (23x12).
+    rec (optional list) receives what F, G depend on: (Rsb, calibrated gyro, calibrated accel, h)."""
     gyro_c = Cg @ gyro - X.bg
     accel_c = Ca @ accel - X.ba
+    if rec is not None:
+        rec.append(np.concatenate([X.Rsb.ravel(), gyro_c, accel_c, [h]]))
     R = X.Rsb
     F = np.zeros((K_MOTION, K_MOTION))
     G = np.zeros((K_MOTION, 12))
@@ -520,12 +523,12 @@ _PD_A = [
 _PD_B = [0.0862, 0.0, 0.6660, -0.7857, 0.9570, 0.0965, -0.0200]
 
 
-def prince_dormand_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu):
+def prince_dormand_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu, rec=None, h_enc=None):
     """Estimator::PrinceDormandStep, src/princedormand.cpp:85-221.  Returns
     (F_total 23x23, new Pmm); mutates X.  The strip update P[0:23,23:] = F P[0:23,23:]
     (:211-215) is applied by the caller."""
     Ks, FKs, PKs = [], [], []
-    F, G = motion_jacobian(X, gyro0, accel0, Cg, Ca, g)
+    F, G = motion_jacobian(X, gyro0, accel0, Cg, Ca, g, rec, dt if h_enc is None else h_enc)
     GQG = lambda G_: G_ @ Qimu @ G_.T
     Ks.append(X.Vsb.copy())
     FKs.append(F.copy())
@@ -538,7 +541,7 @@ def prince_dormand_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_ac
         V = sum(ai * Ki for ai, Ki in zip(a, Ks))
         compose_motion(X0, V, gy, ac, step, Cg, Ca, g)
         X0.Rsb = quat_normalize_rot(X0.Rsb)
-        F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g)
+        F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g, rec)
         Ks.append(X0.Vsb.copy())
         FKs.append(F + F @ sum(ai * FKi for ai, FKi in zip(a, FKs)) * dt)
         P0 = Pmm + sum(ai * PKi for ai, PKi in zip(a, PKs)) * dt
@@ -552,12 +555,12 @@ def prince_dormand_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_ac
     return Ftot, Pmm + PK * dt
 
 
-def rk4_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu):
+def rk4_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu, rec=None, h_enc=None):
     """Estimator::RK4Step, src/rk4.cpp:35-103 (including its use of the half-step
     input for the 4th stage, :79)."""
     half = 0.5 * dt
     GQG = lambda G_: G_ @ Qimu @ G_.T
-    F, G = motion_jacobian(X, gyro0, accel0, Cg, Ca, g)
+    F, G = motion_jacobian(X, gyro0, accel0, Cg, Ca, g, rec, dt if h_enc is None else h_enc)
     K1, FK1 = X.Vsb.copy(), F.copy()
     PK1 = F @ Pmm + Pmm @ F.T + GQG(G)
     gy, ac = gyro0 + half * slope_gyro, accel0 + half * slope_accel
@@ -565,7 +568,7 @@ def rk4_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg
     compose_motion(X0, 0.5 * K1, gy, ac, half, Cg, Ca, g)
     X0.Rsb = quat_normalize_rot(X0.Rsb)
     K2 = X0.Vsb.copy()
-    F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g)
+    F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g, rec)
     FK2 = F + F @ FK1 * half
     P0 = Pmm + half * PK1
     PK2 = F @ P0 + P0 @ F.T + GQG(G)
@@ -573,7 +576,7 @@ def rk4_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg
     compose_motion(X0, 0.5 * K2, gy, ac, half, Cg, Ca, g)
     X0.Rsb = quat_normalize_rot(X0.Rsb)
     K3 = X0.Vsb.copy()
-    F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g)
+    F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g, rec)
     FK3 = F + F @ FK2 * half
     P0 = Pmm + half * PK2
     PK3 = F @ P0 + P0 @ F.T + GQG(G)
@@ -581,7 +584,7 @@ def rk4_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg
     compose_motion(X0, K3, gy, ac, dt, Cg, Ca, g)
     X0.Rsb = quat_normalize_rot(X0.Rsb)
     K4 = X0.Vsb.copy()
-    F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g)
+    F, G = motion_jacobian(X0, gy, ac, Cg, Ca, g, rec)
     FK4 = F + F @ FK3 * dt
     P0 = Pmm + dt * PK3
     PK4 = F @ P0 + P0 @ F.T + GQG(G)
@@ -593,14 +596,14 @@ def rk4_step(X: MotionState, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg
     return np.eye(K_MOTION) + FK * dt, Pmm + PK * dt
 
 
-def integrate(method, X, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu, h0=0.002):
+def integrate(method, X, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu, h0=0.002, rec=None):
     """Fixed-step driver with the half-step trick: Estimator::PrinceDormand
     (princedormand.cpp:60-81, control_stepsize=false) / Estimator::RK4 (rk4.cpp:14-31).
     Returns (Phi = product of per-substep F, Pmm)."""
     step_fn = prince_dormand_step if method == "PrinceDormand" else rk4_step
     Phi = np.eye(K_MOTION)
     if h0 < 0:
-        F, Pmm = step_fn(X, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu)
+        F, Pmm = step_fn(X, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca, g, Qimu, rec, -dt)
         return F @ Phi, Pmm
     total = 0.0
     gyro, accel = gyro0.copy(), accel0.copy()
@@ -610,7 +613,8 @@ def integrate(method, X, Pmm, gyro0, accel0, slope_gyro, slope_accel, dt, Cg, Ca
             h = dt - total
         elif total + h + 0.5 * h > dt:
             h = 0.5 * h
-        F, Pmm = step_fn(X, Pmm, gyro, accel, slope_gyro, slope_accel, h, Cg, Ca, g, Qimu)
+        last = not (total + h < dt)
+        F, Pmm = step_fn(X, Pmm, gyro, accel, slope_gyro, slope_accel, h, Cg, Ca, g, Qimu, rec, -h if last else h)
         Phi = F @ Phi
         gyro = gyro + slope_gyro * h
         accel = accel + slope_accel * h

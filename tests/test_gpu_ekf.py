@@ -189,8 +189,9 @@ def test_oos_projection_invariants(ctx, k):
 
 
 @pytest.mark.parametrize("method", ["PrinceDormand", "RK4"])
-def test_imu_propagate_matches_oracle(ctx, method):
-    """Device integrator vs the numpy restatement of Propagate + PrinceDormand/RK4 (fp64, 1e-10)."""
+def test_imu_cov_propagate_matches_oracle(ctx, method):
+    """Device covariance propagation (from per-stage records) vs the numpy restatement of
+    Propagate + PrinceDormand/RK4 (fp64, 1e-10)."""
     rng = np.random.default_rng(7)
     lay = E.Layout(4, 14)
     N = lay.N
@@ -206,18 +207,16 @@ def test_imu_propagate_matches_oracle(ctx, method):
     qimu = np.array([2.5e-5] * 3 + [2.5e-3] * 3 + [1e-8] * 3 + [1e-7] * 3)
     qmodel = np.zeros(23)
     qmodel[0:3], qmodel[15:18], qmodel[21:23] = 1e-4, 1e-6, 1e-7
-    segs = []
+    rec = []
     Pr, Xr = P.copy(), X.copy()
     for k in range(9):
         gyro0, accel0 = rng.normal(0, 0.2, 3), np.array([0.0, 0.0, 9.8]) + rng.normal(0, 0.5, 3)
         sg, sa = rng.normal(0, 2.0, 3), rng.normal(0, 5.0, 3)
         dt = [0.005, 0.0025, 0.0071, 0.04][k % 4]
-        segs.append(np.concatenate([gyro0, accel0, sg, sa, [dt]]))
-        Phi, Pmm = E.integrate(method, Xr, Pr[:23, :23].copy(), gyro0, accel0, sg, sa, dt, Cg, Ca, g, np.diag(qimu), 0.002)
+        Phi, Pmm = E.integrate(method, Xr, Pr[:23, :23].copy(), gyro0, accel0, sg, sa, dt, Cg, Ca, g, np.diag(qimu), 0.002, rec)
         E.apply_propagation(Pr, Phi, Pmm, np.diag(qmodel))
-    X30 = np.concatenate([X.Rsb.ravel(), X.Tsb, X.Vsb, X.bg, X.ba, X.Rsg.ravel()])
-    Pg, Xg = ctx.imu_propagate(P, X30, segs, Cg, Ca, g, qimu, qmodel, 0.002, method == "PrinceDormand")
-    Xref = np.concatenate([Xr.Rsb.ravel(), Xr.Tsb, Xr.Vsb, Xr.bg, Xr.ba, Xr.Rsg.ravel()])
-    assert np.abs(Xg - Xref).max() <= 1e-10 * max(1.0, np.abs(Xref).max())
+    nst = 7 if method == "PrinceDormand" else 4
+    assert len(rec) % nst == 0 and len(rec) > 9 * nst
+    Pg = ctx.imu_cov_propagate(P, np.array(rec), g, qimu, qmodel, nst)
     assert np.abs(Pg - Pr).max() <= 1e-10 * np.abs(Pr).max()
     assert np.abs(Pg - Pg.T).max() <= 1e-13 * np.abs(Pg).max()

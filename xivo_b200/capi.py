@@ -231,10 +231,9 @@ class Context:
         _check(lib().xivo_cov_propagate(self._h, P.shape[0], _p(P), _p(_f64(Phi)), _p(_f64(Pmm))), "xivo_cov_propagate")
         return P
 
-    def imu_propagate(self, P, X30, segs, Cg, Ca, g, qimu, qmodel, h0, prince_dormand=True):
+    def imu_cov_propagate(self, P, stages, g, qimu, qmodel, stages_per_step):
         P = np.array(P, dtype=np.float64, order="C", copy=True)
-        X = np.array(X30, dtype=np.float64, copy=True).ravel()
-        segs = _f64(segs).reshape(-1, 13)
-        _check(lib().xivo_imu_propagate(self._h, P.shape[0], _p(P), _p(X), len(segs), _p(segs), _p(_f64(Cg)), _p(_f64(Ca)), _p(_f64(g)),
-                                        _p(_f64(qimu)), _p(_f64(qmodel)), C.c_double(h0), int(bool(prince_dormand))), "xivo_imu_propagate")
-        return P, X
+        stages = _f64(stages).reshape(-1, 16)
+        _check(lib().xivo_imu_cov_propagate(self._h, P.shape[0], _p(P), len(stages), _p(stages), _p(_f64(g)), _p(_f64(qimu)), _p(_f64(qmodel)),
+                                            int(stages_per_step)), "xivo_imu_cov_propagate")
+        return P

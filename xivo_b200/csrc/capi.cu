@@ -416,39 +416,33 @@ int xivo_cov_propagate(xivo_ctx* ctx, int N, double* P, const double* Phi, const
   return XIVO_OK;
 }
 
-int xivo_imu_propagate(xivo_ctx* ctx, int N, double* P, double* X30, int nseg, const double* seg13, const double* Cg9, const double* Ca9,
-                       const double* g3, const double* qimu12, const double* qmodel23, double h0, int prince_dormand) {
+int xivo_imu_cov_propagate(xivo_ctx* ctx, int N, double* P, int nstages, const double* stage16, const double* g3, const double* qimu12,
+                           const double* qmodel23, int stages_per_step) {
   API_BEGIN;
-  XB_REQUIRE(N >= 23 && P && X30 && nseg >= 0 && nseg <= kMaxSegments && (nseg == 0 || seg13) && Cg9 && Ca9 && g3 && qimu12 && qmodel23,
-             "imu_propagate: bad arguments");
-  if (nseg == 0) return XIVO_OK;
+  XB_REQUIRE(N >= 23 && P && nstages >= 0 && nstages <= kMaxStages && (nstages == 0 || stage16) && g3 && qimu12 && qmodel23 &&
+                 (stages_per_step == 7 || stages_per_step == 4) && nstages % stages_per_step == 0,
+             "imu_cov_propagate: bad arguments");
+  if (nstages == 0) return XIVO_OK;
+  static_assert(sizeof(ImuStage) == 16 * sizeof(double), "ImuStage layout");
   cudaStream_t st = ctx->stream;
-  std::vector<ImuSegment> hs(kMaxSegments);
-  for (int i = 0; i < nseg; ++i) {
-    memcpy(hs[i].gyro0, seg13 + 13 * i, 24);
-    memcpy(hs[i].accel0, seg13 + 13 * i + 3, 24);
-    memcpy(hs[i].slope_gyro, seg13 + 13 * i + 6, 24);
-    memcpy(hs[i].slope_accel, seg13 + 13 * i + 9, 24);
-    hs[i].dt = seg13[13 * i + 12];
-  }
   ImuConst ic;
-  memcpy(ic.Cg, Cg9, 72); memcpy(ic.Ca, Ca9, 72); memcpy(ic.g, g3, 24); memcpy(ic.qimu, qimu12, 96); memcpy(ic.qmodel, qmodel23, 184);
-  ic.h0 = h0; ic.pd = prince_dormand ? 1 : 0; ic.pad = 0;
-  DevBuf<double> dP((size_t)N * N), dX(kMotionDoubles);
-  DevBuf<ImuSegment> dS(kMaxSegments);
+  memcpy(ic.g, g3, 24); memcpy(ic.qimu, qimu12, 96); memcpy(ic.qmodel, qmodel23, 184);
+  ic.stages_per_step = stages_per_step; ic.pad = 0;
+  const int zero = 0;
+  DevBuf<double> dP((size_t)N * N);
+  DevBuf<ImuStage> dS(nstages);
   DevBuf<ImuConst> dC(1);
-  DevBuf<int> dn(1);
-  XB_REQUIRE(dP.ok() && dX.ok() && dS.ok() && dC.ok() && dn.ok(), "cudaMalloc failed");
+  DevBuf<int> dn(1), df(1);
+  XB_REQUIRE(dP.ok() && dS.ok() && dC.ok() && dn.ok() && df.ok(), "cudaMalloc failed");
   XB_CUDA(cudaMemcpyAsync(dP.p, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
-  XB_CUDA(cudaMemcpyAsync(dX.p, X30, sizeof(double) * kMotionDoubles, cudaMemcpyHostToDevice, st));
-  XB_CUDA(cudaMemcpyAsync(dS.p, hs.data(), sizeof(ImuSegment) * kMaxSegments, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dS.p, stage16, sizeof(ImuStage) * nstages, cudaMemcpyHostToDevice, st));
   XB_CUDA(cudaMemcpyAsync(dC.p, &ic, sizeof(ic), cudaMemcpyHostToDevice, st));
-  XB_CUDA(cudaMemcpyAsync(dn.p, &nseg, sizeof(int), cudaMemcpyHostToDevice, st));
-  int rc = launch_imu_integrate(st, N, dP.p, dX.p, dS.p, dn.p, dC.p, 1);
+  XB_CUDA(cudaMemcpyAsync(dn.p, &nstages, sizeof(int), cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(df.p, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+  int rc = launch_imu_cov_propagate(st, N, dP.p, dS.p, df.p, dn.p, dC.p, 1);
   if (rc) return rc;
   g_launches += 1;
   XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
-  XB_CUDA(cudaMemcpyAsync(X30, dX.p, sizeof(double) * kMotionDoubles, cudaMemcpyDeviceToHost, st));
   XB_CUDA(cudaStreamSynchronize(st));
   return XIVO_OK;
 }

@@ -460,39 +460,16 @@ int launch_pack_state(cudaStream_t st, int N, const double* P, const double* err
 }
 
 // ------------------------------------------------------------------------------------------
-// IMU propagation on the device: Estimator::Propagate -> PrinceDormand / RK4 sub-steps
-// (/root/reference/src/estimator.cpp:539-704, src/princedormand.cpp:60-221, src/rk4.cpp:14-103).
-// One warp per filter walks its queued segments; lane 0 advances the nominal state (a few hundred
-// flops per stage), all lanes do the 23x23 covariance algebra in shared memory.  Structure used:
-// only the Wsb/Tsb/Vsb rows of F are non-zero, so F*X is a 9 x 23 strip and
-//   Pdot = [A;0] + [A;0]^T + G Q G^T,   A = F[0:9,:] P,   G Q G^T block diagonal (Q diagonal).
-// At the end the motion/structure strips get Phi = prod(I + FK dt) (only rows 0..8 differ from I).
+// IMU covariance propagation: the covariance side of Estimator::Propagate -> PrinceDormand / RK4
+// (/root/reference/src/estimator.cpp:539-704, src/princedormand.cpp:85-221, src/rk4.cpp:35-103).
+// One warp per filter consumes the per-stage records the host wrote while integrating the nominal
+// state (kernels.h: ImuStage).  Structure used: only the Wsb/Tsb/Vsb rows of F are non-zero, so
+// F*X is a 9 x 23 strip and  Pdot = [A;0] + [A;0]^T + G Q G^T,  A = F[0:9,:] P,  G Q G^T block diagonal
+// (Q diagonal).  At the end the motion/structure strips get Phi = prod(I + FK h) (rows >= 9 = identity).
 // ------------------------------------------------------------------------------------------
-struct MotionDev {
-  M3 Rsb, Rsg;
-  V3 Tsb, Vsb, bg, ba;
-};
 struct F9s {  // shared-memory image of the non-zero blocks of F and of R
   double dW[9], dVW[9], dVba[9], dVg[6], R[9];
 };
-__device__ __forceinline__ void f9_of_dev(const ImuConst& c, const MotionDev& X, const V3& gyro, const V3& accel, F9s* f) {
-  M3 Cg, Ca;
-  for (int i = 0; i < 9; ++i) { Cg.m[i] = c.Cg[i]; Ca.m[i] = c.Ca[i]; }
-  const V3 g{{c.g[0], c.g[1], c.g[2]}};
-  const V3 gc = v3_sub(m3_mulv(Cg, gyro), X.bg), ac = v3_sub(m3_mulv(Ca, accel), X.ba);
-  const M3 dW = m3_neg(m3_hat(gc)), dVW = m3_neg(m3_mul(X.Rsb, m3_hat(ac))), dVba = m3_neg(X.Rsb), dVg = m3_neg(m3_mul(X.Rsb, m3_hat(g)));
-  for (int i = 0; i < 9; ++i) { f->dW[i] = dW.m[i]; f->dVW[i] = dVW.m[i]; f->dVba[i] = dVba.m[i]; f->R[i] = X.Rsb.m[i]; }
-  for (int i = 0; i < 3; ++i) { f->dVg[2 * i] = dVg.m[3 * i]; f->dVg[2 * i + 1] = dVg.m[3 * i + 1]; }
-}
-__device__ __forceinline__ void compose_motion_dev(const ImuConst& c, MotionDev& X, const V3& V, const V3& gyro, const V3& accel, double dt) {
-  M3 Cg, Ca;
-  for (int i = 0; i < 9; ++i) { Cg.m[i] = c.Cg[i]; Ca.m[i] = c.Ca[i]; }
-  const V3 g{{c.g[0], c.g[1], c.g[2]}};
-  const V3 gc = v3_sub(m3_mulv(Cg, gyro), X.bg), ac = v3_sub(m3_mulv(Ca, accel), X.ba);
-  X.Tsb = v3_add(X.Tsb, v3_scale(V, dt));
-  X.Vsb = v3_add(X.Vsb, v3_scale(v3_add(m3_mulv(X.Rsb, ac), m3_mulv(X.Rsg, g)), dt));
-  X.Rsb = so3_normalize(m3_mul(X.Rsb, so3_exp(v3_scale(gc, dt))));
-}
 // element (i, j), i < 9, of F[0:9,:] * B for a 23-column B; lt9: rows >= 9 of B are zero
 __device__ __forceinline__ double f9_elem(const F9s& f, const double* B, int i, int j, bool lt9) {
   const int blk = i / 3, r = i - 3 * blk;
@@ -517,25 +494,28 @@ __device__ __forceinline__ double f9_dense(const F9s& f, int i, int j) {  // F[i
   if (j >= 21) return f.dVg[2 * r + j - 21];
   return 0.0;
 }
+__device__ __forceinline__ double hat_elem(const double* w, int k, int j) {  // hat(w)[k][j]
+  if (k == j) return 0.0;
+  const int o = 3 - k - j;  // the remaining index
+  const double sgn = ((j - k + 3) % 3 == 1) ? -1.0 : 1.0;  // hat: [0,-w2,w1; w2,0,-w0; -w1,w0,0]
+  return sgn * w[o];
+}
 
-__global__ void __launch_bounds__(32) imu_integrate_kernel(int N, double* __restrict__ P, double* __restrict__ Xm,
-                                                           const ImuSegment* __restrict__ segs, const int* __restrict__ nseg,
-                                                           const ImuConst* __restrict__ cst) {
+__global__ void __launch_bounds__(32) imu_cov_propagate_kernel(int N, double* __restrict__ P, const ImuStage* __restrict__ stages,
+                                                               const int* __restrict__ first, const int* __restrict__ nstages,
+                                                               const ImuConst* __restrict__ cst) {
   const int b = blockIdx.x, lane = threadIdx.x;
-  const int ns = nseg[b];
-  if (ns == 0) return;
-  __shared__ double sP[529], sP0[529], sA[7][207], sFK[7][207], sSA[207], sAcc[207], sT9[207], sPhi[207], sV[7][9], sCV[9], sK[7][3];
+  const int nall = nstages[b];
+  if (nall == 0) return;
+  __shared__ double sP[529], sP0[529], sA[7][207], sFK[7][207], sSA[207], sAcc[207], sT9[207], sPhi[207], sV[7][9], sCV[9];
   __shared__ F9s sF;
+  __shared__ ImuStage sStage;
   const ImuConst c = cst[b];
+  const int nst = c.stages_per_step;
   double* __restrict__ Pb = P + (size_t)b * N * N;
+  const ImuStage* __restrict__ stg = stages + first[b];
   for (int t = lane; t < 529; t += 32) sP[t] = Pb[(size_t)(t / 23) * N + t % 23];
   for (int t = lane; t < 207; t += 32) sPhi[t] = (t / 23 == t % 23) ? 1.0 : 0.0;
-  MotionDev X;  // meaningful on lane 0 only
-  if (lane == 0) {
-    const double* x = Xm + (size_t)b * kMotionDoubles;
-    for (int i = 0; i < 9; ++i) { X.Rsb.m[i] = x[i]; X.Rsg.m[i] = x[21 + i]; }
-    for (int i = 0; i < 3; ++i) { X.Tsb.v[i] = x[9 + i]; X.Vsb.v[i] = x[12 + i]; X.bg.v[i] = x[15 + i]; X.ba.v[i] = x[18 + i]; }
-  }
   __syncwarp();
   const double A_pd[6][6] = {{2.0 / 9, 0, 0, 0, 0, 0},
                              {1.0 / 12, 3.0 / 12, 0, 0, 0, 0},
@@ -543,13 +523,10 @@ __global__ void __launch_bounds__(32) imu_integrate_kernel(int N, double* __rest
                              {83.0 / 330, -195.0 / 330, 305.0 / 330, 27.0 / 330, 0, 0},
                              {-19.0 / 28, 63.0 / 28, 4.0 / 28, -108.0 / 28, 88.0 / 28, 0},
                              {38.0 / 400, 0, 240.0 / 400, -243.0 / 400, 330.0 / 400, 35.0 / 400}};
-  const double C_pd[6] = {2.0 / 9, 3.0 / 9, 5.0 / 9, 6.0 / 9, 1.0, 1.0};
   const double B_pd[7] = {0.0862, 0.0, 0.6660, -0.7857, 0.9570, 0.0965, -0.0200};
   const double A_rk[3][6] = {{0.5, 0, 0, 0, 0, 0}, {0, 0.5, 0, 0, 0, 0}, {0, 0, 1.0, 0, 0, 0}};
-  const double C_rk[3] = {0.5, 0.5, 1.0};
   const double B_rk[4] = {1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6};
-  const int nst = c.pd ? 7 : 4;
-  // P0 / Pmm increment from the strips:  X[i][j] (+)= w * ( S[i][j] (i<9) + S[j][i] (j<9) + const )
+  const bool pd = nst == 7;
   auto strip_sym = [&](const double* S, int i, int j) { return (i < 9 ? S[i * 23 + j] : 0.0) + (j < 9 ? S[j * 23 + i] : 0.0); };
   auto gqg_const = [&](int i, int j) {  // the state-independent diagonal part of G Q G^T
     if (i != j) return 0.0;
@@ -558,126 +535,105 @@ __global__ void __launch_bounds__(32) imu_integrate_kernel(int N, double* __rest
     if (i >= 12 && i < 15) return c.qimu[9 + i - 12];
     return 0.0;
   };
-  auto stage_products = [&](int s, const double* Pin, double dt_fk) {
-    // FK[s] = F + (F acc) dt  (acc already holds sum a FK, zero for s == 0), A[s] = F[0:9,:] Pin, V[s] = R qa R^T
+  // build the non-zero blocks of F from a stage record: dW = -hat(gc), dVW = -R hat(ac), dVba = -R, dVg = (-R hat(g))[:, :2]
+  auto load_stage = [&](int idx) {
+    const double* src = reinterpret_cast<const double*>(stg + idx);
+    if (lane < 16) reinterpret_cast<double*>(&sStage)[lane] = src[lane];
+    __syncwarp();
+    if (lane < 9) {
+      const int i = lane / 3, j = lane - 3 * i;
+      sF.R[lane] = sStage.R[lane];
+      sF.dVba[lane] = -sStage.R[lane];
+      sF.dW[lane] = -hat_elem(sStage.gc, i, j);
+      double v = 0, vg = 0;
+      for (int k = 0; k < 3; ++k) {
+        v += sStage.R[3 * i + k] * hat_elem(sStage.ac, k, j);
+        vg += sStage.R[3 * i + k] * hat_elem(c.g, k, j);
+      }
+      sF.dVW[lane] = -v;
+      if (j < 2) sF.dVg[2 * i + j] = -vg;
+    }
+    __syncwarp();
+  };
+  auto stage_products = [&](int s, const double* Pin, double h) {
+    // FK[s] = F + (F acc) h  (acc holds sum a FK; unused for s == 0), A[s] = F[0:9,:] Pin, V[s] = R qa R^T
     for (int t = lane; t < 207; t += 32) {
       const int i = t / 23, j = t - 23 * i;
       const double fd = f9_dense(sF, i, j);
-      sFK[s][t] = s == 0 ? fd : fd + f9_elem(sF, sAcc, i, j, true) * dt_fk;
+      sFK[s][t] = s == 0 ? fd : fd + f9_elem(sF, sAcc, i, j, true) * h;
       sA[s][t] = f9_elem(sF, Pin, i, j, false);
     }
     if (lane < 9) {
       const int i = lane / 3, j = lane - 3 * i;
       sV[s][lane] = sF.R[3 * i] * c.qimu[3] * sF.R[3 * j] + sF.R[3 * i + 1] * c.qimu[4] * sF.R[3 * j + 1] + sF.R[3 * i + 2] * c.qimu[5] * sF.R[3 * j + 2];
     }
+    __syncwarp();
   };
-  for (int sg = 0; sg < ns; ++sg) {
-    const ImuSegment S = segs[(size_t)b * kMaxSegments + sg];
-    const V3 slope_g{{S.slope_gyro[0], S.slope_gyro[1], S.slope_gyro[2]}}, slope_a{{S.slope_accel[0], S.slope_accel[1], S.slope_accel[2]}};
-    V3 gyro{{S.gyro0[0], S.gyro0[1], S.gyro0[2]}}, accel{{S.accel0[0], S.accel0[1], S.accel0[2]}};
-    double total = 0.0;
-    const double dt_seg = S.dt;
-    bool first = true;
-    while (first || (c.h0 >= 0 && total < dt_seg)) {
-      first = false;
-      double h;
-      if (c.h0 < 0) h = dt_seg;
-      else {
-        h = c.h0;
-        if (total + h > dt_seg) h = dt_seg - total;
-        else if (total + h + 0.5 * h > dt_seg) h = 0.5 * h;
-      }
-      // ---- one integrator step of length h from (gyro, accel)
-      if (lane == 0) {
-        f9_of_dev(c, X, gyro, accel, &sF);
-        sK[0][0] = X.Vsb.v[0]; sK[0][1] = X.Vsb.v[1]; sK[0][2] = X.Vsb.v[2];
-      }
-      __syncwarp();
-      stage_products(0, sP, h);
-      __syncwarp();
-      for (int s = 1; s < nst; ++s) {
-        const double* a = c.pd ? A_pd[s - 1] : A_rk[s - 1];
-        const double cs = c.pd ? C_pd[s - 1] : C_rk[s - 1];
-        const double cin = c.pd ? cs : 0.5;
-        if (lane == 0) {
-          MotionDev X0 = X;
-          V3 V{{0, 0, 0}};
-          for (int q = 0; q < s; ++q) V = v3_add(V, V3{{a[q] * sK[q][0], a[q] * sK[q][1], a[q] * sK[q][2]}});
-          const V3 gy = v3_add(gyro, v3_scale(slope_g, cin * h)), ac = v3_add(accel, v3_scale(slope_a, cin * h));
-          compose_motion_dev(c, X0, V, gy, ac, cs * h);
-          f9_of_dev(c, X0, gy, ac, &sF);
-          sK[s][0] = X0.Vsb.v[0]; sK[s][1] = X0.Vsb.v[1]; sK[s][2] = X0.Vsb.v[2];
-        }
-        double sa = 0;
-        for (int q = 0; q < s; ++q) sa += a[q];
-        for (int t = lane; t < 207; t += 32) {
-          double f = 0, p = 0;
-          for (int q = 0; q < s; ++q) { f += a[q] * sFK[q][t]; p += a[q] * sA[q][t]; }
-          sAcc[t] = f;
-          sSA[t] = p;
-        }
-        if (lane < 9) {
-          double v = 0;
-          for (int q = 0; q < s; ++q) v += a[q] * sV[q][lane];
-          sCV[lane] = v;
-        }
-        __syncwarp();
-        for (int t = lane; t < 529; t += 32) {
-          const int i = t / 23, j = t - 23 * i;
-          double inc = strip_sym(sSA, i, j) + sa * gqg_const(i, j);
-          if (i >= 6 && i < 9 && j >= 6 && j < 9) inc += sCV[(i - 6) * 3 + j - 6];
-          sP0[t] = sP[t] + inc * h;
-        }
-        __syncwarp();
-        stage_products(s, sP0, h);
-        __syncwarp();
-      }
-      const double* bw = c.pd ? B_pd : B_rk;
-      if (lane == 0) {
-        V3 Kt{{0, 0, 0}};
-        for (int q = 0; q < nst; ++q) Kt = v3_add(Kt, V3{{bw[q] * sK[q][0], bw[q] * sK[q][1], bw[q] * sK[q][2]}});
-        compose_motion_dev(c, X, Kt, v3_add(gyro, v3_scale(slope_g, h)), v3_add(accel, v3_scale(slope_a, h)), h);
-      }
-      double sb = 0;
-      for (int q = 0; q < nst; ++q) sb += bw[q];
+  for (int base = 0; base + nst <= nall; base += nst) {
+    load_stage(base);
+    const double henc = sStage.h;
+    const double h = fabs(henc);
+    stage_products(0, sP, h);
+    for (int s = 1; s < nst; ++s) {
+      const double* a = pd ? A_pd[s - 1] : A_rk[s - 1];
+      double sa = 0;
+      for (int q = 0; q < s; ++q) sa += a[q];
       for (int t = lane; t < 207; t += 32) {
         double f = 0, p = 0;
-        for (int q = 0; q < nst; ++q) { f += bw[q] * sFK[q][t]; p += bw[q] * sA[q][t]; }
-        sAcc[t] = ((t / 23 == t % 23) ? 1.0 : 0.0) + f * h;  // rows 0..8 of I + FK h
+        for (int q = 0; q < s; ++q) { f += a[q] * sFK[q][t]; p += a[q] * sA[q][t]; }
+        sAcc[t] = f;
         sSA[t] = p;
       }
       if (lane < 9) {
         double v = 0;
-        for (int q = 0; q < nst; ++q) v += bw[q] * sV[q][lane];
+        for (int q = 0; q < s; ++q) v += a[q] * sV[q][lane];
         sCV[lane] = v;
       }
       __syncwarp();
       for (int t = lane; t < 529; t += 32) {
         const int i = t / 23, j = t - 23 * i;
-        double inc = strip_sym(sSA, i, j) + sb * gqg_const(i, j);
+        double inc = strip_sym(sSA, i, j) + sa * gqg_const(i, j);
         if (i >= 6 && i < 9 && j >= 6 && j < 9) inc += sCV[(i - 6) * 3 + j - 6];
-        sP[t] += inc * h;
+        sP0[t] = sP[t] + inc * h;
       }
-      // Phi <- (I + FK h) Phi; rows >= 9 of both factors are identity rows
-      for (int t = lane; t < 207; t += 32) {
-        const int i = t / 23, j = t - 23 * i;
-        double v = j >= 9 ? sAcc[i * 23 + j] : 0.0;
-        for (int k = 0; k < 9; ++k) v += sAcc[i * 23 + k] * sPhi[k * 23 + j];
-        sT9[t] = v;
-      }
-      __syncwarp();
-      for (int t = lane; t < 207; t += 32) sPhi[t] = sT9[t];
-      __syncwarp();
-      gyro = v3_add(gyro, v3_scale(slope_g, h));
-      accel = v3_add(accel, v3_scale(slope_a, h));
-      total += h;
-      if (c.h0 < 0) break;
+      load_stage(base + s);  // (syncs the warp)
+      stage_products(s, sP0, h);
     }
-    // P[0:23,0:23] += Qmodel after every Propagate call (estimator.cpp:590); Qmodel is diagonal
-    for (int t = lane; t < 23; t += 32) sP[t * 23 + t] += c.qmodel[t];
+    const double* bw = pd ? B_pd : B_rk;
+    double sb = 0;
+    for (int q = 0; q < nst; ++q) sb += bw[q];
+    for (int t = lane; t < 207; t += 32) {
+      double f = 0, p = 0;
+      for (int q = 0; q < nst; ++q) { f += bw[q] * sFK[q][t]; p += bw[q] * sA[q][t]; }
+      sAcc[t] = ((t / 23 == t % 23) ? 1.0 : 0.0) + f * h;  // rows 0..8 of I + FK h
+      sSA[t] = p;
+    }
+    if (lane < 9) {
+      double v = 0;
+      for (int q = 0; q < nst; ++q) v += bw[q] * sV[q][lane];
+      sCV[lane] = v;
+    }
+    __syncwarp();
+    for (int t = lane; t < 529; t += 32) {
+      const int i = t / 23, j = t - 23 * i;
+      double inc = strip_sym(sSA, i, j) + sb * gqg_const(i, j);
+      if (i >= 6 && i < 9 && j >= 6 && j < 9) inc += sCV[(i - 6) * 3 + j - 6];
+      sP[t] += inc * h;
+    }
+    // Phi <- (I + FK h) Phi; rows >= 9 of both factors are identity rows
+    for (int t = lane; t < 207; t += 32) {
+      const int i = t / 23, j = t - 23 * i;
+      double v = j >= 9 ? sAcc[i * 23 + j] : 0.0;
+      for (int k = 0; k < 9; ++k) v += sAcc[i * 23 + k] * sPhi[k * 23 + j];
+      sT9[t] = v;
+    }
+    __syncwarp();
+    for (int t = lane; t < 207; t += 32) sPhi[t] = sT9[t];
+    if (henc < 0)  // end of a Propagate call: P[0:23,0:23] += Qmodel (diagonal)
+      for (int t = lane; t < 23; t += 32) sP[t * 23 + t] += c.qmodel[t];
     __syncwarp();
   }
-  // write back: motion block, strips (rows 0..8 change), nominal state
+  // write back: motion block and strips (rows 0..8 change)
   for (int t = lane; t < 529; t += 32) Pb[(size_t)(t / 23) * N + t % 23] = sP[t];
   for (int j = 23 + lane; j < N; j += 32) {
     double col[23];
@@ -692,17 +648,12 @@ __global__ void __launch_bounds__(32) imu_integrate_kernel(int N, double* __rest
       Pb[(size_t)j * N + i] = acc;
     }
   }
-  if (lane == 0) {
-    double* x = Xm + (size_t)b * kMotionDoubles;
-    for (int i = 0; i < 9; ++i) { x[i] = X.Rsb.m[i]; x[21 + i] = X.Rsg.m[i]; }
-    for (int i = 0; i < 3; ++i) { x[9 + i] = X.Tsb.v[i]; x[12 + i] = X.Vsb.v[i]; x[15 + i] = X.bg.v[i]; x[18 + i] = X.ba.v[i]; }
-  }
 }
 
-int launch_imu_integrate(cudaStream_t st, int N, double* P, double* Xm, const ImuSegment* segs, const int* nseg, const ImuConst* cst,
-                         int batch) {
-  ProfScope ps("imu_integrate", st);
-  imu_integrate_kernel<<<batch, 32, 0, st>>>(N, P, Xm, segs, nseg, cst);
+int launch_imu_cov_propagate(cudaStream_t st, int N, double* P, const ImuStage* stages, const int* first, const int* nstages,
+                             const ImuConst* cst, int batch) {
+  ProfScope ps("imu_cov_propagate", st);
+  imu_cov_propagate_kernel<<<batch, 32, 0, st>>>(N, P, stages, first, nstages, cst);
   XB_CUDA(cudaGetLastError());
   return 0;
 }

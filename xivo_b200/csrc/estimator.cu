@@ -97,10 +97,9 @@ class Batch {
   Mirror<EditOp> ops;
   Mirror<SubfilterIn> sub_in;
   Mirror<SubfilterOut> sub_out;
-  Mirror<ImuSegment> segs;
-  Mirror<int> nsegs;
+  Mirror<ImuStage> stg;     // packed stage records of all filters
+  Mirror<int> stg_first, stg_n;
   Mirror<ImuConst> icst;
-  Mirror<double> Xm;
   // tracker device state (allocated at the first image)
   bool img_ready = false;
   int rows = 0, cols = 0, cn = 0, ring_n = 0, max_pts = 0, max_kp = 0;
@@ -136,8 +135,8 @@ class Batch {
          Pmm.alloc((size_t)B * 529) && mh.alloc((size_t)B * lay.F) && pack.alloc((size_t)B * (2 * N + 529)) &&
          fref.alloc((size_t)B * lay.F) && fsind.alloc((size_t)B * lay.F) && nfeat.alloc(B) && sel.alloc((size_t)B * lay.F) &&
          nsel.alloc(B) && nops.alloc(B) && active.alloc(B) && ops.alloc((size_t)B * maxops) &&
-         sub_in.alloc((size_t)B * max_sub) && sub_out.alloc((size_t)B * max_sub) && segs.alloc((size_t)B * kMaxSegments) && nsegs.alloc(B) &&
-         icst.alloc(B) && Xm.alloc((size_t)B * kMotionDoubles);
+         sub_in.alloc((size_t)B * max_sub) && sub_out.alloc((size_t)B * max_sub) && stg.alloc((size_t)B * kMaxStages) && stg_first.alloc(B) && stg_n.alloc(B) &&
+         icst.alloc(B);
     if (!ok) throw std::runtime_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     // initial covariance: identity with the motion block from the config (estimator.cpp:258-302)
     std::vector<double> P0((size_t)N * N, 0.0);
@@ -151,11 +150,10 @@ class Batch {
       {
         const EstimatorCfg& ec = est[b]->c;
         ImuConst& ic = icst.h[b];
-        memcpy(ic.Cg, ec.Cg.m, 72); memcpy(ic.Ca, ec.Ca.m, 72); memcpy(ic.g, ec.g.v, 24);
+        memcpy(ic.g, ec.g.v, 24);
         for (int i = 0; i < 12; ++i) ic.qimu[i] = ec.Qimu[i * 12 + i];
         for (int i = 0; i < 23; ++i) ic.qmodel[i] = ec.Qmodel[i * 23 + i];
-        ic.pd = ec.integration_method == "PrinceDormand" ? 1 : 0;
-        ic.h0 = ic.pd ? ec.pd_stepsize : ec.rk4_stepsize;
+        ic.stages_per_step = ec.integration_method == "PrinceDormand" ? 7 : 4;
         ic.pad = 0;
       }
       for (int i = 0; i < N; ++i) est[b]->diagP[i] = P0[(size_t)i * N + i];
@@ -171,8 +169,8 @@ class Batch {
       if (p) cudaFree(p);
     cam.release(); X.release(); groups.release(); fx.release(); fxp.release(); R.release(); Phi.release(); Pmm.release();
     mh.release(); pack.release(); fref.release(); fsind.release(); nfeat.release(); sel.release(); nsel.release();
-    nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); segs.release(); nsegs.release();
-    icst.release(); Xm.release(); off_prev.release();
+    nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); stg.release(); stg_first.release(); stg_n.release();
+    icst.release(); off_prev.release();
     off_cur.release(); pts0.release(); pts1.release(); lkerr.release(); lkst.release(); npts.release(); kpcount.release();
     kp.release();
   }
@@ -195,38 +193,28 @@ class Batch {
     }
     return 0;
   }
-  // Run the queued Propagate calls of the given sequences on the device (imu_integrate_kernel) and
-  // bring the propagated nominal state back.  One launch + one sync for all of them.
+  // Enqueue the covariance algebra of the queued Runge-Kutta stage records of the given sequences
+  // (imu_cov_propagate_kernel).  Asynchronous: the host already holds the propagated nominal state.
   int integrate(const std::vector<int>& act) {
     cudaStream_t st = ctx->stream;
-    bool any = false;
-    for (int b = 0; b < B; ++b) nsegs.h[b] = 0;
+    int total = 0;
+    for (int b = 0; b < B; ++b) { stg_n.h[b] = 0; stg_first.h[b] = 0; }
     for (int b : act) {
       Estimator& e = *est[b];
-      const int n = (int)e.segments.size();
+      const int n = (int)e.stages.size();
       if (!n) continue;
-      if (n > kMaxSegments) return fail(XIVO_ERR_STATE, "IMU segment queue overflow");
-      any = true;
-      nsegs.h[b] = n;
-      memcpy(segs.h + (size_t)b * kMaxSegments, e.segments.data(), sizeof(ImuSegment) * n);
-      double* x = Xm.h + (size_t)b * kMotionDoubles;
-      memcpy(x, e.X.Rsb.m, 72); memcpy(x + 9, e.X.Tsb.v, 24); memcpy(x + 12, e.X.Vsb.v, 24);
-      memcpy(x + 15, e.X.bg.v, 24); memcpy(x + 18, e.X.ba.v, 24); memcpy(x + 21, e.X.Rsg.m, 72);
-    }
-    if (!any) return 0;
-    XB_CUDA(segs.up(st)); XB_CUDA(nsegs.up(st)); XB_CUDA(Xm.up(st));
-    if (int rc = launch_imu_integrate(st, N, dP, Xm.d, segs.d, nsegs.d, icst.d, B)) return rc;
-    g_launches += 1;
-    XB_CUDA(Xm.down(st));
-    XB_CUDA(cudaStreamSynchronize(st));
-    for (int b : act) {
-      Estimator& e = *est[b];
-      if (!nsegs.h[b]) continue;
-      const double* x = Xm.h + (size_t)b * kMotionDoubles;
-      memcpy(e.X.Rsb.m, x, 72); memcpy(e.X.Tsb.v, x + 9, 24); memcpy(e.X.Vsb.v, x + 12, 24);
-      e.segments.clear();
+      if (n > kMaxStages) return fail(XIVO_ERR_STATE, "IMU stage queue overflow (a single Propagate call longer than ~140 ms?)");
+      stg_first.h[b] = total;
+      stg_n.h[b] = n;
+      memcpy(stg.h + total, e.stages.data(), sizeof(ImuStage) * n);
+      total += n;
+      e.stages.clear();
       e.prop_pending = false;
     }
+    if (!total) return 0;
+    XB_CUDA(stg.up(st, total)); XB_CUDA(stg_first.up(st)); XB_CUDA(stg_n.up(st));
+    if (int rc = launch_imu_cov_propagate(st, N, dP, stg.d, stg_first.d, stg_n.d, icst.d, B)) return rc;
+    g_launches += 1;
     return 0;
   }
   // apply pending propagation + edits of the given sequences (used before state / P read-back)
@@ -463,11 +451,7 @@ class Batch {
     }
     if (int rc = first_error(act_in)) return rc;
     {
-      // propagate up to the frame time on the device, then predict / point-cloud bookkeeping on the host
-      std::vector<int> prop;
-      for (size_t i = 0; i < act_in.size(); ++i)
-        if (proceed[i] && (msgs[i].type == 1 || msgs[i].type == 3)) prop.push_back(act_in[i]);
-      if (int rc = integrate(prop)) return rc;
+      // predict / point-cloud bookkeeping on the host (the nominal state is already propagated)
       HostScope hs("predict");
       std::vector<int> ord(act_in.size());
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
@@ -573,6 +557,7 @@ class Batch {
     }
     XB_CUDA(groups.up(st)); XB_CUDA(fx.up(st)); XB_CUDA(fxp.up(st)); XB_CUDA(fref.up(st)); XB_CUDA(fsind.up(st));
     XB_CUDA(nfeat.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
+    if (int rc = integrate(full)) return rc;  // covariance side of Propagate, before the slot edits read P
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
     if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B))
       return rc;
@@ -854,20 +839,17 @@ static void put34(const SE3h& g, double* out) {
 }
 int xivo_get_gsb(xivo_batch* b, int seq, double* out) {
   BATCH_BEGIN; SEQ_CHECK;
-  if (int rc = B_.integrate({seq})) return rc;
   put34(B_.est[seq]->gsb(), out);
   return 0;
 }
 int xivo_get_gbc(xivo_batch* b, int seq, double* out) { BATCH_BEGIN; SEQ_CHECK; put34(B_.est[seq]->gbc(), out); return 0; }
 int xivo_get_gsc(xivo_batch* b, int seq, double* out) {
   BATCH_BEGIN; SEQ_CHECK;
-  if (int rc = B_.integrate({seq})) return rc;
   put34(se3_mul(B_.est[seq]->gsb(), B_.est[seq]->gbc()), out);
   return 0;
 }
 int xivo_get_motion(xivo_batch* b, int seq, double* Vsb, double* bg, double* ba, double* Rsg) {
   BATCH_BEGIN; SEQ_CHECK;
-  if (int rc = B_.integrate({seq})) return rc;
   const MotionX& X = B_.est[seq]->X;
   if (Vsb) memcpy(Vsb, X.Vsb.v, 24);
   if (bg) memcpy(bg, X.bg.v, 24);

@@ -229,9 +229,9 @@ class Estimator {
   double Pmm[529];  // host mirror of the motion block of P
   double Phi[529];  // pending strip transition (product of per-substep F)
   bool prop_pending = false;
-  std::vector<ImuSegment> segments;  // Propagate calls not yet integrated on the device
-  // true when host logic needs the propagated nominal state before the next message (clamping uses Rsb)
-  bool needs_state_now() const { return !segments.empty() && (c.clamp_signals || (int)segments.size() >= kMaxSegments - 2); }
+  std::vector<ImuStage> stages;  // Runge-Kutta stage records whose covariance algebra has not run on the device yet
+  // the queue must be flushed to the device before it can overflow (one Propagate call adds <= ~256 records)
+  bool needs_state_now() const { return (int)stages.size() > kMaxStages - 320; }
   std::vector<EditOp> edits;  // pending covariance edits, in order
   std::vector<double> diagP;  // last downloaded diagonal of P
   std::vector<char> gsel, fsel;
@@ -280,6 +280,10 @@ class Estimator {
   void update_system_clock(uint64_t now);
   bool initialize_gravity();
   void propagate(bool visual_meas);
+  void compose_motion(MotionX& Xs, const V3& V, const V3& gyro, const V3& accel, double dt) const;
+  void record_stage(const MotionX& Xs, const V3& gyro, const V3& accel, double h_enc);
+  void nominal_step(bool pd, const V3& gyro0, const V3& accel0, double h, bool closes_call);
+  void integrate_nominal(const V3& gyro0, const V3& accel0, double dt);
   void state_plus(const double* dX);
   // state slots
   void add_group_to_state(Group* g);

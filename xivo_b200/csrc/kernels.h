@@ -95,21 +95,25 @@ int launch_oos(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const do
 }  // namespace xb
 
 namespace xb {
-// ---------------- IMU propagation on device (ekf_kernels.cu) ----------------
-// One integration segment = one Estimator::Propagate call (src/estimator.cpp:539-592): constant
-// slopes, duration dt, split into fixed sub-steps like PrinceDormand()/RK4() do.
-struct ImuSegment {
-  double gyro0[3], accel0[3], slope_gyro[3], slope_accel[3], dt;
+// ---------------- IMU covariance propagation on device (ekf_kernels.cu) ----------------
+// The nominal motion state is a short, strictly sequential fp64 chain (sin/cos, quaternion
+// renormalisation) — a CPU core runs it ~30x faster than one GPU thread — so the host integrates it and
+// records, for every Runge-Kutta stage, what the motion Jacobian depends on.  The device does the
+// covariance algebra (23x23 block + strips) of all filters in parallel from those records.
+struct ImuStage {
+  double R[9];   // Rsb at the stage
+  double gc[3];  // calibrated gyro  Cg*gyro - bg
+  double ac[3];  // calibrated accel Ca*accel - ba
+  double h;      // sub-step length, stored on the FIRST stage of each sub-step; negative = this sub-step closes a
+                 // Propagate call (add Qmodel afterwards, src/estimator.cpp:590)
 };
-constexpr int kMaxSegments = 24;
-constexpr int kMotionDoubles = 30;  // Rsb(9) Tsb(3) Vsb(3) bg(3) ba(3) Rsg(9)
-struct ImuConst {                   // per filter
-  double Cg[9], Ca[9], g[3], qimu[12], qmodel[23], h0;
-  int pd;  // 1 = Prince-Dormand, 0 = RK4
+constexpr int kMaxStages = 1024;  // per filter between two flushes (one Propagate call with dt = 40 ms needs 140)
+struct ImuConst {  // per filter
+  double g[3], qimu[12], qmodel[23];
+  int stages_per_step;  // 7 = Prince-Dormand, 4 = RK4
   int pad;
 };
-// Integrates nominal motion state, P[0:23,0:23] and the strips P[0:23,23:] / P[23:,0:23] through
-// the queued segments of every filter.  Xm: B x 30 in/out.
-int launch_imu_integrate(cudaStream_t st, int N, double* P, double* Xm, const ImuSegment* segs /*B x kMaxSegments*/,
-                         const int* nseg /*B*/, const ImuConst* cst /*B*/, int batch);
+// stages: packed; filter b reads stages[first[b] .. first[b] + nstages[b])
+int launch_imu_cov_propagate(cudaStream_t st, int N, double* P, const ImuStage* stages, const int* first /*B*/, const int* nstages /*B*/,
+                             const ImuConst* cst /*B*/, int batch);
 }  // namespace xb
