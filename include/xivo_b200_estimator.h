@@ -57,7 +57,8 @@ int xivo_batch_visual_meas_device(xivo_batch* b, const uint64_t* ts_ns, const ui
 int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const double* gyro, const double* accel,
                     const uint64_t* frame_ts, const uint8_t* const* imgs, int rows, int cols, int channels, int on_device);
 
-/* Per-kernel CUDA-event timing + host<->device byte counters (bench.py's roofline / e2e fields). */
+/* Per-kernel CUDA-event timing + host<->device byte counters (bench.py's roofline / e2e fields).
+ * on: 0 off, 1 kernels + batch-level host phases, 2 additionally per-sequence host scopes (slow). */
 void xivo_profile_enable(int on);
 void xivo_profile_reset(void);
 int xivo_profile_report(char* json_out, int capacity);

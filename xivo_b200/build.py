@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxivo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp", "-Xptxas", "-v"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-pthread", "-Xptxas", "-v"]
 
 # (source, extra flags).  The tracker is compiled without FMA contraction so its float math
 # rounds exactly like the scalar CPU arithmetic of OpenCV's LK (see tracker_kernels.cu).
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 f.write(r.stderr)
         objs.append(o)
     if force or _newer(objs, LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lgomp"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

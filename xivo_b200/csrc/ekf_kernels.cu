@@ -501,73 +501,88 @@ __device__ __forceinline__ double hat_elem(const double* w, int k, int j) {  // 
   return sgn * w[o];
 }
 
-__global__ void __launch_bounds__(32) imu_cov_propagate_kernel(int N, double* __restrict__ P, const ImuStage* __restrict__ stages,
-                                                               const int* __restrict__ first, const int* __restrict__ nstages,
-                                                               const ImuConst* __restrict__ cst) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+__constant__ double kApd[6][6] = {{2.0 / 9, 0, 0, 0, 0, 0},
+                                  {1.0 / 12, 3.0 / 12, 0, 0, 0, 0},
+                                  {55.0 / 324, -75.0 / 324, 200.0 / 324, 0, 0, 0},
+                                  {83.0 / 330, -195.0 / 330, 305.0 / 330, 27.0 / 330, 0, 0},
+                                  {-19.0 / 28, 63.0 / 28, 4.0 / 28, -108.0 / 28, 88.0 / 28, 0},
+                                  {38.0 / 400, 0, 240.0 / 400, -243.0 / 400, 330.0 / 400, 35.0 / 400}};
+__constant__ double kBpd[7] = {0.0862, 0.0, 0.6660, -0.7857, 0.9570, 0.0965, -0.0200};
+__constant__ double kArk[3][6] = {{0.5, 0, 0, 0, 0, 0}, {0, 0.5, 0, 0, 0, 0}, {0, 0, 1.0, 0, 0, 0}};
+__constant__ double kBrk[4] = {1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6};
+
+constexpr int IMU_THREADS = 128;
+__global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, double* __restrict__ P, const ImuStage* __restrict__ stages,
+                                                                        const int* __restrict__ first, const int* __restrict__ nstages,
+                                                                        const ImuConst* __restrict__ cst) {
+  const int b = blockIdx.x, tid = threadIdx.x;
   const int nall = nstages[b];
   if (nall == 0) return;
-  __shared__ double sP[529], sP0[529], sA[7][207], sFK[7][207], sSA[207], sAcc[207], sT9[207], sPhi[207], sV[7][9], sCV[9];
+  __shared__ double sP[529], sP0[529], sA[7][207], sFK[7][207], sSA[207], sAcc[207], sT9[207], sPhi[207], sV[7][9], sCV[9], sGc[23];
   __shared__ F9s sF;
   __shared__ ImuStage sStage;
-  const ImuConst c = cst[b];
-  const int nst = c.stages_per_step;
+  __shared__ ImuConst c;
+  __shared__ unsigned char sI[529], sJ[529];  // row / column of a flat 23x23 index (no div/mod in the loops)
+  if (tid < (int)(sizeof(ImuConst) / 8)) reinterpret_cast<double*>(&c)[tid] = reinterpret_cast<const double*>(cst + b)[tid];
+  for (int t = tid; t < 529; t += IMU_THREADS) { sI[t] = (unsigned char)(t / 23); sJ[t] = (unsigned char)(t % 23); }
   double* __restrict__ Pb = P + (size_t)b * N * N;
   const ImuStage* __restrict__ stg = stages + first[b];
-  for (int t = lane; t < 529; t += 32) sP[t] = Pb[(size_t)(t / 23) * N + t % 23];
-  for (int t = lane; t < 207; t += 32) sPhi[t] = (t / 23 == t % 23) ? 1.0 : 0.0;
-  __syncwarp();
-  const double A_pd[6][6] = {{2.0 / 9, 0, 0, 0, 0, 0},
-                             {1.0 / 12, 3.0 / 12, 0, 0, 0, 0},
-                             {55.0 / 324, -75.0 / 324, 200.0 / 324, 0, 0, 0},
-                             {83.0 / 330, -195.0 / 330, 305.0 / 330, 27.0 / 330, 0, 0},
-                             {-19.0 / 28, 63.0 / 28, 4.0 / 28, -108.0 / 28, 88.0 / 28, 0},
-                             {38.0 / 400, 0, 240.0 / 400, -243.0 / 400, 330.0 / 400, 35.0 / 400}};
-  const double B_pd[7] = {0.0862, 0.0, 0.6660, -0.7857, 0.9570, 0.0965, -0.0200};
-  const double A_rk[3][6] = {{0.5, 0, 0, 0, 0, 0}, {0, 0.5, 0, 0, 0, 0}, {0, 0, 1.0, 0, 0, 0}};
-  const double B_rk[4] = {1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6};
+  for (int t = tid; t < 529; t += IMU_THREADS) sP[t] = Pb[(size_t)(t / 23) * N + t % 23];
+  for (int t = tid; t < 207; t += IMU_THREADS) sPhi[t] = (t / 23 == t % 23) ? 1.0 : 0.0;
+  __syncthreads();
+  const int nst = c.stages_per_step;
   const bool pd = nst == 7;
-  auto strip_sym = [&](const double* S, int i, int j) { return (i < 9 ? S[i * 23 + j] : 0.0) + (j < 9 ? S[j * 23 + i] : 0.0); };
-  auto gqg_const = [&](int i, int j) {  // the state-independent diagonal part of G Q G^T
-    if (i != j) return 0.0;
-    if (i < 3) return c.qimu[i];
-    if (i >= 9 && i < 12) return c.qimu[6 + i - 9];
-    if (i >= 12 && i < 15) return c.qimu[9 + i - 12];
-    return 0.0;
-  };
+  if (tid < 23) {  // state-independent diagonal of G Q G^T
+    double v = 0.0;
+    if (tid < 3) v = c.qimu[tid];
+    else if (tid >= 9 && tid < 12) v = c.qimu[6 + tid - 9];
+    else if (tid >= 12 && tid < 15) v = c.qimu[9 + tid - 12];
+    sGc[tid] = v;
+  }
+  __syncthreads();
   // build the non-zero blocks of F from a stage record: dW = -hat(gc), dVW = -R hat(ac), dVba = -R, dVg = (-R hat(g))[:, :2]
   auto load_stage = [&](int idx) {
     const double* src = reinterpret_cast<const double*>(stg + idx);
-    if (lane < 16) reinterpret_cast<double*>(&sStage)[lane] = src[lane];
-    __syncwarp();
-    if (lane < 9) {
-      const int i = lane / 3, j = lane - 3 * i;
-      sF.R[lane] = sStage.R[lane];
-      sF.dVba[lane] = -sStage.R[lane];
-      sF.dW[lane] = -hat_elem(sStage.gc, i, j);
+    if (tid < 16) reinterpret_cast<double*>(&sStage)[tid] = src[tid];
+    __syncthreads();
+    if (tid < 9) {
+      const int i = tid / 3, j = tid - 3 * i;
+      sF.R[tid] = sStage.R[tid];
+      sF.dVba[tid] = -sStage.R[tid];
+      sF.dW[tid] = -hat_elem(sStage.gc, i, j);
       double v = 0, vg = 0;
       for (int k = 0; k < 3; ++k) {
         v += sStage.R[3 * i + k] * hat_elem(sStage.ac, k, j);
         vg += sStage.R[3 * i + k] * hat_elem(c.g, k, j);
       }
-      sF.dVW[lane] = -v;
+      sF.dVW[tid] = -v;
       if (j < 2) sF.dVg[2 * i + j] = -vg;
     }
-    __syncwarp();
+    __syncthreads();
   };
   auto stage_products = [&](int s, const double* Pin, double h) {
     // FK[s] = F + (F acc) h  (acc holds sum a FK; unused for s == 0), A[s] = F[0:9,:] Pin, V[s] = R qa R^T
-    for (int t = lane; t < 207; t += 32) {
-      const int i = t / 23, j = t - 23 * i;
+    for (int t = tid; t < 207; t += IMU_THREADS) {
+      const int i = sI[t], j = sJ[t];
       const double fd = f9_dense(sF, i, j);
       sFK[s][t] = s == 0 ? fd : fd + f9_elem(sF, sAcc, i, j, true) * h;
       sA[s][t] = f9_elem(sF, Pin, i, j, false);
     }
-    if (lane < 9) {
-      const int i = lane / 3, j = lane - 3 * i;
-      sV[s][lane] = sF.R[3 * i] * c.qimu[3] * sF.R[3 * j] + sF.R[3 * i + 1] * c.qimu[4] * sF.R[3 * j + 1] + sF.R[3 * i + 2] * c.qimu[5] * sF.R[3 * j + 2];
+    if (tid < 9) {
+      const int i = tid / 3, j = tid - 3 * i;
+      sV[s][tid] = sF.R[3 * i] * c.qimu[3] * sF.R[3 * j] + sF.R[3 * i + 1] * c.qimu[4] * sF.R[3 * j + 1] + sF.R[3 * i + 2] * c.qimu[5] * sF.R[3 * j + 2];
     }
-    __syncwarp();
+    __syncthreads();
+  };
+  // X += w * (strip_sym(S) + sw * gqg_const + V-block CV)
+  auto add_sym = [&](double* dst, const double* base, double sw, double h) {
+    for (int t = tid; t < 529; t += IMU_THREADS) {
+      const int i = sI[t], j = sJ[t];
+      double inc = (i < 9 ? sSA[i * 23 + j] : 0.0) + (j < 9 ? sSA[j * 23 + i] : 0.0);
+      if (i == j) inc += sw * sGc[i];
+      if (i >= 6 && i < 9 && j >= 6 && j < 9) inc += sCV[(i - 6) * 3 + j - 6];
+      dst[t] = base[t] + inc * h;
+    }
   };
   for (int base = 0; base + nst <= nall; base += nst) {
     load_stage(base);
@@ -575,67 +590,57 @@ __global__ void __launch_bounds__(32) imu_cov_propagate_kernel(int N, double* __
     const double h = fabs(henc);
     stage_products(0, sP, h);
     for (int s = 1; s < nst; ++s) {
-      const double* a = pd ? A_pd[s - 1] : A_rk[s - 1];
+      const double* a = pd ? kApd[s - 1] : kArk[s - 1];
       double sa = 0;
       for (int q = 0; q < s; ++q) sa += a[q];
-      for (int t = lane; t < 207; t += 32) {
+      for (int t = tid; t < 207; t += IMU_THREADS) {
         double f = 0, p = 0;
         for (int q = 0; q < s; ++q) { f += a[q] * sFK[q][t]; p += a[q] * sA[q][t]; }
         sAcc[t] = f;
         sSA[t] = p;
       }
-      if (lane < 9) {
+      if (tid < 9) {
         double v = 0;
-        for (int q = 0; q < s; ++q) v += a[q] * sV[q][lane];
-        sCV[lane] = v;
+        for (int q = 0; q < s; ++q) v += a[q] * sV[q][tid];
+        sCV[tid] = v;
       }
-      __syncwarp();
-      for (int t = lane; t < 529; t += 32) {
-        const int i = t / 23, j = t - 23 * i;
-        double inc = strip_sym(sSA, i, j) + sa * gqg_const(i, j);
-        if (i >= 6 && i < 9 && j >= 6 && j < 9) inc += sCV[(i - 6) * 3 + j - 6];
-        sP0[t] = sP[t] + inc * h;
-      }
-      load_stage(base + s);  // (syncs the warp)
+      __syncthreads();
+      add_sym(sP0, sP, sa, h);
+      load_stage(base + s);  // (block-wide syncs inside)
       stage_products(s, sP0, h);
     }
-    const double* bw = pd ? B_pd : B_rk;
+    const double* bw = pd ? kBpd : kBrk;
     double sb = 0;
     for (int q = 0; q < nst; ++q) sb += bw[q];
-    for (int t = lane; t < 207; t += 32) {
+    for (int t = tid; t < 207; t += IMU_THREADS) {
       double f = 0, p = 0;
       for (int q = 0; q < nst; ++q) { f += bw[q] * sFK[q][t]; p += bw[q] * sA[q][t]; }
-      sAcc[t] = ((t / 23 == t % 23) ? 1.0 : 0.0) + f * h;  // rows 0..8 of I + FK h
+      sAcc[t] = ((sI[t] == sJ[t]) ? 1.0 : 0.0) + f * h;  // rows 0..8 of I + FK h
       sSA[t] = p;
     }
-    if (lane < 9) {
+    if (tid < 9) {
       double v = 0;
-      for (int q = 0; q < nst; ++q) v += bw[q] * sV[q][lane];
-      sCV[lane] = v;
+      for (int q = 0; q < nst; ++q) v += bw[q] * sV[q][tid];
+      sCV[tid] = v;
     }
-    __syncwarp();
-    for (int t = lane; t < 529; t += 32) {
-      const int i = t / 23, j = t - 23 * i;
-      double inc = strip_sym(sSA, i, j) + sb * gqg_const(i, j);
-      if (i >= 6 && i < 9 && j >= 6 && j < 9) inc += sCV[(i - 6) * 3 + j - 6];
-      sP[t] += inc * h;
-    }
+    __syncthreads();
+    add_sym(sP, sP, sb, h);
     // Phi <- (I + FK h) Phi; rows >= 9 of both factors are identity rows
-    for (int t = lane; t < 207; t += 32) {
-      const int i = t / 23, j = t - 23 * i;
+    for (int t = tid; t < 207; t += IMU_THREADS) {
+      const int i = sI[t], j = sJ[t];
       double v = j >= 9 ? sAcc[i * 23 + j] : 0.0;
+#pragma unroll
       for (int k = 0; k < 9; ++k) v += sAcc[i * 23 + k] * sPhi[k * 23 + j];
       sT9[t] = v;
     }
-    __syncwarp();
-    for (int t = lane; t < 207; t += 32) sPhi[t] = sT9[t];
-    if (henc < 0)  // end of a Propagate call: P[0:23,0:23] += Qmodel (diagonal)
-      for (int t = lane; t < 23; t += 32) sP[t * 23 + t] += c.qmodel[t];
-    __syncwarp();
+    __syncthreads();
+    for (int t = tid; t < 207; t += IMU_THREADS) sPhi[t] = sT9[t];
+    if (henc < 0 && tid < 23) sP[tid * 23 + tid] += c.qmodel[tid];  // end of a Propagate call: += Qmodel (diagonal)
+    __syncthreads();
   }
   // write back: motion block and strips (rows 0..8 change)
-  for (int t = lane; t < 529; t += 32) Pb[(size_t)(t / 23) * N + t % 23] = sP[t];
-  for (int j = 23 + lane; j < N; j += 32) {
+  for (int t = tid; t < 529; t += IMU_THREADS) Pb[(size_t)sI[t] * N + sJ[t]] = sP[t];
+  for (int j = 23 + tid; j < N; j += IMU_THREADS) {
     double col[23];
 #pragma unroll
     for (int k = 0; k < 23; ++k) col[k] = Pb[(size_t)k * N + j];
@@ -653,7 +658,7 @@ __global__ void __launch_bounds__(32) imu_cov_propagate_kernel(int N, double* __
 int launch_imu_cov_propagate(cudaStream_t st, int N, double* P, const ImuStage* stages, const int* first, const int* nstages,
                              const ImuConst* cst, int batch) {
   ProfScope ps("imu_cov_propagate", st);
-  imu_cov_propagate_kernel<<<batch, 32, 0, st>>>(N, P, stages, first, nstages, cst);
+  imu_cov_propagate_kernel<<<batch, IMU_THREADS, 0, st>>>(N, P, stages, first, nstages, cst);
   XB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,7 +1,6 @@
 // Estimator-level C ABI (include/xivo_b200_estimator.h): a Batch of independent estimators that
 // advance in lock-step.  The host state machines (estimator_host.cpp.inc) decide; every numeric hot
 // loop runs in the CUDA kernels of tracker_kernels.cu / ekf_kernels.cu, batched over sequences.
-#include <omp.h>
 
 #include <algorithm>
 #include <atomic>
@@ -14,6 +13,7 @@
 #include "ctx.h"
 #include "estimator.h"
 #include "prof.h"
+#include "workpool.h"
 
 namespace xb {
 // Host wall-clock phases go into the same profile report as the kernels ("host:<phase>").
@@ -23,6 +23,11 @@ struct HostScope {
   explicit HostScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
   ~HostScope() {
     if (!Prof::get().enabled.load(std::memory_order_relaxed)) return;
+    if (name[0] == 'x' && name[1] == '_') {
+      if (Prof::get().fine.load(std::memory_order_relaxed))
+        Prof::get().fine_tab.add(name, (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+      return;
+    }
     Prof::get().add_host(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   }
 };
@@ -64,18 +69,11 @@ struct Mirror {
 
 class Batch {
  public:
-  int nthreads = 1;
-  // Per-sequence host logic is independent across sequences: run it on a small OpenMP team.  CUDA calls
-  // stay on the calling thread.
+  // Per-sequence host logic is independent across sequences: run it on the process-wide worker pool
+  // (workpool.h).  CUDA calls stay on the calling thread.
   template <typename Fn>
   void pfor(const std::vector<int>& idx, Fn fn) {
-    const int n = (int)idx.size();
-    if (nthreads <= 1 || n <= 1) {
-      for (int i = 0; i < n; ++i) fn(idx[i], i);
-      return;
-    }
-#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
-    for (int i = 0; i < n; ++i) fn(idx[i], i);
+    WorkPool::get().pfor((int)idx.size(), [&](int i) { fn(idx[i], i); });
   }
   int first_error(const std::vector<int>& idx) {
     for (int b : idx)
@@ -100,6 +98,11 @@ class Batch {
   Mirror<ImuStage> stg;     // packed stage records of all filters
   Mirror<int> stg_first, stg_n;
   Mirror<ImuConst> icst;
+  // The covariance side (IMU propagation, slot edits, Jacobians, update) runs on its own stream so that it
+  // overlaps the image tracker's kernels and host phases, which use ctx->stream.
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t stg_ev = nullptr;  // stage-record upload finished (the pinned staging buffer may be refilled)
+  bool stg_inflight = false;
   // tracker device state (allocated at the first image)
   bool img_ready = false;
   int rows = 0, cols = 0, cn = 0, ring_n = 0, max_pts = 0, max_kp = 0;
@@ -116,13 +119,9 @@ class Batch {
 
   Batch(xivo_ctx* c, const Json& cfg, int nseq, EkfLayout l, bool tracker_only) : ctx(c), B(nseq), lay(l) {
     N = lay.N();
+    cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&stg_ev, cudaEventDisableTiming);
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
-    {
-      const char* env = getenv("XIVO_THREADS");
-      int hw = (int)std::thread::hardware_concurrency();
-      nthreads = env ? atoi(env) : std::min(32, std::max(1, hw / 2));
-      nthreads = std::max(1, std::min(nthreads, B));
-    }
     maxops = 4 * (lay.F + lay.G) + 16;
     max_sub = est[0]->tc.num_features_max + 8;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dP), sizeof(double) * B * N * N) == cudaSuccess &&
@@ -165,6 +164,8 @@ class Batch {
   }
   ~Batch() {
     cudaStreamSynchronize(ctx->stream);
+    if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
+    if (stg_ev) cudaEventDestroy(stg_ev);
     for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr})
       if (p) cudaFree(p);
     cam.release(); X.release(); groups.release(); fx.release(); fxp.release(); R.release(); Phi.release(); Pmm.release();
@@ -196,8 +197,12 @@ class Batch {
   // Enqueue the covariance algebra of the queued Runge-Kutta stage records of the given sequences
   // (imu_cov_propagate_kernel).  Asynchronous: the host already holds the propagated nominal state.
   int integrate(const std::vector<int>& act) {
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = st2;
     int total = 0;
+    bool any = false;
+    for (int b : act) any = any || !est[b]->stages.empty();
+    if (!any) return 0;
+    if (stg_inflight) { XB_CUDA(cudaEventSynchronize(stg_ev)); stg_inflight = false; }
     for (int b = 0; b < B; ++b) { stg_n.h[b] = 0; stg_first.h[b] = 0; }
     for (int b : act) {
       Estimator& e = *est[b];
@@ -213,19 +218,21 @@ class Batch {
     }
     if (!total) return 0;
     XB_CUDA(stg.up(st, total)); XB_CUDA(stg_first.up(st)); XB_CUDA(stg_n.up(st));
+    XB_CUDA(cudaEventRecord(stg_ev, st));
+    stg_inflight = true;
     if (int rc = launch_imu_cov_propagate(st, N, dP, stg.d, stg_first.d, stg_n.d, icst.d, B)) return rc;
     g_launches += 1;
     return 0;
   }
   // apply pending propagation + edits of the given sequences (used before state / P read-back)
   int flush(const std::vector<int>& act) {
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = st2;
     if (int rc = integrate(act)) return rc;
     if (int rc = stage_edits(act)) return rc;
     XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
     g_launches += 1;
-    XB_CUDA(cudaStreamSynchronize(st));
+    { HostScope hw("wait_flush"); XB_CUDA(cudaStreamSynchronize(st)); }
     return 0;
   }
 
@@ -308,6 +315,7 @@ class Batch {
     std::atomic<int> overflow{0};
     {
       HostScope hs("tracker_prepare");
+      HostScope hrc("ring_copy");
       for (size_t i = 0; i < act.size(); ++i) {
         const int b = act[i];
         const int cur = 1 - prev_slot[b];
@@ -374,7 +382,7 @@ class Batch {
         Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
       }
       XB_CUDA(pts1.down(st)); XB_CUDA(lkst.down(st));
-      XB_CUDA(cudaStreamSynchronize(st));
+      { HostScope hw("wait_lk"); XB_CUDA(cudaStreamSynchronize(st)); }
       HostScope hs("tracker_accept");
       std::vector<int> need(B, 0);
       pfor(lk_list, [&](int b, int) {
@@ -415,12 +423,12 @@ class Batch {
       g_launches += 1;
       Prof::get().add_work("fast_detect", det_list.size() * 2.0 * rows * cols);  // §8d: 2 W H bytes
       XB_CUDA(kpcount.down(st));
-      XB_CUDA(cudaStreamSynchronize(st));
+      { HostScope hw("wait_fastcount"); XB_CUDA(cudaStreamSynchronize(st)); }
       for (int b : det_list) {
         const int n = std::min(kpcount.h[b], max_kp);
         if (n) { Prof::get().d2h += sizeof(unsigned) * n; XB_CUDA(cudaMemcpyAsync(kp.h + (size_t)b * max_kp, kp.d + (size_t)b * max_kp, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st)); }
       }
-      XB_CUDA(cudaStreamSynchronize(st));
+      { HostScope hw("wait_fastkp"); XB_CUDA(cudaStreamSynchronize(st)); }
       HostScope hs("tracker_select");
       pfor(det_list, [&](int b, int) {
         Estimator& e = *est[b];
@@ -435,7 +443,7 @@ class Batch {
 
   // ---- one visual message per active sequence ----------------------------------------------
   int process_visual(const std::vector<int>& act_in, std::vector<Msg>& msgs) {
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = st2;  // covariance-side stream; the image tracker uses ctx->stream
     std::vector<int> act, full, lk_act, lk_slots;
     std::vector<char> proceed(act_in.size(), 0);
     {
@@ -476,6 +484,8 @@ class Batch {
       if (msgs[i].type == 1 || msgs[i].type == 2) { lk_act.push_back(b); lk_slots.push_back(msgs[i].img_slot); }
       if (msgs[i].type == 1 || msgs[i].type == 3) full.push_back(b);
     }
+    // covariance side of Propagate: enqueued now, overlaps the tracker (nothing below touches P before phase J)
+    if (int rc = integrate(full)) return rc;
     if (!lk_act.empty()) {
       if (int rc = tracker_update_lk(lk_act, lk_slots)) return rc;
       if (int rc = first_error(lk_act)) return rc;
@@ -521,7 +531,7 @@ class Batch {
       if (int rc = launch_subfilter(st, cam.d, X.d, sub_in.d, sub_out.d, nsub, est[0]->c.sub_Rtri, est[0]->c.sub_mh)) return rc;
       g_launches += 1;
       XB_CUDA(sub_out.down(st, nsub));
-      XB_CUDA(cudaStreamSynchronize(st));
+      { HostScope hw("wait_subfilter"); XB_CUDA(cudaStreamSynchronize(st)); }
     }
     // ---- select/add features, fill the device tables ----
     std::atomic<int> bad_slot{0};
@@ -557,7 +567,6 @@ class Batch {
     }
     XB_CUDA(groups.up(st)); XB_CUDA(fx.up(st)); XB_CUDA(fxp.up(st)); XB_CUDA(fref.up(st)); XB_CUDA(fsind.up(st));
     XB_CUDA(nfeat.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
-    if (int rc = integrate(full)) return rc;  // covariance side of Propagate, before the slot edits read P
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
     if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B))
       return rc;
@@ -568,7 +577,7 @@ class Batch {
       Prof::get().add_work("jacobian_gate", nf * 2.0 * N * 8.0);  // §8d: M N 8 bytes of H written
     }
     XB_CUDA(mh.down(st));
-    XB_CUDA(cudaStreamSynchronize(st));
+    { HostScope hw("wait_jacobian"); XB_CUDA(cudaStreamSynchronize(st)); }
     // ---- gating decisions (host), post-gate edits, update (device) ----
     {
       HostScope hs("gating");
@@ -598,7 +607,7 @@ class Batch {
       if (M > 0) Prof::get().add_work("ekf_update", 4 * Nn * Nn * Nn + 6 * M * Nn * Nn + 4 * M * M * Nn + M * M * M / 3.0);  // §8d Joseph flop count
     }
     XB_CUDA(pack.down(st));
-    XB_CUDA(cudaStreamSynchronize(st));
+    { HostScope hw("wait_update"); XB_CUDA(cudaStreamSynchronize(st)); }
     Prof::get().collect();
     std::atomic<int> notpd{0};
     {
@@ -619,6 +628,7 @@ class Batch {
   // sequence runs ahead through its IMU messages until its heap releases a visual message; those are
   // then processed together, and the loop continues with the remaining messages.
   int ingest_many(std::vector<std::vector<Msg>>& in) {
+    WorkPool::get().pin_driver();
     std::vector<int> all(B), vis;
     std::vector<size_t> pos(B, 0);
     std::vector<Msg> popped(B), vmsgs;
@@ -661,6 +671,7 @@ class Batch {
 
   // Push one message per sequence, then execute whatever each heap releases (MaintainBuffer).
   int ingest(std::vector<Msg>& in) {
+    WorkPool::get().pin_driver();
     std::vector<int> all(B), vis;
     std::vector<Msg> popped(B), vmsgs;
     std::vector<char> has(B, 0);
@@ -785,6 +796,7 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
   const size_t ib = (size_t)rows * cols * channels;
   const int nb = B_.B;
   std::vector<std::vector<Msg>> in(nb);
+  HostScope* hm = new HostScope("marshal");
   for (int s = 0; s < nb; ++s) {
     XB_REQUIRE(imgs[s], "batch_step: null image");
     in[s].resize(n_imu + 1);
@@ -805,10 +817,15 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
     v.type = 1;
     v.img_slot = slot;
   }
+  delete hm;
+  HostScope hst("ingest_many_total");
   return B_.ingest_many(in);
 }
 
-void xivo_profile_enable(int on) { Prof::get().enabled = on != 0; }
+void xivo_profile_enable(int on) {
+  Prof::get().enabled = on != 0;
+  Prof::get().fine = on >= 2;
+}
 void xivo_profile_reset(void) { Prof::get().reset(); }
 int xivo_profile_report(char* buf, int n) {
   const std::string s = Prof::get().json();

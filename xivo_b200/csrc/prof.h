@@ -24,13 +24,41 @@ struct ProfRec {
   cudaEvent_t a = nullptr, b = nullptr;
   bool armed = false;
 };
+// Lock-free accumulators for the per-sequence host scopes (many threads, microsecond regions).
+struct FineTable {
+  struct Slot {
+    std::atomic<const char*> name{nullptr};
+    std::atomic<unsigned long long> ns{0}, calls{0};
+    char pad[40];
+  } slot[64];
+  void add(const char* n, unsigned long long ns) {
+    for (auto& e : slot) {
+      const char* cur = e.name.load(std::memory_order_relaxed);
+      if (!cur) {
+        const char* expect = nullptr;
+        if (e.name.compare_exchange_strong(expect, n)) cur = n;
+        else cur = expect;
+      }
+      if (cur == n) {
+        e.ns.fetch_add(ns, std::memory_order_relaxed);
+        e.calls.fetch_add(1, std::memory_order_relaxed);
+        return;
+      }
+    }
+  }
+  void reset() {
+    for (auto& e : slot) { e.ns = 0; e.calls = 0; }
+  }
+};
 class Prof {
  public:
+  FineTable fine_tab;
   static Prof& get() {
     static Prof p;
     return p;
   }
   std::atomic<bool> enabled{false};
+  std::atomic<bool> fine{false};  // per-sequence host scopes ("x_*"): contended, only for host-side diagnosis
   std::atomic<unsigned long long> h2d{0}, d2h{0};
   ProfRec* start(const char* name, cudaStream_t st) {
     if (!enabled.load(std::memory_order_relaxed)) return nullptr;
@@ -90,6 +118,7 @@ class Prof {
     collect(true);
     std::lock_guard<std::mutex> lk(mu_);
     acc_.clear();
+    fine_tab.reset();
     h2d = 0;
     d2h = 0;
   }
@@ -102,6 +131,14 @@ class Prof {
       char buf[256];
       snprintf(buf, sizeof(buf), "%s\"%s\": {\"calls\": %llu, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ", kv.first.c_str(), kv.second.calls,
                kv.second.ms, kv.second.work);
+      s += buf;
+      first = false;
+    }
+    for (auto& e : fine_tab.slot) {
+      const char* n = e.name.load();
+      if (!n || !e.calls.load()) continue;
+      char buf[256];
+      snprintf(buf, sizeof(buf), "%s\"host:%s\": {\"calls\": %llu, \"ms\": %.6f, \"work\": 0}", first ? "" : ", ", n, e.calls.load(), e.ns.load() * 1e-6);
       s += buf;
       first = false;
     }
