@@ -125,3 +125,30 @@ def test_lk_no_initial_flow_and_params(ctx):
         assert np.array_equal(st, rst)
         ok = st == 1
         assert np.abs(p1[ok] - r1[ok]).max() < 1e-4
+
+
+@pytest.mark.parametrize("win", [3, 7, 13, 15])
+def test_lk_fast_path_equals_generic_kernel(ctx, win, monkeypatch):
+    """Single-channel frames with win <= 15 take lk_kernel_fast (register template, shuffled neighbours);
+    XIVO_LK_GENERIC=1 routes the same call through lk_kernel<1>.  Both evaluate the same exact integer
+    window sums, so every output is bit-identical — including points whose windows cross the border."""
+    a, b = synth.frame_pair(240, 320, seed=11, shift=(2, -1))
+    xy, sc, _ = T.fast_detect(a, 20)
+    p0 = xy[np.lexsort((xy[:, 0], xy[:, 1], -sc))[:100]].astype(np.float32)
+    border = np.float32([[1, 1], [318, 2], [3, 237], [317, 238], [0.5, 120.25], [319, 100], [160.5, 0], [100, 239]])
+    p0 = np.concatenate([p0, border])
+    init = p0 + np.float32([1.5, -0.75])
+    max_level = 3 if win >= 7 else 4
+    monkeypatch.delenv("XIVO_LK_GENERIC", raising=False)
+    p1, st, er = ctx.lk_track(a, b, p0, init, win=win, max_level=max_level)
+    monkeypatch.setenv("XIVO_LK_GENERIC", "1")
+    g1, gst, ger = ctx.lk_track(a, b, p0, init, win=win, max_level=max_level)
+    monkeypatch.delenv("XIVO_LK_GENERIC", raising=False)
+    assert np.array_equal(st, gst)
+    assert np.array_equal(p1, g1)
+    assert np.array_equal(er, ger)
+    r1, rst, rer = T.lk_track(a, b, p0, init, win=win, max_level=max_level)
+    assert np.array_equal(st, rst)
+    ok = st == 1
+    assert np.abs(p1[ok] - r1[ok]).max() < 1e-4
+    assert np.abs(er[ok] - rer[ok]).max() < 1e-4

@@ -260,7 +260,8 @@ class Batch {
     prev_slot.assign(B, 0);
     for (auto& e : est) {
       e->rows = rows; e->cols = cols;
-      e->mask.assign((size_t)rows * cols, 0);
+      e->mask_stride = (cols + 63) / 64;
+      e->mask.assign((size_t)rows * e->mask_stride, 0);
     }
     img_ready = true;
     return 0;
@@ -274,7 +275,7 @@ class Batch {
     int cnt[257] = {0};
     for (int i = 0; i < n; ++i) {
       const unsigned k = kps[i];
-      if (e.mask[(size_t)(k >> 20) * e.cols + ((k >> 8) & 0xfff)]) cnt[(k & 0xff) + 1]++;
+      if (e.mask_bit((k >> 8) & 0xfff, k >> 20)) cnt[(k & 0xff) + 1]++;
     }
     for (int s = 0; s < 256; ++s) cnt[s + 1] += cnt[s];  // cnt[s] = start of bucket s
     sorted.resize(cnt[256]);
@@ -282,7 +283,7 @@ class Batch {
     for (int s = 0; s < 256; ++s) cursor[s] = cnt[s];
     for (int i = 0; i < n; ++i) {
       const unsigned k = kps[i];
-      if (e.mask[(size_t)(k >> 20) * e.cols + ((k >> 8) & 0xfff)]) sorted[cursor[k & 0xff]++] = k;
+      if (e.mask_bit((k >> 8) & 0xfff, k >> 20)) sorted[cursor[k & 0xff]++] = k;
     }
     for (int s = 255; s >= 0; --s) {
       if (cnt[s + 1] == cnt[s]) continue;
@@ -395,7 +396,7 @@ class Batch {
             const double dx = f->xp()[0] - (double)p1[0], dy = f->xp()[1] - (double)p1[1];
             if (e.mask_valid(p1[0], p1[1]) && std::sqrt(dx * dx + dy * dy) < e.tc.max_pixel_displacement) {
               f->tstatus = TrackStatus::TRACKED;
-              f->track.push_back({(double)p1[0], (double)p1[1]});
+              f->observe((double)p1[0], (double)p1[1]);
               e.mask_out(p1[0], p1[1]);
               ++num_valid;
             } else {

@@ -17,7 +17,9 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <algorithm>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -31,13 +33,33 @@ enum class TrackStatus : int { CREATED = 0, TRACKED = 1, DROPPED = 2 };
 enum class FeatureStatus : int { CREATED = 0, INITIALIZING = 1, READY = 2, INSTATE = 3, REJECTED_BY_FILTER = 4, REJECTED_BY_TRACKER = 5, NULLREFED = 6, GAUGE = 7 };
 enum class GroupStatus : int { CREATED = 0, INSTATE = 1, FLOATING = 2, GAUGE = 3 };
 
+// sorted-vector set of ids (the adjacency lists of the visibility graph; ascending = the iteration
+// order of the ordered containers they replace)
+inline void ids_insert(std::vector<int>& v, int id) {
+  if (v.empty() || v.back() < id) { v.push_back(id); return; }
+  auto it = std::lower_bound(v.begin(), v.end(), id);
+  if (it == v.end() || *it != id) v.insert(it, id);
+}
+inline void ids_erase(std::vector<int>& v, int id) {
+  auto it = std::lower_bound(v.begin(), v.end(), id);
+  if (it != v.end() && *it == id) v.erase(it);
+}
+
 struct Group {
   int id = -1, sind = -1, lifetime = 0, slot = -1;
   GroupStatus status = GroupStatus::CREATED;
   M3 Rsb = m3_eye();
   V3 Tsb{{0, 0, 0}};
+  std::vector<int> adj;  // ids of the features seen from this group (GroupAdj), ascending
+  std::set<int> gauge;   // ids of its gauge features (Graph::gauge_features_)
   bool instate() const { return status == GroupStatus::INSTATE || status == GroupStatus::GAUGE; }
   SE3h gsb() const { return SE3h{Rsb, Tsb}; }
+  void reset(int new_id) {  // Group::Create/Reset; keeps the slot and the containers' capacity
+    id = new_id; sind = -1; lifetime = 0;
+    status = GroupStatus::CREATED;
+    Rsb = m3_eye(); Tsb = V3{{0, 0, 0}};
+    adj.clear(); gauge.clear();
+  }
 };
 
 struct Feature {
@@ -51,10 +73,27 @@ struct Feature {
   double outlier_counter = 0;
   bool tri_ok = false;
   float response = 0.f;
-  std::vector<std::array<double, 2>> track;  // Track (vector of pixel observations)
+  // Track: only the newest pixel observation is ever read on this path (the full history feeds the
+  // OOS update / triangulation, out of scope), so the track is its back() and its length.
+  std::array<double, 2> last_xp{{0, 0}};
+  int track_len = 0;
+  std::vector<int> adj;  // ids of the groups that saw this feature (FeatureAdj keys), ascending
   V3 Xs{{0, 0, 0}};
   bool instate() const { return status == FeatureStatus::INSTATE || status == FeatureStatus::GAUGE; }
-  const std::array<double, 2>& xp() const { return track.back(); }
+  const std::array<double, 2>& xp() const { return last_xp; }
+  void observe(double u, double v) { last_xp = {u, v}; ++track_len; }
+  void reset(int new_id, double u, double v) {  // Feature::Create/Reset (feature.cpp:43-91); keeps slot + capacity
+    id = new_id; sind = -1; lifetime = 0; init_counter = 0;
+    status = FeatureStatus::CREATED; tstatus = TrackStatus::CREATED;
+    ref = nullptr;
+    x[0] = u; x[1] = v; x[2] = 2.0;
+    for (double& p : P) p = 0;
+    pred[0] = pred[1] = -1;
+    outlier_counter = 0; tri_ok = false; response = 0.f;
+    track_len = 0; adj.clear();
+    Xs = V3{{0, 0, 0}};
+    observe(u, v);
+  }
   double z() const { return std::exp(x[2]); }
   double score() const { return -P[8]; }
 };
@@ -65,11 +104,8 @@ class Pool {
  public:
   void init(int n) {
     items_.clear();
-    items_.reserve(n);
-    for (int i = 0; i < n; ++i) {
-      items_.emplace_back(new T());
-      items_.back()->slot = i;
-    }
+    items_.resize(n);  // contiguous, never resized afterwards: pointers into it stay valid
+    for (int i = 0; i < n; ++i) items_[i].slot = i;
     initialized_.assign(n, false);
     active_.assign(n, false);
     n_init_ = 0;
@@ -82,7 +118,7 @@ class Pool {
         if (!initialized_[search_]) {
           initialized_[search_] = active_[search_] = true;
           ++n_init_;
-          T* r = items_[search_].get();
+          T* r = &items_[search_];
           search_ = (search_ + 1) % n;
           return r;
         }
@@ -93,7 +129,7 @@ class Pool {
     do {
       if (!active_[search_]) {
         active_[search_] = true;
-        T* r = items_[search_].get();
+        T* r = &items_[search_];
         search_ = (search_ + 1) % n;
         return r;
       }
@@ -109,18 +145,53 @@ class Pool {
   }
 
  private:
-  std::vector<std::unique_ptr<T>> items_;
+  std::vector<T> items_;
   std::vector<char> initialized_, active_;
   int n_init_ = 0, search_ = 0;
 };
 
-// Visibility graph (src/graph.cpp, src/graphbase.cpp) with ordered containers.
+// id -> object map as a sorted vector (ids are handed out in increasing order, so insertion is a
+// push_back); iteration is ascending by id like the ordered maps of the reference's graph.
+template <typename T>
+struct FlatMap {
+  using value_type = std::pair<int, T*>;
+  std::vector<value_type> v;
+  typename std::vector<value_type>::iterator begin() { return v.begin(); }
+  typename std::vector<value_type>::iterator end() { return v.end(); }
+  typename std::vector<value_type>::const_iterator begin() const { return v.begin(); }
+  typename std::vector<value_type>::const_iterator end() const { return v.end(); }
+  size_t size() const { return v.size(); }
+  typename std::vector<value_type>::iterator find(int id) {
+    auto it = std::lower_bound(v.begin(), v.end(), id, [](const value_type& a, int k) { return a.first < k; });
+    return it != v.end() && it->first == id ? it : v.end();
+  }
+  typename std::vector<value_type>::const_iterator find(int id) const {
+    auto it = std::lower_bound(v.begin(), v.end(), id, [](const value_type& a, int k) { return a.first < k; });
+    return it != v.end() && it->first == id ? it : v.end();
+  }
+  size_t count(int id) const { return find(id) != v.end(); }
+  T* at(int id) const {
+    auto it = find(id);
+    if (it == v.end()) throw std::out_of_range("FlatMap::at");
+    return it->second;
+  }
+  void put(int id, T* p) {
+    if (v.empty() || v.back().first < id) { v.emplace_back(id, p); return; }
+    auto it = std::lower_bound(v.begin(), v.end(), id, [](const value_type& a, int k) { return a.first < k; });
+    if (it != v.end() && it->first == id) it->second = p;
+    else v.insert(it, value_type(id, p));
+  }
+  void erase(int id) {
+    auto it = find(id);
+    if (it != v.end()) v.erase(it);
+  }
+};
+
+// Visibility graph (src/graph.cpp, src/graphbase.cpp): id-ordered object maps; the adjacency lists live
+// in the objects themselves (Feature::adj, Group::adj, Group::gauge).
 struct Graph {
-  std::map<int, Feature*> features;
-  std::map<int, Group*> groups;
-  std::map<int, std::map<int, std::array<double, 2>>> feature_adj;  // fid -> gid -> pixel
-  std::map<int, std::set<int>> group_adj;                            // gid -> fids
-  std::map<int, std::set<int>> gauge_features;                       // gid -> fids
+  FlatMap<Feature> features;
+  FlatMap<Group> groups;
   void add_feature(Feature* f);
   void add_group(Group* g);
   void remove_feature(Feature* f);
@@ -238,7 +309,7 @@ class Estimator {
   Graph graph;
   Pool<Feature> fpool;
   Pool<Group> gpool;
-  std::list<Feature*> tracks;  // Tracker::features_
+  std::vector<Feature*> tracks;  // Tracker::features_ (a list in the reference; order is what matters)
   std::vector<Feature*> instate_features, new_features, inliers, in_update, subfilter_list;
   std::vector<Group*> instate_groups, needs_new_gauge;
   std::set<int> affected_groups;
@@ -249,7 +320,11 @@ class Estimator {
   int feature_counter = 10000, group_counter = 0;
   // tracker bookkeeping (src/tracker.h)
   bool tracker_initialized = false;
-  std::vector<uint8_t> mask;
+  // Tracker::mask_ as a bitmap: bit (y, x) set = free pixel; one row = mask_stride 64-bit words
+  std::vector<uint64_t> mask;
+  int mask_stride = 0;
+  bool mask_bit(int x, int y) const { return (mask[(size_t)y * mask_stride + (x >> 6)] >> (x & 63)) & 1; }
+  void mask_fill_row(int y, int x0, int x1, bool v);  // [x0, x1] inclusive
   int mask_half = -1;  // MaskOut's function-local static (tracker.cpp:763)
   int rows = 0, cols = 0;
   int num_failed_to_track = 0, num_new_detections = 0, num_mh_rejected = 0;

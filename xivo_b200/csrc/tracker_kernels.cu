@@ -5,6 +5,7 @@
 //
 // All kernels take a batch dimension (blockIdx.z or .y = independent sequence) because the
 // only way a 640x480 frame fills a B200 is by processing many sequences per launch.
+#include <cstdlib>
 #include "kernels.h"
 #include "prof.h"
 
@@ -477,6 +478,230 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(const uint8_t* __rest
   }
 }
 
+// Single-channel fast path for win <= 15.  Same arithmetic as lk_kernel<1> (every window sum is an exact
+// integer, so the lane <-> pixel assignment is free): a half-warp spans one window row (16 columns,
+// the 16th only feeds the bilinear neighbour), the two half-warps take consecutive rows, and a lane
+// keeps its <= 8 template samples (I, Ix, Iy) in registers for the whole level.  Per iteration a lane
+// loads 2 bytes per sample slot (rows y, y+1 of its column) and gets the x+1 neighbours by shuffle,
+// instead of 4 loads + 3 shared-memory reads; no integer divisions remain in the loops.
+template <int WIN>
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_fast(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
+                                                               unsigned long long pyr_stride,
+                                                               const unsigned long long* __restrict__ prev_off,
+                                                               const unsigned long long* __restrict__ next_off, PyrDesc d,
+                                                               const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+                                                               uint8_t* __restrict__ status, float* __restrict__ err,
+                                                               const int* __restrict__ npts, LKParams prm) {
+  static_assert(WIN >= 3 && WIN <= 15 && (WIN & 1), "fast LK path: odd window up to 15");
+  constexpr int RW = WIN + 3, DW = WIN + 1, NS = (WIN + 1) / 2;
+  constexpr int REG_BYTES = ((RW * RW + 15) / 16) * 16;
+  constexpr int PER_WARP = ((REG_BYTES + DW * DW * 2 * 2 + 15) / 16) * 16;
+  __shared__ __align__(16) uint8_t smem_raw[LK_WARPS * PER_WARP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seq = blockIdx.y;
+  const int p = blockIdx.x * LK_WARPS + warp;
+  if (p >= npts[seq]) return;  // whole warp exits together
+  uint8_t* region = smem_raw + warp * PER_WARP;
+  short* dtile = reinterpret_cast<short*>(region + REG_BYTES);
+  const int r = lane >> 4, c = lane & 15;
+  const int cx = c < WIN ? c : WIN;  // column offset this lane loads (clamped: lanes past the window only feed neighbours)
+
+  const uint8_t* __restrict__ ppyr = prev_pyr + (prev_off ? prev_off[seq] : (unsigned long long)seq * pyr_stride);
+  const uint8_t* __restrict__ npyr = next_pyr + (next_off ? next_off[seq] : (unsigned long long)seq * pyr_stride);
+  const size_t pi = (size_t)seq * prm.max_pts + p;
+  const float ppx = prev_pts[2 * pi], ppy = prev_pts[2 * pi + 1];
+  float outx = next_pts[2 * pi], outy = next_pts[2 * pi + 1];
+  int st = 1;
+  float errv = 0.f;
+  const float half = (WIN - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  const int max_level = d.n_levels - 1;
+
+  for (int level = max_level; level >= 0; --level) {
+    const int rows = d.rows[level], cols = d.cols[level];
+    const uint8_t* __restrict__ I = ppyr + d.off[level];
+    const uint8_t* __restrict__ J = npyr + d.off[level];
+    const float scale = (float)(1. / (1 << level));
+    float px = ppx * scale, py = ppy * scale;
+    float nx, ny;
+    if (level == max_level) {
+      if (prm.use_initial_flow) { nx = outx * scale; ny = outy * scale; }
+      else { nx = px; ny = py; }
+    } else {
+      nx = outx * 2.f;
+      ny = outy * 2.f;
+    }
+    outx = nx;
+    outy = ny;
+    px -= half;
+    py -= half;
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows) {
+      if (level == 0) { st = 0; errv = 0.f; }
+      continue;
+    }
+    float a = px - ipx, b = py - ipy;
+    int iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+    int iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+    int iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+    int iw11 = 16384 - iw00 - iw01 - iw10;
+
+    __syncwarp();
+    // stage region: origin (ipx-1, ipy-1), REFLECT_101 == reads of OpenCV's padded level
+    for (int i = lane; i < RW * RW; i += 32) {
+      const int ry = i / RW, rx = i - ry * RW;
+      const int sy = reflect101(ipy - 1 + ry, rows), sx = reflect101(ipx - 1 + rx, cols);
+      region[i] = I[(size_t)sy * cols + sx];
+    }
+    __syncwarp();
+    // Scharr derivatives on the (win+1)^2 grid; zero outside the image (BORDER_CONSTANT)
+    for (int i = lane; i < DW * DW; i += 32) {
+      const int ty = i / DW, tx = i - ty * DW;
+      const int X = ipx + tx, Y = ipy + ty;
+      const bool inside = (X >= 0 && X < cols && Y >= 0 && Y < rows);
+      const uint8_t* r0 = region + ty * RW + tx;  // row Y-1, col X-1
+      const uint8_t* r1 = r0 + RW;
+      const uint8_t* r2 = r1 + RW;
+      int dx = 0, dy = 0;
+      if (inside) {
+        const int t0l = (r0[0] + r2[0]) * 3 + r1[0] * 10;
+        const int t0r = (r0[2] + r2[2]) * 3 + r1[2] * 10;
+        const int t1l = r2[0] - r0[0], t1c = r2[1] - r0[1], t1r = r2[2] - r0[2];
+        dx = t0r - t0l;
+        dy = (t1r + t1l) * 3 + t1c * 10;
+      }
+      dtile[i * 2] = (short)dx;
+      dtile[i * 2 + 1] = (short)dy;
+    }
+    __syncwarp();
+    // template + structure tensor: slot s of this lane is window pixel (y = 2 s + r, x = c)
+    int tI[NS], tX[NS], tY[NS];
+    long long lA11 = 0, lA12 = 0, lA22 = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int y = 2 * s + r;
+      int ival = 0, ix = 0, iy = 0;
+      if (c < WIN && y < WIN) {
+        const uint8_t* q = region + (y + 1) * RW + (c + 1);
+        const short* dq = dtile + (y * DW + c) * 2;
+        ival = descale(q[0] * iw00 + q[1] * iw01 + q[RW] * iw10 + q[RW + 1] * iw11, 9);
+        ix = descale(dq[0] * iw00 + dq[2] * iw01 + dq[2 * DW] * iw10 + dq[2 * DW + 2] * iw11, 14);
+        iy = descale(dq[1] * iw00 + dq[3] * iw01 + dq[2 * DW + 1] * iw10 + dq[2 * DW + 3] * iw11, 14);
+      }
+      tI[s] = ival; tX[s] = ix; tY[s] = iy;
+      lA11 += ix * ix;
+      lA12 += ix * iy;
+      lA22 += iy * iy;
+    }
+    lA11 = warp_sum_ll(lA11);
+    lA12 = warp_sum_ll(lA12);
+    lA22 = warp_sum_ll(lA22);
+    const float A11 = __ll2float_rn(lA11) * FLT_SCALE, A12 = __ll2float_rn(lA12) * FLT_SCALE, A22 = __ll2float_rn(lA22) * FLT_SCALE;
+    float D = A11 * A22 - A12 * A12;
+    const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+    if ((double)minEig < prm.min_eig || D < 1.1920928955078125e-7f) {
+      if (level == 0) st = 0;
+      continue;
+    }
+    D = 1.f / D;
+    nx -= half;
+    ny -= half;
+    float pdx = 0.f, pdy = 0.f;
+    // bilinear samples of J on this lane's slots: v = descale(sum w * J, 9); lanes outside the window return junk
+    // that is multiplied by a zero template gradient (or masked in the error pass)
+    auto sample = [&](int inx, int iny, int s, bool interior) -> int {
+      int Y0 = iny + min(2 * s + r, WIN), Y1 = iny + min(2 * s + r + 1, WIN), X = inx + cx;
+      if (!interior) {
+        X = reflect101(X, cols);
+        Y0 = reflect101(Y0, rows);
+        Y1 = reflect101(Y1, rows);
+      }
+      const int v0 = __ldg(J + (size_t)Y0 * cols + X), v1 = __ldg(J + (size_t)Y1 * cols + X);
+      const int v0r = __shfl_down_sync(0xffffffffu, v0, 1), v1r = __shfl_down_sync(0xffffffffu, v1, 1);
+      return descale(v0 * iw00 + v0r * iw01 + v1 * iw10 + v1r * iw11, 9);
+    };
+    for (int j = 0; j < prm.max_iter; ++j) {
+      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+      if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
+        if (level == 0) st = 0;
+        break;
+      }
+      a = nx - inx;
+      b = ny - iny;
+      iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+      iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+      iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+      iw11 = 16384 - iw00 - iw01 - iw10;
+      const bool interior = (inx >= 0 && iny >= 0 && inx + WIN < cols && iny + WIN < rows);
+      long long lb1 = 0, lb2 = 0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int diff = sample(inx, iny, s, interior) - tI[s];
+        lb1 += diff * tX[s];
+        lb2 += diff * tY[s];
+      }
+      lb1 = warp_sum_ll(lb1);
+      lb2 = warp_sum_ll(lb2);
+      const float b1 = __ll2float_rn(lb1) * FLT_SCALE, b2 = __ll2float_rn(lb2) * FLT_SCALE;
+      const float dx = (A12 * b2 - A22 * b1) * D;
+      const float dy = (A12 * b1 - A11 * b2) * D;
+      nx += dx;
+      ny += dy;
+      outx = nx + half;
+      outy = ny + half;
+      if ((double)dx * dx + (double)dy * dy <= prm.eps_sq) break;
+      if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+        outx -= dx * 0.5f;
+        outy -= dy * 0.5f;
+        break;
+      }
+      pdx = dx;
+      pdy = dy;
+    }
+    if (st && level == 0) {
+      // default-flags error measure: mean |J - I| over the window / 32 (lkpyramid.cpp tail)
+      const float fx = outx - half, fy = outy - half;
+      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+      if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
+        st = 0;
+        continue;
+      }
+      const float aa = fx - inx, bb = fy - iny;
+      iw00 = __float2int_rn((1.f - aa) * (1.f - bb) * 16384.f);
+      iw01 = __float2int_rn(aa * (1.f - bb) * 16384.f);
+      iw10 = __float2int_rn((1.f - aa) * bb * 16384.f);
+      iw11 = 16384 - iw00 - iw01 - iw10;
+      long long le = 0;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int diff = sample(inx, iny, s, false) - tI[s];
+        if (c < WIN && 2 * s + r < WIN) le += abs(diff);
+      }
+      le = warp_sum_ll(le);
+      errv = __ll2float_rn(le) * 1.f / (float)(32 * WIN * WIN);
+    }
+  }
+  if (lane == 0) {
+    next_pts[2 * pi] = outx;
+    next_pts[2 * pi + 1] = outy;
+    status[pi] = (uint8_t)st;
+    if (err) err[pi] = errv;
+  }
+}
+
+template <int WIN>
+static void launch_lk_fast(dim3 grid, cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, unsigned long long pyr_stride,
+                           const unsigned long long* prev_off, const unsigned long long* next_off, const PyrDesc& d, const float* prev_pts,
+                           float* next_pts, uint8_t* status, float* err, const int* npts_dev, const LKParams& prm) {
+  lk_kernel_fast<WIN><<<grid, LK_WARPS * 32, 0, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
+}
+
+// XIVO_LK_GENERIC=1 routes single-channel frames through the generic kernel (parity tests compare the two)
+static bool prm_force_generic_lk() {
+  const char* e = getenv("XIVO_LK_GENERIC");
+  return e && e[0] == '1';
+}
+
 size_t lk_smem_bytes(int win, int cn) {
   const int RW = win + 3, DW = win + 1;
   const int reg_bytes = ((RW * RW * cn + 15) / 16) * 16;
@@ -502,7 +727,14 @@ int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* nex
   size_t smem = lk_smem_bytes(win, d.cn);
   dim3 grid((max_pts + LK_WARPS - 1) / LK_WARPS, batch);
   ProfScope ps("lk_track", st);
-  if (d.cn == 1) {
+  const bool generic = prm_force_generic_lk();
+  if (d.cn == 1 && win <= 15 && !generic) {
+    switch (win) {
+#define XB_LK_CASE(W) case W: launch_lk_fast<W>(grid, st, prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm); break;
+      XB_LK_CASE(3) XB_LK_CASE(5) XB_LK_CASE(7) XB_LK_CASE(9) XB_LK_CASE(11) XB_LK_CASE(13) XB_LK_CASE(15)
+#undef XB_LK_CASE
+    }
+  } else if (d.cn == 1) {
     XB_CUDA(cudaFuncSetAttribute(lk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lk_kernel<1><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
   } else {
