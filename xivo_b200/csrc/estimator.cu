@@ -101,6 +101,10 @@ class Batch {
   // The covariance side (IMU propagation, slot edits, Jacobians, update) runs on its own stream so that it
   // overlaps the image tracker's kernels and host phases, which use ctx->stream.
   cudaStream_t st2 = nullptr;
+  // Frames are uploaded on their own stream: the message heap releases a frame several messages after it was
+  // pushed, so its copy overlaps the tracking of the frame released now.  ring_ev[slot] orders the two.
+  cudaStream_t st_copy = nullptr;
+  std::vector<cudaEvent_t> ring_ev;
   cudaEvent_t stg_ev = nullptr;  // stage-record upload finished (the pinned staging buffer may be refilled)
   bool stg_inflight = false;
   // tracker device state (allocated at the first image)
@@ -111,6 +115,8 @@ class Batch {
   uint8_t* dPyr = nullptr;    // B x 2 x pd.total
   std::vector<int> ring_next, prev_slot;
   Mirror<unsigned long long> off_prev, off_cur;
+  Mirror<const uint8_t*> frame_ptr, ingest_ptr;  // ring slot of the frame being tracked; sources of a device-resident ingest
+  Mirror<unsigned long long> ingest_off;
   Mirror<float> pts0, pts1, lkerr;
   Mirror<uint8_t> lkst;
   Mirror<int> npts, kpcount;
@@ -120,6 +126,7 @@ class Batch {
   Batch(xivo_ctx* c, const Json& cfg, int nseq, EkfLayout l, bool tracker_only) : ctx(c), B(nseq), lay(l) {
     N = lay.N();
     cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&stg_ev, cudaEventDisableTiming);
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
     maxops = 4 * (lay.F + lay.G) + 16;
@@ -166,12 +173,14 @@ class Batch {
     cudaStreamSynchronize(ctx->stream);
     if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
     if (stg_ev) cudaEventDestroy(stg_ev);
+    if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
+    for (cudaEvent_t e : ring_ev) cudaEventDestroy(e);
     for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr})
       if (p) cudaFree(p);
     cam.release(); X.release(); groups.release(); fx.release(); fxp.release(); R.release(); Phi.release(); Pmm.release();
     mh.release(); pack.release(); fref.release(); fsind.release(); nfeat.release(); sel.release(); nsel.release();
     nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); stg.release(); stg_first.release(); stg_n.release();
-    icst.release(); off_prev.release();
+    icst.release(); off_prev.release(); frame_ptr.release(); ingest_ptr.release(); ingest_off.release();
     off_cur.release(); pts0.release(); pts1.release(); lkerr.release(); lkst.release(); npts.release(); kpcount.release();
     kp.release();
   }
@@ -236,6 +245,17 @@ class Batch {
     return 0;
   }
 
+  // mark the uploads enqueued on st_copy for ring slot `slot` (call after the last one)
+  int ring_uploaded(const std::vector<int>& slots_used) {
+    for (int k : slots_used) XB_CUDA(cudaEventRecord(ring_ev[k], st_copy));
+    return 0;
+  }
+  // the caller's frame buffers are free again once the uploads have landed
+  int ingest_done() {
+    XB_CUDA(cudaStreamSynchronize(st_copy));
+    return 0;
+  }
+
   // ---- image tracker ---------------------------------------------------------------------
   int ensure_images(int r, int c, int ch) {
     if (img_ready) {
@@ -252,11 +272,13 @@ class Batch {
     const size_t ib = (size_t)rows * cols * cn;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dRing), (size_t)B * ring_n * ib) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dPyr), (size_t)B * 2 * pd.total) == cudaSuccess;
-    ok = ok && off_prev.alloc(B) && off_cur.alloc(B) && pts0.alloc((size_t)B * max_pts * 2) && pts1.alloc((size_t)B * max_pts * 2) &&
+    ok = ok && frame_ptr.alloc(B) && ingest_ptr.alloc(B) && ingest_off.alloc(B) && off_prev.alloc(B) && off_cur.alloc(B) && pts0.alloc((size_t)B * max_pts * 2) && pts1.alloc((size_t)B * max_pts * 2) &&
          lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && npts.alloc(B) && kpcount.alloc(B) &&
          kp.alloc((size_t)B * max_kp);
     if (!ok) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
     ring_next.assign(B, 0);
+    ring_ev.resize(ring_n);
+    for (auto& e : ring_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     prev_slot.assign(B, 0);
     for (auto& e : est) {
       e->rows = rows; e->cols = cols;
@@ -316,13 +338,17 @@ class Batch {
     std::atomic<int> overflow{0};
     {
       HostScope hs("tracker_prepare");
-      HostScope hrc("ring_copy");
+      {
+        std::vector<char> seen(ring_n, 0);
+        for (int k : slots)
+          if (!seen[k]) { seen[k] = 1; XB_CUDA(cudaStreamWaitEvent(st, ring_ev[k], 0)); }
+      }
       for (size_t i = 0; i < act.size(); ++i) {
         const int b = act[i];
         const int cur = 1 - prev_slot[b];
         off_cur.h[b] = ((size_t)b * 2 + cur) * pd.total;
         off_prev.h[b] = ((size_t)b * 2 + prev_slot[b]) * pd.total;
-        XB_CUDA(cudaMemcpyAsync(dPyr + off_cur.h[b], dRing + ((size_t)b * ring_n + slots[i]) * ib, ib, cudaMemcpyDeviceToDevice, st));
+        frame_ptr.h[b] = dRing + ((size_t)b * ring_n + slots[i]) * ib;  // consumed by the first pyrDown pass
       }
       pfor(act, [&](int b, int) {
         Estimator& e = *est[b];
@@ -362,9 +388,9 @@ class Batch {
         else off_cur.h[b] = ~0ull;
       }
     }
-    XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st));
-    if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B)) return rc;
-    g_launches += pd.n_levels - 1;
+    XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st)); XB_CUDA(frame_ptr.up(st));
+    if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B, frame_ptr.d)) return rc;
+    g_launches += std::max(1, pd.n_levels - 1);
     {
       int nact = 0;
       for (int b = 0; b < B; ++b) nact += off_cur.h[b] != ~0ull;
@@ -767,18 +793,23 @@ static int visual_meas_impl(xivo_batch* b, const uint64_t* ts_ns, const uint8_t*
   if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
   const size_t ib = (size_t)rows * cols * channels;
   std::vector<Msg> in(B_.B);
+  std::vector<int> used;
   for (int s = 0; s < B_.B; ++s) {
     XB_REQUIRE(imgs[s], "visual_meas: null image");
     const int slot = B_.ring_next[s];
     B_.ring_next[s] = (slot + 1) % B_.ring_n;
     if (!on_device) Prof::get().h2d += ib;
     XB_CUDA(cudaMemcpyAsync(B_.dRing + ((size_t)s * B_.ring_n + slot) * ib, imgs[s], ib,
-                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, B_.ctx->stream));
+                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, B_.st_copy));
+    if (std::find(used.begin(), used.end(), slot) == used.end()) used.push_back(slot);
     in[s].ts = ts_ns[s];
     in[s].type = tracker_only ? 2 : 1;
     in[s].img_slot = slot;
   }
-  return B_.ingest(in);
+  if (int rc = B_.ring_uploaded(used)) return rc;
+  const int rc = B_.ingest(in);
+  const int rc2 = B_.ingest_done();
+  return rc ? rc : rc2;
 }
 
 int xivo_batch_visual_meas(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs, int rows, int cols, int channels,
@@ -797,6 +828,7 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
   const size_t ib = (size_t)rows * cols * channels;
   const int nb = B_.B;
   std::vector<std::vector<Msg>> in(nb);
+  std::vector<int> used;
   HostScope* hm = new HostScope("marshal");
   for (int s = 0; s < nb; ++s) {
     XB_REQUIRE(imgs[s], "batch_step: null image");
@@ -810,17 +842,30 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
     }
     const int slot = B_.ring_next[s];
     B_.ring_next[s] = (slot + 1) % B_.ring_n;
-    if (!on_device) Prof::get().h2d += ib;
-    XB_CUDA(cudaMemcpyAsync(B_.dRing + ((size_t)s * B_.ring_n + slot) * ib, imgs[s], ib,
-                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, B_.ctx->stream));
+    if (!on_device) {
+      Prof::get().h2d += ib;
+      XB_CUDA(cudaMemcpyAsync(B_.dRing + ((size_t)s * B_.ring_n + slot) * ib, imgs[s], ib, cudaMemcpyHostToDevice, B_.st_copy));
+    } else {
+      B_.ingest_ptr.h[s] = imgs[s];
+      B_.ingest_off.h[s] = ((size_t)s * B_.ring_n + slot) * ib;
+    }
+    if (std::find(used.begin(), used.end(), slot) == used.end()) used.push_back(slot);
     Msg& v = in[s][n_imu];
     v.ts = frame_ts[s];
     v.type = 1;
     v.img_slot = slot;
   }
+  if (on_device) {  // one gather launch instead of n_seq device-to-device copies
+    XB_CUDA(B_.ingest_ptr.up(B_.st_copy)); XB_CUDA(B_.ingest_off.up(B_.st_copy));
+    if (int rc = launch_gather_frames(B_.st_copy, B_.ingest_ptr.d, B_.dRing, 0, B_.ingest_off.d, ib, nb)) return rc;
+    g_launches += 1;
+  }
+  if (int rc = B_.ring_uploaded(used)) return rc;
   delete hm;
   HostScope hst("ingest_many_total");
-  return B_.ingest_many(in);
+  const int rc = B_.ingest_many(in);
+  const int rc2 = B_.ingest_done();
+  return rc ? rc : rc2;
 }
 
 void xivo_profile_enable(int on) {

@@ -5,6 +5,7 @@
 //
 // All kernels take a batch dimension (blockIdx.z or .y = independent sequence) because the
 // only way a 640x480 frame fills a B200 is by processing many sequences per launch.
+#include <algorithm>
 #include <cstdlib>
 #include "kernels.h"
 #include "prof.h"
@@ -17,17 +18,49 @@ namespace xb {
 // derivatives are NOT materialised: the LK kernel recomputes them from the staged patch.
 // Tile: 32x8 output pixels; input region (2*32+3)x(2*8+3) staged in shared memory.
 // ------------------------------------------------------------------------------------------
+// One launch copies one frame per sequence: src[z] -> dst + (off ? off[z] : z * stride).  Replaces B
+// cudaMemcpyAsync calls (the API cost, not the bytes, is what matters at 0.3 MB per frame).
+__global__ void __launch_bounds__(256) gather_frames_kernel(const uint8_t* const* __restrict__ src, uint8_t* __restrict__ dst,
+                                                           unsigned long long stride, const unsigned long long* __restrict__ off,
+                                                           size_t bytes) {
+  const unsigned long long o = off ? off[blockIdx.y] : (unsigned long long)blockIdx.y * stride;
+  if (o == ~0ull) return;
+  const uint8_t* __restrict__ s = src[blockIdx.y];
+  uint8_t* __restrict__ t = dst + o;
+  const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const size_t step = (size_t)gridDim.x * blockDim.x * 16;
+  if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(t)) & 15) == 0) {
+    for (size_t i = i0; i + 16 <= bytes; i += step) *reinterpret_cast<uint4*>(t + i) = *reinterpret_cast<const uint4*>(s + i);
+    if (blockIdx.x == 0 && threadIdx.x < (bytes & 15)) t[(bytes & ~(size_t)15) + threadIdx.x] = s[(bytes & ~(size_t)15) + threadIdx.x];
+  } else {
+    for (size_t i = i0; i < bytes; i += step)
+      for (int k = 0; k < 16 && i + k < bytes; ++k) t[i + k] = s[i + k];
+  }
+}
+int launch_gather_frames(cudaStream_t st, const uint8_t* const* src, uint8_t* dst, unsigned long long stride, const unsigned long long* off,
+                         size_t bytes, int batch) {
+  ProfScope ps("gather_frames", st);
+  const int chunks = (int)std::min<size_t>(64, (bytes + 256 * 16 - 1) / (256 * 16));
+  gather_frames_kernel<<<dim3(chunks, batch), 256, 0, st>>>(src, dst, stride, off, bytes);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 constexpr int PD_TX = 32, PD_TY = 8;
 
 template <int CN>
 __global__ void __launch_bounds__(PD_TX* PD_TY) pyrdown_kernel(uint8_t* __restrict__ pyr, unsigned long long pyr_stride,
                                                                 const unsigned long long* __restrict__ seq_off, PyrDesc d,
-                                                                int lvl_src) {
+                                                                int lvl_src, const uint8_t* const* __restrict__ frame0) {
   const int srows = d.rows[lvl_src], scols = d.cols[lvl_src];
   const int drows = d.rows[lvl_src + 1], dcols = d.cols[lvl_src + 1];
   const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * pyr_stride;
   if (soff == ~0ull) return;  // inactive sequence
-  const uint8_t* __restrict__ src = pyr + soff + d.off[lvl_src];
+  // frame0 (level 0 only): the new frame still lives outside the pyramid (the estimator's frame ring); this
+  // pass then also writes the level-0 copy from its staged tile, so the frame is read once instead of being
+  // copied into place first
+  const bool ingest = frame0 != nullptr && lvl_src == 0;
+  const uint8_t* __restrict__ src = ingest ? frame0[blockIdx.z] : pyr + soff + d.off[lvl_src];
   uint8_t* __restrict__ dst = pyr + soff + d.off[lvl_src + 1];
   constexpr int RW = 2 * PD_TX + 3, RH = 2 * PD_TY + 3;
   __shared__ uint8_t tile[RH][RW * CN + 1];
@@ -43,6 +76,14 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) pyrdown_kernel(uint8_t* __restri
     for (int c = 0; c < CN; ++c) tile[ry][rx * CN + c] = p[c];
   }
   __syncthreads();
+  if (ingest) {  // interior of the staged region = this CTA's 2 PD_TX x 2 PD_TY block of level 0
+    uint8_t* __restrict__ l0 = pyr + soff + d.off[0];
+    for (int i = tid; i < 2 * PD_TY * 2 * PD_TX * CN; i += PD_TX * PD_TY) {
+      const int ry = i / (2 * PD_TX * CN), r = i - ry * (2 * PD_TX * CN);
+      const int gy = 2 * oy + ry, gx = 2 * ox + r / CN;
+      if (gy < srows && gx < scols) l0[((size_t)gy * scols + 2 * ox) * CN + r] = tile[ry + 2][2 * CN + r];
+    }
+  }
   // horizontal pass for all RH rows
   for (int i = tid; i < RH * PD_TX * CN; i += PD_TX * PD_TY) {
     int ry = i / (PD_TX * CN), r = i - ry * (PD_TX * CN);
@@ -64,13 +105,16 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) pyrdown_kernel(uint8_t* __restri
 }
 
 int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off,
-                         const PyrDesc& d, int batch) {
+                         const PyrDesc& d, int batch, const uint8_t* const* frame0) {
   ProfScope ps("pyrdown", st);
+  if (d.n_levels == 1 && frame0) {  // no pyrDown pass to ride on: plain gather copy into level 0
+    if (int rc = launch_gather_frames(st, frame0, pyr, pyr_stride, seq_off, (size_t)d.rows[0] * d.cols[0] * d.cn, batch)) return rc;
+  }
   for (int l = 0; l + 1 < d.n_levels; ++l) {
     dim3 grid((d.cols[l + 1] + PD_TX - 1) / PD_TX, (d.rows[l + 1] + PD_TY - 1) / PD_TY, batch);
     dim3 block(PD_TX, PD_TY);
-    if (d.cn == 1) pyrdown_kernel<1><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l);
-    else pyrdown_kernel<3><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l);
+    if (d.cn == 1) pyrdown_kernel<1><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
+    else pyrdown_kernel<3><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
   }
   XB_CUDA(cudaGetLastError());
   return 0;
