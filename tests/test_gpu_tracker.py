@@ -152,3 +152,42 @@ def test_lk_fast_path_equals_generic_kernel(ctx, win, monkeypatch):
     ok = st == 1
     assert np.abs(p1[ok] - r1[ok]).max() < 1e-4
     assert np.abs(er[ok] - rer[ok]).max() < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (240, 320), (96, 132), (67, 44), (1024, 1280)])
+def test_pyramid_vector_path_equals_bytewise_kernel(ctx, shape, monkeypatch):
+    """Single-channel levels whose width is a multiple of 4 take pyrdown_vec_kernel (word staging, dp4a);
+    XIVO_PYRDOWN_GENERIC=1 forces the byte-wise kernel.  Same integers, so every level is identical —
+    and equal to the C oracle (cv2.pyrDown restated)."""
+    a, _ = synth.frame_pair(shape[0], shape[1], seed=21)
+    monkeypatch.delenv("XIVO_PYRDOWN_GENERIC", raising=False)
+    fast = ctx.build_pyramid(a, 15, 4)
+    monkeypatch.setenv("XIVO_PYRDOWN_GENERIC", "1")
+    slow = ctx.build_pyramid(a, 15, 4)
+    monkeypatch.delenv("XIVO_PYRDOWN_GENERIC", raising=False)
+    ref = T.pyramid(a, 15, 4)
+    assert len(fast) == len(slow) == len(ref)
+    for f, s_, r in zip(fast, slow, ref):
+        assert np.array_equal(f, s_)
+        assert np.array_equal(f, r)
+
+
+@pytest.mark.parametrize("shape,thr,cn", [((480, 640), 5, 1), ((480, 640), 20, 1), ((241, 323), 10, 1), ((96, 70), 5, 3), ((480, 640), 40, 3)])
+def test_fast_pair_kernel_equals_scalar_kernel(ctx, shape, thr, cn, monkeypatch):
+    """fast_pair_kernel (two pixels per thread, s16x2 min/max, decision 'cornerScore > thr') against the scalar
+    kernel (compass pre-test + arc bit-mask) and the C oracle: identical keypoint sets and scores."""
+    a, _ = synth.frame_pair(shape[0], shape[1], seed=31)
+    img = a if cn == 1 else synth.to_bgr(a, True)
+    monkeypatch.delenv("XIVO_FAST_SCALAR", raising=False)
+    xy, sc, n = ctx.fast_detect(img, thr, max_kp=1 << 17)
+    monkeypatch.setenv("XIVO_FAST_SCALAR", "1")
+    xy2, sc2, n2 = ctx.fast_detect(img, thr, max_kp=1 << 17)
+    monkeypatch.delenv("XIVO_FAST_SCALAR", raising=False)
+    rxy, rsc, rn = T.fast_detect(img, thr)
+    key = lambda xy_, sc_: sorted(zip(xy_[:, 1].tolist(), xy_[:, 0].tolist(), sc_.tolist()))
+    assert n == n2 == rn and n > 0
+    assert key(xy, sc) == key(xy2, sc2) == key(rxy, rsc)
+    # without non-max suppression every corner is reported: checks the decision itself
+    xy, sc, n = ctx.fast_detect(img, thr, nonmax=False, max_kp=1 << 18)
+    rxy, rsc, rn = T.fast_detect(img, thr, nonmax=False, max_kp=1 << 18)
+    assert n == rn and key(xy, sc) == key(rxy, rsc)

@@ -105,6 +105,7 @@ class Batch {
   // pushed, so its copy overlaps the tracking of the frame released now.  ring_ev[slot] orders the two.
   cudaStream_t st_copy = nullptr;
   std::vector<cudaEvent_t> ring_ev;
+  cudaEvent_t wait_ev = nullptr;
   cudaEvent_t stg_ev = nullptr;  // stage-record upload finished (the pinned staging buffer may be refilled)
   bool stg_inflight = false;
   // tracker device state (allocated at the first image)
@@ -128,6 +129,7 @@ class Batch {
     cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&stg_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&wait_ev, cudaEventDisableTiming);
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
     maxops = 4 * (lay.F + lay.G) + 16;
     max_sub = est[0]->tc.num_features_max + 8;
@@ -173,6 +175,7 @@ class Batch {
     cudaStreamSynchronize(ctx->stream);
     if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
     if (stg_ev) cudaEventDestroy(stg_ev);
+    if (wait_ev) cudaEventDestroy(wait_ev);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
     for (cudaEvent_t e : ring_ev) cudaEventDestroy(e);
     for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr})
@@ -241,10 +244,23 @@ class Batch {
     XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
     g_launches += 1;
-    { HostScope hw("wait_flush"); XB_CUDA(cudaStreamSynchronize(st)); }
+    { HostScope hw("wait_flush"); if (int rc = wait(st)) return rc; }
     return 0;
   }
 
+  // Wait for a stream without idling the CPU: while the event is pending the driver executes items of
+  // whatever host jobs the other batches of this process have published.
+  int wait(cudaStream_t st) {
+    static const bool help = !(getenv("XIVO_HELP") && getenv("XIVO_HELP")[0] == '0');
+    if (!help) { XB_CUDA(cudaStreamSynchronize(st)); return 0; }
+    XB_CUDA(cudaEventRecord(wait_ev, st));
+    for (;;) {
+      const cudaError_t e = cudaEventQuery(wait_ev);
+      if (e == cudaSuccess) return 0;
+      if (e != cudaErrorNotReady) { set_error("CUDA error while waiting: %s", cudaGetErrorString(e)); return XIVO_ERR_CUDA; }
+      if (!WorkPool::get().help_one()) cpu_relax();
+    }
+  }
   // mark the uploads enqueued on st_copy for ring slot `slot` (call after the last one)
   int ring_uploaded(const std::vector<int>& slots_used) {
     for (int k : slots_used) XB_CUDA(cudaEventRecord(ring_ev[k], st_copy));
@@ -409,7 +425,7 @@ class Batch {
         Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
       }
       XB_CUDA(pts1.down(st)); XB_CUDA(lkst.down(st));
-      { HostScope hw("wait_lk"); XB_CUDA(cudaStreamSynchronize(st)); }
+      { HostScope hw("wait_lk"); if (int rc = wait(st)) return rc; }
       HostScope hs("tracker_accept");
       std::vector<int> need(B, 0);
       pfor(lk_list, [&](int b, int) {
@@ -450,12 +466,12 @@ class Batch {
       g_launches += 1;
       Prof::get().add_work("fast_detect", det_list.size() * 2.0 * rows * cols);  // §8d: 2 W H bytes
       XB_CUDA(kpcount.down(st));
-      { HostScope hw("wait_fastcount"); XB_CUDA(cudaStreamSynchronize(st)); }
+      { HostScope hw("wait_fastcount"); if (int rc = wait(st)) return rc; }
       for (int b : det_list) {
         const int n = std::min(kpcount.h[b], max_kp);
         if (n) { Prof::get().d2h += sizeof(unsigned) * n; XB_CUDA(cudaMemcpyAsync(kp.h + (size_t)b * max_kp, kp.d + (size_t)b * max_kp, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st)); }
       }
-      { HostScope hw("wait_fastkp"); XB_CUDA(cudaStreamSynchronize(st)); }
+      { HostScope hw("wait_fastkp"); if (int rc = wait(st)) return rc; }
       HostScope hs("tracker_select");
       pfor(det_list, [&](int b, int) {
         Estimator& e = *est[b];
@@ -558,7 +574,7 @@ class Batch {
       if (int rc = launch_subfilter(st, cam.d, X.d, sub_in.d, sub_out.d, nsub, est[0]->c.sub_Rtri, est[0]->c.sub_mh)) return rc;
       g_launches += 1;
       XB_CUDA(sub_out.down(st, nsub));
-      { HostScope hw("wait_subfilter"); XB_CUDA(cudaStreamSynchronize(st)); }
+      { HostScope hw("wait_subfilter"); if (int rc = wait(st)) return rc; }
     }
     // ---- select/add features, fill the device tables ----
     std::atomic<int> bad_slot{0};
@@ -604,7 +620,7 @@ class Batch {
       Prof::get().add_work("jacobian_gate", nf * 2.0 * N * 8.0);  // §8d: M N 8 bytes of H written
     }
     XB_CUDA(mh.down(st));
-    { HostScope hw("wait_jacobian"); XB_CUDA(cudaStreamSynchronize(st)); }
+    { HostScope hw("wait_jacobian"); if (int rc = wait(st)) return rc; }
     // ---- gating decisions (host), post-gate edits, update (device) ----
     {
       HostScope hs("gating");
@@ -634,7 +650,7 @@ class Batch {
       if (M > 0) Prof::get().add_work("ekf_update", 4 * Nn * Nn * Nn + 6 * M * Nn * Nn + 4 * M * M * Nn + M * M * M / 3.0);  // §8d Joseph flop count
     }
     XB_CUDA(pack.down(st));
-    { HostScope hw("wait_update"); XB_CUDA(cudaStreamSynchronize(st)); }
+    { HostScope hw("wait_update"); if (int rc = wait(st)) return rc; }
     Prof::get().collect();
     std::atomic<int> notpd{0};
     {

@@ -256,6 +256,21 @@ class WorkPool {
   std::atomic<int> next_driver_{0};
 
  public:
+  // Run at most one item of any published job on the calling thread (a driver that is waiting for the GPU
+  // lends its CPU to the other batches).  Returns false when there was nothing to do.
+  bool help_one() {
+    if (threads_.empty()) return false;
+    Job* j = grab();
+    if (!j) return false;
+    const int i = j->next.fetch_add(1, std::memory_order_relaxed);
+    if (i < j->n) {
+      j->call(j->ctx, i);
+      j->done.fetch_add(1, std::memory_order_release);
+    }
+    j->refs.fetch_sub(1, std::memory_order_release);
+    return true;
+  }
+
   // Pin the calling (driver) thread to one of the cores reserved for drivers; once per thread.
   void pin_driver() {
     static thread_local bool done = false;
