@@ -270,7 +270,7 @@ def run_ours(args):
     log("device-resident pass", r_dev["ms"], "ms")
     r_e2e = timed(False, 0)
     log("e2e pass", r_e2e["ms"], "ms")
-    r_prof = timed(True, args.profile_level)
+    r_prof = timed(not args.profile_e2e, args.profile_level)
     log("profiled pass", r_prof["ms"], "ms")
     frames_total = world * B * K
     value = frames_total / (r_dev["ms"] * 1e-3)
@@ -294,7 +294,15 @@ def run_ours(args):
         achieved, peak, unit = work_per_launch / per_launch_s / 1e9, peaks["hbm"], "GB/s"
     else:
         achieved, peak, unit = work_per_launch / per_launch_s / 1e12, peaks["tf"], "TFLOP/s"
-    roofline = dict(kernel=dom, bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=None, peak_source=peaks["src"],
+    traffic, traffic_src = None, None
+    try:  # ncu-measured DRAM bytes per launch of that kernel (profiles/), scaled to this run's sequences per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if dom in tj:
+            traffic = tj[dom] * (sizes[0] / tj["sequences_per_launch"])
+            traffic_src = "ncu dram__bytes_{read,write}.sum at %d sequences/launch (profiles/r01_traffic.json), scaled to %d" % (tj["sequences_per_launch"], sizes[0])
+    except Exception:
+        pass
+    roofline = dict(kernel=dom, bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peaks["src"],
                     share_of_device_time=d["ms"] / tot_ms, launches=d["calls"], avg_launch_us=per_launch_s * 1e6,
                     kernels={k: dict(ms=round(v["ms"], 4), calls=v["calls"], share=round(v["ms"] / tot_ms, 4)) for k, v in merged.items()},
                     device_busy_frac=tot_ms / r_prof["ms"], profiled_pass_ms_per_step=r_prof["ms"] / K)
@@ -359,6 +367,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-headroom", type=int, default=1, help="CPUs of the quota left to Python / CUDA helper threads")
+    ap.add_argument("--profile-e2e", action="store_true", help="attribute kernel / host-phase time on the host-frame (e2e) path instead of the device-resident one")
     ap.add_argument("--profile-level", type=int, default=1, help="1: kernels + batch-level host phases, 2: + per-sequence host scopes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=192, help="independent sequences per GPU, split over --batches lock-step batches")

@@ -1,7 +1,7 @@
 # usage: [NB=n] bash scripts/prof_run.sh B [level]  -- one profiled bench run with host-phase breakdown (diagnostic)
 B=${1:-128}; LV=${2:-1}
 mkdir -p gpurun_out
-timeout 300 python bench.py --steps 20 --warmup 3 --seqs $B --batches ${NB:-1} --no-cpu-baseline --profile-level $LV > gpurun_out/s.json 2> gpurun_out/s.err
+timeout 300 python bench.py --steps 20 --warmup 3 --seqs $B --batches ${NB:-1} --no-cpu-baseline --profile-level $LV $EXTRA > gpurun_out/s.json 2> gpurun_out/s.err
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/s.json").read().strip().splitlines()[-1])

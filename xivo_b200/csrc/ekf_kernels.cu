@@ -512,6 +512,7 @@ __constant__ double kArk[3][6] = {{0.5, 0, 0, 0, 0, 0}, {0, 0.5, 0, 0, 0, 0}, {0
 __constant__ double kBrk[4] = {1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6};
 
 constexpr int IMU_THREADS = 128;
+constexpr int IMU_CHUNK = 56;
 __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, double* __restrict__ P, const ImuStage* __restrict__ stages,
                                                                         const int* __restrict__ first, const int* __restrict__ nstages,
                                                                         const ImuConst* __restrict__ cst) {
@@ -519,8 +520,6 @@ __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, d
   const int nall = nstages[b];
   if (nall == 0) return;
   __shared__ double sP[529], sP0[529], sA[7][207], sFK[7][207], sSA[207], sAcc[207], sT9[207], sPhi[207], sV[7][9], sCV[9], sGc[23];
-  __shared__ F9s sF;
-  __shared__ ImuStage sStage;
   __shared__ ImuConst c;
   __shared__ unsigned char sI[529], sJ[529];  // row / column of a flat 23x23 index (no div/mod in the loops)
   if (tid < (int)(sizeof(ImuConst) / 8)) reinterpret_cast<double*>(&c)[tid] = reinterpret_cast<const double*>(cst + b)[tid];
@@ -540,37 +539,49 @@ __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, d
     sGc[tid] = v;
   }
   __syncthreads();
-  // build the non-zero blocks of F from a stage record: dW = -hat(gc), dVW = -R hat(ac), dVba = -R, dVg = (-R hat(g))[:, :2]
-  auto load_stage = [&](int idx) {
-    const double* src = reinterpret_cast<const double*>(stg + idx);
-    if (tid < 16) reinterpret_cast<double*>(&sStage)[tid] = src[tid];
-    __syncthreads();
-    if (tid < 9) {
-      const int i = tid / 3, j = tid - 3 * i;
-      sF.R[tid] = sStage.R[tid];
-      sF.dVba[tid] = -sStage.R[tid];
-      sF.dW[tid] = -hat_elem(sStage.gc, i, j);
+  // Stage records are consumed in chunks of IMU_CHUNK (a multiple of both 7 and 4 stages per substep): the non-zero
+  // blocks of F of every stage of the chunk are built in parallel up front, so the serial stage chain below never
+  // waits on global memory.  dW = -hat(gc), dVW = -R hat(ac), dVba = -R, dVg = (-R hat(g))[:, :2]
+  extern __shared__ __align__(16) unsigned char imu_dyn[];
+  F9s* sFc = reinterpret_cast<F9s*>(imu_dyn);
+  double* sH = reinterpret_cast<double*>(sFc + IMU_CHUNK);
+  auto load_chunk = [&](int c0) {
+    __syncthreads();  // the previous chunk is no longer read
+    const int n = min(IMU_CHUNK, nall - c0);
+    for (int u = tid; u < n * 9; u += IMU_THREADS) {
+      const int q = u / 9, e = u - 9 * q;
+      const int i = e / 3, j = e - 3 * i;
+      const double* src = reinterpret_cast<const double*>(stg + c0 + q);
+      const double* Rm = src;
+      const double* gc = src + 9;
+      const double* ac = src + 12;
+      F9s& f = sFc[q];
+      f.R[e] = Rm[e];
+      f.dVba[e] = -Rm[e];
+      f.dW[e] = -hat_elem(gc, i, j);
       double v = 0, vg = 0;
       for (int k = 0; k < 3; ++k) {
-        v += sStage.R[3 * i + k] * hat_elem(sStage.ac, k, j);
-        vg += sStage.R[3 * i + k] * hat_elem(c.g, k, j);
+        v += Rm[3 * i + k] * hat_elem(ac, k, j);
+        vg += Rm[3 * i + k] * hat_elem(c.g, k, j);
       }
-      sF.dVW[tid] = -v;
-      if (j < 2) sF.dVg[2 * i + j] = -vg;
+      f.dVW[e] = -v;
+      if (j < 2) f.dVg[2 * i + j] = -vg;
     }
+    for (int u = tid; u < n; u += IMU_THREADS) sH[u] = reinterpret_cast<const double*>(stg + c0 + u)[15];
     __syncthreads();
   };
+  const F9s* pf = sFc;
   auto stage_products = [&](int s, const double* Pin, double h) {
     // FK[s] = F + (F acc) h  (acc holds sum a FK; unused for s == 0), A[s] = F[0:9,:] Pin, V[s] = R qa R^T
     for (int t = tid; t < 207; t += IMU_THREADS) {
       const int i = sI[t], j = sJ[t];
-      const double fd = f9_dense(sF, i, j);
-      sFK[s][t] = s == 0 ? fd : fd + f9_elem(sF, sAcc, i, j, true) * h;
-      sA[s][t] = f9_elem(sF, Pin, i, j, false);
+      const double fd = f9_dense(*pf, i, j);
+      sFK[s][t] = s == 0 ? fd : fd + f9_elem(*pf, sAcc, i, j, true) * h;
+      sA[s][t] = f9_elem(*pf, Pin, i, j, false);
     }
     if (tid < 9) {
       const int i = tid / 3, j = tid - 3 * i;
-      sV[s][tid] = sF.R[3 * i] * c.qimu[3] * sF.R[3 * j] + sF.R[3 * i + 1] * c.qimu[4] * sF.R[3 * j + 1] + sF.R[3 * i + 2] * c.qimu[5] * sF.R[3 * j + 2];
+      sV[s][tid] = pf->R[3 * i] * c.qimu[3] * pf->R[3 * j] + pf->R[3 * i + 1] * c.qimu[4] * pf->R[3 * j + 1] + pf->R[3 * i + 2] * c.qimu[5] * pf->R[3 * j + 2];
     }
     __syncthreads();
   };
@@ -585,8 +596,9 @@ __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, d
     }
   };
   for (int base = 0; base + nst <= nall; base += nst) {
-    load_stage(base);
-    const double henc = sStage.h;
+    if (base % IMU_CHUNK == 0) load_chunk(base);
+    pf = sFc + base % IMU_CHUNK;
+    const double henc = sH[base % IMU_CHUNK];
     const double h = fabs(henc);
     stage_products(0, sP, h);
     for (int s = 1; s < nst; ++s) {
@@ -606,7 +618,8 @@ __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, d
       }
       __syncthreads();
       add_sym(sP0, sP, sa, h);
-      load_stage(base + s);  // (block-wide syncs inside)
+      __syncthreads();  // sP0 complete
+      pf = sFc + (base + s) % IMU_CHUNK;
       stage_products(s, sP0, h);
     }
     const double* bw = pd ? kBpd : kBrk;
@@ -658,7 +671,13 @@ __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, d
 int launch_imu_cov_propagate(cudaStream_t st, int N, double* P, const ImuStage* stages, const int* first, const int* nstages,
                              const ImuConst* cst, int batch) {
   ProfScope ps("imu_cov_propagate", st);
-  imu_cov_propagate_kernel<<<batch, IMU_THREADS, 0, st>>>(N, P, stages, first, nstages, cst);
+  const size_t dyn = IMU_CHUNK * (sizeof(F9s) + sizeof(double));
+  static bool attr_set = false;
+  if (!attr_set) {
+    XB_CUDA(cudaFuncSetAttribute(imu_cov_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  imu_cov_propagate_kernel<<<batch, IMU_THREADS, dyn, st>>>(N, P, stages, first, nstages, cst);
   XB_CUDA(cudaGetLastError());
   return 0;
 }

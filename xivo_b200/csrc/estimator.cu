@@ -234,6 +234,12 @@ class Batch {
     stg_inflight = true;
     if (int rc = launch_imu_cov_propagate(st, N, dP, stg.d, stg_first.d, stg_n.d, icst.d, B)) return rc;
     g_launches += 1;
+    {
+      int nact = 0;
+      for (int b = 0; b < B; ++b) nact += stg_n.h[b] > 0;
+      // algorithmic bytes: the stage records + the motion block read and written + the 23 x (N-23) strip read, 9 rows of it written (twice: mirrored)
+      Prof::get().add_work("imu_cov_propagate", total * (double)sizeof(ImuStage) + nact * 8.0 * (2 * 529 + (23 + 18) * (double)(N - 23)));
+    }
     return 0;
   }
   // apply pending propagation + edits of the given sequences (used before state / P read-back)
@@ -260,6 +266,39 @@ class Batch {
       if (e != cudaErrorNotReady) { set_error("CUDA error while waiting: %s", cudaGetErrorString(e)); return XIVO_ERR_CUDA; }
       if (!WorkPool::get().help_one()) cpu_relax();
     }
+  }
+  // Bring one frame per sequence into its ring slot (slot_of[s]) on the copy stream.  Device frames and
+  // device-accessible host frames (pinned / registered: the SMs read them over PCIe) take one gather launch,
+  // which keeps the H2D copy engine's FIFO free for the small latency-critical table uploads of the other
+  // phases; pageable host frames fall back to one cudaMemcpyAsync each.
+  int upload_frames(const uint8_t* const* imgs, const std::vector<int>& slot_of, bool on_device, size_t ib) {
+    static const bool zero_copy = !(getenv("XIVO_ZEROCOPY") && getenv("XIVO_ZEROCOPY")[0] == '0');
+    bool gather = on_device || zero_copy;
+    for (int s = 0; s < B; ++s) {
+      ingest_off.h[s] = ((size_t)s * ring_n + slot_of[s]) * ib;
+      ingest_ptr.h[s] = imgs[s];
+      if (!on_device && gather) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, imgs[s]) != cudaSuccess || at.type == cudaMemoryTypeUnregistered || !at.devicePointer) {
+          cudaGetLastError();  // clear the sticky "invalid value" of an unregistered pointer
+          gather = false;
+        } else {
+          ingest_ptr.h[s] = static_cast<const uint8_t*>(at.devicePointer);
+        }
+      }
+    }
+    if (!on_device) Prof::get().h2d += (unsigned long long)ib * B;
+    if (gather) {
+      XB_CUDA(ingest_ptr.up(st_copy)); XB_CUDA(ingest_off.up(st_copy));
+      if (int rc = launch_gather_frames(st_copy, ingest_ptr.d, dRing, 0, ingest_off.d, ib, B, on_device ? 64 : 8)) return rc;
+      g_launches += 1;
+    } else {
+      for (int s = 0; s < B; ++s) XB_CUDA(cudaMemcpyAsync(dRing + ingest_off.h[s], imgs[s], ib, cudaMemcpyHostToDevice, st_copy));
+    }
+    std::vector<int> used;
+    for (int k : slot_of)
+      if (std::find(used.begin(), used.end(), k) == used.end()) used.push_back(k);
+    return ring_uploaded(used);
   }
   // mark the uploads enqueued on st_copy for ring slot `slot` (call after the last one)
   int ring_uploaded(const std::vector<int>& slots_used) {
@@ -809,20 +848,17 @@ static int visual_meas_impl(xivo_batch* b, const uint64_t* ts_ns, const uint8_t*
   if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
   const size_t ib = (size_t)rows * cols * channels;
   std::vector<Msg> in(B_.B);
-  std::vector<int> used;
+  std::vector<int> slot_of(B_.B);
   for (int s = 0; s < B_.B; ++s) {
     XB_REQUIRE(imgs[s], "visual_meas: null image");
     const int slot = B_.ring_next[s];
     B_.ring_next[s] = (slot + 1) % B_.ring_n;
-    if (!on_device) Prof::get().h2d += ib;
-    XB_CUDA(cudaMemcpyAsync(B_.dRing + ((size_t)s * B_.ring_n + slot) * ib, imgs[s], ib,
-                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, B_.st_copy));
-    if (std::find(used.begin(), used.end(), slot) == used.end()) used.push_back(slot);
+    slot_of[s] = slot;
     in[s].ts = ts_ns[s];
     in[s].type = tracker_only ? 2 : 1;
     in[s].img_slot = slot;
   }
-  if (int rc = B_.ring_uploaded(used)) return rc;
+  if (int rc = B_.upload_frames(imgs, slot_of, on_device, ib)) return rc;
   const int rc = B_.ingest(in);
   const int rc2 = B_.ingest_done();
   return rc ? rc : rc2;
@@ -844,7 +880,7 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
   const size_t ib = (size_t)rows * cols * channels;
   const int nb = B_.B;
   std::vector<std::vector<Msg>> in(nb);
-  std::vector<int> used;
+  std::vector<int> slot_of(nb);
   HostScope* hm = new HostScope("marshal");
   for (int s = 0; s < nb; ++s) {
     XB_REQUIRE(imgs[s], "batch_step: null image");
@@ -858,25 +894,13 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
     }
     const int slot = B_.ring_next[s];
     B_.ring_next[s] = (slot + 1) % B_.ring_n;
-    if (!on_device) {
-      Prof::get().h2d += ib;
-      XB_CUDA(cudaMemcpyAsync(B_.dRing + ((size_t)s * B_.ring_n + slot) * ib, imgs[s], ib, cudaMemcpyHostToDevice, B_.st_copy));
-    } else {
-      B_.ingest_ptr.h[s] = imgs[s];
-      B_.ingest_off.h[s] = ((size_t)s * B_.ring_n + slot) * ib;
-    }
-    if (std::find(used.begin(), used.end(), slot) == used.end()) used.push_back(slot);
+    slot_of[s] = slot;
     Msg& v = in[s][n_imu];
     v.ts = frame_ts[s];
     v.type = 1;
     v.img_slot = slot;
   }
-  if (on_device) {  // one gather launch instead of n_seq device-to-device copies
-    XB_CUDA(B_.ingest_ptr.up(B_.st_copy)); XB_CUDA(B_.ingest_off.up(B_.st_copy));
-    if (int rc = launch_gather_frames(B_.st_copy, B_.ingest_ptr.d, B_.dRing, 0, B_.ingest_off.d, ib, nb)) return rc;
-    g_launches += 1;
-  }
-  if (int rc = B_.ring_uploaded(used)) return rc;
+  if (int rc = B_.upload_frames(imgs, slot_of, on_device != 0, ib)) return rc;
   delete hm;
   HostScope hst("ingest_many_total");
   const int rc = B_.ingest_many(in);

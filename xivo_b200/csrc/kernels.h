@@ -11,7 +11,7 @@ namespace xb {
 int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off,
                          const PyrDesc& d, int batch, const uint8_t* const* frame0 = nullptr);
 int launch_gather_frames(cudaStream_t st, const uint8_t* const* src, uint8_t* dst, unsigned long long stride, const unsigned long long* off,
-                         size_t bytes, int batch);
+                         size_t bytes, int batch, int max_chunks = 64);
 int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off,
                        int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch);
 size_t lk_smem_bytes(int win, int cn);

@@ -38,9 +38,10 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(const uint8_t* const
   }
 }
 int launch_gather_frames(cudaStream_t st, const uint8_t* const* src, uint8_t* dst, unsigned long long stride, const unsigned long long* off,
-                         size_t bytes, int batch) {
+                         size_t bytes, int batch, int max_chunks) {
   ProfScope ps("gather_frames", st);
-  const int chunks = (int)std::min<size_t>(64, (bytes + 256 * 16 - 1) / (256 * 16));
+  // max_chunks: CTAs per frame (few when the sources are host memory: the loads wait on PCIe, not on SMs)
+  const int chunks = (int)std::min<size_t>(max_chunks < 1 ? 1 : max_chunks, (bytes + 256 * 16 - 1) / (256 * 16));
   gather_frames_kernel<<<dim3(chunks, batch), 256, 0, st>>>(src, dst, stride, off, bytes);
   XB_CUDA(cudaGetLastError());
   return 0;
