@@ -136,8 +136,10 @@ def run_ours(args):
     # host CPUs: the library's worker pool (workpool.h) is shared by the NB batches of this process; each batch
     # also has one driver thread (the Python thread inside xivo_batch_step), so workers + drivers = CPU budget
     budget = max(1, cpu_budget() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
-    os.environ.setdefault("XIVO_THREADS", str(max(1, budget - max(1, args.batches) + 1 - args.cpu_headroom)))
-    os.environ.setdefault("XIVO_DRIVERS", str(max(1, args.batches)))
+    # one driver per batch needs a CPU of its own: with a small budget (e.g. a node quota shared by 8 ranks) run fewer batches
+    args.batches = max(1, min(args.batches, budget // 4))
+    os.environ.setdefault("XIVO_THREADS", str(max(1, budget - args.batches + 1 - args.cpu_headroom)))
+    os.environ.setdefault("XIVO_DRIVERS", str(args.batches))
     import torch
 
     from xivo_b200 import capi, pyxivo
@@ -314,9 +316,9 @@ def run_ours(args):
             cores = min(cpu_budget(), args.cpu_cores) if args.cpu_cores else cpu_budget()  # CPUs the cgroup quota lets us run concurrently
             t0 = time.time()
             log("cpu baseline on", cores, "cores")
-            r = cpu_reference(cores, 25, 14)
+            r = cpu_reference(cores, 80, 14)
             cpu = dict(value=r["fps"], unit="frames/s", cores=cores, kind="port",
-                       sample=f"{cores} concurrent synthetic 640x480 sequences x 25 frames; timed: cv2 LK+FAST and Eigen-3.3.9 gate+update on the restated pipeline's inputs ({r['mean_frame_ms']:.2f} ms/frame/core, eigen={r['eigen']}, {time.time() - t0:.0f}s)",
+                       sample=f"{cores} concurrent synthetic 640x480 sequences x 80 frames; timed: cv2 LK+FAST and Eigen-3.3.9 gate+update on the restated pipeline's inputs ({r['mean_frame_ms']:.2f} ms/frame/core, eigen={r['eigen']}, {time.time() - t0:.0f}s)",
                        stage_share=r["stage_share"])
         out = dict(metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=W,
                    ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
@@ -370,8 +372,8 @@ def main():
     ap.add_argument("--profile-e2e", action="store_true", help="attribute kernel / host-phase time on the host-frame (e2e) path instead of the device-resident one")
     ap.add_argument("--profile-level", type=int, default=1, help="1: kernels + batch-level host phases, 2: + per-sequence host scopes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=192, help="independent sequences per GPU, split over --batches lock-step batches")
-    ap.add_argument("--batches", type=int, default=3, help="independent lock-step batches per GPU, one driver thread each; their host phases share the library's worker pool")
+    ap.add_argument("--seqs", type=int, default=256, help="independent sequences per GPU, split over --batches lock-step batches")
+    ap.add_argument("--batches", type=int, default=4, help="independent lock-step batches per GPU, one driver thread each; their host phases share the library's worker pool")
     ap.add_argument("--streams", type=int, default=4, help="distinct synthetic input streams shared by the sequences")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -511,7 +511,7 @@ __constant__ double kBpd[7] = {0.0862, 0.0, 0.6660, -0.7857, 0.9570, 0.0965, -0.
 __constant__ double kArk[3][6] = {{0.5, 0, 0, 0, 0, 0}, {0, 0.5, 0, 0, 0, 0}, {0, 0, 1.0, 0, 0, 0}};
 __constant__ double kBrk[4] = {1.0 / 6, 2.0 / 6, 2.0 / 6, 1.0 / 6};
 
-constexpr int IMU_THREADS = 128;
+constexpr int IMU_THREADS = 256;
 constexpr int IMU_CHUNK = 56;
 __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, double* __restrict__ P, const ImuStage* __restrict__ stages,
                                                                         const int* __restrict__ first, const int* __restrict__ nstages,
