@@ -100,6 +100,14 @@ int xivo_mh_gate(xivo_ctx* ctx, int G, int F, const double* camera, const double
 int xivo_ekf_update(xivo_ctx* ctx, int N, int M, const double* H, double* P, const double* inn, const double* diagR,
                     double* err);
 
+/* Same update with options.  XIVO_UPDATE_TF32X3: the rank-M covariance downdate P -= K (H P) runs on the
+ * tensor cores (tcgen05.mma kind::tf32, operands split hi+lo = "3xTF32", fp32 accumulator in TMEM) instead of
+ * fp64 CUDA cores: the "fp32 covariance" mode (BASELINE configs[2]); gain, innovation and the storage of P stay
+ * fp64.  Tolerance vs the fp64 update: |dP| <= 1e-5 * max|P| (tests/test_gpu_ekf.py). */
+#define XIVO_UPDATE_TF32X3 1u
+int xivo_ekf_update_ex(xivo_ctx* ctx, int N, int M, const double* H, double* P, const double* inn, const double* diagR,
+                       double* err, unsigned flags);
+
 /* Production form of the update: Jacobians -> stack H for the selected features with
  * Feature::FillJacobianBlock semantics (src/feature.cpp:658-684) -> update; replaces
  * Estimator::FilterUpdate (src/update.cpp:120-153) up to AbsorbError.  sel: nsel indices into the

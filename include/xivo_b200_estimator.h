@@ -11,7 +11,7 @@
  *     (the filter is sequential per stream; batching sequences is the only parallel axis);
  *   - kMaxGroup / kMaxFeature (compile-time -DEKF_MAX_GROUPS / -DEKF_MAX_FEATURES in the
  *     reference, src/core.h:92-105) are creation-time arguments.
- * cfg_json is the text of a reference config (cfg/*.json, JSON with comments).  "camera_cfg" and
+ * cfg_json is the text of a reference config (cfg/NAME.json, JSON with comments).  "camera_cfg" and
  * "tracker_cfg" may be embedded objects or paths, as in src/factory.cpp:31-45.
  * All functions return 0 or a negative XIVO_ERR_* code (include/xivo_b200.h); nothing throws.
  */

@@ -1,0 +1,45 @@
+// Compile/link check of include/xivo_b200.hpp: instantiates every member of the facade so that a signature
+// drift between the header and the C ABI fails at build time.  Run without a GPU it must report the
+// "no device" error (there is no CPU fallback); with a GPU it runs a two-frame point-cloud smoke.
+#include <cstdio>
+#include <cstring>
+
+#include "xivo_b200.hpp"
+
+int main(int argc, char** argv) {
+  const std::string cfg = argc > 1 ? argv[1] : "";
+  try {
+    auto est = xivo::Estimator::CreateFromFile(cfg, 4, 14);
+    est->InitWithSimDepths();
+    for (int k = 0; k < 30; ++k) {
+      est->InertialMeas(xivo::timestamp_t(k * 5000000LL), {0, 0, 0}, {0, 0, 9.8});
+      if (k % 8 == 0) est->VisualMeasPointCloud(xivo::timestamp_t(k * 5000000LL), {1, 2, 3}, {100, 100, 2, 200, 120, 2.5, 300, 200, 3});
+    }
+    auto g = est->gsb();
+    auto P = est->P();
+    std::printf("ok N=%d tracked=%zu T=(%g %g %g) P00=%g inst=%d groups=%d ts=%lld\n", est->state_dim(), est->tracked_features_no_descriptor().size(),
+                g[3], g[7], g[11], P[0], est->num_instate_features(), est->num_instate_groups(), (long long)est->ts().count());
+    (void)est->gbc(); (void)est->gsc(); (void)est->Pstate(); (void)est->Vsb(); (void)est->bg(); (void)est->ba(); (void)est->Rsg();
+    (void)est->MeasurementUpdateInitialized(); (void)est->VisionInitialized(); (void)est->gauge_group(); (void)est->num_mh_rejected();
+    (void)est->num_tracker_failed_to_track(); (void)est->num_tracker_new_detections();
+    (void)est->InstateFeatureIDs(); (void)est->InstateFeatureSinds(); (void)est->InstateFeatureRefGroups(); (void)est->InstateFeaturePositions();
+    (void)est->InstateGroupIDs(); (void)est->InstateGroupSinds(); (void)est->InstateGroupPoses();
+    std::vector<uint8_t> img(64 * 64, 0);
+    xivo::ImageView v{img.data(), 64, 64, 1};
+    xivo::Tracker trk;
+    auto kp = trk.Detect(v, 20);
+    auto fl = trk.TrackLK(v, v, {32.f, 32.f});
+    std::printf("tracker ok kp=%d status=%d\n", kp.total, (int)fl.status[0]);
+    try {
+      est->VisualMeas(xivo::timestamp_t(1000000000LL), v);  // simulation mode: must throw like the reference (estimator.cpp:1112-1115)
+      est->VisualMeasTrackerOnly(xivo::timestamp_t(1000000000LL), v);
+      est->VisualMeasPointCloudTrackerOnly(xivo::timestamp_t(1000000000LL), {1}, {1, 2, 3});
+    } catch (const xivo::Error& e) {
+      std::printf("expected error: %d\n", e.code);
+    }
+    return 0;
+  } catch (const xivo::Error& e) {
+    std::printf("xivo::Error %d: %s\n", e.code, e.what());
+    return e.code == XIVO_ERR_CUDA ? 42 : 1;
+  }
+}

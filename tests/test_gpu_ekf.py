@@ -68,6 +68,31 @@ def test_dense_update_matches_joseph(ctx, N, M):
     assert np.linalg.eigvalsh(Pg).min() > -1e-12 * np.abs(P).max()
 
 
+@pytest.mark.parametrize("N,M", [(89, 24), (203, 60), (299, 124), (23, 2), (130, 33)])
+def test_dense_update_tensor_core_tf32x3(ctx, N, M):
+    """XIVO_UPDATE_TF32X3: the downdate P -= K (HP) on tcgen05 tensor cores (3xTF32, fp32 accumulate in TMEM).
+    Tolerance (stated in include/xivo_b200.h): fp32-level, |dP_ij| <= 1e-5 sqrt(P_ii P_jj) elementwise and
+    1e-5 max|P|; gain / err are the fp64 kernels, hence identical."""
+    rng = np.random.default_rng(N + M)
+    A = rng.normal(size=(N, N))
+    scale = np.exp(rng.uniform(-5, 1, N))
+    P = (A @ A.T / N + np.eye(N)) * np.outer(scale, scale)
+    P = 0.5 * (P + P.T)
+    H = rng.normal(size=(M, N)) * (rng.uniform(size=(M, N)) < 0.15)
+    inn = rng.normal(size=M)
+    diagR = rng.uniform(0.5, 2.0, M)
+    P64, e64 = ctx.ekf_update(H, P, inn, diagR)
+    P32, e32 = ctx.ekf_update(H, P, inn, diagR, tf32x3=True)
+    d = np.sqrt(np.outer(np.diag(P), np.diag(P)))
+    assert np.abs(P64 - P).max() > 1e-3 * np.abs(P).max()  # the update is not a no-op
+    assert (np.abs(P32 - P64) / d).max() <= 1e-5
+    assert np.abs(P32 - P64).max() <= 1e-5 * np.abs(P).max()
+    assert np.array_equal(e32, e64)
+    assert np.array_equal(P32, P32.T)
+    Pr, _, _, _ = E.update_joseph(H, P, inn, diagR)
+    assert np.abs(P32 - Pr).max() <= 1e-5 * np.abs(P).max()
+
+
 def test_dense_update_zero_measurements(ctx):
     P = np.eye(23)
     Pg, err = ctx.ekf_update(np.zeros((0, 23)), P, np.zeros(0), np.zeros(0))

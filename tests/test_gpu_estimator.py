@@ -64,6 +64,38 @@ def test_pcw_trajectory_parity(G, F, method, sim_depths):
     b.close()
 
 
+def test_pcw_trajectory_tensor_core_covariance():
+    """"covariance_update": "tf32x3" — the downdate of every measurement update runs on tcgen05 tensor cores with
+    fp32-level accuracy (BASELINE configs[2] "fp32 covariance").  Stated tolerance against the fp64 oracle after
+    3 s (75 updates): position 1e-4 m, rotation 1e-5, covariance 1e-4 * max|P|; the in-state id tables stay exact."""
+    G, F = 15, 30
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    msgs, traj = sim.pcw_stream(cfg, duration=3.0, seed=0)
+    ref, ref_out = run_oracle_pcw(cfg, msgs, G, F, True)
+    cfg = dict(cfg)
+    cfg["covariance_update"] = "tf32x3"
+    b = pyxivo.Batch(cfg, n_seq=2, max_groups=G, max_features=F)
+    b.init_with_sim_depths()
+    k = 0
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            b.inertial_meas(ts, p[0], p[1])
+        else:
+            b.visual_meas_pointcloud(ts, p[0], p[1])
+            g_ref, ids_ref, gauge_ref = ref_out[k]
+            k += 1
+            g = b.gsb(0)
+            assert np.abs(g[:, 3] - g_ref[:, 3]).max() <= 1e-4, f"frame {k}"
+            assert np.abs(g[:, :3] - g_ref[:, :3]).max() <= 1e-5
+            assert sorted(b.instate_features(0)["ids"].tolist()) == ids_ref
+    P = b.P(0)
+    assert np.abs(P - ref.P).max() <= 1e-4 * np.abs(ref.P).max()
+    assert np.abs(P - ref.P).max() > 0  # and it is not the fp64 path
+    assert np.array_equal(b.P(1), P)
+    assert np.linalg.eigvalsh(0.5 * (P + P.T)).min() > -1e-9 * np.abs(P).max()
+    b.close()
+
+
 def test_pcw_single_sequence_pyxivo_facade():
     cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
     msgs, _ = sim.pcw_stream(cfg, duration=1.0, seed=3)
@@ -122,6 +154,50 @@ def test_image_pipeline_parity(channels):
     assert nframes > 25 and len(ref.tracks) >= 30
     c = b.counters(0)
     assert c["num_instate_features"] == len(ref.instate_features) and c["VisionInitialized"] == 1
+    b.close()
+
+
+def _run_image_parity(cfg, G, F, duration, seed, pos_tol=1e-5):
+    msgs, _ = sim.image_stream(cfg, duration=duration, seed=seed)
+    ref = EstimatorOracle(cfg, G=G, F=F)
+    b = pyxivo.Batch(cfg, n_seq=1, max_groups=G, max_features=F)
+    nframes = 0
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            ref.InertialMeas(ts, p[0], p[1])
+            b.inertial_meas(ts, p[0], p[1])
+        else:
+            ref.VisualMeas(ts, p)
+            b.visual_meas(ts, [p])
+            nframes += 1
+            ids, xy, _ = b.tracked_features(0)
+            rid = [f.id for f in ref.tracks]
+            assert ids.tolist() == rid, f"frame {nframes}"
+            if rid:
+                assert np.abs(xy - np.array([f.xp() for f in ref.tracks])).max() <= 1e-3
+            assert np.abs(b.gsb(0) - ref.gsb()).max() <= pos_tol, f"frame {nframes}"
+            assert sorted(b.instate_features(0)["ids"].tolist()) == sorted(f.id for f in ref.instate_features)
+    return ref, b, nframes
+
+
+def test_config3_tumvi_equidistant_512_parity():
+    """BASELINE configs[2]: equidistant 512x512 (cfg/tumvi_cam0.json intrinsics), 200 tracked features, N = 203."""
+    cfg = sim.load_cfg(os.path.join(CFG, "tumvi_512_equidistant.json"))
+    ref, b, nframes = _run_image_parity(cfg, 15, 30, 1.6, 1)
+    assert nframes >= 40 and len(ref.tracks) >= 150 and len(ref.instate_features) >= 20
+    P = b.P(0)
+    assert P.shape == (203, 203) and np.abs(P - ref.P).max() <= 1e-7 * np.abs(ref.P).max()
+    b.close()
+
+
+def test_config4_stress_1280x1024_800_features_parity():
+    """BASELINE configs[3]: 1280x1024, 800 tracked features, G = 15, F = 62 -> N = 299, M up to 124."""
+    cfg = sim.load_cfg(os.path.join(CFG, "stress_1280x1024.json"))
+    ref, b, nframes = _run_image_parity(cfg, 15, 62, 1.0, 1)
+    assert nframes >= 25 and len(ref.tracks) >= 500
+    assert b.counters(0)["num_instate_features"] == len(ref.instate_features) >= 25
+    P = b.P(0)
+    assert P.shape == (299, 299) and np.abs(P - ref.P).max() <= 1e-7 * np.abs(ref.P).max()
     b.close()
 
 

@@ -17,6 +17,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-pthread", "-Xp
 SOURCES = [
     ("tracker_kernels.cu", ["-fmad=false"]),
     ("ekf_kernels.cu", []),
+    ("ekf_tc_kernels.cu", []),
     ("capi.cu", []),
     # host state machine: AVX2/FMA for the 23x23 integrator loops (results within 1e-16 relative)
     ("estimator.cu", ["-Xcompiler", "-march=x86-64-v3"]),

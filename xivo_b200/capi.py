@@ -166,12 +166,14 @@ class Context:
         )
         return mh
 
-    def ekf_update(self, H, P, inn, diagR):
+    def ekf_update(self, H, P, inn, diagR, tf32x3=False):
+        """UpdateJosephForm; tf32x3=True runs the covariance downdate on the tensor cores (XIVO_UPDATE_TF32X3)."""
         H, inn, diagR = _f64(H), _f64(inn), _f64(diagR)
         P = np.array(P, dtype=np.float64, order="C", copy=True)
         M, N = H.shape if H.size else (0, P.shape[0])
         err = np.zeros(N)
-        _check(lib().xivo_ekf_update(self._h, N, M, _p(H), _p(P), _p(inn), _p(diagR), _p(err)), "xivo_ekf_update")
+        _check(lib().xivo_ekf_update_ex(self._h, N, M, _p(H), _p(P), _p(inn), _p(diagR), _p(err), C.c_uint(1 if tf32x3 else 0)),
+               "xivo_ekf_update_ex")
         return P, err
 
     def filter_update(self, G, F, camera, X24, groups, feat_x, feat_xp, feat_ref, feat_sind, sel, R, P, want_H=True):

@@ -240,7 +240,13 @@ int xivo_mh_gate(xivo_ctx* ctx, int G, int F, const double* camera, const double
 }
 
 int xivo_ekf_update(xivo_ctx* ctx, int N, int M, const double* H, double* P, const double* inn, const double* diagR, double* err) {
+  return xivo_ekf_update_ex(ctx, N, M, H, P, inn, diagR, err, 0);
+}
+
+int xivo_ekf_update_ex(xivo_ctx* ctx, int N, int M, const double* H, double* P, const double* inn, const double* diagR, double* err,
+                       unsigned flags) {
   API_BEGIN;
+  XB_REQUIRE((flags & ~(unsigned)XIVO_UPDATE_TF32X3) == 0, "ekf_update: unknown flags");
   XB_REQUIRE(N > 0 && M >= 0 && P && err && (M == 0 || (H && inn && diagR)), "ekf_update: bad arguments");
   if (M == 0) {
     for (int i = 0; i < N; ++i) err[i] = 0.0;
@@ -253,12 +259,13 @@ int xivo_ekf_update(xivo_ctx* ctx, int N, int M, const double* H, double* P, con
   XB_CUDA(cudaMemcpyAsync(dP.p, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
   XB_CUDA(cudaMemcpyAsync(dinn.p, inn, sizeof(double) * M, cudaMemcpyHostToDevice, st));
   XB_CUDA(cudaMemcpyAsync(dR.p, diagR, sizeof(double) * M, cudaMemcpyHostToDevice, st));
-  int rc = launch_ekf_update_dense(st, N, M, dH.p, dR.p, dinn.p, dP.p, derr.p, dHP.p, dKt.p, 1);
+  int rc = launch_ekf_update_dense(st, N, M, dH.p, dR.p, dinn.p, dP.p, derr.p, dHP.p, dKt.p, 1, (flags & XIVO_UPDATE_TF32X3) ? 1 : 0);
   if (rc) return rc;
   g_launches += 2;
   XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
   XB_CUDA(cudaMemcpyAsync(err, derr.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
   XB_CUDA(cudaStreamSynchronize(st));
+  if (flags & XIVO_UPDATE_TF32X3) XB_REQUIRE(ekf_cov_tc_fault(st) == 0, "ekf_update: the tensor-core downdate timed out waiting for its MMAs");
   return XIVO_OK;
 }
 

@@ -328,7 +328,7 @@ static size_t gain_smem(int Mmax, bool sparse) {
 }
 
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel, const double* Rmeas,
-                      double* P, double* err, double* HP, double* Kt, double* H_dense, int batch) {
+                      double* P, double* err, double* HP, double* Kt, double* H_dense, int batch, int tensor_core) {
   const int N = lay.N(), Mmax = 2 * lay.F;
   const size_t smem = gain_smem(Mmax, true);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: 2*F too large for the shared-memory Cholesky");
@@ -337,6 +337,7 @@ int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const 
   ekf_gain_kernel<true><<<batch, GAIN_THREADS, smem, st>>>(N, lay, jac, sel, nsel, 0, nullptr, nullptr, nullptr, Rmeas, P, err, HP,
                                                           Kt, H_dense, Mmax);
   Prof::get().stop(pi_, st);
+  if (tensor_core) return launch_ekf_cov_tc(st, N, nsel, 0, Mmax, HP, Kt, P, batch);
   const int nt = (N + CT - 1) / CT;
   {
     ProfScope ps("ekf_cov", st);
@@ -347,13 +348,14 @@ int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const 
 }
 
 int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,
-                            double* err, double* HP, double* Kt, int batch) {
+                            double* err, double* HP, double* Kt, int batch, int tensor_core) {
   const size_t smem = gain_smem(M, false);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: M too large for the shared-memory Cholesky");
   XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   EkfLayout lay{0, 0};
   ekf_gain_kernel<false><<<batch, GAIN_THREADS, smem, st>>>(N, lay, nullptr, nullptr, nullptr, M, H, diagR, inn, nullptr, P, err,
                                                            HP, Kt, nullptr, M);
+  if (tensor_core) return launch_ekf_cov_tc(st, N, nullptr, M, M, HP, Kt, P, batch);
   const int nt = (N + CT - 1) / CT;
   ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nullptr, M, M, HP, Kt, P);
   XB_CUDA(cudaGetLastError());

@@ -1,0 +1,237 @@
+// Tensor-core form of the covariance downdate of the EKF measurement update.
+//
+// Reference: Estimator::UpdateJosephForm (/root/reference/src/estimator.cpp:1257-1288).  After the gain
+// kernel (ekf_kernels.cu) has produced HP = H P (M x N) and K^T = S^-1 HP (M x N), the only dense
+// contraction left in the update is the rank-M downdate
+//        P  <-  P - K (H P),      D[i][j] = sum_k Kt[k][i] * HP[k][j],   i, j < N, k < M.
+// ekf_cov_kernel evaluates D in fp64 on the CUDA cores.  This file evaluates it on the 5th-generation
+// tensor cores: tcgen05.mma kind::tf32 with the fp32 accumulator tile in TMEM, operands split as
+// x = hi + lo (both TF32) and D = Alo*Bhi + Ahi*Blo + Ahi*Bhi ("3xTF32": ~21 mantissa bits per product,
+// fp32 accumulation), then  P(fp64) -= D  in the epilogue.  There is no fp64 kind of tcgen05.mma, so this
+// path is the "fp32 covariance" mode of SURVEY.md §8d (config 3): the correction carries fp32 accuracy,
+// P itself stays fp64 in HBM so every other kernel is unchanged.  It is opt-in ("covariance_update":
+// "tf32x3" in the estimator config, or flags bit 0 of xivo_ekf_update_ex); the default remains fp64.
+//
+// One CTA (128 threads = the 128 TMEM lanes) per (filter, 128-row tile, <=256-column chunk) of the upper
+// triangle.  Operands are staged by the CTA's threads (fp64 -> hi/lo TF32, transposed) into the canonical
+// K-major no-swizzle shared-memory layout of the UMMA matrix descriptor: 8-row x 16-byte core matrices,
+//   byte(row, k) = ((k / 4) * ROWS + row) * 16 + (k % 4) * 4
+// i.e. SBO (8-row group stride) = 128 B and LBO (stride between the two 16-byte K chunks of one MMA) =
+// ROWS * 16 B.  K (= measurement rows) is consumed in blocks of 32 (four K=8 MMAs per pass).
+#include <cstdint>
+#include <cstdlib>
+
+#include "kernels.h"
+#include "prof.h"
+
+namespace xb {
+namespace {
+
+constexpr int TC_MT = 128;       // rows per tile = TMEM lanes
+constexpr int TC_NT_MAX = 256;   // columns per chunk (UMMA N <= 256)
+constexpr int TC_KB = 32;        // K elements staged per block
+constexpr int TC_THREADS = 128;
+
+__device__ int g_tc_fault;  // set when an mbarrier wait timed out (never expected; keeps a bad build from hanging the GPU)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// UMMA shared-memory matrix descriptor (SM100): start address, LBO, SBO in 16-byte units, version 1,
+// layout type 0 (no swizzle), base offset 0.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// Instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_MT >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void split_store(double x, uint32_t* hi, uint32_t* lo, int idx) {
+  const uint32_t h = to_tf32((float)x);
+  hi[idx] = h;
+  lo[idx] = to_tf32((float)(x - (double)__uint_as_float(h)));
+}
+
+__global__ void __launch_bounds__(TC_THREADS) ekf_cov_tc_kernel(int N, const int* __restrict__ nsel, int Mdense, int Mmax,
+                                                                const double* __restrict__ HP, const double* __restrict__ Kt,
+                                                                double* __restrict__ P, int swap_lbo_sbo) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int b = blockIdx.z;
+  const int M = nsel ? 2 * nsel[b] : Mdense;
+  const int m0 = blockIdx.y * TC_MT;
+  const int n0 = m0 + blockIdx.x * TC_NT_MAX;  // only the upper triangle: columns start at the tile's first row
+  if (M == 0 || m0 >= N || n0 >= N) return;    // uniform over the CTA
+  const int ncols = min(TC_NT_MAX, N - n0);
+  const int NT = (ncols + 15) & ~15;           // UMMA N: multiple of 16 for M = 128
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint32_t* Ah = reinterpret_cast<uint32_t*>(tc_smem);
+  uint32_t* Al = Ah + TC_KB * TC_MT;
+  uint32_t* Bh = Al + TC_KB * TC_MT;
+  uint32_t* Bl = Bh + TC_KB * NT;
+  const double* __restrict__ HPb = HP + (size_t)b * Mmax * N;
+  const double* __restrict__ Ktb = Kt + (size_t)b * Mmax * N;
+  double* __restrict__ Pb = P + (size_t)b * N * N;
+
+  const uint32_t tmem_cols = NT <= 32 ? 32u : NT <= 64 ? 64u : NT <= 128 ? 128u : 256u;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_slot;
+
+  const uint32_t idesc = umma_idesc_tf32(NT);
+  const uint32_t a_chunk = TC_MT * 16, b_chunk = (uint32_t)NT * 16;  // bytes between consecutive 16-byte K chunks
+  const uint32_t a_lbo = swap_lbo_sbo ? 128u : a_chunk, a_sbo = swap_lbo_sbo ? a_chunk : 128u;
+  const uint32_t b_lbo = swap_lbo_sbo ? 128u : b_chunk, b_sbo = swap_lbo_sbo ? b_chunk : 128u;
+  const int nkb = (M + TC_KB - 1) / TC_KB;
+  bool ok = true;
+  uint32_t first = 1;
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int k0 = kb * TC_KB;
+    // ---- stage A(i, k) = Kt[k][m0 + i] and B(j, k) = HP[k][n0 + j] as hi/lo TF32, zero padded
+    for (int t = tid; t < TC_KB * TC_MT; t += TC_THREADS) {
+      const int k = t >> 7, r = t & (TC_MT - 1);
+      const int gk = k0 + k, gi = m0 + r;
+      const double x = (gk < M && gi < N) ? Ktb[(size_t)gk * N + gi] : 0.0;
+      split_store(x, Ah, Al, (((k >> 2) * TC_MT + r) << 2) + (k & 3));
+    }
+    for (int t = tid; t < TC_KB * NT; t += TC_THREADS) {
+      const int k = t / NT, r = t - k * NT;
+      const int gk = k0 + k, gj = n0 + r;
+      const double x = (gk < M && gj < N) ? HPb[(size_t)gk * N + gj] : 0.0;
+      split_store(x, Bh, Bl, (((k >> 2) * NT + r) << 2) + (k & 3));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int ksteps = (min(TC_KB, M - k0) + 7) >> 3;  // K = 8 per tf32 MMA; all-zero steps are skipped
+      const uint32_t aH = smem_u32(Ah), aL = smem_u32(Al), bH = smem_u32(Bh), bL = smem_u32(Bl);
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {  // small terms first
+        const uint32_t sa = pass == 0 ? aL : aH, sb = pass == 1 ? bL : bH;
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t da = umma_smem_desc(sa + (uint32_t)ks * 2u * a_chunk, a_lbo, a_sbo);
+          const uint64_t db = umma_smem_desc(sb + (uint32_t)ks * 2u * b_chunk, b_lbo, b_sbo);
+          umma_tf32(tmem, da, db, idesc, first ? 0u : 1u);
+          first = 0;
+        }
+      }
+      // arrives on the mbarrier when every MMA issued so far has completed (implies fence::before_thread_sync)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    __syncwarp();
+    {  // wait for phase kb of the barrier (bounded: a broken build must not hang the device)
+      const uint32_t parity = (uint32_t)kb & 1u, addr = smem_u32(&bar);
+      uint32_t done = 0;
+      const long long t_start = clock64();
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t_start > 400000000LL) break;  // ~0.2 s: the MMAs of one block take microseconds
+      }
+      if (!done) ok = false;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();  // every thread is past the wait before the operands are overwritten
+  }
+
+  // ---- epilogue: TMEM lane = row, 8 consecutive columns per tcgen05.ld; P -= D on the upper triangle, mirrored
+  const int row = m0 + warp * 32 + lane;
+  if (!__all_sync(0xffffffffu, ok)) {
+    if (lane == 0) atomicExch(&g_tc_fault, 1);
+  } else {
+    for (int c = 0; c < NT; c += 8) {
+      uint32_t v[8];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(taddr)
+                   : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < N) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = n0 + c + j;
+          if (col < N && col >= row) {
+            const double val = Pb[(size_t)row * N + col] - (double)__uint_as_float(v[j]);
+            Pb[(size_t)row * N + col] = val;
+            if (col != row) Pb[(size_t)col * N + row] = val;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
+}  // namespace
+
+size_t ekf_cov_tc_smem(int N) {
+  const int nt = std::min(TC_NT_MAX, (N + 15) & ~15);
+  return (size_t)2 * TC_KB * (TC_MT + nt) * sizeof(uint32_t);
+}
+
+int launch_ekf_cov_tc(cudaStream_t st, int N, const int* nsel, int Mdense, int Mmax, const double* HP, const double* Kt, double* P,
+                      int batch) {
+  static const int variant = getenv("XIVO_TC_SWAP") ? atoi(getenv("XIVO_TC_SWAP")) : 0;  // bring-up switch: LBO/SBO roles
+  const size_t smem = ekf_cov_tc_smem(N);
+  XB_CUDA(cudaFuncSetAttribute(ekf_cov_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tm = (N + TC_MT - 1) / TC_MT, tn = (N + TC_NT_MAX - 1) / TC_NT_MAX;
+  ProfScope ps("ekf_cov", st);
+  ekf_cov_tc_kernel<<<dim3(tn, tm, batch), TC_THREADS, smem, st>>>(N, nsel, Mdense, Mmax, HP, Kt, P, variant);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ekf_cov_tc_fault(cudaStream_t st) {
+  int f = 0;
+  if (cudaMemcpyFromSymbolAsync(&f, g_tc_fault, sizeof(int), 0, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  return f;
+}
+
+}  // namespace xb

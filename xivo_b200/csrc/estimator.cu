@@ -82,6 +82,7 @@ class Batch {
   }
   xivo_ctx* ctx;
   int B, N, maxops, max_sub;
+  int cov_tc = 0;  // covariance downdate on the tensor cores ("covariance_update": "tf32x3")
   EkfLayout lay;
   std::vector<std::unique_ptr<Estimator>> est;
   // EKF device state
@@ -131,6 +132,7 @@ class Batch {
     cudaEventCreateWithFlags(&stg_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&wait_ev, cudaEventDisableTiming);
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
+    cov_tc = est[0]->c.cov_update_tf32x3 ? 1 : 0;
     maxops = 4 * (lay.F + lay.G) + 16;
     max_sub = est[0]->tc.num_features_max + 8;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dP), sizeof(double) * B * N * N) == cudaSuccess &&
@@ -681,7 +683,7 @@ class Batch {
     }
     XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st)); XB_CUDA(sel.up(st)); XB_CUDA(nsel.up(st));
     if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
-    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B)) return rc;
+    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B, cov_tc)) return rc;
     if (int rc = launch_pack_state(st, N, dP, dErr, pack.d, B)) return rc;
     g_launches += 4;
     for (int b : full) {

@@ -252,6 +252,7 @@ struct EstimatorCfg {
   double pd_stepsize = 0.002, rk4_stepsize = 0.002;
   int max_features_mem = 256, max_groups_mem = 128;
   int message_buffer_size = 10;
+  bool cov_update_tf32x3 = false;  // "covariance_update": "tf32x3" (ekf_tc_kernels.cu)
 };
 
 struct MotionX {

@@ -54,11 +54,18 @@ int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam
 // scratch: HP (B x 2F x N), Kt (B x 2F x N).  Outputs: err (B x N), P updated in place.
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel,
                       const double* Rmeas /*B*/, double* P, double* err, double* HP, double* Kt, double* H_dense /*or null*/,
-                      int batch);
+                      int batch, int tensor_core = 0);
 
 // Dense-input variant used by the kernel-level C ABI (arbitrary H, diagR), same kernels underneath.
 int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,
-                            double* err, double* HP, double* Kt, int batch);
+                            double* err, double* HP, double* Kt, int batch, int tensor_core = 0);
+
+// Tensor-core (tcgen05, 3xTF32, fp32 accumulator in TMEM) form of the downdate P -= Kt^T HP (ekf_tc_kernels.cu);
+// selected by tensor_core != 0 in the two launchers above.  ekf_cov_tc_fault: 1 if a kernel ever gave up waiting
+// for its MMAs (never expected), -1 on a CUDA error.
+int launch_ekf_cov_tc(cudaStream_t st, int N, const int* nsel, int Mdense, int Mmax, const double* HP, const double* Kt, double* P,
+                      int batch);
+int ekf_cov_tc_fault(cudaStream_t st);
 
 // Covariance edit list (AddGroupToState / AddFeatureToState / Remove* / FixFeatureXY / SwitchRefGroup).
 struct EditOp {

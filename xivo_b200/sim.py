@@ -130,22 +130,47 @@ def pcw_stream(cfg: dict, duration=4.0, imu_dt=0.005, vision_dt=0.04, seed=0, no
     return [(k, int(round(t * 1e9)), p) for (t, _, k, p) in msgs], traj
 
 
-class PlaneRenderer:
-    """Textured wall y = y0 seen by a pinhole camera: each pixel ray is intersected with the plane
-    and the texture is sampled bilinearly.  Physically consistent, so LK tracks are 3-D consistent."""
+def pixel_rays(cam: dict):
+    """Viewing ray (unit z for pinhole, unit norm for equidistant) and vignette weight of every pixel.
+    pinhole: common/camera_pinhole.h:40-52; equidistant (Kannala-Brandt k0123): common/camera_equidist.h:97-160
+    solved per pixel with Newton's method on theta."""
+    rows, cols = cam["rows"], cam["cols"]
+    v, u = np.mgrid[0:rows, 0:cols].astype(float)
+    xn, yn = (u - cam["cx"]) / cam["fx"], (v - cam["cy"]) / cam["fy"]
+    if cam.get("model", "pinhole") == "pinhole":
+        return np.stack([xn, yn, np.ones_like(xn)], -1), None
+    k0, k1, k2, k3 = cam.get("k0123", (0, 0, 0, 0))
+    rd = np.hypot(xn, yn)
+    th = rd.copy()
+    for _ in range(12):
+        t2 = th * th
+        f = th * (1 + t2 * (k0 + t2 * (k1 + t2 * (k2 + t2 * k3)))) - rd
+        df = 1 + t2 * (3 * k0 + t2 * (5 * k1 + t2 * (7 * k2 + t2 * 9 * k3)))
+        th = th - f / df
+    sc = np.sin(th) / np.maximum(rd, 1e-12)
+    rays = np.stack([xn * sc, yn * sc, np.cos(th)], -1)
+    # smooth vignette like a real fisheye: full brightness to 65 deg, dark beyond 80 deg (no hard edge for FAST)
+    w = np.clip((np.deg2rad(80.0) - th) / np.deg2rad(15.0), 0.0, 1.0)
+    return rays, w * w * (3 - 2 * w)
 
-    def __init__(self, rows, cols, K, y0=3.0, seed=0, tex_scale=110.0, size=2048):
+
+class PlaneRenderer:
+    """Textured wall y = y0 seen by a pinhole or equidistant camera: each pixel ray is intersected with the
+    plane and the texture is sampled bilinearly.  Physically consistent, so LK tracks are 3-D consistent."""
+
+    def __init__(self, rows, cols, K, y0=3.0, seed=0, tex_scale=110.0, size=2048, cam=None):
         from . import synth
 
         self.rows, self.cols, self.K, self.y0, self.s, self.size = rows, cols, K, y0, tex_scale, size
         self.tex = synth.texture_canvas(size - 64, size - 64, seed, pad=32)
-        v, u = np.mgrid[0:rows, 0:cols]
-        self.rays = np.stack([(u - K[2]) / K[0], (v - K[3]) / K[1], np.ones_like(u, dtype=float)], -1)
+        cam = cam or dict(model="pinhole", rows=rows, cols=cols, fx=K[0], fy=K[1], cx=K[2], cy=K[3])
+        self.rays, self.vignette = pixel_rays(cam)
 
     def render(self, Rsc, Tsc, noise_rng=None, fast=False):
         """fast=True uses cv2.remap (bench only: ~40x quicker, fixed-point bilinear weights)."""
         d = self.rays @ Rsc.T
-        lam = (self.y0 - Tsc[1]) / d[..., 1]
+        dy = d[..., 1] if self.vignette is None else np.maximum(d[..., 1], 0.05)  # wide-angle rays may miss the wall
+        lam = (self.y0 - Tsc[1]) / dy
         X = Tsc[0] + lam * d[..., 0]
         Z = Tsc[2] + lam * d[..., 2]
         tx = X * self.s + self.size / 2
@@ -156,6 +181,8 @@ class PlaneRenderer:
             img = cv2.remap(self.tex, tx.astype(np.float32), ty.astype(np.float32), cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
         else:
             img = ndimage.map_coordinates(self.tex, [ty, tx], order=1, mode="reflect")
+        if self.vignette is not None:
+            img = img * self.vignette
         if noise_rng is not None:
             img = img + noise_rng.normal(0, 1.5, img.shape)
         return np.clip(np.rint(img), 0, 255).astype(np.uint8)
@@ -173,7 +200,7 @@ def image_stream(cfg: dict, duration=2.0, imu_dt=0.005, vision_dt=0.04, seed=0, 
     Wbc = np.array(X["Wbc"], dtype=float)
     Rbc = rodrigues(Wbc) if Wbc.size == 3 else Wbc.reshape(3, 3)
     Tbc = np.array(X["Tbc"], dtype=float)
-    rend = PlaneRenderer(cam["rows"], cam["cols"], K, seed=seed)
+    rend = PlaneRenderer(cam["rows"], cam["cols"], K, seed=seed, cam=cam)
     tt = lambda t: max(0.0, t - stationary)
     msgs = []
     for t in np.arange(0, duration, imu_dt):
