@@ -155,6 +155,7 @@ def run_ours(args):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = load_cfg()
+    cfg["covariance_update"] = args.cov_update  # "fp64" (default, exact parity) or "tf32x3" (tcgen05 downdate, fp32 accuracy)
     B, K, W = args.seqs, args.steps, args.warmup
     n_frames = PREROLL_FRAMES + 3 * (W + K) + 4
     log("rendering", min(B, args.streams), "streams x", n_frames, "frames")
@@ -321,8 +322,9 @@ def run_ours(args):
                        sample=f"{cores} concurrent synthetic 640x480 sequences x 80 frames; timed: cv2 LK+FAST and Eigen-3.3.9 gate+update on the restated pipeline's inputs ({r['mean_frame_ms']:.2f} ms/frame/core, eigen={r['eigen']}, {time.time() - t0:.0f}s)",
                        stage_share=r["stage_share"])
         out = dict(metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=W,
-                   ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                   config=dict(workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
+                   ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype="f64" if args.cov_update == "fp64" else "f64 state, 3xTF32 tensor-core covariance downdate", data="synthetic",
+                   config=dict(covariance_update=args.cov_update, workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
                                sequences_per_gpu=B, batches_per_gpu=NB, host_threads=int(os.environ.get("XIVO_THREADS", "0")) or None, host_cpu_budget=budget, distinct_streams=S, frames_per_step=world * B, channels=1,
                                l2_policy="inputs larger than L2 are not needed: every step reads a new frame set (B x 307 KB) from the stream buffers; covariance/pyramids are the resident state by design",
                                message_buffer_size=cfg.get("message_buffer_size", 10)),
@@ -376,6 +378,7 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="independent lock-step batches per GPU, one driver thread each; their host phases share the library's worker pool")
     ap.add_argument("--streams", type=int, default=4, help="distinct synthetic input streams shared by the sequences")
     ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--cov-update", default="fp64", choices=["fp64", "tf32x3"], help="arithmetic of the covariance downdate (tf32x3 = tcgen05 tensor cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

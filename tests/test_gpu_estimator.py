@@ -201,6 +201,78 @@ def test_config4_stress_1280x1024_800_features_parity():
     b.close()
 
 
+def test_ate_within_one_percent_of_oracle_through_asl_files(tmp_path):
+    """BASELINE north_star: "ATE within 1 % of reference".  The synthetic sequence goes through the formats around the
+    path (xivo_b200.dataio): written as an ASL folder, loaded like src/loader.cpp, run, trajectory written like
+    src/app/vio.cpp:101-106, evaluated like scripts/tum_rgbd_benchmark_tools/evaluate_ate.py against the ground truth."""
+    from xivo_b200 import dataio
+
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    cfg["camera_cfg"].update(rows=240, cols=320, fx=137.5, fy=137.5, cx=160, cy=120)
+    cfg["tracker_cfg"].update(num_features_min=60, num_features_max=80)
+    msgs, traj = sim.image_stream(cfg, duration=2.4, seed=3)
+    cam_dir, imu_dir = dataio.write_asl(str(tmp_path / "seq"), msgs)
+    loaded = dataio.load_asl(cam_dir, imu_dir)
+    assert sorted((ts, k) for k, ts, _ in loaded) == sorted((ts, k) for k, ts, _ in msgs)
+    ref = EstimatorOracle(cfg, G=4, F=14)
+    b = pyxivo.Batch(cfg, n_seq=1, max_groups=4, max_features=14)
+    st_ours, g_ours, g_ref = [], [], []
+    for kind, ts, p in loaded:
+        if kind == "imu":
+            ref.InertialMeas(ts, p[0], p[1])
+            b.inertial_meas(ts, p[0], p[1])
+        else:
+            img = dataio.read_pnm(p)
+            ref.VisualMeas(ts, img)
+            b.visual_meas(ts, [img])
+            if b.counters(0)["VisionInitialized"]:
+                st_ours.append(b.now(0))
+                g_ours.append(b.gsb(0))
+                g_ref.append(ref.gsb().copy())
+    assert len(st_ours) > 30
+    out = str(tmp_path / "traj.txt")
+    dataio.write_vio_trajectory(out, st_ours, g_ours)
+    stamps, poses = dataio.read_vio_trajectory(out)
+    t = stamps * 1e-9
+    gt = np.array([traj.pos(max(0.0, x - 0.2)) for x in t])  # image_stream keeps the platform at rest for the first 0.2 s
+    ate_ours = dataio.ate(t, gt, t, poses[:, :, 3])["rmse"]
+    ate_ref = dataio.ate(t, gt, t, np.array(g_ref)[:, :, 3])["rmse"]
+    assert abs(ate_ours - ate_ref) <= 0.01 * ate_ref, (ate_ours, ate_ref)
+    assert np.abs(poses - np.array(g_ref)).max() <= 1e-5  # the written file carries the oracle's trajectory
+    b.close()
+
+
+def test_ate_on_point_cloud_world_is_small_and_within_one_percent_of_oracle():
+    """The same criterion where the filter has metric scale (depths initialised from the simulator, like
+    scripts/pyxivo_pcw.py): ATE against the analytic ground truth is centimetres, and ours is within 1 % of the oracle's."""
+    from xivo_b200 import dataio
+
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    msgs, traj = sim.pcw_stream(cfg, duration=4.0, seed=2)
+    ref, _ = run_oracle_pcw(cfg, [], 4, 14, True)
+    b = pyxivo.Batch(cfg, n_seq=1, max_groups=4, max_features=14)
+    b.init_with_sim_depths()
+    t, p_ours, p_ref = [], [], []
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            ref.InertialMeas(ts, p[0], p[1])
+            b.inertial_meas(ts, p[0], p[1])
+        else:
+            ref.VisualMeasPointCloud(ts, p[0], p[1])
+            b.visual_meas_pointcloud(ts, p[0], p[1])
+            t.append(b.now(0) * 1e-9)
+            p_ours.append(b.gsb(0)[:, 3].copy())
+            p_ref.append(ref.gsb()[:, 3].copy())
+    t = np.array(t)
+    keep = t > 0  # the first messages sit in the reorder buffer: the filter clock has not started
+    t, p_ours, p_ref = t[keep], np.array(p_ours)[keep], np.array(p_ref)[keep]
+    gt = np.array([traj.pos(x) for x in t])
+    a_ours, a_ref = dataio.ate(t, gt, t, p_ours), dataio.ate(t, gt, t, p_ref)
+    assert a_ref["rmse"] < 0.05 and a_ours["pairs"] > 60
+    assert abs(a_ours["rmse"] - a_ref["rmse"]) <= 0.01 * a_ref["rmse"], (a_ours, a_ref)
+    b.close()
+
+
 def test_tracker_only_mode():
     cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
     cfg["camera_cfg"].update(rows=240, cols=320, fx=137.5, fy=137.5, cx=160, cy=120)
