@@ -92,7 +92,7 @@ def test_pcw_trajectory_tensor_core_covariance():
     assert np.abs(P - ref.P).max() <= 1e-4 * np.abs(ref.P).max()
     assert np.abs(P - ref.P).max() > 0  # and it is not the fp64 path
     assert np.array_equal(b.P(1), P)
-    assert np.linalg.eigvalsh(0.5 * (P + P.T)).min() > -1e-9 * np.abs(P).max()
+    assert np.linalg.eigvalsh(0.5 * (P + P.T)).min() > -1e-6 * np.abs(P).max()  # PSD to fp32 accuracy
     b.close()
 
 
