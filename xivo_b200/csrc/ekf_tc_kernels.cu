@@ -12,9 +12,10 @@
 // P itself stays fp64 in HBM so every other kernel is unchanged.  It is opt-in ("covariance_update":
 // "tf32x3" in the estimator config, or flags bit 0 of xivo_ekf_update_ex); the default remains fp64.
 //
-// One CTA (128 threads = the 128 TMEM lanes) per (filter, 128-row tile, <=256-column chunk) of the upper
-// triangle.  Operands are staged by the CTA's threads (fp64 -> hi/lo TF32, transposed) into the canonical
-// K-major no-swizzle shared-memory layout of the UMMA matrix descriptor: 8-row x 16-byte core matrices,
+// One CTA (128 threads = the 128 TMEM lanes) per (filter, 128-row tile, 32-column chunk) of the upper
+// triangle (narrow chunks: the tile is latency-, not math-bound, so more CTAs per filter win).  Operands
+// are staged by the CTA's threads (fp64 -> hi/lo TF32, transposed) into the canonical K-major no-swizzle
+// shared-memory layout of the UMMA matrix descriptor: 8-row x 16-byte core matrices,
 //   byte(row, k) = ((k / 4) * ROWS + row) * 16 + (k % 4) * 4
 // i.e. SBO (8-row group stride) = 128 B and LBO (stride between the two 16-byte K chunks of one MMA) =
 // ROWS * 16 B.  K (= measurement rows) is consumed in blocks of 32 (four K=8 MMAs per pass).
@@ -28,7 +29,7 @@ namespace xb {
 namespace {
 
 constexpr int TC_MT = 128;       // rows per tile = TMEM lanes
-constexpr int TC_NT_MAX = 256;   // columns per chunk (UMMA N <= 256)
+constexpr int TC_NT_MAX = 32;    // columns per chunk: narrow chunks = more CTAs per filter (the tile work is latency, not math)
 constexpr int TC_KB = 32;        // K elements staged per block
 constexpr int TC_THREADS = 128;
 
@@ -69,10 +70,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       : "memory");
 }
 
-__device__ __forceinline__ void split_store(double x, uint32_t* hi, uint32_t* lo, int idx) {
-  const uint32_t h = to_tf32((float)x);
-  hi[idx] = h;
-  lo[idx] = to_tf32((float)(x - (double)__uint_as_float(h)));
+// four consecutive k of one row -> 16-byte chunk `chunk` of the hi array and of the lo array (x = hi + lo, both TF32)
+__device__ __forceinline__ void stage_chunk(const double (&x)[4], uint32_t* hi, uint32_t* lo, int chunk) {
+  uint4 h, l;
+  uint32_t* hp = &h.x;
+  uint32_t* lp = &l.x;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t t = to_tf32((float)x[q]);
+    hp[q] = t;
+    lp[q] = to_tf32((float)(x[q] - (double)__uint_as_float(t)));
+  }
+  reinterpret_cast<uint4*>(hi)[chunk] = h;
+  reinterpret_cast<uint4*>(lo)[chunk] = l;
 }
 
 __global__ void __launch_bounds__(TC_THREADS) ekf_cov_tc_kernel(int N, const int* __restrict__ nsel, int Mdense, int Mmax,
@@ -123,24 +133,35 @@ __global__ void __launch_bounds__(TC_THREADS) ekf_cov_tc_kernel(int N, const int
 
   for (int kb = 0; kb < nkb; ++kb) {
     const int k0 = kb * TC_KB;
-    // ---- stage A(i, k) = Kt[k][m0 + i] and B(j, k) = HP[k][n0 + j] as hi/lo TF32, zero padded
-    for (int t = tid; t < TC_KB * TC_MT; t += TC_THREADS) {
-      const int k = t >> 7, r = t & (TC_MT - 1);
-      const int gk = k0 + k, gi = m0 + r;
-      const double x = (gk < M && gi < N) ? Ktb[(size_t)gk * N + gi] : 0.0;
-      split_store(x, Ah, Al, (((k >> 2) * TC_MT + r) << 2) + (k & 3));
+    // ---- stage A(i, k) = Kt[k][m0 + i] and B(j, k) = HP[k][n0 + j] as hi/lo TF32, zero padded.  A thread owns one row and
+    // converts four consecutive k at a time: four coalesced loads -> one 16-byte chunk of the hi array and one of the lo array.
+    const int kreal = min(TC_KB, M - k0);
+    const int kgroups = ((kreal + 7) >> 3) << 1;  // 16-byte chunks the MMAs of this block read
+    {
+      const int gi = m0 + tid;
+      const double* __restrict__ src = Ktb + (size_t)k0 * N + gi;
+#pragma unroll 2
+      for (int g = 0; g < kgroups; ++g) {
+        double x[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x[q] = (gi < N && 4 * g + q < kreal) ? src[(size_t)(4 * g + q) * N] : 0.0;
+        stage_chunk(x, Ah, Al, g * TC_MT + tid);
+      }
     }
-    for (int t = tid; t < TC_KB * NT; t += TC_THREADS) {
-      const int k = t / NT, r = t - k * NT;
-      const int gk = k0 + k, gj = n0 + r;
-      const double x = (gk < M && gj < N) ? HPb[(size_t)gk * N + gj] : 0.0;
-      split_store(x, Bh, Bl, (((k >> 2) * NT + r) << 2) + (k & 3));
+    for (int u = tid; u < kgroups * NT; u += TC_THREADS) {  // NT <= 32 rows: the k groups are spread over the warps
+      const int g = u / NT, r = u - g * NT;
+      const int gj = n0 + r;
+      const double* __restrict__ src = HPb + (size_t)k0 * N + gj;
+      double x[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = (gj < N && 4 * g + q < kreal) ? src[(size_t)(4 * g + q) * N] : 0.0;
+      stage_chunk(x, Bh, Bl, g * NT + r);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int ksteps = (min(TC_KB, M - k0) + 7) >> 3;  // K = 8 per tf32 MMA; all-zero steps are skipped
+      const int ksteps = kgroups >> 1;  // K = 8 per tf32 MMA; all-zero steps are skipped
       const uint32_t aH = smem_u32(Ah), aL = smem_u32(Al), bH = smem_u32(Bh), bL = smem_u32(Bl);
 #pragma unroll 1
       for (int pass = 0; pass < 3; ++pass) {  // small terms first
