@@ -670,6 +670,202 @@ __global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_kernel(int N, d
   }
 }
 
+// Second formulation of the same algebra (identical operation order per element): every thread owns fixed elements — a strip
+// thread keeps its FK[q] / A[q] of all stages of the sub-step in registers, a P thread keeps its covariance entries in registers —
+// so the Runge-Kutta combinations need no shared-memory round trip and no index tables, and the stage chain has two barriers per
+// stage (double-buffered Acc / SA / CV) instead of three.  ncu of the first formulation: 29 % of stall samples at barriers,
+// IMAD/LDS/ISETP index traffic 39 % of the issued instructions, DFMA 6 % (profiles/r01c_source_summaries.txt).
+__device__ __forceinline__ double v_block(const F9s& f, const ImuConst& c, int e) {  // (R diag(qa) R^T)[e / 3][e % 3]
+  const int i = e / 3, j = e - 3 * i;
+  return f.R[3 * i] * c.qimu[3] * f.R[3 * j] + f.R[3 * i + 1] * c.qimu[4] * f.R[3 * j + 1] + f.R[3 * i + 2] * c.qimu[5] * f.R[3 * j + 2];
+}
+
+__global__ void __launch_bounds__(IMU_THREADS) imu_cov_propagate_v2_kernel(int N, double* __restrict__ P, const ImuStage* __restrict__ stages,
+                                                                           const int* __restrict__ first, const int* __restrict__ nstages,
+                                                                           const ImuConst* __restrict__ cst) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int nall = nstages[b];
+  if (nall == 0) return;
+  __shared__ double sP[529], sP0[529], sAcc[2][207], sSA[2][207], sPhi[2][207], sCV[2][9], sGc[23];
+  __shared__ ImuConst c;
+  if (tid < (int)(sizeof(ImuConst) / 8)) reinterpret_cast<double*>(&c)[tid] = reinterpret_cast<const double*>(cst + b)[tid];
+  double* __restrict__ Pb = P + (size_t)b * N * N;
+  const ImuStage* __restrict__ stg = stages + first[b];
+  // ---- fixed ownership
+  const bool strip = tid < 207;               // element (si, sj) of the 9 x 23 strips
+  const int si = strip ? tid / 23 : 0, sj = strip ? tid - 23 * si : 0;
+  const bool vthr = tid >= 224 && tid < 233;  // element ve of the 3 x 3 accel-noise block (its own warp)
+  const int ve = vthr ? tid - 224 : 0;
+  int pi[3], pj[3];                           // covariance entries tid, tid + 256, tid + 512
+  bool pv[3];
+  double preg[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    const int t = tid + IMU_THREADS * m;
+    pv[m] = t < 529;
+    pi[m] = pv[m] ? t / 23 : 0;
+    pj[m] = pv[m] ? t - 23 * pi[m] : 0;
+    preg[m] = pv[m] ? Pb[(size_t)pi[m] * N + pj[m]] : 0.0;
+    if (pv[m]) sP[t] = preg[m];
+  }
+  if (strip) sPhi[0][tid] = si == sj ? 1.0 : 0.0;
+  __syncthreads();
+  const int nst = c.stages_per_step;
+  const bool pd = nst == 7;
+  if (tid < 23) {  // state-independent diagonal of G Q G^T
+    double v = 0.0;
+    if (tid < 3) v = c.qimu[tid];
+    else if (tid >= 9 && tid < 12) v = c.qimu[6 + tid - 9];
+    else if (tid >= 12 && tid < 15) v = c.qimu[9 + tid - 12];
+    sGc[tid] = v;
+  }
+  extern __shared__ __align__(16) unsigned char imu_dyn[];
+  F9s* sFc = reinterpret_cast<F9s*>(imu_dyn);
+  double* sH = reinterpret_cast<double*>(sFc + IMU_CHUNK);
+  auto load_chunk = [&](int c0) {  // as in the first formulation: non-zero blocks of F for IMU_CHUNK stages, built in parallel
+    __syncthreads();
+    const int n = min(IMU_CHUNK, nall - c0);
+    for (int u = tid; u < n * 9; u += IMU_THREADS) {
+      const int q = u / 9, e = u - 9 * q;
+      const int i = e / 3, j = e - 3 * i;
+      const double* src = reinterpret_cast<const double*>(stg + c0 + q);
+      const double* Rm = src;
+      const double* gc = src + 9;
+      const double* ac = src + 12;
+      F9s& f = sFc[q];
+      f.R[e] = Rm[e];
+      f.dVba[e] = -Rm[e];
+      f.dW[e] = -hat_elem(gc, i, j);
+      double v = 0, vg = 0;
+      for (int k = 0; k < 3; ++k) {
+        v += Rm[3 * i + k] * hat_elem(ac, k, j);
+        vg += Rm[3 * i + k] * hat_elem(c.g, k, j);
+      }
+      f.dVW[e] = -v;
+      if (j < 2) f.dVg[2 * i + j] = -vg;
+    }
+    for (int u = tid; u < n; u += IMU_THREADS) sH[u] = reinterpret_cast<const double*>(stg + c0 + u)[15];
+    __syncthreads();
+  };
+  // increment of covariance entry (i, j): strip_sym(SA) + sw * diag(GQG const) + CV on the velocity block
+  auto p_inc = [&](int i, int j, int buf, double sw) {
+    double inc = (i < 9 ? sSA[buf][i * 23 + j] : 0.0) + (j < 9 ? sSA[buf][j * 23 + i] : 0.0);
+    if (i == j) inc += sw * sGc[i];
+    if (i >= 6 && i < 9 && j >= 6 && j < 9) inc += sCV[buf][(i - 6) * 3 + j - 6];
+    return inc;
+  };
+  int buf = 0, pb = 0;
+  for (int base = 0; base + nst <= nall; base += nst) {
+    if (base % IMU_CHUNK == 0) load_chunk(base);
+    const int cb = base % IMU_CHUNK;
+    const double henc = sH[cb];
+    const double h = fabs(henc);
+    double FK[7], A[7], V[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) FK[q] = A[q] = V[q] = 0.0;
+    {
+      const F9s& f = sFc[cb];
+      if (strip) {
+        FK[0] = f9_dense(f, si, sj);
+        A[0] = f9_elem(f, sP, si, sj, false);
+      }
+      if (vthr) V[0] = v_block(f, c, ve);
+    }
+#pragma unroll
+    for (int s = 1; s < 7; ++s) {
+      if (s < nst) {
+        const double* a = pd ? kApd[s - 1] : kArk[s - 1];
+        double sa = 0;
+#pragma unroll
+        for (int q = 0; q < s; ++q) sa += a[q];
+        if (strip) {
+          double f = 0, p = 0;
+#pragma unroll
+          for (int q = 0; q < s; ++q) { f += a[q] * FK[q]; p += a[q] * A[q]; }
+          sAcc[buf][tid] = f;
+          sSA[buf][tid] = p;
+        }
+        if (vthr) {
+          double v = 0;
+#pragma unroll
+          for (int q = 0; q < s; ++q) v += a[q] * V[q];
+          sCV[buf][ve] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          if (pv[m]) sP0[tid + IMU_THREADS * m] = preg[m] + p_inc(pi[m], pj[m], buf, sa) * h;
+        __syncthreads();
+        const F9s& f = sFc[cb + s];
+        if (strip) {
+          const double fd = f9_dense(f, si, sj);
+          FK[s] = fd + f9_elem(f, sAcc[buf], si, sj, true) * h;
+          A[s] = f9_elem(f, sP0, si, sj, false);
+        }
+        if (vthr) V[s] = v_block(f, c, ve);
+        buf ^= 1;
+      }
+    }
+    const double* bw = pd ? kBpd : kBrk;
+    double sb = 0;
+#pragma unroll
+    for (int q = 0; q < 7; ++q)
+      if (q < nst) sb += bw[q];
+    if (strip) {
+      double f = 0, p = 0;
+#pragma unroll
+      for (int q = 0; q < 7; ++q)
+        if (q < nst) { f += bw[q] * FK[q]; p += bw[q] * A[q]; }
+      sAcc[buf][tid] = ((si == sj) ? 1.0 : 0.0) + f * h;  // rows 0..8 of I + FK h
+      sSA[buf][tid] = p;
+    }
+    if (vthr) {
+      double v = 0;
+#pragma unroll
+      for (int q = 0; q < 7; ++q)
+        if (q < nst) v += bw[q] * V[q];
+      sCV[buf][ve] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+      if (pv[m]) {
+        double v = preg[m] + p_inc(pi[m], pj[m], buf, sb) * h;
+        if (henc < 0 && pi[m] == pj[m]) v += c.qmodel[pi[m]];  // end of a Propagate call: += Qmodel (diagonal)
+        preg[m] = v;
+        sP[tid + IMU_THREADS * m] = v;
+      }
+    if (strip) {  // Phi <- (I + FK h) Phi; rows >= 9 of both factors are identity rows
+      double v = sj >= 9 ? sAcc[buf][si * 23 + sj] : 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v += sAcc[buf][si * 23 + k] * sPhi[pb][k * 23 + sj];
+      sPhi[pb ^ 1][tid] = v;
+    }
+    pb ^= 1;
+    buf ^= 1;
+    __syncthreads();
+  }
+  // write back: motion block and strips (rows 0..8 change)
+#pragma unroll
+  for (int m = 0; m < 3; ++m)
+    if (pv[m]) Pb[(size_t)pi[m] * N + pj[m]] = preg[m];
+  const double* __restrict__ phi = sPhi[pb];
+  for (int j = 23 + tid; j < N; j += IMU_THREADS) {
+    double col[23];
+#pragma unroll
+    for (int k = 0; k < 23; ++k) col[k] = Pb[(size_t)k * N + j];
+#pragma unroll 1
+    for (int i = 0; i < 9; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 23; ++k) acc += phi[i * 23 + k] * col[k];
+      Pb[(size_t)i * N + j] = acc;
+      Pb[(size_t)j * N + i] = acc;
+    }
+  }
+}
+
+// XIVO_IMU_V1=1 routes the propagation through the first formulation (parity tests compare the two)
 int launch_imu_cov_propagate(cudaStream_t st, int N, double* P, const ImuStage* stages, const int* first, const int* nstages,
                              const ImuConst* cst, int batch) {
   ProfScope ps("imu_cov_propagate", st);
@@ -677,9 +873,12 @@ int launch_imu_cov_propagate(cudaStream_t st, int N, double* P, const ImuStage* 
   static bool attr_set = false;
   if (!attr_set) {
     XB_CUDA(cudaFuncSetAttribute(imu_cov_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    XB_CUDA(cudaFuncSetAttribute(imu_cov_propagate_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  imu_cov_propagate_kernel<<<batch, IMU_THREADS, dyn, st>>>(N, P, stages, first, nstages, cst);
+  const char* e = getenv("XIVO_IMU_V1");
+  if (e && e[0] == '1') imu_cov_propagate_kernel<<<batch, IMU_THREADS, dyn, st>>>(N, P, stages, first, nstages, cst);
+  else imu_cov_propagate_v2_kernel<<<batch, IMU_THREADS, dyn, st>>>(N, P, stages, first, nstages, cst);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
