@@ -137,7 +137,7 @@ def run_ours(args):
     # also has one driver thread (the Python thread inside xivo_batch_step), so workers + drivers = CPU budget
     budget = max(1, cpu_budget() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
     # one driver per batch needs a CPU of its own: with a small budget (e.g. a node quota shared by 8 ranks) run fewer batches
-    args.batches = max(1, min(args.batches, budget // 4))
+    args.batches = max(1, min(args.batches, budget // 2))
     os.environ.setdefault("XIVO_THREADS", str(max(1, budget - args.batches + 1 - args.cpu_headroom)))
     os.environ.setdefault("XIVO_DRIVERS", str(args.batches))
     import torch
