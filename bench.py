@@ -374,8 +374,8 @@ def main():
     ap.add_argument("--profile-e2e", action="store_true", help="attribute kernel / host-phase time on the host-frame (e2e) path instead of the device-resident one")
     ap.add_argument("--profile-level", type=int, default=1, help="1: kernels + batch-level host phases, 2: + per-sequence host scopes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=256, help="independent sequences per GPU, split over --batches lock-step batches")
-    ap.add_argument("--batches", type=int, default=4, help="independent lock-step batches per GPU, one driver thread each; their host phases share the library's worker pool")
+    ap.add_argument("--seqs", type=int, default=512, help="independent sequences per GPU, split over --batches lock-step batches")
+    ap.add_argument("--batches", type=int, default=8, help="independent lock-step batches per GPU, one driver thread each; their host phases share the library's worker pool")
     ap.add_argument("--streams", type=int, default=4, help="distinct synthetic input streams shared by the sequences")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cov-update", default="fp64", choices=["fp64", "tf32x3"], help="arithmetic of the covariance downdate (tf32x3 = tcgen05 tensor cores)")
