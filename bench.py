@@ -13,7 +13,9 @@ one frame (+ its 8 IMU samples) for every sequence on every GPU.
 Prints ONE JSON line (rank 0).  `value` = frames/s with the frames already resident in HBM;
 `e2e` = the same through the estimator-level C ABI with pinned HOST frames (H2D inside the timed
 region, pose read back every step).  `roofline` describes the kernel with the largest share of
-device time in the timed region (CUDA-event durations recorded by the library on its launch stream).
+device time (CUDA-event durations recorded by the library on its launch streams) in a third pass over
+the next frames of the same streams, in which the batches are stepped one after another so that an
+event pair measures the kernel and not the queueing behind other batches' kernels.
 """
 from __future__ import annotations
 
@@ -214,9 +216,9 @@ def run_ours(args):
             raise RuntimeError(L.xivo_last_error().decode())
         return bts[i].gsb(0)  # host read of the step's result (pose); the err/P_mm D2H happened inside the call
 
-    def step(f, device_resident):
-        if NB == 1:
-            return [step_one(0, f, device_resident)]
+    def step(f, device_resident, serial=False):
+        if NB == 1 or serial:
+            return [step_one(i, f, device_resident) for i in range(NB)]
         return list(pool.map(lambda i: step_one(i, f, device_resident), range(NB)))
 
     def barrier():
@@ -251,7 +253,10 @@ def run_ours(args):
             e0[i].record(exts[i])
         ntracked = 0
         for _ in range(K):
-            step(f, device_resident)
+            # the attribution pass steps the batches one after another: with several batches in flight a CUDA-event pair
+            # around a launch also measures the time the launch queued behind other batches' kernels, which made the
+            # per-kernel shares disagree with the ncu launch list (profiles/r01g_bench.json vs r01c_launch_shares.txt)
+            step(f, device_resident, serial=bool(profile))
             ntracked += bts[0].counters(0)["num_tracked"]
             f += 1
         for i in range(NB):
