@@ -134,6 +134,53 @@ def cpu_budget():
     return n
 
 
+def build_roofline(prof, K, peaks, seqs_per_launch, pass_ms):
+    """Pure post-processing of the library's profile report (xivo_profile_report): per-kernel CUDA-event time and the
+    algorithmic work attributed at the launch sites -> the `roofline` object of the JSON line (dominant kernel by device
+    time; `achieved` = work per launch / average launch duration) and the host phase breakdown.  Unit-tested on CPU."""
+    kern = {k: v for k, v in prof.items() if not k.startswith("_") and not k.startswith("host:")}
+    host_phases = {k[5:]: round(v["ms"] / K, 4) for k, v in prof.items() if k.startswith("host:")}
+    upd_ms = kern.get("ekf_gain", {}).get("ms", 0) + kern.get("ekf_cov", {}).get("ms", 0)
+    merged = {k: dict(v) for k, v in kern.items() if k not in ("ekf_gain", "ekf_cov", "ekf_update")}
+    if upd_ms:
+        merged["ekf_update"] = dict(calls=kern.get("ekf_gain", {}).get("calls", 0), ms=upd_ms, work=kern.get("ekf_update", {}).get("work", 0))
+    if not merged:
+        return dict(kernel=None, bound=None, achieved=None, peak=None, unit=None, frac=None, traffic=None, kernels={}), host_phases
+    tot_ms = sum(v["ms"] for v in merged.values()) or 1.0
+    dom = max(merged, key=lambda k: merged[k]["ms"])
+    d = merged[dom]
+    bound = "tensor" if dom == "ekf_update" else "hbm"
+    per_launch_s = max(d["ms"], 1e-9) * 1e-3 / max(d["calls"], 1)
+    work_per_launch = d.get("work", 0) / max(d["calls"], 1)
+    if bound == "hbm":
+        achieved, peak, unit = work_per_launch / per_launch_s / 1e9, peaks["hbm"], "GB/s"
+    else:
+        achieved, peak, unit = work_per_launch / per_launch_s / 1e12, peaks["tf"], "TFLOP/s"
+    traffic, traffic_src = None, None
+    try:  # ncu-measured DRAM bytes per launch of that kernel (profiles/), scaled to this run's sequences per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if dom in tj:
+            traffic = tj[dom] * (seqs_per_launch / tj["sequences_per_launch"])
+            traffic_src = "ncu dram__bytes_{read,write}.sum at %d sequences/launch (profiles/r01_traffic.json), scaled to %d" % (tj["sequences_per_launch"], seqs_per_launch)
+    except Exception:
+        pass
+    per_kernel = {}
+    for k_, v_ in merged.items():  # the same arithmetic for every kernel with algorithmic work attributed (SURVEY.md §8d, csrc/estimator.cu add_work sites)
+        if not v_.get("work") or not v_["ms"]:
+            continue
+        tens = k_ == "ekf_update"
+        a_ = v_["work"] / (v_["ms"] * 1e-3) / (1e12 if tens else 1e9)
+        per_kernel[k_] = dict(bound="tensor" if tens else "hbm", achieved=round(a_, 4), unit="TFLOP/s" if tens else "GB/s",
+                              frac=round(a_ / (peaks["tf"] if tens else peaks["hbm"]), 6))
+    roofline = dict(kernel=dom, bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peaks["src"],
+                    per_kernel=per_kernel,
+                    share_of_device_time=d["ms"] / tot_ms, launches=d["calls"], avg_launch_us=per_launch_s * 1e6,
+                    kernels={k: dict(ms=round(v["ms"], 4), calls=v["calls"], share=round(v["ms"] / tot_ms, 4)) for k, v in merged.items()},
+                    device_busy_frac=tot_ms / pass_ms, profiled_pass_ms_per_step=pass_ms / K,
+                    attribution="third pass, batches stepped one after another (event durations = kernels, not queueing behind other batches)")
+    return roofline, host_phases
+
+
 def run_ours(args):
     # host CPUs: the library's worker pool (workpool.h) is shared by the NB batches of this process; each batch
     # also has one driver thread (the Python thread inside xivo_batch_step), so workers + drivers = CPU budget
@@ -285,35 +332,7 @@ def run_ours(args):
     e2e = frames_total / (r_e2e["ms"] * 1e-3)
 
     peaks = measured_peaks()
-    prof = r_prof["prof"]
-    kern = {k: v for k, v in prof.items() if not k.startswith("_") and not k.startswith("host:")}
-    host_phases = {k[5:]: round(v["ms"] / K, 4) for k, v in prof.items() if k.startswith("host:")}
-    upd_ms = kern.get("ekf_gain", {}).get("ms", 0) + kern.get("ekf_cov", {}).get("ms", 0)
-    merged = {k: dict(v) for k, v in kern.items() if k not in ("ekf_gain", "ekf_cov", "ekf_update")}
-    if upd_ms:
-        merged["ekf_update"] = dict(calls=kern.get("ekf_gain", {}).get("calls", 0), ms=upd_ms, work=kern.get("ekf_update", {}).get("work", 0))
-    tot_ms = sum(v["ms"] for v in merged.values()) or 1.0
-    dom = max(merged, key=lambda k: merged[k]["ms"])
-    d = merged[dom]
-    bound = "tensor" if dom == "ekf_update" else "hbm"
-    per_launch_s = d["ms"] * 1e-3 / max(d["calls"], 1)
-    work_per_launch = d["work"] / max(d["calls"], 1)
-    if bound == "hbm":
-        achieved, peak, unit = work_per_launch / per_launch_s / 1e9, peaks["hbm"], "GB/s"
-    else:
-        achieved, peak, unit = work_per_launch / per_launch_s / 1e12, peaks["tf"], "TFLOP/s"
-    traffic, traffic_src = None, None
-    try:  # ncu-measured DRAM bytes per launch of that kernel (profiles/), scaled to this run's sequences per launch
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if dom in tj:
-            traffic = tj[dom] * (sizes[0] / tj["sequences_per_launch"])
-            traffic_src = "ncu dram__bytes_{read,write}.sum at %d sequences/launch (profiles/r01_traffic.json), scaled to %d" % (tj["sequences_per_launch"], sizes[0])
-    except Exception:
-        pass
-    roofline = dict(kernel=dom, bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peaks["src"],
-                    share_of_device_time=d["ms"] / tot_ms, launches=d["calls"], avg_launch_us=per_launch_s * 1e6,
-                    kernels={k: dict(ms=round(v["ms"], 4), calls=v["calls"], share=round(v["ms"] / tot_ms, 4)) for k, v in merged.items()},
-                    device_busy_frac=tot_ms / r_prof["ms"], profiled_pass_ms_per_step=r_prof["ms"] / K)
+    roofline, host_phases = build_roofline(r_prof["prof"], K, peaks, sizes[0], r_prof["ms"])
 
     out = None
     if rank == 0:

@@ -1,0 +1,67 @@
+"""Host-side logic of bench.py that does not need a GPU: the roofline post-processing of the library's profile report,
+the CPU budget probe and the argument defaults the driver relies on."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bench)
+
+PEAKS = dict(hbm=6574.1, tf=1404.6, src="test")
+
+
+def fake_prof():
+    return {
+        "lk_track": {"ms": 40.0, "calls": 100, "work": 100 * 38.0e6},      # 0.4 ms per launch, 38 MB each -> 95 GB/s
+        "pyrdown": {"ms": 10.0, "calls": 100, "work": 100 * 45.9e6},
+        "imu_cov_propagate": {"ms": 20.0, "calls": 100, "work": 100 * 2.0e6},
+        "ekf_gain": {"ms": 6.0, "calls": 100, "work": 0},
+        "ekf_cov": {"ms": 2.0, "calls": 100, "work": 0},
+        "ekf_update": {"ms": 0.0, "calls": 0, "work": 100 * 64 * 4.4e6},   # Joseph flops attributed to the pair
+        "cov_edit": {"ms": 1.0, "calls": 200, "work": 0},
+        "host:gating": {"ms": 12.0, "calls": 100},
+        "_h2d_bytes": 1.0e9,
+        "_d2h_bytes": 1.0e8,
+    }
+
+
+def test_roofline_picks_dominant_kernel_and_computes_achieved():
+    r, host = bench.build_roofline(fake_prof(), K=25, peaks=PEAKS, seqs_per_launch=64, pass_ms=60.0)
+    assert r["kernel"] == "lk_track" and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["achieved"] - 38.0e6 / 0.4e-3 / 1e9) < 1e-9 and abs(r["frac"] - r["achieved"] / PEAKS["hbm"]) < 1e-12
+    assert r["launches"] == 100 and abs(r["avg_launch_us"] - 400.0) < 1e-9
+    assert abs(sum(v["share"] for v in r["kernels"].values()) - 1.0) < 1e-3
+    assert "ekf_gain" not in r["kernels"] and abs(r["kernels"]["ekf_update"]["ms"] - 8.0) < 1e-9  # gain + cov merged
+    assert abs(r["device_busy_frac"] - 79.0 / 60.0) < 1e-9 and abs(r["profiled_pass_ms_per_step"] - 2.4) < 1e-12
+    assert host == {"gating": 0.48}
+    pk = r["per_kernel"]
+    assert set(pk) == {"lk_track", "pyrdown", "imu_cov_propagate", "ekf_update"}
+    assert pk["ekf_update"]["bound"] == "tensor" and abs(pk["ekf_update"]["achieved"] - 100 * 64 * 4.4e6 / 8e-3 / 1e12) < 1e-3
+    assert r["traffic"] is None or r["traffic"] > 0  # profiles/r01_traffic.json scaled to 64 sequences per launch
+    json.dumps(r)  # serialisable
+
+
+def test_roofline_tensor_bound_when_update_dominates_and_empty_report():
+    p = fake_prof()
+    p["ekf_gain"]["ms"] = 500.0
+    r, _ = bench.build_roofline(p, 25, PEAKS, 64, 600.0)
+    assert r["kernel"] == "ekf_update" and r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] == PEAKS["tf"]
+    r, host = bench.build_roofline({"_h2d_bytes": 0, "_d2h_bytes": 0}, 25, PEAKS, 64, 1.0)
+    assert r["kernel"] is None and host == {}
+
+
+def test_cpu_budget_is_positive_and_bounded_by_affinity():
+    n = bench.cpu_budget()
+    assert 1 <= n <= len(os.sched_getaffinity(0))
+
+
+def test_defaults_match_the_contract():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0
+    for flag in ("--gpus", "--steps", "--warmup", "--impl", "--seqs", "--batches", "--cov-update"):
+        assert flag in r.stdout
+    assert bench.measured_peaks()["hbm"] > 1000
