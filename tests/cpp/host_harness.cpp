@@ -1,0 +1,99 @@
+// CPU test harness for the host state machine of the estimator (xivo_b200/csrc/estimator.h +
+// estimator_host.cpp.inc): compiled with g++ (no nvcc, no GPU) into a small shared object that
+// tests/test_host_logic.py drives through ctypes.  Test infrastructure only — nothing here is linked into
+// libxivo_b200.so; the device phases of the pipeline are not emulated, only the host-side pieces that need
+// no kernel output: configuration, message heap, clocks, gravity initialisation, the nominal-state
+// Runge-Kutta chain with its per-stage records (what imu_cov_propagate consumes) and the tracker mask.
+#include <chrono>
+#include <cstring>
+#include <string>
+
+#include "../../xivo_b200/csrc/estimator.h"
+
+namespace xb {
+struct HostScope {  // the library's version also feeds the profiler; timing is irrelevant here
+  explicit HostScope(const char*) {}
+};
+}  // namespace xb
+
+#include "../../xivo_b200/csrc/estimator_host.cpp.inc"
+
+namespace {
+std::string g_err;
+}
+
+extern "C" {
+const char* hh_error() { return g_err.c_str(); }
+
+void* hh_create(const char* cfg_json, int G, int F, int tracker_only) {
+  try {
+    return new xb::Estimator(xb::Json::parse(cfg_json), xb::EkfLayout{G, F}, tracker_only != 0);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void hh_destroy(void* h) { delete static_cast<xb::Estimator*>(h); }
+
+void hh_inertial(void* h, unsigned long long ts, const double* gyro, const double* accel) { static_cast<xb::Estimator*>(h)->inertial_internal(ts, gyro, accel); }
+int hh_visual_begin(void* h, unsigned long long ts, int type) { return static_cast<xb::Estimator*>(h)->visual_begin(ts, type) ? 1 : 0; }
+int hh_sticky_error(void* h) { return static_cast<xb::Estimator*>(h)->error; }
+
+// Rsb(9) Tsb(3) Vsb(3) bg(3) ba(3) Rbc(9) Tbc(3) Rsg(9) = 42 doubles
+void hh_motion(void* h, double* out) {
+  const xb::MotionX& X = static_cast<xb::Estimator*>(h)->X;
+  memcpy(out, X.Rsb.m, 72); memcpy(out + 9, X.Tsb.v, 24); memcpy(out + 12, X.Vsb.v, 24); memcpy(out + 15, X.bg.v, 24);
+  memcpy(out + 18, X.ba.v, 24); memcpy(out + 21, X.Rbc.m, 72); memcpy(out + 30, X.Tbc.v, 24); memcpy(out + 33, X.Rsg.m, 72);
+}
+// flags: gravity_initialized, vision_initialized, imu_counter, vision_counter
+void hh_flags(void* h, int* out) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  out[0] = e->gravity_initialized; out[1] = e->vision_initialized; out[2] = e->imu_counter; out[3] = e->vision_counter;
+}
+unsigned long long hh_curr_time(void* h) { return static_cast<xb::Estimator*>(h)->curr_time; }
+// pending Runge-Kutta stage records (16 doubles each: R(9), gyro-bg(3), accel-ba(3), h); returns the count, clears the queue
+int hh_take_stages(void* h, double* out, int max_records) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  static_assert(sizeof(xb::ImuStage) == 16 * sizeof(double), "ImuStage layout");
+  const int n = (int)e->stages.size();
+  if (n <= max_records && n) memcpy(out, e->stages.data(), sizeof(xb::ImuStage) * (size_t)n);
+  e->stages.clear();
+  return n;
+}
+void hh_initial_pmm(void* h, double* out529) { memcpy(out529, static_cast<xb::Estimator*>(h)->Pmm, 529 * 8); }
+void hh_camera(void* h, double* out11) {
+  const xb::CameraParams& c = static_cast<xb::Estimator*>(h)->cam;
+  const double v[11] = {(double)c.model, (double)c.rows, (double)c.cols, c.fx, c.fy, c.cx, c.cy, c.k0, c.k1, c.k2, c.k3};
+  memcpy(out11, v, sizeof(v));
+}
+
+// message heap: push (ts, type) and pop in execution order (MaintainBuffer, estimator.cpp:923-941)
+void hh_push(void* h, unsigned long long ts, int type) {
+  xb::Msg m;
+  m.ts = ts; m.type = type;
+  static_cast<xb::Estimator*>(h)->push(std::move(m));
+}
+int hh_pop(void* h, unsigned long long* ts, int* type) {
+  xb::Msg m;
+  if (!static_cast<xb::Estimator*>(h)->pop_ready(&m)) return 0;
+  *ts = m.ts; *type = m.type;
+  return 1;
+}
+
+// tracker mask (tracker.cpp:471-488, :760-774)
+void hh_mask_init(void* h, int rows, int cols) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  e->rows = rows; e->cols = cols;
+  e->mask_stride = (cols + 63) / 64;
+  e->mask.assign((size_t)rows * e->mask_stride, 0);
+  e->reset_mask();
+}
+void hh_mask_reset(void* h) { static_cast<xb::Estimator*>(h)->reset_mask(); }
+void hh_mask_out(void* h, double x, double y) { static_cast<xb::Estimator*>(h)->mask_out(x, y); }
+int hh_mask_valid(void* h, double x, double y) { return static_cast<xb::Estimator*>(h)->mask_valid(x, y) ? 1 : 0; }
+void hh_mask_dump(void* h, unsigned char* out) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  for (int y = 0; y < e->rows; ++y)
+    for (int x = 0; x < e->cols; ++x) out[(size_t)y * e->cols + x] = e->mask_bit(x, y) ? 255 : 0;
+}
+}

@@ -1,0 +1,256 @@
+"""Host logic of the estimator on CPU (no GPU, no nvcc): tests/cpp/host_harness.cpp compiles the product's host
+state machine (xivo_b200/csrc/estimator.h + estimator_host.cpp.inc) with g++ and exposes the pieces that need no
+kernel output — configuration, message heap, clocks, gravity initialisation, the nominal-state Runge-Kutta chain with
+the per-stage records the device covariance kernel consumes, and the tracker mask — which are checked here against
+the numpy oracle (oracle/estimator_oracle.py, oracle/ekf_oracle.py, oracle/tracker_oracle.py)."""
+import ctypes as C
+import heapq
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ekf_oracle as E
+from oracle import estimator_oracle as EO
+from oracle import tracker_oracle as T
+from xivo_b200 import sim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = os.path.join(ROOT, "xivo_b200", "cfg")
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")),
+                                reason="needs g++ and the CUDA headers (host-only compile)")
+
+
+@pytest.fixture(scope="module")
+def hh(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hh") / "libhost_harness.so")
+    cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-I", CUDA_INC, "-shared", "-fPIC", os.path.join(ROOT, "tests", "cpp", "host_harness.cpp"), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(so)
+    lib.hh_create.restype = C.c_void_p
+    lib.hh_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.hh_error.restype = C.c_char_p
+    lib.hh_curr_time.restype = C.c_ulonglong
+    for name in ("hh_destroy", "hh_motion", "hh_flags", "hh_initial_pmm", "hh_camera", "hh_mask_reset", "hh_mask_dump"):
+        getattr(lib, name).argtypes = [C.c_void_p] + ([C.c_void_p] if name not in ("hh_destroy", "hh_mask_reset") else [])
+    lib.hh_curr_time.argtypes = [C.c_void_p]
+    lib.hh_sticky_error.argtypes = [C.c_void_p]
+    lib.hh_inertial.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_void_p]
+    lib.hh_visual_begin.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int]
+    lib.hh_take_stages.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.hh_push.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int]
+    lib.hh_pop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hh_mask_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.hh_mask_out.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    lib.hh_mask_valid.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    return lib
+
+
+def create(lib, cfg, G=4, F=14, tracker_only=False):
+    text = cfg if isinstance(cfg, str) else json.dumps(cfg)
+    h = lib.hh_create(text.encode(), G, F, int(tracker_only))
+    return h
+
+
+def motion(lib, h):
+    a = np.zeros(42)
+    lib.hh_motion(h, a.ctypes.data)
+    return dict(Rsb=a[:9].reshape(3, 3), Tsb=a[9:12], Vsb=a[12:15], bg=a[15:18], ba=a[18:21], Rbc=a[21:30].reshape(3, 3), Tbc=a[30:33], Rsg=a[33:42].reshape(3, 3))
+
+
+def take_stages(lib, h):
+    buf = np.zeros((1024, 16))
+    n = lib.hh_take_stages(h, buf.ctypes.data, 1024)
+    return buf[:n].copy()
+
+
+# ------------------------------------------------------------------ configuration
+def test_config_files_parse_with_comments_and_camera_models(hh):
+    for name, model, rows in [("pcw_sim.json", 0, 480), ("vio_640x480.json", 0, 480), ("tumvi_512_equidistant.json", 3, 512), ("stress_1280x1024.json", 0, 1024)]:
+        text = open(os.path.join(CFG, name)).read()
+        assert "//" in text  # the files carry comments, like the reference's cfg/*.json
+        h = create(hh, text)
+        assert h, hh.hh_error()
+        cam = np.zeros(11)
+        hh.hh_camera(h, cam.ctypes.data)
+        ref = sim.load_cfg(os.path.join(CFG, name))["camera_cfg"]
+        assert int(cam[0]) == model and int(cam[1]) == rows and cam[3] == ref["fx"] and cam[6] == ref["cy"]
+        if model == 3:
+            assert np.array_equal(cam[7:11], ref["k0123"])
+        hh.hh_destroy(h)
+
+
+@pytest.mark.parametrize("key,value,needle", [("use_OOS", True, "MSCKF"), ("use_1pt_RANSAC", True, "1pt_RANSAC"), ("use_depth_opt", True, "depth_opt"),
+                                               ("integration_method", "Euler", "integration method"), ("covariance_update", "fp16", "covariance_update")])
+def test_unsupported_options_fail_loudly_at_creation(hh, key, value, needle):
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    cfg[key] = value
+    assert not create(hh, cfg)
+    assert needle.lower() in hh.hh_error().decode().lower()
+
+
+def test_unsupported_camera_model_is_an_error(hh):
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    cfg["camera_cfg"]["model"] = "radtan"
+    assert not create(hh, cfg) and b"radtan" in hh.hh_error()
+
+
+def test_initial_motion_covariance_matches_oracle(hh):
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    h = create(hh, cfg)
+    P = np.zeros((23, 23))
+    hh.hh_initial_pmm(h, P.ctypes.data)
+    ref = EO.EstimatorOracle(cfg, G=4, F=14)
+    assert np.array_equal(P, ref.P[:23, :23])  # estimator.cpp:258-302
+    m = motion(hh, h)
+    assert np.allclose(m["Rbc"], ref.X.Rbc, atol=1e-15) and np.array_equal(m["Tbc"], ref.X.Tbc)
+    hh.hh_destroy(h)
+
+
+# ------------------------------------------------------------------ message heap
+def test_message_heap_order_matches_oracle_rule(hh):
+    """MaintainBuffer (estimator.cpp:923-941): nothing executes until more than MESSAGE_BUFFER_SIZE (10) messages are
+    held; then the oldest timestamp pops, ties in arrival order (the documented deviation shared with the oracle)."""
+    h = create(hh, sim.load_cfg(os.path.join(CFG, "pcw_sim.json")))
+    rng = np.random.default_rng(0)
+    ts = rng.integers(0, 40, 200) * 5_000_000  # many ties
+    types = rng.integers(0, 2, 200) * 3
+    model, popped_ref, popped = [], [], []
+    init = False
+    for k in range(200):
+        hh.hh_push(h, int(ts[k]), int(types[k]))
+        model.append((int(ts[k]), k, int(types[k])))
+        if not init and len(model) >= 10:
+            heapq.heapify(model)
+            init = True
+        elif init:
+            heapq.heapify(model)
+        t, ty = C.c_ulonglong(), C.c_int()
+        got = hh.hh_pop(h, C.byref(t), C.byref(ty))
+        if init and len(model) > 10:
+            assert got == 1
+            a = heapq.heappop(model)
+            popped_ref.append((a[0], a[2]))
+            popped.append((t.value, ty.value))
+        else:
+            assert got == 0
+    assert popped == popped_ref and len(popped) == 190  # the last 10 messages are never executed, as in the reference
+    hh.hh_destroy(h)
+
+
+# ------------------------------------------------------------------ inertial path
+@pytest.mark.parametrize("method", ["PrinceDormand", "RK4"])
+def test_nominal_state_chain_and_stage_records_match_oracle(hh, method, monkeypatch):
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    cfg["integration_method"] = method
+    msgs, _ = sim.pcw_stream(cfg, duration=0.5, seed=3)
+    h = create(hh, cfg)
+    ref = EO.EstimatorOracle(cfg, G=4, F=14)
+    rec = []
+    real = E.integrate
+    monkeypatch.setattr(EO.E, "integrate", lambda *a, **k: real(*a, rec=rec, **k))
+    nst = 7 if method == "PrinceDormand" else 4
+    n_imu = n_vis = 0
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            g, a = np.ascontiguousarray(p[0]), np.ascontiguousarray(p[1])
+            hh.hh_inertial(h, ts, g.ctypes.data, a.ctypes.data)
+            ref.inertial_internal(ts, g, a)
+            n_imu += 1
+        else:  # the clock / propagate part of a visual message (estimator.cpp:1106-1122); the update itself needs the device
+            assert hh.hh_visual_begin(h, ts, 3) == (1 if ref.gravity_initialized else 0)
+            if not ref.vision_initialized:
+                if ref.gravity_initialized:
+                    ref.curr_time, ref.vision_initialized = ts, True
+            else:
+                ref.last_time, ref.curr_time = ref.curr_time, ts
+            if ref.vision_initialized:
+                ref.propagate(True)
+            n_vis += 1
+        got = take_stages(hh, h)
+        assert len(got) == len(rec) and len(got) % nst == 0
+        if len(rec):
+            want = np.array(rec)
+            assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+            assert np.array_equal(np.sign(got[:, 15]), np.sign(want[:, 15]))  # the sign of h marks the end of a Propagate call
+        rec.clear()
+        m = motion(hh, h)
+        assert np.abs(m["Rsb"] - ref.X.Rsb).max() <= 1e-12 and np.abs(m["Tsb"] - ref.X.Tsb).max() <= 1e-12
+        assert np.abs(m["Vsb"] - ref.X.Vsb).max() <= 1e-12 and np.abs(m["Rsg"] - ref.X.Rsg).max() <= 1e-15
+        assert hh.hh_curr_time(h) == ref.curr_time
+    assert n_imu == 100 and n_vis >= 12 and np.linalg.norm(ref.X.Tsb) > 0.05  # it moved
+    fl = (C.c_int * 4)()
+    hh.hh_flags(h, fl)
+    assert list(fl) == [1, 1, ref.imu_counter, n_vis]
+    hh.hh_destroy(h)
+
+
+def test_out_of_order_messages_are_dropped_and_wrong_mode_is_sticky(hh):
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    h = create(hh, cfg)
+    z, a = np.zeros(3), np.array([0.0, 0.0, 9.8])
+    hh.hh_inertial(h, 0, z.ctypes.data, a.ctypes.data)
+    assert hh.hh_visual_begin(h, 40_000_000, 3) == 1
+    hh.hh_inertial(h, 45_000_000, z.ctypes.data, a.ctypes.data)
+    n0 = len(take_stages(hh, h))
+    assert n0 > 0
+    hh.hh_inertial(h, 20_000_000, z.ctypes.data, a.ctypes.data)  # older than the clock (ms granularity): dropped, estimator.cpp:706-717
+    assert len(take_stages(hh, h)) == 0 and hh.hh_curr_time(h) == 45_000_000
+    assert hh.hh_visual_begin(h, 30_000_000, 3) == 0 and hh.hh_sticky_error(h) == 0
+    assert hh.hh_visual_begin(h, 80_000_000, 1) == 0 and hh.hh_sticky_error(h) == -3  # VisualMeas in simulation mode (estimator.cpp:1112-1115)
+    hh.hh_destroy(h)
+
+
+def test_gravity_initialisation_from_stationary_samples(hh):
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))  # simulation: false, gravity_init_counter: 20
+    h = create(hh, cfg)
+    ref = EO.EstimatorOracle(cfg, G=4, F=14)
+    rng = np.random.default_rng(4)
+    tilt = E.so3_exp(np.array([0.05, -0.08, 0.3]))
+    for k in range(25):
+        g = rng.normal(0, 1e-3, 3)
+        a = tilt @ np.array([0.0, 0.0, 9.8]) + rng.normal(0, 1e-2, 3)
+        hh.hh_inertial(h, k * 5_000_000, g.ctypes.data, a.ctypes.data)
+        ref.inertial_internal(k * 5_000_000, g, a)
+        fl = (C.c_int * 4)()
+        hh.hh_flags(h, fl)
+        assert bool(fl[0]) == ref.gravity_initialized == (k >= 19)
+    m = motion(hh, h)
+    assert np.abs(m["Rsg"] - ref.X.Rsg).max() <= 1e-14 and not np.allclose(m["Rsg"], np.eye(3), atol=1e-3)
+    w = E.so3_log(m["Rsg"]) if hasattr(E, "so3_log") else None
+    assert w is None or abs(w[2]) < 1e-12  # the yaw component of Wsg is dropped (estimator.cpp:461)
+    hh.hh_destroy(h)
+
+
+# ------------------------------------------------------------------ tracker mask
+@pytest.mark.parametrize("rows,cols", [(480, 640), (67, 130), (64, 64)])
+def test_tracker_mask_matches_oracle(hh, rows, cols):
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    h = create(hh, cfg)
+    tcfg = cfg["tracker_cfg"]
+    ref = T.Mask(rows, cols, tcfg["margin"], tcfg["mask_size"])
+    ref.reset()
+    hh.hh_mask_init(h, rows, cols)
+    out = np.zeros((rows, cols), np.uint8)
+    hh.hh_mask_dump(h, out.ctypes.data)
+    assert np.array_equal(out, ref.m)
+    rng = np.random.default_rng(rows)
+    for k in range(max(8, rows * cols // 1500)):
+        x, y = rng.uniform(-10, cols + 10), rng.uniform(-10, rows + 10)
+        if k % 7 == 0:
+            x, y = np.floor(x) + 0.5, np.floor(y) + 0.5  # cvRound ties (half to even)
+        assert bool(hh.hh_mask_valid(h, x, y)) == ref.valid(x, y)
+        hh.hh_mask_out(h, x, y)
+        ref.mask_out(x, y)
+    hh.hh_mask_dump(h, out.ctypes.data)
+    assert np.array_equal(out, ref.m) and 0 < (out > 0).sum() < rows * cols
+    hh.hh_mask_reset(h)
+    ref.reset()
+    hh.hh_mask_dump(h, out.ctypes.data)
+    assert np.array_equal(out, ref.m)
+    hh.hh_destroy(h)
