@@ -23,6 +23,7 @@ import math
 import numpy as np
 
 from . import ekf_oracle as E
+from . import stdorder as SO
 from . import tracker_oracle as T
 
 CREATED, TRACKED, DROPPED = 0, 1, 2
@@ -115,7 +116,13 @@ def rot_of(v):
 
 
 class EstimatorOracle:
-    def __init__(self, cfg: dict, G=15, F=30, tracker_only=False):
+    def __init__(self, cfg: dict, G=15, F=30, tracker_only=False, std_order=True):
+        # std_order: reproduce the reference's libstdc++-defined orders (oracle/stdorder.py); False = ascending ids + stable sorts,
+        # the deterministic stand-in used before the reference itself could be run (kept to measure what the orders are worth)
+        self.std_order = std_order
+        self.um_features = SO.StdUnorderedIntMap() if std_order else None
+        self.um_groups = SO.StdUnorderedIntMap() if std_order else None
+        self.std_heap = None
         self.lay = E.Layout(G, F)
         N = self.lay.N
         self.tracker_only = tracker_only
@@ -230,9 +237,16 @@ class EstimatorOracle:
 
     # ---------------------------------------------------------------- message heap (estimator.cpp:923-941)
     def _push(self, m):
-        # std::push_heap / pop_heap with cmp(ts): execution order among equal timestamps follows the
-        # libstdc++ heap algorithms in the reference; ties are broken by arrival order here AND in the
-        # product's test streams (IMU pushed before vision on equal ts, as pyxivo_pcw.py:111 orders them).
+        # MaintainBuffer (estimator.cpp:923-941).  The reference's comparator looks at the timestamp only, so the execution order
+        # among equal timestamps is a property of libstdc++'s heap algorithms: std_order reproduces it through oracle/stdumap.cpp;
+        # without it ties are broken by arrival order (IMU pushed before vision on equal ts, as pyxivo_pcw.py:111 orders them).
+        if self.std_order:
+            if self.std_heap is None:
+                self.std_heap = SO.StdMessageHeap(self.msg_buf_size)
+            due = self.std_heap.push(m[0], m)
+            if due is not None:
+                self._execute(due)
+            return
         item = (m[0], self.seq, m)
         self.seq += 1
         self.buf.append(item)
@@ -241,7 +255,6 @@ class EstimatorOracle:
                 heapq.heapify(self.buf)
                 self.buf_init = True
         else:
-            # keep a valid heap
             heapq.heapify(self.buf)
         if self.buf_init and len(self.buf) > self.msg_buf_size:
             _, _, msg = heapq.heappop(self.buf)
@@ -303,15 +316,21 @@ class EstimatorOracle:
 
     # ---------------------------------------------------------------- graph
     def g_add_feature(self, f):
+        if self.std_order:
+            self.um_features.insert(f.id)
         self.features[f.id] = f
         self.feature_adj[f.id] = {}
 
     def g_add_group(self, g):
+        if self.std_order:
+            self.um_groups.insert(g.id)
         self.groups[g.id] = g
         self.group_adj[g.id] = set()
         self.gauge_features[g.id] = set()
 
     def g_remove_feature(self, f):
+        if self.std_order:
+            self.um_features.erase(f.id)
         del self.features[f.id]
         for gid in self.feature_adj[f.id]:
             self.group_adj[gid].discard(f.id)
@@ -320,6 +339,8 @@ class EstimatorOracle:
             self.gauge_features.setdefault(f.ref.id, set()).discard(f.id)
 
     def g_remove_group(self, g):
+        if self.std_order:
+            self.um_groups.erase(g.id)
         del self.groups[g.id]
         for fid in self.group_adj[g.id]:
             self.feature_adj[fid].pop(g.id, None)
@@ -335,6 +356,23 @@ class EstimatorOracle:
 
     def grps(self, pred=lambda g: True):
         return [self.groups[k] for k in sorted(self.groups) if pred(self.groups[k])]
+
+    def feats_std(self, pred=lambda f: True):
+        """GraphBase::GetFeaturesIf in the reference's container order (graphbase.cpp:124-133)."""
+        if not self.std_order:
+            return self.feats(pred)
+        return [self.features[k] for k in self.um_features.keys() if pred(self.features[k])]
+
+    def grps_std(self, pred=lambda g: True):
+        if not self.std_order:
+            return self.grps(pred)
+        return [self.groups[k] for k in self.um_groups.keys() if pred(self.groups[k])]
+
+    def sort_candidates(self, feats):
+        """std::sort(..., Criteria::CandidateComparison) (options.cpp:35-60) on `feats` in their current order."""
+        if self.std_order:
+            return SO.std_sort_candidates(feats)
+        return sorted(feats, key=self.cand_key)
 
     # ---------------------------------------------------------------- features
     def create_feature(self, x, y):
@@ -639,17 +677,20 @@ class EstimatorOracle:
         for f in self.feats(lambda f: f.tstatus == TRACKED):
             self.g_link(f, g)
             self.tracks.append(f)
-        # AdaptInitialDepth (manager.cpp:255-278)
-        depth = [f.z() for f in self.feats(lambda f: f.instate() or (f.status == F_READY and f.lifetime > self.adapt_life))]
-        if depth:
-            med = depth[len(depth) >> 1]
-            if not (med < self.min_z or med > self.max_z):
-                self.init_z = (1 - self.adapt_w) * self.init_z + self.adapt_w * med
+        self.adapt_initial_depth()
         # EnforceMaxGroupLifetime (manager.cpp:282-303)
         for gg in self.grps():
             if gg.lifetime > self.max_group_lifetime and not any(self.features[fid].ref is gg for fid in self.group_adj[gg.id]):
                 self.g_remove_group(gg)
                 self.gpool.deactivate(gg)
+
+    def adapt_initial_depth(self):
+        """AdaptInitialDepth (manager.cpp:255-278): the "median" is the middle element of the UNSORTED depth list, in graph order."""
+        depth = [f.z() for f in self.feats_std(lambda f: f.instate() or (f.status == F_READY and f.lifetime > self.adapt_life))]
+        if depth:
+            med = depth[len(depth) >> 1]
+            if not (med < self.min_z or med > self.max_z):
+                self.init_z = (1 - self.adapt_w) * self.init_z + self.adapt_w * med
 
     def absorb(self, err, inst_groups, in_update):
         X = self.X
@@ -689,8 +730,8 @@ class EstimatorOracle:
 
     def add_within_groups(self, inst):
         strict = not (self.vision_counter < self.strict_steps)
-        cands = sorted(self.feats(lambda f: self.candidate(f, strict) and f.ref.instate()), key=lambda f: f.slot)
-        cands.sort(key=self.cand_key)
+        cands = sorted(self.feats(lambda f: self.candidate(f, strict) and f.ref.instate()), key=lambda f: f.slot)  # MakePtrVectorUnique
+        cands = self.sort_candidates(cands)
         for f in cands:
             if len(inst) >= self.lay.F:
                 break
@@ -701,7 +742,7 @@ class EstimatorOracle:
         free = self.gsel.count(False)
         strict = not (self.vision_counter < self.strict_steps)
         cands = sorted(self.feats(lambda f: self.candidate(f, strict)), key=lambda f: f.slot)
-        cands.sort(key=self.cand_key)
+        cands = self.sort_candidates(cands)
         for f in cands:
             if len(inst) >= self.lay.F:
                 break
@@ -717,11 +758,10 @@ class EstimatorOracle:
     def add_group_of_features(self, inst, free_g):
         to_add = self.lay.F - len(inst)
         n_owned = lambda g: sum(1 for f in self.features.values() if f.ref is g and f.status == F_READY)
-        cands = self.grps(lambda g: g.status == G_CREATED and n_owned(g) >= self.n_gauge)
-        cands.sort(key=lambda g: -n_owned(g))
+        cands = self.grps_std(lambda g: g.status == G_CREATED and n_owned(g) >= self.n_gauge)  # GetInstateGroupCandidates
+        cands = SO.std_sort_desc(cands, [n_owned(g) for g in cands]) if self.std_order else sorted(cands, key=lambda g: -n_owned(g))
         for g in cands:
-            feats = self.feats(lambda f: f.ref is g and f.status == F_READY)
-            feats.sort(key=self.cand_key)
+            feats = self.sort_candidates(self.feats_std(lambda f: f.ref is g and f.status == F_READY))  # GetFeatureCandidatesOwnedBy + std::sort
             for f in feats:
                 self.add_feature_to_state(f)
                 inst.append(f)
@@ -780,7 +820,7 @@ class EstimatorOracle:
                 continue
             gf = self.gauge_features[g.id]
             num_to_find = self.n_gauge - len(gf)
-            cands = self.feats(lambda f: f.status == F_INSTATE and f.ref is g)
+            cands = self.feats_std(lambda f: f.status == F_INSTATE and f.ref is g)  # GetGaugeFeatureCandidates (graph.cpp:107-112)
             backup_c = list(cands)
 
             def fill(C):

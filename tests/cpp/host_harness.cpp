@@ -80,6 +80,74 @@ int hh_pop(void* h, unsigned long long* ts, int* type) {
   return 1;
 }
 
+// ---- the visual path with the device phases supplied by the caller (tests/test_host_twin.py feeds the oracle's values) ----
+void hh_init_with_sim_depths(void* h) { static_cast<xb::Estimator*>(h)->sim_initialize_depths = true; }
+// Batch::process_visual up to the sub-filter launch (estimator.cu): returns -1 when the message does not proceed, else the
+// number of features queued for Feature::SubfilterUpdate
+int hh_pcw_begin(void* h, unsigned long long ts, int n, const int* ids, const double* xp_depth) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  if (!e->visual_begin(ts, 3) || e->error) return -1;
+  e->predict_features();
+  std::vector<int> vi(ids, ids + n);
+  std::vector<double> vx(xp_depth, xp_depth + 3 * (size_t)n);
+  for (int k = 0; k < n; ++k) e->ids_to_depths.insert({vi[k], vx[3 * k + 2]});
+  e->tracker_update_pointcloud(vi, vx);
+  e->stages.clear();  // the covariance side of Propagate is the device's
+  e->update_step_pre();
+  return (int)e->subfilter_list.size();
+}
+void hh_subfilter_ids(void* h, int* out) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  for (size_t i = 0; i < e->subfilter_list.size(); ++i) out[i] = e->subfilter_list[i]->id;
+}
+// out13: n x {x(3), P(9), outlier_counter}; returns the number of in-state features (the Jacobian / gate batch)
+int hh_after_subfilter(void* h, const double* out13) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  static_assert(sizeof(xb::SubfilterOut) == 13 * sizeof(double), "SubfilterOut layout");
+  e->update_step_after_subfilter(reinterpret_cast<const xb::SubfilterOut*>(out13));
+  e->edits.clear();  // applied to P by cov_edit_kernel in the product
+  return (int)e->instate_features.size();
+}
+int hh_after_gate(void* h, const double* mh) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  e->update_step_after_gate(mh);
+  e->edits.clear();
+  return (int)e->in_update.size();
+}
+void hh_after_update(void* h, const double* err, const double* Pmm, const double* diag, int had_update) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  e->update_step_after_update(err, Pmm, diag, had_update != 0);
+  e->edits.clear();
+}
+// which: 0 = instate_features, 1 = in_update, 2 = tracks.  Per feature: id, sind, ref group sind, FeatureStatus, TrackStatus
+int hh_features(void* h, int which, int* out5, int max_n) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  const std::vector<xb::Feature*>& v = which == 0 ? e->instate_features : which == 1 ? e->in_update : e->tracks;
+  int n = 0;
+  for (xb::Feature* f : v) {
+    if (n < max_n) {
+      int* o = out5 + 5 * n;
+      o[0] = f->id; o[1] = f->sind; o[2] = f->ref ? f->ref->sind : -2; o[3] = (int)f->status; o[4] = (int)f->tstatus;
+    }
+    ++n;
+  }
+  return n;
+}
+// in-state groups: id, sind, GroupStatus; returns count; gauge group id in *gauge
+int hh_groups(void* h, int* out3, int max_n, int* gauge) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  *gauge = e->gauge_group;
+  int n = 0;
+  for (auto& kv : e->graph.groups) {
+    xb::Group* g = kv.second;
+    if (!g->instate()) continue;
+    if (n < max_n) { out3[3 * n] = g->id; out3[3 * n + 1] = g->sind; out3[3 * n + 2] = (int)g->status; }
+    ++n;
+  }
+  return n;
+}
+const char* hh_error_msg(void* h) { return static_cast<xb::Estimator*>(h)->error_msg.c_str(); }
+
 // tracker mask (tracker.cpp:471-488, :760-774)
 void hh_mask_init(void* h, int rows, int cols) {
   auto* e = static_cast<xb::Estimator*>(h);

@@ -113,34 +113,40 @@ def test_initial_motion_covariance_matches_oracle(hh):
 
 
 # ------------------------------------------------------------------ message heap
-def test_message_heap_order_matches_oracle_rule(hh):
-    """MaintainBuffer (estimator.cpp:923-941): nothing executes until more than MESSAGE_BUFFER_SIZE (10) messages are
-    held; then the oldest timestamp pops, ties in arrival order (the documented deviation shared with the oracle)."""
+def test_message_heap_order_matches_the_reference_rule(hh):
+    """MaintainBuffer (estimator.cpp:923-941): nothing executes until more than MESSAGE_BUFFER_SIZE (10) messages are held;
+    then the front of a std heap ordered by timestamp ONLY pops, so ties resolve the way libstdc++'s heap algorithms do.
+    The product's host code and the oracle's helper (oracle/stdumap.cpp) must replay exactly the same sequence."""
+    from oracle import stdorder as SO
+
     h = create(hh, sim.load_cfg(os.path.join(CFG, "pcw_sim.json")))
     rng = np.random.default_rng(0)
-    ts = rng.integers(0, 40, 200) * 5_000_000  # many ties
-    types = rng.integers(0, 2, 200) * 3
-    model, popped_ref, popped = [], [], []
-    init = False
-    for k in range(200):
+    ts = rng.integers(0, 40, 400) * 5_000_000  # many ties
+    types = rng.integers(0, 2, 400) * 3
+    ref = SO.StdMessageHeap(10)
+    popped_ref, popped = [], []
+    for k in range(400):
         hh.hh_push(h, int(ts[k]), int(types[k]))
-        model.append((int(ts[k]), k, int(types[k])))
-        if not init and len(model) >= 10:
-            heapq.heapify(model)
-            init = True
-        elif init:
-            heapq.heapify(model)
+        due = ref.push(int(ts[k]), (int(ts[k]), int(types[k])))
         t, ty = C.c_ulonglong(), C.c_int()
         got = hh.hh_pop(h, C.byref(t), C.byref(ty))
-        if init and len(model) > 10:
-            assert got == 1
-            a = heapq.heappop(model)
-            popped_ref.append((a[0], a[2]))
+        assert got == (1 if due is not None else 0) == (1 if k >= 10 else 0)
+        if got:
             popped.append((t.value, ty.value))
-        else:
-            assert got == 0
-    assert popped == popped_ref and len(popped) == 190  # the last 10 messages are never executed, as in the reference
+            popped_ref.append(due)
+    assert popped == popped_ref and len(popped) == 390  # the last 10 messages are never executed, as in the reference
+    # timestamps come out non-decreasing once the stream itself is (almost) ordered
+    ordered = sorted(int(x) for x in ts)
+    h2 = create(hh, sim.load_cfg(os.path.join(CFG, "pcw_sim.json")))
+    out = []
+    for x in ordered:
+        hh.hh_push(h2, x, 0)
+        t, ty = C.c_ulonglong(), C.c_int()
+        if hh.hh_pop(h2, C.byref(t), C.byref(ty)):
+            out.append(t.value)
+    assert out == ordered[:390]
     hh.hh_destroy(h)
+    hh.hh_destroy(h2)
 
 
 # ------------------------------------------------------------------ inertial path

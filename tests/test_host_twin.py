@@ -1,0 +1,181 @@
+"""The product's host state machine (C++, compiled by g++ into tests/cpp/host_harness.cpp) run through WHOLE point-cloud
+sequences on the CPU, with every device phase (depth sub-filter, Mahalanobis distances, EKF update) replaced by the values the numpy
+oracle computed for the same frame.  Each frame the host's decisions — track list, feature/group slots, in-state and gauge sets, the
+features that enter the update, the absorbed pose — must equal the oracle's, and the oracle itself is pinned on the reference's own
+estimator (tests/test_reference_pin.py).  This covers the selection / gating / management logic incl. the libstdc++-defined orders
+(std::unordered_map iteration, unstable std::sort, heap ties) without a GPU; the kernels are covered by the GPU parity tests."""
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import estimator_oracle as EO
+from xivo_b200 import sim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = os.path.join(ROOT, "xivo_b200", "cfg")
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")),
+                                reason="needs g++ and the CUDA headers (host-only compile)")
+
+
+@pytest.fixture(scope="module")
+def hh(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("twin") / "libhost_harness.so")
+    cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-I", CUDA_INC, "-shared", "-fPIC", os.path.join(ROOT, "tests", "cpp", "host_harness.cpp"), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(so)
+    lib.hh_create.restype = C.c_void_p
+    lib.hh_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.hh_error.restype = C.c_char_p
+    lib.hh_error_msg.restype = C.c_char_p
+    lib.hh_error_msg.argtypes = [C.c_void_p]
+    lib.hh_curr_time.restype = C.c_ulonglong
+    for n in ("hh_destroy", "hh_init_with_sim_depths", "hh_curr_time", "hh_sticky_error"):
+        getattr(lib, n).argtypes = [C.c_void_p]
+    lib.hh_motion.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_inertial.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_void_p]
+    lib.hh_push.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int]
+    lib.hh_pop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hh_pcw_begin.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p]
+    lib.hh_subfilter_ids.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_after_subfilter.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_after_gate.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_after_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.hh_features.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.hh_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    return lib
+
+
+def feats(lib, h, which):
+    buf = np.zeros((4096, 5), np.int32)
+    n = lib.hh_features(h, which, buf.ctypes.data, 4096)
+    return buf[:n].copy()
+
+
+class Recorder:
+    """Captures, per visual frame of the oracle, what the device computes in the product."""
+
+    def __init__(self, est, monkeypatch):
+        self.est, self.sub, self.mh, self.err, self.P = est, [], [], None, None
+        E = EO.E
+        sub0, mh0, absorb0, adapt0 = E.subfilter_update, E.mh_distance, est.absorb, est.adapt_initial_depth
+
+        def sub(*a, **k):
+            r = sub0(*a, **k)
+            self.sub.append(np.concatenate([np.asarray(r[0], float).ravel(), np.asarray(r[1], float).ravel(), [float(r[2])]]))
+            return r
+
+        def mh(*a, **k):
+            d = mh0(*a, **k)
+            self.mh.append(float(d))
+            return d
+
+        def absorb(err, *a, **k):
+            self.err = np.array(err, float).copy()
+            return absorb0(err, *a, **k)
+
+        def adapt(*a, **k):
+            self.P = est.P.copy()  # P after the update (or after this frame's slot edits when nothing was updated)
+            return adapt0(*a, **k)
+
+        monkeypatch.setattr(E, "subfilter_update", sub)
+        monkeypatch.setattr(E, "mh_distance", mh)
+        est.absorb, est.adapt_initial_depth = absorb, adapt
+
+    def reset(self):
+        self.sub, self.mh, self.err, self.P = [], [], None, None
+
+
+@pytest.mark.parametrize("G,F,duration,seed,sim_depths,method", [(4, 14, 4.0, 1, True, "PrinceDormand"), (15, 30, 3.0, 0, True, "RK4"),
+                                                                  (4, 14, 3.0, 6, False, "PrinceDormand"), (15, 30, 6.0, 2, True, "PrinceDormand")])
+def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G, F, duration, seed, sim_depths, method):
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    cfg["integration_method"] = method
+    msgs, _ = sim.pcw_stream(cfg, duration=duration, seed=seed)  # IMU and vision share timestamps: heap ties are exercised
+    N = 23 + 6 * G + 3 * F
+    est = EO.EstimatorOracle(cfg, G=G, F=F)
+    est.sim_init_depths = sim_depths
+    rec = Recorder(est, monkeypatch)
+    h = hh.hh_create(json.dumps(cfg).encode(), G, F, 0)
+    assert h, hh.hh_error()
+    if sim_depths:
+        hh.hh_init_with_sim_depths(h)
+    # the oracle executes a message inside InertialMeas / VisualMeasPointCloud once its heap releases one; mirror that with the
+    # product's own heap (hh_push / hh_pop) so that both execute the same message at the same step
+    payload = {}
+    n_vis = n_upd = 0
+    for k, (kind, ts, p) in enumerate(msgs):
+        payload[k] = (kind, ts, p)
+        # ---- oracle
+        rec.reset()
+        vc0 = est.vision_counter
+        if kind == "imu":
+            est.InertialMeas(ts, p[0], p[1])
+        else:
+            est.VisualMeasPointCloud(ts, p[0], p[1])
+        # ---- product host: push, pop, execute
+        hh.hh_push(h, ts, k)  # the message type field carries the payload key
+        t, key = C.c_ulonglong(), C.c_int()
+        if not hh.hh_pop(h, C.byref(t), C.byref(key)):
+            assert est.vision_counter == vc0 and rec.P is None
+            continue
+        mk, mts, mp = payload.pop(key.value)
+        assert mts == t.value
+        if mk == "imu":
+            g, a = np.ascontiguousarray(mp[0], dtype=np.float64), np.ascontiguousarray(mp[1], dtype=np.float64)
+            hh.hh_inertial(h, mts, g.ctypes.data, a.ctypes.data)
+            assert est.vision_counter == vc0, "the oracle executed a visual message where the product executed an IMU one"
+        else:
+            assert est.vision_counter == vc0 + 1, "the product executed a visual message where the oracle did not"
+            ids = np.ascontiguousarray(mp[0], dtype=np.int32)
+            xpd = np.ascontiguousarray(mp[1], dtype=np.float64)
+            nsub = hh.hh_pcw_begin(h, mts, len(ids), ids.ctypes.data, xpd.ctypes.data)
+            assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
+            if nsub < 0:
+                assert rec.P is None  # neither side got past the clock / initialisation checks
+                continue
+            n_vis += 1
+            assert nsub == len(rec.sub), f"frame {n_vis}: sub-filter batch {nsub} vs oracle {len(rec.sub)}"
+            sub = np.ascontiguousarray(np.array(rec.sub).reshape(nsub, 13)) if nsub else np.zeros((1, 13))
+            ninst = hh.hh_after_subfilter(h, sub.ctypes.data)
+            assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
+            # the gate batch: one Mahalanobis distance per in-state feature, in the product's (slot) order
+            gated = len(rec.mh) > 0
+            if gated:
+                assert ninst == len(rec.mh), f"frame {n_vis}: {ninst} in-state features vs {len(rec.mh)} gated by the oracle"
+            mh = np.ascontiguousarray(rec.mh if gated else np.zeros(max(1, ninst)), dtype=np.float64)
+            nupd = hh.hh_after_gate(h, mh.ctypes.data)
+            assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
+            had = rec.err is not None
+            assert (nupd > 0) == had, f"frame {n_vis}"
+            n_upd += had
+            P = rec.P if rec.P is not None else est.P
+            err = np.ascontiguousarray(rec.err if had else np.zeros(N))
+            Pmm, diag = np.ascontiguousarray(P[:23, :23]), np.ascontiguousarray(np.diag(P))
+            hh.hh_after_update(h, err.ctypes.data, Pmm.ctypes.data, diag.ctypes.data, int(had))
+            assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
+            # ---- decisions must be identical
+            tr = feats(hh, h, 2)
+            assert tr[:, 0].tolist() == [f.id for f in est.tracks], f"frame {n_vis}: track list"
+            assert tr[:, 3].tolist() == [int(f.status) for f in est.tracks], f"frame {n_vis}: feature status"
+            inst = feats(hh, h, 0)
+            o_inst = sorted(est.instate_features, key=lambda f: f.slot)
+            assert sorted(map(tuple, inst[:, :3].tolist())) == sorted((f.id, f.sind, f.ref.sind) for f in o_inst), f"frame {n_vis}: in-state slots"
+            assert sorted(inst[inst[:, 3] == 7, 0].tolist()) == sorted(f.id for f in o_inst if f.status == EO.F_GAUGE), f"frame {n_vis}: gauge features"
+            gb, gauge = np.zeros((64, 3), np.int32), C.c_int()
+            ng = hh.hh_groups(h, gb.ctypes.data, 64, C.byref(gauge))
+            assert sorted(map(tuple, gb[:ng, :2].tolist())) == sorted((g.id, g.sind) for g in est.groups.values() if g.instate())
+            assert gauge.value == est.gauge_group
+        m = np.zeros(42)
+        hh.hh_motion(h, m.ctypes.data)
+        # nominal state: the host integrates / absorbs with AVX2-FMA C++, the oracle with numpy: rounding-level drift over 150 updates
+        assert np.abs(m[:9].reshape(3, 3) - est.X.Rsb).max() <= 1e-10 and np.abs(m[9:12] - est.X.Tsb).max() <= 1e-10, f"message {k}"
+        assert np.abs(m[12:15] - est.X.Vsb).max() <= 1e-10 and hh.hh_curr_time(h) == est.curr_time
+    assert n_vis >= 60 and n_upd >= 50 and len(est.instate_features) >= min(F, 10)
+    hh.hh_destroy(h)

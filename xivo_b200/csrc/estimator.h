@@ -21,6 +21,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "hostmath.h"
@@ -192,6 +193,29 @@ struct FlatMap {
 struct Graph {
   FlatMap<Feature> features;
   FlatMap<Group> groups;
+  // The reference keeps its objects in std::unordered_map<int, Ptr> (graphbase.h:49-51) and three decisions read them in
+  // ITERATION order (GraphBase::GetFeaturesIf / GetGroupsIf, graphbase.cpp:124-146): the gauge-feature candidates
+  // (graph.cpp:291), the group candidates and their features in AddGroupOfFeatures (manager.cpp:479-497) and the unsorted
+  // "median" of AdaptInitialDepth (manager.cpp:257-266).  That order is a property of libstdc++'s hash table, so the same
+  // container type is kept here with the same insert / erase history and used for exactly those reads; everything else uses
+  // the id-sorted maps above.  (oracle/estimator_oracle.py does the same through oracle/stdumap.cpp; tests/test_reference_pin.py
+  // checks the result against the reference's own estimator.)
+  std::unordered_map<int, Feature*> um_features;
+  std::unordered_map<int, Group*> um_groups;
+  template <typename Pred>
+  std::vector<Feature*> features_std(Pred p) const {
+    std::vector<Feature*> out;
+    for (const auto& kv : um_features)
+      if (p(kv.second)) out.push_back(kv.second);
+    return out;
+  }
+  template <typename Pred>
+  std::vector<Group*> groups_std(Pred p) const {
+    std::vector<Group*> out;
+    for (const auto& kv : um_groups)
+      if (p(kv.second)) out.push_back(kv.second);
+    return out;
+  }
   void add_feature(Feature* f);
   void add_group(Group* g);
   void remove_feature(Feature* f);
