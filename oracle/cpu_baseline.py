@@ -8,9 +8,15 @@ the fastest faithful CPU implementation available:
                src/tracker.cpp:224, :526; cv2.setNumThreads(1), parallelism comes from processes),
   * EKF      : oracle/_ref/libekf_eigen.so = the reference's Eigen 3.3.9 expression sequence for
                MHGating + UpdateJosephForm (single-threaded, like the reference); numpy if absent.
-Python bookkeeping, propagation, sub-filter and Jacobian assembly are NOT charged to the CPU
-baseline (they are cheap compiled code in the reference), so the figure is an upper bound on the
-reference's frames/s."""
+Python bookkeeping, propagation, sub-filter and Jacobian assembly are NOT charged to that figure
+(`fps`, kind "port": an upper bound on the reference's frames/s).
+
+Since the reference's own estimator builds here (oracle/build_ref.py -> oracle/_ref/libxivo_ref_G<g>_F<f>.so, its unmodified
+sources), every worker additionally runs THAT library on a point-cloud stream with the same state size and about the same
+number of tracked features and measures its wall time per frame (8 IMU messages + 1 visual message: propagation, ProcessTracks,
+sub-filters, Jacobians, gating, update, feature/group management — everything but the image tracker, which needs OpenCV C++).
+`fps_reference` = frames/s with a frame costing (cv2 tracker calls on the image stream) + (reference estimator on the point-cloud
+stream): kind "reference" for the estimator half, OpenCV's own code (through cv2) for the tracker half."""
 from __future__ import annotations
 
 import ctypes as C
@@ -120,8 +126,35 @@ def worker(args):
             last = st.frame_s
         if len(per_frame) >= n_frames:
             break
+    ref_ms, ref_tracks = None, None
+    try:
+        ref_ms, ref_tracks = reference_estimator_ms(G, F, n_frames, skip, seed)
+    except Exception:  # the library is optional: without it only the numerics-only figure is reported
+        ref_ms = None
     return dict(per_frame=per_frame, stage=st.stage, eigen=st.eig is not None, cv2=st.cv2 is not None,
-                ninstate=len(est.instate_features), ntracks=len(est.tracks))
+                ninstate=len(est.instate_features), ntracks=len(est.tracks), ref_ms=ref_ms, ref_tracks=ref_tracks)
+
+
+def reference_estimator_ms(G, F, n_frames, skip, seed):
+    """Wall time per frame [ms] of the reference's own estimator (oracle/_ref) on a point-cloud stream: (mean over the frames after
+    `skip`, tracked features per frame).  One estimator per process (the reference's singletons): call once per worker process."""
+    from xivo_b200 import sim
+
+    from . import ref_runner
+
+    if not ref_runner.available(G, F):
+        return None, None
+    cfg = sim.load_cfg(os.path.join(os.path.dirname(_HERE), "xivo_b200", "cfg", "pcw_sim.json"))
+    cfg["tracker_cfg"].update(num_features_min=120, num_features_max=150)  # Tracker::UpdatePointCloud keeps at most 150 tracks, like the image workload
+    msgs, _ = sim.pcw_stream(cfg, duration=(n_frames + skip + 12) * 0.04, seed=seed)
+    marks = []
+    r = ref_runner.run(cfg, msgs, G, F, True, on_visual=lambda: marks.append(time.perf_counter()))
+    k0 = min(skip + 10, len(marks) - 2)  # +10: the reorder buffer holds the first messages back
+    k1 = min(k0 + n_frames, len(marks) - 1)
+    per_frame_ms = 1e3 * (marks[k1] - marks[k0]) / max(1, k1 - k0)
+    ntr = float(np.mean([min(150, len(p[0])) for kind, _, p in msgs if kind == "pc"]))
+    assert r["n_instate"][-1] > 0
+    return per_frame_ms, ntr
 
 
 def run(cfg, n_procs, n_frames, skip, G, F, channels=1):
@@ -130,14 +163,24 @@ def run(cfg, n_procs, n_frames, skip, G, F, channels=1):
     import multiprocessing as mp
 
     ctx = mp.get_context("fork")
-    with ctx.Pool(n_procs) as pool:
-        res = pool.map(worker, [(cfg, s, n_frames, skip, G, F, channels) for s in range(n_procs)])
+    with ctx.Pool(n_procs, maxtasksperchild=1) as pool:  # one task per process: the reference library keeps process-wide singletons
+        res = pool.map(worker, [(cfg, s, n_frames, skip, G, F, channels) for s in range(n_procs)], chunksize=1)
     fps = sum(len(r["per_frame"]) / max(sum(r["per_frame"]), 1e-12) for r in res)
     mean_ms = 1e3 * float(np.mean([np.mean(r["per_frame"]) for r in res]))
     stage = {k: float(np.mean([r["stage"][k] for r in res])) for k in res[0]["stage"]}
     tot = sum(stage.values()) or 1.0
-    return dict(fps=fps, mean_frame_ms=mean_ms, stage_share={k: v / tot for k, v in stage.items()}, eigen=res[0]["eigen"], cv2=res[0]["cv2"],
-                frames=sum(len(r["per_frame"]) for r in res), ninstate=res[0]["ninstate"], ntracks=res[0]["ntracks"])
+    out = dict(fps=fps, mean_frame_ms=mean_ms, stage_share={k: v / tot for k, v in stage.items()}, eigen=res[0]["eigen"], cv2=res[0]["cv2"],
+               frames=sum(len(r["per_frame"]) for r in res), ninstate=res[0]["ninstate"], ntracks=res[0]["ntracks"], fps_reference=None)
+    if all(r.get("ref_ms") for r in res):
+        # per worker: a frame = the cv2 tracker calls measured on its image stream + the reference's own estimator measured on its point-cloud stream
+        fr = [len(r["per_frame"]) for r in res]
+        trk_ms = [1e3 * (r["stage"]["lk"] + r["stage"]["fast"]) / max(1, (len(r["per_frame"]) + skip)) for r in res]
+        out["fps_reference"] = float(sum(1e3 / (t + r["ref_ms"]) for t, r in zip(trk_ms, res)))
+        out["ref_estimator_ms"] = float(np.mean([r["ref_ms"] for r in res]))
+        out["tracker_ms"] = float(np.mean(trk_ms))
+        out["ref_tracks"] = float(np.mean([r["ref_tracks"] for r in res]))
+        del fr
+    return out
 
 
 if __name__ == "__main__":  # python -m oracle.cpu_baseline <cfg.json> <procs> <frames> <skip> <G> <F>  -> JSON on stdout

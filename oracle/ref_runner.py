@@ -23,7 +23,7 @@ def available(G: int, F: int) -> bool:
     return os.path.exists(lib_path(G, F))
 
 
-def run(cfg: dict, msgs, G: int, F: int, sim_depths: bool = True, lib_file: str | None = None):
+def run(cfg: dict, msgs, G: int, F: int, sim_depths: bool = True, lib_file: str | None = None, on_visual=None):
     """msgs: [(kind, ts_ns, payload)] with 'imu' -> (gyro, accel), 'pc' -> (ids, xp_depth n x 3).  Returns a dict of arrays
     sampled after every visual message: gsb (k x 3 x 4), ts, n_instate, gauge, instate ids (list), and the final P."""
     L = C.CDLL(lib_file or lib_path(G, F))
@@ -59,6 +59,8 @@ def run(cfg: dict, msgs, G: int, F: int, sim_depths: bool = True, lib_file: str 
             out["gauge"].append(cnt[2])
             out["ids"].append(sorted(ids_buf[i] for i in range(min(n, 256))))
             out["vel"].append(v.copy())
+            if on_visual is not None:
+                on_visual()
     P = np.zeros((N, N))
     L.ref_P(P.ctypes.data_as(C.c_void_p))
     out["P"] = P

@@ -65,3 +65,29 @@ def test_defaults_match_the_contract():
     for flag in ("--gpus", "--steps", "--warmup", "--impl", "--seqs", "--batches", "--cov-update"):
         assert flag in r.stdout
     assert bench.measured_peaks()["hbm"] > 1000
+
+
+def test_cpu_baseline_entry_kinds():
+    r = dict(fps=4000.0, mean_frame_ms=4.0, stage_share=dict(lk=0.7, fast=0.2, gate=0.02, update=0.08), eigen=True, fps_reference=None)
+    e = bench.cpu_baseline_entry(r, 16, 80, 12.0)
+    assert e["kind"] == "port" and e["value"] == 4000.0 and e["cores"] == 16
+    r.update(fps_reference=2900.0, tracker_ms=3.2, ref_estimator_ms=2.9, ref_tracks=150.0)
+    e = bench.cpu_baseline_entry(r, 16, 80, 12.0)
+    assert e["kind"] == "reference" and e["value"] == 2900.0 and e["numerics_only_value"] == 4000.0 and "reference's own" in e["sample"]
+    json.dumps(e)
+
+
+def test_cpu_baseline_runs_the_reference_library_when_it_is_built():
+    """oracle/cpu_baseline.py end to end on 2 processes x 6 frames: cv2 tracker timing + (where oracle/_ref is built) the reference's own
+    estimator on a point-cloud stream -> fps_reference below the numerics-only upper bound."""
+    r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", os.path.join(ROOT, "xivo_b200", "cfg", "vio_640x480.json"), "2", "6", "13", "4", "14"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["fps"] > 0 and d["frames"] >= 4 and d["cv2"]
+    from oracle import ref_runner
+
+    if ref_runner.available(4, 14):
+        assert d["fps_reference"] and 0 < d["fps_reference"] < d["fps"] and 0.5 < d["ref_estimator_ms"] < 50 and d["ref_tracks"] == 150
+    else:
+        assert d["fps_reference"] is None

@@ -64,6 +64,40 @@ def test_pcw_trajectory_parity(G, F, method, sim_depths):
     b.close()
 
 
+@pytest.mark.parametrize("case", ["default_203", "small_89", "nodepth_89", "rk4_89"])
+def test_pcw_trajectory_matches_the_reference_estimator(case, tmp_path):
+    """The CUDA pipeline against the REFERENCE'S OWN ESTIMATOR (its unmodified sources built into oracle/_ref by oracle/build_ref.py;
+    golden arrays tests/golden/reference_pcw.npz where the library is absent) on the point-cloud streams of tests/test_reference_pin.py:
+    identical in-state id tables and gauge group after every frame, pose within 1e-7 m / 1e-8, covariance within 1e-7 * max|P|."""
+    import test_reference_pin as RP
+
+    name, G, F, duration, seed, sim_depths, over, offset = next(c for c in RP.CASES if c[0] == case)
+    cfg = sim.load_cfg(RP.CFG)
+    if over:
+        cfg.update(over)
+    ref, how = RP.reference_result(name, over, G, F, duration, seed, sim_depths, offset, tmp_path)
+    msgs, _ = RP.stream(cfg, duration, seed, offset)
+    b = pyxivo.Batch(cfg, n_seq=1, max_groups=G, max_features=F)
+    if sim_depths:
+        b.init_with_sim_depths()
+    k = 0
+    for kind, ts, p in msgs:
+        if kind == "imu":
+            b.inertial_meas(ts, p[0], p[1])
+        else:
+            b.visual_meas_pointcloud(ts, p[0], p[1])
+            g = b.gsb(0)
+            assert b.now(0) == int(ref["ts"][k]), f"{how}: frame {k}: a different message executed (heap order)"
+            assert sorted(b.instate_features(0)["ids"].tolist()) == [int(x) for x in ref["ids"][k] if x >= 0], f"{how}: frame {k}"
+            assert b.counters(0)["gauge_group"] == int(ref["gauge"][k])
+            assert np.abs(g[:, 3] - ref["gsb"][k][:, 3]).max() <= 1e-7 and np.abs(g[:, :3] - ref["gsb"][k][:, :3]).max() <= 1e-8, f"{how}: frame {k}"
+            k += 1
+    assert k == len(ref["gsb"])
+    P = b.P(0)
+    assert np.abs(P - ref["P"]).max() <= 1e-7 * np.abs(ref["P"]).max()
+    b.close()
+
+
 def test_pcw_trajectory_tensor_core_covariance():
     """"covariance_update": "tf32x3" — the downdate of every measurement update runs on tcgen05 tensor cores with
     fp32-level accuracy (BASELINE configs[2] "fp32 covariance").  Stated tolerance against the fp64 oracle after
