@@ -1,5 +1,6 @@
 """Bring-up probe for the tcgen05 covariance downdate (GPU box): error of the tf32x3 update vs the fp64
-kernels, normalised by sqrt(P_ii P_jj).  Usage: [XIVO_TC_SWAP=1] python scripts/tc_probe.py"""
+kernels, normalised by sqrt(P_ii P_jj).  Usage: python scripts/tc_probe.py  (XIVO_TC_SWAP was a bring-up switch for the descriptor
+roles; variant 0 is the one that is right and the only one left)"""
 import os
 import sys
 

@@ -238,7 +238,7 @@ size_t ekf_cov_tc_smem(int N) {
 
 int launch_ekf_cov_tc(cudaStream_t st, int N, const int* nsel, int Mdense, int Mmax, const double* HP, const double* Kt, double* P,
                       int batch) {
-  static const int variant = getenv("XIVO_TC_SWAP") ? atoi(getenv("XIVO_TC_SWAP")) : 0;  // bring-up switch: LBO/SBO roles
+  const int variant = 0;  // LBO = stride between the two 16-byte K chunks, SBO = stride between 8-row groups (confirmed on the B200, profiles/r01d_tc_probe.txt)
   const size_t smem = ekf_cov_tc_smem(N);
   XB_CUDA(cudaFuncSetAttribute(ekf_cov_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tm = (N + TC_MT - 1) / TC_MT, tn = (N + TC_NT_MAX - 1) / TC_NT_MAX;
