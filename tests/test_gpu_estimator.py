@@ -64,7 +64,7 @@ def test_pcw_trajectory_parity(G, F, method, sim_depths):
     b.close()
 
 
-@pytest.mark.parametrize("case", ["default_203", "small_89", "nodepth_89", "rk4_89"])
+@pytest.mark.parametrize("case", ["default_203", "small_89", "nodepth_89", "rk4_89", "equidistant_203"])
 def test_pcw_trajectory_matches_the_reference_estimator(case, tmp_path):
     """The CUDA pipeline against the REFERENCE'S OWN ESTIMATOR (its unmodified sources built into oracle/_ref by oracle/build_ref.py;
     golden arrays tests/golden/reference_pcw.npz where the library is absent) on the point-cloud streams of tests/test_reference_pin.py:

@@ -94,12 +94,23 @@ def camera_pose(traj, t, Rbc, Tbc):
     return Rsb @ Rbc, Rsb @ Tbc + Tsb
 
 
-def observe_points(world, Rsc, Tsc, K, rows, cols, rng, sigma=0.5, zmin=0.3, zmax=4.5, border=10):
+def observe_points(world, Rsc, Tsc, K, rows, cols, rng, sigma=0.5, zmin=0.3, zmax=4.5, border=10, cam=None):
+    """Projects the world points visible from (Rsc, Tsc): pinhole (common/camera_pinhole.h:17-37) or, with cam["model"] ==
+    "equidistant", the Kannala-Brandt model of common/camera_equidist.h:23-60 (r = theta (1 + k0 theta^2 + ...))."""
     Xc = (world - Tsc) @ Rsc
     z = Xc[:, 2]
     ok = (z > zmin) & (z < zmax)
-    u = K[0] * Xc[:, 0] / np.where(ok, z, 1) + K[2]
-    v = K[1] * Xc[:, 1] / np.where(ok, z, 1) + K[3]
+    zs = np.where(ok, z, 1)
+    xn, yn = Xc[:, 0] / zs, Xc[:, 1] / zs
+    if cam is not None and cam.get("model", "pinhole") == "equidistant":
+        k0, k1, k2, k3 = cam.get("k0123", (0, 0, 0, 0))
+        th = np.arctan2(np.hypot(xn, yn), 1.0)
+        phi = np.arctan2(yn, xn)
+        t2 = th * th
+        r = th * (1 + t2 * (k0 + t2 * (k1 + t2 * (k2 + t2 * k3))))
+        u, v = K[0] * r * np.cos(phi) + K[2], K[1] * r * np.sin(phi) + K[3]
+    else:
+        u, v = K[0] * xn + K[2], K[1] * yn + K[3]
     ok &= (u > border) & (u < cols - border) & (v > border) & (v < rows - border)
     idx = np.nonzero(ok)[0]
     xp = np.column_stack([u[idx], v[idx]]) + rng.normal(0, sigma, (len(idx), 2))
@@ -124,7 +135,7 @@ def pcw_stream(cfg: dict, duration=4.0, imu_dt=0.005, vision_dt=0.04, seed=0, no
         msgs.append((t, 0, "imu", (traj.gyro(t) + rng.normal(0, noise_gyro, 3), traj.accel(t) + rng.normal(0, noise_accel, 3))))
     for t in np.arange(0, duration, vision_dt):
         Rsc, Tsc = camera_pose(traj, t, Rbc, Tbc)
-        ids, xpd = observe_points(world, Rsc, Tsc, K, cam["rows"], cam["cols"], rng, pixel_sigma)
+        ids, xpd = observe_points(world, Rsc, Tsc, K, cam["rows"], cam["cols"], rng, pixel_sigma, cam=cam)
         msgs.append((t, 1, "pc", (ids, xpd)))
     msgs.sort(key=lambda m: (m[0], m[1]))
     return [(k, int(round(t * 1e9)), p) for (t, _, k, p) in msgs], traj
