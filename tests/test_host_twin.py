@@ -92,8 +92,15 @@ class Recorder:
         self.sub, self.mh, self.err, self.P = [], [], None, None
 
 
-@pytest.mark.parametrize("G,F,duration,seed,sim_depths,method", [(4, 14, 4.0, 1, True, "PrinceDormand"), (15, 30, 3.0, 0, True, "RK4"),
-                                                                  (4, 14, 3.0, 6, False, "PrinceDormand"), (15, 30, 6.0, 2, True, "PrinceDormand")])
+TWIN_CASES = [(4, 14, 4.0, 1, True, "PrinceDormand"), (15, 30, 3.0, 0, True, "RK4"), (4, 14, 3.0, 6, False, "PrinceDormand"), (15, 30, 6.0, 2, True, "PrinceDormand")]
+# XIVO_TWIN_SWEEP=n adds n more seeds x both state sizes x with/without simulated depths (a wider offline sweep; 48 extra sequences passed at n = 12)
+for _s in range(int(os.environ.get("XIVO_TWIN_SWEEP", "0"))):
+    for _g, _f in ((4, 14), (15, 30)):
+        for _d in (True, False):
+            TWIN_CASES.append((_g, _f, 4.0, 100 + _s, _d, "PrinceDormand"))
+
+
+@pytest.mark.parametrize("G,F,duration,seed,sim_depths,method", TWIN_CASES)
 def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G, F, duration, seed, sim_depths, method):
     cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
     cfg["integration_method"] = method
