@@ -37,6 +37,8 @@ ROWS, COLS, G, F = 480, 640, 4, 14
 IMU_PER_FRAME = 8
 FRAME_NS = 40_000_000
 PREROLL_FRAMES = 12  # gravity init (stationary) + first detections, never timed
+CAL_ROUNDS, CAL_STEPS = 2, 4  # frame-ingest calibration: per round and mode one settling step + CAL_STEPS timed steps (untimed region)
+INGEST_MODES = {"zero_copy": 0, "copy_engine": 1}
 
 
 def load_cfg():
@@ -101,6 +103,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].strip().lower().startswith("active")})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def pick_ingest(ms):
+    """ms: {mode: [ms per step of each calibration round]} -> the mode with the best round; the current default
+    (zero_copy) keeps the job unless the alternative is at least 3 % faster (below that it is noise)."""
+    best = {k: min(v) for k, v in ms.items() if v}
+    if "zero_copy" not in best:
+        return min(best, key=best.get)
+    alt = min(best, key=best.get)
+    return alt if best[alt] < 0.97 * best["zero_copy"] else "zero_copy"
 
 
 def make_streams(cfg, n_streams, n_frames):
@@ -221,7 +233,8 @@ def run_ours(args):
     cfg = load_cfg()
     cfg["covariance_update"] = args.cov_update  # "fp64" (default, exact parity) or "tf32x3" (tcgen05 downdate, fp32 accuracy)
     B, K, W = args.seqs, args.steps, args.warmup
-    n_frames = PREROLL_FRAMES + 3 * (W + K) + 4
+    n_cal = CAL_ROUNDS * 2 * (1 + CAL_STEPS) if args.ingest == "auto" else 0
+    n_frames = PREROLL_FRAMES + 3 * (W + K) + 4 + n_cal
     log("rendering", min(B, args.streams), "streams x", n_frames, "frames")
     streams = make_streams(cfg, min(B, args.streams), n_frames)
     log("streams ready")
@@ -334,10 +347,38 @@ def run_ours(args):
         ms = replicas.max_over_ranks(ms, device="cuda")
         return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked / K)
 
+    def calibrate_ingest():
+        """Pinned host frames reach the device either by a gather kernel reading host memory over PCIe or by the copy
+        engine (xivo_set_frame_ingest); same results, the faster one depends on the host's PCIe path.  Picks per rank,
+        outside every timed region, from end-to-end steps of this very workload."""
+        nonlocal f
+        L.xivo_set_frame_ingest.restype = C.c_int
+        if args.ingest != "auto":
+            L.xivo_set_frame_ingest(INGEST_MODES[args.ingest])
+            return args.ingest, None
+        ms = {m: [] for m in INGEST_MODES}
+        for _ in range(CAL_ROUNDS):
+            for name, mode in INGEST_MODES.items():
+                L.xivo_set_frame_ingest(mode)
+                step(f, False)
+                f += 1
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(CAL_STEPS):
+                    step(f, False)
+                    f += 1
+                torch.cuda.synchronize()
+                ms[name].append((time.perf_counter() - t0) * 1e3 / CAL_STEPS)
+        best = pick_ingest(ms)
+        L.xivo_set_frame_ingest(INGEST_MODES[best])
+        return best, {k: [round(x, 3) for x in v] for k, v in ms.items()}
+
     # three passes over consecutive frames of the same streams: the two measured ones run with the in-library
     # profiler off (its event records and locks cost ~1 ms/step); the third only attributes time to kernels
     r_dev = timed(True, 0)
     log("device-resident pass", r_dev["ms"], "ms")
+    ingest, ingest_cal = calibrate_ingest()
+    log("frame ingest:", ingest, ingest_cal)
     r_e2e = timed(False, 0)
     log("e2e pass", r_e2e["ms"], "ms")
     r_prof = timed(not args.profile_e2e, args.profile_level)
@@ -364,7 +405,8 @@ def run_ours(args):
                    config=dict(covariance_update=args.cov_update, workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
                                sequences_per_gpu=B, batches_per_gpu=NB, host_threads=int(os.environ.get("XIVO_THREADS", "0")) or None, host_cpu_budget=budget, distinct_streams=S, frames_per_step=world * B, channels=1,
                                l2_policy="inputs larger than L2 are not needed: every step reads a new frame set (B x 307 KB) from the stream buffers; covariance/pyramids are the resident state by design",
-                               message_buffer_size=cfg.get("message_buffer_size", 10)),
+                               message_buffer_size=cfg.get("message_buffer_size", 10), frame_ingest=ingest,
+                               frame_ingest_calibration_ms_per_step=ingest_cal),
                    e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * fbytes,
                             d2h_bytes_per_step=(r_e2e["prof"]["_d2h_bytes"] / K) if r_e2e["prof"]["_d2h_bytes"] else None, ms_per_step=r_e2e["ms"] / K),
                    gpu_launches=r_dev["launches"], clocks=r_dev["clocks"], roofline=roofline, cpu_baseline=cpu,
@@ -416,6 +458,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cov-update", default="fp64", choices=["fp64", "tf32x3"], help="arithmetic of the covariance downdate (tf32x3 = tcgen05 tensor cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ingest", default="auto", choices=["auto"] + list(INGEST_MODES), help="how pinned host frames reach the device (e2e pass); auto = calibrate both before the timed region")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

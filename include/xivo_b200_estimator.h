@@ -57,6 +57,15 @@ int xivo_batch_visual_meas_device(xivo_batch* b, const uint64_t* ts_ns, const ui
 int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const double* gyro, const double* accel,
                     const uint64_t* frame_ts, const uint8_t* const* imgs, int rows, int cols, int channels, int on_device);
 
+/* How device-accessible (pinned / registered) host frames are brought into the device frame ring:
+ * XIVO_INGEST_ZERO_COPY: one gather launch per call, the SMs read the host memory over PCIe (default);
+ * XIVO_INGEST_COPY_ENGINE: one cudaMemcpyAsync per frame on the copy stream.  Process-wide, takes effect at
+ * the next visual_meas / step call, results are identical.  Returns the previous mode; any other argument
+ * only queries.  Pageable host frames always take the copy-engine path. */
+#define XIVO_INGEST_ZERO_COPY 0
+#define XIVO_INGEST_COPY_ENGINE 1
+int xivo_set_frame_ingest(int mode);
+
 /* Per-kernel CUDA-event timing + host<->device byte counters (bench.py's roofline / e2e fields).
  * on: 0 off, 1 kernels + batch-level host phases, 2 additionally per-sequence host scopes (slow). */
 void xivo_profile_enable(int on);

@@ -91,3 +91,10 @@ def test_cpu_baseline_runs_the_reference_library_when_it_is_built():
         assert d["fps_reference"] and 0 < d["fps_reference"] < d["fps"] and 0.5 < d["ref_estimator_ms"] < 50 and d["ref_tracks"] == 150
     else:
         assert d["fps_reference"] is None
+
+
+def test_pick_ingest_keeps_the_default_unless_clearly_faster():
+    assert bench.pick_ingest({"zero_copy": [8.4, 8.3], "copy_engine": [8.2, 8.25]}) == "zero_copy"   # 1 % is noise
+    assert bench.pick_ingest({"zero_copy": [8.4, 8.3], "copy_engine": [6.1, 6.4]}) == "copy_engine"
+    assert bench.pick_ingest({"zero_copy": [6.0, 6.2], "copy_engine": [9.0, 8.8]}) == "zero_copy"
+    assert set(bench.INGEST_MODES.values()) == {0, 1}

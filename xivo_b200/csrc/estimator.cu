@@ -37,6 +37,10 @@ struct HostScope {
 
 namespace xb {
 extern std::atomic<unsigned long long> g_launches;
+// How pinned host frames reach the frame ring: 0 = one gather launch whose SMs read the host memory over PCIe,
+// 1 = one cudaMemcpyAsync per frame on the copy engine.  Results are identical; which is faster depends on the
+// host's PCIe path, so it is a run-time setting (xivo_set_frame_ingest; initial value from XIVO_ZEROCOPY).
+static std::atomic<int> g_frame_ingest{(getenv("XIVO_ZEROCOPY") && getenv("XIVO_ZEROCOPY")[0] == '0') ? 1 : 0};
 
 // Pinned host mirror + device array.
 template <typename T>
@@ -274,7 +278,7 @@ class Batch {
   // which keeps the H2D copy engine's FIFO free for the small latency-critical table uploads of the other
   // phases; pageable host frames fall back to one cudaMemcpyAsync each.
   int upload_frames(const uint8_t* const* imgs, const std::vector<int>& slot_of, bool on_device, size_t ib) {
-    static const bool zero_copy = !(getenv("XIVO_ZEROCOPY") && getenv("XIVO_ZEROCOPY")[0] == '0');
+    const bool zero_copy = g_frame_ingest.load(std::memory_order_relaxed) == 0;
     bool gather = on_device || zero_copy;
     for (int s = 0; s < B; ++s) {
       ingest_off.h[s] = ((size_t)s * ring_n + slot_of[s]) * ib;
@@ -908,6 +912,11 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
   const int rc = B_.ingest_many(in);
   const int rc2 = B_.ingest_done();
   return rc ? rc : rc2;
+}
+
+int xivo_set_frame_ingest(int mode) {
+  if (mode != XIVO_INGEST_ZERO_COPY && mode != XIVO_INGEST_COPY_ENGINE) return g_frame_ingest.load();
+  return g_frame_ingest.exchange(mode);
 }
 
 void xivo_profile_enable(int on) {
