@@ -331,6 +331,164 @@ def subfilter_update(cam: Camera, x, P, xp_meas, gsb, gbc, gref, Rtri, mh_thresh
     return xn, Pn, outlier_counter
 
 
+# -------------------------------------------------------------------------------------------------
+# Two-view depth triangulation (Feature::Triangulate, src/feature.cpp:686-751; helpers.cpp:103-372).
+# The reference stores several intermediates in `float` (a0/a1, the lambdas, the angles, the thresholds
+# arrive as float parameters): those narrowings are reproduced with numpy.float32.
+# -------------------------------------------------------------------------------------------------
+_f32 = np.float32
+
+
+def _acos_f32(c):
+    """float theta = acos(double).  DOCUMENTED DEVIATION: the cosine is clamped to [-1, 1].  In L1Angular one of the two
+    "reprojected" rays is the measured ray itself, so the reference evaluates acos(m.m / (|m| |m|)) — 1 up to rounding.  Whether
+    that is 1 + ulp (acos = NaN, and a NaN theta0 makes `max_theta > thresh` false, i.e. the check is bypassed) or <= 1 is decided
+    by the compiler's FMA contraction of Eigen's dot products (seen in the disassembly of the reference built here); the intended
+    value is 0, which the clamp gives deterministically.  With a threshold the check cannot fail at (90 deg) the reference is
+    reproduced to 1e-14 (tests/test_reference_pin.py)."""
+    return _f32(math.acos(min(1.0, max(-1.0, c)))) if c == c else _f32(np.nan)
+
+
+def _std_max(a, b):
+    """std::max(a, b) = (a < b) ? b : a  (helpers.cpp:353)."""
+    return b if a < b else a
+
+
+def tri_checks(z, t10, m0, Rf0p, m1, f1p, max_theta, beta_thresh):
+    """check_cheirality && check_angular_reprojection && check_parallax (helpers.cpp:330-372), short-circuit order kept."""
+    zn2 = np.linalg.norm(z) ** 2
+    with np.errstate(all="ignore"):
+        lam0 = _f32(z @ np.cross(t10, f1p) / zn2)
+        lam1 = _f32(z @ np.cross(t10, Rf0p) / zn2)
+        if lam0 <= 0 or lam1 <= 0:
+            return False
+        th0 = _acos_f32(m0 @ Rf0p / (np.linalg.norm(m0) * np.linalg.norm(Rf0p)))
+        th1 = _acos_f32(m1 @ f1p / (np.linalg.norm(m1) * np.linalg.norm(f1p)))
+        if _std_max(th0, th1) > _f32(max_theta):
+            return False
+        beta = _acos_f32(f1p @ Rf0p / (np.linalg.norm(f1p) * np.linalg.norm(Rf0p)))
+        if beta < _f32(beta_thresh):
+            return False
+    return True
+
+
+def _angular_finish(R01, t01, t10, m0, m1, m0p, m1p, max_theta, beta_thresh):
+    z = np.cross(m1p, m0p)
+    with np.errstate(all="ignore"):
+        X = (z @ np.cross(t10, m0p)) / np.linalg.norm(z) ** 2 * m1p
+    X = R01 @ X + t01
+    return tri_checks(z, t10, m0, m0p, m1, m1p, max_theta, beta_thresh), X
+
+
+def _bearings(R01, t01, xc0, xc1):
+    R10 = R01.T
+    t10 = -1 * R01.T @ t01
+    f0 = np.array([xc0[0], xc0[1], 1.0])
+    f0 = f0 / np.linalg.norm(f0)
+    f1 = np.array([xc1[0], xc1[1], 1.0])
+    f1 = f1 / np.linalg.norm(f1)
+    return t10, R10 @ f0, f1
+
+
+def tri_l1_angular(R01, t01, xc0, xc1, max_theta, beta_thresh):
+    """L1Angular, helpers.cpp:157-215.  Returns (ok, X in the first view's camera frame)."""
+    t10, m0, m1 = _bearings(R01, t01, xc0, xc1)
+    a0 = _f32(np.linalg.norm(np.cross(m0 / np.linalg.norm(m0), t10)))
+    a1 = _f32(np.linalg.norm(np.cross(m1 / np.linalg.norm(m1), t10)))
+    if a0 <= a1:
+        n1 = np.cross(m1, t10)
+        n1 = n1 / np.linalg.norm(n1)
+        m0p, m1p = m0 - (m0 @ n1) * n1, m1
+    else:
+        n0 = np.cross(m0, t10)
+        n0 = n0 / np.linalg.norm(n0)
+        m0p, m1p = m0, m1 - (m1 @ n0) * n0
+    return _angular_finish(R01, t01, t10, m0, m1, m0p, m1p, max_theta, beta_thresh)
+
+
+def tri_l2_angular(R01, t01, xc0, xc1, max_theta, beta_thresh):
+    """L2Angular, helpers.cpp:218-275: n' = right singular vector of the second singular value of
+    B = [m0^ m1^]^T (I - t^ t^T)  (JacobiSVD, FullV; the sign of n' cancels in the projections)."""
+    t10, m0, m1 = _bearings(R01, t01, xc0, xc1)
+    A = np.stack([m0 / np.linalg.norm(m0), m1 / np.linalg.norm(m1)], axis=1)
+    th = t10 / np.linalg.norm(t10)
+    B = A.T @ (np.eye(3) - np.outer(th, th))
+    n = np.linalg.svd(B)[2][1]
+    m0p = m0 - (m0 @ n) * n
+    m1p = m1 - (m1 @ n) * n
+    return _angular_finish(R01, t01, t10, m0, m1, m0p, m1p, max_theta, beta_thresh)
+
+
+def tri_linf_angular(R01, t01, xc0, xc1, max_theta, beta_thresh):
+    """LinfAngular, helpers.cpp:277-327.  n' is NOT normalised there (`n_prime_hat` is n_a or n_b as computed); kept."""
+    t10, m0, m1 = _bearings(R01, t01, xc0, xc1)
+    m0h, m1h = m0 / np.linalg.norm(m0), m1 / np.linalg.norm(m1)
+    na, nb = np.cross(m0h + m1h, t10), np.cross(m0h - m1h, t10)
+    n = na if np.linalg.norm(na) >= np.linalg.norm(nb) else nb
+    m0p = m0 - (m0 @ n) * n
+    m1p = m1 - (m1 @ n) * n
+    return _angular_finish(R01, t01, t10, m0, m1, m0p, m1p, max_theta, beta_thresh)
+
+
+def tri_dlt_svd(R12, t12, xc1, xc2):
+    """DirectLinearTransformSVD, helpers.cpp:103-129 (always 'succeeds')."""
+    P1 = np.zeros((3, 4))
+    P1[:, :3] = np.eye(3)
+    P2 = np.zeros((3, 4))
+    P2[:, :3] = R12.T
+    P2[:, 3] = -R12.T @ t12
+    f1 = np.array([xc1[0], xc1[1], 1.0])
+    f1 = f1 / np.linalg.norm(f1)
+    f2 = np.array([xc2[0], xc2[1], 1.0])
+    f2 = f2 / np.linalg.norm(f2)
+    A = np.stack([f1[0] * P1[2] - f1[2] * P1[0], f1[1] * P1[2] - f1[2] * P1[1], f2[0] * P2[2] - f2[2] * P2[0], f2[1] * P2[2] - f2[2] * P2[1]])
+    v = np.linalg.svd(A)[2][3]
+    with np.errstate(all="ignore"):
+        return True, v[:3] / v[3]
+
+
+def tri_dlt_avg(R12, t12, xc1, xc2):
+    """DirectLinearTransformAvg, helpers.cpp:131-154 (mid-point of the two rays; always 'succeeds')."""
+    f1 = np.array([xc1[0], xc1[1], 1.0])
+    f1 = f1 / np.linalg.norm(f1)
+    f2 = np.array([xc2[0], xc2[1], 1.0])
+    f2 = f2 / np.linalg.norm(f2)
+    f2u = R12 @ f2
+    b = np.array([t12 @ f1, t12 @ f2u])
+    A = np.array([[f1 @ f1, -(f1 @ f2u)], [f1 @ f2u, -(f2u @ f2u)]])
+    det = A[0, 0] * A[1, 1] - A[0, 1] * A[1, 0]
+    with np.errstate(all="ignore"):
+        inv = np.array([[A[1, 1], -A[0, 1]], [-A[1, 0], A[0, 0]]]) * (1.0 / det)  # Eigen's 2x2 inverse: adjugate * (1 / determinant)
+        lam = inv @ b
+    return True, (lam[0] * f1 + (t12 + lam[1] * f2u)) / 2.0
+
+
+TRI_METHODS = ("direct_linear_transform_svd", "direct_linear_transform_avg", "l1_angular", "l2_angular", "linf_angular")
+
+
+def triangulate(method, R12, t12, xc1, xc2, zmin, zmax, max_theta, beta_thresh):
+    """Feature::Triangulate after the un-projection (feature.cpp:695-749): g12 = (ref.gsb*gbc)^-1 (gsb*gbc), xc1 / xc2 the
+    normalised first / newest observation.  Returns the new feature state [x/z, y/z, log z] or None (bad triangulation)."""
+    if method == "direct_linear_transform_svd":
+        ok, X = tri_dlt_svd(R12, t12, xc1, xc2)
+    elif method == "direct_linear_transform_avg":
+        ok, X = tri_dlt_avg(R12, t12, xc1, xc2)
+    elif method == "l1_angular":
+        ok, X = tri_l1_angular(R12, t12, xc1, xc2, max_theta, beta_thresh)
+    elif method == "l2_angular":
+        ok, X = tri_l2_angular(R12, t12, xc1, xc2, max_theta, beta_thresh)
+    elif method == "linf_angular":
+        ok, X = tri_linf_angular(R12, t12, xc1, xc2, max_theta, beta_thresh)
+    else:
+        raise ValueError("Incorrect Method for Triangulation: " + str(method))
+    if not ok:
+        return None
+    z = X[2]
+    if z < zmin or z > zmax:  # NaN passes both comparisons in the reference too (then log(NaN) poisons the feature)
+        return None
+    return np.array([X[0] / z, X[1] / z, math.log(z) if z > 0 else float("nan")])
+
+
 def predict_pixel(cam: Camera, x, gref, gsb, gbc):
     """Feature::Predict, src/feature.h:175-179 with Feature::Xs (feature.cpp:108-118)."""
     Xc, _ = unproject_logz(x)

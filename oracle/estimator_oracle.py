@@ -56,6 +56,7 @@ class Feature:
         self.P = np.zeros((3, 3))
         self.pred = np.array([-1.0, -1.0])
         self.outlier_counter = 0.0
+        self.tri_ok = False  # triangulation_successful_ (feature.cpp:80)
         self.track = [np.array([x, y], dtype=np.float64)]
         self.response = 0.0
 
@@ -172,6 +173,15 @@ class EstimatorOracle:
         self.init_z = c["initial_z"]
         self.init_std = (c["initial_std_x"] / fl, c["initial_std_y"] / fl, c["initial_std_z"])
         self.min_z, self.max_z = c["min_depth"], c["max_depth"]
+        # depth triangulation before the sub-filter (estimator.cpp:157-164, :356-358; jsoncpp: a missing number reads as 0)
+        self.tri_pre = c.get("triangulate_pre_subfilter", False)
+        tr = c.get("triangulation", {})
+        self.tri_method = tr.get("method", "l1_angular")
+        self.tri_zmin, self.tri_zmax = tr.get("zmin", 0.05), tr.get("zmax", 5.0)
+        self.tri_max_theta = tr.get("max_theta_thresh", 0.1) * math.pi / 180
+        self.tri_beta = tr.get("beta_thesh", 0.25) * math.pi / 180
+        self.init_std_badtri = (c.get("initial_std_x_badtri", 0.0), c.get("initial_std_y_badtri", 0.0), c.get("initial_std_z_badtri", 0.0))
+        self.num_good_tri = self.num_bad_tri = 0
         self.use_MH = c.get("use_MH_gating", True)
         self.min_inliers = c.get("min_inliers", 5)
         self.MH_thresh, self.MH_mult = c.get("MH_thresh", 5.991), c.get("MH_adjust_factor", 1.1)
@@ -587,6 +597,8 @@ class EstimatorOracle:
                 keep.append(f)
             else:
                 f.init_counter += 1
+                if self.tri_pre and len(f.track) == 2:  # manager.cpp:229-231
+                    self.triangulate(f)
                 f.x, f.P, f.outlier_counter = E.subfilter_update(self.cam, f.x, f.P, f.xp(), gsb, self.gbc(), (f.ref.Rsb, f.ref.Tsb),
                                                                 self.sub_Rtri, self.sub_mh, f.outlier_counter)
                 f.status = F_READY if f.init_counter > self.sub_ready else F_INITIALIZING
@@ -671,6 +683,9 @@ class EstimatorOracle:
             f.x[:2] = self.cam.unproject(f.xp())
             f.x[2] = math.log(z0)
             f.P = np.diag(np.array(self.init_std) ** 2)
+            if self.tri_pre and not f.tri_ok:  # manager.cpp:585-586: takes precedence over the simulated depths
+                f.x[2] = math.log(self.init_z)
+                f.P = np.diag(np.array(self.init_std_badtri) ** 2)
             f.status = F_INITIALIZING
             self.g_add_feature(f)
             self.g_link(f, g)
@@ -684,6 +699,21 @@ class EstimatorOracle:
             if gg.lifetime > self.max_group_lifetime and not any(self.features[fid].ref is gg for fid in self.group_adj[gg.id]):
                 self.g_remove_group(gg)
                 self.gpool.deactivate(gg)
+
+    def triangulate(self, f):
+        """Feature::Triangulate (feature.cpp:686-751) from the first and the newest observation of the track."""
+        xc1, xc2 = self.cam.unproject(f.track[0]), self.cam.unproject(f.track[-1])
+        Rbc, Tbc = self.gbc()
+        Rrc, Trc = f.ref.Rsb @ Rbc, f.ref.Rsb @ Tbc + f.ref.Tsb
+        Rsc, Tsc = self.X.Rsb @ Rbc, self.X.Rsb @ Tbc + self.X.Tsb
+        x = E.triangulate(self.tri_method, Rrc.T @ Rsc, Rrc.T @ (Tsc - Trc), xc1, xc2, self.tri_zmin, self.tri_zmax, self.tri_max_theta,
+                          self.tri_beta)
+        if x is None:
+            self.num_bad_tri += 1
+        else:
+            f.x = x
+            f.tri_ok = True
+            self.num_good_tri += 1
 
     def adapt_initial_depth(self):
         """AdaptInitialDepth (manager.cpp:255-278): the "median" is the middle element of the UNSORTED depth list, in graph order."""

@@ -100,6 +100,28 @@ void hh_subfilter_ids(void* h, int* out) {
   auto* e = static_cast<xb::Estimator*>(h);
   for (size_t i = 0; i < e->subfilter_list.size(); ++i) out[i] = e->subfilter_list[i]->id;
 }
+// the sub-filter's input states (after Feature::Triangulate where it ran): n x x(3), plus tri_ok flags
+void hh_subfilter_inputs(void* h, double* x3, int* tri_ok) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  for (size_t i = 0; i < e->subfilter_list.size(); ++i) {
+    memcpy(x3 + 3 * i, e->subfilter_list[i]->x, 24);
+    tri_ok[i] = e->subfilter_list[i]->tri_ok;
+  }
+}
+void hh_triangulation_counts(void* h, int* good_bad) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  good_bad[0] = e->num_good_triangulations; good_bad[1] = e->num_bad_triangulations;
+}
+// triangulate.h on its own: method index as in xb::TriMethod, g01 = [R(9) | T(3)]; returns 1 and x_out(3) on success
+int hh_triangulate(int method, const double* R9, const double* T3, const double* xc0, const double* xc1, double zmin, double zmax,
+                   double max_theta, double beta, double* x_out) {
+  xb::TriOptions o;
+  o.method = static_cast<xb::TriMethod>(method);
+  o.zmin = zmin; o.zmax = zmax; o.max_theta_thresh = max_theta; o.beta_thresh = beta;
+  xb::SE3h g;
+  memcpy(g.R.m, R9, 72); memcpy(g.T.v, T3, 24);
+  return xb::triangulate_feature_state(o, g, xc0, xc1, x_out) ? 1 : 0;
+}
 // out13: n x {x(3), P(9), outlier_counter}; returns the number of in-state features (the Jacobian / gate batch)
 int hh_after_subfilter(void* h, const double* out13) {
   auto* e = static_cast<xb::Estimator*>(h);

@@ -6,6 +6,7 @@ the numpy oracle (oracle/estimator_oracle.py, oracle/ekf_oracle.py, oracle/track
 import ctypes as C
 import heapq
 import json
+import math
 import os
 import shutil
 import subprocess
@@ -46,6 +47,7 @@ def hh(tmp_path_factory):
     lib.hh_push.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int]
     lib.hh_pop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hh_mask_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.hh_triangulate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.hh_mask_out.argtypes = [C.c_void_p, C.c_double, C.c_double]
     lib.hh_mask_valid.argtypes = [C.c_void_p, C.c_double, C.c_double]
     return lib
@@ -260,3 +262,63 @@ def test_tracker_mask_matches_oracle(hh, rows, cols):
     hh.hh_mask_dump(h, out.ctypes.data)
     assert np.array_equal(out, ref.m)
     hh.hh_destroy(h)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Two-view triangulation (csrc/triangulate.h) against the restatement of helpers.cpp:103-372 in oracle/ekf_oracle.py
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mi,method", list(enumerate(E.TRI_METHODS)))
+def test_triangulation_matches_the_oracle(hh, mi, method):
+    rng = np.random.default_rng(100 + mi)
+    n_ok = n_bad = 0
+    for trial in range(400):
+        # a point in front of view 0, view 1 displaced by a small motion, pixel-noise-like perturbation of both rays
+        X0 = np.array([rng.uniform(-2, 2), rng.uniform(-2, 2), rng.uniform(0.5, 12.0)])
+        R01 = E.so3_exp(rng.normal(0, 0.05, 3))
+        t01 = rng.normal(0, 0.3, 3)
+        X1 = R01.T @ (X0 - t01)
+        if X1[2] < 0.2:
+            continue
+        xc0 = X0[:2] / X0[2] + rng.normal(0, 0.004 if trial % 3 else 0.0002, 2)
+        xc1 = X1[:2] / X1[2] + rng.normal(0, 0.004 if trial % 3 else 0.0002, 2)
+        zmin, zmax = 0.05, (5.0 if trial % 2 else 60.0)
+        th, beta = math.radians(0.1 if trial % 4 else 2.0), math.radians(0.25)
+        want = E.triangulate(method, R01, t01, xc0, xc1, zmin, zmax, th, beta)
+        out = np.zeros(3)
+        ok = hh.hh_triangulate(mi, np.ascontiguousarray(R01).ctypes.data, t01.ctypes.data, np.ascontiguousarray(xc0).ctypes.data,
+                               np.ascontiguousarray(xc1).ctypes.data, C.c_double(zmin), C.c_double(zmax), C.c_double(th), C.c_double(beta), out.ctypes.data)
+        assert bool(ok) == (want is not None), f"{method} trial {trial}: acceptance differs"
+        if ok:
+            n_ok += 1
+            # rounding is amplified by 1 / sin(parallax) in the angular forms (and by the singular-value gap in L2); the DLT variants solve ill-conditioned systems at small parallax (error ~ eps / sin^2(parallax))
+            tol = 1e-10 if "angular" in method else 1e-7
+            assert np.abs(out - want).max() <= tol * max(1.0, np.abs(want).max()), f"{method} trial {trial}: {out} vs {want}"
+        else:
+            n_bad += 1
+    assert n_ok >= 40 and n_bad >= 10, (n_ok, n_bad)
+
+
+def test_triangulation_config_is_parsed_like_the_reference(hh):
+    """estimator.cpp:157-164, :356-358: method default l1_angular, degrees -> radians, a wrong method is fatal (feature.cpp:724-728)."""
+    cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
+    cfg.update({"triangulate_pre_subfilter": True, "triangulation": {"method": "no_such_method"}})
+    assert not hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0) and b"Triangulation" in hh.hh_error()
+    cfg["triangulation"] = {"zmax": 60.0}
+    h = hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0)
+    assert h, hh.hh_error()
+    hh.hh_destroy(h)
+
+
+def test_host_triangulation_on_the_reference_known_answers(hh):
+    """src/test/unittest_triangulation.cpp:18-206 through csrc/triangulate.h (fixtures shared with tests/test_oracle_ekf.py)."""
+    import test_oracle_ekf as TO
+
+    for name, xc1, z1, g21, noise, expect in TO.reference_triangulation_fixtures():
+        R12, t12, x1, x2 = TO.reference_triangulation_inputs(xc1, z1, g21, noise)
+        for mi in (2, 3, 4):  # l1, l2, linf
+            out = np.zeros(3)
+            ok = hh.hh_triangulate(mi, np.ascontiguousarray(R12).ctypes.data, t12.ctypes.data, x1.ctypes.data, x2.ctypes.data, C.c_double(0.0),
+                                   C.c_double(1e9), C.c_double(0.1 * math.pi / 180), C.c_double(0.25 * math.pi / 180), out.ctypes.data)
+            assert bool(ok) == expect, f"{name}: {E.TRI_METHODS[mi]}"
+            if expect:
+                assert abs(math.exp(out[2]) - z1) <= 0.5

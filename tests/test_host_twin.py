@@ -44,6 +44,8 @@ def hh(tmp_path_factory):
     lib.hh_pop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hh_pcw_begin.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p]
     lib.hh_subfilter_ids.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_subfilter_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hh_triangulation_counts.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_after_subfilter.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_after_gate.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_after_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -62,11 +64,12 @@ class Recorder:
     """Captures, per visual frame of the oracle, what the device computes in the product."""
 
     def __init__(self, est, monkeypatch):
-        self.est, self.sub, self.mh, self.err, self.P = est, [], [], None, None
+        self.est, self.sub, self.sub_in, self.mh, self.err, self.P = est, [], [], [], None, None
         E = EO.E
         sub0, mh0, absorb0, adapt0 = E.subfilter_update, E.mh_distance, est.absorb, est.adapt_initial_depth
 
         def sub(*a, **k):
+            self.sub_in.append(np.asarray(a[1], float).copy())  # the state the sub-filter starts from (after Feature::Triangulate)
             r = sub0(*a, **k)
             self.sub.append(np.concatenate([np.asarray(r[0], float).ravel(), np.asarray(r[1], float).ravel(), [float(r[2])]]))
             return r
@@ -89,21 +92,31 @@ class Recorder:
         est.absorb, est.adapt_initial_depth = absorb, adapt
 
     def reset(self):
-        self.sub, self.mh, self.err, self.P = [], [], None, None
+        self.sub, self.sub_in, self.mh, self.err, self.P = [], [], [], None, None
 
 
-TWIN_CASES = [(4, 14, 4.0, 1, True, "PrinceDormand"), (15, 30, 3.0, 0, True, "RK4"), (4, 14, 3.0, 6, False, "PrinceDormand"), (15, 30, 6.0, 2, True, "PrinceDormand")]
+def _tri(method, zmax=60.0, theta=0.1):  # depth triangulation before the sub-filter (manager.cpp:229-231, :585-586), as in cfg/tumvi_cam0.json:119-158
+    return {"triangulate_pre_subfilter": True, "initial_std_x_badtri": 1.0, "initial_std_y_badtri": 1.0, "initial_std_z_badtri": 1.0,
+            "triangulation": {"method": method, "zmin": 0.05, "zmax": zmax, "max_theta_thresh": theta, "beta_thesh": 0.25}}
+
+
+TWIN_CASES = [(4, 14, 4.0, 1, True, "PrinceDormand", None), (15, 30, 3.0, 0, True, "RK4", None), (4, 14, 3.0, 6, False, "PrinceDormand", None),
+              (15, 30, 6.0, 2, True, "PrinceDormand", None),
+              (4, 14, 4.0, 11, False, "PrinceDormand", _tri("l1_angular")), (15, 30, 3.0, 12, True, "PrinceDormand", _tri("l1_angular", zmax=5.0)),
+              (4, 14, 3.0, 13, False, "PrinceDormand", _tri("l2_angular")), (4, 14, 3.0, 14, False, "RK4", _tri("linf_angular")),
+              (4, 14, 3.0, 15, False, "PrinceDormand", _tri("direct_linear_transform_svd")), (4, 14, 3.0, 16, False, "PrinceDormand", _tri("direct_linear_transform_avg"))]
 # XIVO_TWIN_SWEEP=n adds n more seeds x both state sizes x with/without simulated depths (a wider offline sweep; 48 extra sequences passed at n = 12)
 for _s in range(int(os.environ.get("XIVO_TWIN_SWEEP", "0"))):
     for _g, _f in ((4, 14), (15, 30)):
         for _d in (True, False):
-            TWIN_CASES.append((_g, _f, 4.0, 100 + _s, _d, "PrinceDormand"))
+            TWIN_CASES.append((_g, _f, 4.0, 100 + _s, _d, "PrinceDormand", _tri("l1_angular") if _s % 2 else None))
 
 
-@pytest.mark.parametrize("G,F,duration,seed,sim_depths,method", TWIN_CASES)
-def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G, F, duration, seed, sim_depths, method):
+@pytest.mark.parametrize("G,F,duration,seed,sim_depths,method,over", TWIN_CASES)
+def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G, F, duration, seed, sim_depths, method, over):
     cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
     cfg["integration_method"] = method
+    cfg.update(over or {})
     msgs, _ = sim.pcw_stream(cfg, duration=duration, seed=seed)  # IMU and vision share timestamps: heap ties are exercised
     N = 23 + 6 * G + 3 * F
     est = EO.EstimatorOracle(cfg, G=G, F=F)
@@ -149,6 +162,13 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G
                 continue
             n_vis += 1
             assert nsub == len(rec.sub), f"frame {n_vis}: sub-filter batch {nsub} vs oracle {len(rec.sub)}"
+            if nsub:  # what the product uploads to the sub-filter kernel: the feature states, triangulated where the oracle triangulated
+                xin, tri_ok = np.zeros((nsub, 3)), np.zeros(nsub, np.int32)
+                hh.hh_subfilter_inputs(h, xin.ctypes.data, tri_ok.ctypes.data)
+                # the DLT forms solve a system whose conditioning is ~ 1 / sin^2(parallax of two consecutive frames): the rounding-level
+                # difference of the two nominal states is amplified accordingly
+                tol = 1e-6 if over and over["triangulation"]["method"].startswith("direct") else 1e-9
+                assert np.abs(xin - np.array(rec.sub_in)).max() <= tol, f"frame {n_vis}: sub-filter input states"
             sub = np.ascontiguousarray(np.array(rec.sub).reshape(nsub, 13)) if nsub else np.zeros((1, 13))
             ninst = hh.hh_after_subfilter(h, sub.ctypes.data)
             assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
@@ -185,4 +205,9 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G
         assert np.abs(m[:9].reshape(3, 3) - est.X.Rsb).max() <= 1e-10 and np.abs(m[9:12] - est.X.Tsb).max() <= 1e-10, f"message {k}"
         assert np.abs(m[12:15] - est.X.Vsb).max() <= 1e-10 and hh.hh_curr_time(h) == est.curr_time
     assert n_vis >= 60 and n_upd >= 50 and len(est.instate_features) >= min(F, 10)
+    gb2 = (C.c_int * 2)()
+    hh.hh_triangulation_counts(h, gb2)
+    assert (gb2[0], gb2[1]) == (est.num_good_tri, est.num_bad_tri)
+    if over:
+        assert gb2[0] >= 20 and gb2[1] >= 5, "the triangulation case must exercise both outcomes"
     hh.hh_destroy(h)

@@ -1,6 +1,8 @@
 """Pins oracle/ekf_oracle.py with the reference's own unit-test methods (finite differences,
 known answers) — src/test/unittest_jacobians_instate.cpp, unittest_camera_*.cpp,
 unittest_givens.cpp.  CPU only."""
+import math
+
 import numpy as np
 import pytest
 
@@ -144,3 +146,40 @@ def test_propagation_keeps_symmetry_and_psd():
         assert np.abs(Xc.Rsb @ Xc.Rsb.T - np.eye(3)).max() < 1e-12
         assert np.abs(Phi - np.eye(23)).max() < 0.1
         assert abs(Xc.Tsb[0] - 0.1 * 0.005) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The reference's own known-answer test of the angular triangulation methods (src/test/unittest_triangulation.cpp:18-206)
+# ------------------------------------------------------------------------------------------------------------------------
+def reference_triangulation_fixtures():
+    """(name, xc1, z1, g21 (4x4), noise on xc2, expected return value) exactly as written in unittest_triangulation.cpp."""
+    return [
+        ("Normal_Inputs", (0.4, 0.6), 5.0, [[0.9849082, 0, 0.1731, -9.8490], [0, 1, 0, 0], [-0.17310, 0, 0.98490, 1.73101], [0, 0, 0, 1]], 0.0, True),
+        ("Parallax", (2.2, 0.7), 5.0, [[0.9998, 0, 0.01745, -0.01], [0, 1, 0, 0], [-0.01745, 0, 0.9998, 0], [0, 0, 0, 1]], 0.0, False),
+        ("Cheirality", (2.0, -0.77), 5.0, [[-1, 0, 0, 3], [0, 1, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]], 0.0, False),
+        ("Angular_Reprojection_Error", (2.22216, 0.778023), 5.0, [[1, 0, 0, 3], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], 0.7, False),
+        ("Vanishing_Point", (0.2, 0.3), 6000.0, [[1, 0, 0, -0.1], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], 0.0, False),
+    ]
+
+
+def reference_triangulation_inputs(xc1, z1, g21, noise):
+    g21 = np.array(g21, float)
+    X2 = g21 @ np.array([xc1[0] * z1, xc1[1] * z1, z1, 1.0])
+    xc2 = np.array([X2[0] / X2[2] + np.float32(noise), X2[1] / X2[2] + np.float32(noise)])  # `float noise = 0.7`
+    g12 = np.linalg.inv(g21)
+    U, _, Vt = np.linalg.svd(g12[:3, :3])  # SE3::fitToSE3: nearest rotation
+    return U @ Vt, g12[:3, 3].copy(), np.array(xc1, float), xc2
+
+
+@pytest.mark.parametrize("name,xc1,z1,g21,noise,expect", reference_triangulation_fixtures(), ids=[f[0] for f in reference_triangulation_fixtures()])
+def test_reference_triangulation_known_answers(name, xc1, z1, g21, noise, expect):
+    """Thresholds of the fixture: 0.1 deg / 0.25 deg, depth within 0.5 of z1.  Angular_Reprojection_Error is the case the reference's own
+    comment (unittest_triangulation.cpp:151-153) reports as failing for L1Angular in release builds: acos(1 + ulp) = NaN bypasses the check;
+    with the clamped cosine (documented deviation) L1 is rejected as the test intends."""
+    R12, t12, x1, x2 = reference_triangulation_inputs(xc1, z1, g21, noise)
+    th, beta = np.float32(0.1 * math.pi / 180), np.float32(0.25 * math.pi / 180)
+    for fn in (E.tri_l1_angular, E.tri_l2_angular, E.tri_linf_angular):
+        ok, X = fn(R12, t12, x1, x2, th, beta)
+        assert ok == expect, f"{name}: {fn.__name__}"
+        if expect:
+            assert abs(X[2] - z1) <= 0.5

@@ -21,6 +21,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CFG = os.path.join(ROOT, "xivo_b200", "cfg", "pcw_sim.json")
 GOLD = os.path.join(ROOT, "tests", "golden", "reference_pcw.npz")
 
+def _tri(method, zmax=60.0, theta=0.1):
+    """Depth triangulation before the sub-filter (manager.cpp:229-231, :585-586; helpers.cpp:103-372), keys as in cfg/tumvi_cam0.json:119-158."""
+    return {"triangulate_pre_subfilter": True, "initial_std_x_badtri": 1.0, "initial_std_y_badtri": 1.0, "initial_std_z_badtri": 1.0,
+            "triangulation": {"method": method, "zmin": 0.05, "zmax": zmax, "max_theta_thresh": theta, "beta_thesh": 0.25}}
+
+
+# pose tolerance per case (default 1e-11): the mid-point DLT solves a 2x2 system with conditioning ~ 1 / sin^2(parallax between two consecutive
+# frames), which amplifies the rounding differences between numpy and the compiled Eigen expressions (measured 1.5e-10)
+POSE_TOL = {"tri_dltavg_89": 1e-8}
+
 CASES = [  # name, G, F, duration, seed, sim_depths, overrides, stamp offset of vision messages [ns]
     ("default_203", 15, 30, 4.0, 0, True, None, 0),
     ("small_89", 4, 14, 4.0, 1, True, None, 0),
@@ -34,6 +44,14 @@ CASES = [  # name, G, F, duration, seed, sim_depths, overrides, stamp offset of 
                                                                "cx": 254.93170605935475, "cy": 256.8974428996504, "max_iter": 15,
                                                                "k0123": [0.0034823894022493434, 0.0007150348452162257, -0.0020532361418706202, 0.00020293673591811182]},
                                                 "visual_meas_std": 1.5}, 0),
+    # triangulate_pre_subfilter (on in 7 of the reference's 8 estimator configs).  L1Angular with the shipped 0.1 deg threshold depends on
+    # acos(1 +- ulp) of compiler-contracted dot products (see oracle/ekf_oracle.py:_acos_f32), so it is pinned with a threshold the angular
+    # check cannot fail at; every other branch (ray selection, depth, cheirality, parallax, depth window, bad-triangulation prior) is exact
+    ("tri_l1_89", 4, 14, 4.0, 11, False, _tri("l1_angular", theta=90.0), 0),
+    ("tri_l2_89", 4, 14, 4.0, 12, False, _tri("l2_angular"), 1000),
+    ("tri_linf_203", 15, 30, 4.0, 13, True, _tri("linf_angular", zmax=5.0), 0),
+    ("tri_dltsvd_89", 4, 14, 4.0, 14, False, _tri("direct_linear_transform_svd"), 0),
+    ("tri_dltavg_89", 4, 14, 4.0, 15, False, _tri("direct_linear_transform_avg"), 0),
 ]
 
 
@@ -82,10 +100,13 @@ def test_oracle_reproduces_the_reference_estimator(name, G, F, duration, seed, s
     for i in range(len(gsb)):
         assert ids[i] == [int(x) for x in ref["ids"][i] if x >= 0], f"{how}: in-state feature ids differ at frame {i}"
     assert np.array_equal(gauge, ref["gauge"])
-    assert np.abs(gsb - ref["gsb"]).max() <= 1e-11, f"{how}: pose"
-    assert np.abs(est.P - ref["P"]).max() <= 1e-12 * np.abs(ref["P"]).max(), f"{how}: covariance"
+    assert np.abs(gsb - ref["gsb"]).max() <= POSE_TOL.get(name, 1e-11), f"{how}: pose"
+    assert np.abs(est.P - ref["P"]).max() <= 1e3 * POSE_TOL.get(name, 1e-15) * np.abs(ref["P"]).max(), f"{how}: covariance"
+    if name.startswith("tri_"):
+        assert est.num_good_tri >= 20 and est.num_bad_tri >= 5, "both outcomes of Feature::Triangulate must occur"
     assert ref["n_instate"][-1] >= min(F, 10) and (ref["n_instate"] > 0).sum() >= 60  # a filter that is actually updating
-    if sim_depths:  # metric scale is observable -> the reference (and we) track the analytic ground truth
+    if sim_depths and not name.startswith("tri_"):  # metric scale is observable -> the reference (and we) track the analytic ground truth
+        # (with triangulate_pre_subfilter every new feature starts from the bad-triangulation prior, manager.cpp:585-586: the simulated depths are unused)
         assert np.linalg.norm(gsb[-1][:, 3] - traj.pos(float(ts[-1]) * 1e-9)) < 0.05
 
 

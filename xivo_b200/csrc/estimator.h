@@ -27,6 +27,7 @@
 #include "hostmath.h"
 #include "json.h"
 #include "kernels.h"
+#include "triangulate.h"
 
 namespace xb {
 
@@ -74,15 +75,18 @@ struct Feature {
   double outlier_counter = 0;
   bool tri_ok = false;
   float response = 0.f;
-  // Track: only the newest pixel observation is ever read on this path (the full history feeds the
-  // OOS update / triangulation, out of scope), so the track is its back() and its length.
-  std::array<double, 2> last_xp{{0, 0}};
+  // Track: only front() (two-view triangulation), back() and the length are ever read on this path (the full
+  // history feeds the OOS update, out of scope).
+  std::array<double, 2> first_xp{{0, 0}}, last_xp{{0, 0}};
   int track_len = 0;
   std::vector<int> adj;  // ids of the groups that saw this feature (FeatureAdj keys), ascending
   V3 Xs{{0, 0, 0}};
   bool instate() const { return status == FeatureStatus::INSTATE || status == FeatureStatus::GAUGE; }
   const std::array<double, 2>& xp() const { return last_xp; }
-  void observe(double u, double v) { last_xp = {u, v}; ++track_len; }
+  void observe(double u, double v) {
+    last_xp = {u, v};
+    if (track_len++ == 0) first_xp = last_xp;
+  }
   void reset(int new_id, double u, double v) {  // Feature::Create/Reset (feature.cpp:43-91); keeps slot + capacity
     id = new_id; sind = -1; lifetime = 0; init_counter = 0;
     status = FeatureStatus::CREATED; tstatus = TrackStatus::CREATED;
@@ -255,8 +259,8 @@ struct EstimatorCfg {
   double max_accel[3] = {0, 0, 0}, max_gyro[3] = {0, 0, 0};
   double sub_Rtri = 3.5 * 3.5, sub_mh = 5.991;
   int sub_ready_steps = 5;
-  bool triangulate_pre_subfilter = false;
-  double tri_zmin = 0.05, tri_zmax = 5.0;
+  bool triangulate_pre_subfilter = false;  // Feature::Triangulate on a feature's second observation (manager.cpp:229-231)
+  TriOptions tri;
   double adapt_weight = 0.99;
   int adapt_min_lifetime = 5;
   int remove_outlier_counter = 10, group_degrees_fixed = 4, max_group_lifetime = 1;
@@ -265,7 +269,7 @@ struct EstimatorCfg {
   double Qmodel[529] = {0}, Qimu[144] = {0};
   double R = 1, Roos = 1;
   double init_z = 1, init_std_x = 1, init_std_y = 1, init_std_z = 1, min_z = 0.05, max_z = 5;
-  double init_std_x_badtri = 1, init_std_y_badtri = 1, init_std_z_badtri = 1;
+  double init_std_x_badtri = 0, init_std_y_badtri = 0, init_std_z_badtri = 0;  // jsoncpp: a missing number reads as 0 (estimator.cpp:356-358)
   bool use_MH_gating = true;
   int min_inliers = 5;
   double MH_thresh = 5.991, MH_mult = 1.1;
@@ -353,6 +357,7 @@ class Estimator {
   int mask_half = -1;  // MaskOut's function-local static (tracker.cpp:763)
   int rows = 0, cols = 0;
   int num_failed_to_track = 0, num_new_detections = 0, num_mh_rejected = 0;
+  int num_good_triangulations = 0, num_bad_triangulations = 0;  // Feature::num_good/bad_triangulations_ (feature.cpp:730-748)
   // time / imu (src/estimator.cpp)
   bool gravity_initialized = false, vision_initialized = false, meas_update_initialized = false;
   int gravity_init_counter = 0, imu_counter = 0, vision_counter = 0;
@@ -410,6 +415,7 @@ class Estimator {
   V3 feature_Xs(Feature* f, M3* J = nullptr) const;
   bool change_owner(Feature* f, Group* nref);
   void feature_initialize(Feature* f, double z0, double sx, double sy, double sz);
+  void triangulate_feature(Feature* f);
 };
 
 }  // namespace xb
