@@ -11,6 +11,7 @@
 #ifndef XIVO_B200_HPP_
 #define XIVO_B200_HPP_
 
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cstdint>
@@ -117,13 +118,64 @@ class Estimator {
   int num_tracker_new_detections() const { return counters()[5]; }
   void InitWithSimDepths() { check(xivo_init_with_sim_depths(b_)); }
 
-  std::vector<int> InstateFeatureIDs() const { return instate_features().ids; }
-  std::vector<int> InstateFeatureSinds() const { return instate_features().sinds; }
-  std::vector<int> InstateFeatureRefGroups() const { return instate_features().refs; }
-  std::vector<double> InstateFeaturePositions() const { return instate_features().Xs; }  // n x 3
-  std::vector<int> InstateGroupIDs() const { return instate_groups().ids; }
-  std::vector<int> InstateGroupSinds() const { return instate_groups().sinds; }
-  std::vector<double> InstateGroupPoses() const { return instate_groups().gsb; }  // n x 12 (3x4 row-major each)
+  // Per-feature accessors, both overloads of src/estimator_accessors.cpp (row-major flat vectors instead of Eigen MatX*).
+  // No argument: the features of the last update.  (int n_output): every in-state feature sorted by the norm of its covariance
+  // block; like the reference the result has max(count, n_output) rows of which the first min(count, n_output) are filled
+  // (the rest is uninitialised there and zero here).
+  std::vector<int> InstateFeatureIDs() const { return feature_table(-1).ids; }
+  std::vector<int> InstateFeatureIDs(int n) const { return pad(feature_table(n).ids, 1, n); }
+  std::vector<int> InstateFeatureSinds() const { return feature_table(-1).sinds; }
+  std::vector<int> InstateFeatureSinds(int n) const { return pad(feature_table(n).sinds, 1, n); }
+  std::vector<int> InstateFeatureRefGroups() const { return feature_table(-1).refs; }
+  std::vector<int> InstateFeatureRefGroups(int n) const { return pad(feature_table(n).refs, 1, n); }
+  std::vector<double> InstateFeaturePositions() const { return feature_table(-1).Xs; }  // n x 3
+  std::vector<double> InstateFeaturePositions(int n) const { return pad(feature_table(n).Xs, 3, n); }
+  std::vector<double> InstateFeatureXc() const { return feature_table(-1).Xc; }  // n x 3
+  std::vector<double> InstateFeatureXc(int n) const { return pad(feature_table(n).Xc, 3, n); }
+  std::vector<double> InstateFeaturexc() const { return feature_table(-1).xc; }  // n x 3
+  std::vector<double> InstateFeaturexc(int n) const { return pad(feature_table(n).xc, 3, n); }
+  std::vector<double> InstateFeaturePreds() const { return feature_table(-1).pred; }  // n x 2
+  std::vector<double> InstateFeaturePreds(int n) const { return pad(feature_table(n).pred, 2, n); }
+  std::vector<double> InstateFeatureMeas() const { return feature_table(-1).meas; }  // n x 2
+  std::vector<double> InstateFeatureMeas(int n) const { return pad(feature_table(n).meas, 2, n); }
+  std::vector<double> InstateFeatureCovs() const { return feature_table(-1).cov; }  // n x 6: (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+  std::vector<double> InstateFeatureCovs(int n) const { return pad(feature_table(n).cov, 6, n); }
+  std::vector<int> InstateGroupIDs() const { return group_table().ids; }
+  std::vector<int> InstateGroupSinds() const { return group_table().sinds; }
+  std::vector<double> InstateGroupPoses() const { return group_table().pose; }  // n x 7: qx qy qz qw Tx Ty Tz (MatX7)
+  // n x 21 exactly as the reference fills it: its column counter restarts in every row of the 6x6 block, so columns 0..5 end
+  // up as cov(5,5) cov(4,5) cov(3,5) cov(2,5) cov(1,5) cov(0,5) and columns 6..20 are never written (zero here).
+  std::vector<double> InstateGroupCovs() const {
+    const GroupTable g = group_table();
+    const size_t n = g.ids.size();
+    std::vector<double> out(21 * n, 0.0);
+    for (size_t i = 0; i < n; ++i)
+      for (int ii = 0; ii < 6; ++ii)
+        for (int jj = ii, cnt = 0; jj < 6; ++jj, ++cnt) out[21 * i + cnt] = g.cov[36 * i + 6 * ii + jj];
+    return out;
+  }
+  std::vector<double> InstateGroupCovBlocks() const { return group_table().cov; }  // n x 36: the full blocks (not in the reference)
+  std::vector<int> JustDroppedFeatureIDs() const {
+    std::vector<int> ids(kMaxTracks);
+    int n = 0;
+    check(xivo_get_just_dropped(b_, 0, ids.data(), kMaxTracks, &n));
+    ids.resize(std::min(n, kMaxTracks));
+    return ids;
+  }
+  double td() const { double t = 0; check(xivo_get_calibration(b_, 0, nullptr, nullptr, &t, nullptr, nullptr)); return t; }
+  Mat3 Ca() const { Mat3 m; check(xivo_get_calibration(b_, 0, m.data(), nullptr, nullptr, nullptr, nullptr)); return m; }
+  Mat3 Cg() const { Mat3 m; check(xivo_get_calibration(b_, 0, nullptr, m.data(), nullptr, nullptr, nullptr)); return m; }
+  std::array<double, 9> CameraIntrinsics() const {  // fx fy cx cy k0 k1 k2 k3 0 (pybind11/pyxivo.cpp:285-287)
+    std::array<double, 9> v;
+    check(xivo_get_calibration(b_, 0, nullptr, nullptr, nullptr, v.data(), nullptr));
+    return v;
+  }
+  int CameraDistortionType() const { int t = 0; check(xivo_get_calibration(b_, 0, nullptr, nullptr, nullptr, nullptr, &t)); return t; }
+  void ScaleInitVelocity(double scale) { check(xivo_scale_init_velocity(b_, 0, scale)); }
+  int num_tracker_outlier_rejected() const { return tracker_counters()[0]; }
+  int num_oneptransac_rejected() const { return tracker_counters()[3]; }
+  bool UsingLoopClosure() const { return false; }  // USE_MAPPER is off in the reference's default build
+  void CloseLoop() {}
 
   // tracked_features_no_descriptor(): (id, last pixel position) per live track
   std::vector<std::tuple<int, Vec2>> tracked_features_no_descriptor() const {
@@ -144,6 +196,8 @@ class Estimator {
   struct Motion { Vec3 v, bg, ba; Mat3 rsg; };
   struct Features { std::vector<int> ids, sinds, refs; std::vector<double> Xs, x; };
   struct Groups { std::vector<int> ids, sinds; std::vector<double> gsb; };
+  struct FeatureTable { std::vector<int> ids, sinds, refs; std::vector<double> Xs, Xc, xc, pred, meas, cov; };
+  struct GroupTable { std::vector<int> ids, sinds; std::vector<double> pose, cov; };
 
   void check(int rc) const {
     if (rc) throw Error(rc, xivo_last_error());
@@ -179,6 +233,42 @@ class Estimator {
     check(xivo_get_instate_features(b_, 0, f.ids.data(), f.sinds.data(), f.refs.data(), f.Xs.data(), f.x.data(), cap, &n));
     f.ids.resize(n); f.sinds.resize(n); f.refs.resize(n); f.Xs.resize(3 * (size_t)n); f.x.resize(3 * (size_t)n);
     return f;
+  }
+  FeatureTable feature_table(int n_output) const {
+    const int cap = state_dim();
+    FeatureTable t;
+    t.ids.resize(cap); t.sinds.resize(cap); t.refs.resize(cap);
+    t.Xs.resize(3 * (size_t)cap); t.Xc.resize(3 * (size_t)cap); t.xc.resize(3 * (size_t)cap);
+    t.pred.resize(2 * (size_t)cap); t.meas.resize(2 * (size_t)cap); t.cov.resize(6 * (size_t)cap);
+    int n = 0;
+    check(xivo_get_instate_feature_table(b_, 0, n_output, t.ids.data(), t.sinds.data(), t.refs.data(), t.Xs.data(), t.Xc.data(), t.xc.data(),
+                                         t.pred.data(), t.meas.data(), t.cov.data(), cap, &n));
+    t.ids.resize(n); t.sinds.resize(n); t.refs.resize(n);
+    t.Xs.resize(3 * (size_t)n); t.Xc.resize(3 * (size_t)n); t.xc.resize(3 * (size_t)n);
+    t.pred.resize(2 * (size_t)n); t.meas.resize(2 * (size_t)n); t.cov.resize(6 * (size_t)n);
+    return t;
+  }
+  // rows of the (int n_output) overloads: max(number of in-state features, n_output)
+  template <typename T>
+  std::vector<T> pad(std::vector<T> v, int width, int n_output) const {
+    int count = 0;
+    check(xivo_get_instate_feature_table(b_, 0, 1 << 20, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &count));
+    v.resize((size_t)width * std::max(count, n_output), T(0));
+    return v;
+  }
+  GroupTable group_table() const {
+    const int cap = state_dim();
+    GroupTable g;
+    g.ids.resize(cap); g.sinds.resize(cap); g.pose.resize(7 * (size_t)cap); g.cov.resize(36 * (size_t)cap);
+    int n = 0;
+    check(xivo_get_instate_group_table(b_, 0, g.ids.data(), g.sinds.data(), g.pose.data(), g.cov.data(), cap, &n));
+    g.ids.resize(n); g.sinds.resize(n); g.pose.resize(7 * (size_t)n); g.cov.resize(36 * (size_t)n);
+    return g;
+  }
+  std::array<int, 4> tracker_counters() const {
+    std::array<int, 4> c;
+    check(xivo_get_tracker_counters(b_, 0, c.data()));
+    return c;
   }
   Groups instate_groups() const {
     const int cap = state_dim();

@@ -97,6 +97,24 @@ int xivo_get_instate_features(xivo_batch* b, int seq, int* ids, int* sinds, int*
                               double* x3, int max_n, int* n);
 /* InstateGroupIDs/Sinds/Poses (3x4 row-major each). */
 int xivo_get_instate_groups(xivo_batch* b, int seq, int* ids, int* sinds, double* gsb12, int max_n, int* n);
+/* The per-feature accessors of src/estimator_accessors.cpp in one call (any output pointer may be NULL):
+ * InstateFeature{IDs, Sinds, RefGroups, Positions (cached Xs), Xc, xc, Preds, Meas, Covs (upper triangle of the 3x3 block)}.
+ * n_output < 0: the no-argument overloads (the features of the last update; slot order here, raw-pointer order in the reference);
+ * n_output >= 0: the (int n_output) overloads: every in-state feature of the graph sorted by the Frobenius norm of its covariance
+ * block (FeatureCovComparison, src/estimator.cpp:1451-1455), the first min(count, n_output) rows.  *n = rows available. */
+int xivo_get_instate_feature_table(xivo_batch* b, int seq, int n_output, int* ids, int* sinds, int* ref_group_ids, double* Xs3,
+                                   double* Xc3, double* xc3, double* pred2, double* meas2, double* cov6, int max_n, int* n);
+/* InstateGroup{IDs, Sinds, Poses, Covs}: the in-state groups as the last update saw them (Graph::GetInstateGroups order);
+ * pose7 = qx qy qz qw Tx Ty Tz per group (MatX7, estimator_accessors.cpp), cov36 = the full 6x6 block of P row-major (the reference's
+ * InstateGroupCovs keeps six entries of it, see xivo_b200/pyxivo.py). */
+int xivo_get_instate_group_table(xivo_batch* b, int seq, int* ids, int* sinds, double* pose7, double* cov36, int max_n, int* n);
+/* Estimator::Ca / Cg / td (src/estimator.h:173-175) and Camera GetIntrinsics / GetDistortionType (pybind11/pyxivo.cpp:285-291):
+ * Ca9, Cg9 row-major; intrinsics9 = fx fy cx cy k0 k1 k2 k3 0; distortion_type 0 pinhole, 3 equidistant. */
+int xivo_get_calibration(xivo_batch* b, int seq, double* Ca9, double* Cg9, double* td, double* intrinsics9, int* distortion_type);
+int xivo_get_just_dropped(xivo_batch* b, int seq, int* ids, int max_n, int* n); /* Estimator::JustDroppedFeatureIDs */
+/* {num_tracker_outlier_rejected, num_tracker_failed_to_track, num_tracker_new_detections, num_oneptransac_rejected} */
+int xivo_get_tracker_counters(xivo_batch* b, int seq, int out[4]);
+int xivo_scale_init_velocity(xivo_batch* b, int seq, double scale); /* Estimator::ScaleInitVelocity: Vsb /= scale */
 int xivo_init_with_sim_depths(xivo_batch* b); /* Estimator::InitWithSimDepths */
 const char* xivo_batch_error(xivo_batch* b, int seq);
 

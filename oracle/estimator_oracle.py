@@ -690,7 +690,7 @@ class EstimatorOracle:
             self.g_add_feature(f)
             self.g_link(f, g)
             self.tracks.append(f)
-        for f in self.feats(lambda f: f.tstatus == TRACKED):
+        for f in self.feats_std(lambda f: f.tstatus == TRACKED):  # AssociateTrackedFeaturesWithGroup: GetFeaturesIf order (manager.cpp:608-610)
             self.g_link(f, g)
             self.tracks.append(f)
         self.adapt_initial_depth()

@@ -64,8 +64,52 @@ def run(cfg: dict, msgs, G: int, F: int, sim_depths: bool = True, lib_file: str 
     P = np.zeros((N, N))
     L.ref_P(P.ctypes.data_as(C.c_void_p))
     out["P"] = P
+    if hasattr(L, "ref_feature_table"):
+        out["acc"] = accessor_dump(L)
     out["gsb"], out["ts"], out["vel"] = np.array(out["gsb"]), np.array(out["ts"], dtype=np.uint64), np.array(out["vel"])
     out["n_instate"], out["gauge"] = np.array(out["n_instate"]), np.array(out["gauge"])
+    return out
+
+
+def accessor_dump(L) -> dict:
+    """The read-back surface of pybind11/pyxivo.cpp:332-398 as the reference returns it right now (boundary-parity fixtures):
+    per-feature tables through the no-argument overloads (`all.*`) and the (int n_output) overloads for n = 5 and n = 50
+    (`top5.*`, `top50.*`; only the rows the reference initialises), group tables, calibration, counters."""
+    out = {}
+    M = 256
+    ids, sinds, refs = (C.c_int * M)(), (C.c_int * M)(), (C.c_int * M)()
+    bufs = {k: np.zeros((M, w)) for k, w in (("Xs", 3), ("Xc", 3), ("xc", 3), ("pred", 2), ("meas", 2), ("cov", 6))}
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def table(n_output):
+        rows = L.ref_feature_table(n_output, ids, sinds, refs, ptr(bufs["Xs"]), ptr(bufs["Xc"]), ptr(bufs["xc"]), ptr(bufs["pred"]), ptr(bufs["meas"]), ptr(bufs["cov"]), M)
+        return rows
+
+    count = table(0)  # max(#in-state features in the graph, 0)
+    for tag, n in (("all", -1), ("top5", 5), ("top50", 50)):
+        rows = table(n)
+        k = rows if n < 0 else min(n, count)
+        out[f"{tag}.rows"] = np.array(rows)
+        out[f"{tag}.ids"], out[f"{tag}.sinds"], out[f"{tag}.refs"] = np.array(ids[:k]), np.array(sinds[:k]), np.array(refs[:k])
+        for name, b in bufs.items():
+            out[f"{tag}.{name}"] = b[:k].copy()
+    gid, gs, pose, cov = (C.c_int * 64)(), (C.c_int * 64)(), np.zeros((64, 7)), np.zeros((64, 21))
+    ng = L.ref_group_table(gid, gs, ptr(pose), ptr(cov), 64)
+    out["groups.ids"], out["groups.sinds"], out["groups.pose"] = np.array(gid[:ng]), np.array(gs[:ng]), pose[:ng].copy()
+    out["groups.cov6"] = cov[:ng, :6].copy()  # the reference initialises only the first six columns (estimator_accessors.cpp, `cnt = 0` inside the row loop)
+    Ca, Cg, Rsg, intr, Ps, td, dt = np.zeros(9), np.zeros(9), np.zeros(9), np.zeros(9), np.zeros(81), C.c_double(), C.c_int()
+    L.ref_calibration(ptr(Ca), ptr(Cg), C.byref(td), ptr(Rsg), ptr(intr), C.byref(dt), ptr(Ps))
+    out.update({"Ca": Ca.reshape(3, 3), "Cg": Cg.reshape(3, 3), "td": np.array(td.value), "Rsg": Rsg.reshape(3, 3), "intrinsics": intr,
+                "distortion_type": np.array(dt.value), "Pstate": Ps.reshape(9, 9)})
+    jd = (C.c_int * 512)()
+    nj = L.ref_just_dropped(jd, 512)
+    out["just_dropped"] = np.array(jd[:nj], dtype=np.int64)
+    tc = (C.c_int * 4)()
+    L.ref_tracker_counters(tc)
+    out["tracker_counters"] = np.array(tc[:])
+    tid, txy = (C.c_int * 1024)(), np.zeros((1024, 2))
+    nt = L.ref_tracked_features(tid, ptr(txy), 1024)
+    out["tracked.ids"], out["tracked.xy"] = np.array(tid[:nt]), txy[:nt].copy()
     return out
 
 
@@ -86,8 +130,9 @@ def _main():
     ids = np.full((len(r["ids"]), max(1, max(len(x) for x in r["ids"]))), -1, dtype=np.int64)
     for i, x in enumerate(r["ids"]):
         ids[i, : len(x)] = x
+    acc = {"acc." + k: v for k, v in r.get("acc", {}).items()}
     np.savez_compressed(outp, gsb=r["gsb"], ts=r["ts"], n_instate=r["n_instate"], gauge=r["gauge"], ids=ids, P=r["P"], vel=r["vel"],
-                        truth=np.array([traj.pos(t * 1e-9) for t in r["ts"]]))
+                        truth=np.array([traj.pos(t * 1e-9) for t in r["ts"]]), **acc)
 
 
 def run_subprocess(cfg_path, G, F, duration, seed, sim_depths, out_npz, overrides=None, pc_offset_ns=0):

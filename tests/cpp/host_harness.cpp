@@ -168,6 +168,32 @@ int hh_groups(void* h, int* out3, int max_n, int* gauge) {
   }
   return n;
 }
+// read-back tables (estimator_accessors.cpp) from a host copy of P; flat rows of doubles:
+// feature: id, sind, ref group id, Xs(3), Xc(3), xc(3), pred(2), meas(2), cov(6) = 22;  group: id, sind, pose(7), cov(36) = 45
+int hh_feature_rows(void* h, const double* P, int n_output, double* out22, int max_rows) {
+  const auto rows = static_cast<xb::Estimator*>(h)->instate_feature_rows(P, n_output);
+  for (size_t i = 0; i < rows.size() && (int)i < max_rows; ++i) {
+    double* o = out22 + 22 * i;
+    o[0] = rows[i].id; o[1] = rows[i].sind; o[2] = rows[i].ref_group_id;
+    memcpy(o + 3, rows[i].Xs, 24); memcpy(o + 6, rows[i].Xc, 24); memcpy(o + 9, rows[i].xc, 24);
+    memcpy(o + 12, rows[i].pred, 16); memcpy(o + 14, rows[i].meas, 16); memcpy(o + 16, rows[i].cov, 48);
+  }
+  return (int)rows.size();
+}
+int hh_group_rows(void* h, const double* P, double* out45, int max_rows) {
+  const auto rows = static_cast<xb::Estimator*>(h)->instate_group_rows(P);
+  for (size_t i = 0; i < rows.size() && (int)i < max_rows; ++i) {
+    double* o = out45 + 45 * i;
+    o[0] = rows[i].id; o[1] = rows[i].sind;
+    memcpy(o + 2, rows[i].pose, 56); memcpy(o + 9, rows[i].cov, 288);
+  }
+  return (int)rows.size();
+}
+int hh_just_dropped(void* h, int* out, int max_n) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  for (size_t i = 0; i < e->just_dropped_ids.size() && (int)i < max_n; ++i) out[i] = e->just_dropped_ids[i];
+  return (int)e->just_dropped_ids.size();
+}
 const char* hh_error_msg(void* h) { return static_cast<xb::Estimator*>(h)->error_msg.c_str(); }
 
 // tracker mask (tracker.cpp:471-488, :760-774)

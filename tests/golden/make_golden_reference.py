@@ -19,5 +19,9 @@ with tempfile.TemporaryDirectory() as td:
         d = ref_runner.run_subprocess(CFG, G, F, duration, seed, sim_depths, os.path.join(td, name + ".npz"), overrides=over, pc_offset_ns=offset)
         for k in ("gsb", "ts", "n_instate", "gauge", "ids", "P"):
             out[f"{name}.{k}"] = d[k]
+        if name in ("small_89", "default_203"):  # the reference's read-back accessors at the end of the run (boundary-parity fixtures)
+            for k in d.files:
+                if k.startswith("acc."):
+                    out[f"{name}.{k}"] = d[k]
         print(name, d["gsb"].shape, int(d["n_instate"][-1]), np.round(d["gsb"][-1][:, 3] - d["truth"][-1], 4))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference_pcw.npz"), **out)

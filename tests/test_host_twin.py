@@ -46,6 +46,9 @@ def hh(tmp_path_factory):
     lib.hh_subfilter_ids.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_subfilter_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hh_triangulation_counts.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_feature_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.hh_group_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.hh_just_dropped.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.hh_after_subfilter.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_after_gate.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_after_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -101,7 +104,7 @@ def _tri(method, zmax=60.0, theta=0.1):  # depth triangulation before the sub-fi
 
 
 TWIN_CASES = [(4, 14, 4.0, 1, True, "PrinceDormand", None), (15, 30, 3.0, 0, True, "RK4", None), (4, 14, 3.0, 6, False, "PrinceDormand", None),
-              (15, 30, 6.0, 2, True, "PrinceDormand", None),
+              (15, 30, 6.0, 2, True, "PrinceDormand", None), (15, 30, 4.0, 0, True, "PrinceDormand", None),
               (4, 14, 4.0, 11, False, "PrinceDormand", _tri("l1_angular")), (15, 30, 3.0, 12, True, "PrinceDormand", _tri("l1_angular", zmax=5.0)),
               (4, 14, 3.0, 13, False, "PrinceDormand", _tri("l2_angular")), (4, 14, 3.0, 14, False, "RK4", _tri("linf_angular")),
               (4, 14, 3.0, 15, False, "PrinceDormand", _tri("direct_linear_transform_svd")), (4, 14, 3.0, 16, False, "PrinceDormand", _tri("direct_linear_transform_avg"))]
@@ -113,7 +116,7 @@ for _s in range(int(os.environ.get("XIVO_TWIN_SWEEP", "0"))):
 
 
 @pytest.mark.parametrize("G,F,duration,seed,sim_depths,method,over", TWIN_CASES)
-def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G, F, duration, seed, sim_depths, method, over):
+def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, tmp_path, G, F, duration, seed, sim_depths, method, over):
     cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
     cfg["integration_method"] = method
     cfg.update(over or {})
@@ -210,4 +213,55 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, G
     assert (gb2[0], gb2[1]) == (est.num_good_tri, est.num_bad_tri)
     if over:
         assert gb2[0] >= 20 and gb2[1] >= 5, "the triangulation case must exercise both outcomes"
+    check_read_back_against_the_reference(hh, h, est, G, F, duration, seed, sim_depths, method, over, tmp_path)
     hh.hh_destroy(h)
+
+
+# twin cases that are also pinned sequences of tests/test_reference_pin.py: (G, F, duration, seed, sim_depths, method) -> case name
+PINNED = {(4, 14, 4.0, 1, True, "PrinceDormand"): "small_89", (15, 30, 4.0, 0, True, "PrinceDormand"): "default_203"}
+
+
+def check_read_back_against_the_reference(hh, h, est, G, F, duration, seed, sim_depths, method, over, tmp_path):
+    """Drop-in boundary: the host's read-back tables (csrc/estimator_host.cpp.inc: instate_feature_rows / instate_group_rows, what the
+    C ABI's xivo_get_instate_feature_table / xivo_get_instate_group_table return) against what the REFERENCE'S OWN accessors
+    (src/estimator_accessors.cpp through oracle/ref_wrap.cpp; golden copy in tests/golden/reference_pcw.npz) return at the end of
+    the same sequence: InstateFeature{IDs,Sinds,RefGroups,Positions,Xc,xc,Preds,Meas,Covs} in both overloads (as-updated order, and
+    sorted by covariance norm for n = 5 and n = 50), InstateGroup{IDs,Sinds,Poses,Covs}, JustDroppedFeatureIDs."""
+    name = PINNED.get((G, F, duration, seed, sim_depths, method)) if not over else None
+    if name is None:
+        return
+    import test_reference_pin as RP
+
+    ref, how = RP.reference_result(name, None, G, F, duration, seed, sim_depths, 0, tmp_path)
+    assert "acc.all.ids" in ref, f"{how}: no accessor dump (rebuild oracle/_ref or regenerate the golden file)"
+    P = np.ascontiguousarray(est.P)
+    buf = np.zeros((64, 22))
+    for tag, n in (("all", -1), ("top5", 5), ("top50", 50)):
+        k = hh.hh_feature_rows(h, P.ctypes.data, n, buf.ctypes.data, 64)
+        want_ids = ref[f"acc.{tag}.ids"]
+        assert k == len(want_ids)
+        if n < 0:
+            # `instate_features_` order: the reference sorts raw POINTERS (MakePtrVectorUnique, helpers.h:36-39) of separately
+            # allocated pool objects, so its order changes from run to run of the same binary (observed); ours is slot order.
+            # Same rows, matched by id.
+            assert sorted(buf[:k, 0].astype(int).tolist()) == sorted(want_ids.tolist()), f"{how} {tag}: rows of the feature table"
+            perm = [want_ids.tolist().index(i) for i in buf[:k, 0].astype(int)]
+        else:
+            assert buf[:k, 0].astype(int).tolist() == want_ids.tolist(), f"{how} {tag}: order of the feature table (sorted by covariance norm)"
+            perm = list(range(k))
+        assert buf[:k, 1].astype(int).tolist() == ref[f"acc.{tag}.sinds"][perm].tolist() and buf[:k, 2].astype(int).tolist() == ref[f"acc.{tag}.refs"][perm].tolist()
+        for col, key, w in ((3, "Xs", 3), (6, "Xc", 3), (9, "xc", 3), (12, "pred", 2), (14, "meas", 2), (16, "cov", 6)):
+            assert np.abs(buf[:k, col:col + w] - ref[f"acc.{tag}.{key}"][perm]).max() <= 1e-9, f"{how} {tag}.{key}"
+    gbuf = np.zeros((32, 45))
+    ng = hh.hh_group_rows(h, P.ctypes.data, gbuf.ctypes.data, 32)
+    assert gbuf[:ng, 0].astype(int).tolist() == ref["acc.groups.ids"].tolist() and gbuf[:ng, 1].astype(int).tolist() == ref["acc.groups.sinds"].tolist()
+    assert np.abs(gbuf[:ng, 2:9] - ref["acc.groups.pose"]).max() <= 1e-9
+    cov = gbuf[:ng, 9:].reshape(ng, 6, 6)
+    # the reference's InstateGroupCovs resets its column counter inside the row loop: only columns 0..5 are written, ending as
+    # cov(5,5), cov(4,5), cov(3,5), cov(2,5), cov(1,5), cov(0,5) (pyxivo.Estimator.InstateGroupCovs reproduces exactly that)
+    assert np.abs(cov[:, ::-1, 5] - ref["acc.groups.cov6"]).max() <= 1e-12
+    tr = feats(hh, h, 2)  # tracked_features_no_descriptor(): Tracker::features_ order
+    assert tr[:, 0].tolist() == ref["acc.tracked.ids"].tolist(), f"{how}: tracker list order"
+    jd = (C.c_int * 512)()
+    nj = hh.hh_just_dropped(h, jd, 512)
+    assert sorted(jd[:nj]) == sorted(ref["acc.just_dropped"].tolist())

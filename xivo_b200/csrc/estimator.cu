@@ -1057,6 +1057,89 @@ int xivo_get_instate_groups(xivo_batch* b, int seq, int* ids, int* sinds, double
   *n = k;
   return 0;
 }
+// ---- the rest of the reference's read-back surface (estimator.h:153-231, estimator_accessors.cpp) -------------------------
+static int fetch_P(Batch& B_, int seq, std::vector<double>* P) {
+  P->resize((size_t)B_.N * B_.N);
+  if (int rc = B_.flush({seq})) return rc;
+  XB_CUDA(cudaMemcpy(P->data(), B_.dP + (size_t)seq * B_.N * B_.N, sizeof(double) * B_.N * B_.N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int xivo_get_instate_feature_table(xivo_batch* b, int seq, int n_output, int* ids, int* sinds, int* ref_group_ids, double* Xs3, double* Xc3,
+                                   double* xc3, double* pred2, double* meas2, double* cov6, int max_n, int* n) {
+  BATCH_BEGIN; SEQ_CHECK;
+  XB_REQUIRE(n, "get_instate_feature_table: null count");
+  std::vector<double> P;
+  if (int rc = fetch_P(B_, seq, &P)) return rc;
+  const std::vector<FeatureRow> rows = B_.est[seq]->instate_feature_rows(P.data(), n_output);
+  for (size_t i = 0; i < rows.size() && (int)i < max_n; ++i) {
+    const FeatureRow& r = rows[i];
+    if (ids) ids[i] = r.id;
+    if (sinds) sinds[i] = r.sind;
+    if (ref_group_ids) ref_group_ids[i] = r.ref_group_id;
+    if (Xs3) memcpy(Xs3 + 3 * i, r.Xs, 24);
+    if (Xc3) memcpy(Xc3 + 3 * i, r.Xc, 24);
+    if (xc3) memcpy(xc3 + 3 * i, r.xc, 24);
+    if (pred2) memcpy(pred2 + 2 * i, r.pred, 16);
+    if (meas2) memcpy(meas2 + 2 * i, r.meas, 16);
+    if (cov6) memcpy(cov6 + 6 * i, r.cov, 48);
+  }
+  *n = (int)rows.size();
+  return 0;
+}
+int xivo_get_instate_group_table(xivo_batch* b, int seq, int* ids, int* sinds, double* pose7, double* cov36, int max_n, int* n) {
+  BATCH_BEGIN; SEQ_CHECK;
+  XB_REQUIRE(n, "get_instate_group_table: null count");
+  std::vector<double> P;
+  if (int rc = fetch_P(B_, seq, &P)) return rc;
+  const std::vector<GroupRow> rows = B_.est[seq]->instate_group_rows(P.data());
+  for (size_t i = 0; i < rows.size() && (int)i < max_n; ++i) {
+    if (ids) ids[i] = rows[i].id;
+    if (sinds) sinds[i] = rows[i].sind;
+    if (pose7) memcpy(pose7 + 7 * i, rows[i].pose, 56);
+    if (cov36) memcpy(cov36 + 36 * i, rows[i].cov, 288);
+  }
+  *n = (int)rows.size();
+  return 0;
+}
+int xivo_get_calibration(xivo_batch* b, int seq, double* Ca9, double* Cg9, double* td, double* intrinsics9, int* distortion_type) {
+  BATCH_BEGIN; SEQ_CHECK;
+  const Estimator& e = *B_.est[seq];
+  if (Ca9) memcpy(Ca9, e.c.Ca.m, 72);
+  if (Cg9) memcpy(Cg9, e.c.Cg.m, 72);
+  if (td) *td = e.X.td;
+  if (intrinsics9) {  // BaseCamera::GetIntrinsics (camera_base.h:65-69), EquidistantCamera::GetIntrinsics (camera_equidist.h:169-173)
+    const CameraParams& k = e.cam;
+    const double v[9] = {k.fx, k.fy, k.cx, k.cy, k.model == 3 ? k.k0 : 0, k.model == 3 ? k.k1 : 0, k.model == 3 ? k.k2 : 0, k.model == 3 ? k.k3 : 0, 0};
+    memcpy(intrinsics9, v, sizeof(v));
+  }
+  if (distortion_type) *distortion_type = e.cam.model;  // DistortionType (camera_base.h:12-17): PINHOLE 0, EQUI 3
+  return 0;
+}
+int xivo_get_just_dropped(xivo_batch* b, int seq, int* ids, int max_n, int* n) {
+  BATCH_BEGIN; SEQ_CHECK;
+  XB_REQUIRE(n, "get_just_dropped: null count");
+  const std::vector<int>& v = B_.est[seq]->just_dropped_ids;
+  for (size_t i = 0; i < v.size() && (int)i < max_n; ++i)
+    if (ids) ids[i] = v[i];
+  *n = (int)v.size();
+  return 0;
+}
+int xivo_get_tracker_counters(xivo_batch* b, int seq, int out[4]) {
+  BATCH_BEGIN; SEQ_CHECK;
+  const Estimator& e = *B_.est[seq];
+  out[0] = 0;  // Tracker::num_rejected_outliers(): homography outlier rejection is not on this path (do_outlier_rejection fails at creation)
+  out[1] = e.num_failed_to_track;
+  out[2] = e.num_new_detections;
+  out[3] = 0;  // num_oneptransac_rejected: use_1pt_RANSAC fails at creation
+  return 0;
+}
+int xivo_scale_init_velocity(xivo_batch* b, int seq, double scale) {  // Estimator::ScaleInitVelocity: X_.Vsb /= scale
+  BATCH_BEGIN; SEQ_CHECK;
+  Estimator& e = *B_.est[seq];
+  for (int k = 0; k < 3; ++k) e.X.Vsb.v[k] /= scale;
+  return 0;
+}
+
 int xivo_init_with_sim_depths(xivo_batch* b) {
   BATCH_BEGIN;
   for (auto& e : B_.est) e->sim_initialize_depths = true;

@@ -103,6 +103,23 @@ struct Feature {
   double score() const { return -P[8]; }
 };
 
+// One row of the reference's per-feature read-back accessors (src/estimator_accessors.cpp; pybind11/pyxivo.cpp:357-374).
+struct FeatureRow {
+  int id, sind, ref_group_id;
+  double Xs[3];    // InstateFeaturePositions: the cached Feature::Xs_ (last Feature::Xs(gbc) evaluation)
+  double Xc[3];    // InstateFeatureXc: unproject_logz(x)
+  double xc[3];    // InstateFeaturexc: the local state x = [x/z, y/z, log z]
+  double pred[2];  // InstateFeaturePreds: last Feature::Predict pixel
+  double meas[2];  // InstateFeatureMeas: last observation
+  double cov[6];   // InstateFeatureCovs: P block (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+};
+// One row of InstateGroupIDs / Sinds / Poses / Covs.
+struct GroupRow {
+  int id, sind;
+  double pose[7];   // qx qy qz qw Tx Ty Tz (Eigen::Quaternion(Rsb) as in estimator_accessors.cpp InstateGroupPoses)
+  double cov[36];   // the 6x6 block of P, row-major
+};
+
 // CircBufWithHash of src/mm.cpp:35-121 (USE_MAPPER off).
 template <typename T>
 class Pool {
@@ -287,6 +304,7 @@ struct MotionX {
   M3 Rsb = m3_eye(), Rbc = m3_eye(), Rsg = m3_eye();
   V3 Tsb{{0, 0, 0}}, Vsb{{0, 0, 0}}, bg{{0, 0, 0}}, ba{{0, 0, 0}}, Tbc{{0, 0, 0}};
   int counter = 0;
+  double td = 0;  // camera-IMU time offset X.td (estimator.cpp:245); constant: USE_ONLINE_TEMPORAL_CALIB is off in the reference build
 };
 
 struct Msg {
@@ -416,6 +434,11 @@ class Estimator {
   bool change_owner(Feature* f, Group* nref);
   void feature_initialize(Feature* f, double z0, double sx, double sy, double sz);
   void triangulate_feature(Feature* f);
+
+ public:
+  // read-back tables (estimator_accessors.cpp); P = host copy of the N x N covariance, row-major
+  std::vector<FeatureRow> instate_feature_rows(const double* P, int n_output) const;
+  std::vector<GroupRow> instate_group_rows(const double* P) const;
 };
 
 }  // namespace xb

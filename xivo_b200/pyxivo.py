@@ -185,12 +185,66 @@ class Batch:
         k = min(n.value, m)
         return dict(ids=ids[:k].copy(), sinds=sinds[:k].copy(), ref_groups=refs[:k].copy(), Xs=Xs[:k].copy(), x=x[:k].copy())
 
+    def instate_feature_table(self, seq=0, n_output=-1):
+        """src/estimator_accessors.cpp in one call: n_output < 0 = the no-argument overloads (features of the last update),
+        n_output >= 0 = the (int n_output) overloads (sorted by covariance norm, first min(count, n_output) rows)."""
+        m = self.F
+        i32, f64 = (lambda: np.zeros(m, np.int32)), (lambda w: np.zeros((m, w)))
+        t = dict(ids=i32(), sinds=i32(), ref_groups=i32(), Xs=f64(3), Xc=f64(3), xc=f64(3), pred=f64(2), meas=f64(2), cov=f64(6))
+        n = C.c_int()
+        _check(capi.lib().xivo_get_instate_feature_table(self._h, seq, int(n_output), *[_p(t[k]) for k in ("ids", "sinds", "ref_groups", "Xs", "Xc", "xc", "pred", "meas", "cov")],
+                                                         m, C.byref(n)), "xivo_get_instate_feature_table")
+        k = min(n.value, m)
+        return {key: v[:k].copy() for key, v in t.items()}
+
+    def instate_group_table(self, seq=0):
+        """InstateGroup{IDs, Sinds, Poses (qx qy qz qw T), Covs (full 6x6 blocks)} of the groups the last update saw."""
+        m = self.G
+        ids, sinds, pose, cov, n = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros((m, 7)), np.zeros((m, 36)), C.c_int()
+        _check(capi.lib().xivo_get_instate_group_table(self._h, seq, _p(ids), _p(sinds), _p(pose), _p(cov), m, C.byref(n)), "xivo_get_instate_group_table")
+        k = min(n.value, m)
+        return dict(ids=ids[:k].copy(), sinds=sinds[:k].copy(), pose=pose[:k].copy(), cov=cov[:k].reshape(k, 6, 6).copy())
+
+    def calibration(self, seq=0):
+        Ca, Cg, intr, td, dt = np.zeros(9), np.zeros(9), np.zeros(9), C.c_double(), C.c_int()
+        _check(capi.lib().xivo_get_calibration(self._h, seq, _p(Ca), _p(Cg), C.byref(td), _p(intr), C.byref(dt)), "xivo_get_calibration")
+        return dict(Ca=Ca.reshape(3, 3), Cg=Cg.reshape(3, 3), td=td.value, intrinsics=intr, distortion_type=dt.value)
+
+    def just_dropped(self, seq=0, max_n=4096):
+        ids, n = np.zeros(max_n, np.int32), C.c_int()
+        _check(capi.lib().xivo_get_just_dropped(self._h, seq, _p(ids), max_n, C.byref(n)), "xivo_get_just_dropped")
+        return ids[: min(n.value, max_n)].copy()
+
+    TRACKER_COUNTER_NAMES = ("num_tracker_outlier_rejected", "num_tracker_failed_to_track", "num_tracker_new_detections", "num_oneptransac_rejected")
+
+    def tracker_counters(self, seq=0):
+        out = np.zeros(4, np.int32)
+        _check(capi.lib().xivo_get_tracker_counters(self._h, seq, _p(out)), "xivo_get_tracker_counters")
+        return dict(zip(self.TRACKER_COUNTER_NAMES, out.tolist()))
+
+    def scale_init_velocity(self, scale, seq=0):
+        _check(capi.lib().xivo_scale_init_velocity(self._h, seq, C.c_double(scale)), "xivo_scale_init_velocity")
+
     def instate_groups(self, seq=0):
         m = self.G
         ids, sinds, g, n = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros((m, 12)), C.c_int()
         _check(capi.lib().xivo_get_instate_groups(self._h, seq, _p(ids), _p(sinds), _p(g), m, C.byref(n)), "xivo_get_instate_groups")
         k = min(n.value, m)
         return dict(ids=ids[:k].copy(), sinds=sinds[:k].copy(), gsb=g[:k].reshape(k, 3, 4).copy())
+
+
+def reference_group_cov_layout(cov_blocks):
+    """InstateGroupCovs as the reference returns it (src/estimator_accessors.cpp, InstateGroupCovs): n x 21, but the column counter is
+    reset inside the row loop (`cnt = 0` per `ii`), so only columns 0..5 are ever written and they end up holding
+    cov(5,5), cov(4,5), cov(3,5), cov(2,5), cov(1,5), cov(0,5); columns 6..20 are uninitialised there and zero here."""
+    cov_blocks = np.asarray(cov_blocks, dtype=np.float64).reshape(-1, 6, 6)
+    out = np.zeros((len(cov_blocks), 21))
+    for ii in range(6):
+        cnt = 0
+        for jj in range(ii, 6):
+            out[:, cnt] = cov_blocks[:, ii, jj]
+            cnt += 1
+    return out
 
 
 class Estimator:
@@ -284,23 +338,104 @@ class Estimator:
     def UsingLoopClosure(self):
         return False
 
-    def InstateFeatureIDs(self):
-        return self._b.instate_features()["ids"]
+    # ---- per-feature accessors, both overloads of src/estimator_accessors.cpp (pybind11/pyxivo.cpp:357-374) -------------
+    def _feature_column(self, key, n_output):
+        """No argument: the features of the last update.  (int n_output): sorted by covariance norm; the reference returns
+        max(count, n_output) rows of which it fills the first min(count, n_output) (the rest is uninitialised memory there, zeros here)."""
+        if n_output is None:
+            return self._b.instate_feature_table(0, -1)[key]
+        n_output = int(n_output)
+        col = self._b.instate_feature_table(0, n_output)[key]
+        count = len(self._b.instate_feature_table(0, 1 << 20)["ids"])
+        out = np.zeros((max(count, n_output),) + col.shape[1:], dtype=col.dtype)
+        out[: len(col)] = col
+        return out
 
-    def InstateFeatureSinds(self):
-        return self._b.instate_features()["sinds"]
+    def InstateFeatureIDs(self, n_output=None):
+        return self._feature_column("ids", n_output)
 
-    def InstateFeaturePositions(self):
-        return self._b.instate_features()["Xs"]
+    def InstateFeatureSinds(self, n_output=None):
+        return self._feature_column("sinds", n_output)
+
+    def InstateFeatureRefGroups(self, n_output=None):
+        return self._feature_column("ref_groups", n_output)
+
+    def InstateFeaturePositions(self, n_output=None):
+        return self._feature_column("Xs", n_output)
+
+    def InstateFeatureXc(self, n_output=None):
+        return self._feature_column("Xc", n_output)
+
+    def InstateFeaturexc(self, n_output=None):
+        return self._feature_column("xc", n_output)
+
+    def InstateFeaturePreds(self, n_output=None):
+        return self._feature_column("pred", n_output)
+
+    def InstateFeatureMeas(self, n_output=None):
+        return self._feature_column("meas", n_output)
+
+    def InstateFeatureCovs(self, n_output=None):
+        return self._feature_column("cov", n_output)
 
     def InstateGroupIDs(self):
-        return self._b.instate_groups()["ids"]
+        return self._b.instate_group_table()["ids"]
 
     def InstateGroupSinds(self):
-        return self._b.instate_groups()["sinds"]
+        return self._b.instate_group_table()["sinds"]
 
     def InstateGroupPoses(self):
-        return self._b.instate_groups()["gsb"]
+        """n x 7: qx qy qz qw Tx Ty Tz (MatX7, estimator_accessors.cpp InstateGroupPoses)."""
+        return self._b.instate_group_table()["pose"]
+
+    def InstateGroupCovs(self):
+        """n x 21, laid out exactly as the reference fills it (see reference_group_cov_layout)."""
+        return reference_group_cov_layout(self._b.instate_group_table()["cov"])
+
+    def InstateGroupCovBlocks(self):
+        """n x 6 x 6: the groups' full covariance blocks (not in the reference's API; what InstateGroupCovs was meant to expose)."""
+        return self._b.instate_group_table()["cov"]
+
+    def JustDroppedFeatureIDs(self):
+        return self._b.just_dropped()
+
+    def Rg(self):  # the binding's name for Rsg (pybind11/pyxivo.cpp:353)
+        return self._b.motion()[3]
+
+    def td(self):
+        return self._b.calibration()["td"]
+
+    def Ca(self):
+        return self._b.calibration()["Ca"]
+
+    def Cg(self):
+        return self._b.calibration()["Cg"]
+
+    def CameraIntrinsics(self):
+        return self._b.calibration()["intrinsics"]
+
+    def CameraDistortionType(self):
+        return self._b.calibration()["distortion_type"]
+
+    def ScaleInitVelocity(self, scale):
+        self._b.scale_init_velocity(float(scale))
+
+    def num_oneptransac_rejected(self):
+        return self._b.tracker_counters()["num_oneptransac_rejected"]
+
+    def num_tracker_outlier_rejected(self):
+        return self._b.tracker_counters()["num_tracker_outlier_rejected"]
+
+    def num_tracker_failed_to_track(self):
+        return self._b.tracker_counters()["num_tracker_failed_to_track"]
+
+    def Visualize(self):
+        return None  # the Pangolin viewer is outside the hot path (SURVEY.md §2); kept so that reference scripts run unchanged
+
+    def tracked_features(self):
+        """[(id, pixel, descriptor)]: descriptors are not extracted on this path (extract_descriptor), an empty matrix stands in."""
+        ids, xy, _ = self._b.tracked_features()
+        return [(int(i), p, np.zeros((0, 0), np.float32)) for i, p in zip(ids, xy)]
 
     def tracked_features_no_descriptor(self):
         ids, xy, _ = self._b.tracked_features()
