@@ -322,3 +322,22 @@ def test_host_triangulation_on_the_reference_known_answers(hh):
             assert bool(ok) == expect, f"{name}: {E.TRI_METHODS[mi]}"
             if expect:
                 assert abs(math.exp(out[2]) - z1) <= 0.5
+
+
+def test_tracker_only_accepts_the_reference_tracker_only_config_shape(hh):
+    """CreateSystemTrackerOnly (factory.cpp:84-122) is fed configs with only camera_cfg (model, rows, cols) + tracker_cfg
+    (cfg/tumvi_tracker_only_cam0.json); the full estimator still insists on its filter sections."""
+    full = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    cfg = {"simulation": False, "print_timing": False, "use_canvas": True, "async_run": False,
+           "camera_cfg": {"model": "equidistant", "rows": 512, "cols": 512}, "tracker_cfg": dict(full["tracker_cfg"])}
+    h = hh.hh_create(json.dumps(cfg).encode(), 15, 30, 1)
+    assert h, hh.hh_error()
+    hh.hh_destroy(h)
+    assert not hh.hh_create(json.dumps(cfg).encode(), 15, 30, 0)  # not a valid estimator config
+
+
+def test_dropped_track_rescue_is_refused_not_ignored(hh):
+    """tracker.cpp:203-211, :245-292: match_dropped_tracks changes which ids survive a re-detection; it needs descriptors (no oracle)."""
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    cfg["tracker_cfg"]["match_dropped_tracks"] = True
+    assert not hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0) and b"match_dropped_tracks" in hh.hh_error()

@@ -88,3 +88,25 @@ def test_selection_logic_spacing():
     d = np.abs(pts[:, None, :] - pts[None, :, :]).max(-1) + np.eye(len(pts)) * 100
     assert d.min() > 7  # no two picks inside each other's 15x15 box
     assert all(sc[picked[i]] >= sc[picked[i + 1]] for i in range(len(picked) - 1))
+
+
+def test_homography_sampling_kernel_and_ransac_loop_match_cv2():
+    """oracle/homography_oracle.py (work in progress for SURVEY §8f row 3): the parts that are pinned on cv2 4.13.  On unrelated point
+    sets every 4-point hypothesis has its own inlier set (the sample itself plus accidents), so identical masks mean the same cv::RNG
+    draws, the same checkSubset decisions, the same 4-point kernel and the same adaptive stopping rule."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import homography_oracle as HO
+
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        p0 = rng.uniform(0, 500, (4, 2)).astype(np.float32)
+        p1 = (p0 + rng.normal(0, 5, (4, 2))).astype(np.float32)
+        Hc, _m = cv2.findHomography(p0, p1, 0)
+        assert np.abs(Hc - HO.run_kernel(p0, p1)).max() <= 1e-10 * np.abs(Hc).max()
+    for _ in range(40):
+        n = int(rng.integers(5, 40))
+        p0 = rng.uniform(0, 500, (n, 2)).astype(np.float32)
+        p1 = rng.uniform(0, 500, (n, 2)).astype(np.float32)
+        _H, mc = cv2.findHomography(p0, p1, cv2.RANSAC, 3.0, maxIters=200, confidence=0.995)
+        ok, mo = HO.find_homography_mask(p0, p1, HO.RANSAC, 3.0, 200, 0.995)
+        assert np.array_equal(np.zeros(n, np.uint8) if mc is None else mc.ravel(), mo)
