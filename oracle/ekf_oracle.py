@@ -99,7 +99,8 @@ def project(Xc):
 
 def unproject_logz(x):
     """common/project.h:79-95 -> (Xc, dXc_dx 3x3)."""
-    z = math.exp(x[2])
+    with np.errstate(all="ignore"):
+        z = float(np.exp(np.float64(x[2])))  # IEEE like the C library: exp of a diverged log-depth is inf, not an exception
     Xc = np.array([x[0] * z, x[1] * z, z])
     J = np.array([[z, 0, x[0] * z], [0, z, x[1] * z], [0, 0, z]])
     return Xc, J
@@ -487,6 +488,86 @@ def triangulate(method, R12, t12, xc1, xc2, zmin, zmax, max_theta, beta_thresh):
     if z < zmin or z > zmax:  # NaN passes both comparisons in the reference too (then log(NaN) poisons the feature)
         return None
     return np.array([X[0] / z, X[1] / z, math.log(z) if z > 0 else float("nan")])
+
+
+def refine_depth(cam: Camera, x, P, gref, gbc, views, ref_index, two_view, use_hessian, max_iters, eps, max_res_norm, Rtri):
+    """Feature::RefineDepth (src/feature.cpp:299-420; APPROXIMATE_INIT_COVARIANCE is off in the reference build): Gauss-Newton on the
+    feature's local state x = [x/z, y/z, log z] over its stored observations.  views: [(Rsb, Tsb, xp)] of the observing groups in the
+    reference's iteration order, ref_index the entry of the reference group (skipped).  Returns (ok, x, P, Xs) — Xs is the cached
+    Feature::Xs_ the last evaluation leaves behind.
+    Quirks kept: `two_view` picks the first and the last observation (std::minmax_element with a comparator that is always false,
+    feature.cpp:305-310); the accept test compares the SUM of the residual norms with `max_res_norm`; after the last iteration the
+    state has taken a step whose residual is never evaluated; on a revert the Hessian of the rejected state is the one use_hessian keeps."""
+    Rr, Tr = gref
+    Rbc, Tbc = gbc
+    idx = list(range(len(views)))
+    if two_view:
+        idx = [idx[0], idx[-1]]
+    x = np.asarray(x, dtype=np.float64).copy()
+    x0 = x.copy()
+    H = np.zeros((3, 3))
+    res_norm0 = 0.0
+    Xs = None
+    Rsc, Tsc = Rr @ Rbc, Rr @ Tbc + Tr
+    _err = np.seterr(all="ignore")  # a diverging step yields inf / NaN in the reference too; it is carried, not raised
+    for it in range(max_iters):
+        Xc, dXc_dx = unproject_logz(x)
+        Xs = Rsc @ Xc + Tsc
+        dXs_dx = Rsc @ dXc_dx
+        H = np.zeros((3, 3))
+        b = np.zeros(3)
+        res_norm = 0.0
+        for k in idx:
+            if k == ref_index:
+                continue
+            Rg, Tg, xp_obs = views[k]
+            Rgc, Tgc = Rg @ Rbc, Rg @ Tbc + Tg
+            Xcn = Rgc.T @ (Xs - Tgc)
+            dXcn_dx = Rgc.T @ dXs_dx
+            xcn, dxcn_dXcn = project(Xcn)
+            xp, dxp_dxcn = cam.project(xcn)
+            J = dxp_dxcn @ dxcn_dXcn @ dXcn_dx
+            H += J.T @ J / Rtri
+            res = xp - np.asarray(xp_obs, dtype=np.float64)
+            b += J.T @ res / Rtri
+            res_norm += float(np.linalg.norm(res))
+        if it > 0 and res_norm > res_norm0:
+            x = x0.copy()  # RestoreState
+            break
+        # completeOrthogonalDecomposition().solve(b): minimum-norm least squares; a rank-0 decomposition (NaN Hessian, see pinv_sym3)
+        # returns the zero vector whatever b holds
+        delta = pinv_sym3(H) @ b if np.isfinite(H).all() else np.zeros(3)
+        x0 = x.copy()  # BackupState
+        x = x - delta
+        res_norm0 = res_norm
+        if np.abs(delta).max() < eps:
+            break
+    np.seterr(**_err)
+    if res_norm0 > max_res_norm:
+        return False, x, P, Xs
+    if use_hessian:
+        Hp = pinv_sym3(H)
+        if np.isnan(Hp).any():
+            return False, x, P, Xs
+        P = Hp
+    return True, x, P, Xs
+
+
+def pinv_sym3(H):
+    """Pseudo-inverse of the (symmetric, PSD) 3x3 Gauss-Newton Hessian with Eigen's rank rule of completeOrthogonalDecomposition: pivots
+    below epsilon * 3 * max pivot count as zero (rank 2 when a single view constrains the feature)."""
+    if not np.isfinite(H).all():
+        # a diverged iterate (log-depth of several hundred: exp overflows, inf - inf = NaN) makes every pivot NaN; Eigen's rank() counts
+        # pivots with `abs(pivot) > threshold`, which is false for NaN: rank 0, and solve() / pseudoInverse() of a rank-0 decomposition
+        # return ZERO (CompleteOrthogonalDecomposition::_solve_impl).  So the step is 0, the loop ends, and use_hessian stores P = 0.
+        return np.zeros((3, 3))
+    w, V = np.linalg.eigh(0.5 * (H + H.T))
+    wmax = np.abs(w).max()
+    out = np.zeros((3, 3))
+    for i in range(3):
+        if abs(w[i]) > 3 * np.finfo(float).eps * wmax and wmax > 0:
+            out += np.outer(V[:, i], V[:, i]) / w[i]
+    return out
 
 
 def predict_pixel(cam: Camera, x, gref, gsb, gbc):

@@ -67,7 +67,8 @@ class Feature:
         return self.track[-1]
 
     def z(self):
-        return math.exp(self.x[2])
+        with np.errstate(all="ignore"):
+            return float(np.exp(np.float64(self.x[2])))  # IEEE like the C library (a diverged log-depth gives inf, not an exception)
 
 
 class Pool:
@@ -124,6 +125,7 @@ class EstimatorOracle:
         self.std_order = std_order
         self.um_features = SO.StdUnorderedIntMap() if std_order else None
         self.um_groups = SO.StdUnorderedIntMap() if std_order else None
+        self.um_obs = {}
         self.std_heap = None
         self.lay = E.Layout(G, F)
         N = self.lay.N
@@ -182,6 +184,12 @@ class EstimatorOracle:
         self.tri_beta = tr.get("beta_thesh", 0.25) * math.pi / 180
         self.init_std_badtri = (c.get("initial_std_x_badtri", 0.0), c.get("initial_std_y_badtri", 0.0), c.get("initial_std_z_badtri", 0.0))
         self.num_good_tri = self.num_bad_tri = 0
+        # depth refinement of in-state candidates (estimator.cpp:143-155; manager.cpp:387-395, :431-440, :504-519)
+        self.use_depth_opt = c.get("use_depth_opt", False)
+        do = c.get("depth_opt", {})
+        self.depth_opt = dict(two_view=do.get("two_view", False), use_hessian=do.get("use_hessian", False), max_iters=do.get("max_iters", 5),
+                              eps=do.get("eps", 1e-4), max_res_norm=do.get("max_res_norm", 2.0))
+        self.num_refined = self.num_refine_failed = 0
         self.use_MH = c.get("use_MH_gating", True)
         self.min_inliers = c.get("min_inliers", 5)
         self.MH_thresh, self.MH_mult = c.get("MH_thresh", 5.991), c.get("MH_adjust_factor", 1.1)
@@ -331,6 +339,8 @@ class EstimatorOracle:
             self.um_features.insert(f.id)
         self.features[f.id] = f
         self.feature_adj[f.id] = {}
+        if self.std_order and self.use_depth_opt:  # the inner unordered_map<int, Vec2> of feature_adj_ (graphbase.h:49-51): its iteration order
+            self.um_obs[f.id] = SO.StdUnorderedIntMap()  # is read by GetObservationsOf (graphbase.cpp:146-152) -> RefineDepth's two_view pick
 
     def g_add_group(self, g):
         if self.std_order:
@@ -346,6 +356,7 @@ class EstimatorOracle:
         for gid in self.feature_adj[f.id]:
             self.group_adj[gid].discard(f.id)
         del self.feature_adj[f.id]
+        self.um_obs.pop(f.id, None)
         if f.ref is not None:
             self.gauge_features.setdefault(f.ref.id, set()).discard(f.id)
 
@@ -354,12 +365,16 @@ class EstimatorOracle:
             self.um_groups.erase(g.id)
         del self.groups[g.id]
         for fid in self.group_adj[g.id]:
+            if g.id in self.feature_adj[fid] and fid in self.um_obs:
+                self.um_obs[fid].erase(g.id)
             self.feature_adj[fid].pop(g.id, None)
         del self.group_adj[g.id]
         self.gauge_features.pop(g.id, None)
 
     def g_link(self, f, g):
         self.group_adj[g.id].add(f.id)
+        if g.id not in self.feature_adj[f.id] and f.id in self.um_obs:
+            self.um_obs[f.id].insert(g.id)
         self.feature_adj[f.id].setdefault(g.id, f.xp().copy())
 
     def feats(self, pred=lambda f: True):
@@ -763,20 +778,56 @@ class EstimatorOracle:
         strict = not (self.vision_counter < self.strict_steps)
         cands = sorted(self.feats(lambda f: self.candidate(f, strict) and f.ref.instate()), key=lambda f: f.slot)  # MakePtrVectorUnique
         cands = self.sort_candidates(cands)
+        bad = []
         for f in cands:
             if len(inst) >= self.lay.F:
                 break
+            if self.use_depth_opt and len(self.feature_adj[f.id]) > 1 and not self.refine_depth(f):
+                bad.append(f)
+                continue
             inst.append(f)
             self.add_feature_to_state(f)
+        self.destroy_features(bad)
+
+    def observations_of(self, f):
+        """Graph::GetObservationsOf (graphbase.cpp:146-152): (group, pixel) in the inner container's iteration order."""
+        keys = self.um_obs[f.id].keys() if f.id in self.um_obs else sorted(self.feature_adj[f.id])
+        return [(self.groups[g], self.feature_adj[f.id][g]) for g in keys]
+
+    def refine_depth(self, f):
+        obs = self.observations_of(f)
+        views = [(g.Rsb, g.Tsb, xp) for g, xp in obs]
+        ref_index = next((i for i, (g, _) in enumerate(obs) if g.id == f.ref.id), -1)
+        o = self.depth_opt
+        ok, f.x, f.P, f.Xs = E.refine_depth(self.cam, f.x, f.P, (f.ref.Rsb, f.ref.Tsb), self.gbc(), views, ref_index, o["two_view"], o["use_hessian"],
+                                            o["max_iters"], o["eps"], o["max_res_norm"], self.sub_Rtri)
+        self.num_refined += ok
+        self.num_refine_failed += not ok
+        return ok
+
+    def destroy_features(self, feats):
+        """Estimator::DestroyFeatures (estimator.cpp:1352-1360)."""
+        for f in feats:
+            self.g_remove_feature(f)
+        for f in feats:
+            if f.instate() or f.status == F_REJECTED:
+                self.remove_feature_from_state(f)
+            self.fpool.destroy(f)
+            if f in self.tracks:
+                self.tracks.remove(f)
 
     def zero_gauge_add(self, inst):
         free = self.gsel.count(False)
         strict = not (self.vision_counter < self.strict_steps)
         cands = sorted(self.feats(lambda f: self.candidate(f, strict)), key=lambda f: f.slot)
         cands = self.sort_candidates(cands)
+        bad = []
         for f in cands:
             if len(inst) >= self.lay.F:
                 break
+            if self.use_depth_opt and len(self.feature_adj[f.id]) > 1 and not self.refine_depth(f):
+                bad.append(f)
+                continue
             if not f.ref.instate() and free <= 0:
                 continue
             inst.append(f)
@@ -785,6 +836,7 @@ class EstimatorOracle:
                 self.add_group_to_state(f.ref)
                 self.needs_new_gauge.append(f.ref)
                 free -= 1
+        self.destroy_features(bad)
 
     def add_group_of_features(self, inst, free_g):
         to_add = self.lay.F - len(inst)
@@ -793,6 +845,19 @@ class EstimatorOracle:
         cands = SO.std_sort_desc(cands, [n_owned(g) for g in cands]) if self.std_order else sorted(cands, key=lambda g: -n_owned(g))
         for g in cands:
             feats = self.sort_candidates(self.feats_std(lambda f: f.ref is g and f.status == F_READY))  # GetFeatureCandidatesOwnedBy + std::sort
+            if self.use_depth_opt:
+                # manager.cpp:504-536: only features that refine well are added; if fewer than the gauge count do, the failed ones are
+                # destroyed and the group marked affected — and the group is added to the state all the same (fall-through at :553)
+                good, bad = [], []
+                for f in feats:
+                    if len(self.feature_adj[f.id]) > 1:
+                        (good if self.refine_depth(f) else bad).append(f)
+                if len(good) >= self.n_gauge:
+                    feats = good
+                else:
+                    self.destroy_features(bad)
+                    self.affected.add(g.id)
+                    feats = []
             for f in feats:
                 self.add_feature_to_state(f)
                 inst.append(f)

@@ -108,6 +108,21 @@ void hh_subfilter_inputs(void* h, double* x3, int* tri_ok) {
     tri_ok[i] = e->subfilter_list[i]->tri_ok;
   }
 }
+// local state x(3) and own covariance P(9) of the features of list `which` (0 = instate_features, 1 = in_update, 2 = tracks)
+int hh_feature_states(void* h, int which, int* ids, double* x3, double* P9, int max_n) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  const std::vector<xb::Feature*>& v = which == 0 ? e->instate_features : which == 1 ? e->in_update : e->tracks;
+  int n = 0;
+  for (xb::Feature* f : v) {
+    if (n < max_n) { ids[n] = f->id; memcpy(x3 + 3 * n, f->x, 24); memcpy(P9 + 9 * n, f->P, 72); }
+    ++n;
+  }
+  return n;
+}
+void hh_depth_refine_counts(void* h, int* ok_failed) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  ok_failed[0] = e->num_depth_refined; ok_failed[1] = e->num_depth_refine_failed;
+}
 void hh_triangulation_counts(void* h, int* good_bad) {
   auto* e = static_cast<xb::Estimator*>(h);
   good_bad[0] = e->num_good_triangulations; good_bad[1] = e->num_bad_triangulations;

@@ -87,7 +87,7 @@ def test_config_files_parse_with_comments_and_camera_models(hh):
         hh.hh_destroy(h)
 
 
-@pytest.mark.parametrize("key,value,needle", [("use_OOS", True, "MSCKF"), ("use_1pt_RANSAC", True, "1pt_RANSAC"), ("use_depth_opt", True, "depth_opt"),
+@pytest.mark.parametrize("key,value,needle", [("use_OOS", True, "MSCKF"), ("use_1pt_RANSAC", True, "1pt_RANSAC"),
                                                ("integration_method", "Euler", "integration method"), ("covariance_update", "fp16", "covariance_update")])
 def test_unsupported_options_fail_loudly_at_creation(hh, key, value, needle):
     cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))

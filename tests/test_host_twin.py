@@ -46,6 +46,8 @@ def hh(tmp_path_factory):
     lib.hh_subfilter_ids.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_subfilter_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hh_triangulation_counts.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_feature_states.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.hh_depth_refine_counts.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_feature_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.hh_group_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.hh_just_dropped.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -103,11 +105,29 @@ def _tri(method, zmax=60.0, theta=0.1):  # depth triangulation before the sub-fi
             "triangulation": {"method": method, "zmin": 0.05, "zmax": zmax, "max_theta_thresh": theta, "beta_thesh": 0.25}}
 
 
+def _close(a, b, tol, scale=None):
+    """|a - b| <= tol * max(1, |b|) element-wise; non-finite entries (a diverged depth refinement leaves inf / NaN states in the reference
+    too, and the gate throws those features out) must be non-finite on both sides."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    fin = np.isfinite(a) & np.isfinite(b)
+    if not np.array_equal(np.isfinite(a), np.isfinite(b)):
+        return False
+    s = np.maximum(1.0, np.abs(b[fin])) if scale is None else scale
+    return bool(np.all(np.abs(a[fin] - b[fin]) <= tol * s))
+
+
+def _dopt(two_view, use_hessian):  # depth_opt block as in cfg/tumvi_cam1.json:162-169
+    return {"use_depth_opt": True, "depth_opt": {"two_view": two_view, "use_hessian": use_hessian, "max_iters": 5, "eps": 1e-3, "damping": 1e-3, "max_res_norm": 2.5}}
+
+
 TWIN_CASES = [(4, 14, 4.0, 1, True, "PrinceDormand", None), (15, 30, 3.0, 0, True, "RK4", None), (4, 14, 3.0, 6, False, "PrinceDormand", None),
               (15, 30, 6.0, 2, True, "PrinceDormand", None), (15, 30, 4.0, 0, True, "PrinceDormand", None),
               (4, 14, 4.0, 11, False, "PrinceDormand", _tri("l1_angular")), (15, 30, 3.0, 12, True, "PrinceDormand", _tri("l1_angular", zmax=5.0)),
               (4, 14, 3.0, 13, False, "PrinceDormand", _tri("l2_angular")), (4, 14, 3.0, 14, False, "RK4", _tri("linf_angular")),
-              (4, 14, 3.0, 15, False, "PrinceDormand", _tri("direct_linear_transform_svd")), (4, 14, 3.0, 16, False, "PrinceDormand", _tri("direct_linear_transform_avg"))]
+              (4, 14, 3.0, 15, False, "PrinceDormand", _tri("direct_linear_transform_svd")), (4, 14, 3.0, 16, False, "PrinceDormand", _tri("direct_linear_transform_avg")),
+              # use_depth_opt (Feature::RefineDepth on in-state candidates), all-views and two-view, Hessian as covariance on / off
+              (4, 14, 4.0, 21, True, "PrinceDormand", _dopt(False, True)), (15, 30, 4.0, 22, True, "PrinceDormand", _dopt(True, True)),
+              (4, 14, 3.0, 23, True, "RK4", _dopt(True, False))]
 # XIVO_TWIN_SWEEP=n adds n more seeds x both state sizes x with/without simulated depths (a wider offline sweep; 48 extra sequences passed at n = 12)
 for _s in range(int(os.environ.get("XIVO_TWIN_SWEEP", "0"))):
     for _g, _f in ((4, 14), (15, 30)):
@@ -170,8 +190,13 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, t
                 hh.hh_subfilter_inputs(h, xin.ctypes.data, tri_ok.ctypes.data)
                 # the DLT forms solve a system whose conditioning is ~ 1 / sin^2(parallax of two consecutive frames): the rounding-level
                 # difference of the two nominal states is amplified accordingly
-                tol = 1e-6 if over and over["triangulation"]["method"].startswith("direct") else 1e-9
-                assert np.abs(xin - np.array(rec.sub_in)).max() <= tol, f"frame {n_vis}: sub-filter input states"
+                tol = 1e-6 if over and over.get("triangulation", {}).get("method", "").startswith("direct") else 1e-9
+                # all-view depth refinement: Gauss-Newton along the nearly flat depth direction (pseudo-inverse entries up to 1e7,
+                # feature.cpp:382) amplifies the 1e-10 difference between the two nominal states; refined-but-not-added candidates
+                # come back through the sub-filter
+                if over and over.get("use_depth_opt") and not over["depth_opt"]["two_view"]:
+                    tol = 1e-3
+                assert _close(xin, np.array(rec.sub_in), tol), f"frame {n_vis}: sub-filter input states"
             sub = np.ascontiguousarray(np.array(rec.sub).reshape(nsub, 13)) if nsub else np.zeros((1, 13))
             ninst = hh.hh_after_subfilter(h, sub.ctypes.data)
             assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
@@ -198,6 +223,15 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, t
             o_inst = sorted(est.instate_features, key=lambda f: f.slot)
             assert sorted(map(tuple, inst[:, :3].tolist())) == sorted((f.id, f.sind, f.ref.sind) for f in o_inst), f"frame {n_vis}: in-state slots"
             assert sorted(inst[inst[:, 3] == 7, 0].tolist()) == sorted(f.id for f in o_inst if f.status == EO.F_GAUGE), f"frame {n_vis}: gauge features"
+            if over and over.get("use_depth_opt"):  # the refined local states / Hessian covariances of the features now in the state
+                fid, fx, fP = np.zeros(64, np.int32), np.zeros((64, 3)), np.zeros((64, 9))
+                nf = hh.hh_feature_states(h, 1, fid.ctypes.data, fx.ctypes.data, fP.ctypes.data, 64)
+                want = {f.id: f for f in est.instate_features}
+                for i in range(nf):
+                    o = want[int(fid[i])]
+                    rt = 1e-8 if over["depth_opt"]["two_view"] else 1e-3
+                    assert _close(fx[i], o.x, rt), f"frame {n_vis}: refined state of feature {fid[i]}"
+                    assert _close(fP[i].reshape(3, 3), o.P, 100 * rt, scale=max(1e-12, float(np.nanmax(np.abs(o.P))))), f"frame {n_vis}: covariance of feature {fid[i]}"
             gb, gauge = np.zeros((64, 3), np.int32), C.c_int()
             ng = hh.hh_groups(h, gb.ctypes.data, 64, C.byref(gauge))
             assert sorted(map(tuple, gb[:ng, :2].tolist())) == sorted((g.id, g.sind) for g in est.groups.values() if g.instate())
@@ -211,8 +245,11 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, t
     gb2 = (C.c_int * 2)()
     hh.hh_triangulation_counts(h, gb2)
     assert (gb2[0], gb2[1]) == (est.num_good_tri, est.num_bad_tri)
-    if over:
+    if over and over.get("triangulate_pre_subfilter"):
         assert gb2[0] >= 20 and gb2[1] >= 5, "the triangulation case must exercise both outcomes"
+    if over and over.get("use_depth_opt"):
+        hh.hh_depth_refine_counts(h, gb2)
+        assert (gb2[0], gb2[1]) == (est.num_refined, est.num_refine_failed) and gb2[0] >= 100
     check_read_back_against_the_reference(hh, h, est, G, F, duration, seed, sim_depths, method, over, tmp_path)
     hh.hh_destroy(h)
 

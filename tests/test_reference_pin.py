@@ -29,7 +29,16 @@ def _tri(method, zmax=60.0, theta=0.1):
 
 # pose tolerance per case (default 1e-11): the mid-point DLT solves a 2x2 system with conditioning ~ 1 / sin^2(parallax between two consecutive
 # frames), which amplifies the rounding differences between numpy and the compiled Eigen expressions (measured 1.5e-10)
-POSE_TOL = {"tri_dltavg_89": 1e-8}
+def _dopt(two_view, use_hessian):
+    """Depth refinement of in-state candidates (use_depth_opt; Feature::RefineDepth feature.cpp:299-420, manager.cpp:387-395, :431-440, :504-536),
+    block as in cfg/tumvi_cam1.json:162-169."""
+    return {"use_depth_opt": True, "depth_opt": {"two_view": two_view, "use_hessian": use_hessian, "max_iters": 5, "eps": 1e-3, "damping": 1e-3, "max_res_norm": 2.5}}
+
+
+# all-view refinement runs Gauss-Newton along the nearly flat depth direction (pseudo-inverse entries up to 1e7): measured 1e-12 on these
+# sequences; on longer baselines (N = 203 with all views) the reference's own result is chaotic — log-depths of several hundred, NaN Hessians
+# that Eigen's rank-0 decomposition turns into zero steps — and only the decisions up to the first diverged feature can be compared
+POSE_TOL = {"tri_dltavg_89": 1e-8, "dopt_all_89": 1e-9, "dopt_all_nohess_89": 1e-9}
 
 CASES = [  # name, G, F, duration, seed, sim_depths, overrides, stamp offset of vision messages [ns]
     ("default_203", 15, 30, 4.0, 0, True, None, 0),
@@ -52,6 +61,11 @@ CASES = [  # name, G, F, duration, seed, sim_depths, overrides, stamp offset of 
     ("tri_linf_203", 15, 30, 4.0, 13, True, _tri("linf_angular", zmax=5.0), 0),
     ("tri_dltsvd_89", 4, 14, 4.0, 14, False, _tri("direct_linear_transform_svd"), 0),
     ("tri_dltavg_89", 4, 14, 4.0, 15, False, _tri("direct_linear_transform_avg"), 0),
+    # use_depth_opt (on in cfg/tumvi_cam1.json and cfg/phab_calibration.json): all views / two views, Hessian as covariance on / off
+    ("dopt_all_89", 4, 14, 4.0, 21, True, _dopt(False, True), 0),
+    ("dopt_all_nohess_89", 4, 14, 4.0, 21, True, _dopt(False, False), 1000),
+    ("dopt_two_203", 15, 30, 4.0, 22, True, _dopt(True, True), 0),
+    ("dopt_two_nohess_203", 15, 30, 4.0, 23, True, _dopt(True, False), 0),
 ]
 
 
@@ -102,10 +116,12 @@ def test_oracle_reproduces_the_reference_estimator(name, G, F, duration, seed, s
     assert np.array_equal(gauge, ref["gauge"])
     assert np.abs(gsb - ref["gsb"]).max() <= POSE_TOL.get(name, 1e-11), f"{how}: pose"
     assert np.abs(est.P - ref["P"]).max() <= 1e3 * POSE_TOL.get(name, 1e-15) * np.abs(ref["P"]).max(), f"{how}: covariance"
+    if name.startswith("dopt_"):
+        assert est.num_refined >= 100, "Feature::RefineDepth must actually run"
     if name.startswith("tri_"):
         assert est.num_good_tri >= 20 and est.num_bad_tri >= 5, "both outcomes of Feature::Triangulate must occur"
     assert ref["n_instate"][-1] >= min(F, 10) and (ref["n_instate"] > 0).sum() >= 60  # a filter that is actually updating
-    if sim_depths and not name.startswith("tri_"):  # metric scale is observable -> the reference (and we) track the analytic ground truth
+    if sim_depths and not name.startswith(("tri_", "dopt_all")):  # (all-view depth refinement degrades the reference itself: 25 cm after 4 s here)  # metric scale is observable -> the reference (and we) track the analytic ground truth
         # (with triangulate_pre_subfilter every new feature starts from the bad-triangulation prior, manager.cpp:585-586: the simulated depths are unused)
         assert np.linalg.norm(gsb[-1][:, 3] - traj.pos(float(ts[-1]) * 1e-9)) < 0.05
 

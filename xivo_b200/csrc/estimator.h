@@ -80,6 +80,10 @@ struct Feature {
   std::array<double, 2> first_xp{{0, 0}}, last_xp{{0, 0}};
   int track_len = 0;
   std::vector<int> adj;  // ids of the groups that saw this feature (FeatureAdj keys), ascending
+  // FeatureAdj itself (graphbase.h:49-51: unordered_map<group id, pixel at the time the group first saw the feature>), kept only when
+  // use_depth_opt needs it: Graph::GetObservationsOf walks it in ITERATION order (graphbase.cpp:146-152) and RefineDepth's two_view
+  // mode picks the first and the last element of that walk, so it is the same container with the same insert / erase history.
+  std::unordered_map<int, std::array<double, 2>> obs;
   V3 Xs{{0, 0, 0}};
   bool instate() const { return status == FeatureStatus::INSTATE || status == FeatureStatus::GAUGE; }
   const std::array<double, 2>& xp() const { return last_xp; }
@@ -96,6 +100,7 @@ struct Feature {
     pred[0] = pred[1] = -1;
     outlier_counter = 0; tri_ok = false; response = 0.f;
     track_len = 0; adj.clear();
+    std::unordered_map<int, std::array<double, 2>>().swap(obs);  // a fresh map (bucket count and all), as `feature_adj_[fid]` is
     Xs = V3{{0, 0, 0}};
     observe(u, v);
   }
@@ -223,6 +228,7 @@ struct Graph {
   // checks the result against the reference's own estimator.)
   std::unordered_map<int, Feature*> um_features;
   std::unordered_map<int, Group*> um_groups;
+  bool keep_observations = false;  // maintain Feature::obs (use_depth_opt)
   template <typename Pred>
   std::vector<Feature*> features_std(Pred p) const {
     std::vector<Feature*> out;
@@ -276,6 +282,10 @@ struct EstimatorCfg {
   double max_accel[3] = {0, 0, 0}, max_gyro[3] = {0, 0, 0};
   double sub_Rtri = 3.5 * 3.5, sub_mh = 5.991;
   int sub_ready_steps = 5;
+  // Feature::RefineDepth on in-state candidates (estimator.cpp:143-155; depth_opt.damping is parsed by the reference and never used)
+  bool use_depth_opt = false, depth_two_view = false, depth_use_hessian = false;
+  int depth_max_iters = 5;
+  double depth_eps = 1e-4, depth_max_res_norm = 2.0;
   bool triangulate_pre_subfilter = false;  // Feature::Triangulate on a feature's second observation (manager.cpp:229-231)
   TriOptions tri;
   double adapt_weight = 0.99;
@@ -375,6 +385,7 @@ class Estimator {
   int mask_half = -1;  // MaskOut's function-local static (tracker.cpp:763)
   int rows = 0, cols = 0;
   int num_failed_to_track = 0, num_new_detections = 0, num_mh_rejected = 0;
+  int num_depth_refined = 0, num_depth_refine_failed = 0;
   int num_good_triangulations = 0, num_bad_triangulations = 0;  // Feature::num_good/bad_triangulations_ (feature.cpp:730-748)
   // time / imu (src/estimator.cpp)
   bool gravity_initialized = false, vision_initialized = false, meas_update_initialized = false;
@@ -423,6 +434,7 @@ class Estimator {
   void find_new_gauge_features();
   std::vector<Feature*> graph_find_new_gauge_features(Group* g);
   void destroy_features(const std::vector<Feature*>& v);
+  void destroy_and_untrack(const std::vector<Feature*>& v);
   void discard_features(const std::vector<Feature*>& v);
   void discard_group(Group* g);
   void adapt_initial_depth();
@@ -434,6 +446,7 @@ class Estimator {
   bool change_owner(Feature* f, Group* nref);
   void feature_initialize(Feature* f, double z0, double sx, double sy, double sz);
   void triangulate_feature(Feature* f);
+  bool refine_depth(Feature* f);
 
  public:
   // read-back tables (estimator_accessors.cpp); P = host copy of the N x N covariance, row-major
