@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -150,13 +151,17 @@ def cpu_baseline_entry(r, cores, frames, wall_s):
     """`cpu_baseline` object from oracle/cpu_baseline.py's result.  kind "reference": a frame costs the OpenCV tracker calls (cv2 LK + FAST
     on the image stream) plus the reference's OWN estimator (oracle/_ref/libxivo_ref_*.so, its unmodified sources) on a point-cloud
     stream of the same state size and track count; kind "port" (library absent): only the third-party numerics are timed (upper bound)."""
+    upd_us = None
+    if r.get("stage_share", {}).get("update") is not None and r.get("mean_frame_ms"):
+        upd_us = r["stage_share"]["update"] * r["mean_frame_ms"] * 1e3  # Eigen 3.3.9 Joseph update (UpdateJosephForm's expression sequence), one core
+        upd_us = round(upd_us, 2) if math.isfinite(upd_us) else None
     if r.get("fps_reference"):
-        return dict(value=r["fps_reference"], unit="frames/s", cores=cores, kind="reference",
+        return dict(value=r["fps_reference"], ekf_update_us_per_frame=upd_us, unit="frames/s", cores=cores, kind="reference",
                     sample=(f"{cores} concurrent processes x {frames} frames: per frame cv2 LK+FAST on a synthetic 640x480 sequence ({r['tracker_ms']:.2f} ms) + the reference's own "
                             f"estimator library (propagation, ProcessTracks, sub-filters, Jacobians, gating, Joseph update, management) on a point-cloud stream with "
                             f"{r['ref_tracks']:.0f} tracks, state dim 89 ({r['ref_estimator_ms']:.2f} ms); {wall_s:.0f}s wall"),
                     numerics_only_value=r["fps"], numerics_only_note="cv2 LK+FAST + Eigen 3.3.9 gate/update only (kind port): upper bound on the reference", stage_share=r["stage_share"])
-    return dict(value=r["fps"], unit="frames/s", cores=cores, kind="port",
+    return dict(value=r["fps"], ekf_update_us_per_frame=upd_us, unit="frames/s", cores=cores, kind="port",
                 sample=f"{cores} concurrent synthetic 640x480 sequences x {frames} frames; timed: cv2 LK+FAST and Eigen-3.3.9 gate+update on the restated pipeline's inputs ({r['mean_frame_ms']:.2f} ms/frame/core, eigen={r['eigen']}, {wall_s:.0f}s)",
                 stage_share=r["stage_share"])
 
@@ -199,8 +204,15 @@ def build_roofline(prof, K, peaks, seqs_per_launch, pass_ms):
         a_ = v_["work"] / (v_["ms"] * 1e-3) / (1e12 if tens else 1e9)
         per_kernel[k_] = dict(bound="tensor" if tens else "hbm", achieved=round(a_, 4), unit="TFLOP/s" if tens else "GB/s",
                               frac=round(a_ / (peaks["tf"] if tens else peaks["hbm"]), 6))
+    # BASELINE.json's second headline figure: EKF measurement-update time per frame (gain + covariance kernels, one launch = one update of
+    # every filter of a batch)
+    upd = merged.get("ekf_update")
+    ekf_update = None
+    if upd and upd["calls"]:
+        ekf_update = dict(us_per_frame=round(upd["ms"] * 1e3 / (upd["calls"] * seqs_per_launch), 4), us_per_launch=round(upd["ms"] * 1e3 / upd["calls"], 3),
+                          filters_per_launch=seqs_per_launch, launches=upd["calls"], kernels="ekf_gain_kernel + ekf_cov_kernel (or ekf_cov_tc_kernel)")
     roofline = dict(kernel=dom, bound=bound, achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peaks["src"],
-                    per_kernel=per_kernel,
+                    per_kernel=per_kernel, ekf_update=ekf_update,
                     share_of_device_time=d["ms"] / tot_ms, launches=d["calls"], avg_launch_us=per_launch_s * 1e6,
                     kernels={k: dict(ms=round(v["ms"], 4), calls=v["calls"], share=round(v["ms"] / tot_ms, 4)) for k, v in merged.items()},
                     device_busy_frac=tot_ms / pass_ms, profiled_pass_ms_per_step=pass_ms / K,

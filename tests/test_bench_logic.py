@@ -38,6 +38,8 @@ def test_roofline_picks_dominant_kernel_and_computes_achieved():
     assert "ekf_gain" not in r["kernels"] and abs(r["kernels"]["ekf_update"]["ms"] - 8.0) < 1e-9  # gain + cov merged
     assert abs(r["device_busy_frac"] - 79.0 / 60.0) < 1e-9 and abs(r["profiled_pass_ms_per_step"] - 2.4) < 1e-12
     assert host == {"gating": 0.48}
+    # EKF-update time per frame (BASELINE.json's second figure): (6 + 2) ms over 100 launches of 64 filters
+    assert r["ekf_update"]["us_per_launch"] == 80.0 and abs(r["ekf_update"]["us_per_frame"] - 1.25) < 1e-9 and r["ekf_update"]["filters_per_launch"] == 64
     pk = r["per_kernel"]
     assert set(pk) == {"lk_track", "pyrdown", "imu_cov_propagate", "ekf_update"}
     assert pk["ekf_update"]["bound"] == "tensor" and abs(pk["ekf_update"]["achieved"] - 100 * 64 * 4.4e6 / 8e-3 / 1e12) < 1e-3
