@@ -64,3 +64,14 @@ def test_every_read_back_method_matches_the_reference(case, tmp_path):
     e.ScaleInitVelocity(4.0)
     assert np.array_equal(e.Vsb(), v / 4.0)
     e.close()
+
+
+def test_cpp_facade_read_back_surface(tmp_path):
+    """include/xivo_b200.hpp: every new accessor of the C++ facade executed on the GPU (tests/cpp/facade_check.cpp --readback)."""
+    import subprocess
+
+    import test_cpp_facade as TF
+
+    exe = TF.build(tmp_path)
+    r = subprocess.run([exe, RP.CFG, "--readback"], capture_output=True, text=True)
+    assert r.returncode == 0 and "readback ok" in r.stdout, r.stdout + r.stderr
