@@ -130,6 +130,14 @@ int xivo_oos_project(xivo_ctx* ctx, int G, int F, const double* camera, const do
                      const double* Xs, const double* obs_pose, const int* obs_sind, const double* obs_xp,
                      double* Hf, double* Hx, double* inn, double* Hx_proj, double* inn_proj);
 
+/* Tracker-level outlier rejection: the inlier mask of cv::findHomography(pts0, pts1, method, reproj_thresh, mask, max_iters,
+ * confidence) as Tracker::OutlierRejection calls it (src/tracker.cpp:705-753, :131-150); method 4 = cv::LMEDS, 8 = cv::RANSAC.
+ * pts0 / pts1: n x 2 float (cv::Point2f).  Host-side work (a few dozen four-point hypotheses), no context needed.
+ * mask[i] = 1 for inliers of the Levenberg-Marquardt-refined model at reproj_thresh (OpenCV 4.x semantics); *ok = 0 when no
+ * model was found (mask all zero). */
+int xivo_find_homography_mask(const float* pts0, const float* pts1, int n, int method, double reproj_thresh, int max_iters,
+                              double confidence, uint8_t* mask, int* ok);
+
 /* Covariance slot surgery; replaces AddGroupToState / AddFeatureToState+FillCovarianceBlock /
  * RemoveGroupFromState / RemoveFeatureFromState / FixFeatureXY / SwitchRefGroup
  * (src/estimator.cpp:739-846, :1362-1391, :1474-1478, src/feature.cpp:753-776).

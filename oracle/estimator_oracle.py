@@ -213,6 +213,12 @@ class EstimatorOracle:
         self.t_max_disp = tj.get("max_pixel_displacement", 64)
         klt = tj.get("KLT", {})
         self.klt = dict(win=klt.get("win_size", 15), max_level=klt.get("max_level", 4), max_iter=klt.get("max_iter", 15), eps=klt.get("eps", 0.01))
+        # tracker-level outlier rejection by homography (tracker.cpp:131-150)
+        self.do_outlier_rejection = tj.get("do_outlier_rejection", False)
+        oj = tj.get("outlier_rejection", {})
+        self.outlier_rejection = ({"RANSAC": 8, "LMEDS": 4}[oj.get("method", "RANSAC")], oj.get("RANSAC_reproj_thresh", 3.0), oj.get("RANSAC_max_iters", 2000),
+                                  oj.get("confidence", 0.995))
+        self.num_outliers_rejected = self.num_failed_to_track = 0
         self.fast_thr = tj.get("FAST", {}).get("threshold", 5)
         self.fast_nms = tj.get("FAST", {}).get("nonmaxSuppression", True)
         # bookkeeping
@@ -547,7 +553,7 @@ class EstimatorOracle:
         r1, st, _ = T.lk_track(self.prev_img, img, p0, p1, **self.klt)
         if self.stage_timer is not None:
             self.stage_timer.lk(self.prev_img, img, p0, p1, self.klt)
-        valid, dropped = 0, []
+        valid, status = 0, np.zeros(len(self.tracks), np.uint8)
         for i, f in enumerate(self.tracks):
             ok = bool(st[i])
             if ok:
@@ -559,8 +565,16 @@ class EstimatorOracle:
                     valid += 1
                 else:
                     ok = False
-            if not ok:
-                dropped.append(f)
+            status[i] = ok
+        self.num_failed_to_track = int((status == 0).sum())
+        if self.do_outlier_rejection:  # tracker.cpp:594-599: homography outliers lose their status AFTER their track and the mask were updated
+            from oracle import homography_oracle as HO
+
+            done, rej, status = HO.tracker_outlier_rejection_413(p0, r1, status, *self.outlier_rejection)
+            if done:
+                self.num_outliers_rejected = rej  # (stale when OutlierRejection returned early, like the reference's member)
+            valid -= self.num_outliers_rejected
+        dropped = [f for i, f in enumerate(self.tracks) if not status[i]]
         if valid < self.t_min:
             self.detect_lk(img, self.t_max - valid)
         for f in dropped:

@@ -1,20 +1,19 @@
-"""Restatement (IN PROGRESS, not used by the product or by any parity claim) of cv::findHomography's inlier mask as called by the
-reference's tracker-level outlier rejection, Tracker::OutlierRejection (/root/reference/src/tracker.cpp:705-753).  TEST INFRASTRUCTURE ONLY.
+"""Restatement of cv::findHomography's inlier mask (LMEDS and RANSAC) as called by the reference's tracker-level outlier rejection,
+Tracker::OutlierRejection (/root/reference/src/tracker.cpp:705-753, options :131-150).  TEST INFRASTRUCTURE ONLY; the product's version
+is xivo_b200/csrc/homography.h.
 
 The arithmetic lives in OpenCV (un-vendored, version unpinned in the reference): modules/calib3d/src/fundam.cpp
-(HomographyEstimatorCallback::{checkSubset, runKernel, computeError}, findHomography), ptsetreg.cpp ({RANSAC,LMeDS}PointSetRegistrator,
-RANSACUpdateNumIters) and core's cv::RNG.
+(HomographyEstimatorCallback::{checkSubset, runKernel, computeError}, HomographyRefineCallback, findHomography), ptsetreg.cpp
+({RANSAC,LMeDS}PointSetRegistrator, RANSACUpdateNumIters), levmarq.cpp (LMSolver) and core's cv::RNG.  Pinned on cv2 4.13 in this
+container (tests/test_oracle_tracker.py, tests/test_host_logic.py): the cv::RNG sequence, getSubset / checkSubset, the 4-point normalised
+DLT kernel (1e-13 of cv2 with method 0), the RANSAC / LMedS loops and `find_homography_mask_413` = the mask cv2 returns (identical on
+300 structured scenes; H within 1e-6).
 
-Status against cv2 4.13 in this container (tests/test_oracle_tracker.py):
-  * pinned: the cv::RNG sequence, getSubset / checkSubset, the 4-point normalised-DLT kernel (1e-13 of cv2 with method 0) and the RANSAC
-    loop incl. the adaptive iteration count — identical masks on correspondences where every hypothesis has its own inlier set;
-  * found, not yet restated: cv2 4.13 does NOT return the estimator's mask.  After the Levenberg-Marquardt refinement of H on the inliers
-    (LMSolver, 10 iterations) it returns `computeError(H_refined) <= reprojThreshold^2` for RANSAC *and* LMEDS (verified on 200 scenes:
-    mask == float-error test under the returned H), i.e. LMEDS's own sigma = 2.5*1.4826*(1+5/(n-4))*sqrt(median) threshold no longer
-    decides the mask.  OpenCV 3.4 — the version the reference's build evidence points to — returns the estimator's mask,
-    which is what `find_homography_mask` below computes.  Which of the two a drop-in has to follow is a version question the reference
-    does not answer (`find_package(OpenCV REQUIRED)`); the 4.13 rule needs LMSolver restated.
-`do_outlier_rejection` therefore still fails loudly at creation (csrc/estimator_host.cpp.inc); this file is the starting point of §8f row 3.
+A version finding: cv2 4.13 does NOT return the estimator's mask.  After re-estimating H on the estimator's inliers and refining it with
+Levenberg-Marquardt (10 iterations) it returns `computeError(H_refined) <= reprojThreshold^2` for RANSAC *and* LMEDS, i.e. LMEDS's own
+sigma = 2.5*1.4826*(1+5/(n-4))*sqrt(median) threshold no longer decides the mask.  OpenCV 3.4 — the version the reference's build evidence
+points to — returns the estimator's mask (`find_homography_mask` below).  The reference does not pin a version
+(`find_package(OpenCV REQUIRED)`); oracle and product follow the version that can be run and checked here, like the rest of the tracker.
 
 Points are float32 pairs (cv::Point2f); the model is estimated in double and applied in float exactly as computeError does."""
 from __future__ import annotations
@@ -199,6 +198,88 @@ def find_homography_mask(pts0, pts1, method=LMEDS, reproj_thresh=3.0, max_iters=
     raise ValueError("method must be 0, LMEDS or RANSAC")
 
 
+def _refine_residual(h8, M, m, want_J):
+    """HomographyRefineCallback::compute (fundam.cpp): residuals (2n) and Jacobian (2n x 8) of the 8-parameter homography, in double."""
+    Mx, My = M[:, 0].astype(np.float64), M[:, 1].astype(np.float64)
+    ww = h8[6] * Mx + h8[7] * My + 1.0
+    ww = np.where(np.abs(ww) > DBL_EPSILON, 1.0 / np.where(ww == 0, 1.0, ww), 0.0)
+    xi = (h8[0] * Mx + h8[1] * My + h8[2]) * ww
+    yi = (h8[3] * Mx + h8[4] * My + h8[5]) * ww
+    r = np.empty(2 * len(M))
+    r[0::2], r[1::2] = xi - m[:, 0], yi - m[:, 1]
+    if not want_J:
+        return r, None
+    J = np.zeros((2 * len(M), 8))
+    J[0::2, 0], J[0::2, 1], J[0::2, 2] = Mx * ww, My * ww, ww
+    J[0::2, 6], J[0::2, 7] = -Mx * ww * xi, -My * ww * xi
+    J[1::2, 3], J[1::2, 4], J[1::2, 5] = Mx * ww, My * ww, ww
+    J[1::2, 6], J[1::2, 7] = -Mx * ww * yi, -My * ww * yi
+    return r, J
+
+
+def lm_refine(H, M, m, max_iters=10):
+    """cv::LMSolver (calib3d/levmarq.cpp, LMSolverImpl::run) on HomographyRefineCallback, as findHomography calls it (10 iterations,
+    epsx = epsf = FLT_EPSILON): Levenberg-Marquardt with Nielsen-style damping control (Rlo = 0.25, Rhi = 0.75)."""
+    x = np.asarray(H, dtype=np.float64).ravel()[:8].copy()
+    r, J = _refine_residual(x, M, m, True)
+    S = float(r @ r)
+    A, v = J.T @ J, J.T @ r
+    D = np.diag(A).copy()
+    lam, lc = 1.0, 0.75
+    it = 0
+    while True:
+        Ap = A + np.diag(lam * D)
+        d = np.linalg.lstsq(Ap, v, rcond=None)[0]  # solve(Ap, v, d, DECOMP_EIG)
+        xd = x - d
+        rd, _ = _refine_residual(xd, M, m, False)
+        Sd = float(rd @ rd)
+        dS = float(d @ (2 * v - A @ d))
+        R = (S - Sd) / (dS if abs(dS) > DBL_EPSILON else 1.0)
+        if R > 0.75:
+            lam *= 0.5
+            if lam < lc:
+                lam = 0.0
+        elif R < 0.25:
+            t = float(d @ v)
+            nu = (Sd - S) / (t if abs(t) > DBL_EPSILON else 1.0) + 2
+            nu = min(max(nu, 2.0), 10.0)
+            if lam == 0:
+                Ai = np.linalg.pinv(A)  # invert(A, Ap, DECOMP_EIG)
+                lam = lc = 1.0 / max(DBL_EPSILON, float(np.abs(np.diag(Ai)).max()))
+                nu *= 0.5
+            lam *= nu
+        if Sd < S:
+            S, x = Sd, xd
+            r, J = _refine_residual(x, M, m, True)
+            A, v = J.T @ J, J.T @ r
+        it += 1
+        if not (it < max_iters and np.abs(d).max() >= FLT_EPSILON and np.abs(r).max() >= FLT_EPSILON):
+            break
+    return np.append(x, 1.0).reshape(3, 3)
+
+
+def find_homography_mask_413(pts0, pts1, method=LMEDS, reproj_thresh=3.0, max_iters=2000, confidence=0.995):
+    """The mask cv2 4.13 returns: the estimator's inliers (find_homography_mask) are compressed, the model is re-estimated on them
+    (runKernel) and refined (lm_refine), and the FINAL mask is computeError(H_refined) <= reproj_thresh^2 over all points.
+    Returns (ok, mask, H)."""
+    m1, m2 = np.asarray(pts0, dtype=_f32).reshape(-1, 2), np.asarray(pts1, dtype=_f32).reshape(-1, 2)
+    n = len(m1)
+    if reproj_thresh <= 0:
+        reproj_thresh = 3.0
+    ok, mask = find_homography_mask(m1, m2, method, reproj_thresh, max_iters, confidence)
+    if not ok:
+        return False, np.zeros(n, np.uint8), None
+    if n == 4 or method == 0:
+        return True, mask, run_kernel(m1, m2)
+    inl = mask.astype(bool)
+    H = run_kernel(m1[inl], m2[inl])
+    if H is None:
+        return False, np.zeros(n, np.uint8), None
+    H = lm_refine(H, m1[inl], m2[inl])
+    final = (compute_error(m1, m2, H) <= _f32(reproj_thresh * reproj_thresh)).astype(np.uint8)
+    return True, final, H
+
+
 def tracker_outlier_rejection(pts0, pts1, status, method, reproj_thresh, max_iters, confidence):
     """Tracker::OutlierRejection (tracker.cpp:705-753): runs findHomography on the points whose status is non-zero and clears the status of
     the outliers.  Returns (success, number of rejected outliers or None when it returned early, new status)."""
@@ -207,5 +288,16 @@ def tracker_outlier_rejection(pts0, pts1, status, method, reproj_thresh, max_ite
     if len(valid) < 4:
         return False, None, status
     ok, mask = find_homography_mask(np.asarray(pts0, _f32)[valid], np.asarray(pts1, _f32)[valid], method, reproj_thresh, max_iters, confidence)
+    status[valid[mask == 0]] = 0
+    return True, int((mask == 0).sum()), status
+
+
+def tracker_outlier_rejection_413(pts0, pts1, status, method, reproj_thresh, max_iters, confidence):
+    """Tracker::OutlierRejection with the mask cv2 4.13 returns (find_homography_mask_413)."""
+    status = np.asarray(status, dtype=np.uint8).copy()
+    valid = np.nonzero(status)[0]
+    if len(valid) < 4:
+        return False, None, status
+    ok, mask, _H = find_homography_mask_413(np.asarray(pts0, _f32)[valid], np.asarray(pts1, _f32)[valid], method, reproj_thresh, max_iters, confidence)
     status[valid[mask == 0]] = 0
     return True, int((mask == 0).sum()), status

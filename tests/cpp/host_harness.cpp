@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../xivo_b200/csrc/estimator.h"
+#include "../../xivo_b200/csrc/homography.h"
 
 namespace xb {
 struct HostScope {  // the library's version also feeds the profiler; timing is irrelevant here
@@ -99,6 +100,13 @@ int hh_pcw_begin(void* h, unsigned long long ts, int n, const int* ids, const do
 void hh_subfilter_ids(void* h, int* out) {
   auto* e = static_cast<xb::Estimator*>(h);
   for (size_t i = 0; i < e->subfilter_list.size(); ++i) out[i] = e->subfilter_list[i]->id;
+}
+// homography.h on its own: the mask of cv::findHomography(pts0, pts1, method, thresh, mask, max_iters, confidence); returns ok
+int hh_homography_mask(const float* p0, const float* p1, int n, int method, double thresh, int max_iters, double confidence, unsigned char* mask) {
+  std::vector<uint8_t> m;
+  const bool ok = xb::homography::find_homography_mask(p0, p1, n, method, thresh, max_iters, confidence, m);
+  memcpy(mask, m.data(), (size_t)n);
+  return ok ? 1 : 0;
 }
 // the sub-filter's input states (after Feature::Triangulate where it ran): n x x(3), plus tri_ok flags
 void hh_subfilter_inputs(void* h, double* x3, int* tri_ok) {

@@ -45,3 +45,27 @@ def test_pyramid_layout_matches_opencv_level_rule():
     assert [(r, c) for r, c, _ in lv] == [(480, 640), (240, 320), (120, 160), (60, 80), (30, 40)]
     total, lv = capi.Context.pyramid_layout(512, 512, 3, 15, 5)
     assert len(lv) == 6 and lv[-1][:2] == (16, 16) and total >= sum(r * c * 3 for r, c, _ in lv)
+
+
+def test_homography_mask_through_the_c_abi_matches_the_oracle():
+    """xivo_find_homography_mask is host work: the product library itself can be checked without a GPU against the restatement of
+    cv::findHomography (oracle/homography_oracle.py, pinned on cv2 4.13)."""
+    import numpy as np
+
+    from oracle import homography_oracle as HO
+
+    lib = capi.lib()
+    rng = np.random.default_rng(3)
+    for method in (HO.LMEDS, HO.RANSAC):
+        for _ in range(6):
+            n = int(rng.integers(20, 150))
+            p0 = rng.uniform(8, 630, (n, 2)).astype(np.float32)
+            p1 = (p0 + np.float32([4, -2]) + rng.normal(0, 0.5, (n, 2))).astype(np.float32)
+            p1[: n // 5] += rng.normal(0, 25, (n // 5, 2)).astype(np.float32)
+            mask, ok = np.zeros(n, np.uint8), ctypes.c_int()
+            rc = lib.xivo_find_homography_mask(p0.ctypes.data_as(ctypes.c_void_p), p1.ctypes.data_as(ctypes.c_void_p), n, method, ctypes.c_double(3.0), 2000,
+                                               ctypes.c_double(0.995), mask.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ok))
+            assert rc == 0 and ok.value == 1
+            want_ok, want, _H = HO.find_homography_mask_413(p0, p1, method, 3.0, 2000, 0.995)
+            assert want_ok and int((mask != want).sum()) <= 1 and n // 5 <= int((mask == 0).sum()) <= n // 5 + 3
+    assert lib.xivo_find_homography_mask(None, None, 0, 4, ctypes.c_double(3.0), 10, ctypes.c_double(0.9), None, None) == -1

@@ -8,6 +8,7 @@
 
 #include "../../include/xivo_b200.h"
 #include "ctx.h"
+#include "homography.h"
 #include "kernels.h"
 
 namespace xb {
@@ -452,6 +453,20 @@ int xivo_imu_cov_propagate(xivo_ctx* ctx, int N, double* P, int nstages, const d
   XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
   XB_CUDA(cudaStreamSynchronize(st));
   return XIVO_OK;
+}
+
+// Host-side entry point (no device work): the tracker's homography outlier mask, see include/xivo_b200.h.
+int xivo_find_homography_mask(const float* pts0, const float* pts1, int n, int method, double reproj_thresh, int max_iters, double confidence,
+                              uint8_t* mask, int* ok) {
+  if (!pts0 || !pts1 || !mask || n < 0 || (method != xb::homography::kLMEDS && method != xb::homography::kRANSAC)) {
+    set_error("find_homography_mask: bad arguments (method must be 4 = LMEDS or 8 = RANSAC)");
+    return XIVO_ERR_ARG;
+  }
+  std::vector<uint8_t> m;
+  const bool good = xb::homography::find_homography_mask(pts0, pts1, n, method, reproj_thresh, max_iters, confidence, m);
+  for (int i = 0; i < n; ++i) mask[i] = m[i];
+  if (ok) *ok = good ? 1 : 0;
+  return 0;
 }
 
 }  // extern "C"

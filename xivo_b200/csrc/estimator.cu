@@ -12,6 +12,7 @@
 #include "../../include/xivo_b200_estimator.h"
 #include "ctx.h"
 #include "estimator.h"
+#include "homography.h"
 #include "prof.h"
 #include "workpool.h"
 
@@ -476,6 +477,8 @@ class Batch {
       pfor(lk_list, [&](int b, int) {
         Estimator& e = *est[b];
         int i = 0, num_valid = 0, num_failed = 0;
+        static thread_local std::vector<uint8_t> stat;  // cv status vector of this frame (tracker.cpp:501, :573-591)
+        stat.assign(e.tracks.size(), 0);
         for (Feature* f : e.tracks) {
           const float* p1 = pts1.h + ((size_t)b * max_pts + i) * 2;
           bool ok = lkst.h[(size_t)b * max_pts + i] != 0;
@@ -490,11 +493,23 @@ class Batch {
               ok = false;
             }
           }
-          if (!ok) { ++num_failed; f->tstatus = TrackStatus::DROPPED; }  // (no rescue path: dropped right away)
+          stat[i] = ok;
+          if (!ok) ++num_failed;
           ++i;
         }
         e.num_new_detections = 0;
         e.num_failed_to_track = num_failed;
+        if (e.tc.do_outlier_rejection) {
+          // Tracker::OutlierRejection (tracker.cpp:594-599, :705-753): homography outliers lose their status after their track and the
+          // mask were updated; pts0 / pts1 are this frame's LK input and output (cv::Point2f)
+          homography::tracker_outlier_rejection(pts0.h + (size_t)b * max_pts * 2, pts1.h + (size_t)b * max_pts * 2, (int)e.tracks.size(), stat,
+                                                e.tc.outlier_method, e.tc.outlier_reproj_thresh, e.tc.outlier_max_iters, e.tc.outlier_confidence,
+                                                &e.num_outliers_rejected);
+          num_valid -= e.num_outliers_rejected;
+        }
+        i = 0;
+        for (Feature* f : e.tracks)
+          if (!stat[i++]) f->tstatus = TrackStatus::DROPPED;  // (no rescue path: dropped right away)
         if (num_valid < e.tc.num_features_min) need[b] = e.tc.num_features_max - num_valid;
       });
       for (int b : lk_list)
@@ -1127,7 +1142,7 @@ int xivo_get_just_dropped(xivo_batch* b, int seq, int* ids, int max_n, int* n) {
 int xivo_get_tracker_counters(xivo_batch* b, int seq, int out[4]) {
   BATCH_BEGIN; SEQ_CHECK;
   const Estimator& e = *B_.est[seq];
-  out[0] = 0;  // Tracker::num_rejected_outliers(): homography outlier rejection is not on this path (do_outlier_rejection fails at creation)
+  out[0] = e.num_outliers_rejected;  // Tracker::num_rejected_outliers()
   out[1] = e.num_failed_to_track;
   out[2] = e.num_new_detections;
   out[3] = 0;  // num_oneptransac_rejected: use_1pt_RANSAC fails at creation

@@ -273,6 +273,10 @@ struct TrackerCfg {
   double eps = 0.01;
   int fast_threshold = 5;
   bool fast_nonmax = true, normalize = false;
+  // tracker-level outlier rejection by homography (tracker.cpp:131-150): method = cv::RANSAC (8) or cv::LMEDS (4)
+  bool do_outlier_rejection = false;
+  int outlier_method = 8, outlier_max_iters = 2000;
+  double outlier_reproj_thresh = 3.0, outlier_confidence = 0.995;
 };
 
 struct EstimatorCfg {
@@ -385,6 +389,7 @@ class Estimator {
   int mask_half = -1;  // MaskOut's function-local static (tracker.cpp:763)
   int rows = 0, cols = 0;
   int num_failed_to_track = 0, num_new_detections = 0, num_mh_rejected = 0;
+  int num_outliers_rejected = 0;  // Tracker::num_outliers_rejected_ (keeps its last value when OutlierRejection returns early, tracker.cpp:598, :713-715)
   int num_depth_refined = 0, num_depth_refine_failed = 0;
   int num_good_triangulations = 0, num_bad_triangulations = 0;  // Feature::num_good/bad_triangulations_ (feature.cpp:730-748)
   // time / imu (src/estimator.cpp)
