@@ -135,6 +135,8 @@ for _s in range(int(os.environ.get("XIVO_TWIN_SWEEP", "0"))):
             TWIN_CASES.append((_g, _f, 4.0, 100 + _s, _d, "PrinceDormand", _tri("l1_angular") if _s % 2 else None))
 
 
+# (all-view depth refinement carries inf / NaN feature states through the oracle exactly as the reference carries them)
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
 @pytest.mark.parametrize("G,F,duration,seed,sim_depths,method,over", TWIN_CASES)
 def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, tmp_path, G, F, duration, seed, sim_depths, method, over):
     cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))

@@ -101,6 +101,8 @@ def reference_result(name, cfg_over, G, F, duration, seed, sim_depths, offset, t
     return {k[len(name) + 1:]: g[k] for k in g.files if k.startswith(name + ".")}, "golden"
 
 
+# (all-view depth refinement carries inf / NaN feature states through the oracle exactly as the reference carries them)
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
 @pytest.mark.parametrize("name,G,F,duration,seed,sim_depths,over,offset", CASES, ids=[c[0] for c in CASES])
 def test_oracle_reproduces_the_reference_estimator(name, G, F, duration, seed, sim_depths, over, offset, tmp_path):
     cfg = sim.load_cfg(CFG)
