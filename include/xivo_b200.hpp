@@ -297,6 +297,33 @@ class Tracker {
   Tracker(const Tracker&) = delete;
   Tracker& operator=(const Tracker&) = delete;
 
+  // ---- the stateful surface of src/tracker.h:25-54: Tracker::Create(cfg), Update(img), UpdatePointCloud(ids, xps), features_, counters.
+  // cfg_json is a full or tracker-only estimator config (camera_cfg + tracker_cfg, cfg/tumvi_tracker_only_cam0.json); the tracker runs
+  // inside a tracker-only estimator (CreateSystemTrackerOnly) with the message reorder buffer switched off, so that every Update takes
+  // effect immediately as Tracker::Update does.  Frames are stamped 1 ms apart (the tracker itself never looks at time).
+  static std::shared_ptr<Tracker> Create(const std::string& cfg_json, int device = 0) {
+    auto t = std::make_shared<Tracker>(device);
+    std::string cfg = cfg_json;
+    const size_t close = cfg.rfind('}');
+    if (close == std::string::npos) throw Error(XIVO_ERR_ARG, "Tracker::Create: not a JSON object");
+    cfg.insert(close, ", \"message_buffer_size\": 0");  // a repeated key: the last one wins in the parser
+    t->session_ = std::make_shared<Estimator>(cfg, 15, 30, /*tracker_only=*/true, device);
+    return t;
+  }
+  void Update(const ImageView& img) { UpdateLK(img); }
+  void UpdateLK(const ImageView& img) { session().VisualMeasTrackerOnly(next_stamp(), img); }
+  // xps: n x 2 row-major pixel positions (MatX2 rows in the reference)
+  void UpdatePointCloud(const std::vector<int>& feature_ids, const std::vector<double>& xps) {
+    std::vector<double> xpd(3 * feature_ids.size(), 1.0);
+    for (size_t i = 0; i < feature_ids.size(); ++i) { xpd[3 * i] = xps.at(2 * i); xpd[3 * i + 1] = xps.at(2 * i + 1); }
+    session().VisualMeasPointCloudTrackerOnly(next_stamp(), feature_ids, xpd);
+  }
+  // features_: (id, last pixel position) of every live track, in the tracker's list order
+  std::vector<std::tuple<int, Vec2>> features() { return session().tracked_features_no_descriptor(); }
+  int num_rejected_outliers() { return session().num_tracker_outlier_rejected(); }
+  int num_failed_to_track() { return session().num_tracker_failed_to_track(); }
+  int num_new_detections() { return session().num_tracker_new_detections(); }
+
   struct KeyPoints { std::vector<int> xy; std::vector<int> response; int total = 0; };
   // cv::FastFeatureDetector::detect (TYPE_9_16): raster-ordered keypoints, integer scores
   KeyPoints Detect(const ImageView& img, int threshold, bool nonmax = true, int max_kp = 1 << 16) const {
@@ -323,7 +350,14 @@ class Tracker {
   }
 
  private:
+  Estimator& session() {
+    if (!session_) throw Error(XIVO_ERR_STATE, "stateful Tracker calls need Tracker::Create(cfg)");
+    return *session_;
+  }
+  timestamp_t next_stamp() { return timestamp_t((stamp_ += 1000000)); }
   xivo_ctx* ctx_ = nullptr;
+  std::shared_ptr<Estimator> session_;
+  int64_t stamp_ = 0;
 };
 
 }  // namespace xivo

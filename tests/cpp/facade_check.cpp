@@ -40,6 +40,30 @@ int main(int argc, char** argv) {
       const auto v0 = est->Vsb();
       est->ScaleInitVelocity(2.0);
       if (est->Vsb()[0] != v0[0] / 2.0) return 6;
+      // stateful Tracker surface (src/tracker.h:25-54) on a tracker-only session
+      auto st = xivo::Tracker::Create(std::string("{\"simulation\": false, \"camera_cfg\": {\"model\": \"pinhole\", \"rows\": 64, \"cols\": 64}, "
+                                                  "\"tracker_cfg\": {\"num_features_min\": 5, \"num_features_max\": 10, \"margin\": 4, \"KLT\": {\"max_level\": 2}, "
+                                                  "\"FAST\": {\"threshold\": 20}}}"));
+      // random 4x4 blocks + per-pixel dither: plenty of FAST-9 corners (cv2 finds 151 on this very texture, 95 inside the margin), no score ties
+      std::vector<uint8_t> tex(64 * 64);
+      unsigned seed = 12345;
+      auto lcg = [&seed]() { seed = (seed * 1103515245u + 12345u) & 0x7fffffffu; return (seed >> 16); };
+      for (int by = 0; by < 16; ++by)
+        for (int bx = 0; bx < 16; ++bx) {
+          const int v = (int)(lcg() & 0xff);
+          for (int y = 0; y < 4; ++y)
+            for (int x = 0; x < 4; ++x) tex[64 * (4 * by + y) + 4 * bx + x] = (uint8_t)v;
+        }
+      for (int i = 0; i < 64 * 64; ++i) {
+        const int v = (int)tex[i] + (int)(lcg() % 7) - 3;
+        tex[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+      }
+      xivo::ImageView tv{tex.data(), 64, 64, 1};
+      st->Update(tv);
+      st->Update(tv);
+      if (st->features().empty() || st->num_failed_to_track() != 0 || st->num_rejected_outliers() != 0) return 7;
+      (void)st->num_new_detections();
+      try { xivo::Tracker kernel_only; kernel_only.Update(tv); return 8; } catch (const xivo::Error& e) { if (e.code != XIVO_ERR_STATE) return 9; }
       std::printf("readback ok\n");
     }
     std::vector<uint8_t> img(64 * 64, 0);
