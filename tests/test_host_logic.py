@@ -384,3 +384,38 @@ def test_homography_mask_matches_the_oracle_and_cv2(hh, method):
             _Hc, mc = cv2.findHomography(p0, p1, method, thr, maxIters=2000, confidence=0.995)
             flips += int((got != (np.zeros(n, np.uint8) if mc is None else mc.ravel())).sum())
     assert flips <= 2, f"{flips} mask entries differ over 48 scenes"
+
+
+REFERENCE_CFG = "/root/reference/cfg"
+# what each estimator / tracker config shipped with the reference does when it is handed to the host parser unmodified
+# (None = accepted; otherwise a fragment of the refusal).  DESIGN.md §8 discusses every entry.
+SHIPPED = {
+    "pcw.json": None, "pcw_loops.json": None, "phab.json": None, "tumvi_cam1.json": None,
+    "tumvi_cam0.json": "match_dropped_tracks", "void_params.json": "1pt_RANSAC",
+    "phab_calibration.json": "json",        # stale in the reference itself: `"method": 1`, state keys W / T / V
+    "void_params_calib.json": "Wsb",        # stale in the reference itself: state keys W / T / V
+    "tumvi_tracker_only_cam0.json": "match_dropped_tracks", "tumvi_tracker_only_cam1.json": None,  # (LMEDS outlier rejection on, descriptor rescue off)
+    "phab_tracker_only.json": "MATCH", "void_tracker_only.json": "radtan",
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_CFG), reason="the reference checkout is only present in the authoring container")
+@pytest.mark.parametrize("name,refusal", sorted(SHIPPED.items()))
+def test_shipped_reference_configs_through_the_host_parser(hh, name, refusal):
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(REFERENCE_CFG))  # camera_cfg / tracker_cfg may be relative paths
+    try:
+        cfg = sim.load_cfg(os.path.join("cfg", name))
+    finally:
+        os.chdir(cwd)
+    h = hh.hh_create(json.dumps(cfg).encode(), 15, 30, int("tracker_only" in name))
+    if refusal is None:
+        assert h, hh.hh_error()
+        hh.hh_destroy(h)
+    else:
+        assert not h and refusal.lower() in hh.hh_error().decode().lower(), hh.hh_error()
+    if name.startswith("tumvi_tracker_only"):  # with the descriptor rescue off the shipped file runs as it is (LMEDS outlier rejection included)
+        cfg["tracker_cfg"]["match_dropped_tracks"] = False
+        h = hh.hh_create(json.dumps(cfg).encode(), 15, 30, 1)
+        assert h, hh.hh_error()
+        hh.hh_destroy(h)
