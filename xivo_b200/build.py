@@ -32,8 +32,10 @@ def _newer(src_list, target):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
-    hdrs.append(os.path.join(HERE, "..", "include", "xivo_b200.h"))
+    # every header-like file any source may include: csrc/*.{h,cuh,inc} (estimator.cu includes estimator_host.cpp.inc) and the public C headers
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))]
+    inc = os.path.join(HERE, "..", "include")
+    hdrs += [os.path.join(inc, f) for f in os.listdir(inc) if f.endswith(".h")]
     objs = []
     os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
     for src, extra in SOURCES:
