@@ -14,6 +14,7 @@ for m in zero_copy copy_engine; do
 import json,sys
 d=json.loads(open('gpurun_out/r02a_bench_$m.json').read().strip().splitlines()[-1]); print('$m', 'value', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms', round(d['e2e']['ms_per_step'],3))"
 done
+timeout 300 python scripts/explore_image_options.py > gpurun_out/r02a_explore.txt 2>&1; tail -8 gpurun_out/r02a_explore.txt
 CMD="python bench.py --seqs 64 --batches 1 --steps 2 --warmup 3 --no-cpu-baseline --ingest zero_copy"
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02a_launches.csv $CMD > gpurun_out/r02a_launches.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"lk_kernel|pyrdown" -s 40 -c 4 -o gpurun_out/r02a_top -f $CMD > gpurun_out/r02a_top.log 2>&1
