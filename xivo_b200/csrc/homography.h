@@ -119,7 +119,9 @@ inline void compute_error(const float* M, const float* m, int count, const doubl
     const float ww = 1.f / (Hf[6] * M[2 * i] + Hf[7] * M[2 * i + 1] + 1.f);
     const float dx = (Hf[0] * M[2 * i] + Hf[1] * M[2 * i + 1] + Hf[2]) * ww - m[2 * i];
     const float dy = (Hf[3] * M[2 * i] + Hf[4] * M[2 * i + 1] + Hf[5]) * ww - m[2 * i + 1];
-    err[i] = dx * dx + dy * dy;
+    const float e = dx * dx + dy * dy;
+    err[i] = e == e ? e : INFINITY;  // a degenerate model gives NaN: same answers as NaN in every comparison below (never an inlier, never the
+                                     // best median), but a valid ordering for std::nth_element
   }
 }
 
