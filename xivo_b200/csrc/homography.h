@@ -86,6 +86,48 @@ inline bool run_kernel(const float* M, const float* m, int count, double H[9]) {
   for (int k = 0; k < 2; ++k) { sm[k] = count / sm[k]; sM[k] = count / sM[k]; }
   const double inv_hnorm[9] = {1. / sm[0], 0, cm[0], 0, 1. / sm[1], cm[1], 0, 0, 1};
   const double hnorm2[9] = {sM[0], 0, -cM[0] * sM[0], 0, sM[1], -cM[1] * sM[1], 0, 0, 1};
+  double H0[9], T[9];
+  bool have_h0 = false;
+  if (count == 4) {
+    // Minimal sample: L (8 x 9) has an exact null vector, which is what the smallest eigenvector of L^T L is.  Solve L h = 0 with
+    // h[8] = 1 by elimination (500 flop instead of a 9 x 9 Jacobi sweep set; ~55 of these per frame for LMedS); the general path
+    // below takes over when h[8] = 0 makes the system singular.
+    double a[8][9];
+    for (int i = 0; i < 4; ++i) {
+      const double x = (m[2 * i] - cm[0]) * sm[0], y = (m[2 * i + 1] - cm[1]) * sm[1];
+      const double X = (M[2 * i] - cM[0]) * sM[0], Y = (M[2 * i + 1] - cM[1]) * sM[1];
+      const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x}, Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+      for (int k = 0; k < 8; ++k) { a[2 * i][k] = Lx[k]; a[2 * i + 1][k] = Ly[k]; }
+      a[2 * i][8] = -Lx[8];
+      a[2 * i + 1][8] = -Ly[8];
+    }
+    double amax = 0;
+    for (auto& row : a)
+      for (int k = 0; k < 8; ++k) amax = std::max(amax, std::fabs(row[k]));
+    bool ok = amax > 0;
+    for (int k = 0; k < 8 && ok; ++k) {
+      int p = k;
+      for (int r = k + 1; r < 8; ++r)
+        if (std::fabs(a[r][k]) > std::fabs(a[p][k])) p = r;
+      if (!(std::fabs(a[p][k]) > 1e-10 * amax)) { ok = false; break; }
+      if (p != k)
+        for (int c = 0; c < 9; ++c) std::swap(a[p][c], a[k][c]);
+      for (int r = k + 1; r < 8; ++r) {
+        const double f = a[r][k] / a[k][k];
+        for (int c = k; c < 9; ++c) a[r][c] -= f * a[k][c];
+      }
+    }
+    if (ok) {
+      for (int r = 7; r >= 0; --r) {
+        double acc = a[r][8];
+        for (int c = r + 1; c < 8; ++c) acc -= a[r][c] * H0[c];
+        H0[r] = acc / a[r][r];
+      }
+      H0[8] = 1;
+      have_h0 = true;
+    }
+  }
+  if (!have_h0) {
   double LtL[81] = {0};
   for (int i = 0; i < count; ++i) {
     const double x = (m[2 * i] - cm[0]) * sm[0], y = (m[2 * i + 1] - cm[1]) * sm[1];
@@ -101,8 +143,8 @@ inline bool run_kernel(const float* M, const float* m, int count, double H[9]) {
   int k0 = 0;
   for (int j = 1; j < 9; ++j)
     if (sg[j] < sg[k0]) k0 = j;
-  double H0[9], T[9];
   for (int r = 0; r < 9; ++r) H0[r] = V[9 * r + k0];
+  }
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) T[3 * r + c] = inv_hnorm[3 * r] * H0[c] + inv_hnorm[3 * r + 1] * H0[3 + c] + inv_hnorm[3 * r + 2] * H0[6 + c];
   for (int r = 0; r < 3; ++r)
