@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
     (void)est->InstateFeatureIDs(); (void)est->InstateFeatureSinds(); (void)est->InstateFeatureRefGroups(); (void)est->InstateFeaturePositions();
     (void)est->InstateGroupIDs(); (void)est->InstateGroupSinds(); (void)est->InstateGroupPoses();
     // the rest of the read-back surface (estimator_accessors.cpp, pybind11/pyxivo.cpp:332-398), both overloads: always compiled (a
-    // signature drift fails the build), executed when asked for (tests/test_gpu_widen_readback.py)
+    // signature drift fails the build), executed when asked for (tests/test_gpu_widen_1_readback.py)
     if (argc > 2 && !std::strcmp(argv[2], "--readback")) {
       const size_t count = est->InstateFeatureIDs(0).size();  // (int n_output) overloads have max(count, n_output) rows
       if (est->InstateFeatureIDs(count + 3).size() != count + 3 || est->InstateFeaturePositions(2).size() != 3 * std::max<size_t>(count, 2)) return 3;

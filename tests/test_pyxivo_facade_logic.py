@@ -1,6 +1,6 @@
 """Python-side logic of xivo_b200.pyxivo.Estimator that needs no GPU: the (int n_output) overloads' row padding, the column mapping of
 the per-feature table and the reference's InstateGroupCovs layout, on a stand-in batch fed from the reference's own accessor dump
-(tests/golden/reference_pcw.npz `acc.*`).  The same methods run against the device in tests/test_gpu_widen_readback.py."""
+(tests/golden/reference_pcw.npz `acc.*`).  The same methods run against the device in tests/test_gpu_widen_1_readback.py."""
 import os
 
 import numpy as np
