@@ -116,6 +116,37 @@ def pick_ingest(ms):
     return alt if best[alt] < 0.97 * best["zero_copy"] else "zero_copy"
 
 
+def calibration_frames(choice):
+    """Frames the ingest calibration consumes (run_ours renders that many more)."""
+    return CAL_ROUNDS * len(INGEST_MODES) * (1 + CAL_STEPS) if choice == "auto" else 0
+
+
+def calibrate_ingest(choice, set_mode, run_step, sync, f):
+    """Pinned host frames reach the device either by a gather kernel reading host memory over PCIe or by the copy engine
+    (xivo_set_frame_ingest); same results, the faster one depends on the host's PCIe path.  Picks per rank, outside every timed
+    region, from end-to-end steps of this very workload: per round and mode one settling step + CAL_STEPS timed steps.
+    set_mode(int), run_step(frame index), sync() are the caller's; returns (mode name, {mode: [ms per step, ...]} or None, next frame)."""
+    if choice != "auto":
+        set_mode(INGEST_MODES[choice])
+        return choice, None, f
+    ms = {m: [] for m in INGEST_MODES}
+    for _ in range(CAL_ROUNDS):
+        for name, mode in INGEST_MODES.items():
+            set_mode(mode)
+            run_step(f)
+            f += 1
+            sync()
+            t0 = time.perf_counter()
+            for _ in range(CAL_STEPS):
+                run_step(f)
+                f += 1
+            sync()
+            ms[name].append((time.perf_counter() - t0) * 1e3 / CAL_STEPS)
+    best = pick_ingest(ms)
+    set_mode(INGEST_MODES[best])
+    return best, {k: [round(x, 3) for x in v] for k, v in ms.items()}, f
+
+
 def make_streams(cfg, n_streams, n_frames):
     """n_streams distinct synthetic sequences (seeds 0..), each n_frames frames + IMU."""
     from xivo_b200 import sim
@@ -245,7 +276,7 @@ def run_ours(args):
     cfg = load_cfg()
     cfg["covariance_update"] = args.cov_update  # "fp64" (default, exact parity) or "tf32x3" (tcgen05 downdate, fp32 accuracy)
     B, K, W = args.seqs, args.steps, args.warmup
-    n_cal = CAL_ROUNDS * 2 * (1 + CAL_STEPS) if args.ingest == "auto" else 0
+    n_cal = calibration_frames(args.ingest)
     n_frames = PREROLL_FRAMES + 3 * (W + K) + 4 + n_cal
     log("rendering", min(B, args.streams), "streams x", n_frames, "frames")
     streams = make_streams(cfg, min(B, args.streams), n_frames)
@@ -359,37 +390,12 @@ def run_ours(args):
         ms = replicas.max_over_ranks(ms, device="cuda")
         return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked / K)
 
-    def calibrate_ingest():
-        """Pinned host frames reach the device either by a gather kernel reading host memory over PCIe or by the copy
-        engine (xivo_set_frame_ingest); same results, the faster one depends on the host's PCIe path.  Picks per rank,
-        outside every timed region, from end-to-end steps of this very workload."""
-        nonlocal f
-        L.xivo_set_frame_ingest.restype = C.c_int
-        if args.ingest != "auto":
-            L.xivo_set_frame_ingest(INGEST_MODES[args.ingest])
-            return args.ingest, None
-        ms = {m: [] for m in INGEST_MODES}
-        for _ in range(CAL_ROUNDS):
-            for name, mode in INGEST_MODES.items():
-                L.xivo_set_frame_ingest(mode)
-                step(f, False)
-                f += 1
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for _ in range(CAL_STEPS):
-                    step(f, False)
-                    f += 1
-                torch.cuda.synchronize()
-                ms[name].append((time.perf_counter() - t0) * 1e3 / CAL_STEPS)
-        best = pick_ingest(ms)
-        L.xivo_set_frame_ingest(INGEST_MODES[best])
-        return best, {k: [round(x, 3) for x in v] for k, v in ms.items()}
-
     # three passes over consecutive frames of the same streams: the two measured ones run with the in-library
     # profiler off (its event records and locks cost ~1 ms/step); the third only attributes time to kernels
     r_dev = timed(True, 0)
     log("device-resident pass", r_dev["ms"], "ms")
-    ingest, ingest_cal = calibrate_ingest()
+    L.xivo_set_frame_ingest.restype = C.c_int
+    ingest, ingest_cal, f = calibrate_ingest(args.ingest, L.xivo_set_frame_ingest, lambda k: step(k, False), torch.cuda.synchronize, f)
     log("frame ingest:", ingest, ingest_cal)
     r_e2e = timed(False, 0)
     log("e2e pass", r_e2e["ms"], "ms")

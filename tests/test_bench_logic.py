@@ -100,3 +100,27 @@ def test_pick_ingest_keeps_the_default_unless_clearly_faster():
     assert bench.pick_ingest({"zero_copy": [8.4, 8.3], "copy_engine": [6.1, 6.4]}) == "copy_engine"
     assert bench.pick_ingest({"zero_copy": [6.0, 6.2], "copy_engine": [9.0, 8.8]}) == "zero_copy"
     assert set(bench.INGEST_MODES.values()) == {0, 1}
+
+
+def test_ingest_calibration_protocol():
+    """calibrate_ingest with fakes: every mode is tried in every round, the frames it consumes are exactly the extra frames run_ours renders,
+    the winner is left switched on, and a forced mode calibrates nothing."""
+    log, frames = [], []
+    cost = {0: 0.004, 1: 0.001}  # the copy engine is 4x faster in this fake
+    state = {"mode": None}
+
+    def set_mode(m):
+        state["mode"] = m
+        log.append(m)
+
+    def run_step(k):
+        frames.append(k)
+        bench.time.sleep(cost[state["mode"]])
+
+    best, table, f_next = bench.calibrate_ingest("auto", set_mode, run_step, lambda: None, 100)
+    assert best == "copy_engine" and log[-1] == bench.INGEST_MODES["copy_engine"] and log[:-1] == [0, 1] * bench.CAL_ROUNDS
+    assert frames == list(range(100, f_next)) and f_next - 100 == bench.calibration_frames("auto")
+    assert set(table) == set(bench.INGEST_MODES) and all(len(v) == bench.CAL_ROUNDS for v in table.values())
+    log.clear()
+    assert bench.calibrate_ingest("zero_copy", set_mode, run_step, lambda: None, 7) == ("zero_copy", None, 7) and log == [0]
+    assert bench.calibration_frames("zero_copy") == 0
