@@ -130,7 +130,9 @@ TWIN_CASES = [(4, 14, 4.0, 1, True, "PrinceDormand", None), (15, 30, 3.0, 0, Tru
               (4, 14, 3.0, 15, False, "PrinceDormand", _tri("direct_linear_transform_svd")), (4, 14, 3.0, 16, False, "PrinceDormand", _tri("direct_linear_transform_avg")),
               # use_depth_opt (Feature::RefineDepth on in-state candidates), all-views and two-view, Hessian as covariance on / off
               (4, 14, 4.0, 21, True, "PrinceDormand", _dopt(False, True)), (15, 30, 4.0, 22, True, "PrinceDormand", _dopt(True, True)),
-              (4, 14, 3.0, 23, True, "RK4", _dopt(True, False))]
+              (4, 14, 3.0, 23, True, "RK4", _dopt(True, False)),
+              # all views without the Hessian covariance: diverged candidates reach the gate with NaN Jacobians and are rejected there
+              (4, 14, 4.0, 21, True, "PrinceDormand", _dopt(False, False))]
 # XIVO_TWIN_SWEEP=n adds n more seeds x both state sizes x with/without simulated depths (a wider offline sweep; 48 extra sequences passed at n = 12)
 for _s in range(int(os.environ.get("XIVO_TWIN_SWEEP", "0"))):
     for _g, _f in ((4, 14), (15, 30)):
