@@ -69,3 +69,19 @@ def test_homography_mask_through_the_c_abi_matches_the_oracle():
             want_ok, want, _H = HO.find_homography_mask_413(p0, p1, method, 3.0, 2000, 0.995)
             assert want_ok and int((mask != want).sum()) <= 1 and n // 5 <= int((mask == 0).sum()) <= n // 5 + 3
     assert lib.xivo_find_homography_mask(None, None, 0, 4, ctypes.c_double(3.0), 10, ctypes.c_double(0.9), None, None) == -1
+
+
+def test_new_getters_reject_a_null_batch_without_touching_a_device():
+    """Every read-back entry point added for the binding's surface returns XIVO_ERR_ARG (-1) for a null handle (no throw, no crash)."""
+    lib = capi.lib()
+    n = ctypes.c_int()
+    null = ctypes.c_void_p()
+    assert lib.xivo_get_instate_feature_table(null, 0, -1, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(n)) == -1
+    assert lib.xivo_get_instate_group_table(null, 0, None, None, None, None, 0, ctypes.byref(n)) == -1
+    assert lib.xivo_get_calibration(null, 0, None, None, None, None, None) == -1
+    assert lib.xivo_get_just_dropped(null, 0, None, 0, ctypes.byref(n)) == -1
+    assert lib.xivo_get_tracker_counters(null, 0, (ctypes.c_int * 4)()) == -1
+    assert lib.xivo_scale_init_velocity(null, 0, ctypes.c_double(2.0)) == -1
+    assert b"null batch" in lib.xivo_last_error()
+    prev = lib.xivo_set_frame_ingest(1)
+    assert prev in (0, 1) and lib.xivo_set_frame_ingest(7) == 1 and lib.xivo_set_frame_ingest(prev) == 1  # an unknown mode only queries
