@@ -259,6 +259,7 @@ def run_ours(args):
     args.batches = max(1, min(args.batches, budget // 2))
     os.environ.setdefault("XIVO_THREADS", str(max(1, budget - args.batches + 1 - args.cpu_headroom)))
     os.environ.setdefault("XIVO_DRIVERS", str(args.batches))
+    os.environ.setdefault("XIVO_PIN_DRIVERS", "1")  # the batch driver threads are ours: let the library pin them next to its workers
     import torch
 
     from xivo_b200 import capi, pyxivo

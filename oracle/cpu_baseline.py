@@ -148,7 +148,7 @@ def reference_estimator_ms(G, F, n_frames, skip, seed):
     cfg["tracker_cfg"].update(num_features_min=120, num_features_max=150)  # Tracker::UpdatePointCloud keeps at most 150 tracks, like the image workload
     msgs, _ = sim.pcw_stream(cfg, duration=(n_frames + skip + 12) * 0.04, seed=seed)
     marks = []
-    r = ref_runner.run(cfg, msgs, G, F, True, on_visual=lambda: marks.append(time.perf_counter()))
+    r = ref_runner.run(cfg, msgs, G, F, True, lib_file=ref_runner.lib_path(G, F, timing=True), on_visual=lambda: marks.append(time.perf_counter()))
     k0 = min(skip + 10, len(marks) - 2)  # +10: the reorder buffer holds the first messages back
     k1 = min(k0 + n_frames, len(marks) - 1)
     per_frame_ms = 1e3 * (marks[k1] - marks[k0]) / max(1, k1 - k0)

@@ -15,7 +15,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def lib_path(G: int, F: int) -> str:
+def lib_path(G: int, F: int, timing: bool = False) -> str:
+    """timing=True: the -march=x86-64-v4 build when it exists and this CPU has AVX-512 (what the reference's -march=native gives
+    on such a host); the parity pin always uses the x86-64-v3 build."""
+    if timing:
+        p4 = os.path.join(HERE, "_ref", f"libxivo_ref_G{G}_F{F}_v4.so")
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            flags = ""
+        if os.path.exists(p4) and all(f in flags for f in ("avx512f", "avx512dq", "avx512bw", "avx512vl", "avx512cd")):
+            return p4
     return os.path.join(HERE, "_ref", f"libxivo_ref_G{G}_F{F}.so")
 
 

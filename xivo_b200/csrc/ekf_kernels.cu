@@ -271,7 +271,11 @@ __global__ void __launch_bounds__(GAIN_THREADS) ekf_gain_kernel(int N, EkfLayout
       Ktb[(size_t)r * N + j] = acc;
       e += acc * inn[r];
     }
-    errb[j] = bad ? nan("") : e;
+    if (bad) {  // S not positive definite: publish NaN err and a zero gain, so that the covariance downdate that follows is a no-op
+      for (int r = 0; r < M; ++r) Ktb[(size_t)r * N + j] = 0.0;
+      e = nan("");
+    }
+    errb[j] = e;
   }
 }
 

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -76,11 +77,26 @@ class Batch {
  public:
   // Per-sequence host logic is independent across sequences: run it on the process-wide worker pool
   // (workpool.h).  CUDA calls stay on the calling thread.
+  // An exception thrown by the host state machine (std::out_of_range of a container lookup, std::bad_alloc) must neither reach a
+  // worker thread's top frame (std::terminate) nor unwind the publishing frame while workers still hold the job: it is caught per
+  // item, recorded, and reported by the next first_error() as a sticky batch error.
+  std::atomic<int> pfor_bad{0};
+  std::mutex pfor_mu;
+  std::string pfor_msg;
+  void pfor_record(const char* what) {
+    std::lock_guard<std::mutex> lk(pfor_mu);
+    if (!pfor_bad.load()) { pfor_msg = what; pfor_bad.store(1); }
+  }
   template <typename Fn>
   void pfor(const std::vector<int>& idx, Fn fn) {
-    WorkPool::get().pfor((int)idx.size(), [&](int i) { fn(idx[i], i); });
+    WorkPool::get().pfor((int)idx.size(), [&](int i) {
+      try { fn(idx[i], i); }
+      catch (const std::exception& ex) { pfor_record(ex.what()); }
+      catch (...) { pfor_record("unknown exception"); }
+    });
   }
   int first_error(const std::vector<int>& idx) {
+    if (pfor_bad.load()) return fail(XIVO_ERR_STATE, "host state machine threw: " + pfor_msg);
     for (int b : idx)
       if (est[b]->error) return fail(est[b]->error, est[b]->error_msg);
     return 0;
@@ -217,35 +233,47 @@ class Batch {
   // (imu_cov_propagate_kernel).  Asynchronous: the host already holds the propagated nominal state.
   int integrate(const std::vector<int>& act) {
     cudaStream_t st = st2;
-    int total = 0;
     bool any = false;
     for (int b : act) any = any || !est[b]->stages.empty();
     if (!any) return 0;
-    if (stg_inflight) { XB_CUDA(cudaEventSynchronize(stg_ev)); stg_inflight = false; }
-    for (int b = 0; b < B; ++b) { stg_n.h[b] = 0; stg_first.h[b] = 0; }
-    for (int b : act) {
-      Estimator& e = *est[b];
-      const int n = (int)e.stages.size();
-      if (!n) continue;
-      if (n > kMaxStages) return fail(XIVO_ERR_STATE, "IMU stage queue overflow (a single Propagate call longer than ~140 ms?)");
-      stg_first.h[b] = total;
-      stg_n.h[b] = n;
-      memcpy(stg.h + total, e.stages.data(), sizeof(ImuStage) * n);
-      total += n;
-      e.stages.clear();
-      e.prop_pending = false;
+    // A queue longer than the per-filter staging capacity (an IMU / vision gap of several hundred ms: the reference integrates any dt,
+    // estimator.cpp:539-592) goes down in several launches of whole sub-steps each; the kernel composes per launch.
+    const int sps = std::max(1, icst.h[act[0]].stages_per_step);
+    const int chunk = (kMaxStages / sps) * sps;
+    std::vector<size_t> cur(B, 0);
+    for (;;) {
+      if (stg_inflight) { XB_CUDA(cudaEventSynchronize(stg_ev)); stg_inflight = false; }
+      for (int b = 0; b < B; ++b) { stg_n.h[b] = 0; stg_first.h[b] = 0; }
+      int total = 0;
+      bool more = false;
+      for (int b : act) {
+        Estimator& e = *est[b];
+        const int n = (int)std::min<size_t>((size_t)chunk, e.stages.size() - cur[b]);
+        if (n <= 0) continue;
+        stg_first.h[b] = total;
+        stg_n.h[b] = n;
+        memcpy(stg.h + total, e.stages.data() + cur[b], sizeof(ImuStage) * n);
+        total += n;
+        cur[b] += n;
+        more = more || cur[b] < e.stages.size();
+      }
+      if (!total) break;
+      XB_CUDA(stg.up(st, total)); XB_CUDA(stg_first.up(st)); XB_CUDA(stg_n.up(st));
+      XB_CUDA(cudaEventRecord(stg_ev, st));
+      stg_inflight = true;
+      if (int rc = launch_imu_cov_propagate(st, N, dP, stg.d, stg_first.d, stg_n.d, icst.d, B)) return rc;
+      g_launches += 1;
+      {
+        int nact = 0;
+        for (int b = 0; b < B; ++b) nact += stg_n.h[b] > 0;
+        // algorithmic bytes: the stage records + the motion block read and written + the 23 x (N-23) strip read, 9 rows of it written (twice: mirrored)
+        Prof::get().add_work("imu_cov_propagate", total * (double)sizeof(ImuStage) + nact * 8.0 * (2 * 529 + (23 + 18) * (double)(N - 23)));
+      }
+      if (!more) break;
     }
-    if (!total) return 0;
-    XB_CUDA(stg.up(st, total)); XB_CUDA(stg_first.up(st)); XB_CUDA(stg_n.up(st));
-    XB_CUDA(cudaEventRecord(stg_ev, st));
-    stg_inflight = true;
-    if (int rc = launch_imu_cov_propagate(st, N, dP, stg.d, stg_first.d, stg_n.d, icst.d, B)) return rc;
-    g_launches += 1;
-    {
-      int nact = 0;
-      for (int b = 0; b < B; ++b) nact += stg_n.h[b] > 0;
-      // algorithmic bytes: the stage records + the motion block read and written + the 23 x (N-23) strip read, 9 rows of it written (twice: mirrored)
-      Prof::get().add_work("imu_cov_propagate", total * (double)sizeof(ImuStage) + nact * 8.0 * (2 * 529 + (23 + 18) * (double)(N - 23)));
+    for (int b : act) {
+      est[b]->stages.clear();
+      est[b]->prop_pending = false;
     }
     return 0;
   }
@@ -326,6 +354,8 @@ class Batch {
     }
     Estimator& e0 = *est[0];
     if (ch != 1 && ch != 3) return fail(XIVO_ERR_ARG, "images must have 1 or 3 channels");
+    if (e0.cam.rows > 0 && e0.cam.cols > 0 && (r != e0.cam.rows || c != e0.cam.cols))  // Tracker::Tracker sizes its mask from camera_cfg (tracker.cpp:119-127)
+      return fail(XIVO_ERR_ARG, "image is " + std::to_string(r) + " x " + std::to_string(c) + " but camera_cfg says " + std::to_string(e0.cam.rows) + " x " + std::to_string(e0.cam.cols));
     rows = r; cols = c; cn = ch;
     pd = make_pyr_desc(rows, cols, cn, e0.tc.win_size, e0.tc.max_level);
     ring_n = e0.c.message_buffer_size + 2;
@@ -413,6 +443,7 @@ class Batch {
         frame_ptr.h[b] = dRing + ((size_t)b * ring_n + slots[i]) * ib;  // consumed by the first pyrDown pass
       }
       pfor(act, [&](int b, int) {
+        HostScope hx("x_trk_prepare");
         Estimator& e = *est[b];
         if (!e.tracker_initialized) {
           std::fill(e.mask.begin(), e.mask.end(), 0);
@@ -475,6 +506,7 @@ class Batch {
       HostScope hs("tracker_accept");
       std::vector<int> need(B, 0);
       pfor(lk_list, [&](int b, int) {
+        HostScope hx("x_trk_accept");
         Estimator& e = *est[b];
         int i = 0, num_valid = 0, num_failed = 0;
         static thread_local std::vector<uint8_t> stat;  // cv status vector of this frame (tracker.cpp:501, :573-591)
@@ -534,6 +566,7 @@ class Batch {
       { HostScope hw("wait_fastkp"); if (int rc = wait(st)) return rc; }
       HostScope hs("tracker_select");
       pfor(det_list, [&](int b, int) {
+        HostScope hx("x_trk_select");
         Estimator& e = *est[b];
         detect_select(e, kp.h + (size_t)b * max_kp, std::min(kpcount.h[b], max_kp), det_budget[b]);
         e.tracker_initialized = true;
@@ -610,6 +643,7 @@ class Batch {
       }
       sub_off[B] = nsub;
       pfor(full, [&](int b, int) {
+        HostScope hx("x_sub_stage");
         Estimator& e = *est[b];
         int o = sub_off[b];
         for (Feature* f : e.subfilter_list) {
@@ -642,6 +676,7 @@ class Batch {
       HostScope hs("select_and_tables");
       for (int b = 0; b < B; ++b) nfeat.h[b] = 0;
       pfor(full, [&](int b, int) {
+        HostScope hx("x_select_tables");
         Estimator& e = *est[b];
         e.update_step_after_subfilter(sub_out.h + sub_off[b]);
         if (e.error) return;
@@ -712,18 +747,20 @@ class Batch {
     XB_CUDA(pack.down(st));
     { HostScope hw("wait_update"); if (int rc = wait(st)) return rc; }
     Prof::get().collect();
-    std::atomic<int> notpd{0};
     {
       HostScope hs("absorb_and_manage");
       pfor(full, [&](int b, int) {
         Estimator& e = *est[b];
         const double* pk = pack.h + (size_t)b * (2 * N + 529);
-        for (int i = 0; i < N; ++i)
-          if (nsel.h[b] && !(pk[i] == pk[i])) { notpd = 1; return; }
-        e.update_step_after_update(pk, pk + N, pk + N + 529, nsel.h[b] > 0);
+        bool notpd = false;
+        for (int i = 0; i < N && !notpd; ++i) notpd = nsel.h[b] && !(pk[i] == pk[i]);
+        // Innovation covariance not positive definite (the reference's LDLT would return garbage silently): the gain kernel zeroed its
+        // gain, so the device covariance is the prior; the frame's bookkeeping is finished without the correction and the sequence
+        // carries a sticky error, like the reference's LOG(FATAL) paths.
+        e.update_step_after_update(pk, pk + N, pk + N + 529, nsel.h[b] > 0 && !notpd);
+        if (notpd && !e.error) { e.error = XIVO_ERR_STATE; e.error_msg = "innovation covariance not positive definite"; }
       });
     }
-    if (notpd) return fail(XIVO_ERR_STATE, "innovation covariance not positive definite");
     return first_error(full);
   }
 
@@ -741,6 +778,7 @@ class Batch {
       {
         HostScope hs("ingest_imu");
         pfor(all, [&](int b, int) {
+          HostScope hx("x_ingest_imu");
           has[b] = 0;
           while (pos[b] < in[b].size()) {
             est[b]->push(std::move(in[b][pos[b]++]));
@@ -753,6 +791,7 @@ class Batch {
           }
         });
       }
+      if (int rc = first_error(all)) return rc;
       vis.clear();
       vmsgs.clear();
       std::vector<int> need_int;
@@ -789,6 +828,7 @@ class Batch {
         else { popped[b] = std::move(m); has[b] = 1; }
       });
     }
+    if (int rc = first_error(all)) return rc;
     std::vector<int> need_int;
     for (int b = 0; b < B; ++b) {
       if (has[b] == 1) { vis.push_back(b); vmsgs.push_back(std::move(popped[b])); }

@@ -271,10 +271,12 @@ class WorkPool {
     return true;
   }
 
-  // Pin the calling (driver) thread to one of the cores reserved for drivers; once per thread.
+  // Pin the calling (driver) thread to one of the cores reserved for drivers; once per thread.  Changing the affinity of a thread
+  // that belongs to the host application is a lasting side effect, so it is opt-in: XIVO_PIN_DRIVERS=1 (bench.py sets it).
   void pin_driver() {
     static thread_local bool done = false;
-    if (done || driver_cpus_.empty()) return;
+    static const bool enabled = env_int("XIVO_PIN_DRIVERS", 0) != 0;
+    if (!enabled || done || driver_cpus_.empty()) return;
     done = true;
     const std::vector<int>& cpus = driver_cpus_[next_driver_.fetch_add(1) % driver_cpus_.size()];
     cpu_set_t set;

@@ -59,6 +59,8 @@ class Batch:
         self.G, self.F = max_groups, max_features
         self.N = L.xivo_batch_state_dim(self._h)
         self._keep = None
+        cam = self.cfg.get("camera_cfg") if isinstance(self.cfg.get("camera_cfg"), dict) else None
+        self._cam_shape = (int(cam["rows"]), int(cam["cols"])) if cam and "rows" in cam and "cols" in cam else None
 
     def close(self):
         if self._h:
@@ -81,13 +83,29 @@ class Batch:
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(accel, dtype=np.float64), (self.n, 3)))
         _check(capi.lib().xivo_batch_inertial_meas(self._h, _p(ts), _p(g), _p(a)), "xivo_batch_inertial_meas")
 
-    def visual_meas(self, ts_ns, imgs, tracker_only=False):
-        """imgs: list of n arrays (rows x cols [x 3], uint8, C-contiguous) or one array shared by all."""
+    def _check_images(self, imgs):
+        """One image per sequence, all of the same shape (rows x cols [x 1 | 3]), uint8, C-contiguous: the C side reads
+        rows * cols * channels bytes behind every pointer."""
         if isinstance(imgs, np.ndarray):
             imgs = [imgs] * self.n
+        imgs = list(imgs)
+        if len(imgs) != self.n:
+            raise XivoError(f"expected {self.n} images (one per sequence), got {len(imgs)}")
         imgs = [np.ascontiguousarray(i, dtype=np.uint8) for i in imgs]
-        rows, cols = imgs[0].shape[:2]
-        ch = 1 if imgs[0].ndim == 2 else imgs[0].shape[2]
+        shp = imgs[0].shape
+        if len(shp) not in (2, 3) or (len(shp) == 3 and shp[2] not in (1, 3)):
+            raise XivoError(f"image shape {shp}: expected rows x cols or rows x cols x 3")
+        for k, i in enumerate(imgs):
+            if i.shape != shp:
+                raise XivoError(f"image {k} has shape {i.shape}, image 0 has {shp}: all sequences of a batch share one geometry")
+        cam = self._cam_shape
+        if cam and (shp[0], shp[1]) != cam:
+            raise XivoError(f"image is {shp[0]} x {shp[1]} but camera_cfg says {cam[0]} x {cam[1]}")
+        return imgs, shp[0], shp[1], (1 if len(shp) == 2 else shp[2])
+
+    def visual_meas(self, ts_ns, imgs, tracker_only=False):
+        """imgs: list of n arrays (rows x cols [x 3], uint8, C-contiguous) or one array shared by all."""
+        imgs, rows, cols, ch = self._check_images(imgs)
         ts = np.ascontiguousarray(np.broadcast_to(np.asarray(ts_ns, dtype=np.uint64), (self.n,)))
         ptrs = (C.c_void_p * self.n)(*[i.ctypes.data for i in imgs])
         self._keep = imgs
@@ -96,11 +114,7 @@ class Batch:
     def step(self, imu_ts, gyro, accel, frame_ts, imgs):
         """n_imu InertialMeas + one VisualMeas per sequence in one call (xivo_batch_step).
         imu_ts: (n_imu, n) or (n_imu,), gyro/accel: (n_imu, n, 3) or (n_imu, 3)."""
-        if isinstance(imgs, np.ndarray):
-            imgs = [imgs] * self.n
-        imgs = [np.ascontiguousarray(i, dtype=np.uint8) for i in imgs]
-        rows, cols = imgs[0].shape[:2]
-        ch = 1 if imgs[0].ndim == 2 else imgs[0].shape[2]
+        imgs, rows, cols, ch = self._check_images(imgs)
         its = np.asarray(imu_ts, dtype=np.uint64)
         n_imu = its.shape[0]
         its = np.ascontiguousarray(np.broadcast_to(its.reshape(n_imu, -1), (n_imu, self.n)))
@@ -115,8 +129,13 @@ class Batch:
         """ids / xp_depth: lists of per-sequence arrays, or single arrays shared by all."""
         if isinstance(ids, np.ndarray):
             ids, xp_depth = [ids] * self.n, [xp_depth] * self.n
-        ids = [np.ascontiguousarray(i, dtype=np.int32) for i in ids]
+        ids = [np.ascontiguousarray(i, dtype=np.int32).reshape(-1) for i in ids]
         xpd = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3) for x in xp_depth]
+        if len(ids) != self.n or len(xpd) != self.n:
+            raise XivoError(f"expected {self.n} point lists (one per sequence), got {len(ids)} / {len(xpd)}")
+        for k, (i, x) in enumerate(zip(ids, xpd)):
+            if len(i) != len(x):  # the C side reads 3 * n_pts doubles behind xp_depth[k]
+                raise XivoError(f"sequence {k}: {len(i)} ids but {len(x)} (xp, depth) rows")
         npts = np.array([len(i) for i in ids], dtype=np.int32)
         ts = np.ascontiguousarray(np.broadcast_to(np.asarray(ts_ns, dtype=np.uint64), (self.n,)))
         pi = (C.c_void_p * self.n)(*[i.ctypes.data for i in ids])

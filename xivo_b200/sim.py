@@ -177,6 +177,30 @@ class PlaneRenderer:
         cam = cam or dict(model="pinhole", rows=rows, cols=cols, fx=K[0], fy=K[1], cx=K[2], cy=K[3])
         self.rays, self.vignette = pixel_rays(cam)
 
+    _Q = 1024  # sub-texel resolution of the sampling grid
+
+    def _sample_fixed_point(self, tx, ty):
+        """Bilinear sample of the texture in integer arithmetic: the sampling coordinates are snapped to a 1/1024-texel grid and the
+        texture to 1/16 grey level, so the rendered frame does not depend on the host's libm / BLAS / SIMD rounding (a 1e-16 difference
+        in a ray would need to straddle a grid point to change anything).  Mirror boundary like ndimage's mode="reflect"."""
+        Q = self._Q
+        if not hasattr(self, "_texq"):
+            self._texq = np.rint(self.tex.astype(np.float64) * 16.0).astype(np.int64)
+        R, C = self._texq.shape
+        xq = np.rint(tx * Q).astype(np.int64)
+        yq = np.rint(ty * Q).astype(np.int64)
+        x0, fx = xq >> 10, xq & (Q - 1)
+        y0, fy = yq >> 10, yq & (Q - 1)
+
+        def refl(i, n):
+            i = np.mod(i, 2 * n)
+            return np.where(i >= n, 2 * n - 1 - i, i)
+
+        xa, xb, ya, yb = refl(x0, C), refl(x0 + 1, C), refl(y0, R), refl(y0 + 1, R)
+        t = self._texq
+        val = (t[ya, xa] * (Q - fx) + t[ya, xb] * fx) * (Q - fy) + (t[yb, xa] * (Q - fx) + t[yb, xb] * fx) * fy
+        return val.astype(np.float64) / (16.0 * Q * Q)  # < 2^32: exact in float64, division by a power of two is exact
+
     def render(self, Rsc, Tsc, noise_rng=None, fast=False):
         """fast=True uses cv2.remap (bench only: ~40x quicker, fixed-point bilinear weights)."""
         d = self.rays @ Rsc.T
@@ -191,7 +215,7 @@ class PlaneRenderer:
 
             img = cv2.remap(self.tex, tx.astype(np.float32), ty.astype(np.float32), cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
         else:
-            img = ndimage.map_coordinates(self.tex, [ty, tx], order=1, mode="reflect")
+            img = self._sample_fixed_point(tx, ty)
         if self.vignette is not None:
             img = img * self.vignette
         if noise_rng is not None:
