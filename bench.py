@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 ROWS, COLS, G, F = 480, 640, 4, 14
 IMU_PER_FRAME = 8
 FRAME_NS = 40_000_000
-PREROLL_FRAMES = 12  # gravity init (stationary) + first detections, never timed
+PREROLL_FRAMES = 12  # reference arm: gravity init (stationary) + first detections, never timed
 CAL_ROUNDS, CAL_STEPS = 2, 4  # frame-ingest calibration: per round and mode one settling step + CAL_STEPS timed steps (untimed region)
 INGEST_MODES = {"zero_copy": 0, "copy_engine": 1}
 
@@ -51,13 +51,13 @@ def load_cfg():
 ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
 
 
-def cpu_reference(cores, frames, skip):
+def cpu_reference(cores, frames, skip, channels=1):
     """Runs oracle/cpu_baseline.py in a fresh interpreter (no CUDA context there: it forks one worker
     per core) and returns its JSON."""
     cfg_path = os.path.join(ROOT, "xivo_b200", "cfg", "vio_640x480.json")
     if hasattr(os, "sched_setaffinity"):
         os.sched_setaffinity(0, ALL_CPUS)  # the library pins its driver threads; the CPU arm gets every allowed CPU
-    r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", cfg_path, str(cores), str(frames), str(skip), str(G), str(F)], cwd=ROOT,
+    r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", cfg_path, str(cores), str(frames), str(skip), str(G), str(F), str(channels)], cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     if r.returncode != 0:
         raise RuntimeError("cpu baseline failed: " + r.stderr[-2000:])
@@ -147,17 +147,51 @@ def calibrate_ingest(choice, set_mode, run_step, sync, f):
     return best, {k: [round(x, 3) for x in v] for k, v in ms.items()}, f
 
 
-def make_streams(cfg, n_streams, n_frames):
-    """n_streams distinct synthetic sequences (seeds 0..), each n_frames frames + IMU."""
+PERIOD_S = 4.0                      # period of the synthetic trajectories: one rendered period is replayed for ever
+REST_FRAMES = 6                     # frames 0..5 of a base stream show the platform at rest (gravity initialisation)
+PERIOD_FRAMES = int(round(PERIOD_S / 0.04))
+REST_IMU, PERIOD_IMU = 40, int(round(PERIOD_S / 0.005))
+STAGGER = 3                         # start delay [frames] between sequences that replay the same base stream
+
+
+def _render_base(args):
+    """One base stream: REST_FRAMES frames at rest + one period of a periodic trajectory (xivo_b200.sim.periodic_trajectory), its IMU
+    samples (rest: REST_IMU samples, then one period).  The trajectory returns to rest pose / zero velocity after a period, so the
+    period can be replayed indefinitely as a physically consistent stream."""
+    cfg, seed, channels = args
     from xivo_b200 import sim
 
-    out = []
-    for s in range(n_streams):
-        msgs, _ = sim.image_stream(cfg, duration=n_frames * 0.04 + 1e-9, seed=s, channels=1, fast=True)
-        frames = [p for k, _, p in msgs if k == "img"]
-        imu = [(ts, p) for k, ts, p in msgs if k == "imu"]
-        out.append((frames[:n_frames], imu))
-    return out
+    traj = sim.periodic_trajectory(PERIOD_S, amp_scale=0.85 + 0.1 * (seed % 4))
+    msgs, _ = sim.image_stream(cfg, duration=0.2 + PERIOD_S + 0.04 + 1e-9, seed=seed, channels=channels, fast=True, traj=traj, rest_accel_is_gravity=True)
+    frames = np.stack([p for k, _, p in msgs if k == "img"][: REST_FRAMES + PERIOD_FRAMES])
+    imu = [p for k, _, p in msgs if k == "imu"][: REST_IMU + PERIOD_IMU]
+    return frames, np.array([p[0] for p in imu]), np.array([p[1] for p in imu])
+
+
+def make_base_streams(cfg, n_base, channels, procs):
+    """Rendered before CUDA is initialised (fork pool)."""
+    import multiprocessing as mp
+
+    args = [(cfg, s, channels) for s in range(n_base)]
+    if procs <= 1 or n_base == 1:
+        return [_render_base(a) for a in args]
+    with mp.get_context("fork").Pool(min(procs, n_base)) as pool:
+        return pool.map(_render_base, args, chunksize=1)
+
+
+def stream_tables(n_seq, n_base, n_frames, first_seq=0):
+    """Which base-stream frame / IMU sample sequence s consumes at step f.  Sequence s replays base (s % n_base) after a start delay of
+    (s // n_base) * STAGGER frames spent at rest, so at any step all sequences of a GPU read different frames (and sit in different
+    phases of their state machines).  Returns (frame index (n_frames, n_seq), imu index (n_frames * 8, n_seq), base (n_seq,))."""
+    s = np.arange(first_seq, first_seq + n_seq)
+    base, delay = s % n_base, (s // n_base) * STAGGER
+    f = np.arange(n_frames)[:, None]
+    k = f - (REST_FRAMES - 1) - delay[None, :]          # motion phase in frames (k <= 0: still at rest)
+    fidx = np.where(k <= 0, f % REST_FRAMES, REST_FRAMES - 1 + ((k - 1) % PERIOD_FRAMES) + 1)
+    j = np.arange(n_frames * IMU_PER_FRAME)[:, None]
+    jj = j - IMU_PER_FRAME * delay[None, :]
+    iidx = np.where(jj < REST_IMU, j % REST_IMU, REST_IMU + ((jj - REST_IMU) % PERIOD_IMU))
+    return fidx, iidx, base
 
 
 def cpu_budget():
@@ -254,55 +288,56 @@ def build_roofline(prof, K, peaks, seqs_per_launch, pass_ms):
 def run_ours(args):
     # host CPUs: the library's worker pool (workpool.h) is shared by the NB batches of this process; each batch
     # also has one driver thread (the Python thread inside xivo_batch_step), so workers + drivers = CPU budget
-    budget = max(1, cpu_budget() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+    lws = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    budget_all = cpu_budget()
+    budget = max(1, budget_all // lws)
     # one driver per batch needs a CPU of its own: with a small budget (e.g. a node quota shared by 8 ranks) run fewer batches
     args.batches = max(1, min(args.batches, budget // 2))
-    os.environ.setdefault("XIVO_THREADS", str(max(1, budget - args.batches + 1 - args.cpu_headroom)))
+    os.environ.setdefault("XIVO_THREADS", str(max(1, min(args.max_threads, budget) - args.batches + 1 - args.cpu_headroom)))
     os.environ.setdefault("XIVO_DRIVERS", str(args.batches))
     os.environ.setdefault("XIVO_PIN_DRIVERS", "1")  # the batch driver threads are ours: let the library pin them next to its workers
-    import torch
-
-    from xivo_b200 import capi, pyxivo
-
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    cfg = load_cfg()
+    cfg["covariance_update"] = args.cov_update  # "fp64" (default, exact parity) or "tf32x3" (tcgen05 downdate, fp32 accuracy)
+    B, K, W, FPS, CH = args.seqs, args.steps, args.warmup, args.frames_per_step, args.channels
+    S0 = max(1, min(args.streams, B))
+    # ---- synthetic inputs (rendered before CUDA is initialised: fork pool) ----
+    t0 = time.time()
+    bases = make_base_streams(cfg, S0, CH, max(1, budget - 1))
+    log(f"rendered {S0} base streams x {REST_FRAMES + PERIOD_FRAMES} frames in {time.time() - t0:.1f}s")
+    import torch
+
+    from xivo_b200 import capi, pyxivo, replicas
+
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = load_cfg()
-    cfg["covariance_update"] = args.cov_update  # "fp64" (default, exact parity) or "tf32x3" (tcgen05 downdate, fp32 accuracy)
-    B, K, W = args.seqs, args.steps, args.warmup
+    NFB = REST_FRAMES + PERIOD_FRAMES
+    fshape = (ROWS, COLS) if CH == 1 else (ROWS, COLS, CH)
+    fbytes = ROWS * COLS * CH
+    host = torch.empty((S0, NFB) + fshape, dtype=torch.uint8).pin_memory()  # the pool every step reads from (e2e pass)
+    for s, (frames, _, _) in enumerate(bases):
+        host[s] = torch.from_numpy(frames)
+    dev = host.cuda()                                                          # the same pool resident in HBM (device-resident pass)
+    base_g = np.stack([b[1] for b in bases])  # (S0, REST_IMU + PERIOD_IMU, 3)
+    base_a = np.stack([b[2] for b in bases])
+    del bases
+    # ---- schedule: which frame / IMU sample every sequence consumes at every step ----
+    K_prof = min(K, args.profile_steps)
     n_cal = calibration_frames(args.ingest)
-    n_frames = PREROLL_FRAMES + 3 * (W + K) + 4 + n_cal
-    log("rendering", min(B, args.streams), "streams x", n_frames, "frames")
-    streams = make_streams(cfg, min(B, args.streams), n_frames)
-    log("streams ready")
-    S = len(streams)
-    # pinned host copies (e2e pass) and device copies (device-resident pass)
-    host = torch.empty((S, n_frames, ROWS, COLS), dtype=torch.uint8).pin_memory()
-    for s, (frames, _) in enumerate(streams):
-        for f, img in enumerate(frames):
-            host[s, f] = torch.from_numpy(img)
-    dev = host.cuda()
-    hnp = host.numpy()
-    fbytes = ROWS * COLS
-    host_ptr = [[hnp[s, f].ctypes.data for f in range(n_frames)] for s in range(S)]
-    dev_ptr = [[dev.data_ptr() + (s * n_frames + f) * fbytes for f in range(n_frames)] for s in range(S)]
-    from xivo_b200 import replicas
+    max_delay = ((world * B - 1) // S0) * STAGGER
+    PREROLL = max_delay + 20  # every sequence has left its rest phase, initialised gravity and vision, and filled its state
+    n_total = PREROLL + FPS * (2 * (W + K) + (W + K_prof)) + n_cal + 8 + (64 if args.single_stream else 0)
+    fidx, iidx, base = stream_tables(B, S0, n_total, first_seq=rank * B)
+    frame_ts = (np.arange(n_total, dtype=np.uint64) * np.uint64(FRAME_NS))
+    imu_ts_all = (np.arange(n_total * IMU_PER_FRAME, dtype=np.uint64) * np.uint64(FRAME_NS // IMU_PER_FRAME))
 
-    seq_stream = replicas.assign_streams(rank, world, B, S)
-    # IMU arrays per step: (B,3)
-    imu_ts = np.array([[ts for ts, _ in streams[s][1]] for s in range(S)], dtype=np.uint64)
-    imu_g = np.array([[p[0] for _, p in streams[s][1]] for s in range(S)])
-    imu_a = np.array([[p[1] for _, p in streams[s][1]] for s in range(S)])
-
-    # NB independent batches per GPU, each with its own stream and driven by its own host thread
-    # (ctypes releases the GIL): the host phases of one batch overlap the kernels of the others.
     NB = max(1, min(args.batches, B))
     sizes = [B // NB + (1 if i < B % NB else 0) for i in range(NB)]
     L = capi.lib()
@@ -310,32 +345,39 @@ def run_ours(args):
     from concurrent.futures import ThreadPoolExecutor
 
     L.xivo_ctx_stream.restype = C.c_void_p
-    ctxs, bts, exts, idxs = [], [], [], []
+    ctxs, bts, exts, tabs = [], [], [], []
     o = 0
     for nb in sizes:
         c = capi.Context(local)
         ctxs.append(c)
         bts.append(pyxivo.Batch(cfg, n_seq=nb, max_groups=G, max_features=F, ctx=c))
         exts.append(torch.cuda.ExternalStream(L.xivo_ctx_stream(c._h)))
-        idxs.append(np.array(seq_stream[o : o + nb]))
+        sl = slice(o, o + nb)
+        # everything a step passes to the C ABI is laid out once, so that the timed loop is the C call and nothing else
+        t = dict(its=np.ascontiguousarray(np.broadcast_to(imu_ts_all[:, None], (n_total * IMU_PER_FRAME, nb))),
+                 ig=np.ascontiguousarray(base_g[base[sl][None, :], iidx[:, sl]]),   # (n_total * 8, nb, 3)
+                 ia=np.ascontiguousarray(base_a[base[sl][None, :], iidx[:, sl]]),
+                 fts=np.ascontiguousarray(np.broadcast_to(frame_ts[:, None], (n_total, nb))),
+                 hptr=np.ascontiguousarray(np.uint64(host.data_ptr()) + (base[sl][None, :].astype(np.uint64) * np.uint64(NFB) + fidx[:, sl].astype(np.uint64)) * np.uint64(fbytes)),
+                 dptr=np.ascontiguousarray(np.uint64(dev.data_ptr()) + (base[sl][None, :].astype(np.uint64) * np.uint64(NFB) + fidx[:, sl].astype(np.uint64)) * np.uint64(fbytes)))
+        t["addr"] = {k: v.ctypes.data for k, v in t.items()}
+        t["row"] = {k: v.strides[0] for k, v in t.items() if k != "addr"}
+        tabs.append(t)
         o += nb
     pool = ThreadPoolExecutor(NB)
-    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    VP = C.c_void_p
 
     def step_one(i, f, device_resident):
-        idx, nb = idxs[i], sizes[i]
-        ks = slice(f * IMU_PER_FRAME, (f + 1) * IMU_PER_FRAME)
-        its = np.ascontiguousarray(imu_ts[idx, ks].T)                 # (8, nb)
-        ig = np.ascontiguousarray(imu_g[idx, ks].transpose(1, 0, 2))  # (8, nb, 3)
-        ia = np.ascontiguousarray(imu_a[idx, ks].transpose(1, 0, 2))
-        ts = np.full(nb, f * FRAME_NS, dtype=np.uint64)
-        ptrs = (C.c_void_p * nb)(*[(dev_ptr if device_resident else host_ptr)[s][f] for s in idx])
-        rc = L.xivo_batch_step(bts[i]._h, IMU_PER_FRAME, vp(its), vp(ig), vp(ia), vp(ts), ptrs, ROWS, COLS, 1, int(device_resident))
+        t = tabs[i]
+        ad, rw = t["addr"], t["row"]
+        j = f * IMU_PER_FRAME
+        rc = L.xivo_batch_step(bts[i]._h, IMU_PER_FRAME, VP(ad["its"] + j * rw["its"]), VP(ad["ig"] + j * rw["ig"]), VP(ad["ia"] + j * rw["ia"]),
+                               VP(ad["fts"] + f * rw["fts"]), VP((ad["dptr"] if device_resident else ad["hptr"]) + f * rw["hptr"]), ROWS, COLS, CH, int(device_resident))
         if rc != 0:
             raise RuntimeError(L.xivo_last_error().decode())
         return bts[i].gsb(0)  # host read of the step's result (pose); the err/P_mm D2H happened inside the call
 
-    def step(f, device_resident, serial=False):
+    def frame_step(f, device_resident, serial=False):
         if NB == 1 or serial:
             return [step_one(i, f, device_resident) for i in range(NB)]
         return list(pool.map(lambda i: step_one(i, f, device_resident), range(NB)))
@@ -349,15 +391,16 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     f = 0
-    for _ in range(PREROLL_FRAMES):
-        step(f, True)
+    for _ in range(PREROLL):
+        frame_step(f, True)
         f += 1
-    log("preroll done", bts[0].counters(0))
+    log("preroll done", PREROLL, "frames;", bts[0].counters(0), bts[-1].counters(sizes[-1] - 1))
 
-    def timed(device_resident, profile):
+    def timed(device_resident, profile, K_):
+        """W warm-up steps, then exactly K_ timed steps; one step = FPS consecutive frames (+ their IMU samples) of every sequence."""
         nonlocal f
-        for _ in range(W):
-            step(f, device_resident)
+        for _ in range(W * FPS):
+            frame_step(f, device_resident)
             f += 1
         L.xivo_profile_reset()
         L.xivo_profile_enable(int(profile))
@@ -371,13 +414,12 @@ def run_ours(args):
         for i in range(NB):
             e0[i].record(exts[i])
         ntracked = 0
-        for _ in range(K):
+        for _ in range(K_ * FPS):
             # the attribution pass steps the batches one after another: with several batches in flight a CUDA-event pair
-            # around a launch also measures the time the launch queued behind other batches' kernels, which made the
-            # per-kernel shares disagree with the ncu launch list (profiles/r01g_bench.json vs r01c_launch_shares.txt)
-            step(f, device_resident, serial=bool(profile))
-            ntracked += bts[0].counters(0)["num_tracked"]
+            # around a launch also measures the time the launch queued behind other batches' kernels
+            frame_step(f, device_resident, serial=bool(profile) and not args.profile_overlapped)
             f += 1
+        ntracked = float(np.mean([bts[i].counters(s)["num_tracked"] for i in range(NB) for s in range(0, sizes[i], max(1, sizes[i] // 8))]))
         for i in range(NB):
             e1[i].record(exts[i])
         barrier()
@@ -389,47 +431,81 @@ def run_ours(args):
         L.xivo_profile_report(buf, len(buf))
         prof = json.loads(buf.value.decode())
         ms = replicas.max_over_ranks(ms, device="cuda")
-        return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked / K)
+        return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked)
 
     # three passes over consecutive frames of the same streams: the two measured ones run with the in-library
     # profiler off (its event records and locks cost ~1 ms/step); the third only attributes time to kernels
-    r_dev = timed(True, 0)
+    r_dev = timed(True, 0, K)
     log("device-resident pass", r_dev["ms"], "ms")
     L.xivo_set_frame_ingest.restype = C.c_int
-    ingest, ingest_cal, f = calibrate_ingest(args.ingest, L.xivo_set_frame_ingest, lambda k: step(k, False), torch.cuda.synchronize, f)
+
+    def cal_step(k):
+        frame_step(k, False)
+
+    ingest, ingest_cal, f = calibrate_ingest(args.ingest, L.xivo_set_frame_ingest, cal_step, torch.cuda.synchronize, f)
     log("frame ingest:", ingest, ingest_cal)
-    r_e2e = timed(False, 0)
+    r_e2e = timed(False, 0, K)
     log("e2e pass", r_e2e["ms"], "ms")
-    r_prof = timed(not args.profile_e2e, args.profile_level)
+    r_prof = timed(not args.profile_e2e, args.profile_level, K_prof)
     log("profiled pass", r_prof["ms"], "ms")
-    frames_total = world * B * K
+    frames_total = world * B * K * FPS
     value = frames_total / (r_dev["ms"] * 1e-3)
     e2e = frames_total / (r_e2e["ms"] * 1e-3)
 
+    # single-sequence latency (the reference runs ONE stream at 1-7 ms per frame): a batch of one, host frames, synchronous
+    single = None
+    if args.single_stream and rank == 0:
+        b1 = pyxivo.Batch(cfg, n_seq=1, max_groups=G, max_features=F, ctx=ctxs[0])
+        t1 = tabs[0]
+        lat = []
+        for ff in range(48):
+            j = ff * IMU_PER_FRAME
+            its = np.ascontiguousarray(t1["its"][j : j + IMU_PER_FRAME, :1])
+            ig = np.ascontiguousarray(t1["ig"][j : j + IMU_PER_FRAME, :1])
+            ia = np.ascontiguousarray(t1["ia"][j : j + IMU_PER_FRAME, :1])
+            fts = np.ascontiguousarray(t1["fts"][ff, :1])
+            ptr = (C.c_void_p * 1)(int(t1["hptr"][ff, 0]))
+            tq = time.perf_counter()
+            rc = L.xivo_batch_step(b1._h, IMU_PER_FRAME, VP(its.ctypes.data), VP(ig.ctypes.data), VP(ia.ctypes.data), VP(fts.ctypes.data), ptr, ROWS, COLS, CH, 0)
+            b1.gsb(0)
+            lat.append((time.perf_counter() - tq) * 1e3)
+            if rc != 0:
+                raise RuntimeError(L.xivo_last_error().decode())
+        lat = np.array(lat[24:])  # frames after the reorder buffer filled and the first detections happened
+        single = dict(ms_per_frame_median=float(np.median(lat)), ms_per_frame_p95=float(np.percentile(lat, 95)), fps=float(1e3 / np.median(lat)),
+                      note="one sequence, batch of 1, host frame in -> pose out per call (wall clock); the reference's published single-stream figure is 140 FPS (BASELINE.md)")
+        b1.close()
+
     peaks = measured_peaks()
-    roofline, host_phases = build_roofline(r_prof["prof"], K, peaks, sizes[0], r_prof["ms"])
+    roofline, host_phases = build_roofline(r_prof["prof"], K_prof * FPS, peaks, sizes[0], r_prof["ms"])
 
     out = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = min(cpu_budget(), args.cpu_cores) if args.cpu_cores else cpu_budget()  # CPUs the cgroup quota lets us run concurrently
+            # CPUs the cgroup quota lets us run concurrently (measured before the library pinned this thread: pin_driver narrows the affinity mask)
+            cores = min(budget_all, args.cpu_cores) if args.cpu_cores else budget_all
             t0 = time.time()
             log("cpu baseline on", cores, "cores")
-            r = cpu_reference(cores, 80, 14)
-            cpu = cpu_baseline_entry(r, cores, 80, time.time() - t0)
+            r = cpu_reference(cores, 60, 14, CH)
+            cpu = cpu_baseline_entry(r, cores, 60, time.time() - t0)
+        pool_mb = S0 * NFB * fbytes / 1e6
         out = dict(metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=W,
                    ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="f64" if args.cov_update == "fp64" else "f64 state, 3xTF32 tensor-core covariance downdate", data="synthetic",
                    config=dict(covariance_update=args.cov_update, workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
-                               sequences_per_gpu=B, batches_per_gpu=NB, host_threads=int(os.environ.get("XIVO_THREADS", "0")) or None, host_cpu_budget=budget, distinct_streams=S, frames_per_step=world * B, channels=1,
-                               l2_policy="inputs larger than L2 are not needed: every step reads a new frame set (B x 307 KB) from the stream buffers; covariance/pyramids are the resident state by design",
+                               sequences_per_gpu=B, batches_per_gpu=NB, frames_per_sequence_per_step=FPS, frames_per_step=world * B * FPS,
+                               host_threads=int(os.environ.get("XIVO_THREADS", "0")) or None, host_cpu_budget=budget, channels=CH,
+                               distinct_streams=f"{S0} base streams (own texture / trajectory amplitude / noise, period {PERIOD_S:g} s replayed) x start delays of {STAGGER} frames: "
+                                                f"no two sequences of a GPU read the same frame in the same step",
+                               l2_policy=f"inputs larger than L2: a step reads {B * FPS} distinct frames ({B * FPS * fbytes / 1e6:.0f} MB) per GPU out of a {pool_mb:.0f} MB frame pool; "
+                                         f"covariances and pyramids are the resident state by design",
                                message_buffer_size=cfg.get("message_buffer_size", 10), frame_ingest=ingest,
                                frame_ingest_calibration_ms_per_step=ingest_cal),
-                   e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * fbytes,
+                   e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * FPS * fbytes,
                             d2h_bytes_per_step=(r_e2e["prof"]["_d2h_bytes"] / K) if r_e2e["prof"]["_d2h_bytes"] else None, ms_per_step=r_e2e["ms"] / K),
-                   gpu_launches=r_dev["launches"], clocks=r_dev["clocks"], roofline=roofline, cpu_baseline=cpu,
-                   tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K, host_phase_ms_per_step=host_phases)
+                   gpu_launches=r_dev["launches"], clocks=r_dev["clocks"], roofline=roofline, cpu_baseline=cpu, single_stream=single,
+                   tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K, host_phase_ms_per_frame_step=host_phases)
         print(json.dumps(out))
     pool.shutdown()
     for b_ in bts:
@@ -442,21 +518,24 @@ def run_ours(args):
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the same path on this box's host cores (oracle/cpu_baseline.py: cv2 tracker
+    calls + the reference's own estimator library built from its unmodified sources), one sequence per allowed CPU.  A step is the
+    same unit as in the CUDA arm (--frames-per-step consecutive frames of every sequence), on a bounded sample: at most 240 timed
+    frames per sequence, so that the run ends within a few minutes whatever K the driver asks for."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cfg = load_cfg()
     cores = min(cpu_budget(), args.cpu_cores) if args.cpu_cores else cpu_budget()  # CPUs the cgroup quota lets us run concurrently
-    K, W = args.steps, args.warmup
-    K_eff = min(K, 60)  # bounded sample: the restated pipeline around the timed numerics is Python
+    K, W, FPS = args.steps, args.warmup, args.frames_per_step
+    frames = min(K * FPS, 240)
     t0 = time.time()
-    r = cpu_reference(cores, K_eff, PREROLL_FRAMES + W)
-    cb = cpu_baseline_entry(r, cores, K_eff, time.time() - t0)
-    ms_per_step = 1e3 * cores / cb["value"]  # one step = one frame on each of `cores` concurrent sequences
+    r = cpu_reference(cores, frames, PREROLL_FRAMES + min(W * FPS, 24), args.channels)
+    cb = cpu_baseline_entry(r, cores, frames, time.time() - t0)
+    ms_per_step = 1e3 * cores * FPS / cb["value"]  # one step = FPS frames on each of `cores` concurrent sequences
     out = dict(impl="reference", metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=cb["value"], unit="frames/s", n_gpus=args.gpus,
-               steps=K_eff, warmup=W, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+               steps=K, warmup=W, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                config=dict(workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
-                           sequences=cores, channels=1),
+                           sequences=cores, frames_per_sequence_per_step=FPS, timed_frames_per_sequence=frames, channels=args.channels),
                cpu_baseline=cb,
                e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out))
@@ -473,7 +552,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=512, help="independent sequences per GPU, split over --batches lock-step batches")
     ap.add_argument("--batches", type=int, default=8, help="independent lock-step batches per GPU, one driver thread each; their host phases share the library's worker pool")
-    ap.add_argument("--streams", type=int, default=4, help="distinct synthetic input streams shared by the sequences")
+    ap.add_argument("--streams", type=int, default=16, help="rendered base streams (texture / trajectory / noise); every sequence replays one of them with its own start delay")
+    ap.add_argument("--frames-per-step", type=int, default=8, help="a step = this many consecutive frames (+ IMU) of every sequence: K driver-chosen steps then time seconds, not milliseconds")
+    ap.add_argument("--channels", type=int, default=1, choices=[1, 3], help="1 = grey frames (default), 3 = BGR like the reference's cv::imread input (src/app/vio.cpp:72)")
+    ap.add_argument("--profile-steps", type=int, default=4, help="steps of the (serial, slow) kernel-attribution pass")
+    ap.add_argument("--profile-overlapped", action="store_true", help="attribution pass with the batches in flight together (event durations then include queueing)")
+    ap.add_argument("--max-threads", type=int, default=16, help="cap on host threads per rank (workers + drivers): more than this measured slower (SCALE_r01: 88 threads 2.3x slower than 16)")
+    ap.add_argument("--no-single-stream", dest="single_stream", action="store_false", help="skip the batch-of-one latency measurement")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cov-update", default="fp64", choices=["fp64", "tf32x3"], help="arithmetic of the covariance downdate (tf32x3 = tcgen05 tensor cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

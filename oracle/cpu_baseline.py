@@ -188,7 +188,8 @@ if __name__ == "__main__":  # python -m oracle.cpu_baseline <cfg.json> <procs> <
     import sys
 
     cfg_path, procs, frames, skip, G_, F_ = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+    channels_ = int(sys.argv[7]) if len(sys.argv) > 7 else 1
     sys.path.insert(0, os.path.dirname(_HERE))
     from xivo_b200 import sim
 
-    print(json.dumps(run(sim.load_cfg(cfg_path), procs, frames, skip, G_, F_)))
+    print(json.dumps(run(sim.load_cfg(cfg_path), procs, frames, skip, G_, F_, channels_)))

@@ -515,6 +515,13 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   return v;
 }
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+// Exact warp sum of per-lane int32 partials (the total may need 37 bits): the 16-bit halves are reduced separately with the
+// hardware warp reduction (redux.sync, 2 instructions) instead of 5 shuffle + 64-bit add rounds; v = (v >> 16) * 65536 + (v & 0xffff).
+__device__ __forceinline__ long long warp_sum_i32_exact(int v) {
+  const int slo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+  const int shi = __reduce_add_sync(0xffffffffu, v >> 16);
+  return ((long long)shi << 16) + slo;
+}
 
 struct LKParams {
   int win, max_iter, use_initial_flow, max_pts;
@@ -853,7 +860,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
     // template + structure tensor: slot s of this lane is window pixel (y = 2 s + r, x = c)
     // PACK: Ix | Iy << 16 in one register (|Ix|, |Iy| <= 4080) to raise occupancy
     int tI[NS], tX[NS], tY[PACK ? 1 : NS];
-    long long lA11 = 0, lA12 = 0, lA22 = 0;
+    int pA11 = 0, pA12 = 0, pA22 = 0;  // per-lane partials: <= 8 samples of |Ix|, |Iy| <= 4080 -> < 2^27
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       const int y = 2 * s + r;
@@ -868,13 +875,11 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
       tI[s] = ival;
       if (PACK) tX[s] = (ix & 0xffff) | (iy << 16);
       else { tX[s] = ix; tY[s] = iy; }
-      lA11 += ix * ix;
-      lA12 += ix * iy;
-      lA22 += iy * iy;
+      pA11 += ix * ix;
+      pA12 += ix * iy;
+      pA22 += iy * iy;
     }
-    lA11 = warp_sum_ll(lA11);
-    lA12 = warp_sum_ll(lA12);
-    lA22 = warp_sum_ll(lA22);
+    const long long lA11 = warp_sum_i32_exact(pA11), lA12 = warp_sum_i32_exact(pA12), lA22 = warp_sum_i32_exact(pA22);
     const float A11 = __ll2float_rn(lA11) * FLT_SCALE, A12 = __ll2float_rn(lA12) * FLT_SCALE, A22 = __ll2float_rn(lA22) * FLT_SCALE;
     float D = A11 * A22 - A12 * A12;
     const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
@@ -925,22 +930,21 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
       iw10 = __float2int_rn((1.f - a) * b * 16384.f);
       iw11 = 16384 - iw00 - iw01 - iw10;
       const bool interior = (inx >= 0 && iny >= 0 && inx + WIN < cols && iny + WIN < rows);
-      long long lb1 = 0, lb2 = 0;
+      int pb1 = 0, pb2 = 0;  // per-lane partials: <= 8 samples of |diff| <= 8160 times |I'| <= 4080 -> < 2^29
       int v0[NS], v1[NS];
       fetch(inx, iny, interior, v0, v1);
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const int diff = bilinear(v0[s], v1[s]) - tI[s];
         if (PACK) {
-          lb1 += diff * (int)(short)(tX[s] & 0xffff);
-          lb2 += diff * (tX[s] >> 16);
+          pb1 += diff * (int)(short)(tX[s] & 0xffff);
+          pb2 += diff * (tX[s] >> 16);
         } else {
-          lb1 += diff * tX[s];
-          lb2 += diff * tY[s];
+          pb1 += diff * tX[s];
+          pb2 += diff * tY[s];
         }
       }
-      lb1 = warp_sum_ll(lb1);
-      lb2 = warp_sum_ll(lb2);
+      const long long lb1 = warp_sum_i32_exact(pb1), lb2 = warp_sum_i32_exact(pb2);
       const float b1 = __ll2float_rn(lb1) * FLT_SCALE, b2 = __ll2float_rn(lb2) * FLT_SCALE;
       const float dx = (A12 * b2 - A22 * b1) * D;
       const float dy = (A12 * b1 - A11 * b2) * D;
@@ -970,15 +974,15 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
       iw01 = __float2int_rn(aa * (1.f - bb) * 16384.f);
       iw10 = __float2int_rn((1.f - aa) * bb * 16384.f);
       iw11 = 16384 - iw00 - iw01 - iw10;
-      long long le = 0;
+      int pe = 0;
       int v0[NS], v1[NS];
       fetch(inx, iny, false, v0, v1);
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         const int diff = bilinear(v0[s], v1[s]) - tI[s];
-        if (c < WIN && 2 * s + r < WIN) le += abs(diff);
+        if (c < WIN && 2 * s + r < WIN) pe += abs(diff);
       }
-      le = warp_sum_ll(le);
+      const long long le = warp_sum_i32_exact(pe);
       errv = __ll2float_rn(le) * 1.f / (float)(32 * WIN * WIN);
     }
   }

@@ -84,6 +84,15 @@ class Trajectory:
         return self.R(t).T @ (self.acc(t) - G_S)
 
 
+def periodic_trajectory(period=4.0, amp_scale=1.0):
+    """A Trajectory that is exactly periodic with `period` seconds and passes through rest (p = v = theta = omega = 0) at t = k * period:
+    every frequency is a multiple of 1 / period (the attitude terms A sin^2(2 pi f t) have period 1 / (2 f)).  One rendered period can
+    then be replayed for ever as a physically consistent stream (bench.py)."""
+    k = 1.0 / period
+    return Trajectory(amp=np.array([0.6, 0.4, 0.2]) * amp_scale, freq=np.array([2 * k, 1 * k, 1 * k]),
+                      rot_amp=np.array([0.10, 0.08, 0.25]) * amp_scale, rot_freq=np.array([1 * k, 1 * k, 0.5 * k]))
+
+
 def make_world(n=1000, seed=0, xlim=(-4, 4), ylim=(1.0, 6.0), zlim=(-3, 3)):
     rng = np.random.default_rng(seed)
     return np.column_stack([rng.uniform(*xlim, n), rng.uniform(*ylim, n), rng.uniform(*zlim, n)])
@@ -224,7 +233,7 @@ class PlaneRenderer:
 
 
 def image_stream(cfg: dict, duration=2.0, imu_dt=0.005, vision_dt=0.04, seed=0, noise_accel=1e-4, noise_gyro=1e-5,
-                 stationary=0.2, channels=1, traj=None, fast=False):
+                 stationary=0.2, channels=1, traj=None, fast=False, rest_accel_is_gravity=False):
     """IMU + rendered frames.  `stationary` seconds of rest first so that gravity initialisation
     (estimator.cpp:439-473) sees still samples when simulation=false."""
     traj = traj or Trajectory()
@@ -239,7 +248,8 @@ def image_stream(cfg: dict, duration=2.0, imu_dt=0.005, vision_dt=0.04, seed=0, 
     tt = lambda t: max(0.0, t - stationary)
     msgs = []
     for t in np.arange(0, duration, imu_dt):
-        msgs.append((t, 0, "imu", (traj.gyro(tt(t)) * (t >= stationary) + rng.normal(0, noise_gyro, 3), traj.accel(tt(t)) + rng.normal(0, noise_accel, 3))))
+        acc = traj.R(0.0).T @ (-G_S) if (rest_accel_is_gravity and t < stationary) else traj.accel(tt(t))  # bench: a platform at rest measures gravity only
+        msgs.append((t, 0, "imu", (traj.gyro(tt(t)) * (t >= stationary) + rng.normal(0, noise_gyro, 3), acc + rng.normal(0, noise_accel, 3))))
     for t in np.arange(0, duration, vision_dt):
         Rsc, Tsc = camera_pose(traj, tt(t), Rbc, Tbc)
         img = rend.render(Rsc, Tsc, rng, fast)
