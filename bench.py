@@ -494,7 +494,7 @@ def run_ours(args):
                    ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="f64" if args.cov_update == "fp64" else "f64 state, 3xTF32 tensor-core covariance downdate", data="synthetic",
                    config=dict(covariance_update=args.cov_update, workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
-                               sequences_per_gpu=B, batches_per_gpu=NB, frames_per_sequence_per_step=FPS, frames_per_step=world * B * FPS,
+                               sequences_per_gpu=B, batches_per_gpu=NB, lanes_per_batch=bts[0].lanes, cpu_tokens=os.environ.get("XIVO_CPU_TOKENS"), frames_per_sequence_per_step=FPS, frames_per_step=world * B * FPS,
                                host_threads=int(os.environ.get("XIVO_THREADS", "0")) or None, host_cpu_budget=budget, channels=CH,
                                distinct_streams=f"{S0} base streams (own texture / trajectory amplitude / noise, period {PERIOD_S:g} s replayed) x start delays of {STAGGER} frames: "
                                                 f"no two sequences of a GPU read the same frame in the same step",
@@ -551,7 +551,7 @@ def main():
     ap.add_argument("--profile-level", type=int, default=1, help="1: kernels + batch-level host phases, 2: + per-sequence host scopes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=512, help="independent sequences per GPU, split over --batches lock-step batches")
-    ap.add_argument("--batches", type=int, default=8, help="independent lock-step batches per GPU, one driver thread each; their host phases share the library's worker pool")
+    ap.add_argument("--batches", type=int, default=1, help="separate xivo_batch handles per GPU, each stepped from its own Python thread (1 = one handle; the library splits it into lanes, see config.lanes)")
     ap.add_argument("--streams", type=int, default=16, help="rendered base streams (texture / trajectory / noise); every sequence replays one of them with its own start delay")
     ap.add_argument("--frames-per-step", type=int, default=8, help="a step = this many consecutive frames (+ IMU) of every sequence: K driver-chosen steps then time seconds, not milliseconds")
     ap.add_argument("--channels", type=int, default=1, choices=[1, 3], help="1 = grey frames (default), 3 = BGR like the reference's cv::imread input (src/app/vio.cpp:72)")

@@ -5,7 +5,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -73,8 +75,51 @@ struct Mirror {
   }
 };
 
+// CPU tokens: with more lane threads than CPUs in the quota, at most `count` of them run host code at a time; a lane hands its token
+// back while it sleeps on a CUDA event.  (Exceeding a cgroup CPU quota stalls every thread of the process for the rest of the period.)
+class CpuTokens {
+ public:
+  static CpuTokens& get() {
+    static CpuTokens t;
+    return t;
+  }
+  void acquire() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return avail_ > 0; });
+    --avail_;
+  }
+  void release() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      ++avail_;
+    }
+    cv_.notify_one();
+  }
+  int count() const { return count_; }
+
+ private:
+  CpuTokens() {
+    const char* e = getenv("XIVO_CPU_TOKENS");
+    int n = e && *e ? atoi(e) : 0;
+    if (n <= 0) {
+      const char* lw = getenv("LOCAL_WORLD_SIZE");
+      const int local_world = std::max(1, lw && *lw ? atoi(lw) : 1);
+      n = std::max(1, host_cpu_budget() / local_world - 1);  // one CPU stays with the caller / CUDA's helper threads
+    }
+    count_ = avail_ = n;
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  int avail_ = 1, count_ = 1;
+};
+
 class Batch {
  public:
+  // lane mode: this batch is one lane of a multi-lane xivo_batch and is driven by its own thread; its per-sequence host code runs
+  // inline on that thread and GPU waits sleep on a blocking event with the CPU token handed back
+  bool lane_mode = false;
+  cudaStream_t st1 = nullptr;  // image-tracker stream: the context's stream for lane 0, an own one otherwise
+  bool own_st1 = false;
   // Per-sequence host logic is independent across sequences: run it on the process-wide worker pool
   // (workpool.h).  CUDA calls stay on the calling thread.
   // An exception thrown by the host state machine (std::out_of_range of a container lookup, std::bad_alloc) must neither reach a
@@ -89,6 +134,14 @@ class Batch {
   }
   template <typename Fn>
   void pfor(const std::vector<int>& idx, Fn fn) {
+    if (lane_mode) {
+      for (int i = 0; i < (int)idx.size(); ++i) {
+        try { fn(idx[i], i); }
+        catch (const std::exception& ex) { pfor_record(ex.what()); }
+        catch (...) { pfor_record("unknown exception"); }
+      }
+      return;
+    }
     WorkPool::get().pfor((int)idx.size(), [&](int i) {
       try { fn(idx[i], i); }
       catch (const std::exception& ex) { pfor_record(ex.what()); }
@@ -144,14 +197,22 @@ class Batch {
   Mirror<uint8_t> lkst;
   Mirror<int> npts, kpcount;
   Mirror<unsigned> kp;
+  // device-side tracker decisions (track_accept_kernel / track_select_kernel)
+  bool dev_decide = false;
+  Mirror<int> tkind, tneed, tnnew;
+  Mirror<uint8_t> tstat;
+  Mirror<unsigned> tnewkp;
   std::string err;
 
-  Batch(xivo_ctx* c, const Json& cfg, int nseq, EkfLayout l, bool tracker_only) : ctx(c), B(nseq), lay(l) {
+  Batch(xivo_ctx* c, const Json& cfg, int nseq, EkfLayout l, bool tracker_only, int lane = 0, bool lanes = false) : ctx(c), B(nseq), lay(l) {
     N = lay.N();
+    lane_mode = lanes;
+    if (lane == 0) st1 = ctx->stream;
+    else { cudaStreamCreateWithFlags(&st1, cudaStreamNonBlocking); own_st1 = true; }
     cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&stg_ev, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&wait_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&wait_ev, cudaEventDisableTiming | (lane_mode ? cudaEventBlockingSync : 0));
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
     cov_tc = est[0]->c.cov_update_tf32x3 ? 1 : 0;
     maxops = 4 * (lay.F + lay.G) + 16;
@@ -189,13 +250,14 @@ class Batch {
       }
       for (int i = 0; i < N; ++i) est[b]->diagP[i] = P0[(size_t)i * N + i];
     }
-    cam.up(ctx->stream);
-    R.up(ctx->stream);
-    icst.up(ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
+    cam.up(st1);
+    R.up(st1);
+    icst.up(st1);
+    cudaStreamSynchronize(st1);
   }
   ~Batch() {
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(st1);
+    if (own_st1) cudaStreamDestroy(st1);
     if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
     if (stg_ev) cudaEventDestroy(stg_ev);
     if (wait_ev) cudaEventDestroy(wait_ev);
@@ -208,7 +270,7 @@ class Batch {
     nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); stg.release(); stg_first.release(); stg_n.release();
     icst.release(); off_prev.release(); frame_ptr.release(); ingest_ptr.release(); ingest_off.release();
     off_cur.release(); pts0.release(); pts1.release(); lkerr.release(); lkst.release(); npts.release(); kpcount.release();
-    kp.release();
+    kp.release(); tkind.release(); tneed.release(); tnnew.release(); tstat.release(); tnewkp.release();
   }
 
   int fail(int code, const std::string& m) {
@@ -292,6 +354,14 @@ class Batch {
   // Wait for a stream without idling the CPU: while the event is pending the driver executes items of
   // whatever host jobs the other batches of this process have published.
   int wait(cudaStream_t st) {
+    if (lane_mode) {  // sleep on the event; the CPU goes to a lane that has host work
+      XB_CUDA(cudaEventRecord(wait_ev, st));
+      CpuTokens::get().release();
+      const cudaError_t e = cudaEventSynchronize(wait_ev);
+      CpuTokens::get().acquire();
+      if (e != cudaSuccess) { set_error("CUDA error while waiting: %s", cudaGetErrorString(e)); return XIVO_ERR_CUDA; }
+      return 0;
+    }
     static const bool help = !(getenv("XIVO_HELP") && getenv("XIVO_HELP")[0] == '0');
     if (!help) { XB_CUDA(cudaStreamSynchronize(st)); return 0; }
     XB_CUDA(cudaEventRecord(wait_ev, st));
@@ -328,7 +398,24 @@ class Batch {
       if (int rc = launch_gather_frames(st_copy, ingest_ptr.d, dRing, 0, ingest_off.d, ib, B, on_device ? 64 : 8)) return rc;
       g_launches += 1;
     } else {
-      for (int s = 0; s < B; ++s) XB_CUDA(cudaMemcpyAsync(dRing + ingest_off.h[s], imgs[s], ib, cudaMemcpyHostToDevice, st_copy));
+      // copy engine: runs of sequences whose sources are evenly spaced (frames of one pinned pool) and whose ring slots agree go down as
+      // ONE pitched copy each (measured on the B200 box: 55 GB/s for pitched copies of 307 KB rows against 32 GB/s for one call per frame)
+      int s = 0;
+      while (s < B) {
+        int e = s + 1;
+        if (e < B && slot_of[e] == slot_of[s] && imgs[e] > imgs[s]) {
+          const size_t stride = (size_t)(imgs[e] - imgs[s]);
+          if (stride >= ib) {
+            while (e + 1 < B && slot_of[e + 1] == slot_of[s] && imgs[e + 1] > imgs[e] && (size_t)(imgs[e + 1] - imgs[e]) == stride) ++e;
+            ++e;
+            XB_CUDA(cudaMemcpy2DAsync(dRing + ingest_off.h[s], (size_t)ring_n * ib, imgs[s], stride, ib, (size_t)(e - s), cudaMemcpyHostToDevice, st_copy));
+            s = e;
+            continue;
+          }
+        }
+        XB_CUDA(cudaMemcpyAsync(dRing + ingest_off.h[s], imgs[s], ib, cudaMemcpyHostToDevice, st_copy));
+        ++s;
+      }
     }
     std::vector<int> used;
     for (int k : slot_of)
@@ -367,6 +454,14 @@ class Batch {
     ok = ok && frame_ptr.alloc(B) && ingest_ptr.alloc(B) && ingest_off.alloc(B) && off_prev.alloc(B) && off_cur.alloc(B) && pts0.alloc((size_t)B * max_pts * 2) && pts1.alloc((size_t)B * max_pts * 2) &&
          lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && npts.alloc(B) && kpcount.alloc(B) &&
          kp.alloc((size_t)B * max_kp);
+    // the accept / select decisions run on the device unless the homography stage (host code between the two) is on, the mask does
+    // not fit into shared memory, or XIVO_HOST_TRACKER_DECISIONS=1 asks for the host path (parity tests compare the two)
+    {
+      const char* hd = getenv("XIVO_HOST_TRACKER_DECISIONS");
+      dev_decide = !e0.tc.do_outlier_rejection && track_mask_bytes(rows, cols) <= 200 * 1024 && !(hd && hd[0] == '1');
+      if (dev_decide)
+        ok = ok && tkind.alloc(B) && tneed.alloc(B) && tnnew.alloc(B) && tstat.alloc((size_t)B * max_pts) && tnewkp.alloc((size_t)B * e0.tc.num_features_max);
+    }
     if (!ok) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
     ring_next.assign(B, 0);
     ring_ev.resize(ring_n);
@@ -375,7 +470,7 @@ class Batch {
     for (auto& e : est) {
       e->rows = rows; e->cols = cols;
       e->mask_stride = (cols + 63) / 64;
-      e->mask.assign((size_t)rows * e->mask_stride, 0);
+      if (!dev_decide) e->mask.assign((size_t)rows * e->mask_stride, 0);  // the host bitmap exists only on the host-decision path
     }
     img_ready = true;
     return 0;
@@ -419,10 +514,92 @@ class Batch {
     }
   }
 
+  // The rest of Tracker::UpdateLK with the decisions on the device: LK -> accept loop (track_accept_kernel) -> FAST for the sequences
+  // the accept kernel flagged -> greedy selection (track_select_kernel) -> ONE read-back of [positions | keep flags | picks].  The host
+  // then only replays the decisions on its track list (same order, same feature ids as the host path).
+  int tracker_decide_on_device(const std::vector<int>& act, const std::vector<int>& lk_list, const std::vector<int>& det_first,
+                               const std::vector<int>& kind) {
+    cudaStream_t st = st1;
+    const TrackerCfg& tc = est[0]->tc;
+    Estimator& e0 = *est[0];
+    if (e0.mask_half < 0) e0.mask_half = tc.mask_size >> 1;
+    const int max_new = tc.num_features_max;
+    TrackDecideCfg dc{rows, cols, tc.margin, tc.mask_size >> 1, tc.num_features_min, tc.num_features_max, max_pts, max_kp, max_new,
+                      (double)tc.max_pixel_displacement};
+    for (int b = 0; b < B; ++b) tkind.h[b] = 0;
+    for (int b : act) tkind.h[b] = kind[b];
+    XB_CUDA(tkind.up(st));
+    if (!lk_list.empty()) {
+      XB_CUDA(pts0.up(st)); XB_CUDA(pts1.up(st));
+      if (int rc = launch_lk_track(st, dPyr, dPyr, 0, off_prev.d, off_cur.d, pd, pts0.d, pts1.d, lkst.d, lkerr.d, npts.d, max_pts, B,
+                                   tc.win_size, tc.max_iter, tc.eps, 1, 1e-4))
+        return rc;
+      g_launches += 1;
+      double np_ = 0;
+      for (int b : lk_list) np_ += npts.h[b];
+      Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
+    }
+    if (int rc = launch_track_accept(st, dc, tkind.d, npts.d, pts0.d, pts1.d, lkst.d, tstat.d, tneed.d, B)) return rc;
+    // FAST on the current level-0 image of every tracked sequence; the kernel skips those whose need is 0
+    for (int b = 0; b < B; ++b) off_prev.h[b] = ~0ull;  // reuse off_prev as the FAST selector
+    for (int b : act)
+      if (kind[b] == 1 || kind[b] == 2) off_prev.h[b] = ((size_t)b * 2 + (1 - prev_slot[b])) * pd.total;
+    XB_CUDA(off_prev.up(st));
+    if (int rc = launch_fast_detect(st, dPyr, 0, off_prev.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, tneed.d))
+      return rc;
+    if (int rc = launch_track_select(st, dc, tkind.d, npts.d, pts1.d, tstat.d, tneed.d, kp.d, kpcount.d, tnewkp.d, tnnew.d, B)) return rc;
+    g_launches += 3;
+    if (!lk_list.empty()) { XB_CUDA(pts1.down(st)); XB_CUDA(tstat.down(st)); }
+    XB_CUDA(tneed.down(st)); XB_CUDA(tnnew.down(st)); XB_CUDA(tnewkp.down(st));
+    { HostScope hw("wait_lk"); if (int rc = wait(st)) return rc; }
+    {
+      int ndet = 0;
+      for (int b : act) ndet += tneed.h[b] > 0;
+      Prof::get().add_work("fast_detect", ndet * 2.0 * rows * cols);  // §8d: 2 W H bytes
+    }
+    HostScope hs("tracker_accept");
+    pfor(act, [&](int b, int) {
+      HostScope hx("x_trk_replay");
+      Estimator& e = *est[b];
+      if (kind[b] == 3) return;
+      if (kind[b] == 2) {
+        int i = 0, num_failed = 0;
+        for (Feature* f : e.tracks) {
+          const float* p1 = pts1.h + ((size_t)b * max_pts + i) * 2;
+          if (tstat.h[(size_t)b * max_pts + i]) {
+            f->tstatus = TrackStatus::TRACKED;
+            f->observe((double)p1[0], (double)p1[1]);
+          } else {
+            f->tstatus = TrackStatus::DROPPED;
+            ++num_failed;
+          }
+          ++i;
+        }
+        e.num_new_detections = 0;
+        e.num_failed_to_track = num_failed;
+      }
+      if (tneed.h[b] > 0) {
+        const int nn = std::min(tnnew.h[b], max_new);
+        for (int j = 0; j < nn; ++j) {
+          const unsigned k = tnewkp.h[(size_t)b * max_new + j];
+          Feature* f = e.create_feature((double)((k >> 8) & 0xfff), (double)(k >> 20));
+          if (!f) return;
+          f->response = (float)(k & 0xff);
+          e.tracks.push_back(f);
+          e.num_new_detections++;
+        }
+        e.tracker_initialized = true;
+      }
+    });
+    for (int b : act)
+      if (off_cur.h[b] != ~0ull) prev_slot[b] = 1 - prev_slot[b];  // std::swap(pyramid, pyramid_)
+    return 0;
+  }
+
   // Tracker::UpdateLK (tracker.cpp:463-629) for the sequences in `act` whose message holds ring slot
   // slots[i].  Descriptor / rescue / homography branches are out of scope.
   int tracker_update_lk(const std::vector<int>& act, const std::vector<int>& slots) {
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = st1;
     const size_t ib = (size_t)rows * cols * cn;
     std::vector<int> lk_list, det_list;
     std::vector<int> det_budget(B, 0), kind(B, 0);  // kind: 1 = first frame (detect only), 2 = LK, 3 = empty list
@@ -446,12 +623,14 @@ class Batch {
         HostScope hx("x_trk_prepare");
         Estimator& e = *est[b];
         if (!e.tracker_initialized) {
-          std::fill(e.mask.begin(), e.mask.end(), 0);
-          e.reset_mask();
+          if (!dev_decide) {
+            std::fill(e.mask.begin(), e.mask.end(), 0);
+            e.reset_mask();
+          }
           kind[b] = 1;
           return;
         }
-        e.reset_mask();
+        if (!dev_decide) e.reset_mask();
         int n = 0;
         for (Feature* f : e.tracks) {
           if (n >= max_pts) { overflow = 1; return; }
@@ -489,6 +668,7 @@ class Batch {
       for (int b = 0; b < B; ++b) nact += off_cur.h[b] != ~0ull;
       Prof::get().add_work("pyrdown", nact * (7.0 / 3.0) * rows * cols * cn);  // (7/3) W H c bytes
     }
+    if (dev_decide) return tracker_decide_on_device(act, lk_list, det_list, kind);
     if (!lk_list.empty()) {
       XB_CUDA(pts0.up(st)); XB_CUDA(pts1.up(st));
       const TrackerCfg& tc = est[0]->tc;
@@ -768,7 +948,7 @@ class Batch {
   // sequence runs ahead through its IMU messages until its heap releases a visual message; those are
   // then processed together, and the loop continues with the remaining messages.
   int ingest_many(std::vector<std::vector<Msg>>& in) {
-    WorkPool::get().pin_driver();
+    if (!lane_mode) WorkPool::get().pin_driver();
     std::vector<int> all(B), vis;
     std::vector<size_t> pos(B, 0);
     std::vector<Msg> popped(B), vmsgs;
@@ -813,7 +993,7 @@ class Batch {
 
   // Push one message per sequence, then execute whatever each heap releases (MaintainBuffer).
   int ingest(std::vector<Msg>& in) {
-    WorkPool::get().pin_driver();
+    if (!lane_mode) WorkPool::get().pin_driver();
     std::vector<int> all(B), vis;
     std::vector<Msg> popped(B), vmsgs;
     std::vector<char> has(B, 0);
@@ -844,22 +1024,108 @@ class Batch {
 }  // namespace xb
 
 using namespace xb;
+// A batch handle = one or more LANES: independent lock-step sub-batches of consecutive sequences, each with its own streams, device
+// state and a persistent driver thread.  The sequences of a batch are independent Markov chains, so a lane never talks to another lane;
+// while one lane sleeps on the GPU another one runs its host phases, which keeps both the CPUs of the quota and the GPU busy without
+// fork-join parallel-for rounds inside a phase.  Lane count: "lanes" in the config, else XIVO_LANES, else one lane per ~24 sequences
+// (at most twice the CPU budget); a batch of up to 24 sequences is a single lane driven by the calling thread.
 struct xivo_batch {
-  std::unique_ptr<Batch> impl;
+  xivo_ctx* ctx = nullptr;
+  int total = 0, per = 0, N = 0;
+  std::vector<std::unique_ptr<Batch>> lanes;
+  std::vector<int> first;  // lane l owns sequences [first[l], first[l + 1])
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  const std::function<int(int)>* job = nullptr;
+  unsigned long long gen = 0;
+  int pending = 0;
+  bool stop = false;
+  std::vector<int> rc;
+
+  int lane_of(int seq) const { return std::min((int)lanes.size() - 1, seq / per); }
+  void worker(int l) {
+    cudaSetDevice(ctx->device);
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<int(int)>* fn;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_go.wait(lk, [&] { return stop || gen != seen; });
+        if (stop) return;
+        seen = gen;
+        fn = job;
+      }
+      CpuTokens::get().acquire();
+      int r;
+      try { r = (*fn)(l); }
+      catch (const std::exception& ex) { r = lanes[l]->fail(XIVO_ERR_STATE, std::string("lane threw: ") + ex.what()); }
+      catch (...) { r = lanes[l]->fail(XIVO_ERR_STATE, "lane threw"); }
+      CpuTokens::get().release();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        rc[l] = r;
+        if (--pending == 0) cv_done.notify_all();
+      }
+    }
+  }
+  // fn(lane) on every lane (concurrently when there are several); first non-zero return code, its message re-published on this thread
+  int run(const std::function<int(int)>& fn) {
+    if (lanes.size() == 1) return fn(0);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = &fn;
+      pending = (int)lanes.size();
+      ++gen;
+    }
+    cv_go.notify_all();
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    for (size_t l = 0; l < lanes.size(); ++l)
+      if (rc[l]) { set_error("%s", lanes[l]->err.c_str()); return rc[l]; }
+    return 0;
+  }
+  ~xivo_batch() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv_go.notify_all();
+    for (auto& t : threads) t.join();
+  }
 };
 
+static int choose_lanes(const Json& cfg, int n_seq) {
+  int L = cfg.get("lanes", 0);
+  if (L <= 0) {
+    const char* e = getenv("XIVO_LANES");
+    L = e && *e ? atoi(e) : 0;
+  }
+  if (L <= 0) {
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    const int share = std::max(1, host_cpu_budget() / std::max(1, lw && *lw ? atoi(lw) : 1));
+    L = std::min((n_seq + 23) / 24, 2 * share);
+  }
+  return std::max(1, std::min(L, n_seq));
+}
+
 #define BATCH_BEGIN                                        \
-  if (!b || !b->impl) {                                    \
+  if (!b || b->lanes.empty()) {                            \
     set_error("null batch");                               \
     return XIVO_ERR_ARG;                                   \
   }                                                        \
-  Batch& B_ = *b->impl;                                    \
-  XB_CUDA(cudaSetDevice(B_.ctx->device));
+  xivo_batch& S_ = *b;                                     \
+  XB_CUDA(cudaSetDevice(S_.ctx->device));
+// maps the batch-wide sequence index to (lane B_, index inside the lane)
 #define SEQ_CHECK                                                  \
-  if (seq < 0 || seq >= B_.B) {                                    \
+  if (seq < 0 || seq >= S_.total) {                                \
     set_error("sequence index %d out of range", seq);              \
     return XIVO_ERR_ARG;                                           \
-  }
+  }                                                                \
+  Batch& B_ = *S_.lanes[S_.lane_of(seq)];                          \
+  seq -= S_.first[S_.lane_of(seq)];
 
 extern "C" {
 
@@ -872,8 +1138,22 @@ int xivo_batch_create(xivo_ctx* ctx, const char* cfg_json, int n_seq, int max_gr
   XB_CUDA(cudaSetDevice(ctx->device));
   try {
     Json cfg = Json::parse(cfg_json);
-    std::unique_ptr<Batch> impl(new Batch(ctx, cfg, n_seq, EkfLayout{max_groups, max_features}, tracker_only != 0));
-    *out = new xivo_batch{std::move(impl)};
+    std::unique_ptr<xivo_batch> S(new xivo_batch());
+    S->ctx = ctx;
+    S->total = n_seq;
+    const int L = choose_lanes(cfg, n_seq);
+    S->per = (n_seq + L - 1) / L;
+    for (int l = 0; l * S->per < n_seq; ++l) {
+      const int s0 = l * S->per, n = std::min(S->per, n_seq - s0);
+      S->first.push_back(s0);
+      S->lanes.emplace_back(new Batch(ctx, cfg, n, EkfLayout{max_groups, max_features}, tracker_only != 0, l, L > 1));
+    }
+    S->first.push_back(n_seq);
+    S->N = S->lanes[0]->N;
+    S->rc.assign(S->lanes.size(), 0);
+    if (S->lanes.size() > 1)
+      for (size_t l = 0; l < S->lanes.size(); ++l) S->threads.emplace_back([p = S.get(), l] { p->worker((int)l); });
+    *out = S.release();
   } catch (const std::exception& e) {
     set_error("batch_create: %s", e.what());
     return XIVO_ERR_ARG;
@@ -883,46 +1163,55 @@ int xivo_batch_create(xivo_ctx* ctx, const char* cfg_json, int n_seq, int max_gr
 
 void xivo_batch_destroy(xivo_batch* b) {
   if (!b) return;
-  if (b->impl) cudaSetDevice(b->impl->ctx->device);
+  if (b->ctx) cudaSetDevice(b->ctx->device);
   delete b;
 }
-int xivo_batch_size(const xivo_batch* b) { return b && b->impl ? b->impl->B : 0; }
-int xivo_batch_state_dim(const xivo_batch* b) { return b && b->impl ? b->impl->N : 0; }
+int xivo_batch_size(const xivo_batch* b) { return b ? b->total : 0; }
+int xivo_batch_state_dim(const xivo_batch* b) { return b ? b->N : 0; }
+int xivo_batch_lanes(const xivo_batch* b) { return b ? (int)b->lanes.size() : 0; }
 
 int xivo_batch_inertial_meas(xivo_batch* b, const uint64_t* ts_ns, const double* gyro, const double* accel) {
   BATCH_BEGIN;
   XB_REQUIRE(ts_ns && gyro && accel, "inertial_meas: null argument");
-  std::vector<Msg> in(B_.B);
-  for (int s = 0; s < B_.B; ++s) {
-    in[s].ts = ts_ns[s];
-    in[s].type = 0;
-    memcpy(in[s].gyro, gyro + 3 * s, 24);
-    memcpy(in[s].accel, accel + 3 * s, 24);
-  }
-  return B_.ingest(in);
+  return S_.run([&](int l) {
+    Batch& B_ = *S_.lanes[l];
+    const int s0 = S_.first[l];
+    std::vector<Msg> in(B_.B);
+    for (int s = 0; s < B_.B; ++s) {
+      in[s].ts = ts_ns[s0 + s];
+      in[s].type = 0;
+      memcpy(in[s].gyro, gyro + 3 * (size_t)(s0 + s), 24);
+      memcpy(in[s].accel, accel + 3 * (size_t)(s0 + s), 24);
+    }
+    return B_.ingest(in);
+  });
 }
 
 static int visual_meas_impl(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs, int rows, int cols, int channels,
                             int tracker_only, bool on_device) {
   BATCH_BEGIN;
   XB_REQUIRE(ts_ns && imgs && rows > 0 && cols > 0, "visual_meas: bad arguments");
-  if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
-  const size_t ib = (size_t)rows * cols * channels;
-  std::vector<Msg> in(B_.B);
-  std::vector<int> slot_of(B_.B);
-  for (int s = 0; s < B_.B; ++s) {
-    XB_REQUIRE(imgs[s], "visual_meas: null image");
-    const int slot = B_.ring_next[s];
-    B_.ring_next[s] = (slot + 1) % B_.ring_n;
-    slot_of[s] = slot;
-    in[s].ts = ts_ns[s];
-    in[s].type = tracker_only ? 2 : 1;
-    in[s].img_slot = slot;
-  }
-  if (int rc = B_.upload_frames(imgs, slot_of, on_device, ib)) return rc;
-  const int rc = B_.ingest(in);
-  const int rc2 = B_.ingest_done();
-  return rc ? rc : rc2;
+  for (int s = 0; s < S_.total; ++s) XB_REQUIRE(imgs[s], "visual_meas: null image");
+  return S_.run([&](int l) {
+    Batch& B_ = *S_.lanes[l];
+    const int s0 = S_.first[l];
+    if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
+    const size_t ib = (size_t)rows * cols * channels;
+    std::vector<Msg> in(B_.B);
+    std::vector<int> slot_of(B_.B);
+    for (int s = 0; s < B_.B; ++s) {
+      const int slot = B_.ring_next[s];
+      B_.ring_next[s] = (slot + 1) % B_.ring_n;
+      slot_of[s] = slot;
+      in[s].ts = ts_ns[s0 + s];
+      in[s].type = tracker_only ? 2 : 1;
+      in[s].img_slot = slot;
+    }
+    if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device, ib)) return rc;
+    const int rc = B_.ingest(in);
+    const int rc2 = B_.ingest_done();
+    return rc ? rc : rc2;
+  });
 }
 
 int xivo_batch_visual_meas(xivo_batch* b, const uint64_t* ts_ns, const uint8_t* const* imgs, int rows, int cols, int channels,
@@ -937,36 +1226,42 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
                     const uint8_t* const* imgs, int rows, int cols, int channels, int on_device) {
   BATCH_BEGIN;
   XB_REQUIRE(n_imu >= 0 && frame_ts && imgs && (n_imu == 0 || (imu_ts && gyro && accel)), "batch_step: bad arguments");
-  if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
-  const size_t ib = (size_t)rows * cols * channels;
-  const int nb = B_.B;
-  std::vector<std::vector<Msg>> in(nb);
-  std::vector<int> slot_of(nb);
-  HostScope* hm = new HostScope("marshal");
-  for (int s = 0; s < nb; ++s) {
-    XB_REQUIRE(imgs[s], "batch_step: null image");
-    in[s].resize(n_imu + 1);
-    for (int k = 0; k < n_imu; ++k) {
-      Msg& m = in[s][k];
-      m.ts = imu_ts[(size_t)k * nb + s];
-      m.type = 0;
-      memcpy(m.gyro, gyro + ((size_t)k * nb + s) * 3, 24);
-      memcpy(m.accel, accel + ((size_t)k * nb + s) * 3, 24);
-    }
-    const int slot = B_.ring_next[s];
-    B_.ring_next[s] = (slot + 1) % B_.ring_n;
-    slot_of[s] = slot;
-    Msg& v = in[s][n_imu];
-    v.ts = frame_ts[s];
-    v.type = 1;
-    v.img_slot = slot;
-  }
-  if (int rc = B_.upload_frames(imgs, slot_of, on_device != 0, ib)) return rc;
-  delete hm;
+  const int nb = S_.total;  // the IMU arrays are (n_imu, nb[, 3]) over ALL sequences of the batch
+  for (int s = 0; s < nb; ++s) XB_REQUIRE(imgs[s], "batch_step: null image");
   HostScope hst("ingest_many_total");
-  const int rc = B_.ingest_many(in);
-  const int rc2 = B_.ingest_done();
-  return rc ? rc : rc2;
+  return S_.run([&](int l) {
+    Batch& B_ = *S_.lanes[l];
+    const int s0 = S_.first[l];
+    if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
+    const size_t ib = (size_t)rows * cols * channels;
+    std::vector<std::vector<Msg>> in(B_.B);
+    std::vector<int> slot_of(B_.B);
+    {
+      HostScope hm("marshal");
+      for (int s = 0; s < B_.B; ++s) {
+        in[s].resize(n_imu + 1);
+        for (int k = 0; k < n_imu; ++k) {
+          Msg& m = in[s][k];
+          const size_t o = (size_t)k * nb + s0 + s;
+          m.ts = imu_ts[o];
+          m.type = 0;
+          memcpy(m.gyro, gyro + o * 3, 24);
+          memcpy(m.accel, accel + o * 3, 24);
+        }
+        const int slot = B_.ring_next[s];
+        B_.ring_next[s] = (slot + 1) % B_.ring_n;
+        slot_of[s] = slot;
+        Msg& v = in[s][n_imu];
+        v.ts = frame_ts[s0 + s];
+        v.type = 1;
+        v.img_slot = slot;
+      }
+    }
+    if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device != 0, ib)) return rc;
+    const int rc = B_.ingest_many(in);
+    const int rc2 = B_.ingest_done();
+    return rc ? rc : rc2;
+  });
 }
 
 int xivo_set_frame_ingest(int mode) {
@@ -990,14 +1285,18 @@ int xivo_batch_visual_meas_pointcloud(xivo_batch* b, const uint64_t* ts_ns, cons
                                       const double* const* xp_depth, int tracker_only) {
   BATCH_BEGIN;
   XB_REQUIRE(ts_ns && n_pts && ids && xp_depth, "visual_meas_pointcloud: null argument");
-  std::vector<Msg> in(B_.B);
-  for (int s = 0; s < B_.B; ++s) {
-    in[s].ts = ts_ns[s];
-    in[s].type = tracker_only ? 4 : 3;
-    in[s].ids.assign(ids[s], ids[s] + n_pts[s]);
-    in[s].xp_depth.assign(xp_depth[s], xp_depth[s] + 3 * (size_t)n_pts[s]);
-  }
-  return B_.ingest(in);
+  return S_.run([&](int l) {
+    Batch& B_ = *S_.lanes[l];
+    const int s0 = S_.first[l];
+    std::vector<Msg> in(B_.B);
+    for (int s = 0; s < B_.B; ++s) {
+      in[s].ts = ts_ns[s0 + s];
+      in[s].type = tracker_only ? 4 : 3;
+      in[s].ids.assign(ids[s0 + s], ids[s0 + s] + n_pts[s0 + s]);
+      in[s].xp_depth.assign(xp_depth[s0 + s], xp_depth[s0 + s] + 3 * (size_t)n_pts[s0 + s]);
+    }
+    return B_.ingest(in);
+  });
 }
 
 static void put34(const SE3h& g, double* out) {
@@ -1197,12 +1496,14 @@ int xivo_scale_init_velocity(xivo_batch* b, int seq, double scale) {  // Estimat
 
 int xivo_init_with_sim_depths(xivo_batch* b) {
   BATCH_BEGIN;
-  for (auto& e : B_.est) e->sim_initialize_depths = true;
+  for (auto& lane : S_.lanes)
+    for (auto& e : lane->est) e->sim_initialize_depths = true;
   return 0;
 }
 const char* xivo_batch_error(xivo_batch* b, int seq) {
-  if (!b || !b->impl || seq < 0 || seq >= b->impl->B) return "";
-  return b->impl->est[seq]->error_msg.c_str();
+  if (!b || b->lanes.empty() || seq < 0 || seq >= b->total) return "";
+  const int l = b->lane_of(seq);
+  return b->lanes[l]->est[seq - b->first[l]]->error_msg.c_str();
 }
 
 }  // extern "C"

@@ -12,8 +12,20 @@ int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_s
                          const PyrDesc& d, int batch, const uint8_t* const* frame0 = nullptr);
 int launch_gather_frames(cudaStream_t st, const uint8_t* const* src, uint8_t* dst, unsigned long long stride, const unsigned long long* off,
                          size_t bytes, int batch, int max_chunks = 64);
+// need (device, optional): per-sequence gate written by the accept kernel; a sequence with need <= 0 is skipped
 int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off,
-                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch);
+                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch,
+                       const int* need = nullptr);
+// Device-side tracker decisions (accept loop of Tracker::UpdateLK, greedy selection of Tracker::DetectLK); tracker_kernels.cu
+struct TrackDecideCfg {
+  int rows, cols, margin, mask_half, num_min, num_max, max_pts, max_kp, max_new;
+  double max_disp;
+};
+size_t track_mask_bytes(int rows, int cols);
+int launch_track_accept(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts0, const float* pts1,
+                        const uint8_t* lkst, uint8_t* stat, int* need, int batch);
+int launch_track_select(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts1, const uint8_t* stat,
+                        const int* need, unsigned* kp, const int* kp_count, unsigned* new_kp, int* n_new, int batch);
 size_t lk_smem_bytes(int win, int cn);
 int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, unsigned long long pyr_stride,
                     const unsigned long long* prev_off, const unsigned long long* next_off, const PyrDesc& d, const float* prev_pts, float* next_pts, uint8_t* status, float* err,

@@ -297,11 +297,12 @@ template <int CN>
 __global__ void __launch_bounds__(FT_THREADS) fast_kernel(const uint8_t* __restrict__ img, unsigned long long img_stride,
                                                           const unsigned long long* __restrict__ seq_off, int rows, int cols,
                                                           int thr, int nonmax, unsigned* __restrict__ kp_out, int max_kp,
-                                                          int* __restrict__ kp_count) {
+                                                          int* __restrict__ kp_count, const int* __restrict__ need) {
   __shared__ uint8_t tile[FT_RH][FT_RW + 4];
   __shared__ short score[FT_SH][FT_SW + 2];
   const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * img_stride;
   if (soff == ~0ull) return;  // inactive sequence
+  if (need && need[blockIdx.z] <= 0) return;  // device-side decision of the accept kernel: this sequence keeps enough tracks
   const uint8_t* __restrict__ src = img + soff;
   const int ox = blockIdx.x * FT_TX, oy = blockIdx.y * FT_TY;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 thread layout, no integer divisions
@@ -367,11 +368,12 @@ template <int CN>
 __global__ void __launch_bounds__(FT_THREADS) fast_pair_kernel(const uint8_t* __restrict__ img, unsigned long long img_stride,
                                                                const unsigned long long* __restrict__ seq_off, int rows, int cols,
                                                                int thr, int nonmax, unsigned* __restrict__ kp_out, int max_kp,
-                                                               int* __restrict__ kp_count) {
+                                                               int* __restrict__ kp_count, const int* __restrict__ need) {
   __shared__ __align__(8) unsigned short tile[FT_RH][FP_RW];
   __shared__ short score[FT_SH][FP_SW];
   const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * img_stride;
   if (soff == ~0ull) return;  // inactive sequence
+  if (need && need[blockIdx.z] <= 0) return;
   const uint8_t* __restrict__ src = img + soff;
   const int ox = blockIdx.x * FT_TX, oy = blockIdx.y * FT_TY;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -480,18 +482,18 @@ static bool force_scalar_fast() {
 }
 
 int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off,
-                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch) {
+                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch, const int* need) {
   XB_REQUIRE(rows < 4096 && cols < 4096, "FAST: image dimension must be < 4096 (12-bit packed coordinates)");
   XB_REQUIRE(thr >= 0 && thr < 255, "FAST: threshold out of range");
   XB_CUDA(cudaMemsetAsync(kp_count, 0, sizeof(int) * batch, st));
   ProfScope ps("fast_detect", st);
   dim3 grid((cols + FT_TX - 1) / FT_TX, (rows + FT_TY - 1) / FT_TY, batch);
   if (force_scalar_fast()) {
-    if (cn == 1) fast_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
-    else fast_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+    if (cn == 1) fast_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count, need);
+    else fast_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count, need);
   } else {
-    if (cn == 1) fast_pair_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
-    else fast_pair_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+    if (cn == 1) fast_pair_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count, need);
+    else fast_pair_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count, need);
   }
   XB_CUDA(cudaGetLastError());
   return 0;
@@ -1049,6 +1051,247 @@ int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* nex
     XB_CUDA(cudaFuncSetAttribute(lk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lk_kernel<3><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
   }
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-side tracker decisions: Tracker::UpdateLK's accept loop (tracker.cpp:571-589) and Tracker::DetectLK's greedy selection
+// (tracker.cpp:224-229, :295-328) without a host round trip.  Both walk a list in order while a mask of claimed pixels grows, so each
+// sequence is one CTA whose warp 0 does the sequential walk (the 15 x 15 mask-out of one feature is spread over the lanes);
+// the mask lives in shared memory as a bitmap (bit = pixel still free).  Same arithmetic as the host code they replace
+// (estimator_host.cpp.inc: mask_out / mask_valid; estimator.cu: detect_select): truncation for the validity test, round-half-even
+// for the block corners, the displacement test in double precision.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mask_reset(unsigned* m, int stride, const TrackDecideCfg& c, int tid, int nthr) {
+  for (int i = tid; i < c.rows * stride; i += nthr) {
+    const int y = i / stride, w = i - y * stride;
+    unsigned v = 0u;
+    const int x0 = c.margin, x1 = c.cols - c.margin - 1;  // free columns [x0, x1] of the rows [margin, rows - margin)
+    if (y >= c.margin && y < c.rows - c.margin && x1 >= x0) {
+      const int lo = max(x0, 32 * w), hi = min(x1, 32 * w + 31);
+      if (hi >= lo) v = (0xffffffffu >> (31 - (hi - 32 * w))) & (0xffffffffu << (lo - 32 * w));
+    }
+    m[i] = v;
+  }
+}
+// clear the block [x0, x1] x [y0, y1] (already clipped); lanes split the rows; atomic = several blocks may be cleared concurrently
+__device__ __forceinline__ void mask_clear_block(unsigned* m, int stride, int x0, int y0, int x1, int y1, int lane, int nlanes, bool atomic) {
+  if (x1 < x0) return;
+  for (int y = y0 + lane; y <= y1; y += nlanes) {
+    for (int w = x0 >> 5; w <= (x1 >> 5); ++w) {
+      const int lo = max(x0, 32 * w) - 32 * w, hi = min(x1, 32 * w + 31) - 32 * w;
+      const unsigned bits = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+      if (atomic) atomicAnd(&m[y * stride + w], ~bits);
+      else m[y * stride + w] &= ~bits;
+    }
+  }
+}
+__device__ __forceinline__ void block_of(double x, double y, const TrackDecideCfg& c, int* x0, int* y0, int* x1, int* y1) {
+  const int h = c.mask_half;
+  *x0 = max(__double2int_rn(x - h), 0);
+  *y0 = max(__double2int_rn(y - h), 0);
+  *x1 = min(__double2int_rn(x + h), c.cols - 1);
+  *y1 = min(__double2int_rn(y + h), c.rows - 1);
+}
+__device__ __forceinline__ bool mask_free(const unsigned* m, int stride, const TrackDecideCfg& c, double x, double y) {
+  const int col = (int)x, row = (int)y;
+  if (col < 0 || col >= c.cols || row < 0 || row >= c.rows) return false;
+  return (m[row * stride + (col >> 5)] >> (col & 31)) & 1u;
+}
+
+// kind[b]: 1 = first frame (detection only), 2 = tracked by LK, 3 = empty list (nothing to do), 0 = inactive.
+// Outputs: stat[b][i] = feature i keeps its track; need[b] = features the detection should add (0 = none).
+__global__ void __launch_bounds__(128) track_accept_kernel(TrackDecideCfg c, const int* __restrict__ kind, const int* __restrict__ npts,
+                                                           const float* __restrict__ pts0, const float* __restrict__ pts1,
+                                                           const uint8_t* __restrict__ lkst, uint8_t* __restrict__ stat, int* __restrict__ need) {
+  extern __shared__ unsigned tmask[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int k = kind[b];
+  if (k == 1) { if (tid == 0) need[b] = c.num_max; return; }
+  if (k != 2) { if (tid == 0) need[b] = 0; return; }
+  const int stride = (c.cols + 31) >> 5;
+  mask_reset(tmask, stride, c, tid, blockDim.x);
+  __syncthreads();
+  if (tid >= 32) return;
+  const int n = npts[b];
+  const float* p0 = pts0 + (size_t)b * c.max_pts * 2;
+  const float* p1 = pts1 + (size_t)b * c.max_pts * 2;
+  int num_valid = 0;
+  for (int i = 0; i < n; ++i) {
+    bool ok = lkst[(size_t)b * c.max_pts + i] != 0;
+    const double x = (double)p1[2 * i], y = (double)p1[2 * i + 1];
+    if (ok) {
+      const double dx = (double)p0[2 * i] - x, dy = (double)p0[2 * i + 1] - y;
+      ok = mask_free(tmask, stride, c, x, y) && sqrt(dx * dx + dy * dy) < c.max_disp;
+    }
+    if (ok) {
+      int x0, y0, x1, y1;
+      block_of(x, y, c, &x0, &y0, &x1, &y1);
+      __syncwarp();
+      mask_clear_block(tmask, stride, x0, y0, x1, y1, tid, 32, false);
+      __syncwarp();
+      ++num_valid;
+    }
+    if (tid == 0) stat[(size_t)b * c.max_pts + i] = ok ? 1 : 0;
+  }
+  if (tid == 0) need[b] = num_valid < c.num_min ? c.num_max - num_valid : 0;
+}
+
+// Greedy selection of new features from the FAST keypoints of the sequences with need[b] > 0, in the order (score descending, y, x).
+// kp: packed (y << 20 | x << 8 | score), rewritten in place as sort keys ((255 - score) << 24 | y << 12 | x; unique per pixel).
+// The candidates are consumed in sorted chunks of at most SEL_CAP keys: a 4-pass radix select finds the chunk's largest key, the chunk is
+// gathered and bitonic-sorted in shared memory, warp 0 walks it.  new_kp[b][j] = packed (y << 20 | x << 8 | score) of the j-th pick.
+constexpr int SEL_CAP = 1024, SEL_THREADS = 256;
+__global__ void __launch_bounds__(SEL_THREADS) track_select_kernel(TrackDecideCfg c, const int* __restrict__ kind, const int* __restrict__ npts,
+                                                                   const float* __restrict__ pts1, const uint8_t* __restrict__ stat,
+                                                                   const int* __restrict__ need, unsigned* __restrict__ kp,
+                                                                   const int* __restrict__ kp_count, unsigned* __restrict__ new_kp,
+                                                                   int* __restrict__ n_new) {
+  extern __shared__ unsigned tmask[];
+  __shared__ unsigned chunk[SEL_CAP];
+  __shared__ int hist[256];
+  __shared__ int s_cnt, s_budget, s_stop, s_nnew;
+  __shared__ unsigned s_prefix, s_last;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  int budget = need[b];
+  if (budget <= 0) { if (tid == 0) n_new[b] = 0; return; }
+  const int stride = (c.cols + 31) >> 5;
+  mask_reset(tmask, stride, c, tid, SEL_THREADS);
+  __syncthreads();
+  if (kind[b] == 2) {  // the pixels claimed by the tracks that survived (any order: the union is what matters)
+    const int n = npts[b];
+    const float* p1 = pts1 + (size_t)b * c.max_pts * 2;
+    for (int i = tid >> 4; i < n; i += SEL_THREADS >> 4) {
+      if (!stat[(size_t)b * c.max_pts + i]) continue;
+      int x0, y0, x1, y1;
+      block_of((double)p1[2 * i], (double)p1[2 * i + 1], c, &x0, &y0, &x1, &y1);
+      mask_clear_block(tmask, stride, x0, y0, x1, y1, tid & 15, 16, true);
+    }
+  }
+  __syncthreads();
+  unsigned* keys = kp + (size_t)b * c.max_kp;
+  const int n = min(kp_count[b], c.max_kp);
+  // KeyPointsFilter::runByPixelsMask + key conversion; candidates on claimed pixels get the key ~0 (never selected: valid keys are
+  // < 2^32 - 1 because x < 4096)
+  for (int i = tid; i < n; i += SEL_THREADS) {
+    const unsigned k = keys[i];
+    const int x = (k >> 8) & 0xfff, y = k >> 20, sc = k & 0xff;
+    const bool free_px = (tmask[y * stride + (x >> 5)] >> (x & 31)) & 1u;
+    keys[i] = free_px ? (((unsigned)(255 - sc) << 24) | ((unsigned)y << 12) | (unsigned)x) : 0xffffffffu;
+  }
+  if (tid == 0) { s_last = 0u; s_stop = 0; s_nnew = 0; s_budget = budget; }
+  __syncthreads();
+  bool first = true;
+  for (;;) {
+    // ---- the SEL_CAP-th smallest key among those > s_last (or the largest if fewer remain): MSB-first radix select
+    const unsigned last = s_last;
+    unsigned prefix = 0u;
+    int want = SEL_CAP;  // rank (1-based) still to be found inside the current prefix
+    bool exhausted = false;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = tid; i < 256; i += SEL_THREADS) hist[i] = 0;
+      __syncthreads();
+      const unsigned pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = tid; i < n; i += SEL_THREADS) {
+        const unsigned k = keys[i];
+        if (k == 0xffffffffu || (!first && k <= last) ) continue;
+        if ((k & pmask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int acc = 0, d = 0, total = 0;
+        for (int q = 0; q < 256; ++q) total += hist[q];
+        if (total == 0) { s_cnt = -1; }
+        else {
+          if (want > total) want = total;  // fewer than SEL_CAP remain: take them all (rank = total)
+          for (d = 0; d < 256; ++d) { if (acc + hist[d] >= want) break; acc += hist[d]; }
+          s_prefix = prefix | ((unsigned)d << shift);
+          s_cnt = want - acc;
+        }
+      }
+      __syncthreads();
+      if (s_cnt < 0) { exhausted = true; break; }
+      prefix = s_prefix;
+      want = s_cnt;
+      __syncthreads();
+    }
+    if (exhausted) break;
+    const unsigned kth = prefix;  // all keys in (last, kth] form the chunk (<= SEL_CAP of them, keys are unique)
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += SEL_THREADS) {
+      const unsigned k = keys[i];
+      if (k == 0xffffffffu || (!first && k <= last) || k > kth) continue;
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < SEL_CAP) chunk[pos] = k;
+    }
+    __syncthreads();
+    const int m = min(s_cnt, SEL_CAP);
+    for (int i = m + tid; i < SEL_CAP; i += SEL_THREADS) chunk[i] = 0xffffffffu;
+    __syncthreads();
+    for (int k2 = 2; k2 <= SEL_CAP; k2 <<= 1)  // bitonic sort, ascending
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < SEL_CAP; i += SEL_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned a = chunk[i], bb = chunk[ixj];
+            const bool up = (i & k2) == 0;
+            if ((a > bb) == up) { chunk[i] = bb; chunk[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    // ---- greedy walk (warp 0)
+    if (tid < 32) {
+      int bud = s_budget, nn = s_nnew, stop = 0;
+      for (int i = 0; i < m && !stop; ++i) {
+        const unsigned k = chunk[i];
+        const int x = k & 0xfff, y = (k >> 12) & 0xfff, sc = 255 - (int)(k >> 24);
+        const bool free_px = (tmask[y * stride + (x >> 5)] >> (x & 31)) & 1u;
+        if (free_px) {
+          if (tid == 0 && nn < c.max_new) new_kp[(size_t)b * c.max_new + nn] = ((unsigned)y << 20) | ((unsigned)x << 8) | (unsigned)sc;
+          ++nn;
+          int x0, y0, x1, y1;
+          block_of((double)x, (double)y, c, &x0, &y0, &x1, &y1);
+          __syncwarp();
+          mask_clear_block(tmask, stride, x0, y0, x1, y1, tid, 32, false);
+          __syncwarp();
+          --bud;
+        }
+        if (bud <= 0 || sc < 5) stop = 1;  // tracker.cpp:326 (and the host's `s < 5` cut: OpenCV scores below 5 are never asked for)
+      }
+      if (tid == 0) { s_budget = bud; s_nnew = nn; s_stop = stop; s_last = kth; }
+    }
+    __syncthreads();
+    first = false;
+    if (s_stop || m == 0) break;
+  }
+  if (tid == 0) n_new[b] = min(s_nnew, c.max_new);
+}
+
+size_t track_mask_bytes(int rows, int cols) { return (size_t)rows * ((cols + 31) / 32) * sizeof(unsigned); }
+
+int launch_track_accept(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts0, const float* pts1,
+                        const uint8_t* lkst, uint8_t* stat, int* need, int batch) {
+  const size_t smem = track_mask_bytes(c.rows, c.cols);
+  XB_REQUIRE(smem <= 200 * 1024, "track_accept: image too large for the shared-memory mask");
+  static size_t attr = 0;
+  if (smem > attr) { XB_CUDA(cudaFuncSetAttribute(track_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  ProfScope ps("track_accept", st);
+  track_accept_kernel<<<batch, 128, smem, st>>>(c, kind, npts, pts0, pts1, lkst, stat, need);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_track_select(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts1, const uint8_t* stat,
+                        const int* need, unsigned* kp, const int* kp_count, unsigned* new_kp, int* n_new, int batch) {
+  const size_t smem = track_mask_bytes(c.rows, c.cols);
+  XB_REQUIRE(smem <= 200 * 1024, "track_select: image too large for the shared-memory mask");
+  static size_t attr = 0;
+  if (smem > attr) { XB_CUDA(cudaFuncSetAttribute(track_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+  ProfScope ps("track_select", st);
+  track_select_kernel<<<batch, SEL_THREADS, smem, st>>>(c, kind, npts, pts1, stat, need, kp, kp_count, new_kp, n_new);
   XB_CUDA(cudaGetLastError());
   return 0;
 }

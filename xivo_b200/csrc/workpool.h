@@ -256,6 +256,7 @@ class WorkPool {
   std::atomic<int> next_driver_{0};
 
  public:
+  static int budget() { return cpu_budget(); }  // CPUs this process may use (no pool is created by asking)
   // Run at most one item of any published job on the calling thread (a driver that is waiting for the GPU
   // lends its CPU to the other batches).  Returns false when there was nothing to do.
   bool help_one() {
@@ -334,5 +335,7 @@ class WorkPool {
     for (auto& t : threads_) t.join();
   }
 };
+
+inline int host_cpu_budget() { return WorkPool::budget(); }
 
 }  // namespace xb
