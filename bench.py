@@ -295,6 +295,7 @@ def run_ours(args):
     args.batches = max(1, min(args.batches, budget // 2))
     os.environ.setdefault("XIVO_THREADS", str(max(1, min(args.max_threads, budget) - args.batches + 1 - args.cpu_headroom)))
     os.environ.setdefault("XIVO_DRIVERS", str(args.batches))
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # every lane has its own streams: more hardware queues than the default 8, fewer false dependencies
     os.environ.setdefault("XIVO_PIN_DRIVERS", "1")  # the batch driver threads are ours: let the library pin them next to its workers
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -23,6 +23,7 @@ run lanes32 XIVO_LANES=32 --
 run lanes48 XIVO_LANES=48 --
 run lanes32_tok12 XIVO_LANES=32 XIVO_CPU_TOKENS=12 --
 run lanes32_tok20 XIVO_LANES=32 XIVO_CPU_TOKENS=20 --
+run lanes_default_conn8 CUDA_DEVICE_MAX_CONNECTIONS=8 --
 run lanes22_hostdec XIVO_HOST_TRACKER_DECISIONS=1 --
 run legacy_pool XIVO_LANES=1 -- --batches 8
 run legacy_pool_hostdec XIVO_LANES=1 XIVO_HOST_TRACKER_DECISIONS=1 -- --batches 8
