@@ -78,3 +78,24 @@ def test_device_decisions_equal_host_decisions(case):
     assert max(n) > 50
     if case == "texture_big_budget":
         assert n[0] > 1024  # more picks than one chunk holds
+
+
+@pytest.mark.parametrize("size", [(240, 320), (480, 640), (176, 208)])
+def test_tma_pyramid_equals_thread_staged_pyramid(size):
+    """pyrdown_tma_kernel (cp.async.bulk.tensor box loads, REFLECT_101 patched on the rim CTAs) against pyrdown_vec_kernel: the tracks
+    of a short sequence — LK reads every pyramid level, also next to the image border (margin 4) — must be bit-identical.
+    (176, 208): a width whose coarser levels stop being multiples of 16, so TMA and thread-staged passes mix inside one pyramid."""
+    rows, cols = size
+    cfg = _cfg(rows, cols, 150, 200, 10, mask=9, margin=4)
+    canvas = synth.texture_canvas(rows, cols, seed=5, pad=64)
+    frames = [synth.frame_from_canvas(canvas, rows, cols, (3 * k, 2 * k), noise_seed=50 + k, pad=32) for k in range(6)]
+
+    def run(tma):
+        os.environ["XIVO_PYRDOWN_TMA"] = "1" if tma else "0"
+        try:
+            return _run(cfg, frames, host_decisions=False, n_seq=2)
+        finally:
+            os.environ.pop("XIVO_PYRDOWN_TMA", None)
+
+    n = _same(run(True), run(False))
+    assert max(n) > 100

@@ -197,6 +197,12 @@ class Batch {
   Mirror<uint8_t> lkst;
   Mirror<int> npts, kpcount;
   Mirror<unsigned> kp;
+  // TMA pyramid passes (pyrdown_tma_kernel): tensor maps over the frame ring (level-0 source) and over the pyramid levels
+  bool tma_pyr = false;
+  CUtensorMap tm_ring;
+  CUtensorMap tm_lvl[kMaxPyrLevels];
+  bool tm_lvl_ok[kMaxPyrLevels] = {false};
+  Mirror<int> ring_img, pyr_img;  // per sequence: image index of the new frame inside the ring map / of the current pyramid inside the level maps
   // device-side tracker decisions (track_accept_kernel / track_select_kernel)
   bool dev_decide = false;
   Mirror<int> tkind, tneed, tnnew;
@@ -270,7 +276,7 @@ class Batch {
     nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); stg.release(); stg_first.release(); stg_n.release();
     icst.release(); off_prev.release(); frame_ptr.release(); ingest_ptr.release(); ingest_off.release();
     off_cur.release(); pts0.release(); pts1.release(); lkerr.release(); lkst.release(); npts.release(); kpcount.release();
-    kp.release(); tkind.release(); tneed.release(); tnnew.release(); tstat.release(); tnewkp.release();
+    kp.release(); ring_img.release(); pyr_img.release(); tkind.release(); tneed.release(); tnnew.release(); tstat.release(); tnewkp.release();
   }
 
   int fail(int code, const std::string& m) {
@@ -463,6 +469,19 @@ class Batch {
         ok = ok && tkind.alloc(B) && tneed.alloc(B) && tnnew.alloc(B) && tstat.alloc((size_t)B * max_pts) && tnewkp.alloc((size_t)B * e0.tc.num_features_max);
     }
     if (!ok) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
+    {  // TMA passes where the geometry allows (XIVO_PYRDOWN_TMA=0 keeps the thread-staged kernels: parity tests compare the two)
+      const char* tv = getenv("XIVO_PYRDOWN_TMA");
+      const char* gv = getenv("XIVO_PYRDOWN_GENERIC");
+      if (cn == 1 && (cols & 15) == 0 && (pd.total & 15) == 0 && pd.n_levels > 1 && !(tv && tv[0] == '0') && !(gv && gv[0] == '1')) {
+        if (!ring_img.alloc(B) || !pyr_img.alloc(B)) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
+        if (make_pyr_tensor_map(&tm_ring, dRing, rows, cols, ib, (unsigned long long)B * ring_n) == 0) {
+          tma_pyr = true;
+          for (int l = 1; l + 1 < pd.n_levels; ++l)
+            tm_lvl_ok[l] = (pd.cols[l] & 15) == 0 && (pd.off[l] & 15) == 0 &&
+                           make_pyr_tensor_map(&tm_lvl[l], dPyr + pd.off[l], pd.rows[l], pd.cols[l], pd.total, (unsigned long long)B * 2) == 0;
+        }
+      }
+    }
     ring_next.assign(B, 0);
     ring_ev.resize(ring_n);
     for (auto& e : ring_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -618,6 +637,7 @@ class Batch {
         off_cur.h[b] = ((size_t)b * 2 + cur) * pd.total;
         off_prev.h[b] = ((size_t)b * 2 + prev_slot[b]) * pd.total;
         frame_ptr.h[b] = dRing + ((size_t)b * ring_n + slots[i]) * ib;  // consumed by the first pyrDown pass
+        if (tma_pyr) { ring_img.h[b] = b * ring_n + slots[i]; pyr_img.h[b] = b * 2 + cur; }
       }
       pfor(act, [&](int b, int) {
         HostScope hx("x_trk_prepare");
@@ -661,7 +681,15 @@ class Batch {
       }
     }
     XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st)); XB_CUDA(frame_ptr.up(st));
-    if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B, frame_ptr.d)) return rc;
+    if (tma_pyr) {
+      XB_CUDA(ring_img.up(st)); XB_CUDA(pyr_img.up(st));
+      ProfScope ps("pyrdown", st);
+      if (int rc = launch_pyrdown_tma(st, tm_ring, ring_img.d, dPyr, 0, off_cur.d, pd, 0, 1, B)) return rc;
+      for (int l = 1; l + 1 < pd.n_levels; ++l) {
+        if (tm_lvl_ok[l]) { if (int rc = launch_pyrdown_tma(st, tm_lvl[l], pyr_img.d, dPyr, 0, off_cur.d, pd, l, 0, B)) return rc; }
+        else if (int rc = launch_pyrdown_level(st, dPyr, 0, off_cur.d, pd, B, nullptr, l)) return rc;
+      }
+    } else if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B, frame_ptr.d)) return rc;
     g_launches += std::max(1, pd.n_levels - 1);
     {
       int nact = 0;

@@ -2,6 +2,7 @@
 // Every launcher works on DEVICE pointers, takes a batch dimension (independent sequences /
 // filters) and enqueues on the given stream without synchronising.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace xb {
@@ -10,6 +11,12 @@ namespace xb {
 // seq_off (device, optional): per-sequence byte offset of the pyramid / image; ~0ull = skip that sequence.
 int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off,
                          const PyrDesc& d, int batch, const uint8_t* const* frame0 = nullptr);
+int launch_pyrdown_level(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off, const PyrDesc& d,
+                         int batch, const uint8_t* const* frame0, int lvl);
+// TMA pass (tracker_kernels.cu: pyrdown_tma_kernel): single channel, source level with cols % 16 == 0, images at a uniform stride
+int make_pyr_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img);
+int launch_pyrdown_tma(cudaStream_t st, const CUtensorMap& map, const int* src_img, uint8_t* pyr, unsigned long long pyr_stride,
+                       const unsigned long long* seq_off, const PyrDesc& d, int lvl, int ingest, int batch);
 int launch_gather_frames(cudaStream_t st, const uint8_t* const* src, uint8_t* dst, unsigned long long stride, const unsigned long long* off,
                          size_t bytes, int batch, int max_chunks = 64);
 // need (device, optional): per-sequence gate written by the accept kernel; a sequence with need <= 0 is skipped

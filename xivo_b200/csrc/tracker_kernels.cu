@@ -5,6 +5,7 @@
 //
 // All kernels take a batch dimension (blockIdx.z or .y = independent sequence) because the
 // only way a 640x480 frame fills a B200 is by processing many sequences per launch.
+#include <cuda.h>
 #include <algorithm>
 #include <cstdlib>
 #include "kernels.h"
@@ -187,22 +188,162 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_vec_kernel(uint8_t* __rest
   }
 }
 
+// TMA variant of the single-channel pass (source level with cols % 16 == 0, sources at a uniform stride: the frame ring or the
+// pyramid buffer of a batch).  The (2*64+16) x (2*32+3) byte source box of a CTA arrives by ONE cp.async.bulk.tensor issued by one
+// thread (3-D tensor map {cols, rows, image}; coordinates outside the image are zero-filled by the TMA unit), completion on an
+// mbarrier: the ~540 thread instructions per CTA-thread that pyrdown_vec_kernel spends on addresses, border tests and word
+// assembly disappear (ncu, round 2 start: 82 % issue-active at 7 % of DRAM peak).  BORDER_REFLECT_101 only concerns the CTAs on the
+// image rim, which patch their halo rows / columns inside shared memory after the box has landed.  The arithmetic that follows is
+// pyrdown_vec_kernel's (byte-permute + dp4a on the same words), so the output is bit-identical.
+constexpr int PT_BOXW = 2 * PV_TX + 16;      // 144 bytes: source columns [2 ox - 4, 2 ox + 140) (inner box extent must be a multiple of 16 B)
+constexpr int PT_WORDS = PT_BOXW / 4;        // 36 words per staged row
+constexpr int PT_BOX_BYTES = PT_BOXW * PV_ROWS;
+
+__device__ __forceinline__ unsigned smem_addr_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(PV_THREADS) pyrdown_tma_kernel(const __grid_constant__ CUtensorMap src_map, const int* __restrict__ src_img,
+                                                                 uint8_t* __restrict__ pyr, unsigned long long pyr_stride,
+                                                                 const unsigned long long* __restrict__ seq_off, PyrDesc d, int lvl_src, int ingest) {
+  const int srows = d.rows[lvl_src], scols = d.cols[lvl_src];
+  const int drows = d.rows[lvl_src + 1], dcols = d.cols[lvl_src + 1];
+  const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * pyr_stride;
+  if (soff == ~0ull) return;  // inactive sequence
+  uint8_t* __restrict__ dst = pyr + soff + d.off[lvl_src + 1];
+  __shared__ __align__(128) unsigned tile[PV_ROWS][PT_WORDS];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int ox = blockIdx.x * PV_TX, oy = blockIdx.y * PV_TY;
+  const int tid = threadIdx.x;
+  const int sx0 = 2 * ox - 4, sy0 = 2 * oy - 2;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&mbar)), "r"(PT_BOX_BYTES) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_addr_u32(&tile[0][0])), "l"(reinterpret_cast<unsigned long long>(&src_map)), "r"(sx0), "r"(sy0), "r"(src_img[blockIdx.z]),
+                   "r"(smem_addr_u32(&mbar))
+                 : "memory");
+  }
+  {  // every thread waits for the box (phase 0 of the barrier)
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_addr_u32(&mbar)) : "memory");
+    }
+  }
+  // BORDER_REFLECT_101 for the rim CTAs (the TMA unit zero-filled what lies outside the image): columns first, then whole rows
+  const bool rim_x = sx0 < 0 || sx0 + PT_BOXW > scols, rim_y = sy0 < 0 || sy0 + PV_ROWS > srows;
+  if (rim_x) {
+    uint8_t* tb = reinterpret_cast<uint8_t*>(&tile[0][0]);
+    for (int i = tid; i < PV_ROWS * 8; i += PV_THREADS) {  // at most 4 columns on the left and 4 that matter on the right
+      const int ry = i >> 3, k = i & 7;
+      const int rx = k < 4 ? k : (scols - sx0) + (k - 4);  // k < 4: columns sx0 .. sx0 + 3 (left halo); else the first 4 columns past the right edge
+      if (rx < 0 || rx >= PT_BOXW) continue;
+      const int sx = sx0 + rx;
+      if (sx >= 0 && sx < scols) continue;
+      const int rsx = reflect101(sx, scols) - sx0;
+      if (rsx >= 0 && rsx < PT_BOXW) tb[ry * PT_BOXW + rx] = tb[ry * PT_BOXW + rsx];
+    }
+    __syncthreads();
+  }
+  if (rim_y) {
+    for (int i = tid; i < PV_ROWS * PT_WORDS; i += PV_THREADS) {
+      const int ry = i / PT_WORDS, rw = i - ry * PT_WORDS;
+      const int sy = sy0 + ry;
+      if (sy >= 0 && sy < srows) continue;
+      const int rsy = reflect101(sy, srows) - sy0;
+      if (rsy >= 0 && rsy < PV_ROWS && sy < srows + 4) tile[ry][rw] = tile[rsy][rw];
+    }
+    __syncthreads();
+  }
+  if (ingest) {  // level-0 copy of this CTA's 128 x 64 source block (bytes 4 .. 131 of rows 2 .. 65), 16 bytes per store
+    uint8_t* __restrict__ l0 = pyr + soff + d.off[0];
+    for (int i = tid; i < 2 * PV_TY * (2 * PV_TX / 16); i += PV_THREADS) {
+      const int ry = i >> 3, q = i & 7;
+      const int gy = 2 * oy + ry, gx = 2 * ox + 16 * q;
+      if (gy >= srows || gx >= scols) continue;
+      const unsigned* t = &tile[ry + 2][1 + 4 * q];
+      *reinterpret_cast<uint4*>(l0 + (size_t)gy * scols + gx) = make_uint4(t[0], t[1], t[2], t[3]);  // cols % 16 == 0: whole chunks only
+    }
+  }
+  const int tx = tid & 31, ty = tid >> 5;  // outputs x = ox + 2 tx (+1), y = oy + 4 ty (+0..3)
+  int h0[11], h1[11];
+#pragma unroll
+  for (int r = 0; r < 11; ++r) {
+    const unsigned w0 = tile[8 * ty + r][tx], w1 = tile[8 * ty + r][tx + 1], w2 = tile[8 * ty + r][tx + 2];
+    const unsigned a = __byte_perm(w0, w1, 0x5432);
+    h0[r] = __dp4a(a, 0x04060401u, __dp4a(w1, 0x00010000u, 0u));
+    h1[r] = __dp4a(w1, 0x04060401u, __dp4a(w2, 0x00000001u, 0u));
+  }
+  const int x = ox + 2 * tx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int y = oy + 4 * ty + j;
+    if (y >= drows || x >= dcols) continue;
+    const int s0 = h0[2 * j] + h0[2 * j + 4] + 4 * (h0[2 * j + 1] + h0[2 * j + 3]) + 6 * h0[2 * j + 2];
+    const int s1 = h1[2 * j] + h1[2 * j + 4] + 4 * (h1[2 * j + 1] + h1[2 * j + 3]) + 6 * h1[2 * j + 2];
+    uint8_t* q = dst + (size_t)y * dcols + x;
+    q[0] = (uint8_t)((s0 + 128) >> 8);
+    if (x + 1 < dcols) q[1] = (uint8_t)((s1 + 128) >> 8);
+  }
+}
+
+// Tensor map {cols, rows, n_img} over u8 images that lie `img_stride` bytes apart, box PT_BOXW x PV_ROWS x 1, zero fill.
+// cuTensorMapEncodeTiled is fetched from the driver at run time (the library does not link libcuda).
+int make_pyr_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    XB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    XB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  XB_REQUIRE((cols & 15) == 0 && (img_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "pyramid tensor map: 16-byte alignment");
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)n_img};
+  const cuuint64_t strides[2] = {(cuuint64_t)cols, (cuuint64_t)img_stride};  // bytes, dimensions 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)PT_BOXW, (cuuint32_t)PV_ROWS, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+// One pyrDown pass lvl -> lvl + 1 through the TMA kernel.  src_img (device): image index of every sequence inside the tensor map.
+int launch_pyrdown_tma(cudaStream_t st, const CUtensorMap& map, const int* src_img, uint8_t* pyr, unsigned long long pyr_stride,
+                       const unsigned long long* seq_off, const PyrDesc& d, int lvl, int ingest, int batch) {
+  dim3 vgrid((d.cols[lvl + 1] + PV_TX - 1) / PV_TX, (d.rows[lvl + 1] + PV_TY - 1) / PV_TY, batch);
+  pyrdown_tma_kernel<<<vgrid, PV_THREADS, 0, st>>>(map, src_img, pyr, pyr_stride, seq_off, d, lvl, ingest);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// one pass lvl -> lvl + 1 with the thread-staged kernels (any channel count / width)
+int launch_pyrdown_level(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off, const PyrDesc& d,
+                         int batch, const uint8_t* const* frame0, int l) {
+  dim3 grid((d.cols[l + 1] + PD_TX - 1) / PD_TX, (d.rows[l + 1] + PD_TY - 1) / PD_TY, batch);
+  dim3 block(PD_TX, PD_TY);
+  if (d.cn == 1 && (d.cols[l] & 3) == 0 && !force_generic_pyrdown()) {
+    dim3 vgrid((d.cols[l + 1] + PV_TX - 1) / PV_TX, (d.rows[l + 1] + PV_TY - 1) / PV_TY, batch);
+    pyrdown_vec_kernel<<<vgrid, PV_THREADS, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
+  } else if (d.cn == 1) pyrdown_kernel<1><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
+  else pyrdown_kernel<3><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off,
                          const PyrDesc& d, int batch, const uint8_t* const* frame0) {
   ProfScope ps("pyrdown", st);
   if (d.n_levels == 1 && frame0) {  // no pyrDown pass to ride on: plain gather copy into level 0
     if (int rc = launch_gather_frames(st, frame0, pyr, pyr_stride, seq_off, (size_t)d.rows[0] * d.cols[0] * d.cn, batch)) return rc;
   }
-  for (int l = 0; l + 1 < d.n_levels; ++l) {
-    dim3 grid((d.cols[l + 1] + PD_TX - 1) / PD_TX, (d.rows[l + 1] + PD_TY - 1) / PD_TY, batch);
-    dim3 block(PD_TX, PD_TY);
-    if (d.cn == 1 && (d.cols[l] & 3) == 0 && !force_generic_pyrdown()) {
-      dim3 vgrid((d.cols[l + 1] + PV_TX - 1) / PV_TX, (d.rows[l + 1] + PV_TY - 1) / PV_TY, batch);
-      pyrdown_vec_kernel<<<vgrid, PV_THREADS, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
-    } else if (d.cn == 1) pyrdown_kernel<1><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
-    else pyrdown_kernel<3><<<grid, block, 0, st>>>(pyr, pyr_stride, seq_off, d, l, frame0);
-  }
-  XB_CUDA(cudaGetLastError());
+  for (int l = 0; l + 1 < d.n_levels; ++l)
+    if (int rc = launch_pyrdown_level(st, pyr, pyr_stride, seq_off, d, batch, frame0, l)) return rc;
   return 0;
 }
 
@@ -779,7 +920,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
                                                                const int* __restrict__ npts, LKParams prm) {
   static_assert(WIN >= 3 && WIN <= 15 && (WIN & 1), "fast LK path: odd window up to 15");
   constexpr int RW = WIN + 3, DW = WIN + 1, NS = (WIN + 1) / 2;
-  constexpr int REG_BYTES = ((RW * RW + 15) / 16) * 16;
+  constexpr int RPW = (RW + 3) / 4, RP = 4 * RPW;  // region row pitch: whole words (the interior staging path stores words)
+  constexpr int REG_BYTES = ((RP * RW + 15) / 16) * 16;
   constexpr int PER_WARP = ((REG_BYTES + DW * DW * 2 * 2 + 15) / 16) * 16;
   __shared__ __align__(16) uint8_t smem_raw[LK_WARPS * PER_WARP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -832,31 +974,66 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
     int iw11 = 16384 - iw00 - iw01 - iw10;
 
     __syncwarp();
-    // stage region: origin (ipx-1, ipy-1), REFLECT_101 == reads of OpenCV's padded level
-    for (int i = lane; i < RW * RW; i += 32) {
-      const int ry = i / RW, rx = i - ry * RW;
-      const int sy = reflect101(ipy - 1 + ry, rows), sx = reflect101(ipx - 1 + rx, cols);
-      region[i] = I[(size_t)sy * cols + sx];
-    }
-    __syncwarp();
-    // Scharr derivatives on the (win+1)^2 grid; zero outside the image (BORDER_CONSTANT)
-    for (int i = lane; i < DW * DW; i += 32) {
-      const int ty = i / DW, tx = i - ty * DW;
-      const int X = ipx + tx, Y = ipy + ty;
-      const bool inside = (X >= 0 && X < cols && Y >= 0 && Y < rows);
-      const uint8_t* r0 = region + ty * RW + tx;  // row Y-1, col X-1
-      const uint8_t* r1 = r0 + RW;
-      const uint8_t* r2 = r1 + RW;
-      int dx = 0, dy = 0;
-      if (inside) {
-        const int t0l = (r0[0] + r2[0]) * 3 + r1[0] * 10;
-        const int t0r = (r0[2] + r2[2]) * 3 + r1[2] * 10;
-        const int t1l = r2[0] - r0[0], t1c = r2[1] - r0[1], t1r = r2[2] - r0[2];
-        dx = t0r - t0l;
-        dy = (t1r + t1l) * 3 + t1c * 10;
+    // Is the whole (WIN+3)^2 region inside the level?  (Almost always: then no border rule applies and every derivative is inside.)
+    const bool reg_interior = ipx >= 1 && ipy >= 1 && ipx + WIN + 1 < cols && ipy + WIN + 1 < rows;
+    if (reg_interior) {
+      // lane l < RW stages row l: the words that cover its RW bytes, funnel-shifted so that the row starts at byte 0 of its pitch
+      if (lane < RW) {
+        const uint8_t* a = I + (size_t)(ipy - 1 + lane) * cols + (ipx - 1);
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(a) & 3);
+        const unsigned* aw = reinterpret_cast<const unsigned*>(a - sh);
+        unsigned w[RPW + 1];
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) w[j] = __ldg(aw + j);
+        w[RPW] = (sh + RW > 4 * RPW) ? __ldg(aw + RPW) : 0u;  // the last word is needed only when the shift pushes the row into it
+        unsigned* rw_ = reinterpret_cast<unsigned*>(region) + lane * RPW;
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) rw_[j] = __funnelshift_r(w[j], w[j + 1], 8 * sh);
       }
-      dtile[i * 2] = (short)dx;
-      dtile[i * 2 + 1] = (short)dy;
+      __syncwarp();
+      // Scharr on the (WIN+1)^2 grid, separable: lane x < RW walks down column x keeping three pixels, S = 3 a + 10 b + 3 c (vertical
+      // smoothing) and D = c - a (vertical difference); dx = S[x+2] - S[x], dy = 3 D[x] + 10 D[x+1] + 3 D[x+2] come from shuffles.
+      {
+        const int x = lane < RW ? lane : RW - 1;
+        int pa = region[x], pb = region[RP + x];
+#pragma unroll
+        for (int ty = 0; ty < DW; ++ty) {
+          const int pc = region[(ty + 2) * RP + x];
+          const int S = (pa + pc) * 3 + pb * 10, D = pc - pa;
+          const int S2 = __shfl_down_sync(0xffffffffu, S, 2), D1 = __shfl_down_sync(0xffffffffu, D, 1), D2 = __shfl_down_sync(0xffffffffu, D, 2);
+          const int dx = S2 - S, dy = (D2 + D) * 3 + D1 * 10;
+          if (lane < DW) reinterpret_cast<unsigned*>(dtile)[ty * DW + lane] = ((unsigned)dx & 0xffffu) | ((unsigned)dy << 16);
+          pa = pb;
+          pb = pc;
+        }
+      }
+    } else {
+      // stage region: origin (ipx-1, ipy-1), REFLECT_101 == reads of OpenCV's padded level
+      for (int i = lane; i < RW * RW; i += 32) {
+        const int ry = i / RW, rx = i - ry * RW;
+        const int sy = reflect101(ipy - 1 + ry, rows), sx = reflect101(ipx - 1 + rx, cols);
+        region[ry * RP + rx] = I[(size_t)sy * cols + sx];
+      }
+      __syncwarp();
+      // Scharr derivatives on the (win+1)^2 grid; zero outside the image (BORDER_CONSTANT)
+      for (int i = lane; i < DW * DW; i += 32) {
+        const int ty = i / DW, tx = i - ty * DW;
+        const int X = ipx + tx, Y = ipy + ty;
+        const bool inside = (X >= 0 && X < cols && Y >= 0 && Y < rows);
+        const uint8_t* r0 = region + ty * RP + tx;  // row Y-1, col X-1
+        const uint8_t* r1 = r0 + RP;
+        const uint8_t* r2 = r1 + RP;
+        int dx = 0, dy = 0;
+        if (inside) {
+          const int t0l = (r0[0] + r2[0]) * 3 + r1[0] * 10;
+          const int t0r = (r0[2] + r2[2]) * 3 + r1[2] * 10;
+          const int t1l = r2[0] - r0[0], t1c = r2[1] - r0[1], t1r = r2[2] - r0[2];
+          dx = t0r - t0l;
+          dy = (t1r + t1l) * 3 + t1c * 10;
+        }
+        dtile[i * 2] = (short)dx;
+        dtile[i * 2 + 1] = (short)dy;
+      }
     }
     __syncwarp();
     // template + structure tensor: slot s of this lane is window pixel (y = 2 s + r, x = c)
@@ -868,11 +1045,12 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
       const int y = 2 * s + r;
       int ival = 0, ix = 0, iy = 0;
       if (c < WIN && y < WIN) {
-        const uint8_t* q = region + (y + 1) * RW + (c + 1);
-        const short* dq = dtile + (y * DW + c) * 2;
-        ival = descale(q[0] * iw00 + q[1] * iw01 + q[RW] * iw10 + q[RW + 1] * iw11, 9);
-        ix = descale(dq[0] * iw00 + dq[2] * iw01 + dq[2 * DW] * iw10 + dq[2 * DW + 2] * iw11, 14);
-        iy = descale(dq[1] * iw00 + dq[3] * iw01 + dq[2 * DW + 1] * iw10 + dq[2 * DW + 3] * iw11, 14);
+        const uint8_t* q = region + (y + 1) * RP + (c + 1);
+        const unsigned* dq = reinterpret_cast<const unsigned*>(dtile) + (y * DW + c);  // packed (dx | dy << 16)
+        const unsigned d00 = dq[0], d01 = dq[1], d10 = dq[DW], d11 = dq[DW + 1];
+        ival = descale(q[0] * iw00 + q[1] * iw01 + q[RP] * iw10 + q[RP + 1] * iw11, 9);
+        ix = descale((int)(short)(d00 & 0xffffu) * iw00 + (int)(short)(d01 & 0xffffu) * iw01 + (int)(short)(d10 & 0xffffu) * iw10 + (int)(short)(d11 & 0xffffu) * iw11, 14);
+        iy = descale(((int)d00 >> 16) * iw00 + ((int)d01 >> 16) * iw01 + ((int)d10 >> 16) * iw10 + ((int)d11 >> 16) * iw11, 14);
       }
       tI[s] = ival;
       if (PACK) tX[s] = (ix & 0xffff) | (iy << 16);
@@ -900,10 +1078,13 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(co
     auto fetch = [&](int inx, int iny, bool interior, int (&v0)[NS], int (&v1)[NS]) {
       if (interior) {
         const uint8_t* __restrict__ q = J + (size_t)(iny + r) * cols + (inx + cx);
+        const size_t two_rows = 2 * (size_t)cols;
+        const size_t last_off = r == 1 ? 0 : (size_t)cols;  // the last slot of the upper half-warp would step past the window
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-          v0[s] = __ldg(q + (size_t)(2 * s) * cols);
-          v1[s] = __ldg(q + (size_t)(2 * s + ((s == NS - 1 && r == 1) ? 0 : 1)) * cols);
+          v0[s] = __ldg(q);
+          v1[s] = __ldg(q + (s == NS - 1 ? last_off : (size_t)cols));
+          q += two_rows;
         }
       } else {
         const int X = reflect101(inx + cx, cols);
