@@ -52,21 +52,40 @@ struct Mirror {
   T* h = nullptr;
   T* d = nullptr;
   size_t n = 0;
-  bool alloc(size_t count) {
+  // zero_copy: a host-written table that one kernel reads once.  The kernel reads the pinned host memory in place (mapped into the
+  // device address space), so there is no cudaMemcpyAsync call and — what matters end to end — the table does not queue behind the
+  // frame uploads in the H2D copy engine's FIFO.  The host must not rewrite it before the consuming kernel has finished (every table
+  // is rewritten only after the wait that ends its phase).
+  bool zero_copy = false;
+  bool alloc(size_t count, bool zc = false) {
     n = count;
+    zero_copy = zc;
     if (!count) return true;
+    if (zc) {
+      if (cudaHostAlloc(reinterpret_cast<void**>(&h), count * sizeof(T), cudaHostAllocMapped) != cudaSuccess) return false;
+      memset(h, 0, count * sizeof(T));
+      return cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) == cudaSuccess;
+    }
     if (cudaMallocHost(reinterpret_cast<void**>(&h), count * sizeof(T)) != cudaSuccess) return false;
     if (cudaMalloc(reinterpret_cast<void**>(&d), count * sizeof(T)) != cudaSuccess) return false;
     memset(h, 0, count * sizeof(T));
     return cudaMemset(d, 0, count * sizeof(T)) == cudaSuccess;
   }
+  // storage carved out of a parent blob (one upload / download of the parent then covers several tables)
+  bool borrowed = false;
+  void adopt(void* h_, void* d_, size_t count) {
+    h = static_cast<T*>(h_); d = static_cast<T*>(d_); n = count; borrowed = true;
+  }
   void release() {
-    if (h) cudaFreeHost(h);
-    if (d) cudaFree(d);
+    if (!borrowed) {
+      if (h) cudaFreeHost(h);
+      if (d && !zero_copy) cudaFree(d);
+    }
     h = d = nullptr;
   }
   cudaError_t up(cudaStream_t st, size_t count = 0, size_t off = 0) {
-    Prof::get().h2d += (count ? count : n) * sizeof(T);
+    Prof::get().h2d += (count ? count : n) * sizeof(T);  // the bytes cross PCIe either way
+    if (zero_copy) return cudaSuccess;
     return cudaMemcpyAsync(d + off, h + off, (count ? count : n) * sizeof(T), cudaMemcpyHostToDevice, st);
   }
   cudaError_t down(cudaStream_t st, size_t count = 0, size_t off = 0) {
@@ -208,6 +227,10 @@ class Batch {
   Mirror<int> tkind, tneed, tnnew;
   Mirror<uint8_t> tstat;
   Mirror<unsigned> tnewkp;
+  Mirror<unsigned long long> fast_off;  // FAST selector: pyramid offset of the sequences that may need a detection
+  // every table of the tracker phase lives in ONE blob: [inputs | pts1 (in/out) | outputs], so the phase costs one H2D and one D2H call
+  Mirror<unsigned char> tt;
+  size_t tt_up_bytes = 0, tt_down_off = 0, tt_down_bytes = 0;
   std::string err;
 
   Batch(xivo_ctx* c, const Json& cfg, int nseq, EkfLayout l, bool tracker_only, int lane = 0, bool lanes = false) : ctx(c), B(nseq), lay(l) {
@@ -228,12 +251,15 @@ class Batch {
               cudaMalloc(reinterpret_cast<void**>(&dKt), sizeof(double) * B * 2 * lay.F * N) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dErr), sizeof(double) * B * N) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dJac), sizeof(FeatJac) * B * lay.F) == cudaSuccess;
-    ok = ok && cam.alloc(B) && X.alloc((size_t)B * kPoseDoubles) && groups.alloc((size_t)B * lay.G * kGroupDoubles) &&
-         fx.alloc((size_t)B * lay.F * 3) && fxp.alloc((size_t)B * lay.F * 2) && R.alloc(B) && Phi.alloc((size_t)B * 529) &&
+    // host-written per-frame tables of the covariance side: read in place by their kernels (Mirror::zero_copy) unless XIVO_ZC_TABLES=0
+    const char* zce = getenv("XIVO_ZC_TABLES");
+    const bool zc = !(zce && zce[0] == '0');
+    ok = ok && cam.alloc(B) && X.alloc((size_t)B * kPoseDoubles, zc) && groups.alloc((size_t)B * lay.G * kGroupDoubles, zc) &&
+         fx.alloc((size_t)B * lay.F * 3, zc) && fxp.alloc((size_t)B * lay.F * 2, zc) && R.alloc(B) && Phi.alloc((size_t)B * 529) &&
          Pmm.alloc((size_t)B * 529) && mh.alloc((size_t)B * lay.F) && pack.alloc((size_t)B * (2 * N + 529)) &&
-         fref.alloc((size_t)B * lay.F) && fsind.alloc((size_t)B * lay.F) && nfeat.alloc(B) && sel.alloc((size_t)B * lay.F) &&
-         nsel.alloc(B) && nops.alloc(B) && active.alloc(B) && ops.alloc((size_t)B * maxops) &&
-         sub_in.alloc((size_t)B * max_sub) && sub_out.alloc((size_t)B * max_sub) && stg.alloc((size_t)B * kMaxStages) && stg_first.alloc(B) && stg_n.alloc(B) &&
+         fref.alloc((size_t)B * lay.F, zc) && fsind.alloc((size_t)B * lay.F, zc) && nfeat.alloc(B, zc) && sel.alloc((size_t)B * lay.F, zc) &&
+         nsel.alloc(B, zc) && nops.alloc(B, zc) && active.alloc(B) && ops.alloc((size_t)B * maxops, zc) &&
+         sub_in.alloc((size_t)B * max_sub, zc) && sub_out.alloc((size_t)B * max_sub) && stg.alloc((size_t)B * kMaxStages, zc) && stg_first.alloc(B, zc) && stg_n.alloc(B, zc) &&
          icst.alloc(B);
     if (!ok) throw std::runtime_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     // initial covariance: identity with the motion block from the config (estimator.cpp:258-302)
@@ -274,9 +300,9 @@ class Batch {
     cam.release(); X.release(); groups.release(); fx.release(); fxp.release(); R.release(); Phi.release(); Pmm.release();
     mh.release(); pack.release(); fref.release(); fsind.release(); nfeat.release(); sel.release(); nsel.release();
     nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); stg.release(); stg_first.release(); stg_n.release();
-    icst.release(); off_prev.release(); frame_ptr.release(); ingest_ptr.release(); ingest_off.release();
-    off_cur.release(); pts0.release(); pts1.release(); lkerr.release(); lkst.release(); npts.release(); kpcount.release();
-    kp.release(); ring_img.release(); pyr_img.release(); tkind.release(); tneed.release(); tnnew.release(); tstat.release(); tnewkp.release();
+    icst.release(); ingest_ptr.release(); ingest_off.release();
+    lkerr.release(); lkst.release(); kpcount.release();
+    kp.release(); tt.release();
   }
 
   int fail(int code, const std::string& m) {
@@ -327,9 +353,10 @@ class Batch {
       }
       if (!total) break;
       XB_CUDA(stg.up(st, total)); XB_CUDA(stg_first.up(st)); XB_CUDA(stg_n.up(st));
-      XB_CUDA(cudaEventRecord(stg_ev, st));
+      if (!stg.zero_copy) XB_CUDA(cudaEventRecord(stg_ev, st));  // copied tables: the staging buffer is free once the upload is done
       stg_inflight = true;
       if (int rc = launch_imu_cov_propagate(st, N, dP, stg.d, stg_first.d, stg_n.d, icst.d, B)) return rc;
+      if (stg.zero_copy) XB_CUDA(cudaEventRecord(stg_ev, st));   // tables read in place: free once the kernel has consumed them
       g_launches += 1;
       {
         int nact = 0;
@@ -457,23 +484,40 @@ class Batch {
     const size_t ib = (size_t)rows * cols * cn;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dRing), (size_t)B * ring_n * ib) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dPyr), (size_t)B * 2 * pd.total) == cudaSuccess;
-    ok = ok && frame_ptr.alloc(B) && ingest_ptr.alloc(B) && ingest_off.alloc(B) && off_prev.alloc(B) && off_cur.alloc(B) && pts0.alloc((size_t)B * max_pts * 2) && pts1.alloc((size_t)B * max_pts * 2) &&
-         lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && npts.alloc(B) && kpcount.alloc(B) &&
+    ok = ok && ingest_ptr.alloc(B) && ingest_off.alloc(B) && lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && kpcount.alloc(B) &&
          kp.alloc((size_t)B * max_kp);
     // the accept / select decisions run on the device unless the homography stage (host code between the two) is on, the mask does
     // not fit into shared memory, or XIVO_HOST_TRACKER_DECISIONS=1 asks for the host path (parity tests compare the two)
     {
       const char* hd = getenv("XIVO_HOST_TRACKER_DECISIONS");
       dev_decide = !e0.tc.do_outlier_rejection && track_mask_bytes(rows, cols) <= 200 * 1024 && !(hd && hd[0] == '1');
-      if (dev_decide)
-        ok = ok && tkind.alloc(B) && tneed.alloc(B) && tnnew.alloc(B) && tstat.alloc((size_t)B * max_pts) && tnewkp.alloc((size_t)B * e0.tc.num_features_max);
+    }
+    if (ok) {  // the tracker-phase tables, carved out of one pinned + one device blob
+      const size_t nB = (size_t)B, npt = (size_t)B * max_pts, nnew = (size_t)B * e0.tc.num_features_max;
+      struct Sec { size_t bytes, off; };
+      Sec sec[14] = {{npt * 2 * 4, 0}, {nB * 8, 0}, {nB * 8, 0}, {nB * 8, 0}, {nB * 4, 0}, {nB * 8, 0}, {nB * 4, 0}, {nB * 4, 0}, {nB * 4, 0},  // pts0 off_cur off_prev fast_off npts frame_ptr ring_img pyr_img tkind
+                     {npt * 2 * 4, 0},                                                                                                   // pts1
+                     {npt, 0}, {nB * 4, 0}, {nB * 4, 0}, {nnew * 4, 0}};                                                                 // tstat tneed tnnew tnewkp
+      size_t off = 0;
+      for (Sec& q : sec) { q.off = off; off += (q.bytes + 15) & ~(size_t)15; }
+      ok = tt.alloc(off);
+      if (ok) {
+        auto H = [&](int i) { return (void*)(tt.h + sec[i].off); };
+        auto D = [&](int i) { return (void*)(tt.d + sec[i].off); };
+        pts0.adopt(H(0), D(0), npt * 2); off_cur.adopt(H(1), D(1), nB); off_prev.adopt(H(2), D(2), nB); fast_off.adopt(H(3), D(3), nB);
+        npts.adopt(H(4), D(4), nB); frame_ptr.adopt(H(5), D(5), nB); ring_img.adopt(H(6), D(6), nB); pyr_img.adopt(H(7), D(7), nB);
+        tkind.adopt(H(8), D(8), nB); pts1.adopt(H(9), D(9), npt * 2); tstat.adopt(H(10), D(10), npt); tneed.adopt(H(11), D(11), nB);
+        tnnew.adopt(H(12), D(12), nB); tnewkp.adopt(H(13), D(13), nnew);
+        tt_up_bytes = sec[10].off;  // inputs + pts1
+        tt_down_off = sec[9].off;   // pts1 + outputs
+        tt_down_bytes = off - sec[9].off;
+      }
     }
     if (!ok) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
     {  // TMA passes where the geometry allows (XIVO_PYRDOWN_TMA=0 keeps the thread-staged kernels: parity tests compare the two)
       const char* tv = getenv("XIVO_PYRDOWN_TMA");
       const char* gv = getenv("XIVO_PYRDOWN_GENERIC");
       if (cn == 1 && (cols & 15) == 0 && (pd.total & 15) == 0 && pd.n_levels > 1 && !(tv && tv[0] == '0') && !(gv && gv[0] == '1')) {
-        if (!ring_img.alloc(B) || !pyr_img.alloc(B)) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
         if (make_pyr_tensor_map(&tm_ring, dRing, rows, cols, ib, (unsigned long long)B * ring_n) == 0) {
           tma_pyr = true;
           for (int l = 1; l + 1 < pd.n_levels; ++l)
@@ -545,11 +589,7 @@ class Batch {
     const int max_new = tc.num_features_max;
     TrackDecideCfg dc{rows, cols, tc.margin, tc.mask_size >> 1, tc.num_features_min, tc.num_features_max, max_pts, max_kp, max_new,
                       (double)tc.max_pixel_displacement};
-    for (int b = 0; b < B; ++b) tkind.h[b] = 0;
-    for (int b : act) tkind.h[b] = kind[b];
-    XB_CUDA(tkind.up(st));
     if (!lk_list.empty()) {
-      XB_CUDA(pts0.up(st)); XB_CUDA(pts1.up(st));
       if (int rc = launch_lk_track(st, dPyr, dPyr, 0, off_prev.d, off_cur.d, pd, pts0.d, pts1.d, lkst.d, lkerr.d, npts.d, max_pts, B,
                                    tc.win_size, tc.max_iter, tc.eps, 1, 1e-4))
         return rc;
@@ -559,17 +599,13 @@ class Batch {
       Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
     }
     if (int rc = launch_track_accept(st, dc, tkind.d, npts.d, pts0.d, pts1.d, lkst.d, tstat.d, tneed.d, B)) return rc;
-    // FAST on the current level-0 image of every tracked sequence; the kernel skips those whose need is 0
-    for (int b = 0; b < B; ++b) off_prev.h[b] = ~0ull;  // reuse off_prev as the FAST selector
-    for (int b : act)
-      if (kind[b] == 1 || kind[b] == 2) off_prev.h[b] = ((size_t)b * 2 + (1 - prev_slot[b])) * pd.total;
-    XB_CUDA(off_prev.up(st));
-    if (int rc = launch_fast_detect(st, dPyr, 0, off_prev.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, tneed.d))
+    // FAST on the current level-0 image of every tracked sequence (fast_off); the kernel skips those whose need is 0
+    if (int rc = launch_fast_detect(st, dPyr, 0, fast_off.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, tneed.d))
       return rc;
     if (int rc = launch_track_select(st, dc, tkind.d, npts.d, pts1.d, tstat.d, tneed.d, kp.d, kpcount.d, tnewkp.d, tnnew.d, B)) return rc;
     g_launches += 3;
-    if (!lk_list.empty()) { XB_CUDA(pts1.down(st)); XB_CUDA(tstat.down(st)); }
-    XB_CUDA(tneed.down(st)); XB_CUDA(tnnew.down(st)); XB_CUDA(tnewkp.down(st));
+    Prof::get().d2h += tt_down_bytes;  // [pts1 | keep flags | need | picks] in one copy
+    XB_CUDA(cudaMemcpyAsync(tt.h + tt_down_off, tt.d + tt_down_off, tt_down_bytes, cudaMemcpyDeviceToHost, st));
     { HostScope hw("wait_lk"); if (int rc = wait(st)) return rc; }
     {
       int ndet = 0;
@@ -680,9 +716,20 @@ class Batch {
         else off_cur.h[b] = ~0ull;
       }
     }
-    XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st)); XB_CUDA(frame_ptr.up(st));
+    if (dev_decide) {
+      // every table of the phase is known now: one upload of the blob [inputs | pts1], then the whole chain
+      for (int b = 0; b < B; ++b) { tkind.h[b] = 0; fast_off.h[b] = ~0ull; }
+      for (int b : act) {
+        tkind.h[b] = kind[b];
+        if (kind[b] == 1 || kind[b] == 2) fast_off.h[b] = ((size_t)b * 2 + (1 - prev_slot[b])) * pd.total;
+      }
+      Prof::get().h2d += tt_up_bytes;
+      XB_CUDA(cudaMemcpyAsync(tt.d, tt.h, tt_up_bytes, cudaMemcpyHostToDevice, st));
+    } else {
+      XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st)); XB_CUDA(frame_ptr.up(st));
+      if (tma_pyr) { XB_CUDA(ring_img.up(st)); XB_CUDA(pyr_img.up(st)); }
+    }
     if (tma_pyr) {
-      XB_CUDA(ring_img.up(st)); XB_CUDA(pyr_img.up(st));
       ProfScope ps("pyrdown", st);
       if (int rc = launch_pyrdown_tma(st, tm_ring, ring_img.d, dPyr, 0, off_cur.d, pd, 0, 1, B)) return rc;
       for (int l = 1; l + 1 < pd.n_levels; ++l) {

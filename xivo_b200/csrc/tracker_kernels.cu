@@ -219,12 +219,17 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_tma_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&mbar)), "r"(PT_BOX_BYTES) : "memory");
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_addr_u32(&tile[0][0])), "l"(reinterpret_cast<unsigned long long>(&src_map)), "r"(sx0), "r"(sy0), "r"(src_img[blockIdx.z]),
-                   "r"(smem_addr_u32(&mbar))
-                 : "memory");
+  if (tid < 32) {  // warp-uniform branch, one elected lane issues (the canonical form: TMA is a warp-level instruction on a uniform path)
+    const int z = src_img[blockIdx.z];
+    unsigned leader = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    if (leader) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&mbar)), "r"(PT_BOX_BYTES) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(smem_addr_u32(&tile[0][0])), "l"(reinterpret_cast<unsigned long long>(&src_map)), "r"(sx0), "r"(sy0), "r"(z),
+                     "r"(smem_addr_u32(&mbar))
+                   : "memory");
+    }
   }
   {  // every thread waits for the box (phase 0 of the barrier)
     unsigned done = 0;
