@@ -40,7 +40,7 @@ int main(int argc, char** argv) {
   std::vector<double> pack(2 * N + 529, 0.0);
   for (int i = 0; i < N; ++i) pack[N + 529 + i] = 1e-3 * (1 + i % 7);
   for (int i = 0; i < 23; ++i) pack[N + i * 23 + i] = 1e-4;
-  const int NP = 230, W = 640, H = 480;
+  const int NP = 300, W = 640, H = 480;
   std::vector<double> x0(NP), y0(NP);
   unsigned rng = 12345;
   auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return (rng >> 8) / double(1 << 24); };
@@ -89,11 +89,23 @@ int main(int argc, char** argv) {
       if (e.pop_ready(&o)) run_msg(o);
     }
     Msg v; v.ts = (uint64_t)fr * 40000000ull; v.type = 3;
+    // emulate the image tracker's policy: tracks leave one by one, new ones arrive in a burst when fewer than 120 remain
+    static std::vector<char> tracked(NP * 64, 0);
+    auto vis = [&](int i, int* id, double* x) {
+      const double xx = x0[i] + 1.5 * fr;
+      *id = i + 1000 * (int)(xx / (W + 300.0));
+      *x = fmod(xx, W + 300.0) - 150.0;
+      return *x > 10 && *x < W - 10;
+    };
+    int ntr = 0;
+    for (int i = 0; i < NP; ++i) { int id; double x; if (vis(i, &id, &x) && tracked[id % (NP * 64)] == 1) ++ntr; }
+    const bool burst = ntr < 120;
     for (int i = 0; i < NP; ++i) {
-      double x = fmod(x0[i] + 1.5 * fr, W + 300.0) - 150.0, y = y0[i];
-      const int frb = fr - fr % 12;  // new points appear in bursts (like a FAST re-detection), they leave one by one
-      const double xb_ = fmod(x0[i] + 1.5 * frb, W + 300.0) - 150.0;
-      if (x > 10 && x < W - 10 && xb_ > 10 && xb_ < W - 10 && xb_ <= x && (int)v.ids.size() < 170) { v.ids.push_back(i + 1000 * (int)((x0[i] + 1.5 * fr) / (W + 300.0))); v.xp_depth.push_back(x); v.xp_depth.push_back(y); v.xp_depth.push_back(2.0); }
+      int id; double x;
+      if (!vis(i, &id, &x)) continue;
+      char& t = tracked[id % (NP * 64)];
+      if (t != 1 && burst && ntr < 150) { t = 1; ++ntr; }
+      if (t == 1) { v.ids.push_back(id); v.xp_depth.push_back(x); v.xp_depth.push_back(y0[i]); v.xp_depth.push_back(2.0); }
     }
     e.push(std::move(v));
     Msg o;

@@ -517,7 +517,7 @@ class Batch {
     {  // TMA passes where the geometry allows (XIVO_PYRDOWN_TMA=0 keeps the thread-staged kernels: parity tests compare the two)
       const char* tv = getenv("XIVO_PYRDOWN_TMA");
       const char* gv = getenv("XIVO_PYRDOWN_GENERIC");
-      if (cn == 1 && (cols & 15) == 0 && (pd.total & 15) == 0 && pd.n_levels > 1 && !(tv && tv[0] == '0') && !(gv && gv[0] == '1')) {
+      if (cn == 1 && (cols & 15) == 0 && (pd.total & 15) == 0 && pd.n_levels > 1 && (tv && tv[0] == '1') && !(gv && gv[0] == '1')) {  // opt-in until the descriptor fault is understood
         if (make_pyr_tensor_map(&tm_ring, dRing, rows, cols, ib, (unsigned long long)B * ring_n) == 0) {
           tma_pyr = true;
           for (int l = 1; l + 1 < pd.n_levels; ++l)
