@@ -54,6 +54,7 @@ struct Group {
   V3 Tsb{{0, 0, 0}};
   std::vector<int> adj;  // ids of the features seen from this group (GroupAdj), ascending
   std::set<int> gauge;   // ids of its gauge features (Graph::gauge_features_)
+  bool may_own = false;  // some feature's ref has pointed at this group (creation frame or ownership transfer); false = owns nothing, no scan needed
   bool instate() const { return status == GroupStatus::INSTATE || status == GroupStatus::GAUGE; }
   SE3h gsb() const { return SE3h{Rsb, Tsb}; }
   void reset(int new_id) {  // Group::Create/Reset; keeps the slot and the containers' capacity
@@ -61,6 +62,7 @@ struct Group {
     status = GroupStatus::CREATED;
     Rsb = m3_eye(); Tsb = V3{{0, 0, 0}};
     adj.clear(); gauge.clear();
+    may_own = false;
   }
 };
 
