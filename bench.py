@@ -552,7 +552,7 @@ def main():
     ap.add_argument("--profile-level", type=int, default=1, help="1: kernels + batch-level host phases, 2: + per-sequence host scopes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seqs", type=int, default=512, help="independent sequences per GPU, split over --batches lock-step batches")
-    ap.add_argument("--batches", type=int, default=1, help="separate xivo_batch handles per GPU, each stepped from its own Python thread (1 = one handle; the library splits it into lanes, see config.lanes)")
+    ap.add_argument("--batches", type=int, default=8, help="separate lock-step xivo_batch handles per GPU, each stepped from its own thread; their per-sequence host code shares the library's worker pool (capped at half the CPU budget)")
     ap.add_argument("--streams", type=int, default=16, help="rendered base streams (texture / trajectory / noise); every sequence replays one of them with its own start delay")
     ap.add_argument("--frames-per-step", type=int, default=8, help="a step = this many consecutive frames (+ IMU) of every sequence: K driver-chosen steps then time seconds, not milliseconds")
     ap.add_argument("--channels", type=int, default=1, choices=[1, 3], help="1 = grey frames (default), 3 = BGR like the reference's cv::imread input (src/app/vio.cpp:72)")

@@ -21,6 +21,7 @@ CFG = os.path.join(ROOT, "xivo_b200", "cfg")
 pytestmark = pytest.mark.gpu
 
 N_STREAMS, N_SEQ, DURATION, G, F = 8, 64, 2.0, 4, 14
+_STREAM_CACHE = {}  # the oracle runs once per session, both parametrisations compare against it
 
 
 def _oracle_stream(seed):
@@ -49,21 +50,29 @@ def _oracle_streams(n, tmp):
     import pickle
     import subprocess
 
+    if n in _STREAM_CACHE:
+        return _STREAM_CACHE[n]
     procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), str(s), os.path.join(tmp, f"stream{s}.pkl")]) for s in range(n)]
     for p in procs:
         assert p.wait() == 0
-    return [pickle.load(open(os.path.join(tmp, f"stream{s}.pkl"), "rb")) for s in range(n)]
+    _STREAM_CACHE[n] = [pickle.load(open(os.path.join(tmp, f"stream{s}.pkl"), "rb")) for s in range(n)]
+    return _STREAM_CACHE[n]
 
 
-def test_bench_workload_640x480_150_features_batch_of_64_through_batch_step(tmp_path):
+@pytest.mark.parametrize("lanes", [0, 3])
+def test_bench_workload_640x480_150_features_batch_of_64_through_batch_step(tmp_path, lanes):
+    """lanes = 0: one lock-step batch on the shared worker pool (the default and the bench mode); lanes = 3: the same handle split into three
+    independent lanes with a library thread each (`"lanes"` in the config)."""
     from xivo_b200 import pyxivo, sim
 
     streams = _oracle_streams(N_STREAMS, str(tmp_path))
     cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    if lanes:
+        cfg["lanes"] = lanes
     assert cfg["tracker_cfg"]["num_features_max"] == 150 and cfg["camera_cfg"]["rows"] == 480 and cfg["camera_cfg"]["cols"] == 640
     seq_stream = [(5 * s + 3) % N_STREAMS for s in range(N_SEQ)]  # replicas of a stream are scattered over the batch
     b = pyxivo.Batch(cfg, n_seq=N_SEQ, max_groups=G, max_features=F)
-    assert b.N == 89
+    assert b.N == 89 and b.lanes == max(1, lanes)
     nframes = len(streams[0]["frames"])
     assert nframes >= 40
     k0 = 0

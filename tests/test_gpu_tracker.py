@@ -191,3 +191,41 @@ def test_fast_pair_kernel_equals_scalar_kernel(ctx, shape, thr, cn, monkeypatch)
     xy, sc, n = ctx.fast_detect(img, thr, nonmax=False, max_kp=1 << 18)
     rxy, rsc, rn = T.fast_detect(img, thr, nonmax=False, max_kp=1 << 18)
     assert n == rn and key(xy, sc) == key(rxy, rsc)
+
+
+@pytest.mark.parametrize("shape", [(480, 640), (240, 320), (512, 512), (1024, 1280), (67, 48), (176, 208), (35, 16)])
+def test_pyramid_tma_kernel_equals_thread_staged_kernel(ctx, shape, monkeypatch):
+    """Levels whose rows are multiples of 16 bytes take pyrdown_tma_kernel by default (one cp.async.bulk.tensor box per CTA, zero fill
+    outside the image, REFLECT_101 patched on the rim CTAs); XIVO_PYRDOWN_TMA=0 keeps pyrdown_vec_kernel.  Same integers, every level
+    identical and equal to the C oracle.  Shapes: the bench frame, a quarter of it, BASELINE configs[0] / [2] (512 x 512, six levels), the
+    stress frame, widths whose coarser levels stop being 16-byte multiples (TMA and thread-staged passes inside one pyramid), a frame
+    narrower than one box."""
+    a, _ = synth.frame_pair(shape[0], shape[1], seed=23)
+    monkeypatch.delenv("XIVO_PYRDOWN_TMA", raising=False)
+    tma = ctx.build_pyramid(a, 15, 5)
+    monkeypatch.setenv("XIVO_PYRDOWN_TMA", "0")
+    staged = ctx.build_pyramid(a, 15, 5)
+    monkeypatch.delenv("XIVO_PYRDOWN_TMA", raising=False)
+    ref = T.pyramid(a, 15, 5)
+    assert len(tma) == len(staged) == len(ref)
+    for lvl, (f, s_, r) in enumerate(zip(tma, staged, ref)):
+        assert np.array_equal(f, s_), f"level {lvl}: TMA pass differs from the thread-staged pass"
+        assert np.array_equal(f, r), f"level {lvl}: differs from the oracle"
+
+
+@pytest.mark.parametrize("shape,thr", [((480, 640), 5), ((480, 640), 20), ((512, 512), 20), ((1024, 1280), 20), ((240, 320), 40), ((70, 96), 5), ((33, 16), 5)])
+def test_fast_tma_kernel_equals_thread_staged_kernel(ctx, shape, thr, monkeypatch):
+    """Single-channel images with 16-byte rows take fast_pair_tma_kernel by default (the tile arrives as one cp.async.bulk.tensor box,
+    zero-filled outside the image); XIVO_FAST_TMA=0 keeps the thread-staged tile load.  Identical keypoints and scores, equal to the C oracle,
+    with and without non-max suppression."""
+    a, _ = synth.frame_pair(shape[0], shape[1], seed=37)
+    key = lambda xy_, sc_: sorted(zip(xy_[:, 1].tolist(), xy_[:, 0].tolist(), sc_.tolist()))
+    for nonmax in (True, False):
+        monkeypatch.delenv("XIVO_FAST_TMA", raising=False)
+        xy, sc, n = ctx.fast_detect(a, thr, nonmax=nonmax, max_kp=1 << 18)
+        monkeypatch.setenv("XIVO_FAST_TMA", "0")
+        xy2, sc2, n2 = ctx.fast_detect(a, thr, nonmax=nonmax, max_kp=1 << 18)
+        monkeypatch.delenv("XIVO_FAST_TMA", raising=False)
+        rxy, rsc, rn = T.fast_detect(a, thr, nonmax=nonmax, max_kp=1 << 18)
+        assert n == n2 == rn
+        assert key(xy, sc) == key(xy2, sc2) == key(rxy, rsc)

@@ -91,11 +91,12 @@ def test_tma_pyramid_equals_thread_staged_pyramid(size):
     frames = [synth.frame_from_canvas(canvas, rows, cols, (3 * k, 2 * k), noise_seed=50 + k, pad=32) for k in range(6)]
 
     def run(tma):
-        os.environ["XIVO_PYRDOWN_TMA"] = "1" if tma else "0"
+        os.environ["XIVO_PYRDOWN_TMA"] = os.environ["XIVO_FAST_TMA"] = "1" if tma else "0"  # both TMA passes (pyramid, FAST tiles) on / off
         try:
             return _run(cfg, frames, host_decisions=False, n_seq=2)
         finally:
             os.environ.pop("XIVO_PYRDOWN_TMA", None)
+            os.environ.pop("XIVO_FAST_TMA", None)
 
     n = _same(run(True), run(False))
     assert max(n) > 100

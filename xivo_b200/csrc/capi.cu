@@ -93,8 +93,20 @@ int xivo_build_pyramid(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, in
   XB_REQUIRE(pyr.ok(), "cudaMalloc failed");
   cudaStream_t st = ctx->stream;
   XB_CUDA(cudaMemcpyAsync(pyr.p, img, (size_t)rows * cols * cn, cudaMemcpyHostToDevice, st));
-  int rc = launch_build_pyramid(st, pyr.p, d.total, nullptr, d, 1);
-  if (rc) return rc;
+  // levels whose rows are 16-byte multiples go through the TMA pass (pyrdown_tma_kernel) like in the estimator; XIVO_PYRDOWN_TMA=0 keeps
+  // the thread-staged kernels (the parity tests run both against the oracle)
+  const char* tv = getenv("XIVO_PYRDOWN_TMA");
+  const char* gv = getenv("XIVO_PYRDOWN_GENERIC");
+  const bool tma = cn == 1 && !(tv && tv[0] == '0') && !(gv && gv[0] == '1');
+  DevBuf<int> zero(1);
+  XB_REQUIRE(zero.ok(), "cudaMalloc failed");
+  XB_CUDA(cudaMemsetAsync(zero.p, 0, sizeof(int), st));
+  for (int l = 0; l + 1 < d.n_levels; ++l) {
+    CUtensorMap map;
+    if (tma && (d.cols[l] & 15) == 0 && (d.off[l] & 15) == 0 && make_pyr_tensor_map(&map, pyr.p + d.off[l], d.rows[l], d.cols[l], d.total, 1) == 0) {
+      if (int rc = launch_pyrdown_tma(st, map, zero.p, pyr.p, d.total, nullptr, d, l, 0, 1)) return rc;
+    } else if (int rc = launch_pyrdown_level(st, pyr.p, d.total, nullptr, d, 1, nullptr, l)) return rc;
+  }
   g_launches += d.n_levels - 1;
   XB_CUDA(cudaMemcpyAsync(out, pyr.p, d.total, cudaMemcpyDeviceToHost, st));
   XB_CUDA(cudaStreamSynchronize(st));
@@ -112,7 +124,12 @@ int xivo_fast_detect(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int 
   DevBuf<int> dcnt(1);
   XB_REQUIRE(dimg.ok() && dkp.ok() && dcnt.ok(), "cudaMalloc failed");
   XB_CUDA(cudaMemcpyAsync(dimg.p, img, (size_t)rows * cols * cn, cudaMemcpyHostToDevice, st));
-  int rc = launch_fast_detect(st, dimg.p, 0, nullptr, rows, cols, cn, threshold, nonmax, dkp.p, cap, dcnt.p, 1);
+  // single-channel images with 16-byte rows are tiled by TMA (fast_pair_tma_kernel) like in the estimator; XIVO_FAST_TMA=0 = thread-staged tiles
+  const char* fv = getenv("XIVO_FAST_TMA");
+  CUtensorMap map;
+  const bool tma = cn == 1 && (cols & 15) == 0 && !(fv && fv[0] == '0') && make_fast_tensor_map(&map, dimg.p, rows, cols, (size_t)rows * cols, 1) == 0;
+  int rc = launch_fast_detect(st, dimg.p, (size_t)rows * cols * cn, nullptr, rows, cols, cn, threshold, nonmax, dkp.p, cap, dcnt.p, 1, nullptr,
+                              tma ? &map : nullptr, (size_t)rows * cols);
   if (rc) return rc;
   g_launches += 1;
   int cnt = 0;

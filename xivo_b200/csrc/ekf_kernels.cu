@@ -3,6 +3,9 @@
 // projection.  All fp64 (the reference is fp64 Eigen, /root/reference/common/alias.h:11);
 // the covariance P stays resident in HBM, one N x N block per independent filter.
 #include "hostmath.h"
+#include <atomic>
+#include <algorithm>
+
 #include "kernels.h"
 #include "prof.h"
 
@@ -75,25 +78,62 @@ __device__ __forceinline__ int jac_col(int k, int goff, int foff) {
   return k < 6 ? k : (k < 12 ? 15 + (k - 6) : (k < 18 ? goff + (k - 12) : foff + (k - 18)));
 }
 
-__global__ void __launch_bounds__(32) jacobian_gate_kernel(EkfLayout lay, const CameraParams* __restrict__ cam,
+// The covariance edit list of one filter (AddGroupToState / AddFeatureToState / Remove* / FixFeatureXY / SwitchRefGroup,
+// /root/reference/src/estimator.cpp:739-846, :1362-1391, :1474-1478), applied in order by the whole CTA.  cov_edit_kernel is this
+// function alone; the Jacobian / gate kernel and the gain kernel call it first, so that the edits that precede them cost no launch.
+__device__ __forceinline__ void apply_edits(int N, double* __restrict__ Pb, const EditOp* __restrict__ ops, int n, int tid, int nthr) {
+  for (int o = 0; o < n; ++o) {
+    const EditOp op = ops[o];
+    if (op.type == 0) {
+      for (int t = tid; t < op.n * N; t += nthr) {
+        const int r = t / N, c = t - r * N;
+        Pb[(size_t)(op.a + r) * N + c] = 0.0;
+        Pb[(size_t)c * N + op.a + r] = 0.0;
+      }
+    } else if (op.type == 1) {
+      for (int t = tid; t < op.n * N; t += nthr) {  // rows: P[a+r, :] = P[b+r, :]
+        const int r = t / N, c = t - r * N;
+        Pb[(size_t)(op.a + r) * N + c] = Pb[(size_t)(op.b + r) * N + c];
+      }
+      __syncthreads();
+      for (int t = tid; t < op.n * N; t += nthr) {  // cols: P[:, a+r] = P[:, b+r]
+        const int r = t / N, c = t - r * N;
+        Pb[(size_t)c * N + op.a + r] = Pb[(size_t)c * N + op.b + r];
+      }
+    } else if (op.type == 2) {
+      if (tid < 9) Pb[(size_t)(op.a + tid / 3) * N + op.a + tid % 3] = op.blk[tid];
+    }
+    __syncthreads();
+  }
+}
+
+// One CTA per filter: [edit list] -> one warp per in-state feature (Jacobian on lane 0, the 21 x 21 gate contraction over the lanes).
+constexpr int JG_MAX_WARPS = 16;
+__global__ void __launch_bounds__(JG_MAX_WARPS * 32) jacobian_gate_kernel(EkfLayout lay, const CameraParams* __restrict__ cam,
                                                            const double* __restrict__ X, const double* __restrict__ groups,
                                                            const double* __restrict__ feat_x, const double* __restrict__ feat_xp,
                                                            const int* __restrict__ feat_ref, const int* __restrict__ feat_sind,
-                                                           const int* __restrict__ nfeat, const double* __restrict__ P,
+                                                           const int* __restrict__ nfeat, double* __restrict__ P,
                                                            const double* __restrict__ Rmeas, FeatJac* __restrict__ out,
-                                                           double* __restrict__ J_dense, double* __restrict__ mh_out) {
-  const int b = blockIdx.y, i = blockIdx.x, lane = threadIdx.x;
-  if (i >= nfeat[b]) return;
+                                                           double* __restrict__ J_dense, double* __restrict__ mh_out,
+                                                           const EditOp* __restrict__ ops, const int* __restrict__ ops_first,
+                                                           const int* __restrict__ nops) {
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int N = lay.N();
-  __shared__ FeatJac sj;
+  double* __restrict__ Pb = P + (size_t)b * N * N;
+  if (ops) apply_edits(N, Pb, ops + ops_first[b], nops[b], threadIdx.x, blockDim.x);  // uniform over the CTA (barriers inside)
+  __shared__ FeatJac sjs[JG_MAX_WARPS];
+  FeatJac& sj = sjs[warp];
+  const int nf = nfeat[b];
+  for (int i = warp; i < nf; i += nwarps) {
   const size_t fi = (size_t)b * lay.F + i;
+  __syncwarp();
   if (lane == 0) {
     const int ref = feat_ref[fi];
     compute_feature_jacobian(lay, cam[b], X + (size_t)b * kPoseDoubles, groups + ((size_t)b * lay.G + ref) * kGroupDoubles,
                              feat_x + 3 * fi, feat_xp + 2 * fi, ref, feat_sind[fi], &sj);
   }
   __syncwarp();
-  const double* __restrict__ Pb = P + (size_t)b * N * N;
   const int goff = sj.goff, foff = sj.foff;
   double s00 = 0, s01 = 0, s11 = 0;
   for (int t = lane; t < kJacNnz * kJacNnz; t += 32) {
@@ -127,16 +167,17 @@ __global__ void __launch_bounds__(32) jacobian_gate_kernel(EkfLayout lay, const 
       Jd[(size_t)r * N + jac_col(k, goff, foff)] = sj.J[r][k];
     }
   }
+  }  // features of this warp
 }
 
 int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const double* X, const double* groups,
                          const double* feat_x, const double* feat_xp, const int* feat_ref, const int* feat_sind,
-                         const int* nfeat, const double* P, const double* Rmeas, FeatJac* out, double* J_dense, double* mh_out,
-                         int batch) {
-  dim3 grid(lay.F, batch);
+                         const int* nfeat, double* P, const double* Rmeas, FeatJac* out, double* J_dense, double* mh_out,
+                         int batch, const EditOp* ops, const int* ops_first, const int* nops) {
   ProfScope ps("jacobian_gate", st);
-  jacobian_gate_kernel<<<grid, 32, 0, st>>>(lay, cam, X, groups, feat_x, feat_xp, feat_ref, feat_sind, nfeat, P, Rmeas, out,
-                                            J_dense, mh_out);
+  const int warps = std::max(1, std::min(lay.F, JG_MAX_WARPS));
+  jacobian_gate_kernel<<<batch, warps * 32, 0, st>>>(lay, cam, X, groups, feat_x, feat_xp, feat_ref, feat_sind, nfeat, P, Rmeas, out,
+                                                     J_dense, mh_out, ops, ops_first, nops);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -161,13 +202,16 @@ __global__ void __launch_bounds__(GAIN_THREADS) ekf_gain_kernel(int N, EkfLayout
                                                                 const int* __restrict__ sel, const int* __restrict__ nsel,
                                                                 int Mdense, const double* __restrict__ Hd,
                                                                 const double* __restrict__ diagR, const double* __restrict__ innd,
-                                                                const double* __restrict__ Rmeas, const double* __restrict__ P,
+                                                                const double* __restrict__ Rmeas, double* __restrict__ P,
                                                                 double* __restrict__ err, double* __restrict__ HP,
-                                                                double* __restrict__ Kt, double* __restrict__ H_dense, int Mmax) {
+                                                                double* __restrict__ Kt, double* __restrict__ H_dense, int Mmax,
+                                                                const EditOp* __restrict__ ops, const int* __restrict__ ops_first,
+                                                                const int* __restrict__ nops) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int M = SPARSE ? 2 * nsel[b] : Mdense;
-  const double* __restrict__ Pb = P + (size_t)b * N * N;
+  if (ops) apply_edits(N, P + (size_t)b * N * N, ops + ops_first[b], nops[b], tid, GAIN_THREADS);  // the post-gate edit list (uniform over the CTA)
+  const double* Pb = P + (size_t)b * N * N;  // (no __restrict__: the edits above wrote P, the loads below must not take the non-coherent path)
   double* __restrict__ HPb = HP + (size_t)b * Mmax * N;
   double* __restrict__ Ktb = Kt + (size_t)b * Mmax * N;
   double* __restrict__ errb = err + (size_t)b * N;
@@ -332,14 +376,21 @@ static size_t gain_smem(int Mmax, bool sparse) {
 }
 
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel, const double* Rmeas,
-                      double* P, double* err, double* HP, double* Kt, double* H_dense, int batch, int tensor_core) {
+                      double* P, double* err, double* HP, double* Kt, double* H_dense, int batch, int tensor_core, const EditOp* ops,
+                      const int* ops_first, const int* nops) {
   const int N = lay.N(), Mmax = 2 * lay.F;
   const size_t smem = gain_smem(Mmax, true);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: 2*F too large for the shared-memory Cholesky");
-  XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {  // one attribute call per size, not one per launch (every CUDA call of a driver thread contends with the other batches' drivers)
+    static std::atomic<size_t> attr{0};
+    if (smem > attr.load(std::memory_order_relaxed)) {
+      XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr.store(smem, std::memory_order_relaxed);
+    }
+  }
   ProfRec* pi_ = Prof::get().start("ekf_gain", st);
   ekf_gain_kernel<true><<<batch, GAIN_THREADS, smem, st>>>(N, lay, jac, sel, nsel, 0, nullptr, nullptr, nullptr, Rmeas, P, err, HP,
-                                                          Kt, H_dense, Mmax);
+                                                          Kt, H_dense, Mmax, ops, ops_first, nops);
   Prof::get().stop(pi_, st);
   if (tensor_core) return launch_ekf_cov_tc(st, N, nsel, 0, Mmax, HP, Kt, P, batch);
   const int nt = (N + CT - 1) / CT;
@@ -358,7 +409,7 @@ int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, cons
   XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   EkfLayout lay{0, 0};
   ekf_gain_kernel<false><<<batch, GAIN_THREADS, smem, st>>>(N, lay, nullptr, nullptr, nullptr, M, H, diagR, inn, nullptr, P, err,
-                                                           HP, Kt, nullptr, M);
+                                                           HP, Kt, nullptr, M, nullptr, nullptr, nullptr);
   if (tensor_core) return launch_ekf_cov_tc(st, N, nullptr, M, M, HP, Kt, P, batch);
   const int nt = (N + CT - 1) / CT;
   ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nullptr, M, M, HP, Kt, P);
@@ -372,38 +423,15 @@ int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, cons
 // the host queues them and one launch applies them in order.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cov_edit_kernel(int N, double* __restrict__ P, const EditOp* __restrict__ ops,
-                                                       const int* __restrict__ nops, int max_ops) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  double* __restrict__ Pb = P + (size_t)b * N * N;
-  const int n = nops[b];
-  for (int o = 0; o < n; ++o) {
-    const EditOp op = ops[(size_t)b * max_ops + o];
-    if (op.type == 0) {
-      for (int t = tid; t < op.n * N; t += 256) {
-        const int r = t / N, c = t - r * N;
-        Pb[(size_t)(op.a + r) * N + c] = 0.0;
-        Pb[(size_t)c * N + op.a + r] = 0.0;
-      }
-    } else if (op.type == 1) {
-      for (int t = tid; t < op.n * N; t += 256) {  // rows: P[a+r, :] = P[b+r, :]
-        const int r = t / N, c = t - r * N;
-        Pb[(size_t)(op.a + r) * N + c] = Pb[(size_t)(op.b + r) * N + c];
-      }
-      __syncthreads();
-      for (int t = tid; t < op.n * N; t += 256) {  // cols: P[:, a+r] = P[:, b+r]
-        const int r = t / N, c = t - r * N;
-        Pb[(size_t)c * N + op.a + r] = Pb[(size_t)c * N + op.b + r];
-      }
-    } else if (op.type == 2) {
-      if (tid < 9) Pb[(size_t)(op.a + tid / 3) * N + op.a + tid % 3] = op.blk[tid];
-    }
-    __syncthreads();
-  }
+                                                       const int* __restrict__ nops, int max_ops, const int* __restrict__ first) {
+  const int b = blockIdx.x;
+  apply_edits(N, P + (size_t)b * N * N, ops + (first ? (size_t)first[b] : (size_t)b * max_ops), nops[b], threadIdx.x, 256);
 }
 
-int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops, const int* nops, int max_ops, int batch) {
+// first (device, optional): start of filter b's list inside a packed ops array; null = filter b owns ops[b * max_ops ...)
+int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops, const int* nops, int max_ops, int batch, const int* first) {
   ProfScope ps("cov_edit", st);
-  cov_edit_kernel<<<batch, 256, 0, st>>>(N, P, ops, nops, max_ops);
+  cov_edit_kernel<<<batch, 256, 0, st>>>(N, P, ops, nops, max_ops, first);
   XB_CUDA(cudaGetLastError());
   return 0;
 }

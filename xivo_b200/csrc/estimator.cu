@@ -94,6 +94,40 @@ struct Mirror {
   }
 };
 
+// Completion of a stream without CUDA calls in the wait loop: the driver thread asks the stream to write a ticket number into mapped
+// pinned memory behind everything enqueued so far (cuStreamWriteValue32, fetched from the driver at run time; a one-thread kernel where
+// the driver lacks it) and then polls that word.  Why: every runtime call of a driver thread contends with the calls of the other
+// batches' drivers -- measured on the B200 box (profiles/r02g_api_probe.txt), the runtime sustains ~0.7 M calls/s in total however many
+// threads issue them, and threads spinning on cudaEventQuery slow the issuing threads down by a further third.
+typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWriteValue32Fn stream_write_value32() {
+  static StreamWriteValue32Fn fn = [] {
+    const char* off = getenv("XIVO_NO_STREAM_MEMOPS");
+    if (off && off[0] == '1') return (StreamWriteValue32Fn) nullptr;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+    return reinterpret_cast<StreamWriteValue32Fn>(p);
+  }();
+  return fn;
+}
+__global__ void ticket_kernel(unsigned* flag, unsigned value) {
+  *flag = value;
+  __threadfence_system();
+}
+struct StreamTicket {
+  unsigned* h = nullptr;  // mapped pinned word the stream writes
+  unsigned* d = nullptr;  // its device address
+  unsigned next = 0;      // last ticket handed out
+  bool alloc() {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped) != cudaSuccess) return false;
+    memset(h, 0, 64);
+    return cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) == cudaSuccess;
+  }
+  void release() { if (h) cudaFreeHost(h); h = d = nullptr; }
+  bool reached(unsigned t) const { return (int)(*reinterpret_cast<volatile unsigned*>(h) - t) >= 0; }
+};
+
 // CPU tokens: with more lane threads than CPUs in the quota, at most `count` of them run host code at a time; a lane hands its token
 // back while it sleeps on a CUDA event.  (Exceeding a cgroup CPU quota stalls every thread of the process for the rest of the period.)
 class CpuTokens {
@@ -183,15 +217,22 @@ class Batch {
   double *dHP = nullptr, *dKt = nullptr, *dErr = nullptr;
   FeatJac* dJac = nullptr;
   Mirror<CameraParams> cam;
-  Mirror<double> X, groups, fx, fxp, R, Phi, Pmm, mh, pack;
-  Mirror<int> fref, fsind, nfeat, sel, nsel, nops;
-  Mirror<unsigned char> active;
-  Mirror<EditOp> ops;
+  Mirror<double> X, groups, fx, fxp, R, mh, pack;
+  Mirror<int> fref, fsind, nfeat, sel, nsel;
+  // Host-written tables go down as ONE copy per phase: each phase owns a pinned + device blob, its tables are views into it, and the
+  // variable-length table (sub-filter inputs, packed edit list, packed stage records) sits last so that only its used part is copied.
+  Mirror<unsigned char> blobS, blobJ, blobU, blobI[2];
+  size_t blobS_fixed = 0, blobJ_fixed = 0, blobU_fixed = 0, blobI_fixed = 0;  // bytes in front of the variable-length table
+  Mirror<EditOp> opsJ, opsU;              // packed edit lists: filter b owns [first[b], first[b] + nops[b])
+  Mirror<int> nopsJ, firstJ, nopsU, firstU;
   Mirror<SubfilterIn> sub_in;
   Mirror<SubfilterOut> sub_out;
-  Mirror<ImuStage> stg;     // packed stage records of all filters
-  Mirror<int> stg_first, stg_n;
+  Mirror<ImuStage> stg[2];  // packed stage records of all filters, two staging halves used alternately
+  Mirror<int> stg_first[2], stg_n[2];
+  int stg_half = 0;
+  unsigned stg_busy[2] = {0, 0};  // st2 ticket after which the half may be refilled (0 = free)
   Mirror<ImuConst> icst;
+  StreamTicket tk1, tk2;    // completion flags of st1 / st2
   // The covariance side (IMU propagation, slot edits, Jacobians, update) runs on its own stream so that it
   // overlaps the image tracker's kernels and host phases, which use ctx->stream.
   cudaStream_t st2 = nullptr;
@@ -200,8 +241,6 @@ class Batch {
   cudaStream_t st_copy = nullptr;
   std::vector<cudaEvent_t> ring_ev;
   cudaEvent_t wait_ev = nullptr;
-  cudaEvent_t stg_ev = nullptr;  // stage-record upload finished (the pinned staging buffer may be refilled)
-  bool stg_inflight = false;
   // tracker device state (allocated at the first image)
   bool img_ready = false;
   int rows = 0, cols = 0, cn = 0, ring_n = 0, max_pts = 0, max_kp = 0;
@@ -212,6 +251,7 @@ class Batch {
   Mirror<unsigned long long> off_prev, off_cur;
   Mirror<const uint8_t*> frame_ptr, ingest_ptr;  // ring slot of the frame being tracked; sources of a device-resident ingest
   Mirror<unsigned long long> ingest_off;
+  Mirror<unsigned char> blobG;                   // [ingest_ptr | ingest_off]: one copy per gather launch
   Mirror<float> pts0, pts1, lkerr;
   Mirror<uint8_t> lkst;
   Mirror<int> npts, kpcount;
@@ -221,6 +261,8 @@ class Batch {
   CUtensorMap tm_ring;
   CUtensorMap tm_lvl[kMaxPyrLevels];
   bool tm_lvl_ok[kMaxPyrLevels] = {false};
+  bool tma_fast = false;  // FAST tiles by TMA (fast_pair_tma_kernel): tensor map over the level-0 images of the pyramid buffer
+  CUtensorMap tm_fast;
   Mirror<int> ring_img, pyr_img;  // per sequence: image index of the new frame inside the ring map / of the current pyramid inside the level maps
   // device-side tracker decisions (track_accept_kernel / track_select_kernel)
   bool dev_decide = false;
@@ -240,7 +282,6 @@ class Batch {
     else { cudaStreamCreateWithFlags(&st1, cudaStreamNonBlocking); own_st1 = true; }
     cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&stg_ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&wait_ev, cudaEventDisableTiming | (lane_mode ? cudaEventBlockingSync : 0));
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
     cov_tc = est[0]->c.cov_update_tf32x3 ? 1 : 0;
@@ -251,16 +292,62 @@ class Batch {
               cudaMalloc(reinterpret_cast<void**>(&dKt), sizeof(double) * B * 2 * lay.F * N) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dErr), sizeof(double) * B * N) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dJac), sizeof(FeatJac) * B * lay.F) == cudaSuccess;
-    // host-written per-frame tables of the covariance side: read in place by their kernels (Mirror::zero_copy) unless XIVO_ZC_TABLES=0
-    const char* zce = getenv("XIVO_ZC_TABLES");
-    const bool zc = !(zce && zce[0] == '0');
-    ok = ok && cam.alloc(B) && X.alloc((size_t)B * kPoseDoubles, zc) && groups.alloc((size_t)B * lay.G * kGroupDoubles, zc) &&
-         fx.alloc((size_t)B * lay.F * 3, zc) && fxp.alloc((size_t)B * lay.F * 2, zc) && R.alloc(B) && Phi.alloc((size_t)B * 529) &&
-         Pmm.alloc((size_t)B * 529) && mh.alloc((size_t)B * lay.F) && pack.alloc((size_t)B * (2 * N + 529)) &&
-         fref.alloc((size_t)B * lay.F, zc) && fsind.alloc((size_t)B * lay.F, zc) && nfeat.alloc(B, zc) && sel.alloc((size_t)B * lay.F, zc) &&
-         nsel.alloc(B, zc) && nops.alloc(B, zc) && active.alloc(B) && ops.alloc((size_t)B * maxops, zc) &&
-         sub_in.alloc((size_t)B * max_sub, zc) && sub_out.alloc((size_t)B * max_sub) && stg.alloc((size_t)B * kMaxStages, zc) && stg_first.alloc(B, zc) && stg_n.alloc(B, zc) &&
-         icst.alloc(B);
+    ok = ok && cam.alloc(B) && R.alloc(B) && mh.alloc((size_t)B * lay.F) && pack.alloc((size_t)B * (2 * N + 529)) && sub_out.alloc((size_t)B * max_sub) &&
+         icst.alloc(B) && tk1.alloc() && tk2.alloc();
+    if (ok) {  // the per-phase upload blobs and the table views inside them
+      struct Carve {
+        size_t off = 0;
+        size_t take(size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; }
+      };
+      const size_t nB = (size_t)B, nF = (size_t)B * lay.F;
+      {  // sub-filter phase: [X | sub_in ...]
+        Carve c;
+        const size_t oX = c.take(nB * kPoseDoubles * 8);
+        blobS_fixed = c.off;
+        const size_t oS = c.take(nB * max_sub * sizeof(SubfilterIn));
+        ok = ok && blobS.alloc(c.off);
+        if (ok) { X.adopt(blobS.h + oX, blobS.d + oX, nB * kPoseDoubles); sub_in.adopt(blobS.h + oS, blobS.d + oS, nB * max_sub); }
+      }
+      {  // Jacobian / gate phase: [nfeat | nops | first | fref | fsind | fxp | fx | groups | ops ...]
+        Carve c;
+        const size_t o0 = c.take(nB * 4), o1 = c.take(nB * 4), o2 = c.take(nB * 4), o3 = c.take(nF * 4), o4 = c.take(nF * 4), o5 = c.take(nF * 2 * 8),
+                     o6 = c.take(nF * 3 * 8), o7 = c.take(nB * lay.G * kGroupDoubles * 8);
+        blobJ_fixed = c.off;
+        const size_t o8 = c.take(nB * maxops * sizeof(EditOp));
+        ok = ok && blobJ.alloc(c.off);
+        if (ok) {
+          auto H = [&](size_t o) { return (void*)(blobJ.h + o); };
+          auto D = [&](size_t o) { return (void*)(blobJ.d + o); };
+          nfeat.adopt(H(o0), D(o0), nB); nopsJ.adopt(H(o1), D(o1), nB); firstJ.adopt(H(o2), D(o2), nB); fref.adopt(H(o3), D(o3), nF);
+          fsind.adopt(H(o4), D(o4), nF); fxp.adopt(H(o5), D(o5), nF * 2); fx.adopt(H(o6), D(o6), nF * 3);
+          groups.adopt(H(o7), D(o7), nB * lay.G * kGroupDoubles); opsJ.adopt(H(o8), D(o8), nB * maxops);
+        }
+      }
+      {  // update phase: [nsel | nops | first | sel | ops ...]
+        Carve c;
+        const size_t o0 = c.take(nB * 4), o1 = c.take(nB * 4), o2 = c.take(nB * 4), o3 = c.take(nF * 4);
+        blobU_fixed = c.off;
+        const size_t o4 = c.take(nB * maxops * sizeof(EditOp));
+        ok = ok && blobU.alloc(c.off);
+        if (ok) {
+          auto H = [&](size_t o) { return (void*)(blobU.h + o); };
+          auto D = [&](size_t o) { return (void*)(blobU.d + o); };
+          nsel.adopt(H(o0), D(o0), nB); nopsU.adopt(H(o1), D(o1), nB); firstU.adopt(H(o2), D(o2), nB); sel.adopt(H(o3), D(o3), nF);
+          opsU.adopt(H(o4), D(o4), nB * maxops);
+        }
+      }
+      for (int h = 0; h < 2 && ok; ++h) {  // IMU stage records: [first | n | stages ...], two staging halves
+        Carve c;
+        const size_t o0 = c.take(nB * 4), o1 = c.take(nB * 4);
+        blobI_fixed = c.off;
+        const size_t o2 = c.take(nB * kMaxStages * sizeof(ImuStage));
+        ok = ok && blobI[h].alloc(c.off);
+        if (ok) {
+          stg_first[h].adopt(blobI[h].h + o0, blobI[h].d + o0, nB); stg_n[h].adopt(blobI[h].h + o1, blobI[h].d + o1, nB);
+          stg[h].adopt(blobI[h].h + o2, blobI[h].d + o2, nB * kMaxStages);
+        }
+      }
+    }
     if (!ok) throw std::runtime_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     // initial covariance: identity with the motion block from the config (estimator.cpp:258-302)
     std::vector<double> P0((size_t)N * N, 0.0);
@@ -291,16 +378,14 @@ class Batch {
     cudaStreamSynchronize(st1);
     if (own_st1) cudaStreamDestroy(st1);
     if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
-    if (stg_ev) cudaEventDestroy(stg_ev);
     if (wait_ev) cudaEventDestroy(wait_ev);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
     for (cudaEvent_t e : ring_ev) cudaEventDestroy(e);
     for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr})
       if (p) cudaFree(p);
-    cam.release(); X.release(); groups.release(); fx.release(); fxp.release(); R.release(); Phi.release(); Pmm.release();
-    mh.release(); pack.release(); fref.release(); fsind.release(); nfeat.release(); sel.release(); nsel.release();
-    nops.release(); active.release(); ops.release(); sub_in.release(); sub_out.release(); stg.release(); stg_first.release(); stg_n.release();
-    icst.release(); ingest_ptr.release(); ingest_off.release();
+    cam.release(); R.release(); mh.release(); pack.release(); sub_out.release(); blobS.release(); blobJ.release(); blobU.release();
+    blobI[0].release(); blobI[1].release(); tk1.release(); tk2.release();
+    icst.release(); blobG.release();
     lkerr.release(); lkst.release(); kpcount.release();
     kp.release(); tt.release();
   }
@@ -312,20 +397,30 @@ class Batch {
   }
 
   // ---- staging helpers -------------------------------------------------------------------
-  int stage_edits(const std::vector<int>& act) {
-    for (int b = 0; b < B; ++b) nops.h[b] = 0;
+  cudaError_t up_blob(Mirror<unsigned char>& b, size_t bytes, cudaStream_t st) {
+    Prof::get().h2d += bytes;
+    return cudaMemcpyAsync(b.d, b.h, bytes, cudaMemcpyHostToDevice, st);
+  }
+  // pack the pending covariance edits of the given sequences into ops (filter b: [first[b], first[b] + nops[b])); *total = entries used
+  int stage_edits(const std::vector<int>& act, Mirror<EditOp>& ops, Mirror<int>& first, Mirror<int>& nops, int* total) {
+    for (int b = 0; b < B; ++b) { nops.h[b] = 0; first.h[b] = 0; }
+    int n = 0;
     for (int b : act) {
       auto& e = est[b]->edits;
       if ((int)e.size() > maxops) return fail(XIVO_ERR_STATE, "covariance edit list overflow");
+      first.h[b] = n;
       nops.h[b] = (int)e.size();
-      for (size_t i = 0; i < e.size(); ++i) ops.h[(size_t)b * maxops + i] = e[i];
+      for (size_t i = 0; i < e.size(); ++i) ops.h[(size_t)n + i] = e[i];
+      n += (int)e.size();
       e.clear();
     }
+    *total = n;
     return 0;
   }
   // Enqueue the covariance algebra of the queued Runge-Kutta stage records of the given sequences
   // (imu_cov_propagate_kernel).  Asynchronous: the host already holds the propagated nominal state.
   int integrate(const std::vector<int>& act) {
+    HostScope hsi("issue_integrate");
     cudaStream_t st = st2;
     bool any = false;
     for (int b : act) any = any || !est[b]->stages.empty();
@@ -336,31 +431,35 @@ class Batch {
     const int chunk = (kMaxStages / sps) * sps;
     std::vector<size_t> cur(B, 0);
     for (;;) {
-      if (stg_inflight) { XB_CUDA(cudaEventSynchronize(stg_ev)); stg_inflight = false; }
-      for (int b = 0; b < B; ++b) { stg_n.h[b] = 0; stg_first.h[b] = 0; }
+      const int h = stg_half;
+      // the staging half may be refilled once st2 has passed the launch that read it: normally the wait that ended the last frame
+      if (stg_busy[h] && !tk2.reached(stg_busy[h])) {
+        if (int rc = wait(st)) return rc;
+      }
+      stg_busy[h] = 0;
+      for (int b = 0; b < B; ++b) { stg_n[h].h[b] = 0; stg_first[h].h[b] = 0; }
       int total = 0;
       bool more = false;
       for (int b : act) {
         Estimator& e = *est[b];
         const int n = (int)std::min<size_t>((size_t)chunk, e.stages.size() - cur[b]);
         if (n <= 0) continue;
-        stg_first.h[b] = total;
-        stg_n.h[b] = n;
-        memcpy(stg.h + total, e.stages.data() + cur[b], sizeof(ImuStage) * n);
+        stg_first[h].h[b] = total;
+        stg_n[h].h[b] = n;
+        memcpy(stg[h].h + total, e.stages.data() + cur[b], sizeof(ImuStage) * n);
         total += n;
         cur[b] += n;
         more = more || cur[b] < e.stages.size();
       }
       if (!total) break;
-      XB_CUDA(stg.up(st, total)); XB_CUDA(stg_first.up(st)); XB_CUDA(stg_n.up(st));
-      if (!stg.zero_copy) XB_CUDA(cudaEventRecord(stg_ev, st));  // copied tables: the staging buffer is free once the upload is done
-      stg_inflight = true;
-      if (int rc = launch_imu_cov_propagate(st, N, dP, stg.d, stg_first.d, stg_n.d, icst.d, B)) return rc;
-      if (stg.zero_copy) XB_CUDA(cudaEventRecord(stg_ev, st));   // tables read in place: free once the kernel has consumed them
+      XB_CUDA(up_blob(blobI[h], blobI_fixed + (size_t)total * sizeof(ImuStage), st));
+      if (int rc = launch_imu_cov_propagate(st, N, dP, stg[h].d, stg_first[h].d, stg_n[h].d, icst.d, B)) return rc;
+      stg_busy[h] = tk2.next + 1;  // the next ticket of st2 lies behind this launch
+      stg_half ^= 1;
       g_launches += 1;
       {
         int nact = 0;
-        for (int b = 0; b < B; ++b) nact += stg_n.h[b] > 0;
+        for (int b = 0; b < B; ++b) nact += stg_n[h].h[b] > 0;
         // algorithmic bytes: the stage records + the motion block read and written + the 23 x (N-23) strip read, 9 rows of it written (twice: mirrored)
         Prof::get().add_work("imu_cov_propagate", total * (double)sizeof(ImuStage) + nact * 8.0 * (2 * 529 + (23 + 18) * (double)(N - 23)));
       }
@@ -376,16 +475,18 @@ class Batch {
   int flush(const std::vector<int>& act) {
     cudaStream_t st = st2;
     if (int rc = integrate(act)) return rc;
-    if (int rc = stage_edits(act)) return rc;
-    XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
-    if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
+    int nops_total = 0;
+    if (int rc = stage_edits(act, opsJ, firstJ, nopsJ, &nops_total)) return rc;
+    XB_CUDA(up_blob(blobJ, blobJ_fixed + (size_t)nops_total * sizeof(EditOp), st));
+    if (int rc = launch_cov_edit(st, N, dP, opsJ.d, nopsJ.d, maxops, B, firstJ.d)) return rc;
     g_launches += 1;
     { HostScope hw("wait_flush"); if (int rc = wait(st)) return rc; }
     return 0;
   }
 
-  // Wait for a stream without idling the CPU: while the event is pending the driver executes items of
-  // whatever host jobs the other batches of this process have published.
+  // Wait until everything enqueued on st1 / st2 so far has completed, without idling the CPU: the stream writes a ticket into mapped
+  // host memory (StreamTicket); while it is pending the driver executes items of whatever host jobs the other batches of this process
+  // have published.  No CUDA call sits in the loop (a stream query every ~2^16 polls only catches a faulted context).
   int wait(cudaStream_t st) {
     if (lane_mode) {  // sleep on the event; the CPU goes to a lane that has host work
       XB_CUDA(cudaEventRecord(wait_ev, st));
@@ -393,42 +494,85 @@ class Batch {
       const cudaError_t e = cudaEventSynchronize(wait_ev);
       CpuTokens::get().acquire();
       if (e != cudaSuccess) { set_error("CUDA error while waiting: %s", cudaGetErrorString(e)); return XIVO_ERR_CUDA; }
+      if (st == st2) { stg_busy[0] = stg_busy[1] = 0; }
       return 0;
     }
     static const bool help = !(getenv("XIVO_HELP") && getenv("XIVO_HELP")[0] == '0');
-    if (!help) { XB_CUDA(cudaStreamSynchronize(st)); return 0; }
-    XB_CUDA(cudaEventRecord(wait_ev, st));
-    for (;;) {
-      const cudaError_t e = cudaEventQuery(wait_ev);
-      if (e == cudaSuccess) return 0;
-      if (e != cudaErrorNotReady) { set_error("CUDA error while waiting: %s", cudaGetErrorString(e)); return XIVO_ERR_CUDA; }
-      if (!WorkPool::get().help_one()) cpu_relax();
+    StreamTicket& t = st == st2 ? tk2 : tk1;
+    const unsigned want = ++t.next;
+    if (StreamWriteValue32Fn wv = stream_write_value32()) {
+      if (wv(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(t.d), want, 0) != CUDA_SUCCESS) {
+        set_error("cuStreamWriteValue32 failed");
+        return XIVO_ERR_CUDA;
+      }
+    } else {
+      ticket_kernel<<<1, 1, 0, st>>>(t.d, want);
+      XB_CUDA(cudaGetLastError());
     }
+    unsigned polls = 0;
+    while (!t.reached(want)) {
+      if (help && WorkPool::get().help_one()) continue;
+      cpu_relax();
+      if ((++polls & 0xffffu) == 0) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaSuccess && e != cudaErrorNotReady) { set_error("CUDA error while waiting: %s", cudaGetErrorString(e)); return XIVO_ERR_CUDA; }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);  // the copies that precede the ticket in the stream are visible now
+    return 0;
   }
   // Bring one frame per sequence into its ring slot (slot_of[s]) on the copy stream.  Device frames and
   // device-accessible host frames (pinned / registered: the SMs read them over PCIe) take one gather launch,
   // which keeps the H2D copy engine's FIFO free for the small latency-critical table uploads of the other
   // phases; pageable host frames fall back to one cudaMemcpyAsync each.
+  // Device address of a host frame the SMs can read in place (pinned / registered memory), or null.  The answer is cached per
+  // allocation (cuMemGetAddressRange gives its extent): one driver query per pinned pool instead of one runtime call per frame per step.
+  struct HostRange { uintptr_t lo, hi; ptrdiff_t dev_minus_host; };
+  std::vector<HostRange> host_ranges;
+  const uint8_t* mapped_host_pointer(const uint8_t* p, size_t bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    for (const HostRange& r : host_ranges)
+      if (a >= r.lo && a + bytes <= r.hi) return reinterpret_cast<const uint8_t*>(a + r.dev_minus_host);
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type == cudaMemoryTypeUnregistered || !at.devicePointer) {
+      cudaGetLastError();  // clear the sticky "invalid value" of an unregistered pointer
+      return nullptr;
+    }
+    typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn range_fn = [] {
+      void* f = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); f = nullptr; }
+      return reinterpret_cast<RangeFn>(f);
+    }();
+    const uintptr_t da = reinterpret_cast<uintptr_t>(at.devicePointer);
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (range_fn && range_fn(&base, &size, (CUdeviceptr)da) == CUDA_SUCCESS && base && size && da >= (uintptr_t)base && da + bytes <= (uintptr_t)base + size) {
+      const ptrdiff_t d = (ptrdiff_t)da - (ptrdiff_t)a;
+      if (host_ranges.size() >= 64) host_ranges.clear();
+      host_ranges.push_back(HostRange{(uintptr_t)base - d, (uintptr_t)base - d + size, d});
+    }
+    return static_cast<const uint8_t*>(at.devicePointer);
+  }
   int upload_frames(const uint8_t* const* imgs, const std::vector<int>& slot_of, bool on_device, size_t ib) {
+    HostScope hsu("issue_upload_frames");
     const bool zero_copy = g_frame_ingest.load(std::memory_order_relaxed) == 0;
     bool gather = on_device || zero_copy;
     for (int s = 0; s < B; ++s) {
       ingest_off.h[s] = ((size_t)s * ring_n + slot_of[s]) * ib;
       ingest_ptr.h[s] = imgs[s];
       if (!on_device && gather) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, imgs[s]) != cudaSuccess || at.type == cudaMemoryTypeUnregistered || !at.devicePointer) {
-          cudaGetLastError();  // clear the sticky "invalid value" of an unregistered pointer
-          gather = false;
-        } else {
-          ingest_ptr.h[s] = static_cast<const uint8_t*>(at.devicePointer);
-        }
+        if (s == 0) host_ranges.clear();  // one real query per call keeps the cache honest if the caller re-pins / frees its pool between steps
+        const uint8_t* dp = mapped_host_pointer(imgs[s], ib);
+        if (!dp) gather = false;
+        else ingest_ptr.h[s] = dp;
       }
     }
     if (!on_device) Prof::get().h2d += (unsigned long long)ib * B;
     if (gather) {
-      XB_CUDA(ingest_ptr.up(st_copy)); XB_CUDA(ingest_off.up(st_copy));
-      if (int rc = launch_gather_frames(st_copy, ingest_ptr.d, dRing, 0, ingest_off.d, ib, B, on_device ? 64 : 8)) return rc;
+      XB_CUDA(up_blob(blobG, blobG.n, st_copy));  // [sources | ring offsets]
+      if (int rc = launch_gather_frames(st_copy, ingest_ptr.d, dRing, 0, ingest_off.d, ib, B, on_device ? 64 : 2, on_device ? 256 : 128)) return rc;
       g_launches += 1;
     } else {
       // copy engine: runs of sequences whose sources are evenly spaced (frames of one pinned pool) and whose ring slots agree go down as
@@ -462,6 +606,7 @@ class Batch {
   }
   // the caller's frame buffers are free again once the uploads have landed
   int ingest_done() {
+    HostScope hsw("wait_ingest_done");
     XB_CUDA(cudaStreamSynchronize(st_copy));
     return 0;
   }
@@ -484,13 +629,17 @@ class Batch {
     const size_t ib = (size_t)rows * cols * cn;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dRing), (size_t)B * ring_n * ib) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dPyr), (size_t)B * 2 * pd.total) == cudaSuccess;
-    ok = ok && ingest_ptr.alloc(B) && ingest_off.alloc(B) && lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && kpcount.alloc(B) &&
+    ok = ok && blobG.alloc((size_t)B * 16) && lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && kpcount.alloc(B) &&
          kp.alloc((size_t)B * max_kp);
     // the accept / select decisions run on the device unless the homography stage (host code between the two) is on, the mask does
     // not fit into shared memory, or XIVO_HOST_TRACKER_DECISIONS=1 asks for the host path (parity tests compare the two)
     {
       const char* hd = getenv("XIVO_HOST_TRACKER_DECISIONS");
       dev_decide = !e0.tc.do_outlier_rejection && track_mask_bytes(rows, cols) <= 200 * 1024 && !(hd && hd[0] == '1');
+    }
+    if (ok) {
+      ingest_ptr.adopt(blobG.h, blobG.d, B);
+      ingest_off.adopt(blobG.h + (size_t)B * 8, blobG.d + (size_t)B * 8, B);
     }
     if (ok) {  // the tracker-phase tables, carved out of one pinned + one device blob
       const size_t nB = (size_t)B, npt = (size_t)B * max_pts, nnew = (size_t)B * e0.tc.num_features_max;
@@ -514,10 +663,13 @@ class Batch {
       }
     }
     if (!ok) return fail(XIVO_ERR_CUDA, "device allocation for the image tracker failed");
-    {  // TMA passes where the geometry allows (XIVO_PYRDOWN_TMA=0 keeps the thread-staged kernels: parity tests compare the two)
+    {  // TMA passes where the geometry allows (XIVO_PYRDOWN_TMA=0 / XIVO_FAST_TMA=0 keep the thread-staged kernels: parity tests compare the two)
       const char* tv = getenv("XIVO_PYRDOWN_TMA");
       const char* gv = getenv("XIVO_PYRDOWN_GENERIC");
-      if (cn == 1 && (cols & 15) == 0 && (pd.total & 15) == 0 && pd.n_levels > 1 && (tv && tv[0] == '1') && !(gv && gv[0] == '1')) {  // opt-in until the descriptor fault is understood
+      const char* fv = getenv("XIVO_FAST_TMA");
+      if (cn == 1 && (cols & 15) == 0 && (pd.total & 15) == 0 && (pd.off[0] & 15) == 0 && !(fv && fv[0] == '0'))
+        tma_fast = make_fast_tensor_map(&tm_fast, dPyr + pd.off[0], rows, cols, pd.total, (unsigned long long)B * 2) == 0;
+      if (cn == 1 && (cols & 15) == 0 && (pd.total & 15) == 0 && pd.n_levels > 1 && !(tv && tv[0] == '0') && !(gv && gv[0] == '1')) {
         if (make_pyr_tensor_map(&tm_ring, dRing, rows, cols, ib, (unsigned long long)B * ring_n) == 0) {
           tma_pyr = true;
           for (int l = 1; l + 1 < pd.n_levels; ++l)
@@ -581,7 +733,7 @@ class Batch {
   // the accept kernel flagged -> greedy selection (track_select_kernel) -> ONE read-back of [positions | keep flags | picks].  The host
   // then only replays the decisions on its track list (same order, same feature ids as the host path).
   int tracker_decide_on_device(const std::vector<int>& act, const std::vector<int>& lk_list, const std::vector<int>& det_first,
-                               const std::vector<int>& kind) {
+                               const std::vector<int>& kind, std::unique_ptr<HostScope>* hs_issue) {
     cudaStream_t st = st1;
     const TrackerCfg& tc = est[0]->tc;
     Estimator& e0 = *est[0];
@@ -598,14 +750,16 @@ class Batch {
       for (int b : lk_list) np_ += npts.h[b];
       Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
     }
-    if (int rc = launch_track_accept(st, dc, tkind.d, npts.d, pts0.d, pts1.d, lkst.d, tstat.d, tneed.d, B)) return rc;
+    if (int rc = launch_track_accept(st, dc, tkind.d, npts.d, pts0.d, pts1.d, lkst.d, tstat.d, tneed.d, B, kpcount.d)) return rc;
     // FAST on the current level-0 image of every tracked sequence (fast_off); the kernel skips those whose need is 0
-    if (int rc = launch_fast_detect(st, dPyr, 0, fast_off.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, tneed.d))
+    if (int rc = launch_fast_detect(st, dPyr, 0, fast_off.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, tneed.d,
+                                    tma_fast ? &tm_fast : nullptr, pd.total, true))
       return rc;
     if (int rc = launch_track_select(st, dc, tkind.d, npts.d, pts1.d, tstat.d, tneed.d, kp.d, kpcount.d, tnewkp.d, tnnew.d, B)) return rc;
     g_launches += 3;
     Prof::get().d2h += tt_down_bytes;  // [pts1 | keep flags | need | picks] in one copy
     XB_CUDA(cudaMemcpyAsync(tt.h + tt_down_off, tt.d + tt_down_off, tt_down_bytes, cudaMemcpyDeviceToHost, st));
+    hs_issue->reset();
     { HostScope hw("wait_lk"); if (int rc = wait(st)) return rc; }
     {
       int ndet = 0;
@@ -716,6 +870,7 @@ class Batch {
         else off_cur.h[b] = ~0ull;
       }
     }
+    std::unique_ptr<HostScope> hs_issue(new HostScope("issue_tracker"));
     if (dev_decide) {
       // every table of the phase is known now: one upload of the blob [inputs | pts1], then the whole chain
       for (int b = 0; b < B; ++b) { tkind.h[b] = 0; fast_off.h[b] = ~0ull; }
@@ -743,7 +898,8 @@ class Batch {
       for (int b = 0; b < B; ++b) nact += off_cur.h[b] != ~0ull;
       Prof::get().add_work("pyrdown", nact * (7.0 / 3.0) * rows * cols * cn);  // (7/3) W H c bytes
     }
-    if (dev_decide) return tracker_decide_on_device(act, lk_list, det_list, kind);
+    if (dev_decide) return tracker_decide_on_device(act, lk_list, det_list, kind, &hs_issue);
+    hs_issue.reset();
     if (!lk_list.empty()) {
       XB_CUDA(pts0.up(st)); XB_CUDA(pts1.up(st));
       const TrackerCfg& tc = est[0]->tc;
@@ -808,7 +964,8 @@ class Batch {
       for (int b : det_list) off_prev.h[b] = ((size_t)b * 2 + (1 - prev_slot[b])) * pd.total;
       XB_CUDA(off_prev.up(st));
       const TrackerCfg& tc = est[0]->tc;
-      if (int rc = launch_fast_detect(st, dPyr, 0, off_prev.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B))
+      if (int rc = launch_fast_detect(st, dPyr, 0, off_prev.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, nullptr,
+                                      tma_fast ? &tm_fast : nullptr, pd.total))
         return rc;
       g_launches += 1;
       Prof::get().add_work("fast_detect", det_list.size() * 2.0 * rows * cols);  // §8d: 2 W H bytes
@@ -917,16 +1074,19 @@ class Batch {
       });
     }
     const int nsub = sub_off[B];
-    XB_CUDA(X.up(st));
-    if (nsub) {
-      XB_CUDA(sub_in.up(st, nsub));
-      if (int rc = launch_subfilter(st, cam.d, X.d, sub_in.d, sub_out.d, nsub, est[0]->c.sub_Rtri, est[0]->c.sub_mh)) return rc;
-      g_launches += 1;
-      XB_CUDA(sub_out.down(st, nsub));
-      { HostScope hw("wait_subfilter"); if (int rc = wait(st)) return rc; }
+    {
+      HostScope hsi("issue_subfilter");
+      XB_CUDA(up_blob(blobS, blobS_fixed + (size_t)nsub * sizeof(SubfilterIn), st));  // [X | sub_in[0 .. nsub)]
+      if (nsub) {
+        if (int rc = launch_subfilter(st, cam.d, X.d, sub_in.d, sub_out.d, nsub, est[0]->c.sub_Rtri, est[0]->c.sub_mh)) return rc;
+        g_launches += 1;
+        XB_CUDA(sub_out.down(st, nsub));
+      }
     }
+    if (nsub) { HostScope hw("wait_subfilter"); if (int rc = wait(st)) return rc; }
     // ---- select/add features, fill the device tables ----
     std::atomic<int> bad_slot{0};
+    int nops_total = 0;
     {
       HostScope hs("select_and_tables");
       for (int b = 0; b < B; ++b) nfeat.h[b] = 0;
@@ -956,20 +1116,22 @@ class Batch {
       });
       if (int rc = first_error(full)) return rc;
       if (bad_slot) return fail(XIVO_ERR_STATE, "in-state feature without state slot");
-      if (int rc = stage_edits(full)) return rc;
+      if (int rc = stage_edits(full, opsJ, firstJ, nopsJ, &nops_total)) return rc;
     }
-    XB_CUDA(groups.up(st)); XB_CUDA(fx.up(st)); XB_CUDA(fxp.up(st)); XB_CUDA(fref.up(st)); XB_CUDA(fsind.up(st));
-    XB_CUDA(nfeat.up(st)); XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st));
-    if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
-    if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B))
+    std::unique_ptr<HostScope> hs_issue(new HostScope("issue_jacobian"));
+    // one copy: [nfeat | nops | first | fref | fsind | fxp | fx | groups | packed edit list]; the kernel applies the edits, then the features
+    XB_CUDA(up_blob(blobJ, blobJ_fixed + (size_t)nops_total * sizeof(EditOp), st));
+    if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B, opsJ.d,
+                                      firstJ.d, nopsJ.d))
       return rc;
-    g_launches += 2;
+    g_launches += 1;
     {
       double nf = 0;
       for (int b : full) nf += nfeat.h[b];
       Prof::get().add_work("jacobian_gate", nf * 2.0 * N * 8.0);  // §8d: M N 8 bytes of H written
     }
     XB_CUDA(mh.down(st));
+    hs_issue.reset();
     { HostScope hw("wait_jacobian"); if (int rc = wait(st)) return rc; }
     // ---- gating decisions (host), post-gate edits, update (device) ----
     {
@@ -988,18 +1150,19 @@ class Batch {
         nsel.h[b] = k;
       });
       if (int rc = first_error(full)) return rc;
-      if (int rc = stage_edits(full)) return rc;
+      if (int rc = stage_edits(full, opsU, firstU, nopsU, &nops_total)) return rc;
     }
-    XB_CUDA(ops.up(st)); XB_CUDA(nops.up(st)); XB_CUDA(sel.up(st)); XB_CUDA(nsel.up(st));
-    if (int rc = launch_cov_edit(st, N, dP, ops.d, nops.d, maxops, B)) return rc;
-    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B, cov_tc)) return rc;
+    hs_issue.reset(new HostScope("issue_update"));
+    XB_CUDA(up_blob(blobU, blobU_fixed + (size_t)nops_total * sizeof(EditOp), st));  // [nsel | nops | first | sel | packed post-gate edit list]
+    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B, cov_tc, opsU.d, firstU.d, nopsU.d)) return rc;
     if (int rc = launch_pack_state(st, N, dP, dErr, pack.d, B)) return rc;
-    g_launches += 4;
+    g_launches += 3;
     for (int b : full) {
       const double M = 2.0 * nsel.h[b], Nn = N;
       if (M > 0) Prof::get().add_work("ekf_update", 4 * Nn * Nn * Nn + 6 * M * Nn * Nn + 4 * M * M * Nn + M * M * M / 3.0);  // §8d Joseph flop count
     }
     XB_CUDA(pack.down(st));
+    hs_issue.reset();
     { HostScope hw("wait_update"); if (int rc = wait(st)) return rc; }
     Prof::get().collect();
     {
@@ -1102,8 +1265,8 @@ using namespace xb;
 // A batch handle = one or more LANES: independent lock-step sub-batches of consecutive sequences, each with its own streams, device
 // state and a persistent driver thread.  The sequences of a batch are independent Markov chains, so a lane never talks to another lane;
 // while one lane sleeps on the GPU another one runs its host phases, which keeps both the CPUs of the quota and the GPU busy without
-// fork-join parallel-for rounds inside a phase.  Lane count: "lanes" in the config, else XIVO_LANES, else one lane per ~24 sequences
-// (at most twice the CPU budget); a batch of up to 24 sequences is a single lane driven by the calling thread.
+// fork-join parallel-for rounds inside a phase.  Lane count: "lanes" in the config, else XIVO_LANES, else 1 (a single lock-step batch
+// driven by the calling thread, its per-sequence host code on the shared worker pool).
 struct xivo_batch {
   xivo_ctx* ctx = nullptr;
   int total = 0, per = 0, N = 0;
@@ -1178,11 +1341,7 @@ static int choose_lanes(const Json& cfg, int n_seq) {
     const char* e = getenv("XIVO_LANES");
     L = e && *e ? atoi(e) : 0;
   }
-  if (L <= 0) {
-    const char* lw = getenv("LOCAL_WORLD_SIZE");
-    const int share = std::max(1, host_cpu_budget() / std::max(1, lw && *lw ? atoi(lw) : 1));
-    L = std::min((n_seq + 23) / 24, 2 * share);
-  }
+  if (L <= 0) L = 1;  // measured (profiles/r02e_sweep.txt): several lock-step batch handles on the shared worker pool beat lanes (103 k vs 75 k frames/s), so lanes are opt-in
   return std::max(1, std::min(L, n_seq));
 }
 

@@ -14,15 +14,19 @@ int launch_build_pyramid(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_s
 int launch_pyrdown_level(cudaStream_t st, uint8_t* pyr, unsigned long long pyr_stride, const unsigned long long* seq_off, const PyrDesc& d,
                          int batch, const uint8_t* const* frame0, int lvl);
 // TMA pass (tracker_kernels.cu: pyrdown_tma_kernel): single channel, source level with cols % 16 == 0, images at a uniform stride
-int make_pyr_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img);
+int make_pyr_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img, int box_w = 0,
+                        int box_h = 0);
+// box of fast_pair_tma_kernel over the level-0 images of a pyramid buffer (image i at base + i * img_stride)
+int make_fast_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img);
 int launch_pyrdown_tma(cudaStream_t st, const CUtensorMap& map, const int* src_img, uint8_t* pyr, unsigned long long pyr_stride,
                        const unsigned long long* seq_off, const PyrDesc& d, int lvl, int ingest, int batch);
 int launch_gather_frames(cudaStream_t st, const uint8_t* const* src, uint8_t* dst, unsigned long long stride, const unsigned long long* off,
-                         size_t bytes, int batch, int max_chunks = 64);
+                         size_t bytes, int batch, int max_chunks = 64, int threads = 256);
 // need (device, optional): per-sequence gate written by the accept kernel; a sequence with need <= 0 is skipped
 int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off,
                        int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch,
-                       const int* need = nullptr);
+                       const int* need = nullptr, const CUtensorMap* tma_map = nullptr, unsigned long long tma_img_stride = 0,
+                       bool count_is_zero = false /*kp_count was cleared by an earlier kernel of the stream (track_accept)*/);
 // Device-side tracker decisions (accept loop of Tracker::UpdateLK, greedy selection of Tracker::DetectLK); tracker_kernels.cu
 struct TrackDecideCfg {
   int rows, cols, margin, mask_half, num_min, num_max, max_pts, max_kp, max_new;
@@ -30,7 +34,7 @@ struct TrackDecideCfg {
 };
 size_t track_mask_bytes(int rows, int cols);
 int launch_track_accept(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts0, const float* pts1,
-                        const uint8_t* lkst, uint8_t* stat, int* need, int batch);
+                        const uint8_t* lkst, uint8_t* stat, int* need, int batch, int* kp_count_to_zero = nullptr);
 int launch_track_select(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts1, const uint8_t* stat,
                         const int* need, unsigned* kp, const int* kp_count, unsigned* new_kp, int* n_new, int batch);
 size_t lk_smem_bytes(int win, int cn);
@@ -57,6 +61,14 @@ struct FeatJac {
   int goff, foff;
 };
 
+// Covariance edit list (AddGroupToState / AddFeatureToState / Remove* / FixFeatureXY / SwitchRefGroup): applied by cov_edit_kernel or, packed,
+// at the start of the Jacobian / gate kernel and of the gain kernel.
+struct EditOp {
+  int type;  // 0 = zero rows+cols [a, a+n); 1 = copy rows then cols b -> a (n wide); 2 = set 3x3 block at (a, a)
+  int a, b, n;
+  double blk[9];
+};
+
 // Motion + calibration state the Jacobians need: Rsb(9) Tsb(3) Rbc(9) Tbc(3), row-major.
 constexpr int kPoseDoubles = 24;
 constexpr int kGroupDoubles = 12;  // Rsb(9) Tsb(3) of a group slot
@@ -64,16 +76,18 @@ constexpr int kGroupDoubles = 12;  // Rsb(9) Tsb(3) of a group slot
 int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam /*device, per filter*/,
                          const double* X /*B x 24*/, const double* groups /*B x G x 12*/, const double* feat_x /*B x F x 3*/,
                          const double* feat_xp /*B x F x 2*/, const int* feat_ref /*B x F*/, const int* feat_sind /*B x F*/,
-                         const int* nfeat /*B*/, const double* P /*B x N x N*/, const double* Rmeas /*B*/,
+                         const int* nfeat /*B*/, double* P /*B x N x N*/, const double* Rmeas /*B*/,
                          FeatJac* out /*B x F*/, double* J_dense /*B x F x 2 x N or null*/, double* mh_out /*B x F or null*/,
-                         int batch);
+                         int batch, const EditOp* ops = nullptr /*packed edit lists applied to P first*/, const int* ops_first = nullptr /*B*/,
+                         const int* nops = nullptr /*B*/);
 
 // Stack H (FillJacobianBlock semantics) for the selected features and do the measurement update.
 //   sel: B x F indices into the feature table, nsel: B counts (M = 2*nsel)
 // scratch: HP (B x 2F x N), Kt (B x 2F x N).  Outputs: err (B x N), P updated in place.
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel,
                       const double* Rmeas /*B*/, double* P, double* err, double* HP, double* Kt, double* H_dense /*or null*/,
-                      int batch, int tensor_core = 0);
+                      int batch, int tensor_core = 0, const EditOp* ops = nullptr /*packed edit lists applied to P first*/,
+                      const int* ops_first = nullptr /*B*/, const int* nops = nullptr /*B*/);
 
 // Dense-input variant used by the kernel-level C ABI (arbitrary H, diagR), same kernels underneath.
 int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,
@@ -87,13 +101,8 @@ int launch_ekf_cov_tc(cudaStream_t st, int N, const int* nsel, int Mdense, int M
 int ekf_cov_tc_fault(cudaStream_t st);
 
 // Covariance edit list (AddGroupToState / AddFeatureToState / Remove* / FixFeatureXY / SwitchRefGroup).
-struct EditOp {
-  int type;  // 0 = zero rows+cols [a, a+n); 1 = copy rows then cols b -> a (n wide); 2 = set 3x3 block at (a, a)
-  int a, b, n;
-  double blk[9];
-};
-int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops /*B x max_ops*/, const int* nops /*B*/, int max_ops,
-                    int batch);
+int launch_cov_edit(cudaStream_t st, int N, double* P, const EditOp* ops /*B x max_ops, or packed with first*/, const int* nops /*B*/, int max_ops,
+                    int batch, const int* first = nullptr /*B*/);
 
 // Propagation: P[0:23,0:23] <- Pmm ; P[0:23,23:] <- Phi P[0:23,23:] and the symmetric strip.
 int launch_cov_propagate(cudaStream_t st, int N, double* P, const double* Phi /*B x 23 x 23*/, const double* Pmm /*B x 23 x 23*/,

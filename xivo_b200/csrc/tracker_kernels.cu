@@ -31,7 +31,16 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(const uint8_t* const
   const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
   const size_t step = (size_t)gridDim.x * blockDim.x * 16;
   if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(t)) & 15) == 0) {
-    for (size_t i = i0; i + 16 <= bytes; i += step) *reinterpret_cast<uint4*>(t + i) = *reinterpret_cast<const uint4*>(s + i);
+    size_t i = i0;
+    for (; i + 3 * step + 16 <= bytes; i += 4 * step) {  // four loads in flight per thread: what matters when the source is host memory behind PCIe
+      const uint4 v0 = *reinterpret_cast<const uint4*>(s + i), v1 = *reinterpret_cast<const uint4*>(s + i + step);
+      const uint4 v2 = *reinterpret_cast<const uint4*>(s + i + 2 * step), v3 = *reinterpret_cast<const uint4*>(s + i + 3 * step);
+      *reinterpret_cast<uint4*>(t + i) = v0;
+      *reinterpret_cast<uint4*>(t + i + step) = v1;
+      *reinterpret_cast<uint4*>(t + i + 2 * step) = v2;
+      *reinterpret_cast<uint4*>(t + i + 3 * step) = v3;
+    }
+    for (; i + 16 <= bytes; i += step) *reinterpret_cast<uint4*>(t + i) = *reinterpret_cast<const uint4*>(s + i);
     if (blockIdx.x == 0 && threadIdx.x < (bytes & 15)) t[(bytes & ~(size_t)15) + threadIdx.x] = s[(bytes & ~(size_t)15) + threadIdx.x];
   } else {
     for (size_t i = i0; i < bytes; i += step)
@@ -39,11 +48,14 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(const uint8_t* const
   }
 }
 int launch_gather_frames(cudaStream_t st, const uint8_t* const* src, uint8_t* dst, unsigned long long stride, const unsigned long long* off,
-                         size_t bytes, int batch, int max_chunks) {
+                         size_t bytes, int batch, int max_chunks, int threads) {
   ProfScope ps("gather_frames", st);
-  // max_chunks: CTAs per frame (few when the sources are host memory: the loads wait on PCIe, not on SMs)
-  const int chunks = (int)std::min<size_t>(max_chunks < 1 ? 1 : max_chunks, (bytes + 256 * 16 - 1) / (256 * 16));
-  gather_frames_kernel<<<dim3(chunks, batch), 256, 0, st>>>(src, dst, stride, off, bytes);
+  // max_chunks: CTAs per frame.  Host sources (pinned memory read over PCIe): a few small CTAs with four loads in flight per thread already
+  // saturate the link (50.7 GB/s from 8 down to 1 CTA per frame, profiles/r02f_pcie_probe.txt) and leave the SMs' thread slots to the
+  // kernels of the other batches while they wait.
+  threads = threads < 32 ? 32 : (threads > 256 ? 256 : (threads & ~31));
+  const int chunks = (int)std::min<size_t>(max_chunks < 1 ? 1 : max_chunks, (bytes + (size_t)threads * 16 - 1) / ((size_t)threads * 16));
+  gather_frames_kernel<<<dim3(chunks, batch), threads, 0, st>>>(src, dst, stride, off, bytes);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -189,14 +201,19 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_vec_kernel(uint8_t* __rest
 }
 
 // TMA variant of the single-channel pass (source level with cols % 16 == 0, sources at a uniform stride: the frame ring or the
-// pyramid buffer of a batch).  The (2*64+16) x (2*32+3) byte source box of a CTA arrives by ONE cp.async.bulk.tensor issued by one
+// pyramid buffer of a batch).  The (2*64+32) x (2*32+3) byte source box of a CTA arrives by ONE cp.async.bulk.tensor issued by one
 // thread (3-D tensor map {cols, rows, image}; coordinates outside the image are zero-filled by the TMA unit), completion on an
 // mbarrier: the ~540 thread instructions per CTA-thread that pyrdown_vec_kernel spends on addresses, border tests and word
 // assembly disappear (ncu, round 2 start: 82 % issue-active at 7 % of DRAM peak).  BORDER_REFLECT_101 only concerns the CTAs on the
 // image rim, which patch their halo rows / columns inside shared memory after the box has landed.  The arithmetic that follows is
 // pyrdown_vec_kernel's (byte-permute + dp4a on the same words), so the output is bit-identical.
-constexpr int PT_BOXW = 2 * PV_TX + 16;      // 144 bytes: source columns [2 ox - 4, 2 ox + 140) (inner box extent must be a multiple of 16 B)
-constexpr int PT_WORDS = PT_BOXW / 4;        // 36 words per staged row
+// Box geometry (probed on the B200, profiles/r02f_tma_probe.txt): the innermost start coordinate times the element size must be a
+// multiple of 16 bytes -- a box starting at column 2 ox - 4 raises "illegal instruction" -- while negative (aligned) coordinates and
+// boxes that stick out of the tensor are fine.  So the box starts at column 2 ox - 16 and is 160 bytes wide.
+constexpr int PT_LEAD = 16;                  // source column of tile byte 0 = 2 ox - PT_LEAD
+constexpr int PT_BOXW = 2 * PV_TX + 32;      // 160 bytes: source columns [2 ox - 16, 2 ox + 144)
+constexpr int PT_WORDS = PT_BOXW / 4;        // 40 words per staged row
+constexpr int PT_W0 = (PT_LEAD - 4) / 4;     // tile word that holds source columns 2 ox - 4 .. 2 ox - 1 (word 0 of pyrdown_vec_kernel's tile)
 constexpr int PT_BOX_BYTES = PT_BOXW * PV_ROWS;
 
 __device__ __forceinline__ unsigned smem_addr_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_tma_kernel(const __grid_co
   __shared__ __align__(8) unsigned long long mbar;
   const int ox = blockIdx.x * PV_TX, oy = blockIdx.y * PV_TY;
   const int tid = threadIdx.x;
-  const int sx0 = 2 * ox - 4, sy0 = 2 * oy - 2;
+  const int sx0 = 2 * ox - PT_LEAD, sy0 = 2 * oy - 2;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&mbar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -241,12 +258,11 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_tma_kernel(const __grid_co
   const bool rim_x = sx0 < 0 || sx0 + PT_BOXW > scols, rim_y = sy0 < 0 || sy0 + PV_ROWS > srows;
   if (rim_x) {
     uint8_t* tb = reinterpret_cast<uint8_t*>(&tile[0][0]);
-    for (int i = tid; i < PV_ROWS * 8; i += PV_THREADS) {  // at most 4 columns on the left and 4 that matter on the right
+    for (int i = tid; i < PV_ROWS * 8; i += PV_THREADS) {  // the 4 columns left of the image and the first 4 past its right edge
       const int ry = i >> 3, k = i & 7;
-      const int rx = k < 4 ? k : (scols - sx0) + (k - 4);  // k < 4: columns sx0 .. sx0 + 3 (left halo); else the first 4 columns past the right edge
+      const int sx = k < 4 ? k - 4 : scols + (k - 4);
+      const int rx = sx - sx0;
       if (rx < 0 || rx >= PT_BOXW) continue;
-      const int sx = sx0 + rx;
-      if (sx >= 0 && sx < scols) continue;
       const int rsx = reflect101(sx, scols) - sx0;
       if (rsx >= 0 && rsx < PT_BOXW) tb[ry * PT_BOXW + rx] = tb[ry * PT_BOXW + rsx];
     }
@@ -262,13 +278,13 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_tma_kernel(const __grid_co
     }
     __syncthreads();
   }
-  if (ingest) {  // level-0 copy of this CTA's 128 x 64 source block (bytes 4 .. 131 of rows 2 .. 65), 16 bytes per store
+  if (ingest) {  // level-0 copy of this CTA's 128 x 64 source block (bytes 16 .. 143 of rows 2 .. 65), 16 bytes per store
     uint8_t* __restrict__ l0 = pyr + soff + d.off[0];
     for (int i = tid; i < 2 * PV_TY * (2 * PV_TX / 16); i += PV_THREADS) {
       const int ry = i >> 3, q = i & 7;
       const int gy = 2 * oy + ry, gx = 2 * ox + 16 * q;
       if (gy >= srows || gx >= scols) continue;
-      const unsigned* t = &tile[ry + 2][1 + 4 * q];
+      const unsigned* t = &tile[ry + 2][PT_LEAD / 4 + 4 * q];
       *reinterpret_cast<uint4*>(l0 + (size_t)gy * scols + gx) = make_uint4(t[0], t[1], t[2], t[3]);  // cols % 16 == 0: whole chunks only
     }
   }
@@ -276,7 +292,7 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_tma_kernel(const __grid_co
   int h0[11], h1[11];
 #pragma unroll
   for (int r = 0; r < 11; ++r) {
-    const unsigned w0 = tile[8 * ty + r][tx], w1 = tile[8 * ty + r][tx + 1], w2 = tile[8 * ty + r][tx + 2];
+    const unsigned w0 = tile[8 * ty + r][PT_W0 + tx], w1 = tile[8 * ty + r][PT_W0 + tx + 1], w2 = tile[8 * ty + r][PT_W0 + tx + 2];
     const unsigned a = __byte_perm(w0, w1, 0x5432);
     h0[r] = __dp4a(a, 0x04060401u, __dp4a(w1, 0x00010000u, 0u));
     h1[r] = __dp4a(w1, 0x04060401u, __dp4a(w2, 0x00000001u, 0u));
@@ -294,9 +310,12 @@ __global__ void __launch_bounds__(PV_THREADS) pyrdown_tma_kernel(const __grid_co
   }
 }
 
-// Tensor map {cols, rows, n_img} over u8 images that lie `img_stride` bytes apart, box PT_BOXW x PV_ROWS x 1, zero fill.
+// Tensor map {cols, rows, n_img} over u8 images that lie `img_stride` bytes apart, box box_w x box_h x 1 (0 = the pyrDown box), zero fill.
 // cuTensorMapEncodeTiled is fetched from the driver at run time (the library does not link libcuda).
-int make_pyr_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img) {
+int make_pyr_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img, int box_w, int box_h) {
+  if (box_w <= 0) box_w = PT_BOXW;
+  if (box_h <= 0) box_h = PV_ROWS;
+  XB_REQUIRE((box_w & 15) == 0 && box_w <= 256 && box_h <= 256, "tensor map: box width must be a multiple of 16 bytes, extents <= 256");
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn encode = nullptr;
@@ -310,7 +329,7 @@ int make_pyr_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int col
   XB_REQUIRE((cols & 15) == 0 && (img_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, "pyramid tensor map: 16-byte alignment");
   const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)n_img};
   const cuuint64_t strides[2] = {(cuuint64_t)cols, (cuuint64_t)img_stride};  // bytes, dimensions 1 and 2
-  const cuuint32_t box[3] = {(cuuint32_t)PT_BOXW, (cuuint32_t)PV_ROWS, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -510,34 +529,10 @@ __device__ __forceinline__ unsigned pk_max(unsigned a, unsigned b) { return __vm
 __device__ __forceinline__ unsigned pk_min3(unsigned a, unsigned b, unsigned c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ unsigned pk_max3(unsigned a, unsigned b, unsigned c) { return __vimax3_s16x2(a, b, c); }
 
-template <int CN>
-__global__ void __launch_bounds__(FT_THREADS) fast_pair_kernel(const uint8_t* __restrict__ img, unsigned long long img_stride,
-                                                               const unsigned long long* __restrict__ seq_off, int rows, int cols,
-                                                               int thr, int nonmax, unsigned* __restrict__ kp_out, int max_kp,
-                                                               int* __restrict__ kp_count, const int* __restrict__ need) {
-  __shared__ __align__(8) unsigned short tile[FT_RH][FP_RW];
-  __shared__ short score[FT_SH][FP_SW];
-  const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * img_stride;
-  if (soff == ~0ull) return;  // inactive sequence
-  if (need && need[blockIdx.z] <= 0) return;
-  const uint8_t* __restrict__ src = img + soff;
-  const int ox = blockIdx.x * FT_TX, oy = blockIdx.y * FT_TY;
+// scores + NMS + keypoint append of one 64 x 16 tile whose grey values are staged as 16-bit pixels (shared by the thread-staged and the TMA kernel)
+__device__ __forceinline__ void fast_pair_tile(const unsigned short (*tile)[FP_RW], short (*score)[FP_SW], int ox, int oy, int rows, int cols, int thr,
+                                               int nonmax, unsigned* __restrict__ kp_out, int max_kp, int* __restrict__ kp_count) {
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int gx0 = ox - 6, gy0 = oy - 4;
-  for (int ry = ty; ry < FT_RH; ry += 8) {
-    const int gy = gy0 + ry;
-    for (int rx = tx; rx < FP_RW; rx += 32) {
-      const int gx = gx0 + rx;
-      int val = 0;
-      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-        const uint8_t* p = src + ((size_t)gy * cols + gx) * CN;
-        if (CN == 1) val = p[0];
-        else val = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15;
-      }
-      tile[ry][rx] = (unsigned short)val;
-    }
-  }
-  __syncthreads();
   // pair (sx, sx + 1), sx even: image x = ox - 2 + sx, tile column rx = sx + 4; score row sy: image y = oy - 1 + sy, tile row sy + 3
   for (int t = threadIdx.x; t < FT_SH * (FP_SW / 2); t += FT_THREADS) {
     const int sy = t / (FP_SW / 2), sx = 2 * (t - sy * (FP_SW / 2));
@@ -621,20 +616,110 @@ __global__ void __launch_bounds__(FT_THREADS) fast_pair_kernel(const uint8_t* __
   }
 }
 
+template <int CN>
+__global__ void __launch_bounds__(FT_THREADS) fast_pair_kernel(const uint8_t* __restrict__ img, unsigned long long img_stride,
+                                                               const unsigned long long* __restrict__ seq_off, int rows, int cols,
+                                                               int thr, int nonmax, unsigned* __restrict__ kp_out, int max_kp,
+                                                               int* __restrict__ kp_count, const int* __restrict__ need) {
+  __shared__ __align__(8) unsigned short tile[FT_RH][FP_RW];
+  __shared__ short score[FT_SH][FP_SW];
+  const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * img_stride;
+  if (soff == ~0ull) return;  // inactive sequence
+  if (need && need[blockIdx.z] <= 0) return;
+  const uint8_t* __restrict__ src = img + soff;
+  const int ox = blockIdx.x * FT_TX, oy = blockIdx.y * FT_TY;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int gx0 = ox - 6, gy0 = oy - 4;
+  for (int ry = ty; ry < FT_RH; ry += 8) {
+    const int gy = gy0 + ry;
+    for (int rx = tx; rx < FP_RW; rx += 32) {
+      const int gx = gx0 + rx;
+      int val = 0;
+      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+        const uint8_t* p = src + ((size_t)gy * cols + gx) * CN;
+        if (CN == 1) val = p[0];
+        else val = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15;
+      }
+      tile[ry][rx] = (unsigned short)val;
+    }
+  }
+  __syncthreads();
+  fast_pair_tile(tile, score, ox, oy, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+}
+
+// TMA variant (single channel, cols % 16 == 0, images at a uniform stride inside one buffer: the level-0 images of a batch's pyramids).
+// The 96 x 24 byte box [ox - 16, ox + 80) x [oy - 4, oy + 20) of a CTA arrives by one cp.async.bulk.tensor; what lies outside the image
+// is zero-filled by the TMA unit, which is exactly the value the thread-staged kernel stores there (FAST never scores a pixel closer
+// than 3 to the border, so the fill value is never compared).  The bytes are then widened to the 16-bit tile the packed scoring works
+// on; everything after that is fast_pair_tile, so the keypoints are identical.
+constexpr int FTM_BOXW = 96, FTM_LEAD = 16;  // tile byte 0 = image column ox - 16 (16-byte aligned start: profiles/r02f_tma_probe.txt)
+__global__ void __launch_bounds__(FT_THREADS) fast_pair_tma_kernel(const __grid_constant__ CUtensorMap img_map, unsigned long long img_stride,
+                                                                   const unsigned long long* __restrict__ seq_off, int rows, int cols, int thr,
+                                                                   int nonmax, unsigned* __restrict__ kp_out, int max_kp, int* __restrict__ kp_count,
+                                                                   const int* __restrict__ need) {
+  __shared__ __align__(128) uint8_t box[FT_RH][FTM_BOXW];
+  __shared__ __align__(8) unsigned short tile[FT_RH][FP_RW];
+  __shared__ short score[FT_SH][FP_SW];
+  __shared__ __align__(8) unsigned long long mbar;
+  const unsigned long long soff = seq_off ? seq_off[blockIdx.z] : (unsigned long long)blockIdx.z * img_stride;
+  if (soff == ~0ull) return;  // inactive sequence
+  if (need && need[blockIdx.z] <= 0) return;
+  const int ox = blockIdx.x * FT_TX, oy = blockIdx.y * FT_TY;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int z = (int)(soff / img_stride);  // image index of this sequence's level 0 inside the map
+    unsigned leader = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    if (leader) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&mbar)), "r"(FT_RH * FTM_BOXW) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(smem_addr_u32(&box[0][0])), "l"(reinterpret_cast<unsigned long long>(&img_map)), "r"(ox - FTM_LEAD), "r"(oy - 4), "r"(z),
+                     "r"(smem_addr_u32(&mbar))
+                   : "memory");
+    }
+  }
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_addr_u32(&mbar)) : "memory");
+    }
+  }
+  // widen: tile column rx (image x = ox - 6 + rx) = box byte rx + 10; two pixels per 32-bit store
+  for (int i = tid; i < FT_RH * (FP_RW / 2); i += FT_THREADS) {
+    const int ry = i / (FP_RW / 2), rp = i - ry * (FP_RW / 2);
+    const unsigned two = *reinterpret_cast<const unsigned short*>(&box[ry][2 * rp + FTM_LEAD - 6]);
+    *reinterpret_cast<unsigned*>(&tile[ry][2 * rp]) = __byte_perm(two, 0u, 0x4140);
+  }
+  __syncthreads();
+  fast_pair_tile(tile, score, ox, oy, rows, cols, thr, nonmax, kp_out, max_kp, kp_count);
+}
+
 // XIVO_FAST_SCALAR=1 routes detection through the one-pixel-per-thread kernel (parity tests compare the two)
 static bool force_scalar_fast() {
   const char* e = getenv("XIVO_FAST_SCALAR");
   return e && e[0] == '1';
 }
 
+int make_fast_tensor_map(CUtensorMap* out, const uint8_t* base, int rows, int cols, unsigned long long img_stride, unsigned long long n_img) {
+  return make_pyr_tensor_map(out, base, rows, cols, img_stride, n_img, FTM_BOXW, FT_RH);
+}
+
 int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off,
-                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch, const int* need) {
+                       int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch, const int* need,
+                       const CUtensorMap* tma_map, unsigned long long tma_img_stride, bool count_is_zero) {
   XB_REQUIRE(rows < 4096 && cols < 4096, "FAST: image dimension must be < 4096 (12-bit packed coordinates)");
   XB_REQUIRE(thr >= 0 && thr < 255, "FAST: threshold out of range");
-  XB_CUDA(cudaMemsetAsync(kp_count, 0, sizeof(int) * batch, st));
+  if (!count_is_zero) XB_CUDA(cudaMemsetAsync(kp_count, 0, sizeof(int) * batch, st));
   ProfScope ps("fast_detect", st);
   dim3 grid((cols + FT_TX - 1) / FT_TX, (rows + FT_TY - 1) / FT_TY, batch);
-  if (force_scalar_fast()) {
+  if (tma_map && cn == 1 && tma_img_stride && !force_scalar_fast()) {
+    fast_pair_tma_kernel<<<grid, FT_THREADS, 0, st>>>(*tma_map, tma_img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count, need);
+  } else if (force_scalar_fast()) {
     if (cn == 1) fast_kernel<1><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count, need);
     else fast_kernel<3><<<grid, FT_THREADS, 0, st>>>(img, img_stride, seq_off, rows, cols, thr, nonmax, kp_out, max_kp, kp_count, need);
   } else {
@@ -1231,10 +1316,12 @@ int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* nex
 #undef XB_LK_CASE
     }
   } else if (d.cn == 1) {
-    XB_CUDA(cudaFuncSetAttribute(lk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr1 = 0;
+    if (smem > attr1) { XB_CUDA(cudaFuncSetAttribute(lk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = smem; }
     lk_kernel<1><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
   } else {
-    XB_CUDA(cudaFuncSetAttribute(lk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr3 = 0;
+    if (smem > attr3) { XB_CUDA(cudaFuncSetAttribute(lk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr3 = smem; }
     lk_kernel<3><<<grid, LK_WARPS * 32, smem, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
   }
   XB_CUDA(cudaGetLastError());
@@ -1290,9 +1377,11 @@ __device__ __forceinline__ bool mask_free(const unsigned* m, int stride, const T
 // Outputs: stat[b][i] = feature i keeps its track; need[b] = features the detection should add (0 = none).
 __global__ void __launch_bounds__(128) track_accept_kernel(TrackDecideCfg c, const int* __restrict__ kind, const int* __restrict__ npts,
                                                            const float* __restrict__ pts0, const float* __restrict__ pts1,
-                                                           const uint8_t* __restrict__ lkst, uint8_t* __restrict__ stat, int* __restrict__ need) {
+                                                           const uint8_t* __restrict__ lkst, uint8_t* __restrict__ stat, int* __restrict__ need,
+                                                           int* __restrict__ kp_count) {
   extern __shared__ unsigned tmask[];
   const int b = blockIdx.x, tid = threadIdx.x;
+  if (kp_count && tid == 0) kp_count[b] = 0;  // the keypoint cursor of the detection that follows in the stream (saves its memset call)
   const int k = kind[b];
   if (k == 1) { if (tid == 0) need[b] = c.num_max; return; }
   if (k != 2) { if (tid == 0) need[b] = 0; return; }
@@ -1460,13 +1549,13 @@ __global__ void __launch_bounds__(SEL_THREADS) track_select_kernel(TrackDecideCf
 size_t track_mask_bytes(int rows, int cols) { return (size_t)rows * ((cols + 31) / 32) * sizeof(unsigned); }
 
 int launch_track_accept(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts0, const float* pts1,
-                        const uint8_t* lkst, uint8_t* stat, int* need, int batch) {
+                        const uint8_t* lkst, uint8_t* stat, int* need, int batch, int* kp_count_to_zero) {
   const size_t smem = track_mask_bytes(c.rows, c.cols);
   XB_REQUIRE(smem <= 200 * 1024, "track_accept: image too large for the shared-memory mask");
   static size_t attr = 0;
   if (smem > attr) { XB_CUDA(cudaFuncSetAttribute(track_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   ProfScope ps("track_accept", st);
-  track_accept_kernel<<<batch, 128, smem, st>>>(c, kind, npts, pts0, pts1, lkst, stat, need);
+  track_accept_kernel<<<batch, 128, smem, st>>>(c, kind, npts, pts0, pts1, lkst, stat, need, kp_count_to_zero);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
