@@ -35,6 +35,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ROWS, COLS, G, F = 480, 640, 4, 14
+CFG_FILE = "vio_640x480.json"
+WORKLOAD = "BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)"
+METRIC = "VIO frames/sec (640x480 synthetic + 200 Hz IMU)"
+# --config: the other full-pipeline workloads BASELINE.json names (parity cases of tests/test_gpu_estimator.py); the driver's runs use 1
+CONFIGS = {
+    1: dict(cfg="vio_640x480.json", G=4, F=14, seqs=512, streams=16, workload=WORKLOAD, metric=METRIC),
+    2: dict(cfg="tumvi_512_equidistant.json", G=15, F=30, seqs=256, streams=8,
+            workload="BASELINE configs[2]: TUM-VI equidistant 512x512 + 200 Hz IMU, 200 tracked features, state dim 203 (G=15,F=30)",
+            metric="VIO frames/sec (512x512 equidistant synthetic + 200 Hz IMU)"),
+    3: dict(cfg="stress_1280x1024.json", G=15, F=62, seqs=128, streams=4,
+            workload="BASELINE configs[3]: stress 1280x1024 + 200 Hz IMU, 800 tracked features, state dim 299 (G=15,F=62)",
+            metric="VIO frames/sec (1280x1024 synthetic + 200 Hz IMU)"),
+}
+
+
+def select_config(n):
+    """Sets the module-level workload constants from CONFIGS[n] (frame size from the config's camera block)."""
+    global ROWS, COLS, G, F, CFG_FILE, WORKLOAD, METRIC
+    c = CONFIGS[n]
+    CFG_FILE, G, F, WORKLOAD, METRIC = c["cfg"], c["G"], c["F"], c["workload"], c["metric"]
+    cam = load_cfg()["camera_cfg"]
+    ROWS, COLS = int(cam["rows"]), int(cam["cols"])
+    return c
 IMU_PER_FRAME = 8
 FRAME_NS = 40_000_000
 PREROLL_FRAMES = 12  # reference arm: gravity init (stationary) + first detections, never timed
@@ -45,7 +68,7 @@ INGEST_MODES = {"zero_copy": 0, "copy_engine": 1}
 def load_cfg():
     from xivo_b200 import sim
 
-    return sim.load_cfg(os.path.join(ROOT, "xivo_b200", "cfg", "vio_640x480.json"))
+    return sim.load_cfg(os.path.join(ROOT, "xivo_b200", "cfg", CFG_FILE))
 
 
 ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
@@ -54,7 +77,7 @@ ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
 def cpu_reference(cores, frames, skip, channels=1):
     """Runs oracle/cpu_baseline.py in a fresh interpreter (no CUDA context there: it forks one worker
     per core) and returns its JSON."""
-    cfg_path = os.path.join(ROOT, "xivo_b200", "cfg", "vio_640x480.json")
+    cfg_path = os.path.join(ROOT, "xivo_b200", "cfg", CFG_FILE)
     if hasattr(os, "sched_setaffinity"):
         os.sched_setaffinity(0, ALL_CPUS)  # the library pins its driver threads; the CPU arm gets every allowed CPU
     r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", cfg_path, str(cores), str(frames), str(skip), str(G), str(F), str(channels)], cwd=ROOT,
@@ -106,14 +129,14 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
-def pick_ingest(ms):
-    """ms: {mode: [ms per step of each calibration round]} -> the mode with the best round; the current default
-    (zero_copy) keeps the job unless the alternative is at least 3 % faster (below that it is noise)."""
+def pick_ingest(ms, default="copy_engine"):
+    """ms: {mode: [ms per step of each calibration round]} -> the mode with the best round; the library's default
+    (copy_engine) keeps the job unless the alternative is at least 3 % faster (below that it is noise)."""
     best = {k: min(v) for k, v in ms.items() if v}
-    if "zero_copy" not in best:
+    if default not in best:
         return min(best, key=best.get)
     alt = min(best, key=best.get)
-    return alt if best[alt] < 0.97 * best["zero_copy"] else "zero_copy"
+    return alt if best[alt] < 0.97 * best[default] else default
 
 
 def calibration_frames(choice):
@@ -491,10 +514,10 @@ def run_ours(args):
             r = cpu_reference(cores, 60, 14, CH)
             cpu = cpu_baseline_entry(r, cores, 60, time.time() - t0)
         pool_mb = S0 * NFB * fbytes / 1e6
-        out = dict(metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=value, unit="frames/s", n_gpus=world, steps=K, warmup=W,
+        out = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=K, warmup=W,
                    ms_per_step=r_dev["ms"] / K, higher_is_better=True, scaling="weak", vs_baseline=None,
                    dtype="f64" if args.cov_update == "fp64" else "f64 state, 3xTF32 tensor-core covariance downdate", data="synthetic",
-                   config=dict(covariance_update=args.cov_update, workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
+                   config=dict(covariance_update=args.cov_update, workload=WORKLOAD,
                                sequences_per_gpu=B, batches_per_gpu=NB, lanes_per_batch=bts[0].lanes, cpu_tokens=os.environ.get("XIVO_CPU_TOKENS"), frames_per_sequence_per_step=FPS, frames_per_step=world * B * FPS,
                                host_threads=int(os.environ.get("XIVO_THREADS", "0")) or None, host_cpu_budget=budget, channels=CH,
                                distinct_streams=f"{S0} base streams (own texture / trajectory amplitude / noise, period {PERIOD_S:g} s replayed) x start delays of {STAGGER} frames: "
@@ -533,9 +556,9 @@ def run_reference(args):
     r = cpu_reference(cores, frames, PREROLL_FRAMES + min(W * FPS, 24), args.channels)
     cb = cpu_baseline_entry(r, cores, frames, time.time() - t0)
     ms_per_step = 1e3 * cores * FPS / cb["value"]  # one step = FPS frames on each of `cores` concurrent sequences
-    out = dict(impl="reference", metric="VIO frames/sec (640x480 synthetic + 200 Hz IMU)", value=cb["value"], unit="frames/s", n_gpus=args.gpus,
+    out = dict(impl="reference", metric=METRIC, value=cb["value"], unit="frames/s", n_gpus=args.gpus,
                steps=K, warmup=W, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-               config=dict(workload="BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 tracked features, state dim 89 (G=4,F=14)",
+               config=dict(workload=WORKLOAD,
                            sequences=cores, frames_per_sequence_per_step=FPS, timed_frames_per_sequence=frames, channels=args.channels),
                cpu_baseline=cb,
                e2e=dict(value=cb["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -551,9 +574,10 @@ def main():
     ap.add_argument("--profile-e2e", action="store_true", help="attribute kernel / host-phase time on the host-frame (e2e) path instead of the device-resident one")
     ap.add_argument("--profile-level", type=int, default=1, help="1: kernels + batch-level host phases, 2: + per-sequence host scopes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seqs", type=int, default=512, help="independent sequences per GPU, split over --batches lock-step batches")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs[n]: 1 = the headline workload (640x480, 150 features, N=89); 2 = TUM-VI equidistant 512x512, 200 features, N=203; 3 = stress 1280x1024, 800 features, N=299")
+    ap.add_argument("--seqs", type=int, default=0, help="independent sequences per GPU, split over --batches lock-step batches (0 = the config's default: 512 / 256 / 128)")
     ap.add_argument("--batches", type=int, default=8, help="separate lock-step xivo_batch handles per GPU, each stepped from its own thread; their per-sequence host code shares the library's worker pool (capped at half the CPU budget)")
-    ap.add_argument("--streams", type=int, default=16, help="rendered base streams (texture / trajectory / noise); every sequence replays one of them with its own start delay")
+    ap.add_argument("--streams", type=int, default=0, help="rendered base streams (texture / trajectory / noise); every sequence replays one of them with its own start delay")
     ap.add_argument("--frames-per-step", type=int, default=8, help="a step = this many consecutive frames (+ IMU) of every sequence: K driver-chosen steps then time seconds, not milliseconds")
     ap.add_argument("--channels", type=int, default=1, choices=[1, 3], help="1 = grey frames (default), 3 = BGR like the reference's cv::imread input (src/app/vio.cpp:72)")
     ap.add_argument("--profile-steps", type=int, default=4, help="steps of the (serial, slow) kernel-attribution pass")
@@ -567,6 +591,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    c = select_config(args.config)
+    args.seqs = args.seqs or c["seqs"]
+    args.streams = args.streams or c["streams"]
+    if args.impl == "reference" and args.config == 3:
+        # the reference's estimator is a compile-time-sized build (EKF_MAX_GROUPS / EKF_MAX_FEATURES); oracle/build_ref.py builds G4_F14 and G15_F30
+        print(json.dumps(dict(impl="reference", unavailable="reference estimator not built for G=15,F=62 (configs[3]); configs 1 and 2 are")))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -96,9 +96,9 @@ def test_cpu_baseline_runs_the_reference_library_when_it_is_built():
 
 
 def test_pick_ingest_keeps_the_default_unless_clearly_faster():
-    assert bench.pick_ingest({"zero_copy": [8.4, 8.3], "copy_engine": [8.2, 8.25]}) == "zero_copy"   # 1 % is noise
-    assert bench.pick_ingest({"zero_copy": [8.4, 8.3], "copy_engine": [6.1, 6.4]}) == "copy_engine"
-    assert bench.pick_ingest({"zero_copy": [6.0, 6.2], "copy_engine": [9.0, 8.8]}) == "zero_copy"
+    assert bench.pick_ingest({"copy_engine": [8.4, 8.3], "zero_copy": [8.2, 8.25]}) == "copy_engine"   # 1 % is noise
+    assert bench.pick_ingest({"copy_engine": [8.4, 8.3], "zero_copy": [6.1, 6.4]}) == "zero_copy"
+    assert bench.pick_ingest({"copy_engine": [6.0, 6.2], "zero_copy": [9.0, 8.8]}) == "copy_engine"
     assert set(bench.INGEST_MODES.values()) == {0, 1}
 
 
@@ -124,3 +124,17 @@ def test_ingest_calibration_protocol():
     log.clear()
     assert bench.calibrate_ingest("zero_copy", set_mode, run_step, lambda: None, 7) == ("zero_copy", None, 7) and log == [0]
     assert bench.calibration_frames("zero_copy") == 0
+
+
+def test_config_selection_sets_the_workload_constants():
+    """--config 1/2/3 = BASELINE.json configs[1..3]: frame size from the config's camera block, state dimensions as the parity tests use them."""
+    import bench
+
+    try:
+        for n, (rows, cols, g, f, nstate) in {1: (480, 640, 4, 14, 89), 2: (512, 512, 15, 30, 203), 3: (1024, 1280, 15, 62, 299)}.items():
+            c = bench.select_config(n)
+            assert (bench.ROWS, bench.COLS, bench.G, bench.F) == (rows, cols, g, f)
+            assert 23 + 6 * bench.G + 3 * bench.F == nstate and f"configs[{n}]" in bench.WORKLOAD and c["seqs"] >= 128
+            assert bench.load_cfg()["camera_cfg"]["rows"] == rows
+    finally:
+        bench.select_config(1)

@@ -44,7 +44,8 @@ extern std::atomic<unsigned long long> g_launches;
 // How pinned host frames reach the frame ring: 0 = one gather launch whose SMs read the host memory over PCIe,
 // 1 = one cudaMemcpyAsync per frame on the copy engine.  Results are identical; which is faster depends on the
 // host's PCIe path, so it is a run-time setting (xivo_set_frame_ingest; initial value from XIVO_ZEROCOPY).
-static std::atomic<int> g_frame_ingest{(getenv("XIVO_ZEROCOPY") && getenv("XIVO_ZEROCOPY")[0] == '0') ? 1 : 0};
+// Default: the copy engine (with the tables of every phase fetched by kernels, DMA frames delay them least: profiles/r02i_burst_probe.txt).
+static std::atomic<int> g_frame_ingest{(getenv("XIVO_ZEROCOPY") && getenv("XIVO_ZEROCOPY")[0] == '1') ? 0 : 1};
 
 // Pinned host mirror + device array.
 template <typename T>
@@ -57,6 +58,17 @@ struct Mirror {
   // frame uploads in the H2D copy engine's FIFO.  The host must not rewrite it before the consuming kernel has finished (every table
   // is rewritten only after the wait that ends its phase).
   bool zero_copy = false;
+  T* hd = nullptr;  // device alias of the pinned host copy (alloc_fetchable): what fetch_kernel reads
+  // pinned + mapped host copy and a device copy: the upload is a kernel that reads the host copy over PCIe (Batch::up_blob)
+  bool alloc_fetchable(size_t count) {
+    n = count;
+    if (!count) return true;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), count * sizeof(T), cudaHostAllocMapped) != cudaSuccess) return false;
+    memset(h, 0, count * sizeof(T));
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&hd), h, 0) != cudaSuccess) return false;
+    if (cudaMalloc(reinterpret_cast<void**>(&d), count * sizeof(T)) != cudaSuccess) return false;
+    return cudaMemset(d, 0, count * sizeof(T)) == cudaSuccess;
+  }
   bool alloc(size_t count, bool zc = false) {
     n = count;
     zero_copy = zc;
@@ -110,6 +122,13 @@ static StreamWriteValue32Fn stream_write_value32() {
     return reinterpret_cast<StreamWriteValue32Fn>(p);
   }();
   return fn;
+}
+// Upload of a host-written table blob by the SMs: 16-byte loads from the mapped pinned copy, stores to the device copy.  Why not the
+// copy engine: the frames of a step travel by DMA, and a small cudaMemcpyAsync issued behind that burst waits for it in the engine's
+// FIFO -- measured on the B200 box (profiles/r02i_burst_probe.txt): 750 us for a 165 KB table round trip behind the 157 MB frame burst
+// of one step against 112 us when a kernel reads the table in place (31 / 27 us on an idle link).
+__global__ void __launch_bounds__(256) fetch_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned n16) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 __global__ void ticket_kernel(unsigned* flag, unsigned value) {
   *flag = value;
@@ -305,7 +324,7 @@ class Batch {
         const size_t oX = c.take(nB * kPoseDoubles * 8);
         blobS_fixed = c.off;
         const size_t oS = c.take(nB * max_sub * sizeof(SubfilterIn));
-        ok = ok && blobS.alloc(c.off);
+        ok = ok && blobS.alloc_fetchable((c.off + 15) & ~(size_t)15);
         if (ok) { X.adopt(blobS.h + oX, blobS.d + oX, nB * kPoseDoubles); sub_in.adopt(blobS.h + oS, blobS.d + oS, nB * max_sub); }
       }
       {  // Jacobian / gate phase: [nfeat | nops | first | fref | fsind | fxp | fx | groups | ops ...]
@@ -314,7 +333,7 @@ class Batch {
                      o6 = c.take(nF * 3 * 8), o7 = c.take(nB * lay.G * kGroupDoubles * 8);
         blobJ_fixed = c.off;
         const size_t o8 = c.take(nB * maxops * sizeof(EditOp));
-        ok = ok && blobJ.alloc(c.off);
+        ok = ok && blobJ.alloc_fetchable((c.off + 15) & ~(size_t)15);
         if (ok) {
           auto H = [&](size_t o) { return (void*)(blobJ.h + o); };
           auto D = [&](size_t o) { return (void*)(blobJ.d + o); };
@@ -328,7 +347,7 @@ class Batch {
         const size_t o0 = c.take(nB * 4), o1 = c.take(nB * 4), o2 = c.take(nB * 4), o3 = c.take(nF * 4);
         blobU_fixed = c.off;
         const size_t o4 = c.take(nB * maxops * sizeof(EditOp));
-        ok = ok && blobU.alloc(c.off);
+        ok = ok && blobU.alloc_fetchable((c.off + 15) & ~(size_t)15);
         if (ok) {
           auto H = [&](size_t o) { return (void*)(blobU.h + o); };
           auto D = [&](size_t o) { return (void*)(blobU.d + o); };
@@ -341,7 +360,7 @@ class Batch {
         const size_t o0 = c.take(nB * 4), o1 = c.take(nB * 4);
         blobI_fixed = c.off;
         const size_t o2 = c.take(nB * kMaxStages * sizeof(ImuStage));
-        ok = ok && blobI[h].alloc(c.off);
+        ok = ok && blobI[h].alloc_fetchable((c.off + 15) & ~(size_t)15);
         if (ok) {
           stg_first[h].adopt(blobI[h].h + o0, blobI[h].d + o0, nB); stg_n[h].adopt(blobI[h].h + o1, blobI[h].d + o1, nB);
           stg[h].adopt(blobI[h].h + o2, blobI[h].d + o2, nB * kMaxStages);
@@ -399,7 +418,12 @@ class Batch {
   // ---- staging helpers -------------------------------------------------------------------
   cudaError_t up_blob(Mirror<unsigned char>& b, size_t bytes, cudaStream_t st) {
     Prof::get().h2d += bytes;
-    return cudaMemcpyAsync(b.d, b.h, bytes, cudaMemcpyHostToDevice, st);
+    if (!b.hd || !bytes) return bytes ? cudaMemcpyAsync(b.d, b.h, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+    const unsigned n16 = (unsigned)((bytes + 15) / 16);  // blobs are allocated in 16-byte units
+    const unsigned ctas = std::max(1u, std::min(32u, (n16 + 1023) / 1024));
+    fetch_kernel<<<ctas, 256, 0, st>>>(reinterpret_cast<const uint4*>(b.hd), reinterpret_cast<uint4*>(b.d), n16);
+    g_launches += 1;
+    return cudaGetLastError();
   }
   // pack the pending covariance edits of the given sequences into ops (filter b: [first[b], first[b] + nops[b])); *total = entries used
   int stage_edits(const std::vector<int>& act, Mirror<EditOp>& ops, Mirror<int>& first, Mirror<int>& nops, int* total) {
@@ -500,6 +524,7 @@ class Batch {
     static const bool help = !(getenv("XIVO_HELP") && getenv("XIVO_HELP")[0] == '0');
     StreamTicket& t = st == st2 ? tk2 : tk1;
     const unsigned want = ++t.next;
+    std::unique_ptr<HostScope> hx_t(new HostScope("x_i_ticket"));
     if (StreamWriteValue32Fn wv = stream_write_value32()) {
       if (wv(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(t.d), want, 0) != CUDA_SUCCESS) {
         set_error("cuStreamWriteValue32 failed");
@@ -509,6 +534,7 @@ class Batch {
       ticket_kernel<<<1, 1, 0, st>>>(t.d, want);
       XB_CUDA(cudaGetLastError());
     }
+    hx_t.reset();
     unsigned polls = 0;
     while (!t.reached(want)) {
       if (help && WorkPool::get().help_one()) continue;
@@ -572,7 +598,9 @@ class Batch {
     if (!on_device) Prof::get().h2d += (unsigned long long)ib * B;
     if (gather) {
       XB_CUDA(up_blob(blobG, blobG.n, st_copy));  // [sources | ring offsets]
-      if (int rc = launch_gather_frames(st_copy, ingest_ptr.d, dRing, 0, ingest_off.d, ib, B, on_device ? 64 : 2, on_device ? 256 : 128)) return rc;
+      // host sources: one warp per frame with four loads in flight still fills the link when several batches pull at once, and hogs it
+      // less for the other batches' table fetches than wider grids do (profiles/r02i_burst_probe.txt)
+      if (int rc = launch_gather_frames(st_copy, ingest_ptr.d, dRing, 0, ingest_off.d, ib, B, on_device ? 64 : 1, on_device ? 256 : 32)) return rc;
       g_launches += 1;
     } else {
       // copy engine: runs of sequences whose sources are evenly spaced (frames of one pinned pool) and whose ring slots agree go down as
@@ -629,7 +657,7 @@ class Batch {
     const size_t ib = (size_t)rows * cols * cn;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dRing), (size_t)B * ring_n * ib) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dPyr), (size_t)B * 2 * pd.total) == cudaSuccess;
-    ok = ok && blobG.alloc((size_t)B * 16) && lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && kpcount.alloc(B) &&
+    ok = ok && blobG.alloc_fetchable((size_t)B * 16) && lkerr.alloc((size_t)B * max_pts) && lkst.alloc((size_t)B * max_pts) && kpcount.alloc(B) &&
          kp.alloc((size_t)B * max_kp);
     // the accept / select decisions run on the device unless the homography stage (host code between the two) is on, the mask does
     // not fit into shared memory, or XIVO_HOST_TRACKER_DECISIONS=1 asks for the host path (parity tests compare the two)
@@ -649,7 +677,7 @@ class Batch {
                      {npt, 0}, {nB * 4, 0}, {nB * 4, 0}, {nnew * 4, 0}};                                                                 // tstat tneed tnnew tnewkp
       size_t off = 0;
       for (Sec& q : sec) { q.off = off; off += (q.bytes + 15) & ~(size_t)15; }
-      ok = tt.alloc(off);
+      ok = tt.alloc_fetchable((off + 15) & ~(size_t)15);
       if (ok) {
         auto H = [&](int i) { return (void*)(tt.h + sec[i].off); };
         auto D = [&](int i) { return (void*)(tt.d + sec[i].off); };
@@ -742,6 +770,7 @@ class Batch {
     TrackDecideCfg dc{rows, cols, tc.margin, tc.mask_size >> 1, tc.num_features_min, tc.num_features_max, max_pts, max_kp, max_new,
                       (double)tc.max_pixel_displacement};
     if (!lk_list.empty()) {
+      HostScope hx("x_i_trk_lk");
       if (int rc = launch_lk_track(st, dPyr, dPyr, 0, off_prev.d, off_cur.d, pd, pts0.d, pts1.d, lkst.d, lkerr.d, npts.d, max_pts, B,
                                    tc.win_size, tc.max_iter, tc.eps, 1, 1e-4))
         return rc;
@@ -750,15 +779,21 @@ class Batch {
       for (int b : lk_list) np_ += npts.h[b];
       Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
     }
-    if (int rc = launch_track_accept(st, dc, tkind.d, npts.d, pts0.d, pts1.d, lkst.d, tstat.d, tneed.d, B, kpcount.d)) return rc;
+    {
+      HostScope hx("x_i_trk_accept");
+      if (int rc = launch_track_accept(st, dc, tkind.d, npts.d, pts0.d, pts1.d, lkst.d, tstat.d, tneed.d, B, kpcount.d)) return rc;
+    }
+    std::unique_ptr<HostScope> hx_fs(new HostScope("x_i_trk_fast_select"));
     // FAST on the current level-0 image of every tracked sequence (fast_off); the kernel skips those whose need is 0
     if (int rc = launch_fast_detect(st, dPyr, 0, fast_off.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, tneed.d,
                                     tma_fast ? &tm_fast : nullptr, pd.total, true))
       return rc;
     if (int rc = launch_track_select(st, dc, tkind.d, npts.d, pts1.d, tstat.d, tneed.d, kp.d, kpcount.d, tnewkp.d, tnnew.d, B)) return rc;
     g_launches += 3;
+    hx_fs.reset(new HostScope("x_i_trk_d2h"));
     Prof::get().d2h += tt_down_bytes;  // [pts1 | keep flags | need | picks] in one copy
     XB_CUDA(cudaMemcpyAsync(tt.h + tt_down_off, tt.d + tt_down_off, tt_down_bytes, cudaMemcpyDeviceToHost, st));
+    hx_fs.reset();
     hs_issue->reset();
     { HostScope hw("wait_lk"); if (int rc = wait(st)) return rc; }
     {
@@ -878,12 +913,13 @@ class Batch {
         tkind.h[b] = kind[b];
         if (kind[b] == 1 || kind[b] == 2) fast_off.h[b] = ((size_t)b * 2 + (1 - prev_slot[b])) * pd.total;
       }
-      Prof::get().h2d += tt_up_bytes;
-      XB_CUDA(cudaMemcpyAsync(tt.d, tt.h, tt_up_bytes, cudaMemcpyHostToDevice, st));
+      HostScope hx("x_i_trk_h2d");
+      XB_CUDA(up_blob(tt, tt_up_bytes, st));
     } else {
       XB_CUDA(off_cur.up(st)); XB_CUDA(off_prev.up(st)); XB_CUDA(npts.up(st)); XB_CUDA(frame_ptr.up(st));
       if (tma_pyr) { XB_CUDA(ring_img.up(st)); XB_CUDA(pyr_img.up(st)); }
     }
+    std::unique_ptr<HostScope> hx_pyr(new HostScope("x_i_trk_pyr"));
     if (tma_pyr) {
       ProfScope ps("pyrdown", st);
       if (int rc = launch_pyrdown_tma(st, tm_ring, ring_img.d, dPyr, 0, off_cur.d, pd, 0, 1, B)) return rc;
@@ -893,6 +929,7 @@ class Batch {
       }
     } else if (int rc = launch_build_pyramid(st, dPyr, 0, off_cur.d, pd, B, frame_ptr.d)) return rc;
     g_launches += std::max(1, pd.n_levels - 1);
+    hx_pyr.reset();
     {
       int nact = 0;
       for (int b = 0; b < B; ++b) nact += off_cur.h[b] != ~0ull;
@@ -1503,9 +1540,10 @@ int xivo_set_frame_ingest(int mode) {
   return g_frame_ingest.exchange(mode);
 }
 
-void xivo_profile_enable(int on) {
+void xivo_profile_enable(int on) {  // 0 off, 1 kernels + batch-level host phases, 2 + per-sequence host scopes, 3 host scopes only (no kernel events)
   Prof::get().enabled = on != 0;
   Prof::get().fine = on >= 2;
+  Prof::get().kernels = on != 3;
 }
 void xivo_profile_reset(void) { Prof::get().reset(); }
 int xivo_profile_report(char* buf, int n) {

@@ -59,9 +59,10 @@ class Prof {
   }
   std::atomic<bool> enabled{false};
   std::atomic<bool> fine{false};  // per-sequence host scopes ("x_*"): contended, only for host-side diagnosis
+  std::atomic<bool> kernels{true};  // false: host scopes only (no event pair per launch: eight runtime calls each, which distorts the host picture)
   std::atomic<unsigned long long> h2d{0}, d2h{0};
   ProfRec* start(const char* name, cudaStream_t st) {
-    if (!enabled.load(std::memory_order_relaxed)) return nullptr;
+    if (!enabled.load(std::memory_order_relaxed) || !kernels.load(std::memory_order_relaxed)) return nullptr;
     std::unique_ptr<ProfRec> r(new ProfRec());
     r->name = name;
     cudaEventCreate(&r->a);
