@@ -8,4 +8,4 @@ cfg = sim.load_cfg("xivo_b200/cfg/pcw_sim.json")
 cfg["tracker_cfg"].update(num_features_min=120, num_features_max=150)
 open("/tmp/host_perf_cfg.json", "w").write(json.dumps(cfg))
 P
-/tmp/host_perf /tmp/host_perf_cfg.json ${1:-4} ${2:-14} ${3:-600}
+/tmp/host_perf /tmp/host_perf_cfg.json ${1:-4} ${2:-14} ${3:-600} ${4:-1}

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 
@@ -29,27 +30,43 @@ struct HostScope {
 #include "../../xivo_b200/csrc/estimator_host.cpp.inc"
 
 using namespace xb;
+struct Seq {
+  std::unique_ptr<Estimator> e;
+  std::vector<double> pack, x0, y0;
+  std::vector<char> tracked;
+  uint64_t ts = 0;
+  int frames = 0;
+};
+
 int main(int argc, char** argv) {
   std::ifstream f(argv[1]);
   std::stringstream ss;
   ss << f.rdbuf();
   const int G = argc > 2 ? atoi(argv[2]) : 4, F = argc > 3 ? atoi(argv[3]) : 14, NF = argc > 4 ? atoi(argv[4]) : 400;
-  Estimator e(Json::parse(ss.str()), EkfLayout{G, F}, false);
-  e.sim_initialize_depths = true;
-  const int N = e.lay.N();
-  std::vector<double> pack(2 * N + 529, 0.0);
-  for (int i = 0; i < N; ++i) pack[N + 529 + i] = 1e-3 * (1 + i % 7);
-  for (int i = 0; i < 23; ++i) pack[N + i * 23 + i] = 1e-4;
+  const int NE = argc > 5 ? atoi(argv[5]) : 1;  // estimators stepped round-robin: > ~64 makes every phase start cache-cold, like a bench batch
+  const Json cfg = Json::parse(ss.str());
   const int NP = 300, W = 640, H = 480;
-  std::vector<double> x0(NP), y0(NP);
-  unsigned rng = 12345;
-  auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return (rng >> 8) / double(1 << 24); };
-  for (int i = 0; i < NP; ++i) { x0[i] = rnd() * (W + 300); y0[i] = 20 + rnd() * (H - 40); }
-  uint64_t ts = 0;
+  std::vector<Seq> seqs(NE);
+  for (int q = 0; q < NE; ++q) {
+    Seq& s = seqs[q];
+    s.e.reset(new Estimator(cfg, EkfLayout{G, F}, false));
+    s.e->sim_initialize_depths = true;
+    const int N = s.e->lay.N();
+    s.pack.assign(2 * N + 529, 0.0);
+    for (int i = 0; i < N; ++i) s.pack[N + 529 + i] = 1e-3 * (1 + i % 7);
+    for (int i = 0; i < 23; ++i) s.pack[N + i * 23 + i] = 1e-4;
+    s.x0.resize(NP); s.y0.resize(NP);
+    unsigned rng = 12345 + 77 * q;
+    auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return (rng >> 8) / double(1 << 24); };
+    for (int i = 0; i < NP; ++i) { s.x0[i] = rnd() * (W + 300); s.y0[i] = 20 + rnd() * (H - 40); }
+    s.tracked.assign(NP * 64, 0);
+  }
   double gyro[3] = {0, 0, 0}, accel[3] = {0, 0, 9.8};
   auto t_begin = std::chrono::steady_clock::now();
-  int frames = 0;
-  auto run_msg = [&](Msg& m) {
+  long frames = 0;
+  auto run_msg = [&](Seq& s, Msg& m) {
+    Estimator& e = *s.e;
+    const int N = e.lay.N();
     if (m.type == 0) {
       HostScope hs("1 inertial (8 per frame)");
       e.inertial_internal(m.ts, m.gyro, m.accel);
@@ -74,45 +91,50 @@ int main(int argc, char** argv) {
     std::vector<double> mh(e.lay.F, 1.0);
     { HostScope hs("7 after_gate"); e.update_step_after_gate(mh.data()); }
     e.edits.clear();
-    { HostScope hs("8 after_update (absorb, manage)"); e.update_step_after_update(pack.data(), pack.data() + N, pack.data() + N + 529, !e.in_update.empty()); }
+    { HostScope hs("8 after_update (absorb, manage)"); e.update_step_after_update(s.pack.data(), s.pack.data() + N, s.pack.data() + N + 529, !e.in_update.empty()); }
     e.edits.clear();
     ++frames;
-    if (frames % 100 == 0) printf("  frame %d: tracks %zu instate %zu groups %zu\n", frames, e.tracks.size(), e.instate_features.size(), e.graph.groups.size());
+    ++s.frames;
+    if (&s == &seqs[0] && s.frames % 100 == 0) printf("  frame %d: tracks %zu instate %zu groups %zu\n", s.frames, e.tracks.size(), e.instate_features.size(), e.graph.groups.size());
     if (e.error) { printf("error %d %s\n", e.error, e.error_msg.c_str()); exit(1); }
   };
   for (int fr = 0; fr < NF; ++fr) {
-    for (int k = 0; k < 8; ++k) {
-      Msg m; m.ts = ts; m.type = 0; memcpy(m.gyro, gyro, 24); memcpy(m.accel, accel, 24);
-      ts += 5000000;
-      e.push(std::move(m));
+    // like a lock-step batch: every sequence runs its IMU samples, then every sequence its frame
+    for (Seq& s : seqs)
+      for (int k = 0; k < 8; ++k) {
+        Msg m; m.ts = s.ts; m.type = 0; memcpy(m.gyro, gyro, 24); memcpy(m.accel, accel, 24);
+        s.ts += 5000000;
+        s.e->push(std::move(m));
+        Msg o;
+        if (s.e->pop_ready(&o)) run_msg(s, o);
+      }
+    for (Seq& s : seqs) {
+      Msg v; v.ts = (uint64_t)fr * 40000000ull; v.type = 3;
+      // emulate the image tracker's policy: tracks leave one by one, new ones arrive in a burst when fewer than 120 remain
+      auto vis = [&](int i, int* id, double* x) {
+        const double xx = s.x0[i] + 1.5 * fr;
+        *id = i + 1000 * (int)(xx / (W + 300.0));
+        *x = fmod(xx, W + 300.0) - 150.0;
+        return *x > 10 && *x < W - 10;
+      };
+      int ntr = 0;
+      for (int i = 0; i < NP; ++i) { int id; double x; if (vis(i, &id, &x) && s.tracked[id % (NP * 64)] == 1) ++ntr; }
+      const bool burst = ntr < 120;
+      for (int i = 0; i < NP; ++i) {
+        int id; double x;
+        if (!vis(i, &id, &x)) continue;
+        char& t = s.tracked[id % (NP * 64)];
+        if (t != 1 && burst && ntr < 150) { t = 1; ++ntr; }
+        if (t == 1) { v.ids.push_back(id); v.xp_depth.push_back(x); v.xp_depth.push_back(s.y0[i]); v.xp_depth.push_back(2.0); }
+      }
+      s.e->push(std::move(v));
       Msg o;
-      if (e.pop_ready(&o)) run_msg(o);
+      if (s.e->pop_ready(&o)) run_msg(s, o);
     }
-    Msg v; v.ts = (uint64_t)fr * 40000000ull; v.type = 3;
-    // emulate the image tracker's policy: tracks leave one by one, new ones arrive in a burst when fewer than 120 remain
-    static std::vector<char> tracked(NP * 64, 0);
-    auto vis = [&](int i, int* id, double* x) {
-      const double xx = x0[i] + 1.5 * fr;
-      *id = i + 1000 * (int)(xx / (W + 300.0));
-      *x = fmod(xx, W + 300.0) - 150.0;
-      return *x > 10 && *x < W - 10;
-    };
-    int ntr = 0;
-    for (int i = 0; i < NP; ++i) { int id; double x; if (vis(i, &id, &x) && tracked[id % (NP * 64)] == 1) ++ntr; }
-    const bool burst = ntr < 120;
-    for (int i = 0; i < NP; ++i) {
-      int id; double x;
-      if (!vis(i, &id, &x)) continue;
-      char& t = tracked[id % (NP * 64)];
-      if (t != 1 && burst && ntr < 150) { t = 1; ++ntr; }
-      if (t == 1) { v.ids.push_back(id); v.xp_depth.push_back(x); v.xp_depth.push_back(y0[i]); v.xp_depth.push_back(2.0); }
-    }
-    e.push(std::move(v));
-    Msg o;
-    if (e.pop_ready(&o)) run_msg(o);
   }
   const double total = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
-  printf("frames %d  tracks %zu  instate %zu  groups %zu  features in graph %zu   total %.1f us/frame\n", frames, e.tracks.size(), e.instate_features.size(),
+  Estimator& e = *seqs[0].e;
+  printf("estimators %d  frames %ld  tracks %zu  instate %zu  groups %zu  features in graph %zu   total %.1f us/frame\n", NE, frames, e.tracks.size(), e.instate_features.size(),
          e.graph.groups.size(), e.graph.features.size(), total / frames);
   for (auto& kv : g_t) printf("  %-34s %8.2f us/frame  (%ld calls)\n", kv.first.c_str(), kv.second.first / frames, kv.second.second);
   return 0;
