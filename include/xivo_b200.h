@@ -107,6 +107,12 @@ int xivo_ekf_update(xivo_ctx* ctx, int N, int M, const double* H, double* P, con
 #define XIVO_UPDATE_TF32X3 1u
 int xivo_ekf_update_ex(xivo_ctx* ctx, int N, int M, const double* H, double* P, const double* inn, const double* diagR,
                        double* err, unsigned flags);
+/* The same update for `batch` independent filters of one (N, M) in a single launch pair: H (batch x M x N), P (batch x N x N, in / out),
+ * inn, diagR (batch x M), err (batch x N).  repeat > 1 re-applies the update to the original P `repeat` times on the device (kernel timing
+ * through xivo_profile_enable / xivo_profile_report) and returns the result of one application.
+ * Replaces: a loop of Estimator::UpdateJosephForm calls (/root/reference/src/estimator.cpp:1257-1288), one per filter. */
+int xivo_ekf_update_batch(xivo_ctx* ctx, int N, int M, int batch, const double* H, double* P, const double* inn, const double* diagR,
+                          double* err, unsigned flags, int repeat);
 
 /* Production form of the update: Jacobians -> stack H for the selected features with
  * Feature::FillJacobianBlock semantics (src/feature.cpp:658-684) -> update; replaces

@@ -93,6 +93,44 @@ def test_dense_update_tensor_core_tf32x3(ctx, N, M):
     assert np.abs(P32 - Pr).max() <= 1e-5 * np.abs(P).max()
 
 
+@pytest.mark.parametrize("N,M,B", [(89, 28, 7), (203, 60, 5), (299, 124, 3), (299, 40, 3), (130, 33, 4)])
+def test_batched_update_both_tensor_core_kernels_and_fp64(ctx, N, M, B, monkeypatch):
+    """xivo_ekf_update_batch: B filters in one launch pair.  fp64 path against the Joseph oracle per filter; the tensor-core downdate in
+    both formulations -- ekf_cov_tc2_kernel (default: TF32 hi / lo operands written by the gain kernel, TMA-staged, several column chunks
+    per CTA, double-buffered TMEM accumulators) and the first kernel (XIVO_TC_V1=1) -- at the stated fp32 tolerance, exactly symmetric,
+    and equal to each other to fp32 rounding.  Sizes: the three BASELINE state dimensions with their maximal measurement counts, a
+    measurement count that is not a multiple of the 32-row K block, and a state dimension that crosses one 128-row tile by 2 rows."""
+    rng = np.random.default_rng(N * 7 + M + B)
+    Ps, Hs, inns, Rs = [], [], [], []
+    for _ in range(B):
+        A = rng.normal(size=(N, N))
+        scale = np.exp(rng.uniform(-5, 1, N))
+        P = (A @ A.T / N + np.eye(N)) * np.outer(scale, scale)
+        Ps.append(0.5 * (P + P.T))
+        Hs.append(rng.normal(size=(M, N)) * (rng.uniform(size=(M, N)) < 0.15))
+        inns.append(rng.normal(size=M))
+        Rs.append(rng.uniform(0.5, 2.0, M))
+    Ps, Hs, inns, Rs = np.stack(Ps), np.stack(Hs), np.stack(inns), np.stack(Rs)
+    P64, e64 = ctx.ekf_update_batch(Hs, Ps, inns, Rs)
+    monkeypatch.delenv("XIVO_TC_V1", raising=False)
+    P2, e2 = ctx.ekf_update_batch(Hs, Ps, inns, Rs, tf32x3=True)
+    P2r, _ = ctx.ekf_update_batch(Hs, Ps, inns, Rs, tf32x3=True, repeat=3)  # re-applied to the original P: same result
+    monkeypatch.setenv("XIVO_TC_V1", "1")
+    P1, e1 = ctx.ekf_update_batch(Hs, Ps, inns, Rs, tf32x3=True)
+    monkeypatch.delenv("XIVO_TC_V1", raising=False)
+    for b in range(B):
+        Pr, er, _, _ = E.update_joseph(Hs[b], Ps[b], inns[b], Rs[b])
+        pmax = np.abs(Ps[b]).max()
+        d = np.sqrt(np.outer(np.diag(Ps[b]), np.diag(Ps[b])))
+        assert np.abs(P64[b] - Pr).max() <= 1e-9 * pmax and np.abs(e64[b] - er).max() <= 1e-9 * max(1.0, np.abs(er).max())
+        assert np.abs(P64[b] - Ps[b]).max() > 1e-3 * pmax
+        for Pt, et in ((P2[b], e2[b]), (P1[b], e1[b])):
+            assert (np.abs(Pt - P64[b]) / d).max() <= 1e-5 and np.abs(Pt - P64[b]).max() <= 1e-5 * pmax
+            assert np.array_equal(Pt, Pt.T) and np.array_equal(et, e64[b])
+        assert np.array_equal(P2[b], P2r[b])
+        assert (np.abs(P2[b] - P1[b]) / d).max() <= 2e-6
+
+
 def test_dense_update_zero_measurements(ctx):
     P = np.eye(23)
     Pg, err = ctx.ekf_update(np.zeros((0, 23)), P, np.zeros(0), np.zeros(0))

@@ -176,6 +176,18 @@ class Context:
                "xivo_ekf_update_ex")
         return P, err
 
+    def ekf_update_batch(self, H, P, inn, diagR, tf32x3=False, repeat=1):
+        """`batch` filters of one (N, M) in one launch pair: H (B, M, N), P (B, N, N), inn / diagR (B, M) -> (P, err).  repeat > 1 re-applies
+        the update to the original P on the device (kernel timing through the in-library profiler)."""
+        H, inn, diagR = _f64(H), _f64(inn), _f64(diagR)
+        P = np.array(P, dtype=np.float64, order="C", copy=True)
+        B, M, N = H.shape
+        assert P.shape == (B, N, N) and inn.shape == (B, M) and diagR.shape == (B, M)
+        err = np.zeros((B, N))
+        _check(lib().xivo_ekf_update_batch(self._h, N, M, B, _p(H), _p(P), _p(inn), _p(diagR), _p(err), C.c_uint(1 if tf32x3 else 0), int(repeat)),
+               "xivo_ekf_update_batch")
+        return P, err
+
     def filter_update(self, G, F, camera, X24, groups, feat_x, feat_xp, feat_ref, feat_sind, sel, R, P, want_H=True):
         camera, X24, groups = _f64(camera), _f64(X24), _f64(groups)
         fx, fxp = _f64(feat_x).reshape(-1, 3), _f64(feat_xp).reshape(-1, 2)

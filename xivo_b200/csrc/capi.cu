@@ -263,27 +263,52 @@ int xivo_ekf_update(xivo_ctx* ctx, int N, int M, const double* H, double* P, con
 
 int xivo_ekf_update_ex(xivo_ctx* ctx, int N, int M, const double* H, double* P, const double* inn, const double* diagR, double* err,
                        unsigned flags) {
+  return xivo_ekf_update_batch(ctx, N, M, 1, H, P, inn, diagR, err, flags, 1);
+}
+
+// `batch` independent filters with the same (N, M): H (batch x M x N), P (batch x N x N, in/out), inn / diagR (batch x M), err (batch x N).
+// repeat > 1 applies the same update `repeat` times to the ORIGINAL P (restored on the device before every pass) and returns the result of
+// one application: with the in-library profiler on (xivo_profile_enable) the report then holds `repeat` samples of ekf_gain / ekf_cov.
+int xivo_ekf_update_batch(xivo_ctx* ctx, int N, int M, int batch, const double* H, double* P, const double* inn, const double* diagR, double* err,
+                          unsigned flags, int repeat) {
   API_BEGIN;
   XB_REQUIRE((flags & ~(unsigned)XIVO_UPDATE_TF32X3) == 0, "ekf_update: unknown flags");
-  XB_REQUIRE(N > 0 && M >= 0 && P && err && (M == 0 || (H && inn && diagR)), "ekf_update: bad arguments");
+  XB_REQUIRE(N > 0 && M >= 0 && batch > 0 && repeat >= 1 && P && err && (M == 0 || (H && inn && diagR)), "ekf_update: bad arguments");
   if (M == 0) {
-    for (int i = 0; i < N; ++i) err[i] = 0.0;
+    for (size_t i = 0; i < (size_t)batch * N; ++i) err[i] = 0.0;
     return XIVO_OK;
   }
   cudaStream_t st = ctx->stream;
-  DevBuf<double> dH((size_t)M * N), dP((size_t)N * N), dinn(M), dR(M), derr(N), dHP((size_t)M * N), dKt((size_t)M * N);
-  XB_REQUIRE(dH.ok() && dP.ok() && dinn.ok() && dR.ok() && derr.ok() && dHP.ok() && dKt.ok(), "cudaMalloc failed");
-  XB_CUDA(cudaMemcpyAsync(dH.p, H, sizeof(double) * M * N, cudaMemcpyHostToDevice, st));
-  XB_CUDA(cudaMemcpyAsync(dP.p, P, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
-  XB_CUDA(cudaMemcpyAsync(dinn.p, inn, sizeof(double) * M, cudaMemcpyHostToDevice, st));
-  XB_CUDA(cudaMemcpyAsync(dR.p, diagR, sizeof(double) * M, cudaMemcpyHostToDevice, st));
-  int rc = launch_ekf_update_dense(st, N, M, dH.p, dR.p, dinn.p, dP.p, derr.p, dHP.p, dKt.p, 1, (flags & XIVO_UPDATE_TF32X3) ? 1 : 0);
-  if (rc) return rc;
-  g_launches += 2;
-  XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost, st));
-  XB_CUDA(cudaMemcpyAsync(err, derr.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+  const size_t nb = (size_t)batch;
+  DevBuf<double> dH(nb * M * N), dP(nb * N * N), dP0(repeat > 1 ? nb * N * N : 0), dinn(nb * M), dR(nb * M), derr(nb * N), dHP(nb * M * N), dKt(nb * M * N);
+  XB_REQUIRE(dH.ok() && dP.ok() && dP0.ok() && dinn.ok() && dR.ok() && derr.ok() && dHP.ok() && dKt.ok(), "cudaMalloc failed");
+  const bool tensor = (flags & XIVO_UPDATE_TF32X3) != 0;
+  const bool v1 = getenv("XIVO_TC_V1") && getenv("XIVO_TC_V1")[0] == '1';
+  TcOperands tc;
+  DevBuf<uint32_t> dKt32, dHP32;
+  if (tensor && !v1) {  // second formulation: TF32 hi / lo operand buffers written by the gain kernel, staged by TMA in the downdate kernel
+    const size_t words = tc_operand_words(N, M, batch);
+    dKt32.alloc(words); dHP32.alloc(words);
+    XB_REQUIRE(dKt32.ok() && dHP32.ok(), "cudaMalloc failed");
+    XB_CUDA(cudaMemsetAsync(dKt32.p, 0, words * 4, st));
+    XB_CUDA(cudaMemsetAsync(dHP32.p, 0, words * 4, st));
+    if (int rc = tc_operands_init(&tc, N, M, batch, dKt32.p, dHP32.p)) return rc;
+  }
+  XB_CUDA(cudaMemcpyAsync(dH.p, H, sizeof(double) * nb * M * N, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dP.p, P, sizeof(double) * nb * N * N, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dinn.p, inn, sizeof(double) * nb * M, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dR.p, diagR, sizeof(double) * nb * M, cudaMemcpyHostToDevice, st));
+  if (repeat > 1) XB_CUDA(cudaMemcpyAsync(dP0.p, dP.p, sizeof(double) * nb * N * N, cudaMemcpyDeviceToDevice, st));
+  for (int it = 0; it < repeat; ++it) {
+    if (it) XB_CUDA(cudaMemcpyAsync(dP.p, dP0.p, sizeof(double) * nb * N * N, cudaMemcpyDeviceToDevice, st));
+    int rc = launch_ekf_update_dense(st, N, M, dH.p, dR.p, dinn.p, dP.p, derr.p, dHP.p, dKt.p, batch, tensor ? 1 : 0, tensor && !v1 ? &tc : nullptr);
+    if (rc) return rc;
+    g_launches += 2;
+  }
+  XB_CUDA(cudaMemcpyAsync(P, dP.p, sizeof(double) * nb * N * N, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(err, derr.p, sizeof(double) * nb * N, cudaMemcpyDeviceToHost, st));
   XB_CUDA(cudaStreamSynchronize(st));
-  if (flags & XIVO_UPDATE_TF32X3) XB_REQUIRE(ekf_cov_tc_fault(st) == 0, "ekf_update: the tensor-core downdate timed out waiting for its MMAs");
+  if (tensor) XB_REQUIRE(ekf_cov_tc_fault(st) == 0, "ekf_update: the tensor-core downdate timed out waiting for its MMAs");
   return XIVO_OK;
 }
 

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(GAIN_THREADS) ekf_gain_kernel(int N, EkfLayout
                                                                 double* __restrict__ err, double* __restrict__ HP,
                                                                 double* __restrict__ Kt, double* __restrict__ H_dense, int Mmax,
                                                                 const EditOp* __restrict__ ops, const int* __restrict__ ops_first,
-                                                                const int* __restrict__ nops) {
+                                                                const int* __restrict__ nops, uint32_t* __restrict__ kt32,
+                                                                uint32_t* __restrict__ hp32, int Npad, int KCmax) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int M = SPARSE ? 2 * nsel[b] : Mdense;
@@ -321,6 +322,42 @@ __global__ void __launch_bounds__(GAIN_THREADS) ekf_gain_kernel(int N, EkfLayout
     }
     errb[j] = e;
   }
+  // ---- e. (tensor-core downdate only) K^T and HP once more as TF32 hi / lo words in the layout ekf_cov_tc2_kernel's TMA boxes expect:
+  // [filter][hi|lo][k / 4][state column][4].  Thread j converts its own column (the values it has just written), 16-byte stores that
+  // are contiguous across the threads; columns N .. Npad and rows M .. 32 * ceil(M / 32) are zero.
+  if (kt32) {
+    const int kchunks = ((M + 31) / 32) * 8;
+    const size_t slab = (size_t)KCmax * Npad * 4;  // words of one (filter, hi|lo) slab
+    uint32_t* __restrict__ kH = kt32 + (size_t)b * 2 * slab;
+    uint32_t* __restrict__ hH = hp32 + (size_t)b * 2 * slab;
+    for (int j = tid; j < Npad; j += GAIN_THREADS) {
+      for (int kc = 0; kc < kchunks; ++kc) {
+        uint4 kh = make_uint4(0, 0, 0, 0), kl = kh, hh = kh, hl = kh;
+        if (j < N) {
+          uint32_t* khp = &kh.x; uint32_t* klp = &kl.x; uint32_t* hhp = &hh.x; uint32_t* hlp = &hl.x;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = 4 * kc + q;
+            if (r < M) {
+              const double kv = Ktb[(size_t)r * N + j], hv = HPb[(size_t)r * N + j];
+              uint32_t t;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"((float)kv));
+              khp[q] = t;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(klp[q]) : "f"((float)(kv - (double)__uint_as_float(t))));
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"((float)hv));
+              hhp[q] = t;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hlp[q]) : "f"((float)(hv - (double)__uint_as_float(t))));
+            }
+          }
+        }
+        const size_t o = ((size_t)kc * Npad + j) * 4;
+        *reinterpret_cast<uint4*>(kH + o) = kh;
+        *reinterpret_cast<uint4*>(kH + slab + o) = kl;
+        *reinterpret_cast<uint4*>(hH + o) = hh;
+        *reinterpret_cast<uint4*>(hH + slab + o) = hl;
+      }
+    }
+  }
 }
 
 constexpr int CT = 32;  // covariance tile
@@ -377,7 +414,7 @@ static size_t gain_smem(int Mmax, bool sparse) {
 
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel, const double* Rmeas,
                       double* P, double* err, double* HP, double* Kt, double* H_dense, int batch, int tensor_core, const EditOp* ops,
-                      const int* ops_first, const int* nops) {
+                      const int* ops_first, const int* nops, const TcOperands* tc) {
   const int N = lay.N(), Mmax = 2 * lay.F;
   const size_t smem = gain_smem(Mmax, true);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: 2*F too large for the shared-memory Cholesky");
@@ -389,9 +426,12 @@ int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const 
     }
   }
   ProfRec* pi_ = Prof::get().start("ekf_gain", st);
+  const bool tc2 = tensor_core && tc && tc->kt32;
   ekf_gain_kernel<true><<<batch, GAIN_THREADS, smem, st>>>(N, lay, jac, sel, nsel, 0, nullptr, nullptr, nullptr, Rmeas, P, err, HP,
-                                                          Kt, H_dense, Mmax, ops, ops_first, nops);
+                                                          Kt, H_dense, Mmax, ops, ops_first, nops, tc2 ? tc->kt32 : nullptr, tc2 ? tc->hp32 : nullptr,
+                                                          tc2 ? tc->Npad : 0, tc2 ? tc->KCmax : 0);
   Prof::get().stop(pi_, st);
+  if (tc2) return launch_ekf_cov_tc2(st, N, nsel, 0, *tc, P, batch);
   if (tensor_core) return launch_ekf_cov_tc(st, N, nsel, 0, Mmax, HP, Kt, P, batch);
   const int nt = (N + CT - 1) / CT;
   {
@@ -403,16 +443,25 @@ int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const 
 }
 
 int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,
-                            double* err, double* HP, double* Kt, int batch, int tensor_core) {
+                            double* err, double* HP, double* Kt, int batch, int tensor_core, const TcOperands* tc) {
   const size_t smem = gain_smem(M, false);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: M too large for the shared-memory Cholesky");
   XB_CUDA(cudaFuncSetAttribute(ekf_gain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   EkfLayout lay{0, 0};
-  ekf_gain_kernel<false><<<batch, GAIN_THREADS, smem, st>>>(N, lay, nullptr, nullptr, nullptr, M, H, diagR, inn, nullptr, P, err,
-                                                           HP, Kt, nullptr, M, nullptr, nullptr, nullptr);
+  const bool tc2 = tensor_core && tc && tc->kt32;
+  {
+    ProfScope pg("ekf_gain", st);
+    ekf_gain_kernel<false><<<batch, GAIN_THREADS, smem, st>>>(N, lay, nullptr, nullptr, nullptr, M, H, diagR, inn, nullptr, P, err,
+                                                             HP, Kt, nullptr, M, nullptr, nullptr, nullptr, tc2 ? tc->kt32 : nullptr,
+                                                             tc2 ? tc->hp32 : nullptr, tc2 ? tc->Npad : 0, tc2 ? tc->KCmax : 0);
+  }
+  if (tc2) return launch_ekf_cov_tc2(st, N, nullptr, M, *tc, P, batch);
   if (tensor_core) return launch_ekf_cov_tc(st, N, nullptr, M, M, HP, Kt, P, batch);
   const int nt = (N + CT - 1) / CT;
-  ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nullptr, M, M, HP, Kt, P);
+  {
+    ProfScope pc("ekf_cov", st);
+    ekf_cov_kernel<<<dim3(nt, nt, batch), 256, 0, st>>>(N, nullptr, M, M, HP, Kt, P);
+  }
   XB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -229,6 +229,8 @@ class Batch {
   xivo_ctx* ctx;
   int B, N, maxops, max_sub;
   int cov_tc = 0;  // covariance downdate on the tensor cores ("covariance_update": "tf32x3")
+  TcOperands tcops;  // its TF32 operand buffers + tensor maps (ekf_cov_tc2_kernel); XIVO_TC_V1=1 keeps the first formulation
+  uint32_t *dKt32 = nullptr, *dHP32 = nullptr;
   EkfLayout lay;
   std::vector<std::unique_ptr<Estimator>> est;
   // EKF device state
@@ -367,6 +369,12 @@ class Batch {
         }
       }
     }
+    if (ok && cov_tc && !(getenv("XIVO_TC_V1") && getenv("XIVO_TC_V1")[0] == '1')) {
+      const size_t words = tc_operand_words(N, 2 * lay.F, B);
+      ok = cudaMalloc(reinterpret_cast<void**>(&dKt32), words * 4) == cudaSuccess && cudaMalloc(reinterpret_cast<void**>(&dHP32), words * 4) == cudaSuccess &&
+           cudaMemset(dKt32, 0, words * 4) == cudaSuccess && cudaMemset(dHP32, 0, words * 4) == cudaSuccess &&
+           tc_operands_init(&tcops, N, 2 * lay.F, B, dKt32, dHP32) == 0;
+    }
     if (!ok) throw std::runtime_error(std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
     // initial covariance: identity with the motion block from the config (estimator.cpp:258-302)
     std::vector<double> P0((size_t)N * N, 0.0);
@@ -400,7 +408,7 @@ class Batch {
     if (wait_ev) cudaEventDestroy(wait_ev);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
     for (cudaEvent_t e : ring_ev) cudaEventDestroy(e);
-    for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr})
+    for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr, (void*)dKt32, (void*)dHP32})
       if (p) cudaFree(p);
     cam.release(); R.release(); mh.release(); pack.release(); sub_out.release(); blobS.release(); blobJ.release(); blobU.release();
     blobI[0].release(); blobI[1].release(); tk1.release(); tk2.release();
@@ -1191,7 +1199,7 @@ class Batch {
     }
     hs_issue.reset(new HostScope("issue_update"));
     XB_CUDA(up_blob(blobU, blobU_fixed + (size_t)nops_total * sizeof(EditOp), st));  // [nsel | nops | first | sel | packed post-gate edit list]
-    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B, cov_tc, opsU.d, firstU.d, nopsU.d)) return rc;
+    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B, cov_tc, opsU.d, firstU.d, nopsU.d, dKt32 ? &tcops : nullptr)) return rc;
     if (int rc = launch_pack_state(st, N, dP, dErr, pack.d, B)) return rc;
     g_launches += 3;
     for (int b : full) {

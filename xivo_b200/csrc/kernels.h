@@ -81,23 +81,37 @@ int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam
                          int batch, const EditOp* ops = nullptr /*packed edit lists applied to P first*/, const int* ops_first = nullptr /*B*/,
                          const int* nops = nullptr /*B*/);
 
+struct TcOperands;  // TF32 operand buffers + tensor maps of the tensor-core downdate (below)
 // Stack H (FillJacobianBlock semantics) for the selected features and do the measurement update.
 //   sel: B x F indices into the feature table, nsel: B counts (M = 2*nsel)
 // scratch: HP (B x 2F x N), Kt (B x 2F x N).  Outputs: err (B x N), P updated in place.
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel,
                       const double* Rmeas /*B*/, double* P, double* err, double* HP, double* Kt, double* H_dense /*or null*/,
                       int batch, int tensor_core = 0, const EditOp* ops = nullptr /*packed edit lists applied to P first*/,
-                      const int* ops_first = nullptr /*B*/, const int* nops = nullptr /*B*/);
+                      const int* ops_first = nullptr /*B*/, const int* nops = nullptr /*B*/, const TcOperands* tc = nullptr /*tensor_core: second formulation*/);
 
 // Dense-input variant used by the kernel-level C ABI (arbitrary H, diagR), same kernels underneath.
 int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,
-                            double* err, double* HP, double* Kt, int batch, int tensor_core = 0);
+                            double* err, double* HP, double* Kt, int batch, int tensor_core = 0, const TcOperands* tc = nullptr);
 
 // Tensor-core (tcgen05, 3xTF32, fp32 accumulator in TMEM) form of the downdate P -= Kt^T HP (ekf_tc_kernels.cu);
 // selected by tensor_core != 0 in the two launchers above.  ekf_cov_tc_fault: 1 if a kernel ever gave up waiting
 // for its MMAs (never expected), -1 on a CUDA error.
 int launch_ekf_cov_tc(cudaStream_t st, int N, const int* nsel, int Mdense, int Mmax, const double* HP, const double* Kt, double* P,
                       int batch);
+// Second formulation (ekf_cov_tc2_kernel): the gain kernel also writes K^T and HP as TF32 hi/lo words in the UMMA canonical layout
+// [filter][hi|lo][k/4][state column (Npad)][4]; the downdate kernel stages them by TMA.
+struct TcOperands {
+  uint32_t* kt32 = nullptr;
+  uint32_t* hp32 = nullptr;
+  int Npad = 0, KCmax = 0, batch = 0;
+  CUtensorMap mapA, mapB;
+};
+int tc_npad(int N);
+int tc_kcmax(int Mmax);
+size_t tc_operand_words(int N, int Mmax, int batch);  // 32-bit words of ONE operand buffer
+int tc_operands_init(TcOperands* t, int N, int Mmax, int batch, uint32_t* kt32, uint32_t* hp32);
+int launch_ekf_cov_tc2(cudaStream_t st, int N, const int* nsel, int Mdense, const TcOperands& t, double* P, int batch);
 int ekf_cov_tc_fault(cudaStream_t st);
 
 // Covariance edit list (AddGroupToState / AddFeatureToState / Remove* / FixFeatureXY / SwitchRefGroup).
