@@ -19,6 +19,7 @@ random_device-seeded shuffle of collinear gauge candidates (graph.cpp:337).
 from __future__ import annotations
 
 import heapq
+import copy
 import math
 
 import numpy as np
@@ -111,6 +112,13 @@ class Pool:
         self.act[t.slot] = self.init[t.slot] = False
 
 
+class _InsertionOrderedIds(dict):
+    """Set of ids that remembers the insertion order (a re-inserted id keeps its first position, like a hash set)."""
+
+    def add(self, k):
+        self.setdefault(k, True)
+
+
 def rot_of(v):
     v = np.asarray(v, dtype=np.float64)
     if v.size == 3:
@@ -191,6 +199,12 @@ class EstimatorOracle:
                               eps=do.get("eps", 1e-4), max_res_norm=do.get("max_res_norm", 2.0))
         self.num_refined = self.num_refine_failed = 0
         self.use_MH = c.get("use_MH_gating", True)
+        # filter-level 1-point RANSAC (update.cpp:213-393, call site manager.cpp:642-656); keys: estimator.cpp:131-134
+        self.use_1pt = bool(c.get("use_1pt_RANSAC", False))
+        self.ransac_thresh = float(c.get("1pt_RANSAC_thresh", 5))
+        self.ransac_prob = float(c.get("1pt_RANSAC_prob", 0.95))
+        self.ransac_chi2 = float(c.get("1pt_RANSAC_Chi2", 5.89))
+        self.num_oneptransac_rejected = 0
         self.min_inliers = c.get("min_inliers", 5)
         self.MH_thresh, self.MH_mult = c.get("MH_thresh", 5.991), c.get("MH_adjust_factor", 1.1)
         self.owner_cov_factor = c.get("filter_owner_change_cov_factor", 1.5)
@@ -601,7 +615,7 @@ class EstimatorOracle:
 
     def update_step(self):
         lay = self.lay
-        affected, new_features, self.inliers, in_update = set(), [], [], []
+        affected, new_features, self.inliers, in_update = _InsertionOrderedIds(), [], [], []
         for f in self.features.values():
             f.lifetime += 1
         for g in self.groups.values():
@@ -681,6 +695,12 @@ class EstimatorOracle:
                 self.inliers = inl
             else:
                 self.inliers = list(inst)
+        if self.use_1pt and inst:  # manager.cpp:642-656: made observable first, then the global test
+            before = set(self.features)
+            self.discard_affected_groups()
+            self.find_new_gauge_features()
+            self.tracks = [f for f in self.tracks if not (f.id in before and f.id not in self.features)]
+            self.inliers = self.one_point_ransac([f for f in self.inliers if f.instate()], Js, inns)
         before = set(self.features)
         self.discard_affected_groups()
         self.find_new_gauge_features()
@@ -728,6 +748,92 @@ class EstimatorOracle:
             if gg.lifetime > self.max_group_lifetime and not any(self.features[fid].ref is gg for fid in self.group_adj[gg.id]):
                 self.g_remove_group(gg)
                 self.gpool.deactivate(gg)
+
+    def one_point_ransac(self, mh_inliers, Js, inns):
+        """Estimator::OnePointRANSAC (update.cpp:213-393).  What the code does (as opposed to what its comments describe):
+        * every "hypothesis" evaluates the same test |xp - Predict(gsb, gbc)| < 1pt_RANSAC_thresh on every MH inlier -- the sampled index is
+          never used -- so the low-innovation set is a plain threshold test and the RNG only decides how often it is repeated;
+        * all low: the list is returned unchanged;
+        * otherwise: back up X, P (and the active features' / groups' states); zero the P rows / columns of the high-innovation features and
+          of the active groups without a low-innovation feature (and of a temporary reference group if the gauge group has none); a Joseph
+          update with the FULL Jacobian rows J() of the low-innovation features (not FillJacobianBlock's layout); AbsorbError, which at
+          this point of Estimator::Update moves only the motion state (instate_groups_ and in_current_ekf_update_ are still empty,
+          manager.cpp:24, :90-103); every high-innovation feature is re-linearised at that state and kept if r' (J P J' + R)^-1 r <
+          1pt_RANSAC_Chi2, else rejected (REJECTED_BY_FILTER, destroyed, its group affected); X, P and the saved states are restored --
+          P_ = P0_ also brings the rows of the just freed slots back (they stay until the slot is reused; FillCovarianceBlock clears
+          them, feature.cpp:753-760) -- and the Jacobians of the survivors are recomputed at the restored state.
+        The reference returns the survivors in the iteration order of a std::unordered_set<FeaturePtr> (hash of heap addresses); here they
+        keep the order of `mh_inliers`.  That order only permutes the rows of H in the update that follows."""
+        if not mh_inliers:
+            return mh_inliers
+        lay = self.lay
+        gsb = (self.X.Rsb, self.X.Tsb)
+        low = []
+        for f in mh_inliers:
+            pred = E.predict_pixel(self.cam, f.x, (f.ref.Rsb, f.ref.Tsb), gsb, self.gbc())
+            low.append(bool(np.linalg.norm(np.asarray(f.xp()) - pred) < self.ransac_thresh))
+        if all(low):
+            return mh_inliers
+        active_groups = []
+        for f in mh_inliers:
+            if f.ref not in active_groups:
+                active_groups.append(f.ref)
+        groups_low = [g for g in active_groups if any(l and f.ref is g for f, l in zip(mh_inliers, low))]
+        X0, P0 = copy.deepcopy(self.X), self.P.copy()
+        fx0 = {f.id: f.x.copy() for f in mh_inliers}
+        g0 = {g.id: (g.Rsb.copy(), g.Tsb.copy()) for g in active_groups}
+        if any(low):
+            gauge = self.groups.get(self.gauge_group)
+            if gauge is None or gauge not in groups_low:  # temporary reference group: FindNewRefGroup = smallest trace of the 6x6 block
+                cov = lambda g: float(np.trace(self.P[lay.goff(g.sind) : lay.goff(g.sind) + 6, lay.goff(g.sind) : lay.goff(g.sind) + 6]))
+                tmp = min(sorted(groups_low, key=lambda g: g.id), key=cov)
+                o = lay.goff(tmp.sind)
+                self.P[o : o + 6, :] = 0
+                self.P[:, o : o + 6] = 0
+            for f, l in zip(mh_inliers, low):
+                if not l:
+                    o = lay.foff(f.sind)
+                    self.P[o : o + 3, :] = 0
+                    self.P[:, o : o + 3] = 0
+            for g in active_groups:
+                if g not in groups_low:
+                    o = lay.goff(g.sind)
+                    self.P[o : o + 6, :] = 0
+                    self.P[:, o : o + 6] = 0
+            lows = [f for f, l in zip(mh_inliers, low) if l]
+            H, inn = np.zeros((2 * len(lows), lay.N)), np.zeros(2 * len(lows))
+            for i, f in enumerate(lows):
+                H[2 * i : 2 * i + 2] = Js[f.id]
+                inn[2 * i : 2 * i + 2] = inns[f.id]
+            self.P, err, _, _ = E.update_joseph(H, self.P, inn, np.full(2 * len(lows), self.R))
+            self.absorb(err, [], [])
+        out = [f for f, l in zip(mh_inliers, low) if l]
+        rescued, to_destroy = [], []
+        self.num_oneptransac_rejected = 0
+        for f, l in zip(mh_inliers, low):
+            if l:
+                continue
+            J, r, _ = E.feature_jacobian(lay, self.cam, self.X.Rsb, self.X.Tsb, self.X.Rbc, self.X.Tbc, f.ref.Rsb, f.ref.Tsb, f.x, f.xp(), f.ref.sind, f.sind)
+            if E.mh_distance(J, self.P, r, self.R) < self.ransac_chi2:
+                rescued.append(f)
+            else:
+                if f.status == F_GAUGE:
+                    self.needs_new_gauge.append(f.ref)
+                f.status = F_REJECTED
+                to_destroy.append(f)
+                self.num_oneptransac_rejected += 1
+                self.affected.add(f.ref.id)
+        self.destroy_features(to_destroy)
+        self.X, self.P = X0, P0
+        for f in mh_inliers:
+            f.x = fx0[f.id]
+        for g in active_groups:
+            g.Rsb, g.Tsb = g0[g.id]
+        survivors = [f for f in mh_inliers if f in out or f in rescued]
+        for f in survivors:  # Jacobians of the survivors at the restored state (the destroyed ones are recomputed too in the reference: dead objects)
+            J, r, _ = E.feature_jacobian(lay, self.cam, self.X.Rsb, self.X.Tsb, self.X.Rbc, self.X.Tbc, f.ref.Rsb, f.ref.Tsb, f.x, f.xp(), f.ref.sind, f.sind)
+            Js[f.id], inns[f.id] = J, r
+        return survivors
 
     def triangulate(self, f):
         """Feature::Triangulate (feature.cpp:686-751) from the first and the newest observation of the track."""
@@ -885,7 +991,11 @@ class EstimatorOracle:
                 break
 
     def discard_affected_groups(self):  # manager.cpp:307-328
-        for gid in sorted(self.affected):
+        # affected_groups_ is a std::unordered_set<GroupPtr> (estimator.h:364): with its few elements in distinct buckets libstdc++ links every
+        # new node at the head of the list, so the walk meets the groups in REVERSE insertion order (exact for two groups, the common case
+        # of more than one; with three or more and a bucket collision the reference's order depends on heap addresses).  The order matters
+        # when a discarded group's features find their new owner in another affected group.
+        for gid in reversed(list(self.affected)):
             g = self.groups.get(gid)
             if g is None:
                 continue
@@ -922,7 +1032,7 @@ class EstimatorOracle:
                 if g.instate():
                     self.remove_group_from_state(g)
                 self.gpool.deactivate(g)
-        self.affected = set()
+        self.affected = _InsertionOrderedIds()
 
     def find_new_gauge_features(self):  # update.cpp:35-47 + graph.cpp:276-361
         for g in self.needs_new_gauge:

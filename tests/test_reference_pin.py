@@ -66,6 +66,17 @@ CASES = [  # name, G, F, duration, seed, sim_depths, overrides, stamp offset of 
     ("dopt_all_nohess_89", 4, 14, 4.0, 21, True, _dopt(False, False), 1000),
     ("dopt_two_203", 15, 30, 4.0, 22, True, _dopt(True, True), 0),
     ("dopt_two_nohess_203", 15, 30, 4.0, 23, True, _dopt(True, False), 0),
+    # use_1pt_RANSAC (Estimator::OnePointRANSAC, update.cpp:213-393; on in cfg/void_params.json): every measurement below the residual
+    # threshold (the list passes through); a threshold inside the measurement noise (temporary low-innovation update, every high-innovation
+    # feature rescued); gross errors injected into the point-cloud stream (sim_outliers) so that features are rejected, their groups
+    # discarded and P_ restored with the freed slots' rows -- incl. a frame on which two groups are affected at once (the order of
+    # std::unordered_set<GroupPtr> affected_groups_ decides who can adopt whose features)
+    ("ransac_clean_89", 4, 14, 4.0, 31, True, {"use_1pt_RANSAC": True}, 0),
+    ("ransac_tight_89", 4, 14, 4.0, 32, True, {"use_1pt_RANSAC": True, "1pt_RANSAC_thresh": 0.8}, 0),
+    ("ransac_outliers_89", 4, 14, 4.0, 33, True, {"use_1pt_RANSAC": True, "1pt_RANSAC_thresh": 1.5, "sim_outliers": {"fraction": 0.08, "pixels": 2.5}}, 0),
+    ("ransac_outliers_203", 15, 30, 4.0, 34, True, {"use_1pt_RANSAC": True, "1pt_RANSAC_thresh": 1.5, "sim_outliers": {"fraction": 0.08, "pixels": 2.5}}, 1000),
+    ("ransac_two_groups_89", 4, 14, 4.0, 35, True, {"use_1pt_RANSAC": True, "1pt_RANSAC_thresh": 2.0, "1pt_RANSAC_Chi2": 3.0,
+                                                    "sim_outliers": {"fraction": 0.1, "pixels": 3.5}}, 0),
 ]
 
 

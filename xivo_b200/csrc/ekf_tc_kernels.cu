@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS) ekf_cov_tc_kernel(int N, const int
 //    (the first kernel wrote 8-byte words 8 N bytes apart).  The mirrored element is recomputed from its own old value, which equals
 //    P[i][j] bit for bit because P is kept exactly symmetric, so it stays exactly symmetric.
 // The contraction is bound by the fp64 traffic of P (2 N^2 8 B per filter against 3 * 2 N^2 M flop): see DESIGN.md section 4.
-constexpr int T2_MT = 128, T2_NT = 32, T2_KB = 32, T2_THREADS = 128;
+constexpr int T2_MT = 128, T2_NT = 32, T2_KB = 32, T2_THREADS = 512;  // warps 0-3 own the 128 TMEM lanes; all 16 warps stream P in the epilogue
 constexpr int T2_A_BLOCK = (T2_KB / 4) * T2_MT * 16;  // bytes of one k-block of A (hi or lo): 8 chunks x 128 rows x 16 B = 16 KB
 constexpr int T2_B_BLOCK = (T2_KB / 4) * T2_NT * 16;  // 4 KB
 
@@ -354,7 +354,9 @@ __global__ void __launch_bounds__(T2_THREADS) ekf_cov_tc2_kernel(const __grid_co
     bool ok = mbar_wait(smem_u32(&bars[3 + buf]), (uint32_t)(i >> 1) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     ok = __all_sync(0xffffffffu, ok);
-    if (ok) {
+    if (!ok) {
+      if (lane == 0) fault = 1;
+    } else if (warp < 4) {
       // TMEM lane = row of the tile; 4 x 8 consecutive columns -> shared staging (row stride 33 floats: conflict-free both ways)
 #pragma unroll
       for (int c = 0; c < T2_NT; c += 8) {
@@ -368,25 +370,45 @@ __global__ void __launch_bounds__(T2_THREADS) ekf_cov_tc2_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 8; ++j) sD[(warp * 32 + lane) * (T2_NT + 1) + c + j] = __uint_as_float(v[j]);
       }
-    } else if (lane == 0) {
-      fault = 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (!fault) {
       const int n0 = m0 + i * T2_NT;
+      // 4096 tile elements, 512 threads: every thread issues its 8 + 8 loads of P before the first dependent store, so that the SM keeps
+      // ~8 K loads in flight (the first version of this loop, one load per thread at a time, ran at 5 % of the HBM rate).
+      constexpr int PER = T2_MT * T2_NT / T2_THREADS;
+      double pv[PER];
+      size_t po[PER];
+      float dv[PER];
       // direct part: P[m0 + r][n0 + c] for r <= c (global indices), 32 consecutive doubles per row
-      for (int idx = tid; idx < T2_MT * T2_NT; idx += T2_THREADS) {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int idx = tid + k * T2_THREADS;
         const int r = idx >> 5, c = idx & 31;
         const int gi = m0 + r, gj = n0 + c;
-        if (gi < N && gj < N && gi <= gj) Pb[(size_t)gi * N + gj] -= (double)sD[r * (T2_NT + 1) + c];
+        const bool on = gi < N && gj < N && gi <= gj;
+        po[k] = on ? (size_t)gi * N + gj : ~(size_t)0;
+        dv[k] = sD[r * (T2_NT + 1) + c];
+        pv[k] = on ? Pb[po[k]] : 0.0;
       }
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+        if (po[k] != ~(size_t)0) Pb[po[k]] = pv[k] - (double)dv[k];
       // mirrored part: P[n0 + c][m0 + r] for r < c, 128 consecutive doubles per row; the old value read here equals P[m0 + r][n0 + c]
-      for (int idx = tid; idx < T2_MT * T2_NT; idx += T2_THREADS) {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int idx = tid + k * T2_THREADS;
         const int c = idx >> 7, r = idx & 127;
         const int gi = m0 + r, gj = n0 + c;
-        if (gi < N && gj < N && gi < gj) Pb[(size_t)gj * N + gi] -= (double)sD[r * (T2_NT + 1) + c];
+        const bool on = gi < N && gj < N && gi < gj;
+        po[k] = on ? (size_t)gj * N + gi : ~(size_t)0;
+        dv[k] = sD[r * (T2_NT + 1) + c];
+        pv[k] = on ? Pb[po[k]] : 0.0;
       }
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+        if (po[k] != ~(size_t)0) Pb[po[k]] = pv[k] - (double)dv[k];
     }
     __syncthreads();                                            // staging and B buffer `buf` are free again
     if (tid == 0 && i + 2 < ncc && !fault) load_b(i + 2);

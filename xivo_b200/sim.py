@@ -145,6 +145,14 @@ def pcw_stream(cfg: dict, duration=4.0, imu_dt=0.005, vision_dt=0.04, seed=0, no
     for t in np.arange(0, duration, vision_dt):
         Rsc, Tsc = camera_pose(traj, t, Rbc, Tbc)
         ids, xpd = observe_points(world, Rsc, Tsc, K, cam["rows"], cam["cols"], rng, pixel_sigma, cam=cam)
+        so = cfg.get("sim_outliers")  # {"fraction", "pixels", "from_time"}: gross measurement errors for the outlier-rejection paths
+        if so and t >= so.get("from_time", 1.0) and len(ids):
+            ro = np.random.default_rng(seed * 7919 + int(round(t * 1000)))
+            bad = ro.uniform(size=len(ids)) < so.get("fraction", 0.05)
+            ang = ro.uniform(0, 2 * np.pi, len(ids))
+            xpd = np.array(xpd, dtype=float, copy=True)
+            xpd[bad, 0] += so.get("pixels", 3.0) * np.cos(ang[bad])
+            xpd[bad, 1] += so.get("pixels", 3.0) * np.sin(ang[bad])
         msgs.append((t, 1, "pc", (ids, xpd)))
     msgs.sort(key=lambda m: (m[0], m[1]))
     return [(k, int(round(t * 1e9)), p) for (t, _, k, p) in msgs], traj
