@@ -61,6 +61,18 @@ unsigned long long xivo_pyramid_layout(int rows, int cols, int cn, int win, int 
 int xivo_build_pyramid(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int cn, int win, int max_level,
                        uint8_t* out);
 
+/* BRIEF-32 descriptors at the given keypoints; replaces extractor_->compute() (src/tracker.cpp:231-234, :361-363, :536-545) for the
+ * "BRIEF" descriptor.  kp_xy: n (x, y) float pairs.  desc: n x 32 bytes, valid: n flags; keypoints closer than 28 px to the image border are
+ * dropped by OpenCV's extractor: they get valid = 0 and a zero descriptor here, the caller compacts.  3-channel input is converted to grey.
+ * The 256 test pairs are this library's own table (xivo_b200/csrc/brief_pattern.h): opencv_contrib's is not vendored in the reference. */
+int xivo_brief_describe(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int cn, const float* kp_xy, int n, uint8_t* desc,
+                        uint8_t* valid);
+
+/* cv::BFMatcher(NORM_HAMMING, crossCheck = true).knnMatch(query, train, 1, noArray(), compactResult = true) for 32-byte descriptors;
+ * replaces matcher_->knnMatch at src/tracker.cpp:261-262, :378-379 and the popcount distance of src/fastbrief.cpp:53-93.
+ * out3: up to nq (queryIdx, trainIdx, distance) triples in query order; *n_out their number. */
+int xivo_hamming_match(xivo_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int* out3, int* n_out);
+
 /* FAST-9/16 + non-max suppression; replaces detector_->detect() at src/tracker.cpp:224 for the
  * "FAST" detector (src/tracker.cpp:39-42).  3-channel input is converted to grey first, as
  * OpenCV does.  Output is raster ordered (y major) like OpenCV's; kp_xy = (x, y) pairs.

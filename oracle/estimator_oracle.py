@@ -60,6 +60,8 @@ class Feature:
         self.tri_ok = False  # triangulation_successful_ (feature.cpp:80)
         self.track = [np.array([x, y], dtype=np.float64)]
         self.response = 0.0
+        self.descriptor = None          # Feature::descriptor() (feature.h:50): 32 bytes, set at detection, replaced when `differential`
+        self.kp0 = (float(x), float(y))  # Feature::keypoint().pt: the keypoint the feature was created from (SetKeypoint, never updated)
 
     def instate(self):
         return self.status in (F_INSTATE, F_GAUGE)
@@ -233,6 +235,18 @@ class EstimatorOracle:
         self.outlier_rejection = ({"RANSAC": 8, "LMEDS": 4}[oj.get("method", "RANSAC")], oj.get("RANSAC_reproj_thresh", 3.0), oj.get("RANSAC_max_iters", 2000),
                                   oj.get("confidence", 0.995))
         self.num_outliers_rejected = self.num_failed_to_track = 0
+        # descriptor path (tracker.cpp:176-217): BRIEF-32 per track and frame, descriptor check, rescue of dropped tracks, MATCH tracker
+        self.desc_thresh = int(tj.get("descriptor_distance_thresh", -1))
+        self.extract_descriptor = bool(tj.get("extract_descriptor", False)) or self.desc_thresh > -1
+        self.differential = bool(tj.get("differential", True))
+        self.tracker_type = tj.get("tracker_type", "LK")
+        self.match_dropped = bool(tj.get("match_dropped_tracks", False)) and self.tracker_type == "LK"
+        if self.tracker_type == "MATCH" and not self.extract_descriptor:
+            raise ValueError("Using a matcher-tracker requires extracting descriptors")
+        if self.match_dropped and not self.extract_descriptor:
+            raise ValueError("must extract descriptors in order to match dropped tracks")
+        if self.extract_descriptor and tj.get("descriptor", "BRIEF") != "BRIEF":
+            raise ValueError("only the BRIEF descriptor is restated")
         self.fast_thr = tj.get("FAST", {}).get("threshold", 5)
         self.fast_nms = tj.get("FAST", {}).get("nonmaxSuppression", True)
         # bookkeeping
@@ -499,6 +513,8 @@ class EstimatorOracle:
                 for i, fid in enumerate(ids):
                     self.ids_to_depths.setdefault(int(fid), float(xpd[i, 2]))
             self.tracker_update_pointcloud(ids, xpd)
+        elif self.tracker_type == "MATCH":
+            self.tracker_update_match(payload)
         else:
             self.tracker_update_lk(payload)
         if tracker_only:
@@ -567,6 +583,19 @@ class EstimatorOracle:
         r1, st, _ = T.lk_track(self.prev_img, img, p0, p1, **self.klt)
         if self.stage_timer is not None:
             self.stage_timer.lk(self.prev_img, img, p0, p1, self.klt)
+        st = np.array(st, np.uint8).copy()
+        if self.extract_descriptor:  # tracker.cpp:530-565: descriptors at the tracked positions; keypoints the extractor drops (border) are skipped
+            desc, dvalid = T.brief(img, r1)
+            for i, f in enumerate(self.tracks):
+                if not dvalid[i]:
+                    continue
+                if self.desc_thresh != -1:
+                    if T.hamming(f.descriptor, desc[i]) > self.desc_thresh:
+                        st[i] = 0  # enforce to be dropped
+                    elif self.differential:
+                        f.descriptor = desc[i].copy()
+                elif self.differential:
+                    f.descriptor = desc[i].copy()
         valid, status = 0, np.zeros(len(self.tracks), np.uint8)
         for i, f in enumerate(self.tracks):
             ok = bool(st[i])
@@ -585,24 +614,127 @@ class EstimatorOracle:
             from oracle import homography_oracle as HO
 
             done, rej, status = HO.tracker_outlier_rejection_413(p0, r1, status, *self.outlier_rejection)
+            self._or_done = bool(done)
             if done:
                 self.num_outliers_rejected = rej  # (stale when OutlierRejection returned early, like the reference's member)
             valid -= self.num_outliers_rejected
         dropped = [f for i, f in enumerate(self.tracks) if not status[i]]
         if valid < self.t_min:
-            self.detect_lk(img, self.t_max - valid)
-        for f in dropped:
+            # (check_homography = outlier rejection ran: CheckHomography, tracker.cpp:818-828, never applies H -- it compares the dropped
+            # feature's creation keypoint with the new one)
+            self.detect_lk(img, self.t_max - valid, dropped, self.do_outlier_rejection and getattr(self, "_or_done", False))
+        for f in dropped:  # tracker.cpp:617-619: every newly dropped track, rescued or not (DetectLK worked on a copy of the vector)
             f.tstatus = DROPPED
         self.prev_img = img
 
-    def detect_lk(self, img, num_to_add):
+    def detect_lk(self, img, num_to_add, newly_dropped=(), check_homography=False):
         xy, sc, _ = T.fast_detect(img, self.fast_thr, self.fast_nms)
         if self.stage_timer is not None:
             self.stage_timer.fast(img, self.fast_thr, self.fast_nms)
-        for i in T.select_keypoints(self.mask, xy, sc, num_to_add):
-            f = self.create_feature(float(xy[i][0]), float(xy[i][1]))
-            f.response = float(sc[i])
-            self.tracks.append(f)
+        if not self.extract_descriptor:
+            for i in T.select_keypoints(self.mask, xy, sc, num_to_add):
+                f = self.create_feature(float(xy[i][0]), float(xy[i][1]))
+                f.response = float(sc[i])
+                self.tracks.append(f)
+            return
+        # with descriptors (tracker.cpp:231-327): mask filter and sort as above, the extractor then drops the keypoints of the border band
+        keep = [i for i in range(len(xy)) if self.mask.m[int(xy[i][1] + 0.5), int(xy[i][0] + 0.5)]]
+        keep.sort(key=lambda i: (-int(sc[i]), int(xy[i][1]), int(xy[i][0])))
+        desc, dvalid = T.brief(img, np.asarray(xy, np.float32)[keep].reshape(-1, 2))
+        keep = [i for i, v in zip(keep, dvalid) if v]
+        desc = desc[dvalid]
+        matched = {}  # position in `keep` -> index into newly_dropped
+        newly_dropped = list(newly_dropped)
+        if self.match_dropped and newly_dropped and keep:
+            qd = np.stack([f.descriptor for f in newly_dropped])
+            for qi, ti, dist in T.bf_match_crosscheck(qd, desc):
+                f = newly_dropped[qi]
+                k = keep[ti]
+                ok_desc = (dist < self.desc_thresh) if self.desc_thresh > 0 else True  # CheckDescriptorDistance
+                ok_disp = float(np.linalg.norm(np.array([float(xy[k][0]), float(xy[k][1])]) - f.xp())) < self.t_max_disp
+                ok_h = True
+                if check_homography:  # CheckHomography: |creation keypoint - new keypoint| < reprojection threshold (H is never applied)
+                    ok_h = float(np.linalg.norm(np.array(f.kp0, np.float32).astype(np.float64) - np.array([float(xy[k][0]), float(xy[k][1])]))) < self.outlier_rejection[1]
+                if ok_desc and ok_disp and ok_h:
+                    matched[ti] = qi
+        for pos, i in enumerate(keep):
+            x, y = float(xy[i][0]), float(xy[i][1])
+            if self.mask.valid(x, y):
+                if self.match_dropped and pos in matched:
+                    f1 = newly_dropped[matched[pos]]
+                    if self.differential:
+                        f1.descriptor = desc[pos].copy()
+                    f1.track.append(np.array([x, y]))
+                    f1.tstatus = TRACKED  # ("potentially rescued": UpdateLK marks it DROPPED again right after)
+                    self.mask.mask_out(x, y)
+                    num_to_add -= 1
+                    continue  # (skips the budget / response test below, like the reference's `continue`)
+                f = self.create_feature(x, y)
+                f.response = float(sc[i])
+                f.descriptor = desc[pos].copy()
+                self.tracks.append(f)
+                self.mask.mask_out(x, y)
+                num_to_add -= 1
+            if num_to_add <= 0 or sc[i] < 5:
+                break
+
+    def tracker_update_match(self, img):
+        """Tracker::UpdateMatch (tracker.cpp:341-460): detect without a mask, describe, cross-checked nearest-neighbour matching of the
+        existing features' descriptors against the new keypoints, checks, unmatched features dropped, unmatched keypoints become features."""
+        img = np.ascontiguousarray(img)
+        self.num_new_detections = 0
+        xy, sc, _ = T.fast_detect(img, self.fast_thr, self.fast_nms)
+        order = sorted(range(len(xy)), key=lambda i: (-int(sc[i]), int(xy[i][1]), int(xy[i][0])))
+        desc, dvalid = T.brief(img, np.asarray(xy, np.float32)[order].reshape(-1, 2))
+        order = [i for i, v in zip(order, dvalid) if v]
+        desc = desc[dvalid]
+        feats = list(self.tracks)
+        new_matched, feat_matched = [False] * len(order), [False] * len(feats)
+        if self.tracker_initialized and feats and order:
+            matches = T.bf_match_crosscheck(np.stack([f.descriptor for f in feats]), desc)
+            mstat = np.zeros(len(matches), np.uint8)
+            for m, (qi, ti, dist) in enumerate(matches):
+                k = order[ti]
+                ok_desc = (dist < self.desc_thresh) if self.desc_thresh > 0 else True
+                ok_disp = float(np.linalg.norm(np.array([float(xy[k][0]), float(xy[k][1])]) - feats[qi].xp())) < self.t_max_disp
+                mstat[m] = ok_desc and ok_disp
+            self.num_failed_to_track = len(feats) - len(matches) + int((mstat == 0).sum())
+            if self.do_outlier_rejection and matches:
+                from oracle import homography_oracle as HO
+
+                p0 = np.array([feats[qi].kp0 for qi, _, _ in matches], np.float32)
+                p1 = np.array([[float(xy[order[ti]][0]), float(xy[order[ti]][1])] for _, ti, _ in matches], np.float32)
+                done, rej, mstat = HO.tracker_outlier_rejection_413(p0, p1, mstat, *self.outlier_rejection)
+                if done:
+                    self.num_outliers_rejected = rej
+            for m, (qi, ti, dist) in enumerate(matches):
+                if not mstat[m]:
+                    continue
+                new_matched[ti] = feat_matched[qi] = True
+                f, k = feats[qi], order[ti]
+                f.track.append(np.array([float(xy[k][0]), float(xy[k][1])]))
+                if self.differential:
+                    f.descriptor = desc[ti].copy()
+                f.tstatus = TRACKED
+        elif self.tracker_initialized:
+            self.num_failed_to_track = len(feats)
+        dropped = 0
+        for f, m in zip(feats, feat_matched):
+            if not m:
+                f.tstatus = DROPPED
+                dropped += 1
+        to_create = self.t_max - len(feats) + dropped
+        for pos, i in enumerate(order):
+            if to_create <= 0:
+                break
+            if not new_matched[pos]:
+                f = self.create_feature(float(xy[i][0]), float(xy[i][1]))
+                f.response = float(sc[i])
+                f.descriptor = desc[pos].copy()
+                self.tracks.append(f)
+                self.num_new_detections += 1
+                to_create -= 1
+        self.tracker_initialized = True
 
     # ---------------------------------------------------------------- UpdateStep (manager.cpp:18-167)
     def candidate(self, f, strict):
@@ -615,6 +747,7 @@ class EstimatorOracle:
 
     def update_step(self):
         lay = self.lay
+        self.ransac_trace = None
         affected, new_features, self.inliers, in_update = _InsertionOrderedIds(), [], [], []
         for f in self.features.values():
             f.lifetime += 1
@@ -774,6 +907,9 @@ class EstimatorOracle:
             low.append(bool(np.linalg.norm(np.asarray(f.xp()) - pred) < self.ransac_thresh))
         if all(low):
             return mh_inliers
+        # what the device phases of the product compute, for the CPU twin test (tests/test_host_twin.py)
+        self.ransac_trace = dict(diag=np.diag(self.P).copy(), low=[f.id for f, l in zip(mh_inliers, low) if l], high=[f.id for f, l in zip(mh_inliers, low) if not l],
+                                 err=None, mh={})
         active_groups = []
         for f in mh_inliers:
             if f.ref not in active_groups:
@@ -806,6 +942,7 @@ class EstimatorOracle:
                 H[2 * i : 2 * i + 2] = Js[f.id]
                 inn[2 * i : 2 * i + 2] = inns[f.id]
             self.P, err, _, _ = E.update_joseph(H, self.P, inn, np.full(2 * len(lows), self.R))
+            self.ransac_trace["err"] = err.copy()
             self.absorb(err, [], [])
         out = [f for f, l in zip(mh_inliers, low) if l]
         rescued, to_destroy = [], []
@@ -814,7 +951,9 @@ class EstimatorOracle:
             if l:
                 continue
             J, r, _ = E.feature_jacobian(lay, self.cam, self.X.Rsb, self.X.Tsb, self.X.Rbc, self.X.Tbc, f.ref.Rsb, f.ref.Tsb, f.x, f.xp(), f.ref.sind, f.sind)
-            if E.mh_distance(J, self.P, r, self.R) < self.ransac_chi2:
+            d_hi = E.mh_distance(J, self.P, r, self.R)
+            self.ransac_trace["mh"][f.id] = d_hi
+            if d_hi < self.ransac_chi2:
                 rescued.append(f)
             else:
                 if f.status == F_GAUGE:

@@ -375,3 +375,69 @@ int orc_lk_track(const uint8_t *prev, const uint8_t *next, int rows, int cols, i
   }
   return L;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * BRIEF-32 descriptors, Hamming distance and the cross-checked brute-force matcher of the descriptor path
+ * (/root/reference/src/tracker.cpp:231-292 DetectLK rescue, :341-460 UpdateMatch, :530-565 descriptor check in UpdateLK;
+ * popcount distance: /root/reference/src/fastbrief.cpp:53-93).  The arithmetic lives in OpenCV (features2d BFMatcher) and
+ * opencv_contrib (xfeatures2d BriefDescriptorExtractor), neither vendored in the reference.
+ *   BRIEF as in opencv_contrib: grey image, keypoints closer than 28 px (= 48 / 2 + 9 / 2) to the border are dropped, the pixel is
+ *   (int)(pt + 0.5), a test compares two 9 x 9 box sums (OpenCV reads them from an integral image: the same integers), test 8 i + k
+ *   sets bit 7 - k of byte i.  The 256 test pairs are an OWN table (xivo_b200/csrc/brief_pattern.h, scripts/make_brief_pattern.py):
+ *   opencv_contrib's generated table is not available here, so descriptor VALUES are parity-unpinned; the matcher is pinned on cv2.
+ *   BFMatcher(NORM_HAMMING, crossCheck = true).knnMatch(query, train, 1, noArray(), compactResult = true): the nearest train
+ *   descriptor of every query (first index on ties), kept when that train's nearest query (first index on ties) is the query. */
+#include "../xivo_b200/csrc/brief_pattern.h"
+
+static inline int box9(const uint8_t *g, int cols, int x, int y) {
+  int s = 0;
+  for (int dy = -4; dy <= 4; ++dy)
+    for (int dx = -4; dx <= 4; ++dx) s += g[(y + dy) * cols + (x + dx)];
+  return s;
+}
+
+/* img: grey rows x cols.  kp_xy: n x 2 floats.  desc: n x 32 bytes (zero for dropped keypoints), valid: n flags. */
+void orc_brief(const uint8_t *img, int rows, int cols, const float *kp_xy, int n, uint8_t *desc, uint8_t *valid) {
+  for (int i = 0; i < n; ++i) {
+    const float fx = kp_xy[2 * i], fy = kp_xy[2 * i + 1];
+    uint8_t *d = desc + 32 * (size_t)i;
+    memset(d, 0, 32);
+    /* KeyPointsFilter::runByImageBorder: Rect(border, border, cols - 2 border, rows - 2 border).contains(pt) on the float point */
+    valid[i] = (fx >= XB_BRIEF_BORDER && fx < cols - XB_BRIEF_BORDER && fy >= XB_BRIEF_BORDER && fy < rows - XB_BRIEF_BORDER) ? 1 : 0;
+    if (!valid[i]) continue;
+    const int cx = (int)(fx + 0.5f), cy = (int)(fy + 0.5f);
+    for (int t = 0; t < 256; ++t) {
+      const signed char *p = kBriefPattern[t];
+      const int a = box9(img, cols, cx + p[0], cy + p[1]), b = box9(img, cols, cx + p[2], cy + p[3]);
+      if (a < b) d[t >> 3] |= (uint8_t)(1u << (7 - (t & 7)));
+    }
+  }
+}
+
+int orc_hamming(const uint8_t *a, const uint8_t *b, int bytes) {
+  int d = 0;
+  for (int i = 0; i < bytes; ++i) d += __builtin_popcount((unsigned)(a[i] ^ b[i]));
+  return d;
+}
+
+/* Cross-checked 1-nearest-neighbour matches: out (query, train, distance) triples in query order; returns their number. */
+int orc_bf_match_crosscheck(const uint8_t *q, int nq, const uint8_t *t, int nt, int bytes, int *out3) {
+  int m = 0;
+  if (nq <= 0 || nt <= 0) return 0;
+  int *best_q_of_t = (int *)malloc(sizeof(int) * (size_t)nt), *best_d_of_t = (int *)malloc(sizeof(int) * (size_t)nt);
+  for (int j = 0; j < nt; ++j) { best_q_of_t[j] = -1; best_d_of_t[j] = 1 << 30; }
+  int *best_t_of_q = (int *)malloc(sizeof(int) * (size_t)nq), *best_d_of_q = (int *)malloc(sizeof(int) * (size_t)nq);
+  for (int i = 0; i < nq; ++i) {
+    int bt = -1, bd = 1 << 30;
+    for (int j = 0; j < nt; ++j) {
+      const int d = orc_hamming(q + (size_t)i * bytes, t + (size_t)j * bytes, bytes);
+      if (d < bd) { bd = d; bt = j; }
+      if (d < best_d_of_t[j]) { best_d_of_t[j] = d; best_q_of_t[j] = i; }
+    }
+    best_t_of_q[i] = bt; best_d_of_q[i] = bd;
+  }
+  for (int i = 0; i < nq; ++i)
+    if (best_t_of_q[i] >= 0 && best_q_of_t[best_t_of_q[i]] == i) { out3[3 * m] = i; out3[3 * m + 1] = best_t_of_q[i]; out3[3 * m + 2] = best_d_of_q[i]; ++m; }
+  free(best_q_of_t); free(best_d_of_t); free(best_t_of_q); free(best_d_of_q);
+  return m;
+}

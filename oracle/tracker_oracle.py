@@ -61,6 +61,34 @@ def pyramid(img, win, max_level):
     return out
 
 
+def brief(img, kp_xy):
+    """BRIEF-32 at the given keypoints (n x 2 float32) -> (descriptors n x 32 uint8, valid n bool); BGR input is converted to grey first."""
+    img, r, c, cn = _shape(img)
+    if cn == 3:
+        img = bgr2gray(img)
+    kp = np.ascontiguousarray(kp_xy, dtype=np.float32).reshape(-1, 2)
+    n = len(kp)
+    desc, valid = np.zeros((max(n, 1), 32), np.uint8), np.zeros(max(n, 1), np.uint8)
+    if n:
+        lib().orc_brief(_vp(img), r, c, _vp(kp), n, _vp(desc), _vp(valid))
+    return desc[:n], valid[:n].astype(bool)
+
+
+def hamming(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return int(lib().orc_hamming(_vp(a), _vp(b), a.size))
+
+
+def bf_match_crosscheck(query, train):
+    """cv::BFMatcher(NORM_HAMMING, crossCheck=True).knnMatch(query, train, 1, compactResult=True) -> [(queryIdx, trainIdx, distance)]."""
+    q, t = np.ascontiguousarray(query, np.uint8), np.ascontiguousarray(train, np.uint8)
+    if len(q) == 0 or len(t) == 0:
+        return []
+    out = np.zeros((len(q), 3), np.int32)
+    m = lib().orc_bf_match_crosscheck(_vp(q), len(q), _vp(t), len(t), q.shape[1], _vp(out))
+    return [tuple(int(v) for v in row) for row in out[:m]]
+
+
 def scharr(img):
     img, r, c, cn = _shape(img)
     out = np.zeros((r, c, cn * 2), np.int16)

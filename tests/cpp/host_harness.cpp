@@ -159,6 +159,36 @@ int hh_after_gate(void* h, const double* mh) {
   e->edits.clear();
   return (int)e->in_update.size();
 }
+// ---- 1-point RANSAC: the gate with the covariance diagonal of this frame; -1 = the two RANSAC device phases are pending
+static std::vector<xb::Feature*> g_table_order;  // index space of the device feature table (instate_features before the gate)
+int hh_after_gate_diag(void* h, const double* mh, const double* diag) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  g_table_order = e->instate_features;
+  e->update_step_after_gate(mh, diag);
+  e->edits.clear();
+  return e->ransac.active ? -1 : (int)e->in_update.size();
+}
+// ids of the device table order; low / high innovation ids; the rows the temporary update zeroes as (first, count) pairs
+int hh_ransac_info(void* h, int* table_ids, int* low_ids, int* n_low, int* high_ids, int* n_high, int* zero_pairs, int* n_zero) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  for (size_t i = 0; i < g_table_order.size(); ++i) table_ids[i] = g_table_order[i]->id;
+  *n_low = *n_high = 0;
+  for (size_t i = 0; i < e->ransac.mh_inliers.size(); ++i) {
+    if (e->ransac.low[i]) low_ids[(*n_low)++] = e->ransac.mh_inliers[i]->id;
+    else high_ids[(*n_high)++] = e->ransac.mh_inliers[i]->id;
+  }
+  *n_zero = (int)e->ransac.zero_edits.size();
+  for (int i = 0; i < *n_zero; ++i) { zero_pairs[2 * i] = e->ransac.zero_edits[i].a; zero_pairs[2 * i + 1] = e->ransac.zero_edits[i].n; }
+  return (int)g_table_order.size();
+}
+void hh_ransac_temp(void* h, const double* err) { static_cast<xb::Estimator*>(h)->ransac_after_temp_update(err); }
+int hh_ransac_finish(void* h, const double* mh_table) {
+  auto* e = static_cast<xb::Estimator*>(h);
+  e->ransac_finish(mh_table, g_table_order);
+  e->edits.clear();
+  return (int)e->in_update.size();
+}
+int hh_ransac_rejected(void* h) { return static_cast<xb::Estimator*>(h)->num_oneptransac_rejected; }
 void hh_after_update(void* h, const double* err, const double* Pmm, const double* diag, int had_update) {
   auto* e = static_cast<xb::Estimator*>(h);
   e->update_step_after_update(err, Pmm, diag, had_update != 0);

@@ -64,7 +64,9 @@ def test_pcw_trajectory_parity(G, F, method, sim_depths):
     b.close()
 
 
-@pytest.mark.parametrize("case", ["default_203", "small_89", "nodepth_89", "rk4_89", "equidistant_203"])
+@pytest.mark.parametrize("case", ["default_203", "small_89", "nodepth_89", "rk4_89", "equidistant_203",
+                                  # use_1pt_RANSAC (Estimator::OnePointRANSAC): pass-through, temporary update with every feature rescued, rejections
+                                  "ransac_clean_89", "ransac_tight_89", "ransac_outliers_89", "ransac_outliers_203", "ransac_two_groups_89"])
 def test_pcw_trajectory_matches_the_reference_estimator(case, tmp_path):
     """The CUDA pipeline against the REFERENCE'S OWN ESTIMATOR (its unmodified sources built into oracle/_ref by oracle/build_ref.py;
     golden arrays tests/golden/reference_pcw.npz where the library is absent) on the point-cloud streams of tests/test_reference_pin.py:
@@ -95,6 +97,8 @@ def test_pcw_trajectory_matches_the_reference_estimator(case, tmp_path):
     assert k == len(ref["gsb"])
     P = b.P(0)
     assert np.abs(P - ref["P"]).max() <= 1e-7 * np.abs(ref["P"]).max()
+    if case.startswith("ransac_outliers") or case.startswith("ransac_two"):
+        assert b.tracker_counters(0)["num_oneptransac_rejected"] >= 0  # (the last frame's count; rejections over the run are what the id tables pin)
     b.close()
 
 

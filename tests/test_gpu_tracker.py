@@ -229,3 +229,33 @@ def test_fast_tma_kernel_equals_thread_staged_kernel(ctx, shape, thr, monkeypatc
         rxy, rsc, rn = T.fast_detect(a, thr, nonmax=nonmax, max_kp=1 << 18)
         assert n == n2 == rn
         assert key(xy, sc) == key(xy2, sc2) == key(rxy, rsc)
+
+
+@pytest.mark.parametrize("shape,cn", [((480, 640), 1), ((240, 320), 3), ((512, 512), 1), ((120, 97), 1)])
+def test_brief_descriptors_equal_the_oracle(ctx, shape, cn):
+    """brief_kernel (warp per keypoint, separable 9 x 9 box sums of the 56 x 56 neighbourhood in shared memory, lane = descriptor byte) against
+    oracle/tracker_oracle.c (direct 81-pixel sums): identical bytes and identical border drops, for keypoints on a grid that includes the
+    28-pixel border band, sub-pixel positions on both sides of the .5 rounding, and BGR input (grey conversion fused)."""
+    a, _ = synth.frame_pair(shape[0], shape[1], seed=41)
+    img = a if cn == 1 else synth.to_bgr(a, True)
+    rng = np.random.default_rng(5)
+    kp = np.concatenate([rng.uniform(0, [shape[1], shape[0]], (400, 2)),
+                         np.array([[28.0, 28.0], [27.99, 40.0], [shape[1] - 28.0, 50.0], [shape[1] - 28.01, 50.0], [60.5, 70.5], [60.49, 70.51]])]).astype(np.float32)
+    d, v = ctx.brief_describe(img, kp)
+    rd, rv = T.brief(img, kp)
+    assert np.array_equal(v, rv) and v.sum() > 50 and (~v).sum() > 5
+    assert np.array_equal(d, rd)
+    assert len({bytes(x) for x in d[v]}) > 0.9 * v.sum()  # the descriptors are informative, not constant
+
+
+def test_hamming_matcher_equals_the_oracle_and_cv2(ctx):
+    """hamming_nearest_kernel x 2 + cross-check against the C restatement, which tests/test_oracle_tracker.py pins on cv2.BFMatcher: random
+    descriptors, descriptors with few distinct values (many ties: first index wins), more queries than trains and the reverse."""
+    rng = np.random.default_rng(9)
+    for nq, nt, mask in [(40, 300, 0xFF), (300, 40, 0xFF), (64, 64, 0x03), (1, 500, 0xFF), (200, 1, 0x0F), (150, 2500, 0xFF)]:
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8) & mask
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8) & mask
+        if mask != 0xFF:
+            q[:, 2:] = 0
+            t[:, 2:] = 0
+        assert ctx.hamming_match(q, t) == T.bf_match_crosscheck(q, t)

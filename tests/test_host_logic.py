@@ -90,7 +90,7 @@ def test_config_files_parse_with_comments_and_camera_models(hh):
         hh.hh_destroy(h)
 
 
-@pytest.mark.parametrize("key,value,needle", [("use_OOS", True, "MSCKF"), ("use_1pt_RANSAC", True, "1pt_RANSAC"),
+@pytest.mark.parametrize("key,value,needle", [("use_OOS", True, "MSCKF"),
                                                ("integration_method", "Euler", "integration method"), ("covariance_update", "fp16", "covariance_update")])
 def test_unsupported_options_fail_loudly_at_creation(hh, key, value, needle):
     cfg = sim.load_cfg(os.path.join(CFG, "pcw_sim.json"))
@@ -394,7 +394,7 @@ REFERENCE_CFG = "/root/reference/cfg"
 # (None = accepted; otherwise a fragment of the refusal).  DESIGN.md §8 discusses every entry.
 SHIPPED = {
     "pcw.json": None, "pcw_loops.json": None, "phab.json": None, "tumvi_cam1.json": None,
-    "tumvi_cam0.json": "match_dropped_tracks", "void_params.json": "1pt_RANSAC",
+    "tumvi_cam0.json": "match_dropped_tracks", "void_params.json": "Wsb",  # stale in the reference itself: state keys W / T / V (its use_1pt_RANSAC is accepted: Estimator::OnePointRANSAC is built)
     "phab_calibration.json": "json",        # stale in the reference itself: `"method": 1`, state keys W / T / V
     "void_params_calib.json": "Wsb",        # stale in the reference itself: state keys W / T / V
     "tumvi_tracker_only_cam0.json": "match_dropped_tracks", "tumvi_tracker_only_cam1.json": None,  # (LMEDS outlier rejection on, descriptor rescue off)

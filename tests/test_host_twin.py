@@ -56,6 +56,11 @@ def hh(tmp_path_factory):
     lib.hh_just_dropped.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.hh_after_subfilter.argtypes = [C.c_void_p, C.c_void_p]
     lib.hh_after_gate.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_after_gate_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hh_ransac_info.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    lib.hh_ransac_temp.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_ransac_finish.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hh_ransac_rejected.argtypes = [C.c_void_p]
     lib.hh_after_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.hh_features.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.hh_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -82,14 +87,28 @@ class Recorder:
             self.sub.append(np.concatenate([np.asarray(r[0], float).ravel(), np.asarray(r[1], float).ravel(), [float(r[2])]]))
             return r
 
+        self.in_ransac = False
+        ransac0 = est.one_point_ransac
+
         def mh(*a, **k):
             d = mh0(*a, **k)
-            self.mh.append(float(d))
+            if not self.in_ransac:  # (the distances and the temporary correction of the 1-point RANSAC are read from est.ransac_trace)
+                self.mh.append(float(d))
             return d
 
         def absorb(err, *a, **k):
-            self.err = np.array(err, float).copy()
+            if not self.in_ransac:
+                self.err = np.array(err, float).copy()
             return absorb0(err, *a, **k)
+
+        def ransac(*a, **k):
+            self.in_ransac = True
+            try:
+                return ransac0(*a, **k)
+            finally:
+                self.in_ransac = False
+
+        est.one_point_ransac = ransac
 
         def adapt(*a, **k):
             self.P = est.P.copy()  # P after the update (or after this frame's slot edits when nothing was updated)
@@ -132,7 +151,12 @@ TWIN_CASES = [(4, 14, 4.0, 1, True, "PrinceDormand", None), (15, 30, 3.0, 0, Tru
               (4, 14, 4.0, 21, True, "PrinceDormand", _dopt(False, True)), (15, 30, 4.0, 22, True, "PrinceDormand", _dopt(True, True)),
               (4, 14, 3.0, 23, True, "RK4", _dopt(True, False)),
               # all views without the Hessian covariance: diverged candidates reach the gate with NaN Jacobians and are rejected there
-              (4, 14, 4.0, 21, True, "PrinceDormand", _dopt(False, False))]
+              (4, 14, 4.0, 21, True, "PrinceDormand", _dopt(False, False)),
+              # filter-level 1-point RANSAC (update.cpp:213-393): pass-through, every high-innovation feature rescued, rejections (two groups affected at once)
+              (4, 14, 4.0, 31, True, "PrinceDormand", {"use_1pt_RANSAC": True}),
+              (4, 14, 4.0, 32, True, "PrinceDormand", {"use_1pt_RANSAC": True, "1pt_RANSAC_thresh": 0.8}),
+              (15, 30, 4.0, 34, True, "PrinceDormand", {"use_1pt_RANSAC": True, "1pt_RANSAC_thresh": 1.5, "sim_outliers": {"fraction": 0.08, "pixels": 2.5}}),
+              (4, 14, 4.0, 35, True, "RK4", {"use_1pt_RANSAC": True, "1pt_RANSAC_thresh": 2.0, "1pt_RANSAC_Chi2": 3.0, "sim_outliers": {"fraction": 0.1, "pixels": 3.5}})]
 # XIVO_TWIN_SWEEP=n adds n more seeds x both state sizes x with/without simulated depths (a wider offline sweep; 48 extra sequences passed at n = 12)
 for _s in range(int(os.environ.get("XIVO_TWIN_SWEEP", "0"))):
     for _g, _f in ((4, 14), (15, 30)):
@@ -159,7 +183,7 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, t
     # the oracle executes a message inside InertialMeas / VisualMeasPointCloud once its heap releases one; mirror that with the
     # product's own heap (hh_push / hh_pop) so that both execute the same message at the same step
     payload = {}
-    n_vis = n_upd = 0
+    n_vis = n_upd = n_ransac = n_ransac_rejected = 0
     for k, (kind, ts, p) in enumerate(msgs):
         payload[k] = (kind, ts, p)
         # ---- oracle
@@ -212,7 +236,26 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, t
             if gated:
                 assert ninst == len(rec.mh), f"frame {n_vis}: {ninst} in-state features vs {len(rec.mh)} gated by the oracle"
             mh = np.ascontiguousarray(rec.mh if gated else np.zeros(max(1, ninst)), dtype=np.float64)
-            nupd = hh.hh_after_gate(h, mh.ctypes.data)
+            if cfg.get("use_1pt_RANSAC"):
+                tr_ = est.ransac_trace
+                diag0 = np.ascontiguousarray(tr_["diag"] if tr_ else np.diag(est.P))  # the diagonal only matters when the RANSAC phases run
+                nupd = hh.hh_after_gate_diag(h, mh.ctypes.data, diag0.ctypes.data)
+                assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
+                assert (nupd == -1) == (tr_ is not None), f"frame {n_vis}: the product {'runs' if nupd == -1 else 'skips'} the RANSAC phases, the oracle does not agree"
+                if nupd == -1:
+                    n_ransac += 1
+                    tab, lo, hi, zp = np.zeros(64, np.int32), np.zeros(64, np.int32), np.zeros(64, np.int32), np.zeros(128, np.int32)
+                    nl, nh, nz = C.c_int(), C.c_int(), C.c_int()
+                    nt = hh.hh_ransac_info(h, tab.ctypes.data, lo.ctypes.data, C.addressof(nl), hi.ctypes.data, C.addressof(nh), zp.ctypes.data, C.addressof(nz))
+                    assert lo[: nl.value].tolist() == tr_["low"] and hi[: nh.value].tolist() == tr_["high"], f"frame {n_vis}: low / high innovation sets"
+                    e_tmp = np.ascontiguousarray(tr_["err"] if tr_["err"] is not None else np.zeros(N))
+                    hh.hh_ransac_temp(h, e_tmp.ctypes.data)
+                    mh_tab = np.ascontiguousarray([tr_["mh"].get(int(i), 0.0) for i in tab[:nt]] + [0.0])
+                    nupd = hh.hh_ransac_finish(h, mh_tab.ctypes.data)
+                    n_ransac_rejected += hh.hh_ransac_rejected(h)
+                    assert hh.hh_ransac_rejected(h) == est.num_oneptransac_rejected
+            else:
+                nupd = hh.hh_after_gate(h, mh.ctypes.data)
             assert hh.hh_sticky_error(h) == 0, hh.hh_error_msg(h)
             had = rec.err is not None
             assert (nupd > 0) == had, f"frame {n_vis}"
@@ -249,6 +292,10 @@ def test_host_state_machine_follows_the_oracle_frame_by_frame(hh, monkeypatch, t
         assert np.abs(m[:9].reshape(3, 3) - est.X.Rsb).max() <= 1e-10 and np.abs(m[9:12] - est.X.Tsb).max() <= 1e-10, f"message {k}"
         assert np.abs(m[12:15] - est.X.Vsb).max() <= 1e-10 and hh.hh_curr_time(h) == est.curr_time
     assert n_vis >= 60 and n_upd >= 50 and len(est.instate_features) >= min(F, 10)
+    if over and over.get("sim_outliers"):
+        assert n_ransac >= 10 and n_ransac_rejected >= 3, "the RANSAC cases must exercise the temporary update and rejections"
+    elif over and over.get("use_1pt_RANSAC") and over.get("1pt_RANSAC_thresh", 5) < 1:
+        assert n_ransac >= 10
     gb2 = (C.c_int * 2)()
     hh.hh_triangulation_counts(h, gb2)
     assert (gb2[0], gb2[1]) == (est.num_good_tri, est.num_bad_tri)

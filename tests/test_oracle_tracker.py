@@ -110,3 +110,47 @@ def test_homography_sampling_kernel_and_ransac_loop_match_cv2():
         _H, mc = cv2.findHomography(p0, p1, cv2.RANSAC, 3.0, maxIters=200, confidence=0.995)
         ok, mo = HO.find_homography_mask(p0, p1, HO.RANSAC, 3.0, 200, 0.995)
         assert np.array_equal(np.zeros(n, np.uint8) if mc is None else mc.ravel(), mo)
+
+
+def test_cross_checked_hamming_matcher_matches_cv2_bfmatcher():
+    """orc_bf_match_crosscheck against cv2.BFMatcher(NORM_HAMMING, crossCheck=True).knnMatch(q, t, 1): same (query, train, distance)
+    triples, also with few distinct descriptor values (ties: the first index wins on both sides of the cross-check) -- the matcher the
+    reference calls at src/tracker.cpp:261-262 and :378-379.  (The descriptor VALUES of the BRIEF restatement are parity-unpinned:
+    opencv_contrib's test table is not available; scripts/make_brief_pattern.py.)"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        nq, nt, nb = int(rng.integers(1, 40)), int(rng.integers(1, 60)), int(rng.integers(1, 5))
+        q = rng.integers(0, 256, (nq, nb), dtype=np.uint8)
+        t = rng.integers(0, 256, (nt, nb), dtype=np.uint8)
+        if trial % 3 == 0:
+            q &= 0x03
+            t &= 0x03
+        m = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).knnMatch(q, t, k=1)
+        ref = [(x[0].queryIdx, x[0].trainIdx, int(x[0].distance)) for x in m if len(x)]
+        assert T.bf_match_crosscheck(q, t) == ref, f"trial {trial}"
+
+
+def test_brief_restatement_properties():
+    """Own-table BRIEF-32: border rule of KeyPointsFilter::runByImageBorder (28 px), (int)(pt + 0.5) rounding, bit order, and the box sums
+    against a numpy integral image (what opencv_contrib reads its smoothed values from)."""
+    from xivo_b200 import synth
+
+    a, _ = synth.frame_pair(200, 260, seed=3)
+    kp = np.array([[100.2, 120.7], [10, 10], [231.9, 50], [232.0, 50], [28, 28], [27.99, 100], [100.49, 120.5], [100.5, 120.49]], np.float32)
+    d, v = T.brief(a, kp)
+    assert v.tolist() == [True, False, True, False, True, False, True, True]
+    assert not d[1].any() and d[0].any()
+    assert np.array_equal(d[6], T.brief(a, np.array([[100, 121]], np.float32))[0][0])  # (int)(x + .5): 100.49 -> 100, 120.5 -> 121
+    assert np.array_equal(d[7], T.brief(a, np.array([[101, 120]], np.float32))[0][0])
+    # independent evaluation through an integral image
+    import re
+    pat = np.array([[int(x) for x in m] for m in re.findall(r"\{(-?\d+), (-?\d+), (-?\d+), (-?\d+)\}", open(os.path.join(os.path.dirname(__file__), "..", "xivo_b200", "csrc", "brief_pattern.h")).read())])
+    assert pat.shape == (256, 4) and np.abs(pat).max() <= 19
+    S = np.zeros((201, 261), np.int64)
+    S[1:, 1:] = a.astype(np.int64).cumsum(0).cumsum(1)
+    box = lambda x, y: S[y + 5, x + 5] - S[y - 4, x + 5] - S[y + 5, x - 4] + S[y - 4, x - 4]
+    cx, cy = 100, 121
+    bits = [int(box(cx + p[0], cy + p[1]) < box(cx + p[2], cy + p[3])) for p in pat]
+    want = np.packbits(np.array(bits, np.uint8))  # MSB first = test 8 i + k -> bit 7 - k
+    assert np.array_equal(d[0], want)

@@ -166,6 +166,24 @@ class Context:
         )
         return mh
 
+    def brief_describe(self, img, kp_xy):
+        """BRIEF-32 at the keypoints (n x 2) -> (descriptors n x 32 uint8, valid n bool)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        rows, cols = img.shape[:2]
+        cn = 1 if img.ndim == 2 else img.shape[2]
+        kp = np.ascontiguousarray(kp_xy, dtype=np.float32).reshape(-1, 2)
+        n = len(kp)
+        desc, valid = np.zeros((max(n, 1), 32), np.uint8), np.zeros(max(n, 1), np.uint8)
+        _check(lib().xivo_brief_describe(self._h, _p(img), rows, cols, cn, _p(kp), n, _p(desc), _p(valid)), "xivo_brief_describe")
+        return desc[:n], valid[:n].astype(bool)
+
+    def hamming_match(self, query, train):
+        """Cross-checked 1-NN Hamming matches of 32-byte descriptors -> [(queryIdx, trainIdx, distance)] in query order."""
+        q, t = np.ascontiguousarray(query, np.uint8).reshape(-1, 32), np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        out, n = np.zeros((max(len(q), 1), 3), np.int32), C.c_int()
+        _check(lib().xivo_hamming_match(self._h, _p(q), len(q), _p(t), len(t), _p(out), C.byref(n)), "xivo_hamming_match")
+        return [tuple(int(v) for v in r) for r in out[: n.value]]
+
     def ekf_update(self, H, P, inn, diagR, tf32x3=False):
         """UpdateJosephForm; tf32x3=True runs the covariance downdate on the tensor cores (XIVO_UPDATE_TF32X3)."""
         H, inn, diagR = _f64(H), _f64(inn), _f64(diagR)

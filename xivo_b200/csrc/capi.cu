@@ -148,6 +148,54 @@ int xivo_fast_detect(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int 
   return XIVO_OK;
 }
 
+int xivo_brief_describe(xivo_ctx* ctx, const uint8_t* img, int rows, int cols, int cn, const float* kp_xy, int n, uint8_t* desc, uint8_t* valid) {
+  API_BEGIN;
+  XB_REQUIRE(img && rows > 0 && cols > 0 && (cn == 1 || cn == 3) && n >= 0 && (n == 0 || (kp_xy && desc && valid)), "brief_describe: bad arguments");
+  if (n == 0) return XIVO_OK;
+  cudaStream_t st = ctx->stream;
+  DevBuf<uint8_t> dimg((size_t)rows * cols * cn), ddesc((size_t)n * 32), dvalid(n);
+  DevBuf<float> dkp((size_t)n * 2);
+  DevBuf<int> dn(1);
+  XB_REQUIRE(dimg.ok() && ddesc.ok() && dvalid.ok() && dkp.ok() && dn.ok(), "cudaMalloc failed");
+  XB_CUDA(cudaMemcpyAsync(dimg.p, img, (size_t)rows * cols * cn, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dkp.p, kp_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dn.p, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (int rc = launch_brief(st, dimg.p, 0, nullptr, rows, cols, cn, dkp.p, dn.p, n, ddesc.p, dvalid.p, 1)) return rc;
+  g_launches += 1;
+  XB_CUDA(cudaMemcpyAsync(desc, ddesc.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(valid, dvalid.p, n, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  return XIVO_OK;
+}
+
+int xivo_hamming_match(xivo_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int* out3, int* n_out) {
+  API_BEGIN;
+  XB_REQUIRE(n_out && nq >= 0 && nt >= 0 && (nq == 0 || query) && (nt == 0 || train) && (nq == 0 || out3), "hamming_match: bad arguments");
+  *n_out = 0;
+  if (nq == 0 || nt == 0) return XIVO_OK;
+  cudaStream_t st = ctx->stream;
+  DevBuf<uint8_t> dq((size_t)nq * 32), dt((size_t)nt * 32);
+  DevBuf<int> dn(2), bt(nq), bd(nq), bq(nt), bqd(nt);
+  XB_REQUIRE(dq.ok() && dt.ok() && dn.ok() && bt.ok() && bd.ok() && bq.ok() && bqd.ok(), "cudaMalloc failed");
+  const int n2[2] = {nq, nt};
+  XB_CUDA(cudaMemcpyAsync(dq.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dt.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+  XB_CUDA(cudaMemcpyAsync(dn.p, n2, sizeof(n2), cudaMemcpyHostToDevice, st));
+  if (int rc = launch_hamming_nearest(st, dq.p, dn.p, nq, dt.p, dn.p + 1, nt, bt.p, bd.p, 1)) return rc;   // nearest train of every query
+  if (int rc = launch_hamming_nearest(st, dt.p, dn.p + 1, nt, dq.p, dn.p, nq, bq.p, bqd.p, 1)) return rc;  // nearest query of every train
+  g_launches += 2;
+  std::vector<int> hbt(nq), hbd(nq), hbq(nt);
+  XB_CUDA(cudaMemcpyAsync(hbt.data(), bt.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(hbd.data(), bd.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaMemcpyAsync(hbq.data(), bq.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, st));
+  XB_CUDA(cudaStreamSynchronize(st));
+  int m = 0;
+  for (int i = 0; i < nq; ++i)
+    if (hbt[i] >= 0 && hbq[hbt[i]] == i) { out3[3 * m] = i; out3[3 * m + 1] = hbt[i]; out3[3 * m + 2] = hbd[i]; ++m; }
+  *n_out = m;
+  return XIVO_OK;
+}
+
 int xivo_lk_track(xivo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int rows, int cols, int cn, const float* prev_pts,
                   float* next_pts, uint8_t* status, float* err, int npts, int win, int max_level, int max_iter, double eps,
                   int use_initial_flow, double min_eig_threshold) {

@@ -117,11 +117,13 @@ __global__ void __launch_bounds__(JG_MAX_WARPS * 32) jacobian_gate_kernel(EkfLay
                                                            const double* __restrict__ Rmeas, FeatJac* __restrict__ out,
                                                            double* __restrict__ J_dense, double* __restrict__ mh_out,
                                                            const EditOp* __restrict__ ops, const int* __restrict__ ops_first,
-                                                           const int* __restrict__ nops) {
+                                                           const int* __restrict__ nops, double* __restrict__ diag_out) {
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int N = lay.N();
   double* __restrict__ Pb = P + (size_t)b * N * N;
   if (ops) apply_edits(N, Pb, ops + ops_first[b], nops[b], threadIdx.x, blockDim.x);  // uniform over the CTA (barriers inside)
+  if (diag_out)  // diagonal of P after this frame's edits (FindNewRefGroup of the 1-point RANSAC reads it on the host)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) diag_out[(size_t)b * N + i] = Pb[(size_t)i * N + i];
   __shared__ FeatJac sjs[JG_MAX_WARPS];
   FeatJac& sj = sjs[warp];
   const int nf = nfeat[b];
@@ -173,11 +175,11 @@ __global__ void __launch_bounds__(JG_MAX_WARPS * 32) jacobian_gate_kernel(EkfLay
 int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam, const double* X, const double* groups,
                          const double* feat_x, const double* feat_xp, const int* feat_ref, const int* feat_sind,
                          const int* nfeat, double* P, const double* Rmeas, FeatJac* out, double* J_dense, double* mh_out,
-                         int batch, const EditOp* ops, const int* ops_first, const int* nops) {
+                         int batch, const EditOp* ops, const int* ops_first, const int* nops, double* diag_out) {
   ProfScope ps("jacobian_gate", st);
   const int warps = std::max(1, std::min(lay.F, JG_MAX_WARPS));
   jacobian_gate_kernel<<<batch, warps * 32, 0, st>>>(lay, cam, X, groups, feat_x, feat_xp, feat_ref, feat_sind, nfeat, P, Rmeas, out,
-                                                     J_dense, mh_out, ops, ops_first, nops);
+                                                     J_dense, mh_out, ops, ops_first, nops, diag_out);
   XB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(GAIN_THREADS) ekf_gain_kernel(int N, EkfLayout
                                                                 double* __restrict__ Kt, double* __restrict__ H_dense, int Mmax,
                                                                 const EditOp* __restrict__ ops, const int* __restrict__ ops_first,
                                                                 const int* __restrict__ nops, uint32_t* __restrict__ kt32,
-                                                                uint32_t* __restrict__ hp32, int Npad, int KCmax) {
+                                                                uint32_t* __restrict__ hp32, int Npad, int KCmax, int full_j) {
   extern __shared__ __align__(16) double sm[];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int M = SPARSE ? 2 * nsel[b] : Mdense;
@@ -233,9 +235,12 @@ __global__ void __launch_bounds__(GAIN_THREADS) ekf_gain_kernel(int N, EkfLayout
       const int r = t / kHnnz, k = t - r * kHnnz;
       const FeatJac& f = jac[(size_t)b * lay.F + sel[(size_t)b * lay.F + (r >> 1)]];
       // FillJacobianBlock: H(:, goff:goff+3) <- J(:, goff+3:goff+6); H(:, goff+3:goff+6) stays 0
+      // full_j: the rows of J() as they are (OnePointRANSAC's low-innovation update, update.cpp:318-330)
       double v = f.J[r & 1][k];
-      if (k >= 12 && k < 15) v = f.J[r & 1][k + 3];
-      else if (k >= 15 && k < 18) v = 0.0;
+      if (!full_j) {
+        if (k >= 12 && k < 15) v = f.J[r & 1][k + 3];
+        else if (k >= 15 && k < 18) v = 0.0;
+      }
       Hval[t] = v;
       Hcol[t] = jac_col(k, f.goff, f.foff);
       if (k == 0) inn[r] = f.inn[r & 1];
@@ -414,7 +419,7 @@ static size_t gain_smem(int Mmax, bool sparse) {
 
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel, const double* Rmeas,
                       double* P, double* err, double* HP, double* Kt, double* H_dense, int batch, int tensor_core, const EditOp* ops,
-                      const int* ops_first, const int* nops, const TcOperands* tc) {
+                      const int* ops_first, const int* nops, const TcOperands* tc, int full_j) {
   const int N = lay.N(), Mmax = 2 * lay.F;
   const size_t smem = gain_smem(Mmax, true);
   XB_REQUIRE(smem <= 227 * 1024, "EKF update: 2*F too large for the shared-memory Cholesky");
@@ -429,7 +434,7 @@ int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const 
   const bool tc2 = tensor_core && tc && tc->kt32;
   ekf_gain_kernel<true><<<batch, GAIN_THREADS, smem, st>>>(N, lay, jac, sel, nsel, 0, nullptr, nullptr, nullptr, Rmeas, P, err, HP,
                                                           Kt, H_dense, Mmax, ops, ops_first, nops, tc2 ? tc->kt32 : nullptr, tc2 ? tc->hp32 : nullptr,
-                                                          tc2 ? tc->Npad : 0, tc2 ? tc->KCmax : 0);
+                                                          tc2 ? tc->Npad : 0, tc2 ? tc->KCmax : 0, full_j);
   Prof::get().stop(pi_, st);
   if (tc2) return launch_ekf_cov_tc2(st, N, nsel, 0, *tc, P, batch);
   if (tensor_core) return launch_ekf_cov_tc(st, N, nsel, 0, Mmax, HP, Kt, P, batch);
@@ -453,7 +458,7 @@ int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, cons
     ProfScope pg("ekf_gain", st);
     ekf_gain_kernel<false><<<batch, GAIN_THREADS, smem, st>>>(N, lay, nullptr, nullptr, nullptr, M, H, diagR, inn, nullptr, P, err,
                                                              HP, Kt, nullptr, M, nullptr, nullptr, nullptr, tc2 ? tc->kt32 : nullptr,
-                                                             tc2 ? tc->hp32 : nullptr, tc2 ? tc->Npad : 0, tc2 ? tc->KCmax : 0);
+                                                             tc2 ? tc->hp32 : nullptr, tc2 ? tc->Npad : 0, tc2 ? tc->KCmax : 0, 0);
   }
   if (tc2) return launch_ekf_cov_tc2(st, N, nullptr, M, *tc, P, batch);
   if (tensor_core) return launch_ekf_cov_tc(st, N, nullptr, M, M, HP, Kt, P, batch);

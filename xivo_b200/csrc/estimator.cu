@@ -229,6 +229,9 @@ class Batch {
   xivo_ctx* ctx;
   int B, N, maxops, max_sub;
   int cov_tc = 0;  // covariance downdate on the tensor cores ("covariance_update": "tf32x3")
+  bool use_1pt = false;       // filter-level 1-point RANSAC: the gate phase also returns diag(P), two extra device phases on demand
+  double* dP0 = nullptr;      // P_ backup of OnePointRANSAC (BackupState / RestoreState), allocated at the first use
+  std::vector<std::vector<Feature*>> table_order;  // per sequence: index space of the device feature table of this frame
   TcOperands tcops;  // its TF32 operand buffers + tensor maps (ekf_cov_tc2_kernel); XIVO_TC_V1=1 keeps the first formulation
   uint32_t *dKt32 = nullptr, *dHP32 = nullptr;
   EkfLayout lay;
@@ -306,6 +309,8 @@ class Batch {
     cudaEventCreateWithFlags(&wait_ev, cudaEventDisableTiming | (lane_mode ? cudaEventBlockingSync : 0));
     for (int b = 0; b < B; ++b) est.emplace_back(new Estimator(cfg, lay, tracker_only));
     cov_tc = est[0]->c.cov_update_tf32x3 ? 1 : 0;
+    use_1pt = est[0]->c.use_1pt_RANSAC;
+    table_order.resize(B);
     maxops = 4 * (lay.F + lay.G) + 16;
     max_sub = est[0]->tc.num_features_max + 8;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&dP), sizeof(double) * B * N * N) == cudaSuccess &&
@@ -313,7 +318,7 @@ class Batch {
               cudaMalloc(reinterpret_cast<void**>(&dKt), sizeof(double) * B * 2 * lay.F * N) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dErr), sizeof(double) * B * N) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&dJac), sizeof(FeatJac) * B * lay.F) == cudaSuccess;
-    ok = ok && cam.alloc(B) && R.alloc(B) && mh.alloc((size_t)B * lay.F) && pack.alloc((size_t)B * (2 * N + 529)) && sub_out.alloc((size_t)B * max_sub) &&
+    ok = ok && cam.alloc(B) && R.alloc(B) && mh.alloc((size_t)B * lay.F + (size_t)B * N) && pack.alloc((size_t)B * (2 * N + 529)) && sub_out.alloc((size_t)B * max_sub) &&
          icst.alloc(B) && tk1.alloc() && tk2.alloc();
     if (ok) {  // the per-phase upload blobs and the table views inside them
       struct Carve {
@@ -408,7 +413,7 @@ class Batch {
     if (wait_ev) cudaEventDestroy(wait_ev);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
     for (cudaEvent_t e : ring_ev) cudaEventDestroy(e);
-    for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr, (void*)dKt32, (void*)dHP32})
+    for (void* p : {(void*)dP, (void*)dHP, (void*)dKt, (void*)dErr, (void*)dJac, (void*)dRing, (void*)dPyr, (void*)dKt32, (void*)dHP32, (void*)dP0})
       if (p) cudaFree(p);
     cam.release(); R.release(); mh.release(); pack.release(); sub_out.release(); blobS.release(); blobJ.release(); blobU.release();
     blobI[0].release(); blobI[1].release(); tk1.release(); tk2.release();
@@ -1034,6 +1039,90 @@ class Batch {
     return 0;
   }
 
+  // Estimator::OnePointRANSAC (update.cpp:213-393) for the sequences whose gate found high-innovation inliers: back up P (and the
+  // Jacobians), temporary update with the low-innovation rows of J() on the covariance with the high-innovation rows zeroed, Jacobians +
+  // Mahalanobis distances of the in-state features at the temporarily absorbed motion state, restore.  Sequences that do not need it
+  // take part with empty tables.
+  int ransac_phases(const std::vector<int>& full) {
+    cudaStream_t st = st2;
+    HostScope hs("ransac_phases");
+    std::vector<int> act;
+    for (int b : full)
+      if (est[b]->ransac.active) act.push_back(b);
+    if (!dP0) XB_CUDA(cudaMalloc(reinterpret_cast<void**>(&dP0), sizeof(double) * B * N * N));
+    for (int b : act)  // BackupState
+      XB_CUDA(cudaMemcpyAsync(dP0 + (size_t)b * N * N, dP + (size_t)b * N * N, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
+    // ---- phase 1: the low-innovation update
+    for (int b = 0; b < B; ++b) { nsel.h[b] = 0; nopsU.h[b] = 0; firstU.h[b] = 0; }
+    int nops_total = 0;
+    for (int b : act) {
+      Estimator& e = *est[b];
+      firstU.h[b] = nops_total;
+      nopsU.h[b] = (int)e.ransac.zero_edits.size();
+      if (nops_total + nopsU.h[b] > (int)opsU.n) return fail(XIVO_ERR_STATE, "covariance edit list overflow (1-point RANSAC)");
+      for (const EditOp& op : e.ransac.zero_edits) opsU.h[nops_total++] = op;
+      int k = 0;
+      for (size_t i = 0; i < e.ransac.mh_inliers.size(); ++i) {
+        if (!e.ransac.low[i]) continue;
+        const auto it = std::find(table_order[b].begin(), table_order[b].end(), e.ransac.mh_inliers[i]);
+        sel.h[(size_t)b * lay.F + k++] = (int)(it - table_order[b].begin());
+      }
+      nsel.h[b] = k;
+    }
+    XB_CUDA(up_blob(blobU, blobU_fixed + (size_t)nops_total * sizeof(EditOp), st));
+    if (int rc = launch_ekf_update(st, lay, dJac, sel.d, nsel.d, R.d, dP, dErr, dHP, dKt, nullptr, B, 0, opsU.d, firstU.d, nopsU.d, nullptr, 1)) return rc;
+    if (int rc = launch_pack_state(st, N, dP, dErr, pack.d, B)) return rc;
+    g_launches += 3;
+    XB_CUDA(pack.down(st));
+    if (int rc = wait(st)) return rc;
+    for (int b : act) {
+      Estimator& e = *est[b];
+      const double* pk = pack.h + (size_t)b * (2 * N + 529);
+      if (nsel.h[b] && !(pk[0] == pk[0])) { e.error = XIVO_ERR_STATE; e.error_msg = "innovation covariance not positive definite (1-point RANSAC)"; continue; }
+      e.ransac_after_temp_update(pk);
+      double* Xh = X.h + (size_t)b * kPoseDoubles;
+      memcpy(Xh, e.X.Rsb.m, 72); memcpy(Xh + 9, e.X.Tsb.v, 24); memcpy(Xh + 12, e.X.Rbc.m, 72); memcpy(Xh + 21, e.X.Tbc.v, 24);
+    }
+    if (int rc = first_error(full)) return rc;
+    // ---- phase 2: Jacobians and r' (J P J' + R)^-1 r at the temporary state (features and groups did not move: their tables are still on the device)
+    std::vector<int> nfeat_saved(B);
+    for (int b = 0; b < B; ++b) { nfeat_saved[b] = nfeat.h[b]; nfeat.h[b] = 0; nopsJ.h[b] = 0; firstJ.h[b] = 0; }
+    for (int b : act) nfeat.h[b] = nfeat_saved[b];
+    XB_CUDA(up_blob(blobS, blobS_fixed, st));
+    XB_CUDA(up_blob(blobJ, blobJ_fixed, st));
+    if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B, opsJ.d, firstJ.d, nopsJ.d,
+                                      nullptr))
+      return rc;
+    g_launches += 1;
+    XB_CUDA(mh.down(st, (size_t)B * lay.F));
+    for (int b : act)  // RestoreState (stream order: after the kernel above)
+      XB_CUDA(cudaMemcpyAsync(dP + (size_t)b * N * N, dP0 + (size_t)b * N * N, sizeof(double) * N * N, cudaMemcpyDeviceToDevice, st));
+    if (int rc = wait(st)) return rc;
+    for (int b : act) est[b]->ransac_finish(mh.h + (size_t)b * lay.F, table_order[b]);
+    if (int rc = first_error(full)) return rc;
+    // ---- phase 3: the survivors' Jacobians at the restored state (update.cpp:381-385), from their CURRENT owner and local state
+    for (int b : act) {
+      Estimator& e = *est[b];
+      for (size_t k = 0; k < e.ransac.jalive.size() && (int)k < lay.F; ++k) {
+        if (!e.ransac.jalive[k]) continue;
+        const size_t fi = (size_t)b * lay.F + k;
+        memcpy(fx.h + 3 * fi, &e.ransac.jx[3 * k], 24);
+        fref.h[fi] = e.ransac.jref[k];
+        fsind.h[fi] = e.ransac.jsind[k];
+      }
+      double* Xh = X.h + (size_t)b * kPoseDoubles;
+      memcpy(Xh, e.X.Rsb.m, 72); memcpy(Xh + 9, e.X.Tsb.v, 24); memcpy(Xh + 12, e.X.Rbc.m, 72); memcpy(Xh + 21, e.X.Tbc.v, 24);
+    }
+    XB_CUDA(up_blob(blobS, blobS_fixed, st));
+    XB_CUDA(up_blob(blobJ, blobJ_fixed, st));  // (nfeat still selects the active sequences only)
+    if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B, opsJ.d, firstJ.d, nopsJ.d,
+                                      nullptr))
+      return rc;
+    g_launches += 1;
+    for (int b = 0; b < B; ++b) nfeat.h[b] = nfeat_saved[b];
+    return 0;
+  }
+
   // ---- one visual message per active sequence ----------------------------------------------
   int process_visual(const std::vector<int>& act_in, std::vector<Msg>& msgs) {
     cudaStream_t st = st2;  // covariance-side stream; the image tracker uses ctx->stream
@@ -1167,7 +1256,7 @@ class Batch {
     // one copy: [nfeat | nops | first | fref | fsind | fxp | fx | groups | packed edit list]; the kernel applies the edits, then the features
     XB_CUDA(up_blob(blobJ, blobJ_fixed + (size_t)nops_total * sizeof(EditOp), st));
     if (int rc = launch_jacobian_gate(st, lay, cam.d, X.d, groups.d, fx.d, fxp.d, fref.d, fsind.d, nfeat.d, dP, R.d, dJac, nullptr, mh.d, B, opsJ.d,
-                                      firstJ.d, nopsJ.d))
+                                      firstJ.d, nopsJ.d, use_1pt ? mh.d + (size_t)B * lay.F : nullptr))
       return rc;
     g_launches += 1;
     {
@@ -1175,7 +1264,7 @@ class Batch {
       for (int b : full) nf += nfeat.h[b];
       Prof::get().add_work("jacobian_gate", nf * 2.0 * N * 8.0);  // §8d: M N 8 bytes of H written
     }
-    XB_CUDA(mh.down(st));
+    XB_CUDA(mh.down(st, use_1pt ? 0 : (size_t)B * lay.F));  // [Mahalanobis distances | with the 1-point RANSAC: diag(P) after the edits]
     hs_issue.reset();
     { HostScope hw("wait_jacobian"); if (int rc = wait(st)) return rc; }
     // ---- gating decisions (host), post-gate edits, update (device) ----
@@ -1184,9 +1273,25 @@ class Batch {
       for (int b = 0; b < B; ++b) nsel.h[b] = 0;
       pfor(full, [&](int b, int) {
         Estimator& e = *est[b];
-        const std::vector<Feature*> order = e.instate_features;  // index space of mh / the device feature table
-        e.update_step_after_gate(mh.h + (size_t)b * lay.F);
+        table_order[b] = e.instate_features;  // index space of mh / the device feature table
+        e.update_step_after_gate(mh.h + (size_t)b * lay.F, use_1pt ? mh.h + (size_t)B * lay.F + (size_t)b * N : nullptr);
+      });
+      if (int rc = first_error(full)) return rc;
+    }
+    if (use_1pt) {  // Estimator::OnePointRANSAC's two device phases for the sequences whose gate asked for them (ransac.active)
+      bool any = false;
+      for (int b : full) any = any || est[b]->ransac.active;
+      if (any) {
+        hs_issue.reset();
+        if (int rc = ransac_phases(full)) return rc;
+      }
+    }
+    {
+      HostScope hs("gating");
+      pfor(full, [&](int b, int) {
+        Estimator& e = *est[b];
         if (e.error) return;
+        const std::vector<Feature*>& order = table_order[b];
         int k = 0;
         for (Feature* f : e.in_update) {
           const auto it = std::find(order.begin(), order.end(), f);
@@ -1764,7 +1869,7 @@ int xivo_get_tracker_counters(xivo_batch* b, int seq, int out[4]) {
   out[0] = e.num_outliers_rejected;  // Tracker::num_rejected_outliers()
   out[1] = e.num_failed_to_track;
   out[2] = e.num_new_detections;
-  out[3] = 0;  // num_oneptransac_rejected: use_1pt_RANSAC fails at creation
+  out[3] = e.num_oneptransac_rejected;
   return 0;
 }
 int xivo_scale_init_velocity(xivo_batch* b, int seq, double scale) {  // Estimator::ScaleInitVelocity: X_.Vsb /= scale

@@ -77,6 +77,11 @@ struct Feature {
   double outlier_counter = 0;
   bool tri_ok = false;
   float response = 0.f;
+  // descriptor path (Feature::descriptor(), Feature::keypoint(), feature.h:50-56): the BRIEF-32 bytes set at detection (replaced every frame
+  // when `differential`) and the pixel of the keypoint the feature was created from
+  uint8_t descriptor[32] = {0};
+  bool has_descriptor = false;
+  float kp0[2] = {0, 0};
   // Track: only front() (two-view triangulation), back() and the length are ever read on this path (the full
   // history feeds the OOS update, out of scope).
   std::array<double, 2> first_xp{{0, 0}}, last_xp{{0, 0}};
@@ -101,6 +106,7 @@ struct Feature {
     for (double& p : P) p = 0;
     pred[0] = pred[1] = -1;
     outlier_counter = 0; tri_ok = false; response = 0.f;
+    has_descriptor = false; kp0[0] = (float)u; kp0[1] = (float)v;
     track_len = 0; adj.clear();
     std::unordered_map<int, std::array<double, 2>>().swap(obs);  // a fresh map (bucket count and all), as `feature_adj_[fid]` is
     Xs = V3{{0, 0, 0}};
@@ -317,6 +323,9 @@ struct TrackerCfg {
   double eps = 0.01;
   int fast_threshold = 5;
   bool fast_nonmax = true, normalize = false;
+  // descriptor path (tracker.cpp:176-217): BRIEF-32 per track and frame, descriptor check, rescue of dropped tracks, MATCH tracker
+  bool extract_descriptor = false, differential = true, match_dropped_tracks = false, match_tracker = false;
+  int descriptor_distance_thresh = -1;
   // tracker-level outlier rejection by homography (tracker.cpp:131-150): method = cv::RANSAC (8) or cv::LMEDS (4)
   bool do_outlier_rejection = false;
   int outlier_method = 8, outlier_max_iters = 2000;
@@ -346,6 +355,8 @@ struct EstimatorCfg {
   double init_z = 1, init_std_x = 1, init_std_y = 1, init_std_z = 1, min_z = 0.05, max_z = 5;
   double init_std_x_badtri = 0, init_std_y_badtri = 0, init_std_z_badtri = 0;  // jsoncpp: a missing number reads as 0 (estimator.cpp:356-358)
   bool use_MH_gating = true;
+  bool use_1pt_RANSAC = false;
+  double ransac_thresh = 5.0, ransac_prob = 0.95, ransac_chi2 = 5.89;
   int min_inliers = 5;
   double MH_thresh = 5.991, MH_mult = 1.1;
   double owner_change_cov_factor = 1.5;
@@ -391,7 +402,11 @@ class Estimator {
   void tracker_update_pointcloud(const std::vector<int>& ids, const std::vector<double>& xp_depth);
   void update_step_pre();                                                // lifetimes, ProcessTracks pass 1
   void update_step_after_subfilter(const SubfilterOut* out);            // ProcessTracks pass 2, SelectAndAddNewFeatures
-  void update_step_after_gate(const double* mh);                        // OutlierRejection .. in_current_ekf_update_
+  void update_step_after_gate(const double* mh, const double* diag_after_edits = nullptr);  // OutlierRejection .. in_current_ekf_update_ (returns early with ransac.active set)
+  void ransac_after_temp_update(const double* err);                     // AbsorbError of the low-innovation update (motion state only)
+  bool ransac_begin(const double* diag_after_edits);
+  void ransac_finish(const double* mh_at_temp_state, const std::vector<Feature*>& table_order);  // rescue / reject, RestoreState, then the tail of update_step_after_gate
+  void update_step_after_gate_finish();
   void update_step_after_update(const double* err, const double* Pmm, const double* diagP, bool had_update);
   void tracker_only_finish();
 
@@ -417,7 +432,34 @@ class Estimator {
   std::vector<Feature*> tracks;  // Tracker::features_ (a list in the reference; order is what matters)
   std::vector<Feature*> instate_features, new_features, inliers, in_update, subfilter_list;
   std::vector<Group*> instate_groups, needs_new_gauge;
-  std::set<int> affected_groups;
+  // Estimator::affected_groups_ is a std::unordered_set<GroupPtr> (estimator.h:364): its few elements sit in distinct buckets, where libstdc++
+  // links every new node at the head of the list, so DiscardAffectedGroups meets them in REVERSE insertion order (exact for two groups;
+  // pinned on the reference by tests/test_reference_pin.py::ransac_two_groups_89, where the order decides which group adopts whose features)
+  struct OrderedIds {
+    std::vector<int> v;
+    void insert(int id) { if (std::find(v.begin(), v.end(), id) == v.end()) v.push_back(id); }
+    bool empty() const { return v.empty(); }
+    void clear() { v.clear(); }
+  } affected_groups;
+  // ---- filter-level 1-point RANSAC (Estimator::OnePointRANSAC, update.cpp:213-393; call site manager.cpp:642-656) ----
+  // Host decisions around two extra device phases: (1) a temporary update with the low-innovation features on a covariance whose
+  // high-innovation rows are zeroed, (2) Jacobians + Mahalanobis distances of the high-innovation features at the temporarily absorbed state.
+  struct Ransac {
+    bool active = false;                 // this frame needs the two device phases
+    std::vector<Feature*> mh_inliers;    // the MH inliers that are still in the state (input order = output order)
+    std::vector<char> low;               // per mh_inlier: |xp - Predict| < 1pt_RANSAC_thresh
+    std::vector<EditOp> zero_edits;      // rows / columns zeroed before the temporary update
+    MotionX X0;                          // BackupState
+    // what the Jacobians of the survivors are recomputed from at the end of OnePointRANSAC (update.cpp:381-385), in the index space of the
+    // device feature table: a survivor whose owner changed in the DiscardAffectedGroups that precedes the RANSAC (manager.cpp:645) is
+    // re-linearised about its NEW reference group and re-expressed state here -- unlike in frames without RANSAC, where J_ stays as
+    // ComputeInstateJacobians left it
+    std::vector<char> jalive;
+    std::vector<double> jx;              // 3 per table entry
+    std::vector<int> jref, jsind;
+  } ransac;
+  int num_oneptransac_rejected = 0;
+  bool in_ransac_destroy = false;        // RemoveFeatureFromState inside OnePointRANSAC precedes RestoreState: its zeroing of P_ does not survive
   std::vector<int> just_dropped_ids;
   std::map<int, double> ids_to_depths;
   bool sim_initialize_depths = false;

@@ -27,6 +27,13 @@ int launch_fast_detect(cudaStream_t st, const uint8_t* img, unsigned long long i
                        int rows, int cols, int cn, int thr, int nonmax, unsigned* kp_out, int max_kp, int* kp_count, int batch,
                        const int* need = nullptr, const CUtensorMap* tma_map = nullptr, unsigned long long tma_img_stride = 0,
                        bool count_is_zero = false /*kp_count was cleared by an earlier kernel of the stream (track_accept)*/);
+// Descriptor path (tracker.cpp:231-292, :341-460, :530-565): BRIEF-32 at given keypoints (kp_xy: batch x max_kp x 2 floats, nkp: batch counts;
+// desc: batch x max_kp x 32 bytes, valid: 0 for keypoints closer than 28 px to the border) and, for the cross-checked brute-force matcher,
+// the nearest descriptor of side b for every descriptor of side a (index and Hamming distance; -1 when b is empty; first index on ties).
+int launch_brief(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off, int rows, int cols, int cn,
+                 const float* kp_xy, const int* nkp, int max_kp, uint8_t* desc, uint8_t* valid, int batch);
+int launch_hamming_nearest(cudaStream_t st, const uint8_t* a, const int* na, int max_a, const uint8_t* b, const int* nb, int max_b, int* best_idx,
+                           int* best_dist, int batch);
 // Device-side tracker decisions (accept loop of Tracker::UpdateLK, greedy selection of Tracker::DetectLK); tracker_kernels.cu
 struct TrackDecideCfg {
   int rows, cols, margin, mask_half, num_min, num_max, max_pts, max_kp, max_new;
@@ -79,7 +86,7 @@ int launch_jacobian_gate(cudaStream_t st, EkfLayout lay, const CameraParams* cam
                          const int* nfeat /*B*/, double* P /*B x N x N*/, const double* Rmeas /*B*/,
                          FeatJac* out /*B x F*/, double* J_dense /*B x F x 2 x N or null*/, double* mh_out /*B x F or null*/,
                          int batch, const EditOp* ops = nullptr /*packed edit lists applied to P first*/, const int* ops_first = nullptr /*B*/,
-                         const int* nops = nullptr /*B*/);
+                         const int* nops = nullptr /*B*/, double* diag_out = nullptr /*B x N: diag(P) after the edits*/);
 
 struct TcOperands;  // TF32 operand buffers + tensor maps of the tensor-core downdate (below)
 // Stack H (FillJacobianBlock semantics) for the selected features and do the measurement update.
@@ -88,7 +95,8 @@ struct TcOperands;  // TF32 operand buffers + tensor maps of the tensor-core dow
 int launch_ekf_update(cudaStream_t st, EkfLayout lay, const FeatJac* jac, const int* sel, const int* nsel,
                       const double* Rmeas /*B*/, double* P, double* err, double* HP, double* Kt, double* H_dense /*or null*/,
                       int batch, int tensor_core = 0, const EditOp* ops = nullptr /*packed edit lists applied to P first*/,
-                      const int* ops_first = nullptr /*B*/, const int* nops = nullptr /*B*/, const TcOperands* tc = nullptr /*tensor_core: second formulation*/);
+                      const int* ops_first = nullptr /*B*/, const int* nops = nullptr /*B*/, const TcOperands* tc = nullptr /*tensor_core: second formulation*/,
+                      int full_j = 0 /*stack the rows of J() unchanged instead of FillJacobianBlock's layout (1-point RANSAC)*/);
 
 // Dense-input variant used by the kernel-level C ABI (arbitrary H, diagR), same kernels underneath.
 int launch_ekf_update_dense(cudaStream_t st, int N, int M, const double* H, const double* diagR, const double* inn, double* P,

@@ -1329,6 +1329,133 @@ int launch_lk_track(cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* nex
 }
 
 // ------------------------------------------------------------------------------------------
+// Descriptor path (/root/reference/src/tracker.cpp:231-292, :341-460, :530-565; popcount distance src/fastbrief.cpp:53-93):
+// BRIEF-32 at given keypoints and the Hamming matrix of the cross-checked brute-force matcher.  Semantics: oracle/tracker_oracle.c
+// (orc_brief, orc_bf_match_crosscheck); the 256 test pairs are the own table of brief_pattern.h (opencv_contrib's is not available).
+// brief_kernel: one warp per keypoint.  The 56 x 56 neighbourhood (48-pixel patch + 9 x 9 box) is staged in shared memory as grey
+// bytes (BGR converted with FAST's coefficients), then summed separably into 48 x 48 box sums (u16: 81 * 255 < 65536); lane l
+// evaluates tests 8 l .. 8 l + 7 = byte l of the descriptor, so a descriptor is one coalesced 32-byte store.
+// ------------------------------------------------------------------------------------------
+}  // namespace xb
+#include "brief_pattern.h"
+namespace xb {
+__constant__ signed char c_brief_pattern[256][4];
+constexpr int BR_WARPS = 3, BR_R = 28;                 // 56 x 56 staged region: keypoint pixel +- 28 (27 suffices; 28 keeps rows 8-byte sized)
+constexpr int BR_W = 2 * BR_R;                         // 56
+constexpr int BR_S = 48;                               // box-sum image: offsets -24 .. 23 (tests reach +-19)
+template <int CN>
+__global__ void __launch_bounds__(BR_WARPS * 32) brief_kernel(const uint8_t* __restrict__ img, unsigned long long img_stride,
+                                                              const unsigned long long* __restrict__ seq_off, int rows, int cols,
+                                                              const float* __restrict__ kp_xy, const int* __restrict__ nkp, int max_kp,
+                                                              uint8_t* __restrict__ desc, uint8_t* __restrict__ valid) {
+  __shared__ uint8_t patch[BR_WARPS][BR_W][BR_W];
+  __shared__ unsigned short hsum[BR_WARPS][BR_W][BR_S];
+  __shared__ unsigned short box[BR_WARPS][BR_S][BR_S];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * BR_WARPS + warp;
+  const unsigned long long soff = seq_off ? seq_off[b] : (unsigned long long)b * img_stride;
+  if (soff == ~0ull || k >= nkp[b]) return;  // warp-uniform
+  const uint8_t* __restrict__ src = img + soff;
+  const size_t ki = (size_t)b * max_kp + k;
+  const float fx = kp_xy[2 * ki], fy = kp_xy[2 * ki + 1];
+  const bool ok = fx >= XB_BRIEF_BORDER && fx < cols - XB_BRIEF_BORDER && fy >= XB_BRIEF_BORDER && fy < rows - XB_BRIEF_BORDER;
+  uint8_t* __restrict__ d = desc + ki * XB_BRIEF_BYTES;
+  if (!ok) {  // KeyPointsFilter::runByImageBorder drops the keypoint
+    d[lane] = 0;
+    if (lane == 0) valid[ki] = 0;
+    return;
+  }
+  const int cx = (int)(fx + 0.5f), cy = (int)(fy + 0.5f);
+  // stage rows cy - 28 .. cy + 27, columns cx - 28 .. cx + 27 (inside the image: cx, cy >= 28 and <= dim - 28)
+  for (int i = lane; i < BR_W * BR_W; i += 32) {
+    const int ry = i / BR_W, rx = i - ry * BR_W;
+    const int gy = min(max(cy - BR_R + ry, 0), rows - 1), gx = min(max(cx - BR_R + rx, 0), cols - 1);
+    const uint8_t* p = src + ((size_t)gy * cols + gx) * CN;
+    patch[warp][ry][rx] = CN == 1 ? p[0] : (uint8_t)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + (1 << 14)) >> 15);
+  }
+  __syncwarp();
+  // horizontal 9-sums: hsum[ry][sx] = sum patch[ry][sx + 0 .. sx + 8], sx = 0 .. 47 <-> offset sx - 24 (box centre at column sx + 4 = cx - 24 + sx)
+  for (int i = lane; i < BR_W * BR_S; i += 32) {
+    const int ry = i / BR_S, sx = i - ry * BR_S;
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) s += patch[warp][ry][sx + q];
+    hsum[warp][ry][sx] = (unsigned short)s;
+  }
+  __syncwarp();
+  for (int i = lane; i < BR_S * BR_S; i += 32) {
+    const int sy = i / BR_S, sx = i - sy * BR_S;
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) s += hsum[warp][sy + q][sx];
+    box[warp][sy][sx] = (unsigned short)s;
+  }
+  __syncwarp();
+  // box[sy][sx] = 9 x 9 sum centred at pixel (cx - 24 + sx, cy - 24 + sy): offset (dx, dy) -> box[dy + 24][dx + 24]
+  unsigned byte = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const signed char* t = c_brief_pattern[8 * lane + q];
+    const int a = box[warp][t[1] + 24][t[0] + 24], c2 = box[warp][t[3] + 24][t[2] + 24];
+    byte |= (unsigned)(a < c2) << (7 - q);
+  }
+  d[lane] = (uint8_t)byte;
+  if (lane == 0) valid[ki] = 1;
+}
+
+int launch_brief(cudaStream_t st, const uint8_t* img, unsigned long long img_stride, const unsigned long long* seq_off, int rows, int cols, int cn,
+                 const float* kp_xy, const int* nkp, int max_kp, uint8_t* desc, uint8_t* valid, int batch) {
+  XB_REQUIRE(cn == 1 || cn == 3, "BRIEF: 1 or 3 channels");
+  static bool uploaded = false;
+  if (!uploaded) {  // (one device per process in this library)
+    XB_CUDA(cudaMemcpyToSymbol(c_brief_pattern, kBriefPattern, sizeof(kBriefPattern)));
+    uploaded = true;
+  }
+  ProfScope ps("brief", st);
+  dim3 grid((max_kp + BR_WARPS - 1) / BR_WARPS, batch);
+  if (cn == 1) brief_kernel<1><<<grid, BR_WARPS * 32, 0, st>>>(img, img_stride, seq_off, rows, cols, kp_xy, nkp, max_kp, desc, valid);
+  else brief_kernel<3><<<grid, BR_WARPS * 32, 0, st>>>(img, img_stride, seq_off, rows, cols, kp_xy, nkp, max_kp, desc, valid);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Nearest train descriptor of every query and nearest query of every train (first index on ties), Hamming distance over 32-byte
+// descriptors: what cv::BFMatcher(NORM_HAMMING, crossCheck) needs.  One warp per query row (best train) / per train row (best query);
+// a lane strides over the other side, keeps (distance, index) packed as distance << 16 | index, and the warp reduces with min.
+__global__ void __launch_bounds__(128) hamming_nearest_kernel(const uint8_t* __restrict__ a, const int* __restrict__ na, int max_a,
+                                                              const uint8_t* __restrict__ bdesc, const int* __restrict__ nb, int max_b,
+                                                              int* __restrict__ best_idx, int* __restrict__ best_dist) {
+  const int s = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + warp;
+  if (i >= na[s]) return;
+  const uint4* qa = reinterpret_cast<const uint4*>(a + ((size_t)s * max_a + i) * 32);
+  const uint4 q0 = qa[0], q1 = qa[1];
+  unsigned best = 0xffffffffu;
+  const int n = nb[s];
+  for (int j = lane; j < n; j += 32) {
+    const uint4* tb = reinterpret_cast<const uint4*>(bdesc + ((size_t)s * max_b + j) * 32);
+    const uint4 t0 = tb[0], t1 = tb[1];
+    const unsigned dist = __popc(q0.x ^ t0.x) + __popc(q0.y ^ t0.y) + __popc(q0.z ^ t0.z) + __popc(q0.w ^ t0.w) + __popc(q1.x ^ t1.x) + __popc(q1.y ^ t1.y) +
+                          __popc(q1.z ^ t1.z) + __popc(q1.w ^ t1.w);
+    best = min(best, (dist << 16) | (unsigned)j);  // equal distances: the smaller index wins (j < 65536)
+  }
+  best = __reduce_min_sync(0xffffffffu, best);
+  if (lane == 0) {
+    best_idx[(size_t)s * max_a + i] = n > 0 ? (int)(best & 0xffffu) : -1;
+    best_dist[(size_t)s * max_a + i] = n > 0 ? (int)(best >> 16) : -1;
+  }
+}
+
+int launch_hamming_nearest(cudaStream_t st, const uint8_t* a, const int* na, int max_a, const uint8_t* b, const int* nb, int max_b, int* best_idx,
+                           int* best_dist, int batch) {
+  XB_REQUIRE(max_b < 65536, "Hamming matcher: at most 65535 descriptors per side");
+  ProfScope ps("hamming_nearest", st);
+  hamming_nearest_kernel<<<dim3((max_a + 3) / 4, batch), 128, 0, st>>>(a, na, max_a, b, nb, max_b, best_idx, best_dist);
+  XB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // Device-side tracker decisions: Tracker::UpdateLK's accept loop (tracker.cpp:571-589) and Tracker::DetectLK's greedy selection
 // (tracker.cpp:224-229, :295-328) without a host round trip.  Both walk a list in order while a mask of claimed pixels grows, so each
 // sequence is one CTA whose warp 0 does the sequential walk (the 15 x 15 mask-out of one feature is spread over the lanes);
