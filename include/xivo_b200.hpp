@@ -189,6 +189,21 @@ class Estimator {
     return out;
   }
 
+  // tracked_features(): (id, last pixel position, descriptor) like estimator.h:198 -- the descriptor is the feature's 32 BRIEF bytes
+  // (empty when the tracker extracts none; the reference hands out the cv::Mat row)
+  std::vector<std::tuple<int, Vec2, std::vector<uint8_t>>> tracked_features() const {
+    const auto base = tracked_features_no_descriptor();
+    std::vector<uint8_t> desc(32 * (size_t)kMaxTracks), has(kMaxTracks);
+    int n = 0;
+    check(xivo_get_tracked_descriptors(b_, 0, desc.data(), has.data(), kMaxTracks, &n));
+    std::vector<std::tuple<int, Vec2, std::vector<uint8_t>>> out;
+    out.reserve(base.size());
+    for (size_t i = 0; i < base.size(); ++i)
+      out.emplace_back(std::get<0>(base[i]), std::get<1>(base[i]),
+                       (int)i < n && has[i] ? std::vector<uint8_t>(desc.begin() + 32 * i, desc.begin() + 32 * (i + 1)) : std::vector<uint8_t>());
+    return out;
+  }
+
   xivo_batch* handle() { return b_; }
 
  private:

@@ -97,6 +97,10 @@ int xivo_get_counters(xivo_batch* b, int seq, int out[XIVO_NUM_COUNTERS]);
 int xivo_get_time_ns(xivo_batch* b, int seq, uint64_t* ts); /* Estimator::ts() */
 /* tracked_features_no_descriptor(): ids and last pixel positions of Tracker::features_. */
 int xivo_get_tracked_features(xivo_batch* b, int seq, int* ids, double* xy, int* status, int max_n, int* n);
+/* tracked_features(): the descriptor column of the reference's (id, pixel, descriptor) tuples (pybind11/pyxivo.cpp:377-393; Feature::descriptor(),
+ * src/feature.h:50).  desc: max_n x 32 bytes (BRIEF-32), has: max_n flags (0 = the feature carries no descriptor: extract_descriptor off),
+ * same order as xivo_get_tracked_features. */
+int xivo_get_tracked_descriptors(xivo_batch* b, int seq, uint8_t* desc, uint8_t* has, int max_n, int* n);
 /* InstateFeatureIDs/Sinds/Positions(Xs)/x and reference group ids. */
 int xivo_get_instate_features(xivo_batch* b, int seq, int* ids, int* sinds, int* ref_group_ids, double* Xs3,
                               double* x3, int max_n, int* n);

@@ -394,11 +394,13 @@ REFERENCE_CFG = "/root/reference/cfg"
 # (None = accepted; otherwise a fragment of the refusal).  DESIGN.md §8 discusses every entry.
 SHIPPED = {
     "pcw.json": None, "pcw_loops.json": None, "phab.json": None, "tumvi_cam1.json": None,
-    "tumvi_cam0.json": "match_dropped_tracks", "void_params.json": "Wsb",  # stale in the reference itself: state keys W / T / V (its use_1pt_RANSAC is accepted: Estimator::OnePointRANSAC is built)
+    "tumvi_cam0.json": None,                # the reference's flagship config: BRIEF descriptors + rescue of dropped tracks (match_dropped_tracks)
+    "void_params.json": "Wsb",              # stale in the reference itself: state keys W / T / V (its use_1pt_RANSAC is accepted: Estimator::OnePointRANSAC is built)
     "phab_calibration.json": "json",        # stale in the reference itself: `"method": 1`, state keys W / T / V
     "void_params_calib.json": "Wsb",        # stale in the reference itself: state keys W / T / V
-    "tumvi_tracker_only_cam0.json": "match_dropped_tracks", "tumvi_tracker_only_cam1.json": None,  # (LMEDS outlier rejection on, descriptor rescue off)
-    "phab_tracker_only.json": "MATCH", "void_tracker_only.json": "radtan",
+    "tumvi_tracker_only_cam0.json": None, "tumvi_tracker_only_cam1.json": None,  # (LMEDS outlier rejection + descriptor rescue on)
+    "phab_tracker_only.json": "SIFT",       # MATCH tracker is built, its SIFT descriptor is not (BRIEF only)
+    "void_tracker_only.json": "radtan",
 }
 
 
@@ -417,8 +419,8 @@ def test_shipped_reference_configs_through_the_host_parser(hh, name, refusal):
         hh.hh_destroy(h)
     else:
         assert not h and refusal.lower() in hh.hh_error().decode().lower(), hh.hh_error()
-    if name.startswith("tumvi_tracker_only"):  # with the descriptor rescue off the shipped file runs as it is (LMEDS outlier rejection included)
-        cfg["tracker_cfg"]["match_dropped_tracks"] = False
+    if name == "phab_tracker_only.json":  # with BRIEF in place of SIFT the shipped MATCH-tracker file runs as it is
+        cfg["tracker_cfg"]["descriptor"] = "BRIEF"
         h = hh.hh_create(json.dumps(cfg).encode(), 15, 30, 1)
         assert h, hh.hh_error()
         hh.hh_destroy(h)

@@ -294,6 +294,16 @@ class Batch {
   Mirror<uint8_t> tstat;
   Mirror<unsigned> tnewkp;
   Mirror<unsigned long long> fast_off;  // FAST selector: pyramid offset of the sequences that may need a detection
+  // descriptor path (tracker.cpp:231-292, :341-460, :530-565): BRIEF-32 at the tracked positions and at the detected keypoints, Hamming
+  // nearest neighbours for the cross-checked matcher.  Allocated when the tracker extracts descriptors; decisions then stay on the host.
+  bool desc_on = false;
+  Mirror<uint8_t> descT, validT;        // B x max_pts (x 32): descriptors at this frame's LK positions
+  Mirror<float> kpxy;                   // B x max_kp x 2: detected keypoints in selection order (mask- and border-filtered, sorted)
+  Mirror<int> nkps, nq;                 // B
+  Mirror<uint8_t> descK, validK, qdesc; // B x max_kp x 32 / B x max_kp / B x max_pts x 32 (queries: descriptors of dropped / existing tracks)
+  Mirror<int> bestT_idx, bestT_dist, bestQ_idx, bestQ_dist;  // nearest keypoint of every query; nearest query of every keypoint
+  std::vector<std::vector<unsigned>> sorted_kp;   // per sequence: packed keypoints (y << 20 | x << 8 | score) in selection order
+  std::vector<std::vector<Feature*>> query_feats; // per sequence: the features behind the query descriptors
   // every table of the tracker phase lives in ONE blob: [inputs | pts1 (in/out) | outputs], so the phase costs one H2D and one D2H call
   Mirror<unsigned char> tt;
   size_t tt_up_bytes = 0, tt_down_off = 0, tt_down_bytes = 0;
@@ -420,6 +430,8 @@ class Batch {
     icst.release(); blobG.release();
     lkerr.release(); lkst.release(); kpcount.release();
     kp.release(); tt.release();
+    descT.release(); validT.release(); kpxy.release(); nkps.release(); nq.release(); descK.release(); validK.release(); qdesc.release();
+    bestT_idx.release(); bestT_dist.release(); bestQ_idx.release(); bestQ_dist.release();
   }
 
   int fail(int code, const std::string& m) {
@@ -676,7 +688,15 @@ class Batch {
     // not fit into shared memory, or XIVO_HOST_TRACKER_DECISIONS=1 asks for the host path (parity tests compare the two)
     {
       const char* hd = getenv("XIVO_HOST_TRACKER_DECISIONS");
-      dev_decide = !e0.tc.do_outlier_rejection && track_mask_bytes(rows, cols) <= 200 * 1024 && !(hd && hd[0] == '1');
+      dev_decide = !e0.tc.do_outlier_rejection && !e0.tc.extract_descriptor && track_mask_bytes(rows, cols) <= 200 * 1024 && !(hd && hd[0] == '1');
+    }
+    desc_on = e0.tc.extract_descriptor;
+    if (ok && desc_on) {
+      const size_t npt = (size_t)B * max_pts, nk = (size_t)B * max_kp;
+      ok = descT.alloc(npt * 32) && validT.alloc(npt) && kpxy.alloc(nk * 2) && nkps.alloc(B) && nq.alloc(B) && descK.alloc(nk * 32) && validK.alloc(nk) &&
+           qdesc.alloc(npt * 32) && bestT_idx.alloc(npt) && bestT_dist.alloc(npt) && bestQ_idx.alloc(nk) && bestQ_dist.alloc(nk);
+      sorted_kp.resize(B);
+      query_feats.resize(B);
     }
     if (ok) {
       ingest_ptr.adopt(blobG.h, blobG.d, B);
@@ -770,6 +790,124 @@ class Batch {
     }
   }
 
+  // Detected keypoints of one sequence in the order DetectLK / UpdateMatch walks them: [mask filter (detect(img, kps, mask_))] -> sort by
+  // response (total order (score desc, y, x): the reference's std::sort is unstable) -> the descriptor extractor drops the 28-pixel border band.
+  void order_keypoints(int b, const unsigned* kps, int n, bool use_mask) {
+    Estimator& e = *est[b];
+    std::vector<unsigned>& v = sorted_kp[b];
+    v.clear();
+    for (int i = 0; i < n; ++i) {
+      const unsigned k = kps[i];
+      const int x = (k >> 8) & 0xfff, y = k >> 20;
+      if (use_mask && !e.mask_bit(x, y)) continue;
+      if (x < 28 || x >= cols - 28 || y < 28 || y >= rows - 28) continue;  // KeyPointsFilter::runByImageBorder(.., 48 / 2 + 9 / 2)
+      v.push_back(k);
+    }
+    std::sort(v.begin(), v.end(), [](unsigned a, unsigned c) {
+      const unsigned sa = a & 0xff, sc = c & 0xff;
+      return sa != sc ? sa > sc : (a >> 8) < (c >> 8);  // (y, x) ascending within a score
+    });
+    float* xy = kpxy.h + (size_t)b * max_kp * 2;
+    for (size_t i = 0; i < v.size(); ++i) { xy[2 * i] = (float)((v[i] >> 8) & 0xfff); xy[2 * i + 1] = (float)(v[i] >> 20); }
+    nkps.h[b] = (int)v.size();
+  }
+  // BRIEF at the ordered keypoints of `seqs` (level-0 image of the current pyramid: sel_off) and, where a sequence has query descriptors
+  // (query_feats), the two nearest-neighbour tables of the cross-checked matcher.  One wait.
+  int describe_and_match(const std::vector<int>& seqs, const unsigned long long* sel_off_dev) {
+    cudaStream_t st = st1;
+    bool any_q = false;
+    for (int b = 0; b < B; ++b) nq.h[b] = 0;
+    for (int b : seqs) {
+      const int n = nkps.h[b];
+      if (n) XB_CUDA(cudaMemcpyAsync(kpxy.d + (size_t)b * max_kp * 2, kpxy.h + (size_t)b * max_kp * 2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, st));
+      const int q = (int)query_feats[b].size();
+      if (q > max_pts) return fail(XIVO_ERR_STATE, "descriptor matcher: more query features than max_pts");
+      nq.h[b] = n ? q : 0;
+      for (int j = 0; j < nq.h[b]; ++j) memcpy(qdesc.h + ((size_t)b * max_pts + j) * 32, query_feats[b][j]->descriptor, 32);
+      if (nq.h[b]) {
+        any_q = true;
+        XB_CUDA(cudaMemcpyAsync(qdesc.d + (size_t)b * max_pts * 32, qdesc.h + (size_t)b * max_pts * 32, (size_t)32 * nq.h[b], cudaMemcpyHostToDevice, st));
+      }
+    }
+    XB_CUDA(nkps.up(st)); XB_CUDA(nq.up(st));
+    if (int rc = launch_brief(st, dPyr, 0, sel_off_dev, rows, cols, cn, kpxy.d, nkps.d, max_kp, descK.d, validK.d, B)) return rc;
+    g_launches += 1;
+    if (any_q) {
+      if (int rc = launch_hamming_nearest(st, qdesc.d, nq.d, max_pts, descK.d, nkps.d, max_kp, bestT_idx.d, bestT_dist.d, B)) return rc;
+      if (int rc = launch_hamming_nearest(st, descK.d, nkps.d, max_kp, qdesc.d, nq.d, max_pts, bestQ_idx.d, bestQ_dist.d, B)) return rc;
+      g_launches += 2;
+    }
+    for (int b : seqs) {
+      const int n = nkps.h[b];
+      if (!n) continue;
+      XB_CUDA(cudaMemcpyAsync(descK.h + (size_t)b * max_kp * 32, descK.d + (size_t)b * max_kp * 32, (size_t)32 * n, cudaMemcpyDeviceToHost, st));
+      if (nq.h[b]) {
+        XB_CUDA(cudaMemcpyAsync(bestT_idx.h + (size_t)b * max_pts, bestT_idx.d + (size_t)b * max_pts, sizeof(int) * nq.h[b], cudaMemcpyDeviceToHost, st));
+        XB_CUDA(cudaMemcpyAsync(bestT_dist.h + (size_t)b * max_pts, bestT_dist.d + (size_t)b * max_pts, sizeof(int) * nq.h[b], cudaMemcpyDeviceToHost, st));
+        XB_CUDA(cudaMemcpyAsync(bestQ_idx.h + (size_t)b * max_kp, bestQ_idx.d + (size_t)b * max_kp, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    HostScope hw("wait_describe");
+    return wait(st);
+  }
+  // cross-checked matches of sequence b as (query, keypoint, distance), in query order (cv::BFMatcher::knnMatch with compactResult)
+  void cross_checked(int b, std::vector<std::array<int, 3>>* out) const {
+    out->clear();
+    for (int q = 0; q < nq.h[b]; ++q) {
+      const int t = bestT_idx.h[(size_t)b * max_pts + q];
+      if (t >= 0 && bestQ_idx.h[(size_t)b * max_kp + t] == q) out->push_back({q, t, bestT_dist.h[(size_t)b * max_pts + q]});
+    }
+  }
+  // Tracker::DetectLK with descriptors (tracker.cpp:231-327): rescue matching of the newly dropped tracks, then the greedy pick.
+  void detect_select_desc(int b, int num_to_add, bool check_homography) {
+    Estimator& e = *est[b];
+    const std::vector<unsigned>& v = sorted_kp[b];
+    const uint8_t* D = descK.h + (size_t)b * max_kp * 32;
+    std::vector<int> match_of(v.size(), -1);  // keypoint -> index into query_feats[b] (the newly dropped tracks)
+    if (e.tc.match_dropped_tracks && nq.h[b] && !v.empty()) {
+      std::vector<std::array<int, 3>> m;
+      cross_checked(b, &m);
+      for (const auto& d : m) {
+        Feature* f = query_feats[b][d[0]];
+        const double x = (v[d[1]] >> 8) & 0xfff, y = v[d[1]] >> 20;
+        const bool ok_desc = e.tc.descriptor_distance_thresh > 0 ? d[2] < e.tc.descriptor_distance_thresh : true;  // CheckDescriptorDistance
+        const double dx = x - f->xp()[0], dy = y - f->xp()[1];
+        const bool ok_disp = std::sqrt(dx * dx + dy * dy) < e.tc.max_pixel_displacement;
+        bool ok_h = true;
+        if (check_homography) {  // CheckHomography (tracker.cpp:818-828) never applies H: |creation keypoint - new keypoint| < reprojection threshold
+          const double hx = (double)f->kp0[0] - x, hy = (double)f->kp0[1] - y;
+          ok_h = std::sqrt(hx * hx + hy * hy) < e.tc.outlier_reproj_thresh;
+        }
+        if (ok_desc && ok_disp && ok_h) match_of[d[1]] = d[0];
+      }
+    }
+    for (size_t i = 0; i < v.size(); ++i) {
+      const unsigned k = v[i];
+      const double x = (k >> 8) & 0xfff, y = k >> 20;
+      if (e.mask_valid(x, y)) {
+        if (e.tc.match_dropped_tracks && match_of[i] >= 0) {
+          Feature* f1 = query_feats[b][match_of[i]];
+          if (e.tc.differential) memcpy(f1->descriptor, D + 32 * i, 32);
+          f1->observe(x, y);
+          f1->tstatus = TrackStatus::TRACKED;  // "potentially rescued": UpdateLK marks every newly dropped track DROPPED right after (tracker.cpp:617-619)
+          e.mask_out(x, y);
+          --num_to_add;
+          continue;  // (skips the budget / response test, like the reference)
+        }
+        Feature* f = e.create_feature(x, y);
+        if (!f) return;
+        f->response = (float)(k & 0xff);
+        memcpy(f->descriptor, D + 32 * i, 32);
+        f->has_descriptor = true;
+        e.tracks.push_back(f);
+        e.num_new_detections++;
+        e.mask_out(x, y);
+        --num_to_add;
+      }
+      if (num_to_add <= 0 || (k & 0xff) < 5) return;
+    }
+  }
+
   // The rest of Tracker::UpdateLK with the decisions on the device: LK -> accept loop (track_accept_kernel) -> FAST for the sequences
   // the accept kernel flagged -> greedy selection (track_select_kernel) -> ONE read-back of [positions | keep flags | picks].  The host
   // then only replays the decisions on its track list (same order, same feature ids as the host path).
@@ -859,6 +997,9 @@ class Batch {
     cudaStream_t st = st1;
     const size_t ib = (size_t)rows * cols * cn;
     std::vector<int> lk_list, det_list;
+    std::vector<char> check_h(B, 0);  // DetectLK's check_homography: the frame's outlier rejection ran
+    if (desc_on)
+      for (int b : act) query_feats[b].clear();
     std::vector<int> det_budget(B, 0), kind(B, 0);  // kind: 1 = first frame (detect only), 2 = LK, 3 = empty list
     for (int b = 0; b < B; ++b) { off_cur.h[b] = ~0ull; off_prev.h[b] = 0; npts.h[b] = 0; }
     std::atomic<int> overflow{0};
@@ -963,6 +1104,11 @@ class Batch {
         Prof::get().add_work("lk_track", np_ * pd.n_levels * (17.0 * 17.0 + 25.0 * 25.0) * cn);  // §8d: L (17^2+25^2) c bytes / feature
       }
       XB_CUDA(pts1.down(st)); XB_CUDA(lkst.down(st));
+      if (desc_on) {  // descriptors at the tracked positions (tracker.cpp:530-545), same stream, same wait
+        if (int rc = launch_brief(st, dPyr, 0, off_cur.d, rows, cols, cn, pts1.d, npts.d, max_pts, descT.d, validT.d, B)) return rc;
+        g_launches += 1;
+        XB_CUDA(descT.down(st)); XB_CUDA(validT.down(st));
+      }
       { HostScope hw("wait_lk"); if (int rc = wait(st)) return rc; }
       HostScope hs("tracker_accept");
       std::vector<int> need(B, 0);
@@ -972,6 +1118,22 @@ class Batch {
         int i = 0, num_valid = 0, num_failed = 0;
         static thread_local std::vector<uint8_t> stat;  // cv status vector of this frame (tracker.cpp:501, :573-591)
         stat.assign(e.tracks.size(), 0);
+        if (desc_on) {  // tracker.cpp:546-565: keypoints the extractor dropped (border band) are skipped; a distant descriptor forces a drop
+          int j = 0;
+          for (Feature* f : e.tracks) {
+            const size_t k = (size_t)b * max_pts + j++;
+            if (!validT.h[k]) continue;
+            const uint8_t* dnew = descT.h + k * 32;
+            if (e.tc.descriptor_distance_thresh != -1) {
+              int dist = 0;
+              for (int q = 0; q < 32; ++q) dist += __builtin_popcount((unsigned)(f->descriptor[q] ^ dnew[q]));
+              if (dist > e.tc.descriptor_distance_thresh) lkst.h[k] = 0;  // enforce to be dropped
+              else if (e.tc.differential) memcpy(f->descriptor, dnew, 32);
+            } else if (e.tc.differential) {
+              memcpy(f->descriptor, dnew, 32);
+            }
+          }
+        }
         for (Feature* f : e.tracks) {
           const float* p1 = pts1.h + ((size_t)b * max_pts + i) * 2;
           bool ok = lkst.h[(size_t)b * max_pts + i] != 0;
@@ -992,17 +1154,23 @@ class Batch {
         }
         e.num_new_detections = 0;
         e.num_failed_to_track = num_failed;
+        bool or_done = false;
         if (e.tc.do_outlier_rejection) {
           // Tracker::OutlierRejection (tracker.cpp:594-599, :705-753): homography outliers lose their status after their track and the
           // mask were updated; pts0 / pts1 are this frame's LK input and output (cv::Point2f)
-          homography::tracker_outlier_rejection(pts0.h + (size_t)b * max_pts * 2, pts1.h + (size_t)b * max_pts * 2, (int)e.tracks.size(), stat,
-                                                e.tc.outlier_method, e.tc.outlier_reproj_thresh, e.tc.outlier_max_iters, e.tc.outlier_confidence,
-                                                &e.num_outliers_rejected);
+          or_done = homography::tracker_outlier_rejection(pts0.h + (size_t)b * max_pts * 2, pts1.h + (size_t)b * max_pts * 2, (int)e.tracks.size(), stat,
+                                                          e.tc.outlier_method, e.tc.outlier_reproj_thresh, e.tc.outlier_max_iters, e.tc.outlier_confidence,
+                                                          &e.num_outliers_rejected);
           num_valid -= e.num_outliers_rejected;
         }
+        check_h[b] = or_done && e.tc.do_outlier_rejection;
         i = 0;
+        if (desc_on) query_feats[b].clear();
         for (Feature* f : e.tracks)
-          if (!stat[i++]) f->tstatus = TrackStatus::DROPPED;  // (no rescue path: dropped right away)
+          if (!stat[i++]) {
+            f->tstatus = TrackStatus::DROPPED;  // (with the rescue path the reference marks them after DetectLK: the same final state)
+            if (desc_on) query_feats[b].push_back(f);  // newly_dropped_tracks (tracker.cpp:601-608)
+          }
         if (num_valid < e.tc.num_features_min) need[b] = e.tc.num_features_max - num_valid;
       });
       for (int b : lk_list)
@@ -1026,16 +1194,138 @@ class Batch {
         if (n) { Prof::get().d2h += sizeof(unsigned) * n; XB_CUDA(cudaMemcpyAsync(kp.h + (size_t)b * max_kp, kp.d + (size_t)b * max_kp, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st)); }
       }
       { HostScope hw("wait_fastkp"); if (int rc = wait(st)) return rc; }
-      HostScope hs("tracker_select");
-      pfor(det_list, [&](int b, int) {
-        HostScope hx("x_trk_select");
-        Estimator& e = *est[b];
-        detect_select(e, kp.h + (size_t)b * max_kp, std::min(kpcount.h[b], max_kp), det_budget[b]);
-        e.tracker_initialized = true;
-      });
+      if (desc_on) {  // DetectLK with descriptors: every masked keypoint gets one, dropped tracks may claim a keypoint (tracker.cpp:231-327)
+        pfor(det_list, [&](int b, int) { order_keypoints(b, kp.h + (size_t)b * max_kp, std::min(kpcount.h[b], max_kp), true); });
+        if (!est[0]->tc.match_dropped_tracks)
+          for (int b : det_list) query_feats[b].clear();
+        if (int rc = describe_and_match(det_list, off_prev.d)) return rc;
+        HostScope hs("tracker_select");
+        pfor(det_list, [&](int b, int) {
+          detect_select_desc(b, det_budget[b], check_h[b] != 0);
+          est[b]->tracker_initialized = true;
+        });
+      } else {
+        HostScope hs("tracker_select");
+        pfor(det_list, [&](int b, int) {
+          HostScope hx("x_trk_select");
+          Estimator& e = *est[b];
+          detect_select(e, kp.h + (size_t)b * max_kp, std::min(kpcount.h[b], max_kp), det_budget[b]);
+          e.tracker_initialized = true;
+        });
+      }
     }
+    if (desc_on)  // tracker.cpp:617-619: every newly dropped track ends DROPPED, "rescued" or not (DetectLK worked on a copy of the vector)
+      for (int b : lk_list)
+        for (Feature* f : query_feats[b]) f->tstatus = TrackStatus::DROPPED;
     for (int b : act)
       if (off_cur.h[b] != ~0ull) prev_slot[b] = 1 - prev_slot[b];  // std::swap(pyramid, pyramid_)
+    return 0;
+  }
+
+  // Tracker::UpdateMatch (tracker.cpp:341-460): detect without a mask, describe, cross-checked nearest-neighbour matching of the existing
+  // features' descriptors against the new keypoints (device), checks + optional homography rejection, unmatched features dropped,
+  // unmatched keypoints become features (host).
+  int tracker_update_match(const std::vector<int>& act, const std::vector<int>& slots) {
+    cudaStream_t st = st1;
+    const size_t ib = (size_t)rows * cols * cn;
+    const TrackerCfg& tc = est[0]->tc;
+    for (int b = 0; b < B; ++b) { off_cur.h[b] = ~0ull; off_prev.h[b] = 0; npts.h[b] = 0; }
+    {
+      std::vector<char> seen(ring_n, 0);
+      for (int k : slots)
+        if (!seen[k]) { seen[k] = 1; XB_CUDA(cudaStreamWaitEvent(st, ring_ev[k], 0)); }
+    }
+    for (size_t i = 0; i < act.size(); ++i) {
+      const int b = act[i];
+      const int cur = 1 - prev_slot[b];
+      off_cur.h[b] = ((size_t)b * 2 + cur) * pd.total;
+      frame_ptr.h[b] = dRing + ((size_t)b * ring_n + slots[i]) * ib;
+      if (tma_pyr) { ring_img.h[b] = b * ring_n + slots[i]; pyr_img.h[b] = b * 2 + cur; }
+    }
+    XB_CUDA(off_cur.up(st)); XB_CUDA(frame_ptr.up(st));
+    if (tma_pyr) { XB_CUDA(ring_img.up(st)); XB_CUDA(pyr_img.up(st)); }
+    // the frame enters through the pyramid's ingest pass (level 0 of the current pyramid is the image the detector and the extractor read)
+    if (tma_pyr) { if (int rc = launch_pyrdown_tma(st, tm_ring, ring_img.d, dPyr, 0, off_cur.d, pd, 0, 1, B)) return rc; }
+    else if (int rc = launch_pyrdown_level(st, dPyr, 0, off_cur.d, pd, B, frame_ptr.d, 0)) return rc;
+    if (int rc = launch_fast_detect(st, dPyr, 0, off_cur.d, rows, cols, cn, tc.fast_threshold, tc.fast_nonmax, kp.d, max_kp, kpcount.d, B, nullptr,
+                                    tma_fast ? &tm_fast : nullptr, pd.total))
+      return rc;
+    g_launches += 2;
+    XB_CUDA(kpcount.down(st));
+    { HostScope hw("wait_fastcount"); if (int rc = wait(st)) return rc; }
+    for (int b : act) {
+      const int n = std::min(kpcount.h[b], max_kp);
+      if (n) XB_CUDA(cudaMemcpyAsync(kp.h + (size_t)b * max_kp, kp.d + (size_t)b * max_kp, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, st));
+    }
+    { HostScope hw("wait_fastkp"); if (int rc = wait(st)) return rc; }
+    std::atomic<int> overflow{0};
+    pfor(act, [&](int b, int) {
+      Estimator& e = *est[b];
+      order_keypoints(b, kp.h + (size_t)b * max_kp, std::min(kpcount.h[b], max_kp), false);
+      query_feats[b].clear();
+      if (e.tracker_initialized) query_feats[b].assign(e.tracks.begin(), e.tracks.end());
+      if ((int)query_feats[b].size() > max_pts) overflow = 1;
+    });
+    if (overflow) return fail(XIVO_ERR_STATE, "tracker feature list exceeds max_pts");
+    if (int rc = describe_and_match(act, off_cur.d)) return rc;
+    pfor(act, [&](int b, int) {
+      Estimator& e = *est[b];
+      const std::vector<unsigned>& v = sorted_kp[b];
+      const uint8_t* D = descK.h + (size_t)b * max_kp * 32;
+      const std::vector<Feature*>& feats = query_feats[b];
+      std::vector<char> kp_matched(v.size(), 0), feat_matched(feats.size(), 0);
+      e.num_new_detections = 0;
+      if (e.tracker_initialized) {
+        std::vector<std::array<int, 3>> m;
+        if (nq.h[b] && !v.empty()) cross_checked(b, &m);
+        std::vector<uint8_t> mstat(m.size(), 0);
+        int zeros = 0;
+        for (size_t i = 0; i < m.size(); ++i) {
+          Feature* f = feats[m[i][0]];
+          const double x = (v[m[i][1]] >> 8) & 0xfff, y = v[m[i][1]] >> 20;
+          const bool ok_desc = e.tc.descriptor_distance_thresh > 0 ? m[i][2] < e.tc.descriptor_distance_thresh : true;
+          const double dx = x - f->xp()[0], dy = y - f->xp()[1];
+          mstat[i] = ok_desc && std::sqrt(dx * dx + dy * dy) < e.tc.max_pixel_displacement;
+          zeros += !mstat[i];
+        }
+        e.num_failed_to_track = (int)feats.size() - (int)m.size() + zeros;
+        if (e.tc.do_outlier_rejection && !m.empty()) {  // pts0 = the features' creation keypoints, pts1 = the matched new keypoints (tracker.cpp:398-408)
+          std::vector<float> p0(2 * m.size()), p1(2 * m.size());
+          for (size_t i = 0; i < m.size(); ++i) {
+            p0[2 * i] = feats[m[i][0]]->kp0[0]; p0[2 * i + 1] = feats[m[i][0]]->kp0[1];
+            p1[2 * i] = (float)((v[m[i][1]] >> 8) & 0xfff); p1[2 * i + 1] = (float)(v[m[i][1]] >> 20);
+          }
+          homography::tracker_outlier_rejection(p0.data(), p1.data(), (int)m.size(), mstat, e.tc.outlier_method, e.tc.outlier_reproj_thresh, e.tc.outlier_max_iters,
+                                                e.tc.outlier_confidence, &e.num_outliers_rejected);
+        }
+        for (size_t i = 0; i < m.size(); ++i) {
+          if (!mstat[i]) continue;
+          kp_matched[m[i][1]] = 1; feat_matched[m[i][0]] = 1;
+          Feature* f = feats[m[i][0]];
+          f->observe((double)((v[m[i][1]] >> 8) & 0xfff), (double)(v[m[i][1]] >> 20));
+          if (e.tc.differential) memcpy(f->descriptor, D + 32 * (size_t)m[i][1], 32);
+          f->tstatus = TrackStatus::TRACKED;
+        }
+      }
+      int dropped = 0;
+      for (size_t i = 0; i < feats.size(); ++i)
+        if (!feat_matched[i]) { feats[i]->tstatus = TrackStatus::DROPPED; ++dropped; }
+      // (before the first frame features_ is empty: everything detected is new)
+      int to_create = e.tc.num_features_max - (int)e.tracks.size() + (e.tracker_initialized ? dropped : 0);
+      for (size_t i = 0; i < v.size() && to_create > 0; ++i) {
+        if (kp_matched[i]) continue;
+        Feature* f = e.create_feature((double)((v[i] >> 8) & 0xfff), (double)(v[i] >> 20));
+        if (!f) return;
+        f->response = (float)(v[i] & 0xff);
+        memcpy(f->descriptor, D + 32 * i, 32);
+        f->has_descriptor = true;
+        e.tracks.push_back(f);
+        e.num_new_detections++;
+        --to_create;
+      }
+      e.tracker_initialized = true;
+    });
+    for (int b : act) prev_slot[b] = 1 - prev_slot[b];
     return 0;
   }
 
@@ -1169,7 +1459,7 @@ class Batch {
     // covariance side of Propagate: enqueued now, overlaps the tracker (nothing below touches P before phase J)
     if (int rc = integrate(full)) return rc;
     if (!lk_act.empty()) {
-      if (int rc = tracker_update_lk(lk_act, lk_slots)) return rc;
+      if (int rc = est[0]->tc.match_tracker ? tracker_update_match(lk_act, lk_slots) : tracker_update_lk(lk_act, lk_slots)) return rc;
       if (int rc = first_error(lk_act)) return rc;
       for (size_t i = 0; i < act_in.size(); ++i)
         if (proceed[i] && msgs[i].type == 2) est[act_in[i]]->tracker_only_finish();
@@ -1752,6 +2042,20 @@ int xivo_get_tracked_features(xivo_batch* b, int seq, int* ids, double* xy, int*
       if (ids) ids[k] = f->id;
       if (xy) { xy[2 * k] = f->xp()[0]; xy[2 * k + 1] = f->xp()[1]; }
       if (status) status[k] = (int)f->tstatus;
+    }
+    ++k;
+  }
+  *n = k;
+  return 0;
+}
+int xivo_get_tracked_descriptors(xivo_batch* b, int seq, uint8_t* desc, uint8_t* has, int max_n, int* n) {
+  BATCH_BEGIN; SEQ_CHECK;
+  XB_REQUIRE(n, "get_tracked_descriptors: null count");
+  int k = 0;
+  for (Feature* f : B_.est[seq]->tracks) {
+    if (k < max_n) {
+      if (desc) memcpy(desc + 32 * (size_t)k, f->descriptor, 32);
+      if (has) has[k] = f->has_descriptor ? 1 : 0;
     }
     ++k;
   }

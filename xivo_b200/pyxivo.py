@@ -197,6 +197,13 @@ class Batch:
         k = min(n.value, max_n)
         return ids[:k].copy(), xy[:k].copy(), st[:k].copy()
 
+    def tracked_descriptors(self, seq=0, max_n=4096):
+        """BRIEF-32 descriptors of the tracked features (rows of 32 bytes, same order as tracked_features) and which features carry one."""
+        d, has, n = np.zeros((max_n, 32), np.uint8), np.zeros(max_n, np.uint8), C.c_int()
+        _check(capi.lib().xivo_get_tracked_descriptors(self._h, seq, _p(d), _p(has), max_n, C.byref(n)), "xivo_get_tracked_descriptors")
+        k = min(n.value, max_n)
+        return d[:k].copy(), has[:k].astype(bool)
+
     def instate_features(self, seq=0):
         m = self.F
         ids, sinds, refs, Xs, x, n = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros((m, 3)), np.zeros((m, 3)), C.c_int()
@@ -453,9 +460,11 @@ class Estimator:
         return None  # the Pangolin viewer is outside the hot path (SURVEY.md §2); kept so that reference scripts run unchanged
 
     def tracked_features(self):
-        """[(id, pixel, descriptor)]: descriptors are not extracted on this path (extract_descriptor), an empty matrix stands in."""
+        """[(id, pixel, descriptor)] like the reference's binding (pybind11/pyxivo.cpp:377-393: the cv::Mat descriptor converted to a float
+        matrix): a 1 x 32 float32 row of the BRIEF bytes, or an empty matrix when the tracker extracts no descriptors."""
         ids, xy, _ = self._b.tracked_features()
-        return [(int(i), p, np.zeros((0, 0), np.float32)) for i, p in zip(ids, xy)]
+        d, has = self._b.tracked_descriptors()
+        return [(int(i), p, d[k : k + 1].astype(np.float32) if has[k] else np.zeros((0, 0), np.float32)) for k, (i, p) in enumerate(zip(ids, xy))]
 
     def tracked_features_no_descriptor(self):
         ids, xy, _ = self._b.tracked_features()
