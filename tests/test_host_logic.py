@@ -339,11 +339,24 @@ def test_tracker_only_accepts_the_reference_tracker_only_config_shape(hh):
     assert not hh.hh_create(json.dumps(cfg).encode(), 15, 30, 0)  # not a valid estimator config
 
 
-def test_dropped_track_rescue_is_refused_not_ignored(hh):
-    """tracker.cpp:203-211, :245-292: match_dropped_tracks changes which ids survive a re-detection; it needs descriptors (no oracle)."""
+def test_descriptor_options_follow_the_reference_constructor(hh):
+    """Tracker::Tracker (tracker.cpp:176-217): the rescue of dropped tracks needs descriptors (LOG(FATAL) "must extract descriptors in order
+    to match dropped tracks"), the MATCH tracker too; a distance threshold switches the extraction on; only BRIEF is built."""
     cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
     cfg["tracker_cfg"]["match_dropped_tracks"] = True
-    assert not hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0) and b"match_dropped_tracks" in hh.hh_error()
+    assert not hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0) and b"must extract descriptors" in hh.hh_error()
+    cfg["tracker_cfg"]["extract_descriptor"] = True
+    h = hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0)
+    assert h, hh.hh_error()
+    hh.hh_destroy(h)
+    cfg["tracker_cfg"].update(extract_descriptor=False, match_dropped_tracks=False, tracker_type="MATCH")
+    assert not hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0) and b"matcher-tracker requires" in hh.hh_error()
+    cfg["tracker_cfg"].update(descriptor_distance_thresh=50)  # > -1 implies extraction (tracker.cpp:178-179)
+    h = hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0)
+    assert h, hh.hh_error()
+    hh.hh_destroy(h)
+    cfg["tracker_cfg"].update(descriptor="ORB")
+    assert not hh.hh_create(json.dumps(cfg).encode(), 4, 14, 0) and b"ORB" in hh.hh_error()
 
 
 # ------------------------------------------------------------------------------------------------------------------------

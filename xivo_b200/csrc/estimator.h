@@ -48,50 +48,61 @@ inline void ids_erase(std::vector<int>& v, int id) {
 }
 
 struct Group {
-  int id = -1, sind = -1, lifetime = 0, slot = -1;
+  int id = -1, sind = -1, birth = 0, slot = -1;  // birth: Estimator::step_counter when the group entered the graph (lifetime = step_counter - birth)
   GroupStatus status = GroupStatus::CREATED;
   M3 Rsb = m3_eye();
   V3 Tsb{{0, 0, 0}};
-  std::vector<int> adj;  // ids of the features seen from this group (GroupAdj), ascending
+  // GroupAdj (the features seen from this group) is not stored: a feature is seen by every group created while it lives (one group per
+  // frame, every live feature is TRACKED or new in it: manager.cpp:569-627), so "g saw f" <=> f.first_gid <= g.id <= f.last_gid -- see Feature.
   std::set<int> gauge;   // ids of its gauge features (Graph::gauge_features_)
-  bool may_own = false;  // some feature's ref has pointed at this group (creation frame or ownership transfer); false = owns nothing, no scan needed
+  int n_owned = 0;       // features of the graph whose ref is this group ("does the group own any feature it saw", manager.cpp:288-296, without a scan)
   bool instate() const { return status == GroupStatus::INSTATE || status == GroupStatus::GAUGE; }
   SE3h gsb() const { return SE3h{Rsb, Tsb}; }
   void reset(int new_id) {  // Group::Create/Reset; keeps the slot and the containers' capacity
-    id = new_id; sind = -1; lifetime = 0;
+    id = new_id; sind = -1; birth = 0;
     status = GroupStatus::CREATED;
     Rsb = m3_eye(); Tsb = V3{{0, 0, 0}};
-    adj.clear(); gauge.clear();
-    may_own = false;
+    gauge.clear(); n_owned = 0;
   }
 };
 
-struct Feature {
-  int id = -1, sind = -1, lifetime = 0, slot = -1, init_counter = 0;
+struct alignas(64) Feature {
+  // Layout: with hundreds of sequences per GPU every per-frame loop over the features starts cache-cold, so what those loops read sits in
+  // the first two cache lines (ids / status / owner / id range | local state, prediction, last pixel), the sub-filter's 3 x 3 covariance and
+  // the cached world position in the next two, and what only detection, read-back or the optional paths touch comes last.
+  // ---- line 0
+  int id = -1, sind = -1, birth = 0, slot = -1, init_counter = 0;  // birth: as for Group
   FeatureStatus status = FeatureStatus::CREATED;
   TrackStatus tstatus = TrackStatus::CREATED;
+  int track_len = 0;
   Group* ref = nullptr;
-  double x[3] = {0, 0, 2.0};
-  double P[9] = {0};
-  double pred[2] = {-1, -1};
+  // FeatureAdj keys (the groups that saw this feature) as an id range: every group created between the feature's first and latest frame saw
+  // it, groups that were removed since simply no longer exist in Graph::groups.  The per-frame association then costs two stores instead of
+  // a sorted insert into a per-feature heap vector and a per-group one (cold: one cache miss each for ~130 features per frame), and removing
+  // a group touches no feature.
+  int first_gid = -1, last_gid = -1;
   double outlier_counter = 0;
-  bool tri_ok = false;
+  bool tri_ok = false, has_descriptor = false;
   float response = 0.f;
+  // ---- line 1
+  alignas(64) double x[3] = {0, 0, 2.0};
+  double pred[2] = {-1, -1};
+  // Track: only front() (two-view triangulation), back() and the length are ever read on this path (the full
+  // history feeds the OOS update, out of scope).
+  std::array<double, 2> last_xp{{0, 0}};
+  // ---- lines 2, 3
+  alignas(64) double P[9] = {0};
+  V3 Xs{{0, 0, 0}};
+  std::array<double, 2> first_xp{{0, 0}};
+  // ---- cold
   // descriptor path (Feature::descriptor(), Feature::keypoint(), feature.h:50-56): the BRIEF-32 bytes set at detection (replaced every frame
   // when `differential`) and the pixel of the keypoint the feature was created from
   uint8_t descriptor[32] = {0};
-  bool has_descriptor = false;
   float kp0[2] = {0, 0};
-  // Track: only front() (two-view triangulation), back() and the length are ever read on this path (the full
-  // history feeds the OOS update, out of scope).
-  std::array<double, 2> first_xp{{0, 0}}, last_xp{{0, 0}};
-  int track_len = 0;
-  std::vector<int> adj;  // ids of the groups that saw this feature (FeatureAdj keys), ascending
   // FeatureAdj itself (graphbase.h:49-51: unordered_map<group id, pixel at the time the group first saw the feature>), kept only when
   // use_depth_opt needs it: Graph::GetObservationsOf walks it in ITERATION order (graphbase.cpp:146-152) and RefineDepth's two_view
   // mode picks the first and the last element of that walk, so it is the same container with the same insert / erase history.
   std::unordered_map<int, std::array<double, 2>> obs;
-  V3 Xs{{0, 0, 0}};
   bool instate() const { return status == FeatureStatus::INSTATE || status == FeatureStatus::GAUGE; }
   const std::array<double, 2>& xp() const { return last_xp; }
   void observe(double u, double v) {
@@ -99,7 +110,7 @@ struct Feature {
     if (track_len++ == 0) first_xp = last_xp;
   }
   void reset(int new_id, double u, double v) {  // Feature::Create/Reset (feature.cpp:43-91); keeps slot + capacity
-    id = new_id; sind = -1; lifetime = 0; init_counter = 0;
+    id = new_id; sind = -1; birth = 0; init_counter = 0;
     status = FeatureStatus::CREATED; tstatus = TrackStatus::CREATED;
     ref = nullptr;
     x[0] = u; x[1] = v; x[2] = 2.0;
@@ -107,7 +118,7 @@ struct Feature {
     pred[0] = pred[1] = -1;
     outlier_counter = 0; tri_ok = false; response = 0.f;
     has_descriptor = false; kp0[0] = (float)u; kp0[1] = (float)v;
-    track_len = 0; adj.clear();
+    track_len = 0; first_gid = last_gid = -1;
     std::unordered_map<int, std::array<double, 2>>().swap(obs);  // a fresh map (bucket count and all), as `feature_adj_[fid]` is
     Xs = V3{{0, 0, 0}};
     observe(u, v);
@@ -279,6 +290,7 @@ struct Graph {
   IdHashMap<Feature*> um_features;
   IdHashMap<Group*> um_groups;
   bool keep_observations = false;  // maintain Feature::obs (use_depth_opt)
+  const int* step = nullptr;       // the owning estimator's step counter: objects entering the graph are stamped with it
   template <typename Pred>
   std::vector<Feature*> features_std(Pred p) const {
     std::vector<Feature*> out;
@@ -464,6 +476,7 @@ class Estimator {
   std::map<int, double> ids_to_depths;
   bool sim_initialize_depths = false;
   int gauge_group = -1;
+  int step_counter = 0;  // update steps so far (UpdateStep, manager.cpp:18-46): the clock of Feature::lifetime_ / Group::lifetime_
   int feature_counter = 10000, group_counter = 0;
   // tracker bookkeeping (src/tracker.h)
   bool tracker_initialized = false;
