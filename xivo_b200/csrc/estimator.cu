@@ -495,12 +495,18 @@ class Batch {
         if (n <= 0) continue;
         stg_first[h].h[b] = total;
         stg_n[h].h[b] = n;
-        memcpy(stg[h].h + total, e.stages.data() + cur[b], sizeof(ImuStage) * n);
         total += n;
-        cur[b] += n;
-        more = more || cur[b] < e.stages.size();
       }
       if (!total) break;
+      // the records themselves (~20 KB per sequence and frame) are copied by the pool, not by the driver thread alone
+      pfor(act, [&](int b, int) {
+        const int n = stg_n[h].h[b];
+        if (n > 0) memcpy(stg[h].h + stg_first[h].h[b], est[b]->stages.data() + cur[b], sizeof(ImuStage) * n);
+      });
+      for (int b : act) {
+        cur[b] += stg_n[h].h[b];
+        more = more || cur[b] < est[b]->stages.size();
+      }
       XB_CUDA(up_blob(blobI[h], blobI_fixed + (size_t)total * sizeof(ImuStage), st));
       if (int rc = launch_imu_cov_propagate(st, N, dP, stg[h].d, stg_first[h].d, stg_n[h].d, icst.d, B)) return rc;
       stg_busy[h] = tk2.next + 1;  // the next ticket of st2 lies behind this launch
@@ -1521,9 +1527,9 @@ class Batch {
         if (e.error) return;
         const int n = (int)e.instate_features.size();
         nfeat.h[b] = n;
-        for (auto& kv : e.graph.groups) {
-          Group* g = kv.second;
-          if (g->sind < 0) continue;
+        for (int s2 = 0; s2 < lay.G; ++s2) {  // the groups in the state, by slot
+          Group* g = e.gslot[s2];
+          if (!g) continue;
           double* gh = groups.h + ((size_t)b * lay.G + g->sind) * kGroupDoubles;
           memcpy(gh, g->Rsb.m, 72);
           memcpy(gh + 9, g->Tsb.v, 24);

@@ -438,6 +438,7 @@ class Estimator {
   std::vector<EditOp> edits;  // pending covariance edits, in order
   std::vector<double> diagP;  // last downloaded diagonal of P
   std::vector<char> gsel, fsel;
+  std::vector<Group*> gslot;  // the group in state slot s (null = free): the per-frame tables walk G slots instead of every live group
   Graph graph;
   Pool<Feature> fpool;
   Pool<Group> gpool;
@@ -519,7 +520,8 @@ class Estimator {
   bool initialize_gravity();
   void propagate(bool visual_meas);
   void compose_motion(MotionX& Xs, const V3& V, const V3& gyro, const V3& accel, double dt) const;
-  void record_stage(const MotionX& Xs, const V3& gyro, const V3& accel, double h_enc);
+  static void compose_motion_core(M3& Rsb, V3& Tsb, V3& Vsb, const V3& V, const V3& gc, const V3& ac, const V3& g_s, double dt);
+  void record_stage(const M3& Rsb, const V3& gc, const V3& ac, double h_enc);
   void nominal_step(bool pd, const V3& gyro0, const V3& accel0, double h, bool closes_call);
   void integrate_nominal(const V3& gyro0, const V3& accel0, double dt);
   void state_plus(const double* dX);
