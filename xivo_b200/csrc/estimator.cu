@@ -127,8 +127,23 @@ static StreamWriteValue32Fn stream_write_value32() {
 // copy engine: the frames of a step travel by DMA, and a small cudaMemcpyAsync issued behind that burst waits for it in the engine's
 // FIFO -- measured on the B200 box (profiles/r02i_burst_probe.txt): 750 us for a 165 KB table round trip behind the 157 MB frame burst
 // of one step against 112 us when a kernel reads the table in place (31 / 27 us on an idle link).
+// Four loads in flight per thread: the reads cross PCIe (2-3 us each on an idle link, far more while a frame burst holds it), so the
+// number of round trips, not the byte count, is what a table upload costs.
 __global__ void __launch_bounds__(256) fetch_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned n16) {
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  const unsigned tile = 4u * blockDim.x;
+  for (unsigned base = blockIdx.x * tile; base < n16; base += gridDim.x * tile) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned i = base + k * blockDim.x + threadIdx.x;
+      if (i < n16) v[k] = __ldcv(src + i);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned i = base + k * blockDim.x + threadIdx.x;
+      if (i < n16) dst[i] = v[k];
+    }
+  }
 }
 __global__ void ticket_kernel(unsigned* flag, unsigned value) {
   *flag = value;
@@ -445,7 +460,7 @@ class Batch {
     Prof::get().h2d += bytes;
     if (!b.hd || !bytes) return bytes ? cudaMemcpyAsync(b.d, b.h, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
     const unsigned n16 = (unsigned)((bytes + 15) / 16);  // blobs are allocated in 16-byte units
-    const unsigned ctas = std::max(1u, std::min(32u, (n16 + 1023) / 1024));
+    const unsigned ctas = std::max(1u, std::min(64u, (n16 + 1023) / 1024));
     fetch_kernel<<<ctas, 256, 0, st>>>(reinterpret_cast<const uint4*>(b.hd), reinterpret_cast<uint4*>(b.d), n16);
     g_launches += 1;
     return cudaGetLastError();
@@ -966,6 +981,7 @@ class Batch {
       if (kind[b] == 2) {
         int i = 0, num_failed = 0;
         for (Feature* f : e.tracks) {
+          prefetch_ahead(e.tracks, (size_t)i, 2);
           const float* p1 = pts1.h + ((size_t)b * max_pts + i) * 2;
           if (tstat.h[(size_t)b * max_pts + i]) {
             f->tstatus = TrackStatus::TRACKED;
@@ -1038,6 +1054,7 @@ class Batch {
         if (!dev_decide) e.reset_mask();
         int n = 0;
         for (Feature* f : e.tracks) {
+          prefetch_ahead(e.tracks, (size_t)n, 2);
           if (n >= max_pts) { overflow = 1; return; }
           float* p0 = pts0.h + ((size_t)b * max_pts + n) * 2;
           float* p1 = pts1.h + ((size_t)b * max_pts + n) * 2;
@@ -1488,7 +1505,9 @@ class Batch {
         HostScope hx("x_sub_stage");
         Estimator& e = *est[b];
         int o = sub_off[b];
-        for (Feature* f : e.subfilter_list) {
+        for (size_t i = 0; i < e.subfilter_list.size(); ++i) {
+          Feature* f = e.subfilter_list[i];
+          prefetch_ahead(e.subfilter_list, i, 4);
           SubfilterIn& s = sub_in.h[o++];
           memcpy(s.x, f->x, sizeof(s.x));
           memcpy(s.P, f->P, sizeof(s.P));

@@ -126,6 +126,16 @@ struct alignas(64) Feature {
   double z() const { return std::exp(x[2]); }
   double score() const { return -P[8]; }
 };
+// The per-frame loops walk ~130 features that were last touched a whole round of other sequences ago: ask for the lines of the feature
+// `ahead` positions further down the list while the current one is processed (lines = 2: ids + local state, 4: + sub-filter covariance).
+inline void prefetch_feature(const Feature* f, int lines) {
+  const char* p = reinterpret_cast<const char*>(f);
+  for (int k = 0; k < lines; ++k) __builtin_prefetch(p + 64 * k, 1, 1);
+}
+template <class Vec>
+inline void prefetch_ahead(const Vec& v, size_t i, int lines, size_t ahead = 6) {
+  if (i + ahead < v.size()) prefetch_feature(v[i + ahead], lines);
+}
 
 // One row of the reference's per-feature read-back accessors (src/estimator_accessors.cpp; pybind11/pyxivo.cpp:357-374).
 struct FeatureRow {

@@ -1513,31 +1513,52 @@ __global__ void __launch_bounds__(128) track_accept_kernel(TrackDecideCfg c, con
   if (k == 1) { if (tid == 0) need[b] = c.num_max; return; }
   if (k != 2) { if (tid == 0) need[b] = 0; return; }
   const int stride = (c.cols + 31) >> 5;
+  // the serial walk below touches shared memory only: points and the order-independent part of the test are staged by all threads
+  float* sx = reinterpret_cast<float*>(tmask + (size_t)c.rows * stride);
+  float* sy = sx + c.max_pts;
+  uint8_t* sok = reinterpret_cast<uint8_t*>(sy + c.max_pts);
+  const int n = min(npts[b], c.max_pts);
+  {
+    const float* p0 = pts0 + (size_t)b * c.max_pts * 2;
+    const float* p1 = pts1 + (size_t)b * c.max_pts * 2;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const float2 a = reinterpret_cast<const float2*>(p0)[i], q = reinterpret_cast<const float2*>(p1)[i];
+      bool ok = lkst[(size_t)b * c.max_pts + i] != 0;
+      const double x = (double)q.x, y = (double)q.y;
+      if (ok) {
+        const double dx = (double)a.x - x, dy = (double)a.y - y;
+        const int col = (int)x, row = (int)y;
+        ok = col >= 0 && col < c.cols && row >= 0 && row < c.rows && sqrt(dx * dx + dy * dy) < c.max_disp;
+      }
+      sx[i] = q.x;
+      sy[i] = q.y;
+      sok[i] = ok ? 1 : 0;
+    }
+  }
   mask_reset(tmask, stride, c, tid, blockDim.x);
   __syncthreads();
-  if (tid >= 32) return;
-  const int n = npts[b];
-  const float* p0 = pts0 + (size_t)b * c.max_pts * 2;
-  const float* p1 = pts1 + (size_t)b * c.max_pts * 2;
-  int num_valid = 0;
-  for (int i = 0; i < n; ++i) {
-    bool ok = lkst[(size_t)b * c.max_pts + i] != 0;
-    const double x = (double)p1[2 * i], y = (double)p1[2 * i + 1];
-    if (ok) {
-      const double dx = (double)p0[2 * i] - x, dy = (double)p0[2 * i + 1] - y;
-      ok = mask_free(tmask, stride, c, x, y) && sqrt(dx * dx + dy * dy) < c.max_disp;
+  if (tid < 32) {
+    int num_valid = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!sok[i]) continue;  // warp-uniform
+      const double x = (double)sx[i], y = (double)sy[i];
+      const int col = (int)x, row = (int)y;
+      const bool ok = (tmask[row * stride + (col >> 5)] >> (col & 31)) & 1u;
+      if (ok) {
+        int x0, y0, x1, y1;
+        block_of(x, y, c, &x0, &y0, &x1, &y1);
+        __syncwarp();  // every lane has read the mask word before it changes
+        mask_clear_block(tmask, stride, x0, y0, x1, y1, tid, 32, false);
+        __syncwarp();
+        ++num_valid;
+      } else if (tid == 0) {
+        sok[i] = 0;
+      }
     }
-    if (ok) {
-      int x0, y0, x1, y1;
-      block_of(x, y, c, &x0, &y0, &x1, &y1);
-      __syncwarp();
-      mask_clear_block(tmask, stride, x0, y0, x1, y1, tid, 32, false);
-      __syncwarp();
-      ++num_valid;
-    }
-    if (tid == 0) stat[(size_t)b * c.max_pts + i] = ok ? 1 : 0;
+    if (tid == 0) need[b] = num_valid < c.num_min ? c.num_max - num_valid : 0;
   }
-  if (tid == 0) need[b] = num_valid < c.num_min ? c.num_max - num_valid : 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) stat[(size_t)b * c.max_pts + i] = sok[i];
 }
 
 // Greedy selection of new features from the FAST keypoints of the sequences with need[b] > 0, in the order (score descending, y, x).
@@ -1587,9 +1608,12 @@ __global__ void __launch_bounds__(SEL_THREADS) track_select_kernel(TrackDecideCf
   bool first = true;
   for (;;) {
     // ---- the SEL_CAP-th smallest key among those > s_last (or the largest if fewer remain): MSB-first radix select
+    // the first chunk is small: the budget is a few dozen picks and the best-scored candidates are rarely all on claimed pixels, so one short
+    // sort usually ends the walk; later chunks are full-sized (the chunking does not change the order in which candidates are visited)
+    const int cap = first ? SEL_CAP / 4 : SEL_CAP;
     const unsigned last = s_last;
     unsigned prefix = 0u;
-    int want = SEL_CAP;  // rank (1-based) still to be found inside the current prefix
+    int want = cap;  // rank (1-based) still to be found inside the current prefix
     bool exhausted = false;
     for (int pass = 0; pass < 4; ++pass) {
       const int shift = 24 - 8 * pass;
@@ -1627,15 +1651,15 @@ __global__ void __launch_bounds__(SEL_THREADS) track_select_kernel(TrackDecideCf
       const unsigned k = keys[i];
       if (k == 0xffffffffu || (!first && k <= last) || k > kth) continue;
       const int pos = atomicAdd(&s_cnt, 1);
-      if (pos < SEL_CAP) chunk[pos] = k;
+      if (pos < cap) chunk[pos] = k;
     }
     __syncthreads();
-    const int m = min(s_cnt, SEL_CAP);
-    for (int i = m + tid; i < SEL_CAP; i += SEL_THREADS) chunk[i] = 0xffffffffu;
+    const int m = min(s_cnt, cap);
+    for (int i = m + tid; i < cap; i += SEL_THREADS) chunk[i] = 0xffffffffu;
     __syncthreads();
-    for (int k2 = 2; k2 <= SEL_CAP; k2 <<= 1)  // bitonic sort, ascending
+    for (int k2 = 2; k2 <= cap; k2 <<= 1)  // bitonic sort, ascending
       for (int j = k2 >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < SEL_CAP; i += SEL_THREADS) {
+        for (int i = tid; i < cap; i += SEL_THREADS) {
           const int ixj = i ^ j;
           if (ixj > i) {
             const unsigned a = chunk[i], bb = chunk[ixj];
@@ -1677,7 +1701,7 @@ size_t track_mask_bytes(int rows, int cols) { return (size_t)rows * ((cols + 31)
 
 int launch_track_accept(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts0, const float* pts1,
                         const uint8_t* lkst, uint8_t* stat, int* need, int batch, int* kp_count_to_zero) {
-  const size_t smem = track_mask_bytes(c.rows, c.cols);
+  const size_t smem = track_mask_bytes(c.rows, c.cols) + (size_t)c.max_pts * 9 + 16;
   XB_REQUIRE(smem <= 200 * 1024, "track_accept: image too large for the shared-memory mask");
   static size_t attr = 0;
   if (smem > attr) { XB_CUDA(cudaFuncSetAttribute(track_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
