@@ -40,7 +40,7 @@ WORKLOAD = "BASELINE configs[1]: full VIO 640x480 pinhole + 200 Hz IMU, 150 trac
 METRIC = "VIO frames/sec (640x480 synthetic + 200 Hz IMU)"
 # --config: the other full-pipeline workloads BASELINE.json names (parity cases of tests/test_gpu_estimator.py); the driver's runs use 1
 CONFIGS = {
-    1: dict(cfg="vio_640x480.json", G=4, F=14, seqs=512, streams=16, workload=WORKLOAD, metric=METRIC),
+    1: dict(cfg="vio_640x480.json", G=4, F=14, seqs=1024, streams=32, workload=WORKLOAD, metric=METRIC),  # 1024 x 32: profiles/r02w_sweep.txt
     2: dict(cfg="tumvi_512_equidistant.json", G=15, F=30, seqs=256, streams=8,
             workload="BASELINE configs[2]: TUM-VI equidistant 512x512 + 200 Hz IMU, 200 tracked features, state dim 203 (G=15,F=30)",
             metric="VIO frames/sec (512x512 equidistant synthetic + 200 Hz IMU)"),
@@ -395,6 +395,12 @@ def run_ours(args):
         t = tabs[i]
         ad, rw = t["addr"], t["row"]
         j = f * IMU_PER_FRAME
+        if not device_resident and args.prefetch:
+            # streaming ingest: the copy of frame f + 1 is started before frame f is processed (it overlaps this step's compute) and is
+            # consumed by the next call; every step still uploads exactly one frame per sequence inside the timed region
+            rc = L.xivo_batch_prefetch_frames(bts[i]._h, VP(ad["hptr"] + (f + 1) * rw["hptr"]), ROWS, COLS, CH)
+            if rc != 0:
+                raise RuntimeError(L.xivo_last_error().decode())
         rc = L.xivo_batch_step(bts[i]._h, IMU_PER_FRAME, VP(ad["its"] + j * rw["its"]), VP(ad["ig"] + j * rw["ig"]), VP(ad["ia"] + j * rw["ia"]),
                                VP(ad["fts"] + f * rw["fts"]), VP((ad["dptr"] if device_resident else ad["hptr"]) + f * rw["hptr"]), ROWS, COLS, CH, int(device_resident))
         if rc != 0:
@@ -524,7 +530,7 @@ def run_ours(args):
                                                 f"no two sequences of a GPU read the same frame in the same step",
                                l2_policy=f"inputs larger than L2: a step reads {B * FPS} distinct frames ({B * FPS * fbytes / 1e6:.0f} MB) per GPU out of a {pool_mb:.0f} MB frame pool; "
                                          f"covariances and pyramids are the resident state by design",
-                               message_buffer_size=cfg.get("message_buffer_size", 10), frame_ingest=ingest,
+                               message_buffer_size=cfg.get("message_buffer_size", 10), frame_ingest=ingest, frame_prefetch=bool(args.prefetch),
                                frame_ingest_calibration_ms_per_step=ingest_cal),
                    e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * FPS * fbytes,
                             d2h_bytes_per_step=(r_e2e["prof"]["_d2h_bytes"] / K) if r_e2e["prof"]["_d2h_bytes"] else None, ms_per_step=r_e2e["ms"] / K),
@@ -575,7 +581,7 @@ def main():
     ap.add_argument("--profile-level", type=int, default=1, help="1: kernels + batch-level host phases, 2: + per-sequence host scopes")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configs[n]: 1 = the headline workload (640x480, 150 features, N=89); 2 = TUM-VI equidistant 512x512, 200 features, N=203; 3 = stress 1280x1024, 800 features, N=299")
-    ap.add_argument("--seqs", type=int, default=0, help="independent sequences per GPU, split over --batches lock-step batches (0 = the config's default: 512 / 256 / 128)")
+    ap.add_argument("--seqs", type=int, default=0, help="independent sequences per GPU, split over --batches lock-step batches (0 = the config's default: 1024 / 256 / 128)")
     ap.add_argument("--batches", type=int, default=8, help="separate lock-step xivo_batch handles per GPU, each stepped from its own thread; their per-sequence host code shares the library's worker pool (capped at half the CPU budget)")
     ap.add_argument("--streams", type=int, default=0, help="rendered base streams (texture / trajectory / noise); every sequence replays one of them with its own start delay")
     ap.add_argument("--frames-per-step", type=int, default=8, help="a step = this many consecutive frames (+ IMU) of every sequence: K driver-chosen steps then time seconds, not milliseconds")
@@ -587,6 +593,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cov-update", default="fp64", choices=["fp64", "tf32x3"], help="arithmetic of the covariance downdate (tf32x3 = tcgen05 tensor cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false", help="e2e pass without xivo_batch_prefetch_frames: the upload of a frame starts inside the call that processes it")
     ap.add_argument("--ingest", default="auto", choices=["auto"] + list(INGEST_MODES), help="how pinned host frames reach the device (e2e pass); auto = calibrate both before the timed region")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -62,6 +62,14 @@ int xivo_batch_visual_meas_device(xivo_batch* b, const uint64_t* ts_ns, const ui
 int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const double* gyro, const double* accel,
                     const uint64_t* frame_ts, const uint8_t* const* imgs, int rows, int cols, int channels, int on_device);
 
+/* Optional streaming hint: start the host->device copy of the NEXT frame of every sequence now, so that it
+ * overlaps the step that is still being computed (the reference decouples acquisition from estimation the same
+ * way, with its message queue: /root/reference/src/estimator_process.cpp).  The next xivo_batch_step /
+ * xivo_batch_visual_meas call that is given exactly these host pointers uses the prefetched copy instead of
+ * uploading again; any other call drops the prefetch.  The buffers must stay valid and unchanged until that
+ * call returns.  Results are identical with and without the hint. */
+int xivo_batch_prefetch_frames(xivo_batch* b, const uint8_t* const* imgs, int rows, int cols, int channels);
+
 /* How device-accessible (pinned / registered) host frames are brought into the device frame ring:
  * XIVO_INGEST_ZERO_COPY: one gather launch per call, the SMs read the host memory over PCIe (default);
  * XIVO_INGEST_COPY_ENGINE: one cudaMemcpyAsync per frame on the copy stream.  Process-wide, takes effect at

@@ -363,3 +363,36 @@ def test_step_call_equals_message_by_message():
     assert a.counters(0)["num_instate_features"] > 0
     a.close()
     b.close()
+
+
+def test_prefetched_frames_give_identical_results():
+    """xivo_batch_prefetch_frames only moves the upload of the next frame ahead of the current step: the results are bit-identical; a
+    prefetch that the next call does not consume (other buffers) is dropped without leaving a trace in the frame ring."""
+    cfg = sim.load_cfg(os.path.join(CFG, "vio_640x480.json"))
+    cfg["camera_cfg"].update(rows=240, cols=320, fx=137.5, fy=137.5, cx=160, cy=120)
+    cfg["tracker_cfg"].update(num_features_min=60, num_features_max=80)
+    msgs, _ = sim.image_stream(cfg, duration=1.2, seed=5)
+    a = pyxivo.Batch(cfg, n_seq=2, max_groups=4, max_features=14)
+    b = pyxivo.Batch(cfg, n_seq=2, max_groups=4, max_features=14)
+    imu = [m for m in msgs if m[0] == "imu"]
+    frames = [m for m in msgs if m[0] == "img"]
+    imgs = [np.ascontiguousarray(f[2]) for f in frames]
+    decoy = np.ascontiguousarray(imgs[0][::-1].copy())
+    n = min(len(frames), len(imu) // 8)
+    for f in range(n):
+        chunk = imu[8 * f : 8 * f + 8]
+        fts = frames[f][1]
+        its, g, ac = [ts for _, ts, _ in chunk], [p[0] for _, _, p in chunk], [p[1] for _, _, p in chunk]
+        a.step(its, g, ac, fts, [imgs[f], imgs[f]])
+        if f % 5 == 3:
+            b.prefetch_frames([decoy, decoy])  # replaces the pending prefetch and is never consumed: the step brings other buffers
+        b.step(its, g, ac, fts, [imgs[f], imgs[f]])
+        if f + 1 < n:
+            b.prefetch_frames([imgs[f + 1], imgs[f + 1]])  # streaming order: frame f + 1 travels while the caller handles the results of f
+        for s in range(2):
+            assert np.array_equal(a.gsb(s), b.gsb(s)), f
+            assert a.tracked_features(s)[0].tolist() == b.tracked_features(s)[0].tolist()
+    assert np.array_equal(a.P(0), b.P(0))
+    assert a.counters(0)["num_instate_features"] > 0
+    a.close()
+    b.close()

@@ -287,6 +287,10 @@ class Batch {
   uint8_t* dRing = nullptr;   // B x ring_n x img_bytes
   uint8_t* dPyr = nullptr;    // B x 2 x pd.total
   std::vector<int> ring_next, prev_slot;
+  // xivo_batch_prefetch_frames: host pointers and ring slots of the frames whose upload is already in flight on st_copy
+  std::vector<const uint8_t*> pref_ptr;
+  std::vector<int> pref_slot;
+  bool pref_valid = false;
   Mirror<unsigned long long> off_prev, off_cur;
   Mirror<const uint8_t*> frame_ptr, ingest_ptr;  // ring slot of the frame being tracked; sources of a device-resident ingest
   Mirror<unsigned long long> ingest_off;
@@ -627,6 +631,35 @@ class Batch {
     }
     return static_cast<const uint8_t*>(at.devicePointer);
   }
+  // Ring slots of the frame about to be ingested.  If xivo_batch_prefetch_frames was called with exactly these host buffers, their upload is
+  // already enqueued (*uploaded = true) and its slots are taken over; any other prefetch is abandoned and its slots are handed out again
+  // (st_copy is in order: the new upload lands after the abandoned one).
+  void take_slots(const uint8_t* const* imgs, bool on_device, std::vector<int>& slot_of, bool* uploaded) {
+    bool match = pref_valid && !on_device;
+    if (match)
+      for (int s = 0; s < B; ++s)
+        if (pref_ptr[s] != imgs[s]) { match = false; break; }
+    if (pref_valid && !match)
+      for (int s = 0; s < B; ++s) ring_next[s] = pref_slot[s];
+    pref_valid = false;
+    for (int s = 0; s < B; ++s) {
+      if (match) { slot_of[s] = pref_slot[s]; continue; }
+      const int slot = ring_next[s];
+      ring_next[s] = (slot + 1) % ring_n;
+      slot_of[s] = slot;
+    }
+    *uploaded = match;
+  }
+  int prefetch_frames(const uint8_t* const* imgs, size_t ib) {
+    std::vector<int> slot_of(B);
+    bool dummy = false;
+    take_slots(imgs, true, slot_of, &dummy);  // (drops an earlier prefetch that was never consumed)
+    if (int rc = upload_frames(imgs, slot_of, false, ib)) return rc;
+    pref_ptr.assign(imgs, imgs + B);
+    pref_slot = slot_of;
+    pref_valid = true;
+    return 0;
+  }
   int upload_frames(const uint8_t* const* imgs, const std::vector<int>& slot_of, bool on_device, size_t ib) {
     HostScope hsu("issue_upload_frames");
     const bool zero_copy = g_frame_ingest.load(std::memory_order_relaxed) == 0;
@@ -709,7 +742,7 @@ class Batch {
     // not fit into shared memory, or XIVO_HOST_TRACKER_DECISIONS=1 asks for the host path (parity tests compare the two)
     {
       const char* hd = getenv("XIVO_HOST_TRACKER_DECISIONS");
-      dev_decide = !e0.tc.do_outlier_rejection && !e0.tc.extract_descriptor && track_mask_bytes(rows, cols) <= 200 * 1024 && !(hd && hd[0] == '1');
+      dev_decide = !e0.tc.do_outlier_rejection && !e0.tc.extract_descriptor && track_mask_bytes(rows, cols) <= 200 * 1024 && max_pts <= 1024 && !(hd && hd[0] == '1');
     }
     desc_on = e0.tc.extract_descriptor;
     if (ok && desc_on) {
@@ -1898,15 +1931,15 @@ static int visual_meas_impl(xivo_batch* b, const uint64_t* ts_ns, const uint8_t*
     const size_t ib = (size_t)rows * cols * channels;
     std::vector<Msg> in(B_.B);
     std::vector<int> slot_of(B_.B);
+    bool uploaded = false;
+    B_.take_slots(imgs + s0, on_device, slot_of, &uploaded);
     for (int s = 0; s < B_.B; ++s) {
-      const int slot = B_.ring_next[s];
-      B_.ring_next[s] = (slot + 1) % B_.ring_n;
-      slot_of[s] = slot;
       in[s].ts = ts_ns[s0 + s];
       in[s].type = tracker_only ? 2 : 1;
-      in[s].img_slot = slot;
+      in[s].img_slot = slot_of[s];
     }
-    if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device, ib)) return rc;
+    if (!uploaded)
+      if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device, ib)) return rc;
     const int rc = B_.ingest(in);
     const int rc2 = B_.ingest_done();
     return rc ? rc : rc2;
@@ -1935,6 +1968,8 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
     const size_t ib = (size_t)rows * cols * channels;
     std::vector<std::vector<Msg>> in(B_.B);
     std::vector<int> slot_of(B_.B);
+    bool uploaded = false;
+    B_.take_slots(imgs + s0, on_device != 0, slot_of, &uploaded);
     {
       HostScope hm("marshal");
       for (int s = 0; s < B_.B; ++s) {
@@ -1947,19 +1982,28 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
           memcpy(m.gyro, gyro + o * 3, 24);
           memcpy(m.accel, accel + o * 3, 24);
         }
-        const int slot = B_.ring_next[s];
-        B_.ring_next[s] = (slot + 1) % B_.ring_n;
-        slot_of[s] = slot;
         Msg& v = in[s][n_imu];
         v.ts = frame_ts[s0 + s];
         v.type = 1;
-        v.img_slot = slot;
+        v.img_slot = slot_of[s];
       }
     }
-    if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device != 0, ib)) return rc;
+    if (!uploaded)
+      if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device != 0, ib)) return rc;
     const int rc = B_.ingest_many(in);
     const int rc2 = B_.ingest_done();
     return rc ? rc : rc2;
+  });
+}
+
+int xivo_batch_prefetch_frames(xivo_batch* b, const uint8_t* const* imgs, int rows, int cols, int channels) {
+  BATCH_BEGIN;
+  XB_REQUIRE(imgs && rows > 0 && cols > 0, "prefetch_frames: bad arguments");
+  for (int s = 0; s < S_.total; ++s) XB_REQUIRE(imgs[s], "prefetch_frames: null image");
+  return S_.run([&](int l) {
+    Batch& B_ = *S_.lanes[l];
+    if (int rc = B_.ensure_images(rows, cols, channels)) return rc;
+    return B_.prefetch_frames(imgs + S_.first[l], (size_t)rows * cols * channels);
   });
 }
 

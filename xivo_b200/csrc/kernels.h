@@ -40,6 +40,7 @@ struct TrackDecideCfg {
   double max_disp;
 };
 size_t track_mask_bytes(int rows, int cols);
+size_t track_accept_smem_bytes(int max_pts);
 int launch_track_accept(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts0, const float* pts1,
                         const uint8_t* lkst, uint8_t* stat, int* need, int batch, int* kp_count_to_zero = nullptr);
 int launch_track_select(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts1, const uint8_t* stat,

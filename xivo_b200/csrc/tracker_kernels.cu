@@ -1502,54 +1502,74 @@ __device__ __forceinline__ bool mask_free(const unsigned* m, int stride, const T
 
 // kind[b]: 1 = first frame (detection only), 2 = tracked by LK, 3 = empty list (nothing to do), 0 = inactive.
 // Outputs: stat[b][i] = feature i keeps its track; need[b] = features the detection should add (0 = none).
+// The reference walks the list while a mask of claimed pixels grows (tracker.cpp:571-589).  The mask only ever loses the margin band and
+// the (2 mask_half + 1)^2 blocks of the tracks accepted so far, so "pixel of track i still free" == "inside the margin band and in no
+// block of an earlier ACCEPTED track": all threads build the bit matrix C[i] = {j : block(j) contains pixel(i)}, then warp 0 resolves the
+// order dependence with one AND + vote per track (lane l keeps word l of the accepted set) instead of clearing bitmap blocks.
 __global__ void __launch_bounds__(128) track_accept_kernel(TrackDecideCfg c, const int* __restrict__ kind, const int* __restrict__ npts,
                                                            const float* __restrict__ pts0, const float* __restrict__ pts1,
                                                            const uint8_t* __restrict__ lkst, uint8_t* __restrict__ stat, int* __restrict__ need,
                                                            int* __restrict__ kp_count) {
-  extern __shared__ unsigned tmask[];
+  extern __shared__ unsigned acc_smem[];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (kp_count && tid == 0) kp_count[b] = 0;  // the keypoint cursor of the detection that follows in the stream (saves its memset call)
   const int k = kind[b];
   if (k == 1) { if (tid == 0) need[b] = c.num_max; return; }
   if (k != 2) { if (tid == 0) need[b] = 0; return; }
-  const int stride = (c.cols + 31) >> 5;
-  // the serial walk below touches shared memory only: points and the order-independent part of the test are staged by all threads
-  float* sx = reinterpret_cast<float*>(tmask + (size_t)c.rows * stride);
-  float* sy = sx + c.max_pts;
-  uint8_t* sok = reinterpret_cast<uint8_t*>(sy + c.max_pts);
   const int n = min(npts[b], c.max_pts);
+  const int nw = (c.max_pts + 31) >> 5;  // <= 32 (launch_track_accept)
+  int* px = reinterpret_cast<int*>(acc_smem);
+  int* py = px + c.max_pts;
+  int* bx0 = py + c.max_pts;
+  int* by0 = bx0 + c.max_pts;
+  int* bx1 = by0 + c.max_pts;
+  int* by1 = bx1 + c.max_pts;
+  unsigned* C = reinterpret_cast<unsigned*>(by1 + c.max_pts);
+  uint8_t* sok = reinterpret_cast<uint8_t*>(C + (size_t)c.max_pts * nw);
   {
-    const float* p0 = pts0 + (size_t)b * c.max_pts * 2;
-    const float* p1 = pts1 + (size_t)b * c.max_pts * 2;
+    const float2* p0 = reinterpret_cast<const float2*>(pts0 + (size_t)b * c.max_pts * 2);
+    const float2* p1 = reinterpret_cast<const float2*>(pts1 + (size_t)b * c.max_pts * 2);
     for (int i = tid; i < n; i += blockDim.x) {
-      const float2 a = reinterpret_cast<const float2*>(p0)[i], q = reinterpret_cast<const float2*>(p1)[i];
+      const float2 a = p0[i], q = p1[i];
       bool ok = lkst[(size_t)b * c.max_pts + i] != 0;
       const double x = (double)q.x, y = (double)q.y;
+      const int col = (int)x, row = (int)y;
       if (ok) {
         const double dx = (double)a.x - x, dy = (double)a.y - y;
-        const int col = (int)x, row = (int)y;
-        ok = col >= 0 && col < c.cols && row >= 0 && row < c.rows && sqrt(dx * dx + dy * dy) < c.max_disp;
+        // mask_valid on the fresh mask (inside the image and the margin band) + the displacement test
+        ok = col >= 0 && col < c.cols && row >= 0 && row < c.rows && row >= c.margin && row < c.rows - c.margin && col >= c.margin &&
+             col <= c.cols - c.margin - 1 && sqrt(dx * dx + dy * dy) < c.max_disp;
       }
-      sx[i] = q.x;
-      sy[i] = q.y;
+      int x0, y0, x1, y1;
+      block_of(x, y, c, &x0, &y0, &x1, &y1);
+      px[i] = col; py[i] = row;
+      bx0[i] = x0; by0[i] = y0; bx1[i] = x1; by1[i] = y1;
       sok[i] = ok ? 1 : 0;
     }
   }
-  mask_reset(tmask, stride, c, tid, blockDim.x);
+  __syncthreads();
+  for (int item = tid; item < n * nw; item += blockDim.x) {
+    const int i = item / nw, w = item - i * nw;
+    unsigned bits = 0u;
+    if (32 * w < i && sok[i]) {  // only earlier tracks can have claimed the pixel
+      const int x = px[i], y = py[i], jend = min(32, i - 32 * w);
+      for (int jj = 0; jj < jend; ++jj) {
+        const int j = 32 * w + jj;
+        if (x >= bx0[j] && x <= bx1[j] && y >= by0[j] && y <= by1[j]) bits |= 1u << jj;
+      }
+    }
+    C[item] = bits;
+  }
   __syncthreads();
   if (tid < 32) {
+    unsigned acc = 0u;  // lane l: tracks 32 l .. 32 l + 31 accepted so far
     int num_valid = 0;
     for (int i = 0; i < n; ++i) {
       if (!sok[i]) continue;  // warp-uniform
-      const double x = (double)sx[i], y = (double)sy[i];
-      const int col = (int)x, row = (int)y;
-      const bool ok = (tmask[row * stride + (col >> 5)] >> (col & 31)) & 1u;
-      if (ok) {
-        int x0, y0, x1, y1;
-        block_of(x, y, c, &x0, &y0, &x1, &y1);
-        __syncwarp();  // every lane has read the mask word before it changes
-        mask_clear_block(tmask, stride, x0, y0, x1, y1, tid, 32, false);
-        __syncwarp();
+      const unsigned cw = tid < nw ? C[i * nw + tid] : 0u;
+      const bool claimed = __any_sync(0xffffffffu, (cw & acc) != 0u);
+      if (!claimed) {
+        if (tid == (i >> 5)) acc |= 1u << (i & 31);
         ++num_valid;
       } else if (tid == 0) {
         sok[i] = 0;
@@ -1560,6 +1580,7 @@ __global__ void __launch_bounds__(128) track_accept_kernel(TrackDecideCfg c, con
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) stat[(size_t)b * c.max_pts + i] = sok[i];
 }
+size_t track_accept_smem_bytes(int max_pts) { return (size_t)max_pts * (6 * 4 + ((max_pts + 31) / 32) * 4 + 1) + 16; }
 
 // Greedy selection of new features from the FAST keypoints of the sequences with need[b] > 0, in the order (score descending, y, x).
 // kp: packed (y << 20 | x << 8 | score), rewritten in place as sort keys ((255 - score) << 24 | y << 12 | x; unique per pixel).
@@ -1701,8 +1722,8 @@ size_t track_mask_bytes(int rows, int cols) { return (size_t)rows * ((cols + 31)
 
 int launch_track_accept(cudaStream_t st, const TrackDecideCfg& c, const int* kind, const int* npts, const float* pts0, const float* pts1,
                         const uint8_t* lkst, uint8_t* stat, int* need, int batch, int* kp_count_to_zero) {
-  const size_t smem = track_mask_bytes(c.rows, c.cols) + (size_t)c.max_pts * 9 + 16;
-  XB_REQUIRE(smem <= 200 * 1024, "track_accept: image too large for the shared-memory mask");
+  const size_t smem = track_accept_smem_bytes(c.max_pts);
+  XB_REQUIRE(c.max_pts <= 1024 && smem <= 200 * 1024, "track_accept: more than 1024 tracks per sequence");
   static size_t attr = 0;
   if (smem > attr) { XB_CUDA(cudaFuncSetAttribute(track_accept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
   ProfScope ps("track_accept", st);

@@ -112,6 +112,13 @@ class Batch:
         self._keep = imgs
         _check(capi.lib().xivo_batch_visual_meas(self._h, _p(ts), ptrs, rows, cols, ch, int(bool(tracker_only))), "xivo_batch_visual_meas")
 
+    def prefetch_frames(self, imgs):
+        """Start uploading the frames of the NEXT visual_meas / step call (same arrays) while the current one is computed."""
+        imgs, rows, cols, ch = self._check_images(imgs)
+        ptrs = (C.c_void_p * self.n)(*[i.ctypes.data for i in imgs])
+        self._keep_next = imgs
+        _check(capi.lib().xivo_batch_prefetch_frames(self._h, ptrs, rows, cols, ch), "xivo_batch_prefetch_frames")
+
     def step(self, imu_ts, gyro, accel, frame_ts, imgs):
         """n_imu InertialMeas + one VisualMeas per sequence in one call (xivo_batch_step).
         imu_ts: (n_imu, n) or (n_imu,), gyro/accel: (n_imu, n, 3) or (n_imu, 3)."""
