@@ -235,6 +235,53 @@ def cpu_budget():
     return n
 
 
+def parse_cpulist(text):
+    out = []
+    for tok in text.strip().split(","):
+        if not tok:
+            continue
+        a, _, b = tok.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def pin_to_gpu_numa_node(local, lws):
+    """Narrow this process to the CPUs of the NUMA node its GPU hangs off (pinned frame pool, table blobs and the library's host threads
+    then sit next to the GPU's PCIe root) and tell the library which of the ranks of THAT node this one is (XIVO_CPU_SLICE), so that the
+    ranks of a node split its cores without overlap.  No-op where sysfs has no NUMA information."""
+    try:
+        import torch
+
+        def node_of(i):
+            try:
+                p = torch.cuda.get_device_properties(i)
+                addr = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            except AttributeError:  # older property set: ask NVML (same enumeration when CUDA_VISIBLE_DEVICES is unset)
+                import pynvml
+
+                pynvml.nvmlInit()
+                bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(i)).busId
+                bus = bus.decode() if isinstance(bus, bytes) else bus
+                addr = bus.lower()[-12:]
+            return int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read())
+
+        nodes = [node_of(i) for i in range(max(lws, local + 1))]
+        me = nodes[local]
+        if me < 0:
+            return None
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(set(parse_cpulist(open(f"/sys/devices/system/node/node{me}/cpulist").read())) & allowed)
+        peers = [i for i in range(lws) if nodes[i] == me] or [local]
+        if len(cpus) < 2 * len(peers):
+            return None
+        os.sched_setaffinity(0, cpus)
+        os.environ["XIVO_CPU_SLICE"] = f"{peers.index(local)}/{len(peers)}"
+        return dict(node=me, cpus=len(cpus), rank_in_node=peers.index(local), ranks_in_node=len(peers))
+    except Exception as e:  # noqa: BLE001 - placement is an optimisation, never a reason to fail
+        log("numa placement skipped:", repr(e))
+        return None
+
+
 def cpu_baseline_entry(r, cores, frames, wall_s):
     """`cpu_baseline` object from oracle/cpu_baseline.py's result.  kind "reference": a frame costs the OpenCV tracker calls (cv2 LK + FAST
     on the image stream) plus the reference's OWN estimator (oracle/_ref/libxivo_ref_*.so, its unmodified sources) on a point-cloud
@@ -338,6 +385,7 @@ def run_ours(args):
     from xivo_b200 import capi, pyxivo, replicas
 
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local, lws) if args.numa else None
     if world > 1:
         import torch.distributed as dist
 
@@ -390,21 +438,32 @@ def run_ours(args):
         o += nb
     pool = ThreadPoolExecutor(NB)
     VP = C.c_void_p
+    pending = [-1] * NB  # per batch: the frame whose upload xivo_batch_prefetch_frames has started
 
     def step_one(i, f, device_resident):
         t = tabs[i]
         ad, rw = t["addr"], t["row"]
         j = f * IMU_PER_FRAME
-        if not device_resident and args.prefetch:
-            # streaming ingest: the copy of frame f + 1 is started before frame f is processed (it overlaps this step's compute) and is
-            # consumed by the next call; every step still uploads exactly one frame per sequence inside the timed region
-            rc = L.xivo_batch_prefetch_frames(bts[i]._h, VP(ad["hptr"] + (f + 1) * rw["hptr"]), ROWS, COLS, CH)
-            if rc != 0:
+        stream = not device_resident and args.prefetch
+
+        def prefetch_next():
+            # streaming ingest: the copy of frame f + 1 overlaps the computation of frame f and is consumed by the next call; every step
+            # still uploads exactly one frame per sequence inside the timed region
+            if L.xivo_batch_prefetch_frames(bts[i]._h, VP(ad["hptr"] + (f + 1) * rw["hptr"]), ROWS, COLS, CH) != 0:
                 raise RuntimeError(L.xivo_last_error().decode())
+            pending[i] = f + 1
+
+        primed = stream and pending[i] == f  # frame f is already on its way (prefetched by the previous call)
+        if primed:
+            prefetch_next()
+        else:
+            pending[i] = -1  # whatever was pending is dropped by the library: these are other buffers
         rc = L.xivo_batch_step(bts[i]._h, IMU_PER_FRAME, VP(ad["its"] + j * rw["its"]), VP(ad["ig"] + j * rw["ig"]), VP(ad["ia"] + j * rw["ia"]),
                                VP(ad["fts"] + f * rw["fts"]), VP((ad["dptr"] if device_resident else ad["hptr"]) + f * rw["hptr"]), ROWS, COLS, CH, int(device_resident))
         if rc != 0:
             raise RuntimeError(L.xivo_last_error().decode())
+        if stream and not primed:
+            prefetch_next()
         return bts[i].gsb(0)  # host read of the step's result (pose); the err/P_mm D2H happened inside the call
 
     def frame_step(f, device_resident, serial=False):
@@ -530,7 +589,7 @@ def run_ours(args):
                                                 f"no two sequences of a GPU read the same frame in the same step",
                                l2_policy=f"inputs larger than L2: a step reads {B * FPS} distinct frames ({B * FPS * fbytes / 1e6:.0f} MB) per GPU out of a {pool_mb:.0f} MB frame pool; "
                                          f"covariances and pyramids are the resident state by design",
-                               message_buffer_size=cfg.get("message_buffer_size", 10), frame_ingest=ingest, frame_prefetch=bool(args.prefetch),
+                               message_buffer_size=cfg.get("message_buffer_size", 10), frame_ingest=ingest, frame_prefetch=bool(args.prefetch), numa=numa,
                                frame_ingest_calibration_ms_per_step=ingest_cal),
                    e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * FPS * fbytes,
                             d2h_bytes_per_step=(r_e2e["prof"]["_d2h_bytes"] / K) if r_e2e["prof"]["_d2h_bytes"] else None, ms_per_step=r_e2e["ms"] / K),
@@ -593,7 +652,8 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cov-update", default="fp64", choices=["fp64", "tf32x3"], help="arithmetic of the covariance downdate (tf32x3 = tcgen05 tensor cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false", help="e2e pass without xivo_batch_prefetch_frames: the upload of a frame starts inside the call that processes it")
+    ap.add_argument("--no-numa", dest="numa", action="store_false", help="leave the process on every allowed CPU instead of the NUMA node of its GPU")
+    ap.add_argument("--prefetch", action="store_true", help="e2e pass with xivo_batch_prefetch_frames (the upload of frame k + 1 is started before frame k is processed); measured neutral on the B200 box (profiles/r02z_sweep.txt), so the default is the plain call")
     ap.add_argument("--ingest", default="auto", choices=["auto"] + list(INGEST_MODES), help="how pinned host frames reach the device (e2e pass); auto = calibrate both before the timed region")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -64,10 +64,12 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
 
 /* Optional streaming hint: start the host->device copy of the NEXT frame of every sequence now, so that it
  * overlaps the step that is still being computed (the reference decouples acquisition from estimation the same
- * way, with its message queue: /root/reference/src/estimator_process.cpp).  The next xivo_batch_step /
- * xivo_batch_visual_meas call that is given exactly these host pointers uses the prefetched copy instead of
- * uploading again; any other call drops the prefetch.  The buffers must stay valid and unchanged until that
- * call returns.  Results are identical with and without the hint. */
+ * way, with its message queue: /root/reference/src/estimator_process.cpp).  Up to two prefetched frames may
+ * be pending (the one the next call consumes and the one after it), consumed oldest first: an
+ * xivo_batch_step / xivo_batch_visual_meas call that is given exactly the host pointers of the oldest one uses
+ * its copy instead of uploading again; a call with any other buffers drops every pending prefetch.  The
+ * buffers must stay valid and unchanged until the call that consumes them returns.  Results are identical
+ * with and without the hint. */
 int xivo_batch_prefetch_frames(xivo_batch* b, const uint8_t* const* imgs, int rows, int cols, int channels);
 
 /* How device-accessible (pinned / registered) host frames are brought into the device frame ring:

@@ -138,3 +138,27 @@ def test_config_selection_sets_the_workload_constants():
             assert bench.load_cfg()["camera_cfg"]["rows"] == rows
     finally:
         bench.select_config(1)
+
+
+def test_stream_tables_never_hand_one_frame_to_two_sequences_at_the_default_size():
+    """bench.py's claim `no two sequences of a GPU read the same frame in the same step` for the default workload (1024 sequences over
+    32 base streams, start delays of 3 frames inside a 100-frame period)."""
+    import numpy as np
+
+    import bench
+
+    c = bench.CONFIGS[1]
+    n, s0 = c["seqs"], c["streams"]
+    assert (n // s0) * bench.STAGGER <= bench.PERIOD_FRAMES
+    fidx, iidx, base = bench.stream_tables(n, s0, 260)
+    key = base[None, :].astype(np.int64) * 100000 + fidx
+    for f in range(bench.REST_FRAMES + (n // s0) * bench.STAGGER + 2, 260):  # once every sequence has left its rest phase
+        assert len(np.unique(key[f])) == n, f
+
+
+def test_cpulist_parser_and_numa_placement_is_optional():
+    import bench
+
+    assert bench.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert bench.parse_cpulist("") == []
+    assert bench.pin_to_gpu_numa_node(0, 1) is None  # no GPU here: placement is skipped, never an error

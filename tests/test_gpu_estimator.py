@@ -379,16 +379,29 @@ def test_prefetched_frames_give_identical_results():
     imgs = [np.ascontiguousarray(f[2]) for f in frames]
     decoy = np.ascontiguousarray(imgs[0][::-1].copy())
     n = min(len(frames), len(imu) // 8)
+    pending = []  # what the library holds, oldest first (frame index, or "decoy")
     for f in range(n):
         chunk = imu[8 * f : 8 * f + 8]
         fts = frames[f][1]
         its, g, ac = [ts for _, ts, _ in chunk], [p[0] for _, _, p in chunk], [p[1] for _, _, p in chunk]
         a.step(its, g, ac, fts, [imgs[f], imgs[f]])
-        if f % 5 == 3:
-            b.prefetch_frames([decoy, decoy])  # replaces the pending prefetch and is never consumed: the step brings other buffers
+        primed = bool(pending) and pending[0] == f
+        if primed and len(pending) < 2:
+            # streaming order: frame f is on its way already; frame f + 1 (or, now and then, buffers that are never consumed) starts to travel
+            if f % 5 == 3:
+                b.prefetch_frames([decoy, decoy])
+                pending.append("decoy")
+            elif f + 1 < n:
+                b.prefetch_frames([imgs[f + 1], imgs[f + 1]])
+                pending.append(f + 1)
+        if len(pending) == 2 and f == 2:
+            with pytest.raises(pyxivo.XivoError):
+                b.prefetch_frames([decoy, decoy])  # a third pending frame is refused, nothing changes
         b.step(its, g, ac, fts, [imgs[f], imgs[f]])
-        if f + 1 < n:
-            b.prefetch_frames([imgs[f + 1], imgs[f + 1]])  # streaming order: frame f + 1 travels while the caller handles the results of f
+        pending = pending[1:] if primed else []  # a step with other buffers drops everything that was pending
+        if not pending and f + 1 < n:
+            b.prefetch_frames([imgs[f + 1], imgs[f + 1]])  # (re)prime after the call
+            pending.append(f + 1)
         for s in range(2):
             assert np.array_equal(a.gsb(s), b.gsb(s)), f
             assert a.tracked_features(s)[0].tolist() == b.tracked_features(s)[0].tolist()

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <stdexcept>
@@ -288,9 +289,8 @@ class Batch {
   uint8_t* dPyr = nullptr;    // B x 2 x pd.total
   std::vector<int> ring_next, prev_slot;
   // xivo_batch_prefetch_frames: host pointers and ring slots of the frames whose upload is already in flight on st_copy
-  std::vector<const uint8_t*> pref_ptr;
-  std::vector<int> pref_slot;
-  bool pref_valid = false;
+  struct Prefetched { std::vector<const uint8_t*> ptr; std::vector<int> slot; };
+  std::deque<Prefetched> pref;  // oldest first; at most two (the frame about to be consumed and the one after it)
   Mirror<unsigned long long> off_prev, off_cur;
   Mirror<const uint8_t*> frame_ptr, ingest_ptr;  // ring slot of the frame being tracked; sources of a device-resident ingest
   Mirror<unsigned long long> ingest_off;
@@ -631,33 +631,42 @@ class Batch {
     }
     return static_cast<const uint8_t*>(at.devicePointer);
   }
-  // Ring slots of the frame about to be ingested.  If xivo_batch_prefetch_frames was called with exactly these host buffers, their upload is
-  // already enqueued (*uploaded = true) and its slots are taken over; any other prefetch is abandoned and its slots are handed out again
-  // (st_copy is in order: the new upload lands after the abandoned one).
-  void take_slots(const uint8_t* const* imgs, bool on_device, std::vector<int>& slot_of, bool* uploaded) {
-    bool match = pref_valid && !on_device;
-    if (match)
-      for (int s = 0; s < B; ++s)
-        if (pref_ptr[s] != imgs[s]) { match = false; break; }
-    if (pref_valid && !match)
-      for (int s = 0; s < B; ++s) ring_next[s] = pref_slot[s];
-    pref_valid = false;
+  // Ring slots of the frame about to be ingested.  If the oldest pending xivo_batch_prefetch_frames call brought exactly these host buffers,
+  // their upload is already enqueued (*uploaded = true) and its slots are taken over; otherwise every pending prefetch is abandoned and its
+  // slots are handed out again (st_copy is in order: the new upload lands after the abandoned ones).
+  void fresh_slots(std::vector<int>& slot_of) {
     for (int s = 0; s < B; ++s) {
-      if (match) { slot_of[s] = pref_slot[s]; continue; }
       const int slot = ring_next[s];
       ring_next[s] = (slot + 1) % ring_n;
       slot_of[s] = slot;
     }
-    *uploaded = match;
+  }
+  void take_slots(const uint8_t* const* imgs, bool on_device, std::vector<int>& slot_of, bool* uploaded) {
+    bool match = !pref.empty() && !on_device;
+    if (match)
+      for (int s = 0; s < B; ++s)
+        if (pref.front().ptr[s] != imgs[s]) { match = false; break; }
+    if (match) {
+      slot_of = pref.front().slot;
+      pref.pop_front();
+      *uploaded = true;
+      return;
+    }
+    if (!pref.empty()) {
+      for (int s = 0; s < B; ++s) ring_next[s] = pref.front().slot[s];
+      pref.clear();
+    }
+    fresh_slots(slot_of);
+    *uploaded = false;
   }
   int prefetch_frames(const uint8_t* const* imgs, size_t ib) {
-    std::vector<int> slot_of(B);
-    bool dummy = false;
-    take_slots(imgs, true, slot_of, &dummy);  // (drops an earlier prefetch that was never consumed)
-    if (int rc = upload_frames(imgs, slot_of, false, ib)) return rc;
-    pref_ptr.assign(imgs, imgs + B);
-    pref_slot = slot_of;
-    pref_valid = true;
+    if (pref.size() >= 2) return fail(XIVO_ERR_STATE, "prefetch_frames: two prefetched frames are pending already (consume one with a step / visual_meas call first)");
+    Prefetched p;
+    p.slot.resize(B);
+    fresh_slots(p.slot);
+    if (int rc = upload_frames(imgs, p.slot, false, ib)) return rc;
+    p.ptr.assign(imgs, imgs + B);
+    pref.push_back(std::move(p));
     return 0;
   }
   int upload_frames(const uint8_t* const* imgs, const std::vector<int>& slot_of, bool on_device, size_t ib) {
@@ -701,20 +710,24 @@ class Batch {
         ++s;
       }
     }
+    return ring_uploaded(distinct_slots(slot_of));
+  }
+  static std::vector<int> distinct_slots(const std::vector<int>& slot_of) {
     std::vector<int> used;
     for (int k : slot_of)
       if (std::find(used.begin(), used.end(), k) == used.end()) used.push_back(k);
-    return ring_uploaded(used);
+    return used;
   }
   // mark the uploads enqueued on st_copy for ring slot `slot` (call after the last one)
   int ring_uploaded(const std::vector<int>& slots_used) {
     for (int k : slots_used) XB_CUDA(cudaEventRecord(ring_ev[k], st_copy));
     return 0;
   }
-  // the caller's frame buffers are free again once the uploads have landed
-  int ingest_done() {
+  // the caller's frame buffers are free again once THEIR uploads have landed (the events of the ring slots they went to: a prefetched copy
+  // of the next frame may already be queued behind them on st_copy and must not be waited for)
+  int ingest_done(const std::vector<int>& slot_of) {
     HostScope hsw("wait_ingest_done");
-    XB_CUDA(cudaStreamSynchronize(st_copy));
+    for (int k : distinct_slots(slot_of)) XB_CUDA(cudaEventSynchronize(ring_ev[k]));
     return 0;
   }
 
@@ -1941,7 +1954,7 @@ static int visual_meas_impl(xivo_batch* b, const uint64_t* ts_ns, const uint8_t*
     if (!uploaded)
       if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device, ib)) return rc;
     const int rc = B_.ingest(in);
-    const int rc2 = B_.ingest_done();
+    const int rc2 = B_.ingest_done(slot_of);
     return rc ? rc : rc2;
   });
 }
@@ -1991,7 +2004,7 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
     if (!uploaded)
       if (int rc = B_.upload_frames(imgs + s0, slot_of, on_device != 0, ib)) return rc;
     const int rc = B_.ingest_many(in);
-    const int rc2 = B_.ingest_done();
+    const int rc2 = B_.ingest_done(slot_of);
     return rc ? rc : rc2;
   });
 }

@@ -303,8 +303,15 @@ class WorkPool {
     std::vector<std::vector<int>> cs;
     if (pin) cs = cores();
     if (!cs.empty()) {
-      // this rank's contiguous share of the cores (ranks of one node must not overlap)
-      const size_t lo = cs.size() * (size_t)local_rank / local_world, hi = cs.size() * (size_t)(local_rank + 1) / local_world;
+      // this rank's contiguous share of the cores (ranks of one node must not overlap).  XIVO_CPU_SLICE="i/n" overrides the torchrun
+      // numbering: an application that has already narrowed the affinity mask to the NUMA node of its GPU says which of the n ranks of
+      // THAT node it is (bench.py does)
+      int si = local_rank, sn = local_world;
+      if (const char* sl = getenv("XIVO_CPU_SLICE")) {
+        int a = 0, b = 0;
+        if (sscanf(sl, "%d/%d", &a, &b) == 2 && b > 0 && a >= 0 && a < b) { si = a; sn = b; }
+      }
+      const size_t lo = cs.size() * (size_t)si / sn, hi = cs.size() * (size_t)(si + 1) / sn;
       std::vector<std::vector<int>> mine(cs.begin() + lo, cs.begin() + std::max(hi, lo + 1));
       if (pin >= 2) {
         const std::vector<double> load = cpu_load(100);
