@@ -1000,8 +1000,10 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(const uint8_t* __rest
 // keeps its <= 8 template samples (I, Ix, Iy) in registers for the whole level.  Per iteration a lane
 // loads 2 bytes per sample slot (rows y, y+1 of its column) and gets the x+1 neighbours by shuffle,
 // instead of 4 loads + 3 shared-memory reads; no integer divisions remain in the loops.
-template <int WIN, bool PACK, int MINB>
-__global__ void __launch_bounds__(LK_WARPS * 32, PACK ? MINB : 1) lk_kernel_fast(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
+// (6 CTAs of 4 warps per SM at 80 registers.  A 64-register cap for 8 CTAs spills a few words and measured 7 % slower on the B200:
+// 334 against 312 us per launch of 128 sequences, profiles/r02aa_lk_occupancy.txt.)
+template <int WIN, bool PACK>
+__global__ void __launch_bounds__(LK_WARPS * 32, PACK ? 6 : 1) lk_kernel_fast(const uint8_t* __restrict__ prev_pyr, const uint8_t* __restrict__ next_pyr,
                                                                unsigned long long pyr_stride,
                                                                const unsigned long long* __restrict__ prev_off,
                                                                const unsigned long long* __restrict__ next_off, PyrDesc d,
@@ -1267,19 +1269,11 @@ __global__ void __launch_bounds__(LK_WARPS * 32, PACK ? MINB : 1) lk_kernel_fast
   }
 }
 
-// XIVO_LK_MINB=8: register cap 64 (8 CTAs of 4 warps per SM instead of 6 at 80 registers; a few spilled words outside the iteration loop)
-static int lk_min_blocks() {
-  static const int v = [] { const char* e = getenv("XIVO_LK_MINB"); return e && atoi(e) == 8 ? 8 : 6; }();
-  return v;
-}
 template <int WIN, bool PACK>
 static void launch_lk_fast(dim3 grid, cudaStream_t st, const uint8_t* prev_pyr, const uint8_t* next_pyr, unsigned long long pyr_stride,
                            const unsigned long long* prev_off, const unsigned long long* next_off, const PyrDesc& d, const float* prev_pts,
                            float* next_pts, uint8_t* status, float* err, const int* npts_dev, const LKParams& prm) {
-  if (PACK && lk_min_blocks() == 8)
-    lk_kernel_fast<WIN, PACK, 8><<<grid, LK_WARPS * 32, 0, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
-  else
-    lk_kernel_fast<WIN, PACK, 6><<<grid, LK_WARPS * 32, 0, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
+  lk_kernel_fast<WIN, PACK><<<grid, LK_WARPS * 32, 0, st>>>(prev_pyr, next_pyr, pyr_stride, prev_off, next_off, d, prev_pts, next_pts, status, err, npts_dev, prm);
 }
 
 // XIVO_LK_GENERIC=1 routes single-channel frames through the generic kernel (parity tests compare the two)
