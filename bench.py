@@ -282,6 +282,24 @@ def pin_to_gpu_numa_node(local, lws):
         return None
 
 
+def cgroup_cpu_stat():
+    """nr_throttled / throttled_usec / usage_usec of this container's CPU controller (cgroup v2), or None."""
+    try:
+        kv = dict(line.split() for line in open("/sys/fs/cgroup/cpu.stat"))
+        return {k: int(kv[k]) for k in ("usage_usec", "nr_periods", "nr_throttled", "throttled_usec") if k in kv}
+    except Exception:
+        return None
+
+
+def cpu_stat_delta(a, b, wall_ms):
+    """CPU time the whole container used during a timed pass (in CPUs) and how much of the pass the quota throttled it."""
+    if not a or not b:
+        return None
+    d = {k: b[k] - a[k] for k in a if k in b}
+    return dict(cpus_used=round(d.get("usage_usec", 0) / (wall_ms * 1e3), 2), throttled_periods=d.get("nr_throttled"), periods=d.get("nr_periods"),
+                throttled_ms=round(d.get("throttled_usec", 0) / 1e3, 1))
+
+
 def cpu_baseline_entry(r, cores, frames, wall_s):
     """`cpu_baseline` object from oracle/cpu_baseline.py's result.  kind "reference": a frame costs the OpenCV tracker calls (cv2 LK + FAST
     on the image stream) plus the reference's OWN estimator (oracle/_ref/libxivo_ref_*.so, its unmodified sources) on a point-cloud
@@ -325,10 +343,11 @@ def build_roofline(prof, K, peaks, seqs_per_launch, pass_ms):
         achieved, peak, unit = work_per_launch / per_launch_s / 1e12, peaks["tf"], "TFLOP/s"
     traffic, traffic_src = None, None
     try:  # ncu-measured DRAM bytes per launch of that kernel (profiles/), scaled to this run's sequences per launch
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tname = "r02_traffic.json"
+        tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
         if dom in tj:
             traffic = tj[dom] * (seqs_per_launch / tj["sequences_per_launch"])
-            traffic_src = "ncu dram__bytes_{read,write}.sum at %d sequences/launch (profiles/r01_traffic.json), scaled to %d" % (tj["sequences_per_launch"], seqs_per_launch)
+            traffic_src = "ncu dram__bytes_{read,write}.sum at %d sequences/launch (profiles/%s), scaled to %d" % (tj["sequences_per_launch"], tname, seqs_per_launch)
     except Exception:
         pass
     per_kernel = {}
@@ -362,7 +381,7 @@ def run_ours(args):
     budget_all = cpu_budget()
     budget = max(1, budget_all // lws)
     # one driver per batch needs a CPU of its own: with a small budget (e.g. a node quota shared by 8 ranks) run fewer batches
-    args.batches = max(1, min(args.batches, budget // 2))
+    args.batches = max(1, min(args.batches, budget * 3 // 4 if args.batches > 8 else budget // 2))  # asked for more than the default: leave a quarter of the CPUs to the workers
     os.environ.setdefault("XIVO_THREADS", str(max(1, min(args.max_threads, budget) - args.batches + 1 - args.cpu_headroom)))
     os.environ.setdefault("XIVO_DRIVERS", str(args.batches))
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # every lane has its own streams: more hardware queues than the default 8, fewer false dependencies
@@ -496,6 +515,7 @@ def run_ours(args):
         launches0 = capi.launch_count()
         clk = ClockSampler(local)
         barrier()
+        cst0 = cgroup_cpu_stat()
         clk.start()
         e0 = [torch.cuda.Event(enable_timing=True) for _ in range(NB)]
         e1 = [torch.cuda.Event(enable_timing=True) for _ in range(NB)]
@@ -513,6 +533,7 @@ def run_ours(args):
             e1[i].record(exts[i])
         barrier()
         wall = time.perf_counter() - t0
+        cst = cpu_stat_delta(cst0, cgroup_cpu_stat(), wall * 1e3)
         clocks = clk.stop()
         ms = max(e0[0].elapsed_time(e1[i]) for i in range(NB))  # first start -> last end, on the launch streams
         L.xivo_profile_enable(0)
@@ -520,7 +541,7 @@ def run_ours(args):
         L.xivo_profile_report(buf, len(buf))
         prof = json.loads(buf.value.decode())
         ms = replicas.max_over_ranks(ms, device="cuda")
-        return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked)
+        return dict(ms=ms, wall_ms=wall * 1e3, prof=prof, launches=capi.launch_count() - launches0, clocks=clocks, ntracked=ntracked, cpu_stat=cst)
 
     # three passes over consecutive frames of the same streams: the two measured ones run with the in-library
     # profiler off (its event records and locks cost ~1 ms/step); the third only attributes time to kernels
@@ -594,7 +615,8 @@ def run_ours(args):
                    e2e=dict(value=e2e, unit="frames/s", h2d_bytes_per_step=r_e2e["prof"]["_h2d_bytes"] / K if r_e2e["prof"]["_h2d_bytes"] else world * B * FPS * fbytes,
                             d2h_bytes_per_step=(r_e2e["prof"]["_d2h_bytes"] / K) if r_e2e["prof"]["_d2h_bytes"] else None, ms_per_step=r_e2e["ms"] / K),
                    gpu_launches=r_dev["launches"], clocks=r_dev["clocks"], roofline=roofline, cpu_baseline=cpu, single_stream=single,
-                   tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K, host_phase_ms_per_frame_step=host_phases)
+                   tracked_features_mean=r_dev["ntracked"], wall_ms_per_step=r_dev["wall_ms"] / K, host_phase_ms_per_frame_step=host_phases,
+                   host_cpu=dict(value_pass=r_dev["cpu_stat"], e2e_pass=r_e2e["cpu_stat"], note="container CPU time / wall of the pass and cgroup quota throttling (cpu.stat), rank 0's view of the whole container"))
         print(json.dumps(out))
     pool.shutdown()
     for b_ in bts:
