@@ -21,6 +21,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <fstream>
 #include <mutex>
 #include <algorithm>
@@ -67,6 +68,7 @@ class WorkPool {
       if (slot >= 0) break;
       cpu_relax();
     }
+    avail_.fetch_add(1, std::memory_order_release);
     epoch_.fetch_add(1);
     if (sleepers_.load() > 0) {
       std::lock_guard<std::mutex> lk(mu_);
@@ -78,6 +80,9 @@ class WorkPool {
     slots_[slot] = nullptr;
     unlock();
     while (job.refs.load(std::memory_order_acquire) > 0) cpu_relax();
+    // an item that threw (FlatMap::at, bad_alloc ...) was counted as done on whatever thread ran it; the first exception resurfaces here,
+    // on the thread that owns the job, once no worker refers to the job any more
+    if (job.failed.load(std::memory_order_acquire)) std::rethrow_exception(job.err);
   }
 
  private:
@@ -87,7 +92,12 @@ class WorkPool {
     int n = 0;
     void (*call)(void*, int) = nullptr;
     void* ctx = nullptr;
+    std::atomic<bool> failed{false};
+    std::exception_ptr err;
   };
+  // published jobs that still have unclaimed items: drivers polling for the GPU call help_one() in a tight loop, and a look at this
+  // counter keeps them off the slot lock (and its cache line) while there is nothing to take
+  std::atomic<int> avail_{0};
   Job* slots_[kSlots] = {nullptr};
   std::atomic_flag lk_ = ATOMIC_FLAG_INIT;
   std::atomic<unsigned long long> epoch_{0};
@@ -102,15 +112,24 @@ class WorkPool {
   }
   void unlock() { lk_.clear(std::memory_order_release); }
 
-  static void run(Job& j) {
+  void run_item(Job& j, int i) {
+    if (i == j.n - 1) avail_.fetch_sub(1, std::memory_order_relaxed);  // whoever claims the last item retires the job from the counter
+    try {
+      j.call(j.ctx, i);
+    } catch (...) {
+      if (!j.failed.exchange(true, std::memory_order_acq_rel)) j.err = std::current_exception();
+    }
+    j.done.fetch_add(1, std::memory_order_release);
+  }
+  void run(Job& j) {
     for (;;) {
       const int i = j.next.fetch_add(1, std::memory_order_relaxed);
       if (i >= j.n) break;
-      j.call(j.ctx, i);
-      j.done.fetch_add(1, std::memory_order_release);
+      run_item(j, i);
     }
   }
   Job* grab() {  // a published job that still has unclaimed items, with a reference held
+    if (avail_.load(std::memory_order_acquire) <= 0) return nullptr;
     Job* r = nullptr;
     lock();
     for (int s = 0; s < kSlots; ++s) {
@@ -264,10 +283,7 @@ class WorkPool {
     Job* j = grab();
     if (!j) return false;
     const int i = j->next.fetch_add(1, std::memory_order_relaxed);
-    if (i < j->n) {
-      j->call(j->ctx, i);
-      j->done.fetch_add(1, std::memory_order_release);
-    }
+    if (i < j->n) run_item(*j, i);
     j->refs.fetch_sub(1, std::memory_order_release);
     return true;
   }
