@@ -381,7 +381,9 @@ def run_ours(args):
     budget_all = cpu_budget()
     budget = max(1, budget_all // lws)
     # one driver per batch needs a CPU of its own: with a small budget (e.g. a node quota shared by 8 ranks) run fewer batches
-    args.batches = max(1, min(args.batches, budget * 3 // 4 if args.batches > 8 else budget // 2))  # asked for more than the default: leave a quarter of the CPUs to the workers
+    # a batch needs a driver thread; at least a quarter of the CPUs stay with the workers.  (Half, the rule until r02ae, turned the 12 CPUs a
+    # rank gets on a multi-GPU box into 6 batches of 171 sequences: two waves of the CTA-per-filter kernels on 148 SMs.)
+    args.batches = max(1, min(args.batches, budget * 3 // 4))
     os.environ.setdefault("XIVO_THREADS", str(max(1, min(args.max_threads, budget) - args.batches + 1 - args.cpu_headroom)))
     os.environ.setdefault("XIVO_DRIVERS", str(args.batches))
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # every lane has its own streams: more hardware queues than the default 8, fewer false dependencies
