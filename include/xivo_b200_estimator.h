@@ -73,8 +73,10 @@ int xivo_batch_step(xivo_batch* b, int n_imu, const uint64_t* imu_ts, const doub
 int xivo_batch_prefetch_frames(xivo_batch* b, const uint8_t* const* imgs, int rows, int cols, int channels);
 
 /* How device-accessible (pinned / registered) host frames are brought into the device frame ring:
- * XIVO_INGEST_ZERO_COPY: one gather launch per call, the SMs read the host memory over PCIe (default);
- * XIVO_INGEST_COPY_ENGINE: one cudaMemcpyAsync per frame on the copy stream.  Process-wide, takes effect at
+ * XIVO_INGEST_ZERO_COPY: one gather launch per call, the SMs read the host memory over PCIe (initial value
+ * when XIVO_ZEROCOPY=1);
+ * XIVO_INGEST_COPY_ENGINE (default): the copy engine on the copy stream, one pitched copy per run of evenly
+ * spaced source frames, else one cudaMemcpyAsync per frame.  Process-wide, takes effect at
  * the next visual_meas / step call, results are identical.  Returns the previous mode; any other argument
  * only queries.  Pageable host frames always take the copy-engine path. */
 #define XIVO_INGEST_ZERO_COPY 0
